@@ -1,0 +1,171 @@
+// common.cu -- error state, device init, caching allocator, launch counter.
+#include "common.h"
+#include <stdarg.h>
+#include <mutex>
+#include <map>
+#include <vector>
+#include <atomic>
+
+namespace gb {
+
+static thread_local char t_err[512] = {0};
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+void clear_error() { t_err[0] = 0; }
+
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    return false;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::once_flag g_once;
+static bool g_dev_ok = false;
+static int g_sms = 0;
+
+bool ensure_device()
+{
+    std::call_once(g_once, [] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) {
+            set_error("gamut_b200: no CUDA device available (%s); there is no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+            return;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return; }
+        if (p.major != 10) {
+            set_error("gamut_b200: built for sm_100a only, found sm_%d%d", p.major, p.minor);
+            return;
+        }
+        g_sms = p.multiProcessorCount;
+        g_dev_ok = true;
+    });
+    if (!g_dev_ok && t_err[0] == 0) set_error("gamut_b200: no usable sm_100 CUDA device; there is no CPU fallback");
+    return g_dev_ok;
+}
+int sm_count() { return g_sms > 0 ? g_sms : 148; }
+
+// ---------------------------------------------------------------------------------------------
+// Caching allocator: power-of-two-ish buckets (round up to 1/8 octave above 1 MiB, 512 B below).
+// Keyed per device.
+struct Pool {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> free_;   // (device,size) -> ptr
+    std::map<void*, std::pair<int, size_t>> live_;
+    size_t cached_bytes = 0;
+};
+static Pool& dpool() { static Pool* p = new Pool; return *p; }
+static Pool& hpool() { static Pool* p = new Pool; return *p; }
+
+static size_t bucket(size_t n)
+{
+    if (n < 512) return 512;
+    size_t p = 512;
+    while (p < n) p <<= 1;
+    // 8 sub-buckets per octave to bound waste at 12.5 %
+    size_t step = p >> 4;
+    size_t lo = p >> 1;
+    size_t b = lo + ((n - lo + step - 1) / step) * step;
+    return b < n ? p : b;
+}
+
+static void* pool_alloc(Pool& P, size_t bytes, bool pinned)
+{
+    if (!ensure_device()) return nullptr;
+    int dev = 0; cudaGetDevice(&dev);
+    if (pinned) dev = -1;
+    size_t b = bucket(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> g(P.m);
+        auto it = P.free_.find({dev, b});
+        if (it != P.free_.end()) {
+            void* p = it->second;
+            P.free_.erase(it);
+            P.cached_bytes -= b;
+            P.live_[p] = {dev, b};
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = pinned ? cudaMallocHost(&p, b) : cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+        // release the cache and retry once
+        cudaGetLastError();
+        if (pinned) { /* nothing */ } else dev_trim();
+        e = pinned ? cudaMallocHost(&p, b) : cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("gamut_b200: out of %s memory allocating %zu bytes", pinned ? "pinned host" : "device", b);
+            return nullptr;
+        }
+    }
+    std::lock_guard<std::mutex> g(P.m);
+    P.live_[p] = {dev, b};
+    return p;
+}
+static void pool_free(Pool& P, void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> g(P.m);
+    auto it = P.live_.find(p);
+    if (it == P.live_.end()) return;
+    P.free_.insert({it->second, p});
+    P.cached_bytes += it->second.second;
+    P.live_.erase(it);
+}
+
+void* dev_alloc(size_t bytes) { return pool_alloc(dpool(), bytes, false); }
+void  dev_free(void* p) { pool_free(dpool(), p); }
+void  dev_trim()
+{
+    Pool& P = dpool();
+    std::vector<void*> v;
+    {
+        std::lock_guard<std::mutex> g(P.m);
+        for (auto& kv : P.free_) v.push_back(kv.second);
+        P.free_.clear();
+        P.cached_bytes = 0;
+    }
+    for (void* p : v) cudaFree(p);
+}
+void* pinned_alloc(size_t bytes) { return pool_alloc(hpool(), bytes, true); }
+void  pinned_free(void* p) { pool_free(hpool(), p); }
+
+cudaStream_t thread_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    if (!s) {
+        if (!ensure_device()) return nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { s = nullptr; }
+    }
+    return s;
+}
+
+} // namespace gb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: library-level entry points (declared in include/gamut_b200.h)
+GB_API const char* gb200_last_error(void) { return gb::t_err; }
+GB_API long long gb200_launch_count(void) { return gb::g_launches.load(); }
+GB_API int gb200_init(void) { return gb::ensure_device() ? 1 : 0; }
+GB_API int gb200_sm_count(void) { return gb::ensure_device() ? gb::sm_count() : 0; }
+GB_API void* gb200_device_alloc(size_t bytes) { return gb::dev_alloc(bytes); }
+GB_API void gb200_device_free(void* p) { gb::dev_free(p); }
+GB_API void gb200_device_trim(void) { gb::dev_trim(); }
+GB_API void* gb200_host_alloc(size_t bytes) { return gb::pinned_alloc(bytes); }
+GB_API void gb200_host_free(void* p) { gb::pinned_free(p); }
+GB_API const char* gb200_version(void) { return "gamut_b200 0.1 (sm_100a)"; }
+GB_API void gb200_free(void* p) { free(p); }

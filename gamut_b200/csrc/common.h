@@ -1,0 +1,54 @@
+// common.h -- shared host-side plumbing for the gamut_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+#define GB_API extern "C" __attribute__((visibility("default")))
+
+namespace gb {
+
+// Sticky per-thread error string, the C-ABI analogue of Image.error(kStr...) (image.d:1563).
+void set_error(const char* fmt, ...);
+void clear_error();
+
+// Returns false (and records the error) when a CUDA call failed.
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line);
+#define GB_CUDA(x) do { if (!gb::cuda_ok((x), #x, __FILE__, __LINE__)) return 0; } while (0)
+#define GB_CUDA_NULL(x) do { if (!gb::cuda_ok((x), #x, __FILE__, __LINE__)) return nullptr; } while (0)
+#define GB_CUDA_B(x) do { if (!gb::cuda_ok((x), #x, __FILE__, __LINE__)) return false; } while (0)
+
+// Count of kernels this library launched (bench.py's "gpu_launches").
+void count_launch(int n = 1);
+
+// Lazy one-time context init on the current device; fails loudly when there is no GPU.
+bool ensure_device();
+int  sm_count();
+
+// Size-bucketed caching device allocator (cudaMalloc is ~100 us; the host-pointer entry points
+// are called once per image). Thread-safe.
+void* dev_alloc(size_t bytes);
+void  dev_free(void* p);
+void  dev_trim();
+
+// Pinned staging buffers for the host-pointer entry points.
+void* pinned_alloc(size_t bytes);
+void  pinned_free(void* p);
+
+// The library's own non-blocking stream for host-pointer entry points (one per thread).
+cudaStream_t thread_stream();
+
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() {}
+    explicit DevBuf(size_t n) { p = dev_alloc(n); }
+    ~DevBuf() { if (p) dev_free(p); }
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    bool alloc(size_t n) { if (p) dev_free(p); p = dev_alloc(n); return p != nullptr; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+} // namespace gb

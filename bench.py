@@ -38,54 +38,63 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, in-process, every ~2 ms;
+    same fields as the nvidia-smi query of B200_PROFILING.md)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.mx = None
+        self.stop_flag = False
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            def run():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        try:
+                            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception as e:  # noqa: BLE001
+                        self.err = str(e)
+                        break
+                    time.sleep(0.002)
+
+            self.t = threading.Thread(target=run, daemon=True)
+            self.t.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        med = float(np.median(sm)) if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "samples": 0, "reasons": ["nvml unavailable: %s" % self.err]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.mx, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -234,7 +243,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="convert", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

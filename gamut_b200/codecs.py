@@ -1,0 +1,138 @@
+"""Python bindings of the codec-level C ABI (include/gamut_b200.h): the seam one level below the
+reference's plugins (stbi_load_from_callbacks, decompress_jpeg_image_from_stream, qoi_decode,
+qoix_lz4_decode). All pixel work happens in the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+u8p = C.POINTER(C.c_uint8)
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("channels", C.c_int),
+                ("file_channels", C.c_int), ("bits", C.c_int), ("pixel_type", C.c_int), ("pitch", C.c_int),
+                ("status", C.c_int), ("ppmX", C.c_float), ("ppmY", C.c_float), ("pixelAspectRatio", C.c_float)]
+
+
+_declared = False
+
+
+def _L():
+    global _declared
+    L = _lib.lib()
+    if not _declared:
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        fp = C.POINTER(C.c_float)
+        ip = C.POINTER(C.c_int)
+        L.gb200_batch_count.argtypes = [vp]
+        L.gb200_batch_images.restype = C.POINTER(ImageDesc)
+        L.gb200_batch_images.argtypes = [vp]
+        L.gb200_batch_free.argtypes = [vp]
+        L.gb200_png_is16.argtypes = [C.c_char_p, sz]
+        L.gb200_png_load.restype = vp
+        L.gb200_png_load.argtypes = [C.c_char_p, sz, i32, i32, ip, ip, ip, fp, fp, fp]
+        L.gb200_png_decode_batch.restype = vp
+        L.gb200_png_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, i32, vp]
+        L.gb200_png_unfilter_device.argtypes = [vp, sz, vp, sz, i32, i32, i32, i32, vp, vp]
+        L.gb200_inflate_device.argtypes = [i32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp),
+                                           C.POINTER(C.c_uint32), i32, vp, vp, vp]
+        _declared = True
+    return L
+
+
+def _take_host(ptr: int, nbytes: int) -> np.ndarray:
+    a = np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(max(nbytes, 1),))[:nbytes].copy()
+    _lib.lib().gb200_free(ptr)
+    return a
+
+
+@dataclass
+class PngResult:
+    pixels: np.ndarray      # (h, w, channels) uint8 or uint16
+    width: int
+    height: int
+    file_channels: int
+    ppmX: float
+    ppmY: float
+    pixelRatio: float
+
+
+def png_is16(data: bytes) -> bool:
+    return bool(_L().gb200_png_is16(data, len(data)))
+
+
+def png_load(data: bytes, req_comp: int = 0, want16: bool = False) -> Optional[PngResult]:
+    """stbi_load_from_callbacks / stbi_load_16_from_callbacks (stbdec.d:713-735) on a memory buffer."""
+    L = _L()
+    w, h, comp = C.c_int(), C.c_int(), C.c_int()
+    px, py, pr = C.c_float(), C.c_float(), C.c_float()
+    p = L.gb200_png_load(data, len(data), req_comp, 1 if want16 else 0, C.byref(w), C.byref(h), C.byref(comp),
+                         C.byref(px), C.byref(py), C.byref(pr))
+    if not p:
+        return None
+    ch = req_comp if req_comp else comp.value
+    n = w.value * h.value * ch * (2 if want16 else 1)
+    a = _take_host(p, n)
+    if want16:
+        a = a.view(np.uint16)
+    return PngResult(a.reshape(h.value, w.value, ch), w.value, h.value, comp.value, px.value, py.value, pr.value)
+
+
+class Batch:
+    """Owner of a device-resident decoded batch (gb200_batch)."""
+
+    def __init__(self, handle: int):
+        self.handle = handle
+        L = _L()
+        n = L.gb200_batch_count(handle)
+        arr = L.gb200_batch_images(handle)
+        self.images = [arr[i] for i in range(n)]
+
+    def to_host(self, i: int) -> Optional[np.ndarray]:
+        import torch  # plumbing only: device -> host copy
+        d = self.images[i]
+        if not d.status:
+            return None
+        n = d.pitch * d.height
+        out = np.empty(n, np.uint8)
+        from ctypes import c_void_p
+        cudart = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        err = cudart.cudaMemcpy(out.ctypes.data, d.pixels, n, 2)  # cudaMemcpyDeviceToHost
+        assert int(err) == 0 if not isinstance(err, tuple) else int(err[0]) == 0
+        a = out.view(np.uint16) if d.bits == 16 else out
+        return a.reshape(d.height, d.width, d.channels)
+
+    def free(self):
+        if self.handle:
+            _L().gb200_batch_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _batch_args(files: Sequence[bytes], files_dev: Optional[Sequence[int]]):
+    n = len(files)
+    arr = (C.c_char_p * n)(*files)
+    lens = (C.c_size_t * n)(*[len(f) for f in files])
+    dev = (C.c_void_p * n)(*files_dev) if files_dev is not None else None
+    return n, arr, lens, dev
+
+
+def png_decode_batch(files: Sequence[bytes], req_comp: int = 0, want16: int = -1,
+                     files_dev: Optional[Sequence[int]] = None, stream: int = 0) -> Batch:
+    n, arr, lens, dev = _batch_args(files, files_dev)
+    h = _L().gb200_png_decode_batch(n, arr, lens, dev, req_comp, want16, stream)
+    if not h:
+        raise _lib.GamutB200Error("png_decode_batch: " + _lib.last_error())
+    return Batch(h)

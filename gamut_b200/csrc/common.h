@@ -51,4 +51,10 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// Grow-only device scratch (used where a launch outlives the call that built its job table).
+struct Scratch {
+    void* p = nullptr; size_t cap = 0;
+    void* get(size_t n) { if (n > cap) { if (p) dev_free(p); p = dev_alloc(n); cap = p ? n : 0; } return p; }
+};
+
 } // namespace gb

@@ -1,0 +1,241 @@
+// png_kernels.cu -- PNG device kernels: batched inflate, row unfilter (wavefront), finish.
+#include "common.h"
+#include "png_kernels.cuh"
+
+namespace gb {
+
+// ---------------------------------------------------------------------------------------------
+// Batched inflate: one warp per zlib stream (see inflate.cuh).
+__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+inflate_batch_kernel(InflateJob* jobs, int njobs)
+{
+    __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int j = blockIdx.x * INF_WARPS_PER_CTA + warp;
+    if (j >= njobs) return;
+    InflateJob job = jobs[j];
+    inflate_stream(job, smem[warp], lane);
+    if (lane == 0) { jobs[j].out_len = job.out_len; jobs[j].status = job.status; }
+}
+
+void launch_inflate(InflateJob* d_jobs, int njobs, cudaStream_t st)
+{
+    if (njobs <= 0) return;
+    int grid = (njobs + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
+    inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather: concatenates the IDAT payloads of every image into one padded, 16-byte aligned stream per
+// image (stbdec.d:1952-1989 does this with realloc + getn on the host).
+struct Segment { const uint8_t* src; uint8_t* dst; uint32_t len; };
+
+__global__ void __launch_bounds__(256)
+gather_segments_kernel(const Segment* segs, int nsegs)
+{
+    for (int s = blockIdx.x; s < nsegs; s += gridDim.x) {
+        Segment g = segs[s];
+        for (uint32_t i = threadIdx.x; i < g.len; i += 256) g.dst[i] = g.src[i];
+    }
+}
+void launch_gather(const void* d_segs, int nsegs, cudaStream_t st)
+{
+    if (nsegs <= 0) return;
+    int grid = nsegs < 148 * 16 ? nsegs : 148 * 16;
+    gather_segments_kernel<<<grid, 256, 0, st>>>((const Segment*)d_segs, nsegs);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row unfilter. PNG filters Sub/Avg/Paeth are serial along a row and Up/Avg/Paeth depend on the
+// row above, so a job is processed as a skewed wavefront: lane l of a warp owns row (band*32 + l)
+// and runs one pixel behind lane l-1; the pixel above comes from a warp shuffle, the pixel
+// above-left is last step's shuffle result. With a zero row above row 0 and zero pixels left of
+// column 0 the five filters reduce to the reference's first-row / first-pixel special cases
+// (stbdec.d:1381-1388,1453-1465).
+__device__ __forceinline__ int paeth_pred(int a, int b, int c)
+{
+    int p = a + b - c;
+    int pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+template <int BPP>
+__device__ void unfilter_warp(const UnfilterJob& J, int* status, int lane)
+{
+    const uint32_t rb = J.row_bytes, H = J.height;
+    const uint32_t npx = rb / BPP;
+    for (uint32_t band = 0; band * 32 < H; ++band) {
+        const uint32_t row = band * 32 + lane;
+        const bool valid = row < H;
+        const uint8_t* rr = J.raw + (size_t)(valid ? row : 0) * (rb + 1);
+        int f = valid ? rr[0] : 0;
+        if (f > 4) { status[J.image] = 0; f = 0; }       // "invalid filter" (stbdec.d:1438)
+        rr += 1;
+        uint8_t* orow = J.out + (size_t)(valid ? row : 0) * J.out_pitch;
+        const uint8_t* prow = orow - J.out_pitch;
+        uint64_t cur = 0, left = 0, upleft = 0;
+        for (uint32_t t = 0; t < npx + 31; ++t) {
+            const int x = (int)t - lane;
+            uint64_t up;
+            if (BPP <= 4) up = __shfl_up_sync(0xffffffffu, (uint32_t)cur, 1);
+            else up = __shfl_up_sync(0xffffffffu, cur, 1);
+            const bool active = valid && x >= 0 && x < (int)npx;
+            if (lane == 0) {
+                up = 0;
+                if (active && row > 0) {
+#pragma unroll
+                    for (int k = 0; k < BPP; ++k) up |= (uint64_t)__ldcg(prow + (size_t)x * BPP + k) << (8 * k);
+                }
+            }
+            if (active) {
+                if (x == 0) { left = 0; upleft = 0; }
+                uint64_t o = 0;
+#pragma unroll
+                for (int k = 0; k < BPP; ++k) {
+                    int raw = rr[(size_t)x * BPP + k];
+                    int a = (int)(left >> (8 * k)) & 255, b = (int)(up >> (8 * k)) & 255, c = (int)(upleft >> (8 * k)) & 255;
+                    int pred = f == 0 ? 0 : f == 1 ? a : f == 2 ? b : f == 3 ? ((a + b) >> 1) : paeth_pred(a, b, c);
+                    int v = (raw + pred) & 255;
+                    o |= (uint64_t)v << (8 * k);
+                    orow[(size_t)x * BPP + k] = (uint8_t)v;
+                }
+                cur = o;
+                left = o;
+            }
+            upleft = up;
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf)
+{
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int j = blockIdx.x * 4 + warp;
+    if (j >= njobs) return;
+    UnfilterJob J = jobs[j];
+    if (inf && J.inflate_idx >= 0) {
+        // the inflated stream must be complete and long enough, else the image fails as a whole
+        const InflateJob& ij = inf[J.inflate_idx];
+        if (ij.status != INF_OK || ij.out_len < J.need_len) { if (lane == 0) status[J.image] = 0; return; }
+    }
+    switch (J.bpp) {
+    case 1: unfilter_warp<1>(J, status, lane); break;
+    case 2: unfilter_warp<2>(J, status, lane); break;
+    case 3: unfilter_warp<3>(J, status, lane); break;
+    case 4: unfilter_warp<4>(J, status, lane); break;
+    case 6: unfilter_warp<6>(J, status, lane); break;
+    default: unfilter_warp<8>(J, status, lane); break;
+    }
+}
+void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st)
+{
+    if (njobs <= 0) return;
+    unfilter_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, njobs, d_status, d_inf);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finish: one thread per output pixel; every remaining step of the reference pipeline, in source order.
+__device__ __forceinline__ int compute_y(int r, int g, int b) { return ((r * 77) + (g * 150) + (29 * b)) >> 8; }   // stbdec.d:911
+
+__global__ void __launch_bounds__(256)
+png_finish_kernel(const FinishJob* jobs)
+{
+    const FinishJob& J = jobs[blockIdx.y];
+    const uint32_t W = J.w, H = J.h;
+    const uint64_t npix = (uint64_t)W * H;
+    const int depth = J.depth, img_n = J.img_n;
+    const int maxv = depth == 16 ? 65535 : 255;
+    const int scale = (J.color == 0) ? (depth == 1 ? 0xff : depth == 2 ? 0x55 : depth == 4 ? 0x11 : 1) : 1;   // stbdec.d:1403,1560
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < npix; i += (uint64_t)gridDim.x * 256) {
+        uint32_t y = (uint32_t)(i / W), x = (uint32_t)(i - (uint64_t)y * W);
+        int p = 0; uint32_t px = x, py = y;
+        if (J.interlace) {
+            // Adam7 (stbdec.d:1650-1653): find the pass that owns (x, y)
+            const int xorig[7] = {0, 4, 0, 2, 0, 1, 0}, yorig[7] = {0, 0, 4, 0, 2, 0, 1};
+            const int xspc[7] = {8, 8, 4, 4, 2, 2, 1}, yspc[7] = {8, 8, 8, 4, 4, 2, 2};
+#pragma unroll
+            for (int q = 6; q >= 0; --q) {
+                if ((int)x >= xorig[q] && (int)y >= yorig[q] && (x - xorig[q]) % xspc[q] == 0 && (y - yorig[q]) % yspc[q] == 0) {
+                    p = q; px = (x - xorig[q]) / xspc[q]; py = (y - yorig[q]) / yspc[q];
+                }
+            }
+        }
+        const uint8_t* row = J.packed + J.pass_off[p] + (size_t)py * J.pass_rb[p];
+        int s[4] = {0, 0, 0, 0};
+        int n = img_n;
+        if (depth == 8) {
+            for (int k = 0; k < img_n; ++k) s[k] = row[(size_t)px * img_n + k];
+        } else if (depth == 16) {
+            for (int k = 0; k < img_n; ++k) { const uint8_t* q = row + ((size_t)px * img_n + k) * 2; s[k] = (q[0] << 8) | q[1]; }
+        } else {
+            for (int k = 0; k < img_n; ++k) {
+                uint32_t idx = px * img_n + k;
+                uint32_t bit = idx * depth;
+                int byte = row[bit >> 3];
+                int v = (byte >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+                s[k] = (scale * v) & 255;
+            }
+        }
+        if (J.add_alpha) s[n++] = maxv;
+        if (J.has_trans) {
+            if (depth == 16) {
+                if (n == 2) s[1] = (s[0] == J.tc16[0]) ? 0 : 65535;
+                else if (s[0] == J.tc16[0] && s[1] == J.tc16[1] && s[2] == J.tc16[2]) s[3] = 0;
+            } else {
+                if (n == 2) s[1] = (s[0] == J.tc[0]) ? 0 : 255;
+                else if (s[0] == J.tc[0] && s[1] == J.tc[1] && s[2] == J.tc[2]) s[3] = 0;
+            }
+        }
+        if (J.pal_n) {
+            int idx = s[0] * 4;
+            for (int k = 0; k < 4; ++k) s[k] = J.palette[idx + k];
+            n = J.pal_n;
+        }
+        const int req = J.req_n;
+        int o[4] = {s[0], s[1], s[2], s[3]};
+        if (req != n) {
+            // stbi__convert_format / stbi__convert_format16 (stbdec.d:916-1200)
+            switch (n * 8 + req) {
+            case 1*8+2: o[1] = maxv; break;
+            case 1*8+3: o[1] = o[2] = s[0]; break;
+            case 1*8+4: o[1] = o[2] = s[0]; o[3] = maxv; break;
+            case 2*8+1: break;
+            case 2*8+3: o[1] = o[2] = s[0]; break;
+            case 2*8+4: o[1] = o[2] = s[0]; o[3] = s[1]; break;
+            case 3*8+4: o[3] = maxv; break;
+            case 3*8+1: o[0] = compute_y(s[0], s[1], s[2]) & maxv; break;
+            case 3*8+2: o[0] = compute_y(s[0], s[1], s[2]) & maxv; o[1] = maxv; break;
+            case 4*8+1: o[0] = compute_y(s[0], s[1], s[2]) & maxv; break;
+            case 4*8+2: o[0] = compute_y(s[0], s[1], s[2]) & maxv; o[1] = s[3]; break;
+            case 4*8+3: break;
+            }
+        }
+        if (J.out16) {
+            uint16_t* dst = (uint16_t*)J.out + i * req;
+            for (int k = 0; k < req; ++k) dst[k] = (uint16_t)(depth == 16 ? o[k] : (o[k] << 8) + o[k]);       // stbdec.d:662
+        } else {
+            uint8_t* dst = J.out + i * req;
+            for (int k = 0; k < req; ++k) dst[k] = (uint8_t)(depth == 16 ? (o[k] >> 8) & 0xFF : o[k]);         // stbdec.d:645
+        }
+    }
+}
+void launch_finish(const FinishJob* d_jobs, int njobs, uint64_t max_pixels, cudaStream_t st)
+{
+    if (njobs <= 0) return;
+    uint64_t bx = (max_pixels + 255) / 256;
+    if (bx > 148 * 32) bx = 148 * 32;
+    if (bx < 1) bx = 1;
+    for (int base = 0; base < njobs; base += 65535) {
+        int ny = njobs - base < 65535 ? njobs - base : 65535;
+        png_finish_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, st>>>(d_jobs + base);
+        count_launch();
+    }
+}
+
+} // namespace gb

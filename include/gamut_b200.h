@@ -68,6 +68,54 @@ int gb200_scanlines_convert_device(int srcType, const uint8_t* src, long long sr
                                    int dstType, uint8_t* dst, long long dstPitch,
                                    int width, int height, void* stream);
 
+/* ---- batched, device-resident decode (one call decodes n independent images) ----
+ * The result object owns the device memory of every decoded image; descriptors are valid until
+ * gb200_batch_free(). A failed image has status 0 and pixels NULL -- it never poisons its neighbours
+ * (the reference's per-Image sticky error, image.d:1563). The call returns after the work on `stream`
+ * has completed (statuses and sizes are read back). */
+typedef struct gb200_batch gb200_batch;
+typedef struct gb200_image_desc {
+    uint8_t* pixels;        /* device pointer, gapless rows */
+    int width, height;
+    int channels;           /* channels of the decoded buffer */
+    int file_channels;      /* channels reported by the file (stb `comp`, jpgd `actual_comps`) */
+    int bits;               /* bits per channel: 8 or 16 */
+    int pixel_type;         /* gb200_pixel_type of the decoded buffer */
+    int pitch;              /* bytes per row */
+    int status;             /* 1 decoded, 0 failed */
+    float ppmX, ppmY, pixelAspectRatio;   /* PNG pHYs (-1 unknown); JPEG: ppmY holds dpiY */
+} gb200_image_desc;
+
+int                     gb200_batch_count(const gb200_batch* b);
+const gb200_image_desc* gb200_batch_images(const gb200_batch* b);
+void                    gb200_batch_free(gb200_batch* b);
+
+/* ---- PNG: source/gamut/codecs/stbdec.d (stb_image PNG path) + miniz inflate ---- */
+/* stbi__png_is16 (stbdec.d:2090-2110): 1 if the file stores 16-bit samples. Host-only header scan. */
+int gb200_png_is16(const uint8_t* data, size_t len);
+/* stbi_load_from_callbacks (want16 = 0, stbdec.d:725) / stbi_load_16_from_callbacks (want16 = 1,
+ * stbdec.d:713) over a memory buffer. req_comp 0 = keep the file's channels, 1..4 = force.
+ * Returns malloc()'d host pixels (free with gb200_free) or NULL. *comp = channels in the file. */
+uint8_t* gb200_png_load(const uint8_t* data, size_t len, int req_comp, int want16,
+                        int* width, int* height, int* comp, float* ppmX, float* ppmY, float* pixelRatio);
+/* Batched PNG decode: files[i]/lens[i] are HOST copies of the files (chunk headers are walked on the
+ * host); files_dev, if not NULL, holds device-resident copies of the same bytes (no H2D copy is made
+ * then). want16: 0 / 1 as above, -1 = auto per file (what loadPNG does, plugins/png.d:77-79). */
+gb200_batch* gb200_png_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                    const uint8_t* const* files_dev, int req_comp, int want16, void* stream);
+/* Kernel-level entry for the row unfilter alone (stbi__create_png_image_raw, stbdec.d:1406-1547,
+ * 8/16-bit samples, img_n == out_n): `raw` = n_images inflated streams of (1+row_bytes)*height bytes,
+ * device-resident, `raw_stride` apart; out = n_images * row_bytes * height. bpp = channels*bytes.
+ * status_dev (device int per image, may be NULL) is set to 0 for an image with a filter byte > 4. */
+int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint8_t* out, size_t out_stride,
+                              int n_images, int row_bytes, int height, int bpp, int* status_dev, void* stream);
+/* Kernel-level entry for inflate alone: n zlib (parse_header=1) or raw deflate streams, device-resident,
+ * each 4-byte aligned with >= 16 readable bytes after its end. out_lens/statuses are device arrays
+ * (status 0 ok, 1 output buffer too small, 2 corrupt). */
+int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint32_t* in_lens,
+                         uint8_t* const* out_dev, const uint32_t* out_caps, int parse_header,
+                         uint32_t* out_lens_dev, int* statuses_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

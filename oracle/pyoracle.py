@@ -24,6 +24,11 @@ def build(force: bool = False) -> str:
     return LIBPATH
 
 
+class PngInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("file_channels", C.c_int),
+                ("bits", C.c_int), ("ppmX", C.c_float), ("ppmY", C.c_float), ("pixelRatio", C.c_float)]
+
+
 _lib = None
 u8p = C.POINTER(C.c_uint8)
 
@@ -39,6 +44,12 @@ def lib():
                                           C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.or_scanlinesCopy.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.or_free.argtypes = [C.c_void_p]
+        L.or_png_load.restype = C.c_void_p
+        L.or_png_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(PngInfo)]
+        L.or_png_is16.argtypes = [C.c_char_p, C.c_size_t]
+        L.or_png_unfilter.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.or_zlib_decode.restype = C.c_void_p
+        L.or_zlib_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
     return _lib
 
 
@@ -54,3 +65,42 @@ def scanlines_convert(src_type: int, src: np.ndarray, src_pitch: int, dst_type: 
     interbuf = np.zeros(max(1, w) * 16, dtype=np.uint8)
     return bool(L.or_scanlinesConvert(src_type, _ptr(src, src_off), src_pitch, dst_type, _ptr(dst, dst_off),
                                       dst_pitch, w, h, inter, _ptr(interbuf)))
+
+
+def _take(ptr: int, nbytes: int) -> np.ndarray:
+    """Copy a malloc'd oracle result into numpy and free it."""
+    a = np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(nbytes,)).copy() if nbytes else np.zeros(0, np.uint8)
+    lib().or_free(ptr)
+    return a
+
+
+def png_load(data: bytes, req_comp: int = 0, want16: int = 0):
+    """or_png_load. Returns (pixels (h, w, ch) uint8|uint16, info) or (None, info)."""
+    L = lib()
+    info = PngInfo()
+    p = L.or_png_load(data, len(data), req_comp, want16, C.byref(info))
+    if not p:
+        return None, info
+    n = info.width * info.height * info.channels * (2 if want16 else 1)
+    a = _take(p, n)
+    if want16:
+        a = a.view(np.uint16)
+    return a.reshape(info.height, info.width, info.channels), info
+
+
+def png_is16(data: bytes) -> bool:
+    return bool(lib().or_png_is16(data, len(data)))
+
+
+def png_unfilter(raw: np.ndarray, img_n: int, out_n: int, w: int, h: int, depth: int):
+    out = np.zeros(w * h * out_n * (2 if depth == 16 else 1), np.uint8)
+    ok = lib().or_png_unfilter(raw.ctypes.data, raw.size, img_n, out_n, w, h, depth, out.ctypes.data)
+    return out if ok else None
+
+
+def zlib_decode(data: bytes, guess: int, parse_header: int = 1):
+    n = C.c_size_t(0)
+    p = lib().or_zlib_decode(data, len(data), guess, parse_header, C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value)

@@ -1,0 +1,329 @@
+"""Workloads for bench.py (one class per BASELINE.json config that runs on the GPU).
+
+Every workload keeps its inputs resident in HBM for `step()` (the `value` leg), offers an end-to-end
+leg through the host-pointer C ABI (`e2e_*`), and a CPU leg that times the oracle port on a bounded
+sample of the same workload (`cpu_run`; the only place besides tests/ and smoke() that uses oracle/)."""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import os
+import threading
+import time
+
+import numpy as np
+
+
+def _threads_run(fn, threads):
+    if threads == 1:
+        fn(0)
+        return
+    ts = [threading.Thread(target=fn, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+
+
+class EventLog:
+    """Collects (tag, start_event, end_event) on torch's current stream; elapsed read after the sync."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.items = []
+
+    def span(self, tag, stream):
+        a = self.torch.cuda.Event(enable_timing=True)
+        b = self.torch.cuda.Event(enable_timing=True)
+        self.items.append((tag, a, b))
+        a.record(stream)
+        return b
+
+    def collect(self):
+        out = {}
+        for tag, a, b in self.items:
+            out.setdefault(tag, []).append(a.elapsed_time(b))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+class ConvertWorkload:
+    """BASELINE configs[1]: PixelType convert rgba8 <-> rgbaf32, 8192x8192, 1 GPU (HBM roofline probe)."""
+    name = "PixelType convert rgba8<->rgbaf32 8192x8192 (BASELINE configs[1])"
+    dtype = "f32"
+    default_steps = 100
+    default_e2e_steps = 3
+    W = H = 8192
+    bytes_per_px = 20            # 4 B rgba8 + 16 B rgbaf32 per direction
+    e2e_api = "gb200_scanlines_convert (host pointers, pinned)"
+
+    def __init__(self, rank, world, args):
+        import torch
+        from gamut_b200 import _lib
+        self.L = _lib.lib()
+        W, H = self.W, self.H
+        g = torch.Generator(device="cuda").manual_seed(1 + rank)
+        self.u8 = torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device="cuda", generator=g)
+        self.f32 = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+        self.f32_in = torch.rand((H, W, 4), dtype=torch.float32, device="cuda", generator=g)
+        self.u8_out = torch.empty_like(self.u8)
+        self.px_per_step = 2 * W * H
+        self.e2e_px_per_step = 2 * W * H
+        self.log = EventLog()
+        self.kernel_ms = {}
+
+    def step(self, stream, timed):
+        from gamut_b200.types import PixelType as PT
+        W, H, L = self.W, self.H, self.L
+        st = stream.cuda_stream
+        e = self.log.span("convert_direct<rgba8,rgbaf32>", stream) if timed else None
+        ok1 = L.gb200_scanlines_convert_device(PT.rgba8, self.u8.data_ptr(), W * 4, PT.rgbaf32, self.f32.data_ptr(), W * 16, W, H, st)
+        if e:
+            e.record(stream)
+        e = self.log.span("convert_direct<rgbaf32,rgba8>", stream) if timed else None
+        ok2 = L.gb200_scanlines_convert_device(PT.rgbaf32, self.f32_in.data_ptr(), W * 16, PT.rgba8, self.u8_out.data_ptr(), W * 4, W, H, st)
+        if e:
+            e.record(stream)
+        if not (ok1 and ok2):
+            raise RuntimeError(L.gb200_last_error().decode())
+
+    def finish_timing(self):
+        self.kernel_ms = self.log.collect()
+
+    def config(self):
+        return {"units_per_rank": "1 image 8192x8192, forward+reverse",
+                "l2": "inputs larger than L2 (256 MiB / 1 GiB per launch, separate buffers per direction)"}
+
+    def roofline(self, peak, peak_kind):
+        avg = {k: float(np.mean(v)) for k, v in self.kernel_ms.items() if v}
+        k = max(avg, key=avg.get)
+        alg = self.bytes_per_px * self.W * self.H
+        ach = alg / (avg[k] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "peak_kind": peak_kind,
+                "traffic": 1283941000 if "rgba8,rgbaf32" in k else 1317897000,
+                "traffic_source": "profiles/r1_convert_ncu_full.txt (dram read+write per launch, one ncu --set full capture)",
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": round(avg[k], 4),
+                "all_kernels_GBps": {kk: round(alg / (vv * 1e-3) / 1e9, 1) for kk, vv in avg.items()}}
+
+    def extra(self):
+        return None
+
+    def e2e_setup(self):
+        W, H, L = self.W, self.H, self.L
+        self.h_u8 = L.gb200_host_alloc(W * H * 4)
+        self.h_f32 = L.gb200_host_alloc(W * H * 16)
+        if not self.h_u8 or not self.h_f32:
+            raise RuntimeError("pinned alloc failed")
+        a = np.ctypeslib.as_array(C.cast(self.h_u8, C.POINTER(C.c_uint8)), shape=(W * H * 4,))
+        a[:] = np.random.default_rng(1).integers(0, 256, W * H * 4, dtype=np.uint8)
+        self.h2d = W * H * 4 + W * H * 16
+        self.d2h = W * H * 16 + W * H * 4
+
+    def e2e_step(self):
+        from gamut_b200.types import PixelType as PT
+        W, H, L = self.W, self.H, self.L
+        ok1 = L.gb200_scanlines_convert(PT.rgba8, self.h_u8, W * 4, PT.rgbaf32, self.h_f32, W * 16, W, H)
+        ok2 = L.gb200_scanlines_convert(PT.rgbaf32, self.h_f32, W * 16, PT.rgba8, self.h_u8, W * 4, W, H)
+        if not (ok1 and ok2):
+            raise RuntimeError(L.gb200_last_error().decode())
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        from gamut_b200.types import PixelType as PT
+        W = ConvertWorkload.W
+        rows = 2048 if full else 512
+        rng = np.random.default_rng(1)
+        u8 = rng.integers(0, 256, rows * W * 4, dtype=np.uint8)
+        f = np.zeros(rows * W * 16, np.uint8)
+        back = np.zeros(rows * W * 4, np.uint8)
+        pyoracle.lib()
+        per = (rows + threads - 1) // threads
+
+        def work(t):
+            r0 = t * per
+            n = min(rows, r0 + per) - r0
+            if n <= 0:
+                return
+            pyoracle.scanlines_convert(PT.rgba8, u8, W * 4, PT.rgbaf32, f, W * 16, W, n, src_off=r0 * W * 4, dst_off=r0 * W * 16)
+            pyoracle.scanlines_convert(PT.rgbaf32, f, W * 16, PT.rgba8, back, W * 4, W, n, src_off=r0 * W * 16, dst_off=r0 * W * 4)
+
+        _threads_run(work, threads)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, threads)
+            times.append(time.perf_counter() - t0)
+        assert np.array_equal(back, u8)
+        return 2 * rows * W, times, f"{rows} rows of the 8192-wide image, both directions, {threads} thread(s)"
+
+
+# ----------------------------------------------------------------------------------------------
+def synth_photo(h, w, c, seed):
+    """Photo-like synthetic image: low-frequency sinusoids + noise (+ alpha gradient). uint8 (h, w, c)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, c), np.float32)
+    for k in range(min(c, 3)):
+        a = np.zeros((h, w), np.float32)
+        for _ in range(4):
+            fx, fy, ph = rng.uniform(0.002, 0.03), rng.uniform(0.002, 0.03), rng.uniform(0, 6.28)
+            a += np.sin(xx * fx + yy * fy + ph) * rng.uniform(0.1, 0.3)
+        img[:, :, k] = 0.5 + a * 0.5
+    img[:, :, :min(c, 3)] += rng.normal(0, 0.012, (h, w, min(c, 3))).astype(np.float32)
+    if c in (2, 4):
+        img[:, :, c - 1] = np.clip((xx + yy) / (h + w) * 1.3, 0, 1)
+    return (np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8)
+
+
+def make_png_files(distinct, w, h, seed0=1000):
+    from PIL import Image as PILImage
+    files = []
+    for i in range(distinct):
+        img = synth_photo(h, w, 4, seed0 + i)
+        bio = io.BytesIO()
+        PILImage.fromarray(img, "RGBA").save(bio, format="PNG", compress_level=6)
+        files.append(bio.getvalue())
+    return files
+
+
+def split_idat(png: bytes):
+    """Concatenated IDAT payload of a PNG file (host-side helper for the kernel-only legs)."""
+    import struct
+    pos, out = 8, b""
+    while pos + 8 <= len(png):
+        n, typ = struct.unpack(">I4s", png[pos:pos + 8])
+        if typ == b"IDAT":
+            out += png[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    return out
+
+
+class PngWorkload:
+    """BASELINE configs[2]: PNG 8-bit RGBA decode (inflate + unfilter), batch of 1920x1080 images, 1 GPU."""
+    name = "PNG 8-bit RGBA decode + unfilter, batch 1024 images 1920x1080 (BASELINE configs[2])"
+    dtype = "u8"
+    default_steps = 3
+    default_e2e_steps = 1
+    W, H = 1920, 1080
+    DISTINCT = 16
+    e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back)"
+
+    def __init__(self, rank, world, args):
+        import torch
+        from gamut_b200 import codecs
+        self.torch = torch
+        self.codecs = codecs
+        self.n = args.batch or 1024
+        self.files = make_png_files(self.DISTINCT, self.W, self.H, 1000 + 100 * rank)
+        self.host_files = [self.files[i % self.DISTINCT] for i in range(self.n)]
+        # distinct device copies of every file so that nothing is served from L2 by aliasing
+        base = [torch.frombuffer(bytearray(f + b"\0" * 64), dtype=torch.uint8).cuda() for f in self.files]
+        self.dev_bufs = [base[i % self.DISTINCT].clone() for i in range(self.n)]
+        self.dev_ptrs = [t.data_ptr() for t in self.dev_bufs]
+        self.px_per_step = self.n * self.W * self.H
+        self.e2e_n = min(self.n, 128)
+        self.e2e_px_per_step = self.e2e_n * self.W * self.H
+        self.comp_bytes = sum(len(split_idat(f)) for f in self.files) / self.DISTINCT
+        self.phase = []
+        self.unf_ms = []
+        self.log = EventLog()
+        # raw (inflated) streams resident in HBM for the unfilter-only leg
+        import zlib
+        raw = [np.frombuffer(zlib.decompress(split_idat(f)), np.uint8) for f in self.files]
+        self.raw_len = raw[0].size
+        self.raw_stride = (self.raw_len + 255) // 256 * 256
+        rawbuf = np.zeros((self.DISTINCT, self.raw_stride), np.uint8)
+        for i in range(self.DISTINCT):
+            rawbuf[i, :self.raw_len] = raw[i]
+        d16 = torch.from_numpy(rawbuf).cuda()
+        self.d_raw = d16[torch.arange(self.n, device="cuda") % self.DISTINCT].contiguous()
+        self.out_stride = self.W * self.H * 4
+        self.d_unf = torch.empty((self.n, self.out_stride), dtype=torch.uint8, device="cuda")
+
+    def step(self, stream, timed):
+        b = self.codecs.png_decode_batch(self.host_files, 0, 0, files_dev=self.dev_ptrs, stream=stream.cuda_stream)
+        if timed:
+            ph, hp = b.timing()
+            self.phase.append(ph[:4] + [hp])
+        bad = sum(1 for d in b.images if not d.status)
+        b.free()
+        if bad:
+            raise RuntimeError(f"{bad} PNG images failed to decode")
+        # unfilter-only leg on pre-inflated streams (kernel-level roofline; not part of `value`)
+        if timed:
+            e = self.log.span("unfilter", stream)
+            L = self.codecs._L()
+            ok = L.gb200_png_unfilter_device(self.d_raw.data_ptr(), self.raw_stride, self.d_unf.data_ptr(), self.out_stride,
+                                             self.n, self.W * 4, self.H, 4, None, stream.cuda_stream)
+            e.record(stream)
+            assert ok
+
+    def finish_timing(self):
+        self.unf_ms = self.log.collect().get("unfilter", [])
+
+    def config(self):
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} RGBA8 ({self.DISTINCT} distinct, PIL level 6, adaptive filters)",
+                "compressed_idat_bytes_per_image": int(self.comp_bytes),
+                "l2": "inputs larger than L2 (every image has its own device copy; batch >> 126 MB)",
+                "note": "value = whole decode (gather+inflate+unfilter); the unfilter-only leg is timed separately and excluded"}
+
+    def roofline(self, peak, peak_kind):
+        ph = np.mean(np.array(self.phase), axis=0)
+        # dominant kernel: inflate. algorithmic bytes per launch = compressed in + raw out, per image * n
+        alg = (self.comp_bytes + self.raw_len) * self.n
+        ach = alg / (ph[1] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "inflate_batch_kernel", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": None,
+                "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(float(ph[1]), 3)}
+
+    def extra(self):
+        ph = np.mean(np.array(self.phase), axis=0)
+        px = self.n * self.W * self.H
+        d = {"phase_ms": {"gather": round(float(ph[0]), 3), "inflate": round(float(ph[1]), 3),
+                          "unfilter": round(float(ph[2]), 3), "finish": round(float(ph[3]), 3),
+                          "host_parse": round(float(ph[4]), 3)},
+             "inflate_only_Mpixels_s": round(px / (ph[1] * 1e-3) / 1e6, 1)}
+        if self.unf_ms:
+            ms = float(np.mean(self.unf_ms))
+            alg = (self.raw_len + self.out_stride) * self.n
+            d["unfilter_only"] = {"Mpixels_s": round(px / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 3),
+                                  "algorithmic_bytes": int(alg), "GBps": round(alg / (ms * 1e-3) / 1e9, 1)}
+        return d
+
+    def e2e_setup(self):
+        self.h2d = int(self.comp_bytes * self.e2e_n)
+        self.d2h = self.e2e_n * self.out_stride
+        self.h_out = np.empty(self.e2e_n * self.out_stride, np.uint8)
+
+    def e2e_step(self):
+        b = self.codecs.png_decode_batch(self.host_files[:self.e2e_n], 0, 0)
+        L = self.codecs._L()
+        for i, d in enumerate(b.images):
+            assert d.status
+            L.gb200_copy_to_host(self.h_out.ctypes.data + i * self.out_stride, d.pixels, self.out_stride)
+        b.free()
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        W, H = PngWorkload.W, PngWorkload.H
+        nimg = max(threads, 2) if full else 2
+        files = make_png_files(min(nimg, 4), W, H, 1000)
+        pyoracle.lib()
+
+        def work(t):
+            for i in range(t, nimg, threads):
+                px, _ = pyoracle.png_load(files[i % len(files)], 0, 0)
+                assert px is not None
+
+        _threads_run(work, threads)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, threads)
+            times.append(time.perf_counter() - t0)
+        return nimg * W * H, times, f"{nimg} images 1920x1080 RGBA8, {threads} thread(s), one image per worker"
+
+
+WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload}

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
     L.gb200_host_alloc.argtypes = [sz]
     L.gb200_host_free.argtypes = [vp]
     L.gb200_free.argtypes = [vp]
+    L.gb200_copy_to_host.argtypes = [vp, vp, sz]
+    L.gb200_copy_to_device.argtypes = [vp, vp, sz]
     L.gb200_pixel_type_size.argtypes = [i32]
     L.gb200_scanlines_inter_type.argtypes = [i32, i32]
     L.gb200_scanlines_convert.argtypes = [i32, vp, i32, i32, vp, i32, i32, i32]

@@ -34,6 +34,7 @@ def _L():
         L.gb200_batch_images.restype = C.POINTER(ImageDesc)
         L.gb200_batch_images.argtypes = [vp]
         L.gb200_batch_free.argtypes = [vp]
+        L.gb200_batch_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.gb200_png_is16.argtypes = [C.c_char_p, sz]
         L.gb200_png_load.restype = vp
         L.gb200_png_load.argtypes = [C.c_char_p, sz, i32, i32, ip, ip, ip, fp, fp, fp]
@@ -95,19 +96,20 @@ class Batch:
         self.images = [arr[i] for i in range(n)]
 
     def to_host(self, i: int) -> Optional[np.ndarray]:
-        import torch  # plumbing only: device -> host copy
         d = self.images[i]
         if not d.status:
             return None
         n = d.pitch * d.height
         out = np.empty(n, np.uint8)
-        from ctypes import c_void_p
-        cudart = torch.cuda.cudart()
-        torch.cuda.synchronize()
-        err = cudart.cudaMemcpy(out.ctypes.data, d.pixels, n, 2)  # cudaMemcpyDeviceToHost
-        assert int(err) == 0 if not isinstance(err, tuple) else int(err[0]) == 0
+        _lib.check(_L().gb200_copy_to_host(out.ctypes.data, d.pixels, n), "copy_to_host")
         a = out.view(np.uint16) if d.bits == 16 else out
         return a.reshape(d.height, d.width, d.channels)
+
+    def timing(self):
+        ph = (C.c_float * 8)()
+        hp = C.c_double()
+        _L().gb200_batch_timing(self.handle, ph, C.byref(hp))
+        return list(ph), hp.value
 
     def free(self):
         if self.handle:

@@ -9,5 +9,6 @@ struct gb200_batch {
     std::vector<void*> device_allocs;   // owned device memory (output arena last)
     cudaStream_t stream = nullptr;
     double host_parse_ms = 0, device_ms = 0;
+    float phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase device time (CUDA events), format specific
     ~gb200_batch() { for (void* p : device_allocs) gb::dev_free(p); }
 };

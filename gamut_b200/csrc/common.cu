@@ -169,3 +169,15 @@ GB_API void* gb200_host_alloc(size_t bytes) { return gb::pinned_alloc(bytes); }
 GB_API void gb200_host_free(void* p) { gb::pinned_free(p); }
 GB_API const char* gb200_version(void) { return "gamut_b200 0.1 (sm_100a)"; }
 GB_API void gb200_free(void* p) { free(p); }
+GB_API int gb200_copy_to_host(void* dst_host, const void* src_dev, size_t bytes)
+{
+    if (!gb::ensure_device()) return 0;
+    GB_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return 1;
+}
+GB_API int gb200_copy_to_device(void* dst_dev, const void* src_host, size_t bytes)
+{
+    if (!gb::ensure_device()) return 0;
+    GB_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return 1;
+}

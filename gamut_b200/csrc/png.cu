@@ -337,6 +337,9 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         okc &= cuda_ok(cudaMemcpyAsync(d_ij.p, ijobs.data(), sizeof(InflateJob) * m, cudaMemcpyHostToDevice, st), "ijobs", __FILE__, __LINE__);
         if (!ujobs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_uj.p, ujobs.data(), sizeof(UnfilterJob) * ujobs.size(), cudaMemcpyHostToDevice, st), "ujobs", __FILE__, __LINE__);
         if (!fjobs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_fj.p, fjobs.data(), sizeof(FinishJob) * fjobs.size(), cudaMemcpyHostToDevice, st), "fjobs", __FILE__, __LINE__);
+        cudaEvent_t ev[5];
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
         if (files_dev) {
             okc &= cuda_ok(cudaMemsetAsync(d_idat.p, 0, idat_total, st), "memset", __FILE__, __LINE__);
             if (!segs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_sg.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
@@ -344,15 +347,21 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         } else {
             okc &= cuda_ok(cudaMemcpyAsync(d_idat.p, h_stage, idat_total, cudaMemcpyHostToDevice, st), "idat", __FILE__, __LINE__);
         }
+        cudaEventRecord(ev[1], st);
         launch_inflate(d_ij.as<InflateJob>(), m, st);
+        cudaEventRecord(ev[2], st);
         launch_unfilter(d_uj.as<UnfilterJob>(), (int)ujobs.size(), d_status.as<int>(), d_ij.as<InflateJob>(), st);
+        cudaEventRecord(ev[3], st);
         launch_finish(d_fj.as<FinishJob>(), (int)fjobs.size(), max_pixels, st);
+        cudaEventRecord(ev[4], st);
         std::vector<int> status((size_t)m);
         okc &= cuda_ok(cudaMemcpyAsync(ijobs.data(), d_ij.p, sizeof(InflateJob) * m, cudaMemcpyDeviceToHost, st), "ijobs back", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
         okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
         okc &= cuda_ok(cudaGetLastError(), "kernels", __FILE__, __LINE__);
         if (h_stage) pinned_free(h_stage);
+        if (okc) for (int q = 0; q < 4; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }
+        for (auto& e : ev) cudaEventDestroy(e);
         if (!okc) { delete B; return nullptr; }
 
         std::vector<int> next;
@@ -402,6 +411,12 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
 GB_API int gb200_batch_count(const gb200_batch* b) { return b ? (int)b->images.size() : 0; }
 GB_API const gb200_image_desc* gb200_batch_images(const gb200_batch* b) { return b ? b->images.data() : nullptr; }
 GB_API void gb200_batch_free(gb200_batch* b) { delete b; }
+GB_API void gb200_batch_timing(const gb200_batch* b, float* phase_ms8, double* host_parse_ms)
+{
+    if (!b) return;
+    if (phase_ms8) for (int i = 0; i < 8; ++i) phase_ms8[i] = b->phase_ms[i];
+    if (host_parse_ms) *host_parse_ms = b->host_parse_ms;
+}
 
 GB_API int gb200_png_is16(const uint8_t* data, size_t len)
 {

@@ -52,6 +52,8 @@ void        gb200_device_trim(void);
 void*       gb200_host_alloc(size_t bytes);    /* pinned host memory for the host entry points */
 void        gb200_host_free(void* p);
 void        gb200_free(void* p);               /* free() for pixels returned by host decoders */
+int         gb200_copy_to_host(void* dst_host, const void* src_dev, size_t bytes);    /* synchronous */
+int         gb200_copy_to_device(void* dst_dev, const void* src_host, size_t bytes);  /* synchronous */
 
 /* ---- PixelType converters: source/gamut/scanline.d ---- */
 int gb200_pixel_type_size(int type);                       /* pixelTypeSize, types.d:62 */
@@ -89,6 +91,10 @@ typedef struct gb200_image_desc {
 int                     gb200_batch_count(const gb200_batch* b);
 const gb200_image_desc* gb200_batch_images(const gb200_batch* b);
 void                    gb200_batch_free(gb200_batch* b);
+/* Device time of each phase of the call (CUDA events on the call's stream), ms. PNG: [0] IDAT gather /
+ * H2D, [1] inflate, [2] unfilter, [3] finish. JPEG: [0] upload, [1] Huffman, [2] IDCT+colour. QOIX: [0] upload,
+ * [1] LZ4, [2] opcode decode. */
+void                    gb200_batch_timing(const gb200_batch* b, float* phase_ms8, double* host_parse_ms);
 
 /* ---- PNG: source/gamut/codecs/stbdec.d (stb_image PNG path) + miniz inflate ---- */
 /* stbi__png_is16 (stbdec.d:2090-2110): 1 if the file stores 16-bit samples. Host-only header scan. */

@@ -43,6 +43,10 @@ def _L():
         L.gb200_png_unfilter_device.argtypes = [vp, sz, vp, sz, i32, i32, i32, i32, vp, vp]
         L.gb200_inflate_device.argtypes = [i32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp),
                                            C.POINTER(C.c_uint32), i32, vp, vp, vp]
+        L.gb200_jpeg_load.restype = vp
+        L.gb200_jpeg_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp]
+        L.gb200_jpeg_decode_batch.restype = vp
+        L.gb200_jpeg_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         _declared = True
     return L
 
@@ -137,4 +141,36 @@ def png_decode_batch(files: Sequence[bytes], req_comp: int = 0, want16: int = -1
     h = _L().gb200_png_decode_batch(n, arr, lens, dev, req_comp, want16, stream)
     if not h:
         raise _lib.GamutB200Error("png_decode_batch: " + _lib.last_error())
+    return Batch(h)
+
+
+@dataclass
+class JpegResult:
+    pixels: np.ndarray      # (h, w, channels) uint8
+    width: int
+    height: int
+    actual_comps: int
+    pixelAspectRatio: float
+    dotsPerInchY: float
+
+
+def jpeg_load(data: bytes, req_comps: int = -1) -> Optional[JpegResult]:
+    """decompress_jpeg_image_from_stream (jpegload.d:3720) on a memory buffer."""
+    L = _L()
+    w, h, ac = C.c_int(), C.c_int(), C.c_int()
+    par, dpi = C.c_float(), C.c_float()
+    p = L.gb200_jpeg_load(data, len(data), req_comps, C.byref(w), C.byref(h), C.byref(ac), C.byref(par), C.byref(dpi))
+    if not p:
+        return None
+    c = ac.value if req_comps < 0 else req_comps
+    a = _take_host(p, w.value * h.value * c)
+    return JpegResult(a.reshape(h.value, w.value, c), w.value, h.value, ac.value, par.value, dpi.value)
+
+
+def jpeg_decode_batch(files: Sequence[bytes], req_comps: int = -1, files_dev: Optional[Sequence[int]] = None,
+                      stream: int = 0) -> Batch:
+    n, arr, lens, dev = _batch_args(files, files_dev)
+    h = _L().gb200_jpeg_decode_batch(n, arr, lens, dev, req_comps, stream)
+    if not h:
+        raise _lib.GamutB200Error("jpeg_decode_batch: " + _lib.last_error())
     return Batch(h)

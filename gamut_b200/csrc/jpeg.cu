@@ -1,0 +1,839 @@
+// jpeg.cu -- baseline (sequential Huffman) JPEG decode for sm_100a.
+//
+// Drop-in for decompress_jpeg_image_from_stream (source/gamut/codecs/jpegload.d:3720-3808) as used by
+// loadJPEG (source/gamut/plugins/jpeg.d:42-104). The marker layer (jpegload.d:1177-1967: DQT, DHT, SOF,
+// DRI, SOS, JFIF/EXIF density) is header logic and runs on the host; every per-bit / per-coefficient /
+// per-pixel step runs on the GPU:
+//   jpeg_huffman_kernel   entropy decode + dequantisation into natural-order int16 blocks
+//                         (decode_next_row, jpegload.d:2405-2525; huff_decode :746-813)
+//   jpeg_idct_kernel      integer LL&M IDCT (Row/Col, :156-397) and, for 4:2:0, the frequency-domain
+//                         chroma upsampling DCT_Upsample + idct_4x4 (:827-1073, :2139-2255)
+//   jpeg_colour_kernel    YCbCr -> RGB(A) / Y with the 16.16 fixed-point constants of create_look_ups
+//                         (:2080-2094, H*Convert :2528-2823) fused with the final channel adaptation
+//                         (:3763-3801)
+// Integer arithmetic throughout; results are bit-exact with the restated reference.
+#include "common.h"
+#include "batch.h"
+#include <vector>
+#include <map>
+#include <string>
+#include <chrono>
+#include <cmath>
+
+namespace {
+
+enum { GRAYSCALE = 0, YH1V1, YH2V1, YH1V2, YH2V2 };
+
+// ---- device-side structures ------------------------------------------------------------------
+constexpr int HUFF_FAST = 10;
+struct HuffTable {               // canonical JPEG code (Annex C) + 10-bit lookahead
+    uint16_t fast[1 << HUFF_FAST];   // (len << 8) | symbol, 0 = longer than HUFF_FAST bits / invalid
+    int32_t maxcode[18];             // maxcode[l] for l = 1..16, -1 if none
+    int32_t mincode[18];
+    int32_t valptr[18];
+    uint8_t val[256];
+};
+
+struct JpegImage {
+    const uint8_t* data;         // device copy of the file
+    uint32_t data_len;
+    int width, height;
+    int scan_type, comps;        // comps_in_frame: 1 or 3
+    int mcus_per_row, mcus_per_col, blocks_per_mcu, tiles_per_mcu;
+    int mcu_org[10];             // component of each block in the MCU
+    int dc_tab[3], ac_tab[3];    // indices into the global HuffTable array
+    int16_t quant[3][64];        // per component, zig-zag order (jpegload.d:1312-1327)
+    int16_t* coefs;              // [mcu][block][64]
+    uint8_t* samples;            // [mcu][tile][64]
+    uint8_t* out;
+    int req_comps;
+    int restart_interval;
+};
+
+struct Segment {                 // one independently decodable run of MCUs
+    int image;
+    uint32_t start, end;         // byte range of the entropy data (end = first byte that is not data)
+    int first_mcu, num_mcus;
+};
+
+__constant__ uint8_t c_zag[64] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11,4,5,12,19,26,33,40,48,41,34,27,20,13,6,7,14,21,28,
+                                  35,42,49,56,57,50,43,36,29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63};
+
+// ---- entropy decode ---------------------------------------------------------------------------
+// Bit source with the semantics of get_bits_no_markers/get_octet (jpegload.d:683-743): FF 00 is a
+// literal FF, any other FF xx (a marker) and the end of the data yield 1-bits forever.
+struct BitReader {
+    const uint8_t* p; uint32_t pos, end;
+    uint64_t buf; int cnt;       // `cnt` valid bits, MSB-aligned in buf
+    bool ended;
+    __device__ __forceinline__ void init(const uint8_t* data, uint32_t s, uint32_t e) { p = data; pos = s; end = e; buf = 0; cnt = 0; ended = false; }
+    __device__ __forceinline__ void fill()
+    {
+        while (cnt <= 56) {
+            uint32_t b = 0xFF;
+            if (!ended) {
+                if (pos >= end) ended = true;
+                else {
+                    b = p[pos];
+                    if (b == 0xFF) {
+                        if (pos + 1 < end && p[pos + 1] == 0) pos += 2;
+                        else { ended = true; }
+                    } else pos += 1;
+                }
+            }
+            buf |= (uint64_t)b << (56 - cnt);
+            cnt += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek16() { return (uint32_t)(buf >> 48); }
+    __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t get(int n) { if (n == 0) return 0; uint32_t v = (uint32_t)(buf >> (64 - n)); drop(n); return v; }
+};
+
+__device__ __forceinline__ int huff_decode(BitReader& br, const HuffTable* __restrict__ h)
+{
+    br.fill();
+    uint32_t top = br.peek16();
+    uint32_t e = h->fast[top >> (16 - HUFF_FAST)];
+    if (e) { br.drop(e >> 8); return e & 255; }
+    for (int l = HUFF_FAST + 1; l <= 16; ++l) {
+        int code = (int)(top >> (16 - l));
+        if (code <= h->maxcode[l] && code >= h->mincode[l]) { br.drop(l); return h->val[h->valptr[l] + code - h->mincode[l]]; }
+    }
+    // codes of length <= HUFF_FAST not present in the fast table are invalid as well
+    return -1;
+}
+__device__ __forceinline__ int huff_extend(int x, int s) { return (s == 0) ? x : ((x < (1 << (s - 1))) ? x + (int)(0xFFFFFFFFu << s) + 1 : x); }
+
+__global__ void __launch_bounds__(128)
+jpeg_huffman_kernel(const JpegImage* __restrict__ images, const Segment* __restrict__ segs, int nsegs,
+                    const HuffTable* __restrict__ tables, int* status)
+{
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nsegs) return;
+    const Segment sg = segs[si];
+    const JpegImage& im = images[sg.image];
+    BitReader br; br.init(im.data, sg.start, sg.end);
+    int dc[3] = {0, 0, 0};
+    const int bpm = im.blocks_per_mcu;
+    int16_t* coef = im.coefs + (size_t)sg.first_mcu * bpm * 64;
+    for (int m = 0; m < sg.num_mcus; ++m) {
+        for (int b = 0; b < bpm; ++b, coef += 64) {
+            const int comp = im.mcu_org[b];
+            const int16_t* q = im.quant[comp];
+            int s = huff_decode(br, tables + im.dc_tab[comp]);
+            if (s < 0 || s > 15) { status[sg.image] = 0; return; }
+            br.fill();
+            int r = (int)br.get(s);
+            s = huff_extend(r, s);
+            dc[comp] = (s += dc[comp]);
+            coef[0] = (int16_t)(s * q[0]);
+            const HuffTable* ac = tables + im.ac_tab[comp];
+            for (int k = 1; k < 64; ++k) {
+                int rs = huff_decode(br, ac);
+                if (rs < 0) { status[sg.image] = 0; return; }
+                br.fill();
+                int extra = (int)br.get(rs & 15);
+                r = rs >> 4; s = rs & 15;
+                if (s) {
+                    if (r) { if (k + r > 63) { status[sg.image] = 0; return; } k += r; }
+                    s = huff_extend(extra, s);
+                    coef[c_zag[k]] = (int16_t)(s * q[k]);
+                } else {
+                    if (r == 15) { if (k + 16 > 64) { status[sg.image] = 0; return; } k += 15; }
+                    else break;
+                }
+            }
+        }
+    }
+}
+
+// ---- IDCT -------------------------------------------------------------------------------------
+#define CONST_BITS 13
+#define PASS1_BITS 2
+#define FIX_0_298631336 2446
+#define FIX_0_390180644 3196
+#define FIX_0_541196100 4433
+#define FIX_0_765366865 6270
+#define FIX_0_899976223 7373
+#define FIX_1_175875602 9633
+#define FIX_1_501321110 12299
+#define FIX_1_847759065 15137
+#define FIX_1_961570560 16069
+#define FIX_2_053119869 16819
+#define FIX_2_562915447 20995
+#define FIX_3_072711026 25172
+
+__device__ __forceinline__ int clamp255(int i) { return min(max(i, 0), 255); }
+
+// One 8-point LL&M pass (jpegload.d:172-213 / :236-289). in[] are the 8 inputs; FINAL selects the
+// column-pass descale (+128 level shift, >> 18, clamp) versus the row-pass descale (>> 11).
+template <bool FINAL>
+__device__ __forceinline__ void idct8(const int in[8], int out[8])
+{
+    const int z2 = in[2], z3 = in[6];
+    const int z1 = (z2 + z3) * FIX_0_541196100;
+    const int tmp2 = z1 + z3 * (-FIX_1_847759065);
+    const int tmp3 = z1 + z2 * FIX_0_765366865;
+    const int tmp0 = (int)((unsigned)(in[0] + in[4]) << CONST_BITS);
+    const int tmp1 = (int)((unsigned)(in[0] - in[4]) << CONST_BITS);
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    const int atmp0 = in[7], atmp1 = in[5], atmp2 = in[3], atmp3 = in[1];
+    const int bz1 = atmp0 + atmp3, bz2 = atmp1 + atmp2, bz3 = atmp0 + atmp2, bz4 = atmp1 + atmp3;
+    const int bz5 = (bz3 + bz4) * FIX_1_175875602;
+    const int az1 = bz1 * (-FIX_0_899976223);
+    const int az2 = bz2 * (-FIX_2_562915447);
+    const int az3 = bz3 * (-FIX_1_961570560) + bz5;
+    const int az4 = bz4 * (-FIX_0_390180644) + bz5;
+    const int btmp0 = atmp0 * FIX_0_298631336 + az1 + az3;
+    const int btmp1 = atmp1 * FIX_2_053119869 + az2 + az4;
+    const int btmp2 = atmp2 * FIX_3_072711026 + az2 + az3;
+    const int btmp3 = atmp3 * FIX_1_501321110 + az1 + az4;
+    const int s[8] = {tmp10 + btmp3, tmp11 + btmp2, tmp12 + btmp1, tmp13 + btmp0, tmp13 - btmp0, tmp12 - btmp1, tmp11 - btmp2, tmp10 - btmp3};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (FINAL) out[i] = clamp255((s[i] + (128 << (CONST_BITS + PASS1_BITS + 3)) + (1 << (CONST_BITS + PASS1_BITS + 2))) >> (CONST_BITS + PASS1_BITS + 3));
+        else out[i] = (s[i] + (1 << (CONST_BITS - PASS1_BITS - 1))) >> (CONST_BITS - PASS1_BITS);
+    }
+}
+
+// Full 8x8 IDCT of a block held as blk[row*8+col] (NR rows x NC columns may be non-zero) -> 64 bytes.
+template <int NR, int NC>
+__device__ __forceinline__ void idct_block(const int16_t* blk, uint8_t* dst)
+{
+    int temp[64];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        int in[8], out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) in[c] = c < NC ? (int)blk[r * 8 + c] : 0;
+        idct8<false>(in, out);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) temp[r * 8 + c] = out[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int in[8], out[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = r < NR ? temp[r * 8 + c] : 0;
+        idct8<true>(in, out);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[r * 8 + c] = (uint8_t)out[r];
+    }
+}
+
+// DCT_Upsample (jpegload.d:827-1073): a chroma block -> four 4x4 frequency tiles -> idct_4x4 each.
+__device__ __forceinline__ int UD(int i) { return (i + 512) >> 10; }
+__device__ void chroma_upsample(const int16_t* src, uint8_t* dst /* 4 tiles */)
+{
+    // F!(x) = (int)(x * 1024 + 0.5f) evaluated for the 16 constants (jpegload.d:911)
+    const int a1[4] = {426, 810, -360, 284};
+    const int a2[4] = {23, -99, 502, 887};
+    const int b1[4] = {928, -325, 218, -184};
+    const int b2[4] = {-75, 526, 787, -383};
+    int X0[4][8], X1[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int s0 = src[j * 8 + 0], s1 = src[j * 8 + 1], s2 = src[j * 8 + 2], s3 = src[j * 8 + 3];
+        const int s4 = src[j * 8 + 4], s5 = src[j * 8 + 5], s6 = src[j * 8 + 6], s7 = src[j * 8 + 7];
+        X0[0][j] = s0;
+        X0[1][j] = UD(a1[0] * s1 + a1[1] * s3 + a1[2] * s5 + a1[3] * s7);
+        X0[2][j] = s4;
+        X0[3][j] = UD(a2[0] * s1 + a2[1] * s3 + a2[2] * s5 + a2[3] * s7);
+        X1[0][j] = UD(b1[0] * s1 + b1[1] * s3 + b1[2] * s5 + b1[3] * s7);
+        X1[1][j] = s2;
+        X1[2][j] = UD(b2[0] * s1 + b2[1] * s3 + b2[2] * s5 + b2[3] * s7);
+        X1[3][j] = s6;
+    }
+    int P[4][4], Q[4][4], R[4][4], S[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int* x = X0[i];
+        P[i][0] = x[0];
+        P[i][1] = UD(x[1] * a1[0] + x[3] * a1[1] + x[5] * a1[2] + x[7] * a1[3]);
+        P[i][2] = x[4];
+        P[i][3] = UD(x[1] * a2[0] + x[3] * a2[1] + x[5] * a2[2] + x[7] * a2[3]);
+        Q[i][0] = UD(x[1] * b1[0] + x[3] * b1[1] + x[5] * b1[2] + x[7] * b1[3]);
+        Q[i][1] = x[2];
+        Q[i][2] = UD(x[1] * b2[0] + x[3] * b2[1] + x[5] * b2[2] + x[7] * b2[3]);
+        Q[i][3] = x[6];
+        const int* y = X1[i];
+        R[i][0] = y[0];
+        R[i][1] = UD(y[1] * a1[0] + y[3] * a1[1] + y[5] * a1[2] + y[7] * a1[3]);
+        R[i][2] = y[4];
+        R[i][3] = UD(y[1] * a2[0] + y[3] * a2[1] + y[5] * a2[2] + y[7] * a2[3]);
+        S[i][0] = UD(y[1] * b1[0] + y[3] * b1[1] + y[5] * b1[2] + y[7] * b1[3]);
+        S[i][1] = y[2];
+        S[i][2] = UD(y[1] * b2[0] + y[3] * b2[1] + y[5] * b2[2] + y[7] * b2[3]);
+        S[i][3] = y[6];
+    }
+    // a = P+Q, b = P-Q, c = R+S, d = R-S; tiles: a+c, a-c, b+d, b-d, stored transposed as short
+    // (jpegload.d:886-902, :2230-2251)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int16_t tb[32];   // rows 0..3 of the transposed tile, 8 columns each (columns 4..7 unused)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int a = P[r][c] + Q[r][c], b = P[r][c] - Q[r][c], cc = R[r][c] + S[r][c], d = R[r][c] - S[r][c];
+                const int v = t == 0 ? a + cc : t == 1 ? a - cc : t == 2 ? b + d : b - d;
+                tb[c * 8 + r] = (int16_t)v;
+            }
+        }
+        idct_block<4, 4>(tb, dst + t * 64);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+jpeg_idct_kernel(const JpegImage* __restrict__ images, const int* __restrict__ block_base /* per image prefix */, int nimages,
+                 long long total_blocks, const int* __restrict__ status)
+{
+    long long gb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= total_blocks) return;
+    // find the image (few images per launch: linear/binary search over the prefix array)
+    int lo = 0, hi = nimages - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((long long)block_base[mid] <= gb) lo = mid; else hi = mid - 1; }
+    const JpegImage& im = images[lo];
+    if (!status[lo]) return;
+    const int b = (int)(gb - block_base[lo]);
+    const int mcu = b / im.blocks_per_mcu, bi = b - mcu * im.blocks_per_mcu;
+    __align__(16) int16_t blk[64];
+    const int4* src = (const int4*)(im.coefs + (size_t)b * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int4 v = src[i]; *(int4*)(blk + i * 8) = v; }
+    uint8_t* tiles = im.samples + (size_t)mcu * im.tiles_per_mcu * 64;
+    if (im.scan_type == YH2V2 && bi >= 4) {
+        __align__(16) uint8_t out[256];
+        chroma_upsample(blk, out);
+        uint4* d = (uint4*)(tiles + (4 + (bi - 4) * 4) * 64);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = *(uint4*)(out + i * 16);
+    } else {
+        __align__(16) uint8_t out[64];
+        idct_block<8, 8>(blk, out);
+        uint4* d = (uint4*)(tiles + bi * 64);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = *(uint4*)(out + i * 16);
+    }
+}
+
+// ---- colour conversion + channel adaptation ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+jpeg_colour_kernel(const JpegImage* __restrict__ images, const int* __restrict__ status)
+{
+    const JpegImage& im = images[blockIdx.y];
+    if (!status[blockIdx.y]) return;
+    const int W = im.width, H = im.height;
+    const long long npix = (long long)W * H;
+    // FIX!(x) = (int)(x * 65536 + 0.5f) (jpegload.d:2082)
+    const int F140200 = 91881, F177200 = 116130, F071414 = 46802, F034414 = 22554;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npix; i += (long long)gridDim.x * 256) {
+        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+        int Y, cb = 128, cr = 128;
+        int mx, my, lx, ly;
+        const uint8_t* t;
+        switch (im.scan_type) {
+        case GRAYSCALE:
+            mx = x >> 3; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 64;
+            Y = t[(y & 7) * 8 + (x & 7)];
+            break;
+        case YH1V1:
+            mx = x >> 3; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 3 * 64;
+            lx = (y & 7) * 8 + (x & 7);
+            Y = t[lx]; cb = t[64 + lx]; cr = t[128 + lx];
+            break;
+        case YH2V1:
+            mx = x >> 4; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 4 * 64;
+            lx = x & 15; ly = y & 7;
+            Y = t[(lx >> 3) * 64 + ly * 8 + (lx & 7)];
+            cb = t[128 + ly * 8 + (lx >> 1)]; cr = t[192 + ly * 8 + (lx >> 1)];
+            break;
+        case YH1V2:
+            mx = x >> 3; my = y >> 4; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 4 * 64;
+            lx = x & 7; ly = y & 15;
+            Y = t[(ly >> 3) * 64 + (ly & 7) * 8 + lx];
+            cb = t[128 + (ly >> 1) * 8 + lx]; cr = t[192 + (ly >> 1) * 8 + lx];
+            break;
+        default: {   // YH2V2, frequency-domain upsampled: 12 tiles (jpegload.d:2731-2745)
+            mx = x >> 4; my = y >> 4; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 12 * 64;
+            lx = x & 15; ly = y & 15;
+            const int o = ((ly >> 3) * 2 + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7);
+            Y = t[o]; cb = t[256 + o]; cr = t[512 + o];
+            break; }
+        }
+        uint8_t* d = im.out + (size_t)i * im.req_comps;
+        if (im.comps == 1) {
+            if (im.req_comps == 1) d[0] = (uint8_t)Y;
+            else { d[0] = d[1] = d[2] = (uint8_t)Y; if (im.req_comps == 4) d[3] = 255; }
+        } else {
+            const int r = clamp255(Y + ((F140200 * (cr - 128) + 32768) >> 16));
+            const int g = clamp255(Y + (((-F071414) * (cr - 128) + (-F034414) * (cb - 128) + 32768) >> 16));
+            const int b = clamp255(Y + ((F177200 * (cb - 128) + 32768) >> 16));
+            if (im.req_comps == 1) d[0] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
+            else { d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b; if (im.req_comps == 4) d[3] = 255; }
+        }
+    }
+}
+
+// ---- host: marker layer ----------------------------------------------------------------------
+struct ByteSrc {    // get_char semantics: past the end yields FF D9 FF D9 ... (jpegload.d:640-655)
+    const uint8_t* p; size_t len, pos; int tem;
+    uint32_t next() { if (pos >= len) { int t = tem; tem ^= 1; return t ? 0xD9 : 0xFF; } return p[pos++]; }
+    uint32_t u16() { uint32_t a = next(); return (a << 8) | next(); }
+};
+
+struct HostHuff { bool valid = false; uint8_t num[17]; uint8_t val[256]; };
+
+struct Parsed {
+    bool ok = false;
+    int width = 0, height = 0, comps = 0;
+    int h_samp[4] = {0}, v_samp[4] = {0}, quant_sel[4] = {0}, ident[4] = {0};
+    HostHuff huff[8];
+    bool quant_valid[4] = {false, false, false, false};
+    int16_t quant[4][64];
+    int restart_interval = 0;
+    int comps_in_scan = 0, comp_list[4] = {0}, dc_tab[4] = {0}, ac_tab[4] = {0};
+    size_t scan_start = 0;
+    float ppiX, ppiY, par;
+    int scan_type = 0, mcus_per_row = 0, mcus_per_col = 0, blocks_per_mcu = 0, tiles_per_mcu = 0, mcu_org[10];
+};
+
+float inches_to_meters(float x) { return x * 0.0254f; }
+uint16_t rd16(const uint8_t* p, bool le) { return le ? (uint16_t)(p[0] | (p[1] << 8)) : (uint16_t)((p[0] << 8) | p[1]); }
+uint32_t rd32(const uint8_t* p, bool le) { return le ? ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24))
+                                                      : (((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]); }
+
+// Walks markers until SOFn/SOI/EOI/SOS (process_markers, jpegload.d:1578-1845). Returns marker or -1.
+int walk_markers(ByteSrc& s, Parsed& P)
+{
+    for (;;) {
+        uint32_t c;
+        do {
+            do { c = s.next(); } while (c != 0xFF);
+            do { c = s.next(); } while (c == 0xFF);
+        } while (c == 0);
+        switch (c) {
+        case 0xC0: case 0xC1: case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB:
+        case 0xCD: case 0xCE: case 0xCF: case 0xD8: case 0xD9: case 0xDA:
+            return (int)c;
+        case 0xC4: {  // DHT (:1177-1268)
+            uint32_t left = s.u16();
+            if (left < 2) return -1;
+            left -= 2;
+            while (left) {
+                int index = (int)s.next();
+                uint8_t num[17]; num[0] = 0; int count = 0;
+                for (int i = 1; i <= 16; ++i) { num[i] = (uint8_t)s.next(); count += num[i]; }
+                if (count > 255) return -1;
+                uint8_t val[256]; memset(val, 0, 256);
+                for (int i = 0; i < count; ++i) val[i] = (uint8_t)s.next();
+                uint32_t used = 1 + 16 + (uint32_t)count;
+                if (left < used) return -1;
+                left -= used;
+                index = (index & 0x0F) + ((index & 0x10) >> 4) * 4;
+                if (index >= 8) return -1;
+                P.huff[index].valid = true;
+                memcpy(P.huff[index].num, num, 17); memcpy(P.huff[index].val, val, 256);
+            }
+            break; }
+        case 0xCC: return -1;   // arithmetic coding
+        case 0xDB: {  // DQT (:1272-1340)
+            uint32_t left = s.u16();
+            if (left < 2) return -1;
+            left -= 2;
+            while (left) {
+                int n = (int)s.next(); int prec = n >> 4; n &= 15;
+                if (n >= 4) return -1;
+                P.quant_valid[n] = true;
+                for (int i = 0; i < 64; ++i) { uint32_t t = s.next(); if (prec) t = (t << 8) + s.next(); P.quant[n][i] = (int16_t)t; }
+                uint32_t used = 65 + (prec ? 64 : 0);
+                if (left < used) return -1;
+                left -= used;
+            }
+            break; }
+        case 0xDD:   // DRI (:1445-1463)
+            if (s.u16() != 4) return -1;
+            P.restart_interval = (int)s.u16();
+            break;
+        case 0xE0: {  // APP0 / JFIF density (:1642-1702)
+            uint32_t left = s.u16();
+            if (left < 7) return -1;
+            left -= 2;
+            uint8_t id[5]; for (auto& b : id) b = (uint8_t)s.next();
+            left -= 5;
+            static const uint8_t JFIF[5] = {0x4A, 0x46, 0x49, 0x46, 0x00};
+            if (!memcmp(id, JFIF, 5) && left >= 7) {
+                s.u16();
+                uint32_t units = s.next(); int Xd = (int)s.u16(), Yd = (int)s.u16();
+                left -= 7;
+                P.par = (float)(Xd / (double)Yd);
+                if (units == 0) { P.ppiX = -1; P.ppiY = -1; }
+                else if (units == 1) { P.ppiX = (float)Xd; P.ppiY = (float)Yd; }
+                else if (units == 2) { P.ppiX = inches_to_meters(Xd * 100.0f); P.ppiY = inches_to_meters(Yd * 100.0f); }
+            }
+            while (left) { s.next(); --left; }
+            break; }
+        case 0xE1: {  // APP1 / EXIF resolution (:1703-1800), bounds-checked
+            uint32_t left = s.u16();
+            if (left < 2) return -1;
+            left -= 2;
+            std::vector<uint8_t> ex(left ? left : 1);
+            for (uint32_t i = 0; i < left; ++i) ex[i] = (uint8_t)s.next();
+            static const uint8_t EXIF[6] = {0x45, 0x78, 0x69, 0x66, 0, 0};
+            if (left >= 14 && !memcmp(ex.data(), EXIF, 6)) {
+                const uint8_t* tiff = ex.data() + 6; const uint32_t tlen = left - 6;
+                uint16_t bo = rd16(tiff, false);
+                if (bo != 0x4949 && bo != 0x4D4D) return -1;
+                bool le = bo == 0x4949;
+                if (rd16(tiff + 2, le) != 42) return -1;
+                uint32_t off = rd32(tiff + 4, le);
+                double rx = 72, ry = 72; int unit = 2;
+                while (off != 0) {
+                    if (off > left || (uint64_t)off + 2 > tlen) return -1;
+                    const uint8_t* q = tiff + off;
+                    uint32_t ne = rd16(q, le); q += 2;
+                    if ((uint64_t)(q - tiff) + (uint64_t)ne * 12 + 4 > tlen) return -1;
+                    for (uint32_t e = 0; e < ne; ++e, q += 12) {
+                        uint32_t tag = rd16(q, le), vo = rd32(q + 8, le);
+                        if (tag == 282 || tag == 283) {
+                            if ((uint64_t)vo + 8 > tlen) return -1;
+                            double num = rd32(tiff + vo, le), den = rd32(tiff + vo + 4, le);
+                            if (tag == 282) rx = num / den; else ry = num / den;
+                        }
+                        if (tag == 296) unit = (int)vo;
+                    }
+                    off = rd32(q, le);
+                }
+                if (unit == 2) { P.ppiX = (float)rx; P.ppiY = (float)ry; P.par = (float)(rx / ry); }
+                else if (unit == 3) { P.ppiX = inches_to_meters((float)(rx * 100)); P.ppiY = inches_to_meters((float)(ry * 100)); P.par = (float)(rx / ry); }
+            }
+            break; }
+        case 0xD0: case 0xD1: case 0xD2: case 0xD3: case 0xD4: case 0xD5: case 0xD6: case 0xD7: return -1;
+        case 0xC8: case 0x01: return -1;
+        default: {   // skip_variable_marker (:1408-1432)
+            uint32_t left = s.u16();
+            if (left < 2) return -1;
+            left -= 2;
+            while (left) { s.next(); --left; }
+            break; }
+        }
+    }
+}
+
+bool parse_jpeg(const uint8_t* data, size_t len, Parsed& P)
+{
+    P.ppiX = P.ppiY = P.par = std::nanf("");      // D float.init: never assigned without JFIF/EXIF
+    ByteSrc s{data, len, 0, 0};
+    // the reference pre-fetches 4 bytes into its bit buffer before anything else (initit :2066-2071);
+    // with the stream shorter than that the padding toggles -- reproduce the toggle count
+    // locate_soi_marker (:1851-1895)
+    uint32_t last = s.next(), cur = s.next();
+    if (!(last == 0xFF && cur == 0xD8)) {
+        uint32_t left = 4096;
+        for (;;) {
+            if (--left == 0) return false;
+            last = cur; cur = s.next();
+            if (last == 0xFF) { if (cur == 0xD8) break; if (cur == 0xD9) return false; }
+        }
+        size_t save = s.pos; int st = s.tem;
+        uint32_t nx = s.next(); s.pos = save; s.tem = st;
+        if (nx != 0xFF) return false;
+    }
+    int c = walk_markers(s, P);
+    if (c != 0xC0 && c != 0xC1) return false;      // SOF2 (progressive) and the rest: not on this path
+    // read_sof_marker (:1343-1405)
+    uint32_t left = s.u16();
+    if (s.next() != 8) return false;
+    P.height = (int)s.u16(); if (P.height < 1 || P.height > 16384) return false;
+    P.width = (int)s.u16(); if (P.width < 1 || P.width > 16384) return false;
+    P.comps = (int)s.next(); if (P.comps > 4) return false;
+    if (left != (uint32_t)(P.comps * 3 + 8)) return false;
+    for (int i = 0; i < P.comps; ++i) { P.ident[i] = (int)s.next(); uint32_t hv = s.next(); P.h_samp[i] = hv >> 4; P.v_samp[i] = hv & 15; P.quant_sel[i] = (int)s.next(); }
+    // init_frame (:3130-3268)
+    if (P.comps == 1) { if (P.h_samp[0] != 1 || P.v_samp[0] != 1) return false; P.scan_type = GRAYSCALE; }
+    else if (P.comps == 3) {
+        if (P.h_samp[1] != 1 || P.v_samp[1] != 1 || P.h_samp[2] != 1 || P.v_samp[2] != 1) return false;
+        if (P.h_samp[0] == 1 && P.v_samp[0] == 1) P.scan_type = YH1V1;
+        else if (P.h_samp[0] == 2 && P.v_samp[0] == 1) P.scan_type = YH2V1;
+        else if (P.h_samp[0] == 1 && P.v_samp[0] == 2) P.scan_type = YH1V2;
+        else if (P.h_samp[0] == 2 && P.v_samp[0] == 2) P.scan_type = YH2V2;
+        else return false;
+    } else return false;
+    {
+        static const int bpm[5] = {1, 3, 4, 4, 6};
+        if ((P.width + (P.scan_type == YH2V1 || P.scan_type == YH2V2 ? 15 : 7)) / (P.scan_type == YH2V1 || P.scan_type == YH2V2 ? 16 : 8) * bpm[P.scan_type] > 8192) return false;
+    }
+    // init_scan (:3093-3127): next SOS
+    c = walk_markers(s, P);
+    if (c != 0xDA) return false;
+    // read_sos_marker (:1466-1543)
+    left = s.u16();
+    int n = (int)s.next();
+    P.comps_in_scan = n;
+    left -= 3;
+    if (left != (uint32_t)(n * 2 + 3) || n < 1 || n > 4) return false;
+    for (int i = 0; i < n; ++i) {
+        int cc = (int)s.next(), tc = (int)s.next();
+        left -= 2;
+        int ci = 0;
+        for (; ci < P.comps; ++ci) if (cc == P.ident[ci]) break;
+        if (ci >= P.comps) return false;
+        P.comp_list[i] = ci; P.dc_tab[ci] = (tc >> 4) & 15; P.ac_tab[ci] = (tc & 15) + 4;
+    }
+    s.next(); s.next(); s.next();
+    left -= 3;
+    while (left) { s.next(); --left; }
+    if (s.pos > len) return false;
+    if (P.comps_in_scan != P.comps) return false;  // non-interleaved multi-scan baseline: unsupported
+    // calc_mcu_block_order (:3038-3090)
+    int max_h = P.h_samp[0], max_v = P.v_samp[0];
+    if (P.comps == 1) { P.mcus_per_row = (P.width + 7) / 8; P.mcus_per_col = (P.height + 7) / 8; P.blocks_per_mcu = 1; P.mcu_org[0] = P.comp_list[0]; }
+    else {
+        P.mcus_per_row = (((P.width + 7) / 8) + (max_h - 1)) / max_h;
+        P.mcus_per_col = (((P.height + 7) / 8) + (max_v - 1)) / max_v;
+        P.blocks_per_mcu = 0;
+        for (int k = 0; k < n; ++k) { int ci = P.comp_list[k]; int nb = P.h_samp[ci] * P.v_samp[ci]; while (nb--) { if (P.blocks_per_mcu >= 10) return false; P.mcu_org[P.blocks_per_mcu++] = ci; } }
+    }
+    P.tiles_per_mcu = P.scan_type == YH2V2 ? 12 : P.blocks_per_mcu;
+    for (int i = 0; i < n; ++i) {
+        int ci = P.comp_list[i];
+        if (P.dc_tab[ci] >= 8 || !P.huff[P.dc_tab[ci]].valid) return false;
+        if (P.ac_tab[ci] >= 8 || !P.huff[P.ac_tab[ci]].valid) return false;
+        if (P.quant_sel[ci] >= 4 || !P.quant_valid[P.quant_sel[ci]]) return false;
+    }
+    P.scan_start = s.pos;
+    P.ok = true;
+    return true;
+}
+
+void build_table(const HostHuff& h, HuffTable& T)
+{
+    memset(&T, 0, sizeof(T));
+    memcpy(T.val, h.val, 256);
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; ++l) {
+        T.valptr[l] = k; T.mincode[l] = code;
+        for (int i = 0; i < h.num[l]; ++i, ++k, ++code) {
+            if (l <= HUFF_FAST && code < (1 << l)) {
+                int shift = HUFF_FAST - l;
+                for (int f = 0; f < (1 << shift); ++f) T.fast[(code << shift) | f] = (uint16_t)((l << 8) | h.val[k]);
+            }
+        }
+        T.maxcode[l] = h.num[l] ? code - 1 : -1;
+        code <<= 1;
+    }
+}
+
+inline size_t al(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
+
+} // namespace
+
+namespace gb {
+
+gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                               const uint8_t* const* files_dev, int req_comps_in, cudaStream_t st)
+{
+    if (!ensure_device()) return nullptr;
+    if (n < 0) { set_error("jpeg_decode_batch: negative count"); return nullptr; }
+    gb200_batch* B = new gb200_batch;
+    B->stream = st;
+    B->images.resize((size_t)n);
+    for (auto& D : B->images) { memset(&D, 0, sizeof(D)); D.ppmX = D.ppmY = D.pixelAspectRatio = -1; }
+    if (req_comps_in != -1 && req_comps_in != 1 && req_comps_in != 3 && req_comps_in != 4) return B;   // every image fails (:3727)
+    double t0 = now_ms();
+    std::vector<Parsed> P((size_t)n);
+    std::map<std::string, int> table_ids;
+    std::vector<HuffTable> tables;
+    std::vector<int> live;
+    size_t out_total = 0;
+    std::vector<size_t> out_off((size_t)n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (!files[i] || !parse_jpeg(files[i], lens[i], P[i])) continue;
+        live.push_back(i);
+        int rc = req_comps_in < 0 ? P[i].comps : req_comps_in;
+        out_off[i] = out_total;
+        out_total += al((size_t)P[i].width * P[i].height * rc);
+    }
+    B->host_parse_ms = now_ms() - t0;
+    uint8_t* d_out = nullptr;
+    if (out_total) { d_out = (uint8_t*)dev_alloc(out_total); if (!d_out) { delete B; return nullptr; } B->device_allocs.push_back(d_out); }
+
+    // process in chunks that bound the coefficient/sample scratch
+    const size_t SCRATCH_BUDGET = (size_t)24 << 30;
+    size_t li = 0;
+    std::vector<int> final_ok((size_t)n, 0);
+    while (li < live.size()) {
+        size_t scratch = 0, lj = li;
+        std::vector<size_t> coef_off, samp_off, file_off;
+        size_t file_total = 0;
+        while (lj < live.size()) {
+            const Parsed& p = P[live[lj]];
+            size_t mcus = (size_t)p.mcus_per_row * p.mcus_per_col;
+            size_t need = al(mcus * p.blocks_per_mcu * 128) + al(mcus * p.tiles_per_mcu * 64);
+            if (lj > li && scratch + need > SCRATCH_BUDGET) break;
+            coef_off.push_back(scratch); samp_off.push_back(scratch + al(mcus * p.blocks_per_mcu * 128));
+            scratch += need;
+            file_off.push_back(file_total); file_total += al(lens[live[lj]] + 16);
+            ++lj;
+        }
+        const int m = (int)(lj - li);
+        DevBuf d_scratch(scratch), d_files(files_dev ? 256 : file_total), d_status(sizeof(int) * (size_t)m);
+        if (!d_scratch.p || !d_files.p || !d_status.p) { delete B; return nullptr; }
+        std::vector<JpegImage> imgs((size_t)m);
+        std::vector<Segment> segs;
+        std::vector<int> block_base((size_t)m + 1, 0);
+        uint8_t* h_stage = nullptr;
+        if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
+        std::vector<int> host_fail((size_t)m, 0);
+        long long max_pixels = 1;
+        for (int k = 0; k < m; ++k) {
+            const int i = live[li + k];
+            const Parsed& p = P[i];
+            JpegImage& J = imgs[k];
+            memset(&J, 0, sizeof(J));
+            if (files_dev) J.data = files_dev[i];
+            else { memcpy(h_stage + file_off[k], files[i], lens[i]); J.data = d_files.as<uint8_t>() + file_off[k]; }
+            J.data_len = (uint32_t)lens[i];
+            J.width = p.width; J.height = p.height; J.scan_type = p.scan_type; J.comps = p.comps;
+            J.mcus_per_row = p.mcus_per_row; J.mcus_per_col = p.mcus_per_col; J.blocks_per_mcu = p.blocks_per_mcu; J.tiles_per_mcu = p.tiles_per_mcu;
+            for (int b = 0; b < p.blocks_per_mcu; ++b) J.mcu_org[b] = p.mcu_org[b];
+            for (int c = 0; c < p.comps; ++c) {
+                memcpy(J.quant[c], p.quant[p.quant_sel[c]], 128);
+                for (int which = 0; which < 2; ++which) {
+                    const HostHuff& hh = p.huff[which ? p.ac_tab[c] : p.dc_tab[c]];
+                    std::string key((const char*)hh.num, 17); key.append((const char*)hh.val, 256);
+                    auto it = table_ids.find(key);
+                    int id;
+                    if (it == table_ids.end()) { id = (int)tables.size(); tables.emplace_back(); build_table(hh, tables.back()); table_ids[key] = id; }
+                    else id = it->second;
+                    (which ? J.ac_tab[c] : J.dc_tab[c]) = id;
+                }
+            }
+            J.coefs = (int16_t*)(d_scratch.as<uint8_t>() + coef_off[k]);
+            J.samples = d_scratch.as<uint8_t>() + samp_off[k];
+            J.out = d_out + out_off[i];
+            J.req_comps = req_comps_in < 0 ? p.comps : req_comps_in;
+            J.restart_interval = p.restart_interval;
+            const int total_mcus = p.mcus_per_row * p.mcus_per_col;
+            block_base[k + 1] = block_base[k] + total_mcus * p.blocks_per_mcu;
+            long long px = (long long)p.width * p.height; if (px > max_pixels) max_pixels = px;
+            // segments: the whole scan, or one per restart interval (process_restart, :2335-2402)
+            const uint8_t* f = files[i]; const size_t flen = lens[i];
+            if (!p.restart_interval) segs.push_back(Segment{k, (uint32_t)p.scan_start, (uint32_t)flen, 0, total_mcus});
+            else {
+                size_t pos = p.scan_start; int mcu = 0, expect = 0; bool bad = false;
+                while (mcu < total_mcus) {
+                    int cnt = std::min(p.restart_interval, total_mcus - mcu);
+                    // find the end of this interval's data: the next marker that is not FF00
+                    size_t e = pos;
+                    while (e + 1 < flen && !(f[e] == 0xFF && f[e + 1] != 0x00)) ++e;
+                    if (e + 1 >= flen) e = flen;
+                    segs.push_back(Segment{k, (uint32_t)pos, (uint32_t)e, mcu, cnt});
+                    mcu += cnt;
+                    if (mcu >= total_mcus) break;
+                    // the next interval must start with RST(expect), possibly preceded by fill FFs
+                    size_t q = e;
+                    while (q < flen && f[q] == 0xFF) ++q;
+                    if (q >= flen || q == e || f[q] != (uint8_t)(0xD0 + expect)) { bad = true; break; }
+                    expect = (expect + 1) & 7;
+                    pos = q + 1;
+                }
+                if (bad) host_fail[k] = 1;
+            }
+        }
+        DevBuf d_imgs(sizeof(JpegImage) * (size_t)m), d_segs(sizeof(Segment) * (segs.size() + 1)),
+               d_tables(sizeof(HuffTable) * (tables.size() + 1)), d_base(sizeof(int) * ((size_t)m + 1));
+        if (!d_imgs.p || !d_segs.p || !d_tables.p || !d_base.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+        std::vector<int> st_init((size_t)m);
+        for (int k = 0; k < m; ++k) st_init[k] = host_fail[k] ? 0 : 1;
+        cudaEvent_t ev[4];
+        for (auto& e : ev) cudaEventCreate(&e);
+        bool okc = true;
+        cudaEventRecord(ev[0], st);
+        if (!files_dev) okc &= cuda_ok(cudaMemcpyAsync(d_files.p, h_stage, file_total, cudaMemcpyHostToDevice, st), "files", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_imgs.p, imgs.data(), sizeof(JpegImage) * m, cudaMemcpyHostToDevice, st), "imgs", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_tables.p, tables.data(), sizeof(HuffTable) * tables.size(), cudaMemcpyHostToDevice, st), "tables", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_base.p, block_base.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, st), "base", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
+        // coefficient blocks start zeroed (the reference zero-fills per block, :2459-2510)
+        okc &= cuda_ok(cudaMemsetAsync(d_scratch.p, 0, scratch, st), "memset", __FILE__, __LINE__);
+        cudaEventRecord(ev[1], st);
+        const int nsegs = (int)segs.size();
+        jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>());
+        count_launch();
+        cudaEventRecord(ev[2], st);
+        const long long total_blocks = block_base[m];
+        jpeg_idct_kernel<<<(unsigned)((total_blocks + 127) / 128), 128, 0, st>>>(d_imgs.as<JpegImage>(), d_base.as<int>(), m, total_blocks, d_status.as<int>());
+        count_launch();
+        {
+            long long bx = (max_pixels + 255) / 256; if (bx > 148 * 8) bx = 148 * 8;
+            for (int base = 0; base < m; base += 65535) {
+                int ny = std::min(65535, m - base);
+                jpeg_colour_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, st>>>(d_imgs.as<JpegImage>() + base, d_status.as<int>() + base);
+                count_launch();
+            }
+        }
+        cudaEventRecord(ev[3], st);
+        std::vector<int> status((size_t)m);
+        okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaGetLastError(), "kernels", __FILE__, __LINE__);
+        if (h_stage) pinned_free(h_stage);
+        if (okc) for (int q = 0; q < 3; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (!okc) { delete B; return nullptr; }
+        for (int k = 0; k < m; ++k) final_ok[live[li + k]] = status[k];
+        li = lj;
+    }
+    for (int i = 0; i < n; ++i) {
+        gb200_image_desc& D = B->images[i];
+        if (!final_ok[i]) continue;
+        const Parsed& p = P[i];
+        int rc = req_comps_in < 0 ? p.comps : req_comps_in;
+        D.status = 1; D.pixels = d_out + out_off[i];
+        D.width = p.width; D.height = p.height; D.channels = rc; D.file_channels = p.comps; D.bits = 8;
+        D.pixel_type = rc == 1 ? GB200_l8 : rc == 3 ? GB200_rgb8 : GB200_rgba8;       // plugins/jpeg.d:83-89
+        D.pitch = p.width * rc;
+        D.pixelAspectRatio = p.par; D.ppmY = p.ppiY; D.ppmX = p.ppiX;
+    }
+    B->device_ms = now_ms() - t0 - B->host_parse_ms;
+    return B;
+}
+
+} // namespace gb
+
+GB_API gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                            const uint8_t* const* files_dev, int req_comps, void* stream)
+{
+    gb::clear_error();
+    return gb::jpeg_decode_batch(n, files, lens, files_dev, req_comps, (cudaStream_t)stream);
+}
+
+GB_API uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* width, int* height,
+                                int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY)
+{
+    gb::clear_error();
+    if (pixelAspectRatio) *pixelAspectRatio = -1;
+    if (dotsPerInchY) *dotsPerInchY = -1;
+    if (!gb::ensure_device()) return nullptr;
+    const uint8_t* f[1] = {data}; size_t l[1] = {len};
+    cudaStream_t st = gb::thread_stream();
+    gb200_batch* B = gb::jpeg_decode_batch(1, f, l, nullptr, req_comps, st);
+    if (!B) return nullptr;
+    const gb200_image_desc& D = B->images[0];
+    if (!D.status) { gb::set_error("JPEG decoding failed"); delete B; return nullptr; }
+    size_t bytes = (size_t)D.pitch * D.height;
+    uint8_t* out = (uint8_t*)malloc(bytes ? bytes : 1);
+    if (!out) { delete B; return nullptr; }
+    bool ok = gb::cuda_ok(cudaMemcpyAsync(out, D.pixels, bytes, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) &&
+              gb::cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+    if (width) *width = D.width; if (height) *height = D.height; if (actual_comps) *actual_comps = D.file_channels;
+    if (pixelAspectRatio) *pixelAspectRatio = D.pixelAspectRatio;
+    if (dotsPerInchY) *dotsPerInchY = D.ppmY;
+    delete B;
+    if (!ok) { free(out); return nullptr; }
+    return out;
+}

@@ -122,6 +122,16 @@ int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint32_t* in
                          uint8_t* const* out_dev, const uint32_t* out_caps, int parse_header,
                          uint32_t* out_lens_dev, int* statuses_dev, void* stream);
 
+/* ---- JPEG: source/gamut/codecs/jpegload.d (jpgd port), baseline / extended-sequential Huffman ---- */
+/* decompress_jpeg_image_from_stream (jpegload.d:3720-3808) over a memory buffer. req_comps: -1 keep,
+ * 1, 3 or 4. Returns malloc()'d host pixels or NULL. Progressive (SOF2) files are not on this path and
+ * fail. pixelAspectRatio / dotsPerInchY are NaN when the file carries no JFIF/EXIF density (the
+ * reference's D float members are never assigned in that case). */
+uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* width, int* height,
+                         int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);
+gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                     const uint8_t* const* files_dev, int req_comps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

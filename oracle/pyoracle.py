@@ -48,6 +48,9 @@ def lib():
         L.or_png_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(PngInfo)]
         L.or_png_is16.argtypes = [C.c_char_p, C.c_size_t]
         L.or_png_unfilter.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.or_jpeg_load.restype = C.c_void_p
+        L.or_jpeg_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.or_zlib_decode.restype = C.c_void_p
         L.or_zlib_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
     return _lib
@@ -104,3 +107,15 @@ def zlib_decode(data: bytes, guess: int, parse_header: int = 1):
     if not p:
         return None
     return _take(p, n.value)
+
+
+def jpeg_load(data: bytes, req_comps: int = -1):
+    """or_jpeg_load. Returns (pixels (h, w, c) uint8, actual_comps, par, dpiY) or None."""
+    w, h, ac = C.c_int(), C.c_int(), C.c_int()
+    par, dpi = C.c_float(), C.c_float()
+    p = lib().or_jpeg_load(data, len(data), req_comps, C.byref(w), C.byref(h), C.byref(ac), C.byref(par), C.byref(dpi))
+    if not p:
+        return None
+    c = ac.value if req_comps < 0 else req_comps
+    a = _take(p, w.value * h.value * c)
+    return a.reshape(h.value, w.value, c), ac.value, par.value, dpi.value

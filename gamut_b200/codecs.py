@@ -20,6 +20,16 @@ class ImageDesc(C.Structure):
                 ("status", C.c_int), ("ppmX", C.c_float), ("ppmY", C.c_float), ("pixelAspectRatio", C.c_float)]
 
 
+class QoiDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint8), ("colorspace", C.c_uint8)]
+
+
+class QoixDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitchBytes", C.c_int32), ("channels", C.c_uint8),
+                ("bitdepth", C.c_uint8), ("colorspace", C.c_uint8), ("compression", C.c_uint8),
+                ("pixelAspectRatio", C.c_float), ("resolutionY", C.c_float)]
+
+
 _declared = False
 
 
@@ -47,6 +57,12 @@ def _L():
         L.gb200_jpeg_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp]
         L.gb200_jpeg_decode_batch.restype = vp
         L.gb200_jpeg_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
+        L.gb200_qoi_decode.restype = vp
+        L.gb200_qoi_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoiDesc), i32]
+        L.gb200_qoix_decode.restype = vp
+        L.gb200_qoix_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoixDesc), i32, ip]
+        L.gb200_qoix_decode_batch.restype = vp
+        L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         _declared = True
     return L
 
@@ -173,4 +189,36 @@ def jpeg_decode_batch(files: Sequence[bytes], req_comps: int = -1, files_dev: Op
     h = _L().gb200_jpeg_decode_batch(n, arr, lens, dev, req_comps, stream)
     if not h:
         raise _lib.GamutB200Error("jpeg_decode_batch: " + _lib.last_error())
+    return Batch(h)
+
+
+def qoi_decode(data: bytes, channels: int = 0):
+    """qoi_decode (qoi.d:448). Returns (pixels (h, w, c) uint8, desc) or None."""
+    d = QoiDesc()
+    p = _L().gb200_qoi_decode(data, len(data), C.byref(d), channels)
+    if not p:
+        return None
+    c = channels if channels else d.channels
+    return _take_host(p, d.width * d.height * c).reshape(d.height, d.width, c), d
+
+
+def qoix_decode(data: bytes, flags: int = 0):
+    """qoix_lz4_decode (plugins/qoix.d:350). Returns (pixels (h, w, c) uint8|uint16, desc, PixelType) or None."""
+    d = QoixDesc()
+    t = C.c_int(-1)
+    p = _L().gb200_qoix_decode(data, len(data), C.byref(d), flags, C.byref(t))
+    if not p:
+        return None
+    a = _take_host(p, d.pitchBytes * d.height)
+    if d.bitdepth == 10:
+        a = a.view(np.uint16)
+    return a.reshape(d.height, d.width, d.channels), d, t.value
+
+
+def qoix_decode_batch(files: Sequence[bytes], flags: int = 0, files_dev: Optional[Sequence[int]] = None,
+                      stream: int = 0) -> Batch:
+    n, arr, lens, dev = _batch_args(files, files_dev)
+    h = _L().gb200_qoix_decode_batch(n, arr, lens, dev, flags, stream)
+    if not h:
+        raise _lib.GamutB200Error("qoix_decode_batch: " + _lib.last_error())
     return Batch(h)

@@ -132,6 +132,25 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
 
+/* ---- QOI: source/gamut/codecs/qoi.d ---- */
+typedef struct gb200_qoi_desc { uint32_t width, height; uint8_t channels, colorspace; } gb200_qoi_desc;  /* qoi.d:215-222 minus pitchBytes */
+/* qoi_decode (qoi.d:448-550). channels: 0 = as stored, 3 or 4. malloc()'d host pixels or NULL. */
+uint8_t* gb200_qoi_decode(const uint8_t* data, int size, gb200_qoi_desc* desc, int channels);
+
+/* ---- QOIX (+LZ4): source/gamut/plugins/qoix.d, codecs/{qoi2avg,qoiplane,qoiplane10,qoi10b,lz4}.d ---- */
+typedef struct gb200_qoix_desc {        /* qoi_desc, qoi2avg.d:276-287 */
+    uint32_t width, height;
+    int32_t  pitchBytes;
+    uint8_t  channels, bitdepth, colorspace, compression;
+    float    pixelAspectRatio, resolutionY;
+} gb200_qoix_desc;
+/* qoix_lz4_decode (plugins/qoix.d:350-473): container + optional LZ4 + sub-codec dispatch. `flags` are
+ * LoadFlags (only validated, as in the reference); *decodedType receives the stream's own PixelType.
+ * Built in this round: QOI-Plane10 (10-bit L/LA, version 2) with and without LZ4. */
+uint8_t* gb200_qoix_decode(const uint8_t* data, int size, gb200_qoix_desc* desc, int flags, int* decodedType);
+gb200_batch* gb200_qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                     const uint8_t* const* files_dev, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

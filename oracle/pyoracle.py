@@ -29,6 +29,16 @@ class PngInfo(C.Structure):
                 ("bits", C.c_int), ("ppmX", C.c_float), ("ppmY", C.c_float), ("pixelRatio", C.c_float)]
 
 
+class QoiDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint8), ("colorspace", C.c_uint8)]
+
+
+class QoixDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitchBytes", C.c_int32), ("channels", C.c_uint8),
+                ("bitdepth", C.c_uint8), ("colorspace", C.c_uint8), ("compression", C.c_uint8),
+                ("pixelAspectRatio", C.c_float), ("resolutionY", C.c_float)]
+
+
 _lib = None
 u8p = C.POINTER(C.c_uint8)
 
@@ -51,6 +61,15 @@ def lib():
         L.or_jpeg_load.restype = C.c_void_p
         L.or_jpeg_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.or_qoi_decode.restype = C.c_void_p
+        L.or_qoi_decode.argtypes = [C.c_char_p, C.c_int, C.POINTER(QoiDesc), C.c_int]
+        L.or_qoix_lz4_decode.restype = C.c_void_p
+        L.or_qoix_lz4_decode.argtypes = [C.c_char_p, C.c_int, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
+        L.or_qoix_lz4_encode.restype = C.c_void_p
+        L.or_qoix_lz4_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
+        L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        L.or_lz4_compress_bound.argtypes = [C.c_int]
+        L.or_lz4_decompress_fast.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.or_zlib_decode.restype = C.c_void_p
         L.or_zlib_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
     return _lib
@@ -119,3 +138,51 @@ def jpeg_load(data: bytes, req_comps: int = -1):
     c = ac.value if req_comps < 0 else req_comps
     a = _take(p, w.value * h.value * c)
     return a.reshape(h.value, w.value, c), ac.value, par.value, dpi.value
+
+
+def qoi_decode(data: bytes, channels: int = 0):
+    d = QoiDesc()
+    p = lib().or_qoi_decode(data, len(data), C.byref(d), channels)
+    if not p:
+        return None
+    c = channels if channels else d.channels
+    return _take(p, d.width * d.height * c).reshape(d.height, d.width, c), d
+
+
+def qoix_decode(data: bytes, flags: int = 0):
+    """or_qoix_lz4_decode -> (pixels, desc, PixelType) or None."""
+    d = QoixDesc()
+    t = C.c_int(-1)
+    p = lib().or_qoix_lz4_decode(data, len(data), C.byref(d), flags, C.byref(t))
+    if not p:
+        return None
+    a = _take(p, d.pitchBytes * d.height)
+    if d.bitdepth == 10:
+        a = a.view(np.uint16)
+    return a.reshape(d.height, d.width, d.channels), d, t.value
+
+
+def qoix_encode(pixels: np.ndarray, bitdepth: int, colorspace: int = 0, force_lz4: bool = False,
+                par: float = -1.0, dpi: float = -1.0) -> bytes:
+    """or_qoix_lz4_encode of a (h, w, c) uint16 (10-bit streams) image."""
+    h, w, c = pixels.shape
+    px = np.ascontiguousarray(pixels)
+    d = QoixDesc(w, h, w * c * px.itemsize, c, bitdepth, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = lib().or_qoix_lz4_encode(px.ctypes.data, C.byref(d), 1 if force_lz4 else 0, C.byref(n))
+    if not p:
+        raise RuntimeError("qoix encode failed")
+    return _take(p, n.value).tobytes()
+
+
+def lz4_compress(data: bytes) -> bytes:
+    L = lib()
+    out = np.zeros(L.or_lz4_compress_bound(len(data)) + 16, np.uint8)
+    n = L.or_lz4_compress(data, out.ctypes.data, len(data))
+    return out[:n].tobytes()
+
+
+def lz4_decompress(data: bytes, orig: int):
+    out = np.zeros(orig + 1, np.uint8)
+    r = lib().or_lz4_decompress_fast(data + b"\0" * 16, out.ctypes.data, orig)
+    return out[:orig] if r >= 0 else None

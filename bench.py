@@ -113,7 +113,7 @@ def reference_arm(args, WORKLOADS):
     v = px / t / 1e6
     out = {"metric": "Mpixels/s", "value": round(v, 1), "unit": "Mpixels/s", "impl": "reference",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+           "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
            "config": {"workload": wl.name},
            "cpu_baseline": {"value": round(v, 1), "unit": "Mpixels/s", "cores": cores, "kind": "port",
                             "sample": sample + " (C restatement of the reference; no D toolchain in the image)"},
@@ -218,7 +218,7 @@ def main():
         cfg.update(wl.config())
         out = {"metric": "Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+               "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype,
                "data": "synthetic", "config": cfg,
                "roofline": wl.roofline(peak, peak_kind),
                "e2e": {"value": round(e2e_v, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": wl.h2d,

@@ -326,4 +326,193 @@ class PngWorkload:
         return nimg * W * H, times, f"{nimg} images 1920x1080 RGBA8, {threads} thread(s), one image per worker"
 
 
-WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload}
+
+# ----------------------------------------------------------------------------------------------
+class _BatchDecodeWorkload:
+    """Shared plumbing of the batched decode workloads (JPEG, QOIX): files resident in HBM, one call per step."""
+    dtype = "u8"
+    scaling = "strong"
+    default_steps = 3
+    default_e2e_steps = 1
+    DISTINCT = 8
+
+    def _setup(self, rank, world, args, total_default):
+        import torch
+        from gamut_b200 import codecs
+        self.torch, self.codecs = torch, codecs
+        total = args.batch or total_default
+        self.world = world
+        self.n = max(1, total // world)                      # strong scaling: the batch is sharded across ranks
+        self.total = self.n * world
+        self.files = self.make_files(1000 + 100 * rank)
+        self.host_files = [self.files[i % len(self.files)] for i in range(self.n)]
+        base = [torch.frombuffer(bytearray(f + b"\0" * 64), dtype=torch.uint8).cuda() for f in self.files]
+        self.dev_bufs = [base[i % len(base)].clone() for i in range(self.n)]
+        self.dev_ptrs = [t.data_ptr() for t in self.dev_bufs]
+        self.px_per_step = self.n * self.W * self.H
+        self.e2e_n = min(self.n, 64)
+        self.e2e_px_per_step = self.e2e_n * self.W * self.H
+        self.comp_bytes = sum(len(f) for f in self.files) / len(self.files)
+        self.phase = []
+
+    def step(self, stream, timed):
+        b = self.decode(self.host_files, self.dev_ptrs, stream.cuda_stream)
+        if timed:
+            ph, hp = b.timing()
+            self.phase.append(ph[:3] + [hp])
+        bad = sum(1 for d in b.images if not d.status)
+        b.free()
+        if bad:
+            raise RuntimeError(f"{bad} images failed to decode")
+
+    def finish_timing(self):
+        pass
+
+    def e2e_setup(self):
+        self.h2d = int(self.comp_bytes * self.e2e_n)
+        self.d2h = self.e2e_n * self.out_bytes
+        self.h_out = np.empty(self.e2e_n * self.out_bytes, np.uint8)
+
+    def e2e_step(self):
+        b = self.decode(self.host_files[:self.e2e_n], None, 0)
+        L = self.codecs._L()
+        for i, d in enumerate(b.images):
+            assert d.status
+            L.gb200_copy_to_host(self.h_out.ctypes.data + i * self.out_bytes, d.pixels, self.out_bytes)
+        b.free()
+
+    def roofline(self, peak, peak_kind):
+        ph = np.mean(np.array(self.phase), axis=0)
+        k = 1 if ph[1] >= ph[2] else 2
+        alg = self.kernel_bytes[k] * self.n
+        ach = alg / (ph[k] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": self.kernel_names[k], "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": None,
+                "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(float(ph[k]), 3)}
+
+    def extra(self):
+        ph = np.mean(np.array(self.phase), axis=0)
+        return {"phase_ms": {"upload": round(float(ph[0]), 3), self.kernel_names[1]: round(float(ph[1]), 3),
+                             self.kernel_names[2]: round(float(ph[2]), 3), "host_parse": round(float(ph[3]), 3)}}
+
+
+class JpegWorkload(_BatchDecodeWorkload):
+    """BASELINE configs[3]: JPEG baseline decode (Huffman+IDCT+YCbCr), 3840x2160 4:2:0 q90, batch sharded over ranks."""
+    name = "JPEG baseline decode (Huffman+IDCT+YCbCr) 3840x2160 4:2:0 q90, batch sharded 1/2/4/8 GPU (BASELINE configs[3])"
+    W, H = 3840, 2160
+    e2e_api = "gb200_jpeg_decode_batch (host file bytes staged through pinned memory; rgb8 pixels copied back)"
+    kernel_names = {1: "jpeg_huffman_kernel", 2: "jpeg_idct_kernel+jpeg_colour_kernel"}
+
+    def __init__(self, rank, world, args):
+        self._setup(rank, world, args, 1024)
+        self.out_bytes = self.W * self.H * 3
+        coef = self.W * self.H * 3      # int16 coefficients, 1.5 samples per pixel
+        self.kernel_bytes = {1: self.comp_bytes + coef, 2: coef + self.W * self.H * 3 * 2 + self.out_bytes}
+
+    def make_files(self, seed0):
+        from PIL import Image as PILImage
+        out = []
+        for i in range(self.DISTINCT):
+            img = synth_photo(self.H, self.W, 3, seed0 + i)
+            bio = io.BytesIO()
+            PILImage.fromarray(img, "RGB").save(bio, format="JPEG", quality=90, subsampling=2, optimize=False)
+            out.append(bio.getvalue())
+        return out
+
+    def decode(self, files, dev, stream):
+        return self.codecs.jpeg_decode_batch(files, -1, files_dev=dev, stream=stream)
+
+    def config(self):
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} (total batch {self.total}, {self.DISTINCT} distinct, PIL q90 4:2:0, no DRI)",
+                "compressed_bytes_per_image": int(self.comp_bytes), "scaling_note": "strong: total batch fixed, sharded by image index",
+                "l2": "inputs larger than L2 (every image has its own device copy)"}
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        W, H = JpegWorkload.W, JpegWorkload.H
+        w = JpegWorkload.__new__(JpegWorkload)
+        w.DISTINCT = 2
+        files = w.make_files(1000)
+        nimg = max(threads, 2) if full else 2
+        pyoracle.lib()
+
+        def work(t):
+            for i in range(t, nimg, threads):
+                assert pyoracle.jpeg_load(files[i % len(files)], -1) is not None
+
+        _threads_run(work, threads)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, threads)
+            times.append(time.perf_counter() - t0)
+        return nimg * W * H, times, f"{nimg} images 3840x2160 4:2:0, {threads} thread(s), one image per worker"
+
+
+class QoixWorkload(_BatchDecodeWorkload):
+    """BASELINE configs[4]: QOIX 10-bit LA + LZ4 decode, 2048x2048 images, batch sharded over ranks."""
+    name = "QOIX 10-bit LA + LZ4 decode 2048x2048, batch 2048 sharded over ranks (BASELINE configs[4])"
+    dtype = "u16"
+    W, H = 2048, 2048
+    e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back)"
+    kernel_names = {1: "lz4_kernel", 2: "qoiplane10_kernel"}
+
+    def __init__(self, rank, world, args):
+        self._setup(rank, world, args, 256)
+        self.out_bytes = self.W * self.H * 4
+        self.kernel_bytes = {1: self.comp_bytes + self.payload, 2: self.payload + self.out_bytes}
+
+    def make_files(self, seed0):
+        from oracle import pyoracle            # test-data generation only (the reference's own encoder, restated)
+        sys_path_tests()
+        from qoixutil import depth_map_la
+        out = []
+        pay = 0
+        for i in range(self.DISTINCT):
+            img = depth_map_la(self.H, self.W, seed0 + i, 2)
+            f = pyoracle.qoix_encode(img, 10, force_lz4=True)
+            pay += int.from_bytes(f[25:29], "big")
+            out.append(f)
+        self.payload = pay / self.DISTINCT
+        return out
+
+    def decode(self, files, dev, stream):
+        return self.codecs.qoix_decode_batch(files, 0, files_dev=dev, stream=stream)
+
+    def config(self):
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} la16 (total batch {self.total}, {self.DISTINCT} distinct, LZ4 forced on)",
+                "file_bytes_per_image": int(self.comp_bytes), "opcode_payload_bytes_per_image": int(self.payload),
+                "scaling_note": "strong: total batch fixed, sharded by image index",
+                "l2": "inputs larger than L2 (every image has its own device copy)"}
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        W, H = QoixWorkload.W, QoixWorkload.H
+        w = QoixWorkload.__new__(QoixWorkload)
+        w.DISTINCT = 2
+        files = w.make_files(1000)
+        nimg = max(threads, 2) if full else 2
+
+        def work(t):
+            for i in range(t, nimg, threads):
+                assert pyoracle.qoix_decode(files[i % len(files)], 0) is not None
+
+        _threads_run(work, threads)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, threads)
+            times.append(time.perf_counter() - t0)
+        return nimg * W * H, times, f"{nimg} images 2048x2048 la16 + LZ4, {threads} thread(s), one image per worker"
+
+
+def sys_path_tests():
+    import sys
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload}

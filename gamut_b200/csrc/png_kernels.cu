@@ -111,18 +111,170 @@ __device__ void unfilter_warp(const UnfilterJob& J, int* status, int lane)
     }
 }
 
-__global__ void __launch_bounds__(128)
+// ---------------------------------------------------------------------------------------------
+// Row unfilter, fast path for 4-byte pixels (RGBA8 / LA16 / ...): one CTA of U4_NW warps per job.
+//  * warp w owns bands w, w+U4_NW, ... (a band = 32 rows); inside a band the 32 lanes run the same
+//    skewed wavefront as above, on whole pixels packed in one 32-bit register (SWAR byte arithmetic;
+//    VABSDIFF4 is the only native byte-SIMD instruction on sm_100, the rest lowers to LOP3/IADD);
+//  * the filtered rows are staged into shared memory with coalesced 4-byte cp.async (one 128-byte
+//    transaction per row and chunk), three chunks ahead of use, in a 4-chunk ring per row; rows start at
+//    arbitrary byte offsets (each row is prefixed by its filter byte), so the ring holds aligned words
+//    and a pixel is extracted with one funnel shift;
+//  * results go to a 2-chunk shared ring and are flushed with coalesced 128-byte stores per row;
+//  * the row above a band's first row is the last row of the previous band, produced by another warp
+//    of the same CTA: it is re-read from the (L2-resident) output through the same cp.async ring once
+//    the producer has published the chunk in a shared progress counter.
+// Shared-memory bank = (step - lane) mod 32 for every ring access: conflict-free by construction.
+constexpr int U4_NW = 4;
+constexpr int U4_INW = 128;
+constexpr int U4_OUTW = 64;
+struct U4Smem { uint32_t in[33][U4_INW]; uint32_t out[32][U4_OUTW]; };
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Paeth predictor on four packed bytes. pa = |b-c|, pb = |a-c|; pc = |a+b-2c| equals pa+pb when a-c and
+// b-c have the same sign (saturation keeps every comparison's outcome) and |pa-pb| otherwise.
+__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c);
+    const uint32_t same = ~(__vcmpgeu4(a, c) ^ __vcmpgeu4(b, c));
+    const uint32_t pc = (same & __vaddus4(pa, pb)) | (~same & __vabsdiffu4(pa, pb));
+    const uint32_t m1 = __vcmpleu4(pa, pb) & __vcmpleu4(pa, pc);
+    const uint32_t m2 = __vcmpleu4(pb, pc);
+    return (a & m1) | (~m1 & ((b & m2) | (c & ~m2)));
+}
+
+__device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, volatile int* flushed, int warp, int lane)
+{
+    const uint32_t rb = J.row_bytes, H = J.height, npx = rb >> 2;
+    const int nbands = (int)((H + 31) / 32);
+    const int NCH = (int)((npx + 31) / 32);            // pixel chunks per row
+    const int NCHW = (int)((npx + 1 + 31) / 32);       // aligned-word chunks per row (one extra word when misaligned)
+    const int NSC = (int)((npx + 31 + 31) / 32);       // step chunks per band (31 steps of skew)
+    const int pw = (warp + U4_NW - 1) % U4_NW;         // producer of the row above my bands
+    int kband = 0;
+    for (int band = warp; band < nbands; band += U4_NW, ++kband) {
+        const uint32_t r0 = (uint32_t)band * 32;
+        const uint32_t row = r0 + lane;
+        const bool valid = row < H;
+        const uint8_t* rowaddr = J.raw + (size_t)(valid ? row : H - 1) * (rb + 1) + 1;
+        int f = valid ? rowaddr[-1] : 0;
+        if (f > 4) { status[J.image] = 0; f = 0; }            // "invalid filter" (stbdec.d:1438)
+        const uint32_t sh = ((uint32_t)(uintptr_t)rowaddr & 3u) * 8u;
+        const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
+        const bool anyP = __any_sync(0xffffffffu, f == 4), anyA = __any_sync(0xffffffffu, f == 3);
+        const int kprev = band > 0 ? (band - 1) / U4_NW : 0;
+        const uint8_t* raw0 = J.raw + (size_t)r0 * (rb + 1) + 1;
+        const uint8_t* bnd = band > 0 ? J.out + (size_t)(r0 - 1) * J.out_pitch : nullptr;
+        const uint32_t nrows = min(32u, H - r0);
+
+        auto load_chunk = [&](int c) {
+            if (c < NCHW) {
+                const uint32_t wi = (uint32_t)c * 32 + lane;
+                const uint8_t* p = raw0;
+                for (uint32_t rr = 0; rr < nrows; ++rr, p += rb + 1) {
+                    const uint32_t mis = (uint32_t)(uintptr_t)p & 3u;
+                    const uint32_t nw = (mis + rb + 3) >> 2;
+                    if (wi < nw) cp_async4(&S->in[rr][wi & (U4_INW - 1)], (p - mis) + (size_t)wi * 4);
+                }
+                if (bnd && c < NCH) {
+                    // the producer must have flushed chunk c of its band's last row
+                    const int need = kprev * NCH + c + 1;
+                    while (flushed[pw] < need) __nanosleep(64);
+                    if (wi < npx) cp_async4(&S->in[32][wi & (U4_INW - 1)], bnd + (size_t)wi * 4);
+                }
+            }
+            cp_async_commit();
+        };
+
+        load_chunk(0);
+        load_chunk(1);
+        uint32_t cur = 0, left = 0, upleft = 0;
+        uint8_t* orow = J.out + (size_t)(valid ? row : 0) * J.out_pitch;
+        for (int j = 0; j < NSC; ++j) {
+            load_chunk(j + 2);
+            cp_async_wait<1>();
+            __syncwarp();
+#pragma unroll 4
+            for (int s = 0; s < 32; ++s) {
+                const int x = j * 32 + s - lane;
+                uint32_t up = __shfl_up_sync(0xffffffffu, cur, 1);
+                const bool active = valid && x >= 0 && x < (int)npx;
+                if (lane == 0) up = (bnd && active) ? S->in[32][x & (U4_INW - 1)] : 0u;
+                if (active) {
+                    const uint32_t w0 = S->in[lane][x & (U4_INW - 1)];
+                    const uint32_t w1 = S->in[lane][(x + 1) & (U4_INW - 1)];
+                    const uint32_t raw = __funnelshift_r(w0, w1, sh);
+                    if (x == 0) { left = 0; upleft = 0; }
+                    uint32_t pred = (left & mS) | (up & mU);
+                    if (anyA) pred |= __vhaddu4(left, up) & mA;
+                    if (anyP) pred |= paeth4(left, up, upleft) & mP;
+                    cur = __vadd4(raw, pred);
+                    left = cur;
+                    S->out[lane][x & (U4_OUTW - 1)] = cur;
+                }
+                upleft = up;
+            }
+            __syncwarp();
+            const int fc = j - 1;
+            if (fc >= 0 && fc < NCH) {
+                const uint32_t px = (uint32_t)fc * 32 + lane;
+                if (px < npx) {
+                    uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
+                    for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch)
+                        *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
+            }
+        }
+        for (int fc = max(NSC - 1, 0); fc < NCH; ++fc) {     // chunks not yet flushed by the loop above
+            const uint32_t px = (uint32_t)fc * 32 + lane;
+            if (px < npx) {
+                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
+                for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch)
+                    *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        (void)orow;
+    }
+}
+
+__global__ void __launch_bounds__(U4_NW * 32)
 unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf)
 {
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int j = blockIdx.x * 4 + warp;
+    extern __shared__ __align__(16) uint8_t u4_smem[];
+    __shared__ volatile int flushed[U4_NW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x;
     if (j >= njobs) return;
     UnfilterJob J = jobs[j];
     if (inf && J.inflate_idx >= 0) {
         // the inflated stream must be complete and long enough, else the image fails as a whole
         const InflateJob& ij = inf[J.inflate_idx];
-        if (ij.status != INF_OK || ij.out_len < J.need_len) { if (lane == 0) status[J.image] = 0; return; }
+        if (ij.status != INF_OK || ij.out_len < J.need_len) { if (threadIdx.x == 0) status[J.image] = 0; return; }
     }
+    const bool fast = J.bpp == 4 && (J.row_bytes & 3) == 0 && J.row_bytes >= 4 && (J.out_pitch & 3) == 0 &&
+                      (((uintptr_t)J.out) & 3) == 0;
+    if (fast) {
+        if (threadIdx.x < U4_NW) flushed[threadIdx.x] = 0;
+        __syncthreads();
+        unfilter4_cta(J, status, (U4Smem*)u4_smem + warp, flushed, warp, lane);
+        return;
+    }
+    if (warp != 0) return;
     switch (J.bpp) {
     case 1: unfilter_warp<1>(J, status, lane); break;
     case 2: unfilter_warp<2>(J, status, lane); break;
@@ -135,7 +287,10 @@ unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJo
 void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st)
 {
     if (njobs <= 0) return;
-    unfilter_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, njobs, d_status, d_inf);
+    static bool attr_set = false;
+    const int smem = (int)sizeof(U4Smem) * U4_NW;
+    if (!attr_set) { cudaFuncSetAttribute(unfilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    unfilter_kernel<<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf);
     count_launch();
 }
 

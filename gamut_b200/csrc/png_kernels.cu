@@ -150,14 +150,20 @@ __device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)
     return (a & m1) | (~m1 & ((b & m2) | (c & ~m2)));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
 __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, volatile int* flushed, int warp, int lane)
 {
     const uint32_t rb = J.row_bytes, H = J.height, npx = rb >> 2;
     const int nbands = (int)((H + 31) / 32);
     const int NCH = (int)((npx + 31) / 32);            // pixel chunks per row
-    const int NCHW = (int)((npx + 1 + 31) / 32);       // aligned-word chunks per row (one extra word when misaligned)
     const int NSC = (int)((npx + 31 + 31) / 32);       // step chunks per band (31 steps of skew)
     const int pw = (warp + U4_NW - 1) % U4_NW;         // producer of the row above my bands
+    const bool out16 = ((J.out_pitch & 15) == 0) && ((((uintptr_t)J.out) & 15) == 0);
     int kband = 0;
     for (int band = warp; band < nbands; band += U4_NW, ++kband) {
         const uint32_t r0 = (uint32_t)band * 32;
@@ -166,37 +172,114 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
         const uint8_t* rowaddr = J.raw + (size_t)(valid ? row : H - 1) * (rb + 1) + 1;
         int f = valid ? rowaddr[-1] : 0;
         if (f > 4) { status[J.image] = 0; f = 0; }            // "invalid filter" (stbdec.d:1438)
-        const uint32_t sh = ((uint32_t)(uintptr_t)rowaddr & 3u) * 8u;
-        const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
         const bool anyP = __any_sync(0xffffffffu, f == 4), anyA = __any_sync(0xffffffffu, f == 3);
         const int kprev = band > 0 ? (band - 1) / U4_NW : 0;
         const uint8_t* raw0 = J.raw + (size_t)r0 * (rb + 1) + 1;
         const uint8_t* bnd = band > 0 ? J.out + (size_t)(r0 - 1) * J.out_pitch : nullptr;
         const uint32_t nrows = min(32u, H - r0);
 
+        if (!anyP && !anyA) {
+            // ---- row-parallel mode: only None/Sub/Up rows => no serial dependency except Sub's prefix sum.
+            // lanes = 32 consecutive pixels; loop column blocks (outer) and rows (inner), `upv` in a register.
+            uint32_t carry = 0;                               // lane r: last output pixel of row r in the previous block
+            for (int xb = 0; xb < NCH; ++xb) {
+                const uint32_t px = (uint32_t)xb * 32 + lane;
+                const bool inr = px < npx;
+                uint32_t upv = 0;
+                if (bnd) {
+                    const int need = kprev * NCH + xb + 1;
+                    while (flushed[pw] < need) __nanosleep(64);
+                    if (inr) upv = __ldcg((const uint32_t*)(bnd + (size_t)px * 4));
+                }
+                const uint8_t* p = raw0 + (size_t)px * 4;
+                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
+                for (uint32_t y0 = 0; y0 < nrows; y0 += 8) {
+                    uint32_t w0[8], w1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint8_t* q = p + (size_t)(y0 + u) * (rb + 1);
+                        const uint32_t mis = (uint32_t)(uintptr_t)q & 3u;
+                        const bool ok = inr && (y0 + u) < nrows;
+                        w0[u] = ok ? __ldcs((const uint32_t*)(q - mis)) : 0u;
+                        w1[u] = (ok && mis) ? __ldcs((const uint32_t*)(q - mis) + 1) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t y = y0 + u;
+                        if (y < nrows) {                      // warp-uniform
+                            const uint8_t* q = p + (size_t)y * (rb + 1);
+                            const uint32_t raw = __funnelshift_r(w0[u], w1[u], ((uint32_t)(uintptr_t)q & 3u) * 8u);
+                            const int fy = __shfl_sync(0xffffffffu, f, (int)y);
+                            uint32_t v;
+                            if (fy == 2) v = __vadd4(raw, upv);
+                            else if (fy == 1) {
+                                v = raw;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = __vadd4(v, n); }
+                                v = __vadd4(v, __shfl_sync(0xffffffffu, carry, (int)y));
+                            } else v = raw;
+                            const uint32_t last = __shfl_sync(0xffffffffu, v, 31);
+                            if (lane == (int)y) carry = last;
+                            upv = v;
+                            if (inr) __stcs((uint32_t*)(o + (size_t)y * J.out_pitch), v);
+                        }
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) flushed[warp] = kband * NCH + xb + 1;
+            }
+            continue;
+        }
+
+        // ---- wavefront mode
+        const uint32_t mis16 = (uint32_t)(uintptr_t)rowaddr & 15u;
+        const uint32_t woff = mis16 >> 2, sh = (mis16 & 3u) * 8u;
+        const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
+        const int NCHW = (int)((npx + 4 + 31) / 32);       // 16-byte aligned staging may need up to 4 extra words
+
         auto load_chunk = [&](int c) {
             if (c < NCHW) {
-                const uint32_t wi = (uint32_t)c * 32 + lane;
-                const uint8_t* p = raw0;
-                for (uint32_t rr = 0; rr < nrows; ++rr, p += rb + 1) {
-                    const uint32_t mis = (uint32_t)(uintptr_t)p & 3u;
-                    const uint32_t nw = (mis + rb + 3) >> 2;
-                    if (wi < nw) cp_async4(&S->in[rr][wi & (U4_INW - 1)], (p - mis) + (size_t)wi * 4);
+                const uint32_t vi = (uint32_t)c * 8 + (lane & 7);       // 16-byte vector index within the row
+                const uint8_t* p = raw0 + (size_t)(lane >> 3) * (rb + 1);
+                for (uint32_t rr = lane >> 3; rr < nrows; rr += 4, p += 4 * (size_t)(rb + 1)) {
+                    const uint32_t m = (uint32_t)(uintptr_t)p & 15u;
+                    const uint32_t nv = (m + rb + 15) >> 4;
+                    if (vi < nv) cp_async16(&S->in[rr][(vi * 4) & (U4_INW - 1)], (p - m) + (size_t)vi * 16);
                 }
                 if (bnd && c < NCH) {
                     // the producer must have flushed chunk c of its band's last row
                     const int need = kprev * NCH + c + 1;
                     while (flushed[pw] < need) __nanosleep(64);
+                    const uint32_t wi = (uint32_t)c * 32 + lane;
                     if (wi < npx) cp_async4(&S->in[32][wi & (U4_INW - 1)], bnd + (size_t)wi * 4);
                 }
             }
             cp_async_commit();
         };
+        auto flush_chunk = [&](int fc) {
+            if (out16) {
+                const uint32_t px = (uint32_t)fc * 32 + (lane & 7) * 4;
+                uint8_t* o = J.out + (size_t)(r0 + (lane >> 3)) * J.out_pitch + (size_t)px * 4;
+                for (uint32_t rr = lane >> 3; rr < nrows; rr += 4, o += 4 * (size_t)J.out_pitch) {
+                    if (px + 3 < npx) *(uint4*)o = *(const uint4*)&S->out[rr][px & (U4_OUTW - 1)];
+                    else for (uint32_t k = 0; k < 4 && px + k < npx; ++k) ((uint32_t*)o)[k] = S->out[rr][(px + k) & (U4_OUTW - 1)];
+                }
+            } else {
+                const uint32_t px = (uint32_t)fc * 32 + lane;
+                if (px < npx) {
+                    uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
+                    for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch) *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
+        };
 
         load_chunk(0);
         load_chunk(1);
         uint32_t cur = 0, left = 0, upleft = 0;
-        uint8_t* orow = J.out + (size_t)(valid ? row : 0) * J.out_pitch;
         for (int j = 0; j < NSC; ++j) {
             load_chunk(j + 2);
             cp_async_wait<1>();
@@ -204,51 +287,27 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
 #pragma unroll 4
             for (int s = 0; s < 32; ++s) {
                 const int x = j * 32 + s - lane;
-                uint32_t up = __shfl_up_sync(0xffffffffu, cur, 1);
-                const bool active = valid && x >= 0 && x < (int)npx;
-                if (lane == 0) up = (bnd && active) ? S->in[32][x & (U4_INW - 1)] : 0u;
-                if (active) {
-                    const uint32_t w0 = S->in[lane][x & (U4_INW - 1)];
-                    const uint32_t w1 = S->in[lane][(x + 1) & (U4_INW - 1)];
-                    const uint32_t raw = __funnelshift_r(w0, w1, sh);
-                    if (x == 0) { left = 0; upleft = 0; }
-                    uint32_t pred = (left & mS) | (up & mU);
-                    if (anyA) pred |= __vhaddu4(left, up) & mA;
-                    if (anyP) pred |= paeth4(left, up, upleft) & mP;
-                    cur = __vadd4(raw, pred);
-                    left = cur;
-                    S->out[lane][x & (U4_OUTW - 1)] = cur;
-                }
+                const uint32_t upsh = __shfl_up_sync(0xffffffffu, cur, 1);
+                const uint32_t bv = S->in[32][x & (U4_INW - 1)];
+                const uint32_t up = lane ? upsh : (bnd ? bv : 0u);
+                const bool active = valid && (uint32_t)x < npx;
+                const uint32_t w0 = S->in[lane][(x + woff) & (U4_INW - 1)];
+                const uint32_t w1 = S->in[lane][(x + woff + 1) & (U4_INW - 1)];
+                const uint32_t raw = __funnelshift_r(w0, w1, sh);
+                const uint32_t L = x == 0 ? 0u : left, UL = x == 0 ? 0u : upleft;
+                uint32_t pred = (L & mS) | (up & mU);
+                if (anyA) pred |= __vhaddu4(L, up) & mA;
+                if (anyP) pred |= paeth4(L, up, UL) & mP;
+                const uint32_t nv = __vadd4(raw, pred);
+                if (active) { cur = nv; left = nv; S->out[lane][x & (U4_OUTW - 1)] = nv; }
                 upleft = up;
             }
             __syncwarp();
-            const int fc = j - 1;
-            if (fc >= 0 && fc < NCH) {
-                const uint32_t px = (uint32_t)fc * 32 + lane;
-                if (px < npx) {
-                    uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-                    for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch)
-                        *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
-                }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
-            }
+            if (j - 1 >= 0 && j - 1 < NCH) flush_chunk(j - 1);
         }
-        for (int fc = max(NSC - 1, 0); fc < NCH; ++fc) {     // chunks not yet flushed by the loop above
-            const uint32_t px = (uint32_t)fc * 32 + lane;
-            if (px < npx) {
-                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-                for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch)
-                    *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
-        }
+        for (int fc = max(NSC - 1, 0); fc < NCH; ++fc) flush_chunk(fc);     // chunks not yet flushed by the loop above
         cp_async_wait<0>();
         __syncwarp();
-        (void)orow;
     }
 }
 
@@ -267,7 +326,10 @@ unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJo
         if (ij.status != INF_OK || ij.out_len < J.need_len) { if (threadIdx.x == 0) status[J.image] = 0; return; }
     }
     const bool fast = J.bpp == 4 && (J.row_bytes & 3) == 0 && J.row_bytes >= 4 && (J.out_pitch & 3) == 0 &&
-                      (((uintptr_t)J.out) & 3) == 0;
+                      (((uintptr_t)J.out) & 3) == 0 &&
+                      // 16-byte staging reads up to 15 bytes around each row: fine inside the decoder's padded
+                      // buffers; the stand-alone entry point must hand in 16-byte aligned, padded streams
+                      (J.inflate_idx >= 0 || (((uintptr_t)J.raw) & 15) == 0);
     if (fast) {
         if (threadIdx.x < U4_NW) flushed[threadIdx.x] = 0;
         __syncthreads();

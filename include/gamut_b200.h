@@ -112,7 +112,9 @@ gb200_batch* gb200_png_decode_batch(int n, const uint8_t* const* files, const si
 /* Kernel-level entry for the row unfilter alone (stbi__create_png_image_raw, stbdec.d:1406-1547,
  * 8/16-bit samples, img_n == out_n): `raw` = n_images inflated streams of (1+row_bytes)*height bytes,
  * device-resident, `raw_stride` apart; out = n_images * row_bytes * height. bpp = channels*bytes.
- * status_dev (device int per image, may be NULL) is set to 0 for an image with a filter byte > 4. */
+ * status_dev (device int per image, may be NULL) is set to 0 for an image with a filter byte > 4.
+ * For the fast path `raw` and `raw_stride` should be multiples of 16 with >= 16 readable bytes after each
+ * stream (otherwise a slower generic kernel runs). */
 int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint8_t* out, size_t out_stride,
                               int n_images, int row_bytes, int height, int bpp, int* status_dev, void* stream);
 /* Kernel-level entry for inflate alone: n zlib (parse_header=1) or raw deflate streams, device-resident,

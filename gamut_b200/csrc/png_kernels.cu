@@ -178,66 +178,9 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
         const uint8_t* bnd = band > 0 ? J.out + (size_t)(r0 - 1) * J.out_pitch : nullptr;
         const uint32_t nrows = min(32u, H - r0);
 
-        if (!anyP && !anyA) {
-            // ---- row-parallel mode: only None/Sub/Up rows => no serial dependency except Sub's prefix sum.
-            // lanes = 32 consecutive pixels; loop column blocks (outer) and rows (inner), `upv` in a register.
-            uint32_t carry = 0;                               // lane r: last output pixel of row r in the previous block
-            for (int xb = 0; xb < NCH; ++xb) {
-                const uint32_t px = (uint32_t)xb * 32 + lane;
-                const bool inr = px < npx;
-                uint32_t upv = 0;
-                if (bnd) {
-                    const int need = kprev * NCH + xb + 1;
-                    while (flushed[pw] < need) __nanosleep(64);
-                    if (inr) upv = __ldcg((const uint32_t*)(bnd + (size_t)px * 4));
-                }
-                const uint8_t* p = raw0 + (size_t)px * 4;
-                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-                for (uint32_t y0 = 0; y0 < nrows; y0 += 8) {
-                    uint32_t w0[8], w1[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint8_t* q = p + (size_t)(y0 + u) * (rb + 1);
-                        const uint32_t mis = (uint32_t)(uintptr_t)q & 3u;
-                        const bool ok = inr && (y0 + u) < nrows;
-                        w0[u] = ok ? __ldcs((const uint32_t*)(q - mis)) : 0u;
-                        w1[u] = (ok && mis) ? __ldcs((const uint32_t*)(q - mis) + 1) : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint32_t y = y0 + u;
-                        if (y < nrows) {                      // warp-uniform
-                            const uint8_t* q = p + (size_t)y * (rb + 1);
-                            const uint32_t raw = __funnelshift_r(w0[u], w1[u], ((uint32_t)(uintptr_t)q & 3u) * 8u);
-                            const int fy = __shfl_sync(0xffffffffu, f, (int)y);
-                            uint32_t v;
-                            if (fy == 2) v = __vadd4(raw, upv);
-                            else if (fy == 1) {
-                                v = raw;
-#pragma unroll
-                                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = __vadd4(v, n); }
-                                v = __vadd4(v, __shfl_sync(0xffffffffu, carry, (int)y));
-                            } else v = raw;
-                            const uint32_t last = __shfl_sync(0xffffffffu, v, 31);
-                            if (lane == (int)y) carry = last;
-                            upv = v;
-                            if (inr) __stcs((uint32_t*)(o + (size_t)y * J.out_pitch), v);
-                        }
-                    }
-                }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) flushed[warp] = kband * NCH + xb + 1;
-            }
-            continue;
-        }
-
-        // ---- wavefront mode
-        const uint32_t mis16 = (uint32_t)(uintptr_t)rowaddr & 15u;
-        const uint32_t woff = mis16 >> 2, sh = (mis16 & 3u) * 8u;
-        const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
+        // ---- staging shared by both modes: chunk c = aligned 16-byte vectors [8c, 8c+8) of every row of the
+        // band (+ 4-byte words [32c, 32c+32) of the row above the band), issued two chunks ahead of use
         const int NCHW = (int)((npx + 4 + 31) / 32);       // 16-byte aligned staging may need up to 4 extra words
-
         auto load_chunk = [&](int c) {
             if (c < NCHW) {
                 const uint32_t vi = (uint32_t)c * 8 + (lane & 7);       // 16-byte vector index within the row
@@ -257,6 +200,54 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
             }
             cp_async_commit();
         };
+
+        if (!anyP && !anyA) {
+            // ---- row-parallel mode: only None/Sub/Up rows => no serial dependency except Sub's prefix sum.
+            // lanes = 32 consecutive pixels of one row; loop column blocks (outer) and rows (inner); the pixel
+            // above stays in a register, Sub's carry into the next block lives in lane `row`.
+            uint32_t carry = 0;
+            load_chunk(0);
+            load_chunk(1);
+            for (int xb = 0; xb < NCH; ++xb) {
+                load_chunk(xb + 2);
+                cp_async_wait<1>();
+                __syncwarp();
+                const uint32_t px = (uint32_t)xb * 32 + lane;
+                const bool inr = px < npx;
+                uint32_t upv = bnd ? S->in[32][px & (U4_INW - 1)] : 0u;
+                uint32_t m = (uint32_t)(uintptr_t)raw0 & 15u;
+                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
+#pragma unroll 4
+                for (uint32_t y = 0; y < nrows; ++y, m = (m + rb + 1) & 15u, o += J.out_pitch) {
+                    const uint32_t wo = px + (m >> 2);
+                    const uint32_t w0 = S->in[y][wo & (U4_INW - 1)], w1 = S->in[y][(wo + 1) & (U4_INW - 1)];
+                    const uint32_t raw = __funnelshift_r(w0, w1, (m & 3u) * 8u);
+                    const int fy = __shfl_sync(0xffffffffu, f, (int)y);
+                    uint32_t v = raw;
+                    if (fy == 2) v = __vadd4(raw, upv);
+                    else if (fy == 1) {
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = __vadd4(v, n); }
+                        v = __vadd4(v, __shfl_sync(0xffffffffu, carry, (int)y));
+                        const uint32_t last = __shfl_sync(0xffffffffu, v, 31);
+                        if (lane == (int)y) carry = last;
+                    }
+                    upv = v;
+                    if (inr) __stcs((uint32_t*)o, v);
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) flushed[warp] = kband * NCH + xb + 1;
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            continue;
+        }
+
+        // ---- wavefront mode
+        const uint32_t mis16 = (uint32_t)(uintptr_t)rowaddr & 15u;
+        const uint32_t woff = mis16 >> 2, sh = (mis16 & 3u) * 8u;
+        const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
         auto flush_chunk = [&](int fc) {
             if (out16) {
                 const uint32_t px = (uint32_t)fc * 32 + (lane & 7) * 4;

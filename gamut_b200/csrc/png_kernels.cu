@@ -203,44 +203,78 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
 
         if (!anyP && !anyA) {
             // ---- row-parallel mode: only None/Sub/Up rows => no serial dependency except Sub's prefix sum.
-            // lanes = 32 consecutive pixels of one row; loop column blocks (outer) and rows (inner); the pixel
-            // above stays in a register, Sub's carry into the next block lives in lane `row`.
-            uint32_t carry = 0;
-            load_chunk(0);
-            load_chunk(1);
-            for (int xb = 0; xb < NCH; ++xb) {
-                load_chunk(xb + 2);
-                cp_async_wait<1>();
-                __syncwarp();
-                const uint32_t px = (uint32_t)xb * 32 + lane;
-                const bool inr = px < npx;
-                uint32_t upv = bnd ? S->in[32][px & (U4_INW - 1)] : 0u;
-                uint32_t m = (uint32_t)(uintptr_t)raw0 & 15u;
+            // Each lane owns 4 consecutive pixels (16 bytes) of a 128-pixel column block; blocks are the outer
+            // loop, rows the inner one, so the pixels above stay in registers. Loads are 16-byte vectors straight
+            // from global memory (two per lane and row: rows start at arbitrary byte offsets), four rows in flight.
+            const uint32_t maskU = __ballot_sync(0xffffffffu, f == 2), maskS = __ballot_sync(0xffffffffu, f == 1);
+            const int NB = (int)((npx + 127) / 128);
+            uint32_t carry = 0;                               // lane r: last output pixel of row r in the previous block
+            for (int xb = 0; xb < NB; ++xb) {
+                const uint32_t px = (uint32_t)xb * 128 + lane * 4;
+                uint32_t up0 = 0, up1 = 0, up2 = 0, up3 = 0;
+                if (bnd) {
+                    const int need = kprev * NCH + min(4 * xb + 4, NCH);
+                    while (flushed[pw] < need) __nanosleep(32);
+                    const uint32_t* bp = (const uint32_t*)(bnd + (size_t)px * 4);
+                    if (px + 3 < npx && out16) { const uint4 t = __ldcg((const uint4*)bp); up0 = t.x; up1 = t.y; up2 = t.z; up3 = t.w; }
+                    else { if (px < npx) up0 = __ldcg(bp); if (px + 1 < npx) up1 = __ldcg(bp + 1); if (px + 2 < npx) up2 = __ldcg(bp + 2); if (px + 3 < npx) up3 = __ldcg(bp + 3); }
+                }
+                const uint8_t* rp = raw0 + (size_t)px * 4;    // this lane's first pixel in row 0 of the band
                 uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-#pragma unroll 4
-                for (uint32_t y = 0; y < nrows; ++y, m = (m + rb + 1) & 15u, o += J.out_pitch) {
-                    const uint32_t wo = px + (m >> 2);
-                    const uint32_t w0 = S->in[y][wo & (U4_INW - 1)], w1 = S->in[y][(wo + 1) & (U4_INW - 1)];
-                    const uint32_t raw = __funnelshift_r(w0, w1, (m & 3u) * 8u);
-                    const int fy = __shfl_sync(0xffffffffu, f, (int)y);
-                    uint32_t v = raw;
-                    if (fy == 2) v = __vadd4(raw, upv);
-                    else if (fy == 1) {
+                for (uint32_t y0 = 0; y0 < nrows; y0 += 4) {
+                    uint4 A[4], B[4];
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = __vadd4(v, n); }
-                        v = __vadd4(v, __shfl_sync(0xffffffffu, carry, (int)y));
-                        const uint32_t last = __shfl_sync(0xffffffffu, v, 31);
-                        if (lane == (int)y) carry = last;
+                    for (int u = 0; u < 4; ++u) {
+                        const uint8_t* q = rp + (size_t)(y0 + u) * (rb + 1);
+                        const uint4* v = (const uint4*)(q - ((uintptr_t)q & 15));
+                        const bool ok = (y0 + u) < nrows && px < npx;
+                        A[u] = ok ? __ldg(v) : make_uint4(0, 0, 0, 0);
+                        B[u] = ok ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
                     }
-                    upv = v;
-                    if (inr) __stcs((uint32_t*)o, v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t y = y0 + u;
+                        if (y < nrows) {                      // warp-uniform
+                            const uint8_t* q = rp + (size_t)y * (rb + 1);
+                            const uint32_t m = (uint32_t)(uintptr_t)q & 15u, shb = (m & 3u) * 8u;
+                            uint32_t w0, w1, w2, w3, w4;
+                            switch (m >> 2) {                 // uniform: every lane of the row has the same misalignment
+                            case 0: w0 = A[u].x; w1 = A[u].y; w2 = A[u].z; w3 = A[u].w; w4 = B[u].x; break;
+                            case 1: w0 = A[u].y; w1 = A[u].z; w2 = A[u].w; w3 = B[u].x; w4 = B[u].y; break;
+                            case 2: w0 = A[u].z; w1 = A[u].w; w2 = B[u].x; w3 = B[u].y; w4 = B[u].z; break;
+                            default: w0 = A[u].w; w1 = B[u].x; w2 = B[u].y; w3 = B[u].z; w4 = B[u].w; break;
+                            }
+                            uint32_t v0 = __funnelshift_r(w0, w1, shb), v1 = __funnelshift_r(w1, w2, shb);
+                            uint32_t v2 = __funnelshift_r(w2, w3, shb), v3 = __funnelshift_r(w3, w4, shb);
+                            if ((maskS >> y) & 1u) {
+                                v1 = __vadd4(v1, v0); v2 = __vadd4(v2, v1); v3 = __vadd4(v3, v2);
+                                uint32_t inc = v3;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = __vadd4(inc, n); }
+                                uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+                                if (lane == 0) ex = 0;
+                                ex = __vadd4(ex, __shfl_sync(0xffffffffu, carry, (int)y));
+                                v0 = __vadd4(v0, ex); v1 = __vadd4(v1, ex); v2 = __vadd4(v2, ex); v3 = __vadd4(v3, ex);
+                            } else {
+                                const uint32_t mu = 0u - ((maskU >> y) & 1u);
+                                v0 = __vadd4(v0, up0 & mu); v1 = __vadd4(v1, up1 & mu); v2 = __vadd4(v2, up2 & mu); v3 = __vadd4(v3, up3 & mu);
+                            }
+                            // last pixel of the row inside this block (for Sub's carry into the next block)
+                            const uint32_t lastpx = min(npx - 1, (uint32_t)xb * 128 + 127);
+                            const uint32_t lsel = (lastpx & 3u) == 0 ? v0 : (lastpx & 3u) == 1 ? v1 : (lastpx & 3u) == 2 ? v2 : v3;
+                            const uint32_t last = __shfl_sync(0xffffffffu, lsel, (int)((lastpx >> 2) & 31u));
+                            if (lane == (int)y) carry = last;
+                            up0 = v0; up1 = v1; up2 = v2; up3 = v3;
+                            uint32_t* op = (uint32_t*)(o + (size_t)y * J.out_pitch);
+                            if (px + 3 < npx && out16) __stcs((uint4*)op, make_uint4(v0, v1, v2, v3));
+                            else { if (px < npx) op[0] = v0; if (px + 1 < npx) op[1] = v1; if (px + 2 < npx) op[2] = v2; if (px + 3 < npx) op[3] = v3; }
+                        }
+                    }
                 }
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) flushed[warp] = kband * NCH + xb + 1;
+                if (lane == 0) flushed[warp] = kband * NCH + min(4 * xb + 4, NCH);
             }
-            cp_async_wait<0>();
-            __syncwarp();
             continue;
         }
 

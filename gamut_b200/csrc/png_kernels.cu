@@ -209,71 +209,97 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
             const uint32_t maskU = __ballot_sync(0xffffffffu, f == 2), maskS = __ballot_sync(0xffffffffu, f == 1);
             const int NB = (int)((npx + 127) / 128);
             uint32_t carry = 0;                               // lane r: last output pixel of row r in the previous block
-            for (int xb = 0; xb < NB; ++xb) {
+            uint32_t up0 = 0, up1 = 0, up2 = 0, up3 = 0;
+            const int ngroups = (int)((nrows + 3) / 4);
+            const int total = NB * ngroups;
+
+            auto load_group = [&](int gi, uint4 (&A)[4], uint4 (&B)[4]) {
+                const int xb = gi / ngroups; const uint32_t y0 = (uint32_t)(gi - xb * ngroups) * 4;
                 const uint32_t px = (uint32_t)xb * 128 + lane * 4;
-                uint32_t up0 = 0, up1 = 0, up2 = 0, up3 = 0;
-                if (bnd) {
-                    const int need = kprev * NCH + min(4 * xb + 4, NCH);
-                    while (flushed[pw] < need) __nanosleep(32);
-                    const uint32_t* bp = (const uint32_t*)(bnd + (size_t)px * 4);
-                    if (px + 3 < npx && out16) { const uint4 t = __ldcg((const uint4*)bp); up0 = t.x; up1 = t.y; up2 = t.z; up3 = t.w; }
-                    else { if (px < npx) up0 = __ldcg(bp); if (px + 1 < npx) up1 = __ldcg(bp + 1); if (px + 2 < npx) up2 = __ldcg(bp + 2); if (px + 3 < npx) up3 = __ldcg(bp + 3); }
+                const uint8_t* rp = raw0 + (size_t)px * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint8_t* q = rp + (size_t)(y0 + u) * (rb + 1);
+                    const uint4* v = (const uint4*)(q - ((uintptr_t)q & 15));
+                    const bool ok = gi < total && (y0 + u) < nrows && px < npx;
+                    A[u] = ok ? __ldg(v) : make_uint4(0, 0, 0, 0);
+                    B[u] = ok ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
                 }
-                const uint8_t* rp = raw0 + (size_t)px * 4;    // this lane's first pixel in row 0 of the band
-                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-                for (uint32_t y0 = 0; y0 < nrows; y0 += 4) {
-                    uint4 A[4], B[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint8_t* q = rp + (size_t)(y0 + u) * (rb + 1);
-                        const uint4* v = (const uint4*)(q - ((uintptr_t)q & 15));
-                        const bool ok = (y0 + u) < nrows && px < npx;
-                        A[u] = ok ? __ldg(v) : make_uint4(0, 0, 0, 0);
-                        B[u] = ok ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
+            };
+            auto compute_group = [&](int gi, const uint4 (&A)[4], const uint4 (&B)[4]) {
+                const int xb = gi / ngroups; const uint32_t y0 = (uint32_t)(gi - xb * ngroups) * 4;
+                const uint32_t px = (uint32_t)xb * 128 + lane * 4;
+                if (y0 == 0) {                                // block start: the row above the band
+                    up0 = up1 = up2 = up3 = 0;
+                    if (bnd) {
+                        const int need = kprev * NCH + min(4 * xb + 4, NCH);
+                        while (flushed[pw] < need) __nanosleep(32);
+                        const uint32_t* bp = (const uint32_t*)(bnd + (size_t)px * 4);
+                        if (px + 3 < npx && out16) { const uint4 t = __ldcg((const uint4*)bp); up0 = t.x; up1 = t.y; up2 = t.z; up3 = t.w; }
+                        else { if (px < npx) up0 = __ldcg(bp); if (px + 1 < npx) up1 = __ldcg(bp + 1); if (px + 2 < npx) up2 = __ldcg(bp + 2); if (px + 3 < npx) up3 = __ldcg(bp + 3); }
                     }
+                }
+                const uint8_t* rp = raw0 + (size_t)px * 4;
+                uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t y = y0 + u;
-                        if (y < nrows) {                      // warp-uniform
-                            const uint8_t* q = rp + (size_t)y * (rb + 1);
-                            const uint32_t m = (uint32_t)(uintptr_t)q & 15u, shb = (m & 3u) * 8u;
-                            uint32_t w0, w1, w2, w3, w4;
-                            switch (m >> 2) {                 // uniform: every lane of the row has the same misalignment
-                            case 0: w0 = A[u].x; w1 = A[u].y; w2 = A[u].z; w3 = A[u].w; w4 = B[u].x; break;
-                            case 1: w0 = A[u].y; w1 = A[u].z; w2 = A[u].w; w3 = B[u].x; w4 = B[u].y; break;
-                            case 2: w0 = A[u].z; w1 = A[u].w; w2 = B[u].x; w3 = B[u].y; w4 = B[u].z; break;
-                            default: w0 = A[u].w; w1 = B[u].x; w2 = B[u].y; w3 = B[u].z; w4 = B[u].w; break;
-                            }
-                            uint32_t v0 = __funnelshift_r(w0, w1, shb), v1 = __funnelshift_r(w1, w2, shb);
-                            uint32_t v2 = __funnelshift_r(w2, w3, shb), v3 = __funnelshift_r(w3, w4, shb);
-                            if ((maskS >> y) & 1u) {
-                                v1 = __vadd4(v1, v0); v2 = __vadd4(v2, v1); v3 = __vadd4(v3, v2);
-                                uint32_t inc = v3;
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t y = y0 + u;
+                    if (y < nrows) {                          // warp-uniform
+                        const uint8_t* q = rp + (size_t)y * (rb + 1);
+                        const uint32_t m = (uint32_t)(uintptr_t)q & 15u, shb = (m & 3u) * 8u;
+                        uint32_t w0, w1, w2, w3, w4;
+                        switch (m >> 2) {                     // uniform: every lane of the row has the same misalignment
+                        case 0: w0 = A[u].x; w1 = A[u].y; w2 = A[u].z; w3 = A[u].w; w4 = B[u].x; break;
+                        case 1: w0 = A[u].y; w1 = A[u].z; w2 = A[u].w; w3 = B[u].x; w4 = B[u].y; break;
+                        case 2: w0 = A[u].z; w1 = A[u].w; w2 = B[u].x; w3 = B[u].y; w4 = B[u].z; break;
+                        default: w0 = A[u].w; w1 = B[u].x; w2 = B[u].y; w3 = B[u].z; w4 = B[u].w; break;
+                        }
+                        uint32_t v0 = __funnelshift_r(w0, w1, shb), v1 = __funnelshift_r(w1, w2, shb);
+                        uint32_t v2 = __funnelshift_r(w2, w3, shb), v3 = __funnelshift_r(w3, w4, shb);
+                        if ((maskS >> y) & 1u) {
+                            v1 = __vadd4(v1, v0); v2 = __vadd4(v2, v1); v3 = __vadd4(v3, v2);
+                            uint32_t inc = v3;
 #pragma unroll
-                                for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = __vadd4(inc, n); }
-                                uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
-                                if (lane == 0) ex = 0;
-                                ex = __vadd4(ex, __shfl_sync(0xffffffffu, carry, (int)y));
-                                v0 = __vadd4(v0, ex); v1 = __vadd4(v1, ex); v2 = __vadd4(v2, ex); v3 = __vadd4(v3, ex);
-                            } else {
-                                const uint32_t mu = 0u - ((maskU >> y) & 1u);
-                                v0 = __vadd4(v0, up0 & mu); v1 = __vadd4(v1, up1 & mu); v2 = __vadd4(v2, up2 & mu); v3 = __vadd4(v3, up3 & mu);
-                            }
-                            // last pixel of the row inside this block (for Sub's carry into the next block)
+                            for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = __vadd4(inc, n); }
+                            uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+                            if (lane == 0) ex = 0;
+                            ex = __vadd4(ex, __shfl_sync(0xffffffffu, carry, (int)y));
+                            v0 = __vadd4(v0, ex); v1 = __vadd4(v1, ex); v2 = __vadd4(v2, ex); v3 = __vadd4(v3, ex);
+                            // last pixel of the row inside this block = carry into the next block
                             const uint32_t lastpx = min(npx - 1, (uint32_t)xb * 128 + 127);
                             const uint32_t lsel = (lastpx & 3u) == 0 ? v0 : (lastpx & 3u) == 1 ? v1 : (lastpx & 3u) == 2 ? v2 : v3;
                             const uint32_t last = __shfl_sync(0xffffffffu, lsel, (int)((lastpx >> 2) & 31u));
                             if (lane == (int)y) carry = last;
-                            up0 = v0; up1 = v1; up2 = v2; up3 = v3;
-                            uint32_t* op = (uint32_t*)(o + (size_t)y * J.out_pitch);
-                            if (px + 3 < npx && out16) __stcs((uint4*)op, make_uint4(v0, v1, v2, v3));
-                            else { if (px < npx) op[0] = v0; if (px + 1 < npx) op[1] = v1; if (px + 2 < npx) op[2] = v2; if (px + 3 < npx) op[3] = v3; }
+                        } else {
+                            const uint32_t mu = 0u - ((maskU >> y) & 1u);
+                            v0 = __vadd4(v0, up0 & mu); v1 = __vadd4(v1, up1 & mu); v2 = __vadd4(v2, up2 & mu); v3 = __vadd4(v3, up3 & mu);
+                            if (maskS) {                      // some other row of the band is Sub: keep its carry current
+                                const uint32_t lastpx = min(npx - 1, (uint32_t)xb * 128 + 127);
+                                const uint32_t lsel = (lastpx & 3u) == 0 ? v0 : (lastpx & 3u) == 1 ? v1 : (lastpx & 3u) == 2 ? v2 : v3;
+                                const uint32_t last = __shfl_sync(0xffffffffu, lsel, (int)((lastpx >> 2) & 31u));
+                                if (lane == (int)y) carry = last;
+                            }
                         }
+                        up0 = v0; up1 = v1; up2 = v2; up3 = v3;
+                        uint32_t* op = (uint32_t*)(o + (size_t)y * J.out_pitch);
+                        if (px + 3 < npx && out16) __stcs((uint4*)op, make_uint4(v0, v1, v2, v3));
+                        else { if (px < npx) op[0] = v0; if (px + 1 < npx) op[1] = v1; if (px + 2 < npx) op[2] = v2; if (px + 3 < npx) op[3] = v3; }
                     }
                 }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) flushed[warp] = kband * NCH + min(4 * xb + 4, NCH);
+                if ((int)(y0 / 4) == ngroups - 1) {           // block end: publish it for the band below
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) flushed[warp] = kband * NCH + min(4 * xb + 4, NCH);
+                }
+            };
+
+            uint4 A0[4], B0[4], A1[4], B1[4];
+            load_group(0, A0, B0);
+            for (int gi = 0; gi < total; gi += 2) {
+                load_group(gi + 1, A1, B1);
+                compute_group(gi, A0, B0);
+                load_group(gi + 2, A0, B0);
+                if (gi + 1 < total) compute_group(gi + 1, A1, B1);
             }
             continue;
         }

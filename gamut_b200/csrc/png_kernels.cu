@@ -214,16 +214,19 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
             const int total = NB * ngroups;
 
             auto load_group = [&](int gi, uint4 (&A)[4], uint4 (&B)[4]) {
+                // always load (addresses clamped into the band) so that no select has to wait for the data;
+                // lanes / rows past the end read valid memory and their values are never stored
+                gi = min(gi, total - 1);
                 const int xb = gi / ngroups; const uint32_t y0 = (uint32_t)(gi - xb * ngroups) * 4;
-                const uint32_t px = (uint32_t)xb * 128 + lane * 4;
+                uint32_t px = (uint32_t)xb * 128 + lane * 4;
+                if (px >= npx) px = 0;
                 const uint8_t* rp = raw0 + (size_t)px * 4;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint8_t* q = rp + (size_t)(y0 + u) * (rb + 1);
+                    const uint8_t* q = rp + (size_t)min(y0 + u, nrows - 1) * (rb + 1);
                     const uint4* v = (const uint4*)(q - ((uintptr_t)q & 15));
-                    const bool ok = gi < total && (y0 + u) < nrows && px < npx;
-                    A[u] = ok ? __ldg(v) : make_uint4(0, 0, 0, 0);
-                    B[u] = ok ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
+                    A[u] = __ldg(v);
+                    B[u] = __ldg(v + 1);
                 }
             };
             auto compute_group = [&](int gi, const uint4 (&A)[4], const uint4 (&B)[4]) {

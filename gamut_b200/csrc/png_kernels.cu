@@ -365,6 +365,10 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
     }
 }
 
+// Two launches per batch: <true> handles the images whose rows are all None/Sub/Up (row-parallel mode only,
+// no shared-memory rings => 2x the resident warps), <false> handles every other image. Each CTA classifies its
+// image by scanning the filter bytes first.
+template <bool ROWPAR_ONLY>
 __global__ void __launch_bounds__(U4_NW * 32)
 unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf)
 {
@@ -377,20 +381,24 @@ unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJo
     if (inf && J.inflate_idx >= 0) {
         // the inflated stream must be complete and long enough, else the image fails as a whole
         const InflateJob& ij = inf[J.inflate_idx];
-        if (ij.status != INF_OK || ij.out_len < J.need_len) { if (threadIdx.x == 0) status[J.image] = 0; return; }
+        if (ij.status != INF_OK || ij.out_len < J.need_len) { if (threadIdx.x == 0 && !ROWPAR_ONLY) status[J.image] = 0; return; }
     }
     const bool fast = J.bpp == 4 && (J.row_bytes & 3) == 0 && J.row_bytes >= 4 && (J.out_pitch & 3) == 0 &&
                       (((uintptr_t)J.out) & 3) == 0 &&
-                      // 16-byte staging reads up to 15 bytes around each row: fine inside the decoder's padded
+                      // 16-byte staging reads up to 31 bytes around each row: fine inside the decoder's padded
                       // buffers; the stand-alone entry point must hand in 16-byte aligned, padded streams
                       (J.inflate_idx >= 0 || (((uintptr_t)J.raw) & 15) == 0);
     if (fast) {
+        int wave = 0;
+        for (uint32_t r = threadIdx.x; r < J.height; r += U4_NW * 32) wave |= J.raw[(size_t)r * (J.row_bytes + 1)] > 2;
+        wave = __syncthreads_or(wave);
+        if (ROWPAR_ONLY == (wave != 0)) return;            // the other launch owns this image
         if (threadIdx.x < U4_NW) flushed[threadIdx.x] = 0;
         __syncthreads();
-        unfilter4_cta(J, status, (U4Smem*)u4_smem + warp, flushed, warp, lane);
+        unfilter4_cta(J, status, ROWPAR_ONLY ? nullptr : (U4Smem*)u4_smem + warp, flushed, warp, lane);
         return;
     }
-    if (warp != 0) return;
+    if (ROWPAR_ONLY || warp != 0) return;
     switch (J.bpp) {
     case 1: unfilter_warp<1>(J, status, lane); break;
     case 2: unfilter_warp<2>(J, status, lane); break;
@@ -405,9 +413,10 @@ void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const 
     if (njobs <= 0) return;
     static bool attr_set = false;
     const int smem = (int)sizeof(U4Smem) * U4_NW;
-    if (!attr_set) { cudaFuncSetAttribute(unfilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    unfilter_kernel<<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf);
-    count_launch();
+    if (!attr_set) { cudaFuncSetAttribute(unfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    unfilter_kernel<true><<<njobs, U4_NW * 32, 0, st>>>(d_jobs, njobs, d_status, d_inf);
+    unfilter_kernel<false><<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf);
+    count_launch(2);
 }
 
 // ---------------------------------------------------------------------------------------------

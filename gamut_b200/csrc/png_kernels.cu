@@ -296,13 +296,10 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
                 }
             };
 
-            uint4 A0[4], B0[4], A1[4], B1[4];
-            load_group(0, A0, B0);
-            for (int gi = 0; gi < total; gi += 2) {
-                load_group(gi + 1, A1, B1);
+            uint4 A0[4], B0[4];
+            for (int gi = 0; gi < total; ++gi) {
+                load_group(gi, A0, B0);
                 compute_group(gi, A0, B0);
-                load_group(gi + 2, A0, B0);
-                if (gi + 1 < total) compute_group(gi + 1, A1, B1);
             }
             continue;
         }
@@ -369,7 +366,7 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
 // no shared-memory rings => 2x the resident warps), <false> handles every other image. Each CTA classifies its
 // image by scanning the filter bytes first.
 template <bool ROWPAR_ONLY>
-__global__ void __launch_bounds__(U4_NW * 32)
+__global__ void __launch_bounds__(U4_NW * 32, ROWPAR_ONLY ? 6 : 2)
 unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf)
 {
     extern __shared__ __align__(16) uint8_t u4_smem[];

@@ -14,7 +14,7 @@
 namespace gb {
 void launch_inflate(InflateJob* d_jobs, int njobs, cudaStream_t st);
 void launch_gather(const void* d_segs, int nsegs, cudaStream_t st);
-void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st);
+void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st, int rowpar_threads);
 void launch_finish(const FinishJob* d_jobs, int njobs, uint64_t max_pixels, cudaStream_t st);
 struct Segment { const uint8_t* src; uint8_t* dst; uint32_t len; };
 }
@@ -283,6 +283,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         uint8_t* h_stage = nullptr;
         if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(idat_total); if (!h_stage) { delete B; return nullptr; } }
         uint64_t max_pixels = 1;
+        int rowpar_threads = 32;
         for (int k = 0; k < m; ++k) {
             const int i = pending[k];
             Plan& P = plans[i];
@@ -310,6 +311,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
                 u.row_bytes = P.pass_rb[p]; u.height = P.pass_h[p]; u.bpp = (uint32_t)bpp; u.out_pitch = P.pass_rb[p];
                 u.image = k; u.inflate_idx = k; u.need_len = P.need_len;
                 ujobs.push_back(u);
+                if (bpp == 4) { int t = (int)((P.pass_rb[p] / 4 + 127) / 128) * 32; if (t <= 1024 && t > rowpar_threads) rowpar_threads = t; }
             }
             if (!P.direct) {
                 FinishJob f; memset(&f, 0, sizeof(f));
@@ -350,7 +352,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         cudaEventRecord(ev[1], st);
         launch_inflate(d_ij.as<InflateJob>(), m, st);
         cudaEventRecord(ev[2], st);
-        launch_unfilter(d_uj.as<UnfilterJob>(), (int)ujobs.size(), d_status.as<int>(), d_ij.as<InflateJob>(), st);
+        launch_unfilter(d_uj.as<UnfilterJob>(), (int)ujobs.size(), d_status.as<int>(), d_ij.as<InflateJob>(), st, rowpar_threads);
         cudaEventRecord(ev[3], st);
         launch_finish(d_fj.as<FinishJob>(), (int)fjobs.size(), max_pixels, st);
         cudaEventRecord(ev[4], st);
@@ -477,7 +479,8 @@ GB_API int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint
     int* d_dummy = (int*)s_dummy.get(sizeof(int) * (size_t)n_images);
     if (!d_jobs || !d_dummy) return 0;
     GB_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(gb::UnfilterJob) * (size_t)n_images, cudaMemcpyHostToDevice, st));
-    gb::launch_unfilter(d_jobs, n_images, status_dev ? status_dev : d_dummy, nullptr, st);
+    int rp = bpp == 4 ? (int)(((row_bytes / 4 + 127) / 128) * 32) : 32;
+    gb::launch_unfilter(d_jobs, n_images, status_dev ? status_dev : d_dummy, nullptr, st, rp <= 1024 ? rp : 32);
     GB_CUDA(cudaGetLastError());
     // jobs were copied from pageable memory: the copy has completed on return
     return 1;

@@ -362,12 +362,99 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row unfilter, images whose rows are all None/Sub/Up (4-byte pixels): no pixel depends on anything but the
+// pixel above (Up) or the raw bytes to its left (Sub is a prefix sum of the *filtered* row). One CTA per image,
+// one warp per 128-pixel column block, every warp streams down the image with the row above in registers and
+// 16-byte vector accesses; the warps of a CTA read and write whole rows together (good DRAM locality). A Sub
+// row needs the sum of the blocks to its left: exchanged through shared memory with one barrier per Sub row.
+constexpr int RP_MAX_WARPS = 32;
+__global__ void __launch_bounds__(RP_MAX_WARPS * 32, 1)
+unfilter_rowpar_kernel(const UnfilterJob* jobs, int njobs, const InflateJob* inf)
+{
+    __shared__ uint32_t tot[2][RP_MAX_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x;
+    if (j >= njobs) return;
+    const UnfilterJob J = jobs[j];
+    if (inf && J.inflate_idx >= 0) {
+        const InflateJob& ij = inf[J.inflate_idx];
+        if (ij.status != INF_OK || ij.out_len < J.need_len) return;     // reported by the general kernel
+    }
+    const uint32_t rb = J.row_bytes, H = J.height, npx = rb >> 2;
+    const bool eligible = J.bpp == 4 && (rb & 3) == 0 && rb >= 4 && (J.out_pitch & 3) == 0 && (((uintptr_t)J.out) & 3) == 0 &&
+                          (J.inflate_idx >= 0 || (((uintptr_t)J.raw) & 15) == 0) && (npx + 127) / 128 <= blockDim.x / 32;
+    if (!eligible) return;
+    int wave = 0;
+    for (uint32_t r = threadIdx.x; r < H; r += blockDim.x) wave |= J.raw[(size_t)r * (rb + 1)] > 2;
+    if (__syncthreads_or(wave)) return;                     // has Avg/Paeth (or an invalid filter): general kernel
+    const uint32_t px = (uint32_t)warp * 128 + lane * 4;
+    const bool have = (uint32_t)warp * 128 < npx;           // warp-uniform: this warp owns a column block
+    const uint32_t pxl = px < npx ? px : 0;                 // clamped for loads
+    const bool out16 = ((J.out_pitch & 15) == 0) && ((((uintptr_t)J.out) & 15) == 0);
+    const uint8_t* rp = J.raw + 1 + (size_t)pxl * 4;
+    uint8_t* o = J.out + (size_t)px * 4;
+    uint32_t up0 = 0, up1 = 0, up2 = 0, up3 = 0;
+    int nsub = 0;
+    for (uint32_t y0 = 0; y0 < H; y0 += 4) {
+        uint4 A[4], B[4]; int F[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint8_t* q = rp + (size_t)min(y0 + u, H - 1) * (rb + 1);
+            const uint4* v = (const uint4*)(q - ((uintptr_t)q & 15));
+            A[u] = __ldg(v); B[u] = __ldg(v + 1);
+            F[u] = J.raw[(size_t)min(y0 + u, H - 1) * (rb + 1)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t y = y0 + u;
+            if (y >= H) break;                              // uniform
+            const uint8_t* q = rp + (size_t)y * (rb + 1);
+            const uint32_t m = (uint32_t)(uintptr_t)q & 15u, shb = (m & 3u) * 8u;
+            uint32_t w0, w1, w2, w3, w4;
+            switch (m >> 2) {
+            case 0: w0 = A[u].x; w1 = A[u].y; w2 = A[u].z; w3 = A[u].w; w4 = B[u].x; break;
+            case 1: w0 = A[u].y; w1 = A[u].z; w2 = A[u].w; w3 = B[u].x; w4 = B[u].y; break;
+            case 2: w0 = A[u].z; w1 = A[u].w; w2 = B[u].x; w3 = B[u].y; w4 = B[u].z; break;
+            default: w0 = A[u].w; w1 = B[u].x; w2 = B[u].y; w3 = B[u].z; w4 = B[u].w; break;
+            }
+            uint32_t v0 = __funnelshift_r(w0, w1, shb), v1 = __funnelshift_r(w1, w2, shb);
+            uint32_t v2 = __funnelshift_r(w2, w3, shb), v3 = __funnelshift_r(w3, w4, shb);
+            if (px >= npx) v0 = 0; if (px + 1 >= npx) v1 = 0; if (px + 2 >= npx) v2 = 0; if (px + 3 >= npx) v3 = 0;
+            if (F[u] == 1) {                                // Sub: CTA-wide prefix sum of the filtered row
+                v1 = __vadd4(v1, v0); v2 = __vadd4(v2, v1); v3 = __vadd4(v3, v2);
+                uint32_t inc = v3;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = __vadd4(inc, n); }
+                uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+                if (lane == 0) ex = 0;
+                uint32_t* t = tot[nsub & 1];
+                if (lane == 31) t[warp] = inc;
+                __syncthreads();
+                uint32_t c = 0;
+                for (int b = 0; b < warp; ++b) c = __vadd4(c, t[b]);
+                ex = __vadd4(ex, c);
+                v0 = __vadd4(v0, ex); v1 = __vadd4(v1, ex); v2 = __vadd4(v2, ex); v3 = __vadd4(v3, ex);
+                ++nsub;
+            } else if (F[u] == 2) {
+                v0 = __vadd4(v0, up0); v1 = __vadd4(v1, up1); v2 = __vadd4(v2, up2); v3 = __vadd4(v3, up3);
+            }
+            up0 = v0; up1 = v1; up2 = v2; up3 = v3;
+            if (have) {
+                uint32_t* op = (uint32_t*)(o + (size_t)y * J.out_pitch);
+                if (px + 3 < npx && out16) __stcs((uint4*)op, make_uint4(v0, v1, v2, v3));
+                else { if (px < npx) op[0] = v0; if (px + 1 < npx) op[1] = v1; if (px + 2 < npx) op[2] = v2; if (px + 3 < npx) op[3] = v3; }
+            }
+        }
+    }
+}
+
 // Two launches per batch: <true> handles the images whose rows are all None/Sub/Up (row-parallel mode only,
 // no shared-memory rings => 2x the resident warps), <false> handles every other image. Each CTA classifies its
 // image by scanning the filter bytes first.
 template <bool ROWPAR_ONLY>
 __global__ void __launch_bounds__(U4_NW * 32, ROWPAR_ONLY ? 6 : 2)
-unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf)
+unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf, int rowpar_warps)
 {
     extern __shared__ __align__(16) uint8_t u4_smem[];
     __shared__ volatile int flushed[U4_NW];
@@ -389,7 +476,7 @@ unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJo
         int wave = 0;
         for (uint32_t r = threadIdx.x; r < J.height; r += U4_NW * 32) wave |= J.raw[(size_t)r * (J.row_bytes + 1)] > 2;
         wave = __syncthreads_or(wave);
-        if (ROWPAR_ONLY == (wave != 0)) return;            // the other launch owns this image
+        if (ROWPAR_ONLY == (wave != 0) && ((int)((J.row_bytes / 4 + 127) / 128) <= rowpar_warps)) return;   // the other launch owns this image
         if (threadIdx.x < U4_NW) flushed[threadIdx.x] = 0;
         __syncthreads();
         unfilter4_cta(J, status, ROWPAR_ONLY ? nullptr : (U4Smem*)u4_smem + warp, flushed, warp, lane);
@@ -405,14 +492,17 @@ unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJo
     default: unfilter_warp<8>(J, status, lane); break;
     }
 }
-void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st)
+void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st,
+                     int rowpar_threads)
 {
     if (njobs <= 0) return;
+    if (rowpar_threads < 32) rowpar_threads = 32;
+    if (rowpar_threads > RP_MAX_WARPS * 32) rowpar_threads = RP_MAX_WARPS * 32;
     static bool attr_set = false;
     const int smem = (int)sizeof(U4Smem) * U4_NW;
     if (!attr_set) { cudaFuncSetAttribute(unfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    unfilter_kernel<true><<<njobs, U4_NW * 32, 0, st>>>(d_jobs, njobs, d_status, d_inf);
-    unfilter_kernel<false><<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf);
+    unfilter_rowpar_kernel<<<njobs, rowpar_threads, 0, st>>>(d_jobs, njobs, d_inf);
+    unfilter_kernel<false><<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf, rowpar_threads / 32);
     count_launch(2);
 }
 

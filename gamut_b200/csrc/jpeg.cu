@@ -148,6 +148,8 @@ jpeg_huffman_kernel(const JpegImage* __restrict__ images, const Segment* __restr
     }
 }
 
+#include "jpeg_sync.cuh"
+
 // ---- IDCT -------------------------------------------------------------------------------------
 #define CONST_BITS 13
 #define PASS1_BITS 2
@@ -743,6 +745,31 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
                 if (bad) host_fail[k] = 1;
             }
         }
+        // entropy segments long enough to be worth cutting into chunks go to the self-synchronising decoder
+        std::vector<LongSeg> longsegs;
+        uint32_t total_chunks = 0; size_t clean_total = 0;
+        {
+            std::vector<Segment> shortsegs;
+            for (const Segment& sg : segs) {
+                const uint32_t len = sg.end - sg.start;
+                if (len < JS_LONG_MIN || host_fail[sg.image]) { shortsegs.push_back(sg); continue; }
+                LongSeg L;
+                L.image = sg.image; L.in_start = sg.start; L.in_end = sg.end; L.first_mcu = sg.first_mcu; L.num_mcus = sg.num_mcus;
+                L.chunk_base = total_chunks; L.nchunks = (len + JS_CHUNK_BYTES - 1) / JS_CHUNK_BYTES;
+                L.clean_off = clean_total;
+                total_chunks += L.nchunks; clean_total += al((size_t)len + 64, 16);
+                longsegs.push_back(L);
+            }
+            segs.swap(shortsegs);
+        }
+        const int nlong = (int)longsegs.size();
+        DevBuf d_long(sizeof(LongSeg) * ((size_t)nlong + 1)), d_clean(clean_total + 256), d_clen(4 * ((size_t)nlong + 1)),
+               d_exit(sizeof(ChunkState) * ((size_t)total_chunks + 1)), d_nblk(4 * ((size_t)total_chunks + 1)),
+               d_blkbase(4 * ((size_t)total_chunks + 1)), d_dirty(2 * al(total_chunks) + 256),
+               d_dc(sizeof(int) * 6 * ((size_t)total_chunks + 1)), d_changed(256);
+        if (!d_long.p || !d_clean.p || !d_clen.p || !d_exit.p || !d_nblk.p || !d_blkbase.p || !d_dirty.p || !d_dc.p || !d_changed.p) {
+            if (h_stage) pinned_free(h_stage); delete B; return nullptr;
+        }
         DevBuf d_imgs(sizeof(JpegImage) * (size_t)m), d_segs(sizeof(Segment) * (segs.size() + 1)),
                d_tables(sizeof(HuffTable) * (tables.size() + 1)), d_base(sizeof(int) * ((size_t)m + 1));
         if (!d_imgs.p || !d_segs.p || !d_tables.p || !d_base.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
@@ -754,7 +781,8 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         cudaEventRecord(ev[0], st);
         if (!files_dev) okc &= cuda_ok(cudaMemcpyAsync(d_files.p, h_stage, file_total, cudaMemcpyHostToDevice, st), "files", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_imgs.p, imgs.data(), sizeof(JpegImage) * m, cudaMemcpyHostToDevice, st), "imgs", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
+        if (!segs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
+        if (nlong) okc &= cuda_ok(cudaMemcpyAsync(d_long.p, longsegs.data(), sizeof(LongSeg) * nlong, cudaMemcpyHostToDevice, st), "longsegs", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_tables.p, tables.data(), sizeof(HuffTable) * tables.size(), cudaMemcpyHostToDevice, st), "tables", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_base.p, block_base.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, st), "base", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
@@ -762,8 +790,37 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         okc &= cuda_ok(cudaMemsetAsync(d_scratch.p, 0, scratch, st), "memset", __FILE__, __LINE__);
         cudaEventRecord(ev[1], st);
         const int nsegs = (int)segs.size();
-        jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>());
-        count_launch();
+        if (nsegs) {
+            jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>());
+            count_launch();
+        }
+        if (nlong) {
+            // long entropy segments: chunk-parallel self-synchronising decode (jpeg_sync.cuh)
+            const JpegImage* dI = d_imgs.as<JpegImage>(); const LongSeg* dL = d_long.as<LongSeg>(); const HuffTable* dT = d_tables.as<HuffTable>();
+            uint8_t* clean = d_clean.as<uint8_t>(); uint32_t* clen = d_clen.as<uint32_t>();
+            ChunkState* exitst = d_exit.as<ChunkState>(); uint32_t* nblk = d_nblk.as<uint32_t>(); uint32_t* blkbase = d_blkbase.as<uint32_t>();
+            uint8_t* dirty[2] = {d_dirty.as<uint8_t>(), d_dirty.as<uint8_t>() + al(total_chunks)};
+            int* dcsum = d_dc.as<int>(); int* dcbase = dcsum + (size_t)total_chunks * 3;
+            uint32_t* changed = d_changed.as<uint32_t>();
+            const unsigned cg = (total_chunks + 127) / 128;
+            jpeg_unstuff_kernel<<<nlong, 256, 0, st>>>(dI, dL, clean, clen);
+            jpeg_sync_kernel<<<cg, 128, 0, st>>>(dI, dL, nlong, total_chunks, clean, clen, dT, exitst, nblk, dirty[1], dirty[0], 0, changed);
+            count_launch(2);
+            for (int pass = 1;; ++pass) {
+                uint32_t h_changed = 0;
+                okc &= cuda_ok(cudaMemsetAsync(changed, 0, 4, st), "changed", __FILE__, __LINE__);
+                jpeg_sync_kernel<<<cg, 128, 0, st>>>(dI, dL, nlong, total_chunks, clean, clen, dT, exitst, nblk, dirty[(pass + 1) & 1], dirty[pass & 1], pass, changed);
+                count_launch();
+                okc &= cuda_ok(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, st), "changed back", __FILE__, __LINE__);
+                okc &= cuda_ok(cudaStreamSynchronize(st), "sync pass", __FILE__, __LINE__);
+                if (!okc || h_changed == 0) break;
+            }
+            jpeg_scan_kernel<<<nlong, 256, 0, st>>>(dL, nblk, blkbase);
+            jpeg_write_kernel<<<cg, 128, 0, st>>>(dI, dL, nlong, total_chunks, clean, clen, dT, exitst, blkbase, dcsum, d_status.as<int>());
+            jpeg_scan3_kernel<<<nlong, 256, 0, st>>>(dL, dcsum, dcbase);
+            jpeg_dcfix_kernel<<<cg, 128, 0, st>>>(dI, dL, nlong, total_chunks, exitst, blkbase, nblk, dcbase);
+            count_launch(4);
+        }
         cudaEventRecord(ev[2], st);
         const long long total_blocks = block_base[m];
         jpeg_idct_kernel<<<(unsigned)((total_blocks + 127) / 128), 128, 0, st>>>(d_imgs.as<JpegImage>(), d_base.as<int>(), m, total_blocks, d_status.as<int>());

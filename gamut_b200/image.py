@@ -1,0 +1,394 @@
+"""Host-side mirror of gamut.Image for the decode/convert hot path (source/gamut/image.d).
+
+Only the decision logic lives here -- which codec is called with which arguments, which PixelType the
+buffer is adopted as, which conversion runs and into which layout. Every byte of pixel work is done by
+the CUDA library through the C ABI (include/gamut_b200.h). Names and semantics follow the reference:
+
+    Image.loadFromMemory   image.d:886-901  -> identifyFormatFromMemory (image.d:1037-1061)
+                                            -> loadPNG / loadJPEG / loadQOI / loadQOIX
+                                               (plugins/png.d:44-163, jpeg.d:42-104, qoi.d:48-140, qoix.d:64-146)
+    Image.convertTo        image.d:1180-1332 (getAdHocLayoutConstraints :1809-1905,
+                                              allocatePixelStorage internals/types.d:355-540)
+    applyLoadFlags / computeRequestedImageComponents / validLoadFlags   internals/types.d:563-661
+    convertPixelTypeTo*    types.d:351-602
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import codecs
+from .scanline import scanlinesConvert
+from .types import *  # noqa: F401,F403
+from .types import (PixelType, ImageFormat, pixelTypeSize, LOAD_GREYSCALE, LOAD_ALPHA, LOAD_NO_ALPHA, LOAD_RGB,
+                    LOAD_8BIT, LOAD_16BIT, LOAD_FP32, LOAD_PREMUL, LOAD_NO_PREMUL, LAYOUT_GAPLESS,
+                    LAYOUT_VERT_FLIPPED, LAYOUT_VERT_STRAIGHT, GAMUT_MAX_IMAGE_WIDTH, GAMUT_MAX_IMAGE_HEIGHT,
+                    GAMUT_UNKNOWN_ASPECT_RATIO, GAMUT_UNKNOWN_RESOLUTION)
+
+# internals/errors.d
+kStrImageDecodingFailed = "Image decoding failed"
+kStrImageFormatUnidentified = "Unidentified image format"
+kStrImageFormatNoLoadSupport = "Cannot decode this image format in this build"
+kStrImageTooLarge = "Can't have an image that exceeds Gamut size limitations"
+kStrImageWrongComponents = "Invalid number of component for image"
+kStrInvalidFlags = "Invalid image decoding flags"
+kStrOutOfMemory = "Out of memory"
+kStrUnsupportedTypeConversion = "Unsupported image pixel type conversion"
+kStrImageNotInitialized = "Uninitialized image"
+
+GAMUT_MAX_IMAGE_BYTES = 0x7FFFFFFF  # internals/types.d: a gamut image allocation is bounded by int.max
+LAYOUT_BORDER_MASK = 384
+
+# ---- PixelType algebra (types.d:351-602). Types are laid out as 3 depths x 6 colour models. ----
+_P = PixelType
+
+
+def _model(t):   # 0 l, 1 la, 2 lap, 3 rgb, 4 rgba, 5 rgbap
+    return int(t) // 3
+
+
+def _depth(t):   # 0 8-bit, 1 16-bit, 2 fp32
+    return int(t) % 3
+
+
+def _mk(model, depth):
+    return _P(model * 3 + depth)
+
+
+def _map_model(t, table):
+    if int(t) < 0:
+        return _P.unknown
+    return _mk(table[_model(t)], _depth(t))
+
+
+def convertPixelTypeToGreyscale(t): return _map_model(t, (0, 1, 2, 0, 1, 2))          # types.d:351
+def convertPixelTypeToRGB(t): return _map_model(t, (3, 4, 5, 3, 4, 5))                # types.d:379
+def convertPixelTypeToAddAlphaChannel(t): return _map_model(t, (1, 1, 2, 4, 4, 5))    # types.d:407
+def convertPixelTypeToDropAlphaChannel(t): return _map_model(t, (0, 0, 0, 3, 3, 3))   # types.d:435
+def convertPixelTypeToPremul(t): return _map_model(t, (0, 2, 2, 3, 5, 5))             # types.d:463
+def convertPixelTypeToNoPremul(t): return _map_model(t, (0, 1, 1, 3, 4, 4))           # types.d:491
+def convertPixelTypeTo8Bit(t): return _P.unknown if int(t) < 0 else _mk(_model(t), 0)   # types.d:519
+def convertPixelTypeTo16Bit(t): return _P.unknown if int(t) < 0 else _mk(_model(t), 1)  # types.d:547
+def convertPixelTypeToFP32(t): return _P.unknown if int(t) < 0 else _mk(_model(t), 2)   # types.d:575
+
+
+def validLoadFlags(flags: int) -> bool:  # internals/types.d:563-578
+    if (flags & LOAD_GREYSCALE) and (flags & LOAD_RGB):
+        return False
+    if (flags & LOAD_ALPHA) and (flags & LOAD_NO_ALPHA):
+        return False
+    if (flags & LOAD_PREMUL) and (flags & LOAD_NO_PREMUL):
+        return False
+    return sum(1 for f in (LOAD_8BIT, LOAD_16BIT, LOAD_FP32) if flags & f) <= 1
+
+
+def computeRequestedImageComponents(flags: int) -> int:  # internals/types.d:588-611
+    if not validLoadFlags(flags):
+        return 0
+    if flags & LOAD_GREYSCALE:
+        if flags & LOAD_ALPHA:
+            return 2
+        if flags & LOAD_NO_ALPHA:
+            return 1
+    elif flags & LOAD_RGB:
+        if flags & LOAD_ALPHA:
+            return 4
+        if flags & LOAD_NO_ALPHA:
+            return 3
+    return -1
+
+
+def applyLoadFlags(t, flags: int):  # internals/types.d:627-661
+    if not validLoadFlags(flags):
+        return _P.unknown
+    for bit, fn in ((LOAD_GREYSCALE, convertPixelTypeToGreyscale), (LOAD_RGB, convertPixelTypeToRGB),
+                    (LOAD_ALPHA, convertPixelTypeToAddAlphaChannel), (LOAD_NO_ALPHA, convertPixelTypeToDropAlphaChannel),
+                    (LOAD_8BIT, convertPixelTypeTo8Bit), (LOAD_16BIT, convertPixelTypeTo16Bit),
+                    (LOAD_FP32, convertPixelTypeToFP32), (LOAD_PREMUL, convertPixelTypeToPremul),
+                    (LOAD_NO_PREMUL, convertPixelTypeToNoPremul)):
+        if flags & bit:
+            t = fn(t)
+    return t
+
+
+# ---- layout constraints (internals/types.d:165-300) ----
+def layoutMultiplicity(c): return 1 << (c & 3)
+def layoutTrailingPixels(c): return (1 << ((c & 0x0C) >> 2)) - 1
+def layoutScanlineAlignment(c): return 1 << ((c >> 4) & 0x0F)
+def layoutBorderWidth(c): return (c >> 7) & 3
+def layoutGapless(c): return (c & LAYOUT_GAPLESS) != 0
+
+
+def layoutConstraintsValid(c: int) -> bool:  # internals/types.d:262-283
+    if (c & LAYOUT_VERT_FLIPPED) and (c & LAYOUT_VERT_STRAIGHT):
+        return False
+    if layoutGapless(c):
+        if layoutMultiplicity(c) > 1 or layoutTrailingPixels(c) > 0 or layoutScanlineAlignment(c) > 1 \
+                or layoutBorderWidth(c) > 0:
+            return False
+    return True
+
+
+def layoutConstraintsCompatible(newer: int, older: int) -> bool:  # internals/types.d:236-259
+    if (newer & LAYOUT_GAPLESS) and not (older & LAYOUT_GAPLESS):
+        return False
+    if (newer & LAYOUT_VERT_FLIPPED) and not (older & LAYOUT_VERT_FLIPPED):
+        return False
+    if (newer & LAYOUT_VERT_STRAIGHT) and not (older & LAYOUT_VERT_STRAIGHT):
+        return False
+    return (layoutMultiplicity(newer) <= layoutMultiplicity(older)
+            and layoutTrailingPixels(newer) <= layoutTrailingPixels(older)
+            and layoutScanlineAlignment(newer) <= layoutScanlineAlignment(older)
+            and layoutBorderWidth(newer) <= layoutBorderWidth(older))
+
+
+def _pointer_alignment(p: int) -> int:  # getPointerAlignment, internals/types.d:201-211
+    for bits, flag in ((127, 112), (63, 96), (31, 80), (15, 64), (7, 48), (3, 32), (1, 16)):
+        if (p & bits) == 0:
+            return flag
+    return 0
+
+
+def imageIsValidSize(layers: int, width: int, height: int) -> bool:  # internals/types.d:150-162
+    if layers < 0 or width < 0 or height < 0:
+        return False
+    return width <= GAMUT_MAX_IMAGE_WIDTH and height <= GAMUT_MAX_IMAGE_HEIGHT
+
+
+def allocatePixelStorage(type_, width, height, constraints, bonusBytes=0):
+    """allocatePixelStorage (internals/types.d:355-540) for one layer. Returns (area, data_offset, pitch) --
+    `area` is the allocation (numpy bytes), `data_offset` the byte offset of the first scanline, `pitch`
+    signed -- or None on failure."""
+    if not imageIsValidSize(1, width, height):
+        return None
+    border = layoutBorderWidth(constraints)
+    rowAlign = layoutScanlineAlignment(constraints)
+    trailing = layoutTrailingPixels(constraints)
+    mult = layoutMultiplicity(constraints)
+    rightPad = (width + border + mult - 1) // mult * mult - (width + border)
+    borderRight = max(border + rightPad, trailing)
+    actualW = border + width + borderRight
+    actualH = border + height + border
+    px = pixelTypeSize(type_)
+    pitch = (px * actualW + rowAlign - 1) // rowAlign * rowAlign
+    need = pitch * actualH + (rowAlign - 1) + bonusBytes
+    if need > GAMUT_MAX_IMAGE_BYTES:
+        return None
+    area = np.empty(max(need, 1), np.uint8)
+    base = area.ctypes.data
+    first = base + bonusBytes + pitch * border + px * border
+    first = (first + rowAlign - 1) // rowAlign * rowAlign
+    off = first - base
+    # applyVFlipConstraintsToScanlinePointers (internals/types.d:303-320): a fresh allocation has pitch > 0
+    if (constraints & LAYOUT_VERT_FLIPPED) and pitch > 0:
+        if height >= 2:
+            off += pitch * (height - 1)
+        pitch = -pitch
+    return area, off, pitch
+
+
+class Image:
+    """The fields and the two hot-path methods of gamut.Image (image.d). `_area` is the owned allocation
+    (numpy bytes), `_offset` the byte offset of the first scanline inside it, `_pitch` is signed."""
+
+    def __init__(self):
+        self._area = None
+        self._offset = 0
+        self._type = PixelType.unknown
+        self._width = 0
+        self._height = 0
+        self._pitch = 0
+        self._layoutConstraints = 0
+        self._pixelAspectRatio = GAMUT_UNKNOWN_ASPECT_RATIO
+        self._resolutionY = GAMUT_UNKNOWN_RESOLUTION
+        self._layerCount = 0
+        self._error = kStrImageNotInitialized
+
+    # -- status (image.d:372-400)
+    def isValid(self): return self._error is None
+    def isError(self): return self._error is not None
+    def errorMessage(self): return self._error or ""
+    def error(self, msg): self._error = msg
+    def hasData(self): return self._area is not None
+    def type(self): return self._type
+    def width(self): return self._width
+    def height(self): return self._height
+    def pitchInBytes(self): return self._pitch
+    def layoutConstraints(self): return self._layoutConstraints
+
+    def scanline(self, y: int) -> np.ndarray:
+        """Bytes of scanline y (image.d scanptr)."""
+        n = self._width * pixelTypeSize(self._type)
+        o = self._offset + y * self._pitch
+        return self._area[o:o + n]
+
+    def pixels(self) -> np.ndarray:
+        """(h, w, channels) copy in the image's component type."""
+        rows = np.stack([self.scanline(y) for y in range(self._height)]) if self._height else np.zeros((0, 0), np.uint8)
+        dt = (np.uint8, np.uint16, np.float32)[int(self._type) % 3]
+        return rows.view(dt).reshape(self._height, self._width, -1)
+
+    # -- identifyFormatFromMemory (image.d:1037-1061; detect procs plugins/*.d)
+    @staticmethod
+    def identifyFormatFromMemory(data: bytes) -> ImageFormat:
+        if data[:2] == b"\xff\xd8":
+            return ImageFormat.JPEG
+        if data[:8] == b"\x89PNG\r\n\x1a\n":
+            return ImageFormat.PNG
+        if data[:4] == b"qoif":
+            return ImageFormat.QOI
+        if data[:4] == b"qoix":
+            return ImageFormat.QOIX
+        return ImageFormat.unknown
+
+    def _adopt(self, px: np.ndarray, type_, pitch: int, layout: int, par: float, resY: float):
+        a = np.ascontiguousarray(px).view(np.uint8).reshape(-1)
+        self._area, self._offset = a, 0
+        self._height, self._width = px.shape[0], px.shape[1]
+        self._type, self._pitch = PixelType(type_), pitch
+        self._layoutConstraints = layout
+        self._pixelAspectRatio, self._resolutionY = par, resY
+        self._layerCount = 1
+
+    def loadFromMemory(self, data: bytes, flags: int = 0) -> bool:
+        """image.d:886-901 + loadFromStreamInternal (:1751-1772)."""
+        self.__init__()
+        self._error = None
+        fif = self.identifyFormatFromMemory(data)
+        if fif == ImageFormat.unknown:
+            self.error(kStrImageFormatUnidentified)
+            return False
+        {ImageFormat.PNG: self._loadPNG, ImageFormat.JPEG: self._loadJPEG, ImageFormat.QOI: self._loadQOI,
+         ImageFormat.QOIX: self._loadQOIX}[fif](data, flags)
+        return self.isValid()
+
+    def _loadPNG(self, data, flags):  # plugins/png.d:44-163
+        is16 = codecs.png_is16(data)
+        req = computeRequestedImageComponents(flags)
+        if req == 0:
+            return self.error(kStrInvalidFlags)
+        if req == -1:
+            req = 0
+        to16 = is16
+        if flags & LOAD_8BIT:
+            to16 = False
+        if flags & LOAD_16BIT:
+            to16 = True
+        r = codecs.png_load(data, req, to16)
+        if r is None:
+            return self.error(kStrImageDecodingFailed)
+        comps = req if req else r.file_channels
+        if not imageIsValidSize(1, r.width, r.height):
+            return self.error(kStrImageTooLarge)
+        t = (None, _P.l8, _P.la8, _P.rgb8, _P.rgba8)[comps] if not to16 else (None, _P.l16, _P.la16, _P.rgb16, _P.rgba16)[comps]
+        par = GAMUT_UNKNOWN_ASPECT_RATIO if r.pixelRatio == -1 else r.pixelRatio
+        resY = GAMUT_UNKNOWN_RESOLUTION if r.ppmY == -1 else float(np.float32(r.ppmY) / np.float32(39.37007874))  # convertInchesToMeters, types.d:127
+        self._adopt(r.pixels, t, r.width * comps * (2 if to16 else 1), 0, par, resY)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
+
+    def _loadJPEG(self, data, flags):  # plugins/jpeg.d:42-104
+        req = computeRequestedImageComponents(flags)
+        if req == 0:
+            return self.error(kStrInvalidFlags)
+        if req == 2:
+            req = -1
+        r = codecs.jpeg_load(data, req)
+        if r is None:
+            return self.error(kStrImageDecodingFailed)
+        if r.actual_comps not in (1, 3, 4):
+            return self.error(kStrImageWrongComponents)
+        if not imageIsValidSize(1, r.width, r.height):
+            return self.error(kStrImageTooLarge)
+        comps = r.actual_comps if req == -1 else req
+        t = {1: _P.l8, 3: _P.rgb8, 4: _P.rgba8}[comps]
+        par = GAMUT_UNKNOWN_ASPECT_RATIO if r.pixelAspectRatio == -1 else r.pixelAspectRatio
+        resY = GAMUT_UNKNOWN_RESOLUTION if r.dotsPerInchY == -1 else r.dotsPerInchY
+        self._adopt(r.pixels, t, r.width * comps, 0, par, resY)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
+
+    def _loadQOI(self, data, flags):  # plugins/qoi.d:48-140
+        req = computeRequestedImageComponents(flags)
+        if req == 0:
+            return self.error(kStrInvalidFlags)
+        if req in (-1, 1, 2):
+            req = 0
+        r = codecs.qoi_decode(data, req)
+        if r is None:
+            return self.error(kStrImageDecodingFailed)
+        px, desc = r
+        if not imageIsValidSize(1, desc.width, desc.height):
+            return self.error(kStrImageTooLarge)
+        comps = desc.channels if req == 0 else req
+        t = {3: _P.rgb8, 4: _P.rgba8}[comps]
+        # the reference sets _pitch = desc.channels * width (plugins/qoi.d:131), which equals the buffer's
+        # real pitch only when the requested channel count equals the file's; the buffer itself is gapless
+        self._adopt(px, t, comps * desc.width, 0, GAMUT_UNKNOWN_ASPECT_RATIO, GAMUT_UNKNOWN_RESOLUTION)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
+
+    def _loadQOIX(self, data, flags):  # plugins/qoix.d:64-146
+        req = computeRequestedImageComponents(flags)
+        if req == 0:
+            return self.error(kStrInvalidFlags)
+        r = codecs.qoix_decode(data, flags)
+        if r is None:
+            return self.error(kStrImageDecodingFailed)
+        px, desc, t = r
+        if not imageIsValidSize(1, desc.width, desc.height):
+            return self.error(kStrImageTooLarge)
+        self._adopt(px, t, desc.pitchBytes, 0, desc.pixelAspectRatio, desc.resolutionY)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
+
+    # -- getAdHocLayoutConstraints (image.d:1809-1905)
+    def getAdHocLayoutConstraints(self) -> int:
+        pitch = self._pitch
+        absPitch = abs(pitch)
+        px = pixelTypeSize(self._type)
+        excess = (absPitch - self._width * px) // px
+        c = 0
+        multi = layoutMultiplicity(self._layoutConstraints)
+        gap = 8 if excess >= 7 else 4 if excess >= 3 else 2 if excess >= 1 else 1
+        wdiv = 8 if self._width % 8 == 0 else 4 if self._width % 4 == 0 else 2 if self._width % 2 == 0 else 1
+        multi = max(multi, gap, wdiv)
+        c |= {1: 0, 2: 1, 4: 2, 8: 3}[multi]
+        c |= 12 if excess >= 7 else 8 if excess >= 3 else 4 if excess >= 1 else 0
+        c |= min(_pointer_alignment(self._area.ctypes.data + self._offset), _pointer_alignment(absPitch))
+        if pitch >= 0:
+            c |= LAYOUT_VERT_STRAIGHT
+        if pitch <= 0:
+            c |= LAYOUT_VERT_FLIPPED
+        if pitch == absPitch:            # sic: the reference infers "gapless" from the sign of the pitch (image.d:1886)
+            c |= LAYOUT_GAPLESS
+        c |= self._layoutConstraints & LAYOUT_BORDER_MASK
+        return c
+
+    def convertTo(self, targetType, layoutConstraints: int = 0) -> bool:
+        """image.d:1180-1332. The scanline conversion itself is gb200_scanlines_convert (CUDA)."""
+        if int(targetType) == PixelType.unknown:
+            self.error(kStrUnsupportedTypeConversion)
+            return False
+        assert layoutConstraintsValid(layoutConstraints)
+        if not self.hasData():
+            self._type = PixelType(targetType)
+            self._layoutConstraints = layoutConstraints
+            return True
+        compatible = layoutConstraintsCompatible(layoutConstraints, self.getAdHocLayoutConstraints())
+        if self._type == targetType and compatible:
+            self._layoutConstraints = layoutConstraints
+            return True
+        if (self._width == 0 or self._height == 0) and compatible:
+            self._layoutConstraints = layoutConstraints
+            return True
+        st = allocatePixelStorage(targetType, self._width, self._height, layoutConstraints)
+        if st is None:
+            self.error(kStrOutOfMemory)
+            return False
+        area, off, pitch = st
+        ok = scanlinesConvert(self._type, self._area, self._pitch, targetType, area, pitch, self._width, self._height,
+                              src_offset=self._offset, dest_offset=off)
+        if not ok:
+            self.error(kStrUnsupportedTypeConversion)
+            return False
+        self._area, self._offset, self._pitch = area, off, pitch
+        self._type = PixelType(targetType)
+        self._layoutConstraints = layoutConstraints
+        self._error = None
+        return True

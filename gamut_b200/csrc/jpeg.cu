@@ -378,6 +378,225 @@ jpeg_colour_kernel(const JpegImage* __restrict__ images, const int* __restrict__
     }
 }
 
+// ---- fused IDCT + chroma upsampling + colour conversion -----------------------------------------
+// One CTA converts a run of consecutive MCUs of one MCU row: 8-thread groups run the two IDCT passes of a
+// block (thread = row, then thread = column, transposing through shared memory), sample tiles stay in shared
+// memory in the reference's m_pSample_buf tile order, and the colour pass writes whole output rows of the run
+// with 16-byte stores. Coefficients are read once (16 B per thread, 128 B per group) and pixels written once.
+constexpr int IC_THREADS = 256, IC_GROUPS = 32, IC_GSTRIDE = 264, IC_MAX_TILES = 192;
+
+__device__ __forceinline__ void unpack8(const int4 v, int in[8])
+{
+    in[0] = (int16_t)(v.x & 0xffff); in[1] = v.x >> 16; in[2] = (int16_t)(v.y & 0xffff); in[3] = v.y >> 16;
+    in[4] = (int16_t)(v.z & 0xffff); in[5] = v.z >> 16; in[6] = (int16_t)(v.w & 0xffff); in[7] = v.w >> 16;
+}
+
+__device__ __forceinline__ void ycc_to_rgb(int Y, int cb, int cr, int& r, int& g, int& b)
+{
+    // FIX!(x) = (int)(x * 65536 + 0.5f) (jpegload.d:2082)
+    const int F140200 = 91881, F177200 = 116130, F071414 = 46802, F034414 = 22554;
+    r = clamp255(Y + ((F140200 * (cr - 128) + 32768) >> 16));
+    g = clamp255(Y + (((-F071414) * (cr - 128) + (-F034414) * (cb - 128) + 32768) >> 16));
+    b = clamp255(Y + ((F177200 * (cb - 128) + 32768) >> 16));
+}
+
+__global__ void __launch_bounds__(IC_THREADS)
+jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __restrict__ cta_base, int nimages,
+                        const int* __restrict__ status)
+{
+    __shared__ __align__(16) uint8_t s_tiles[IC_MAX_TILES * 64];
+    __shared__ __align__(16) int s_tmp[IC_GROUPS * IC_GSTRIDE];
+    int lo = 0, hi = nimages - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cta_base[mid] <= blockIdx.x) lo = mid; else hi = mid - 1; }
+    if (!status[lo]) return;
+    const JpegImage& im = images[lo];
+    const int st = im.scan_type;
+    const int NM = st == YH2V2 ? 16 : 32;
+    const int gpr = (im.mcus_per_row + NM - 1) / NM;
+    const int local = (int)(blockIdx.x - cta_base[lo]);
+    const int mrow = local / gpr, g0 = (local - mrow * gpr) * NM;
+    const int nm = min(NM, im.mcus_per_row - g0);
+    const int bpm = im.blocks_per_mcu, tpm = im.tiles_per_mcu;
+    const int16_t* __restrict__ coefs = im.coefs + ((size_t)mrow * im.mcus_per_row + g0) * bpm * 64;
+    const int tid = threadIdx.x, grp = tid >> 3, t = tid & 7;
+    int* tmp = s_tmp + grp * IC_GSTRIDE;
+
+    // ---- stage 1a: plain 8x8 IDCT (every block except 4:2:0 chroma)
+    const int npm = st == YH2V2 ? 4 : bpm;
+    const int nplain = nm * npm;
+    for (int base = 0; base < nplain; base += IC_GROUPS) {
+        const int task = base + grp;
+        const bool active = task < nplain;
+        int m = 0, bi = 0;
+        if (active) {
+            m = task / npm; bi = task - m * npm;
+            int in[8], out[8];
+            unpack8(__ldg((const int4*)(coefs + ((size_t)m * bpm + bi) * 64) + t), in);
+            idct8<false>(in, out);
+            *(int4*)(tmp + t * 8) = make_int4(out[0], out[1], out[2], out[3]);
+            *(int4*)(tmp + t * 8 + 4) = make_int4(out[4], out[5], out[6], out[7]);
+        }
+        __syncwarp();
+        if (active) {
+            int in[8], out[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) in[r] = tmp[r * 8 + t];
+            idct8<true>(in, out);
+            uint8_t* dst = s_tiles + (m * tpm + bi) * 64;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) dst[r * 8 + t] = (uint8_t)out[r];
+        }
+        __syncwarp();
+    }
+    // ---- stage 1b: 4:2:0 chroma, DCT_Upsample (jpegload.d:827-1073) + idct_4x4 on the four tiles
+    if (st == YH2V2) {
+        const int a1[4] = {426, 810, -360, 284};
+        const int a2[4] = {23, -99, 502, 887};
+        const int b1[4] = {928, -325, 218, -184};
+        const int b2[4] = {-75, 526, 787, -383};
+        const int nup = nm * 2;
+        for (int base = 0; base < nup; base += IC_GROUPS) {
+            const int task = base + grp;
+            const bool active = task < nup;
+            const int m = task >> 1, ch = task & 1;
+            if (active) {   // A: thread j = source row j -> X0[0..3][j], X1[0..3][j]
+                int s[8];
+                unpack8(__ldg((const int4*)(coefs + ((size_t)m * 6 + 4 + ch) * 64) + t), s);
+                tmp[0 * 8 + t] = s[0];
+                tmp[1 * 8 + t] = UD(a1[0] * s[1] + a1[1] * s[3] + a1[2] * s[5] + a1[3] * s[7]);
+                tmp[2 * 8 + t] = s[4];
+                tmp[3 * 8 + t] = UD(a2[0] * s[1] + a2[1] * s[3] + a2[2] * s[5] + a2[3] * s[7]);
+                tmp[32 + 0 * 8 + t] = UD(b1[0] * s[1] + b1[1] * s[3] + b1[2] * s[5] + b1[3] * s[7]);
+                tmp[32 + 1 * 8 + t] = s[2];
+                tmp[32 + 2 * 8 + t] = UD(b2[0] * s[1] + b2[1] * s[3] + b2[2] * s[5] + b2[3] * s[7]);
+                tmp[32 + 3 * 8 + t] = s[6];
+            }
+            __syncwarp();
+            if (active) {   // B: thread (i, which): P,Q rows from X0[i], R,S rows from X1[i]
+                const int i = t & 3, which = t >> 2;
+                const int* x = tmp + which * 32 + i * 8;
+                const int4 xa = *(const int4*)x, xb = *(const int4*)(x + 4);
+                const int x1 = xa.y, x3 = xa.w, x5 = xb.y, x7 = xb.w;
+                int* pq = tmp + 64 + which * 32;     // [P|R][i][c] at +0, [Q|S][i][c] at +16
+                *(int4*)(pq + i * 4) = make_int4(xa.x, UD(x1 * a1[0] + x3 * a1[1] + x5 * a1[2] + x7 * a1[3]),
+                                                 xb.x, UD(x1 * a2[0] + x3 * a2[1] + x5 * a2[2] + x7 * a2[3]));
+                *(int4*)(pq + 16 + i * 4) = make_int4(UD(x1 * b1[0] + x3 * b1[1] + x5 * b1[2] + x7 * b1[3]), xa.z,
+                                                      UD(x1 * b2[0] + x3 * b2[1] + x5 * b2[2] + x7 * b2[3]), xb.z);
+            }
+            __syncwarp();
+            if (active) {   // C: row pass of the four transposed 4x4 tiles (jpegload.d:886-902, :2230-2251)
+                const int tt = t >> 1;
+                const int* Pm = tmp + 64, *Qm = tmp + 80, *Rm = tmp + 96, *Sm = tmp + 112;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int rr = (t & 1) * 2 + q;     // row of the transposed tile = column c of P..S
+                    int in[8], out[8];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {    // column of the transposed tile = row r of P..S
+                        const int idx = cc * 4 + rr;
+                        const int a = Pm[idx] + Qm[idx], b = Pm[idx] - Qm[idx], c = Rm[idx] + Sm[idx], d = Rm[idx] - Sm[idx];
+                        const int v = tt == 0 ? a + c : tt == 1 ? a - c : tt == 2 ? b + d : b - d;
+                        in[cc] = (int)(int16_t)v;
+                    }
+                    in[4] = in[5] = in[6] = in[7] = 0;
+                    idct8<false>(in, out);
+                    *(int4*)(tmp + 128 + tt * 32 + rr * 8) = make_int4(out[0], out[1], out[2], out[3]);
+                    *(int4*)(tmp + 128 + tt * 32 + rr * 8 + 4) = make_int4(out[4], out[5], out[6], out[7]);
+                }
+            }
+            __syncwarp();
+            if (active) {   // D: column pass, thread = column
+                uint8_t* dst = s_tiles + (m * 12 + 4 + ch * 4) * 64;
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) {
+                    int in[8], out[8];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) in[r] = tmp[128 + tt * 32 + r * 8 + t];
+                    in[4] = in[5] = in[6] = in[7] = 0;
+                    idct8<true>(in, out);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) dst[tt * 64 + r * 8 + t] = (uint8_t)out[r];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: colour conversion + channel adaptation (H*Convert :2528-2823, :3763-3801)
+    const int W = im.width, H = im.height, rc = im.req_comps;
+    if (st == YH2V2) {
+        const int row = tid >> 4, m = tid & 15;
+        const int y = mrow * 16 + row, x = (g0 + m) * 16;
+        if (m < nm && y < H && x < W) {
+            const uint8_t* tb = s_tiles + m * 768 + (row >> 3) * 128 + (row & 7) * 8;
+            uint8_t px[64];
+            const int n = min(16, W - x);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint2 y8 = *(const uint2*)(tb + h * 64), cb8 = *(const uint2*)(tb + 256 + h * 64), cr8 = *(const uint2*)(tb + 512 + h * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int Y = ((i < 4 ? y8.x : y8.y) >> ((i & 3) * 8)) & 255;
+                    const int cb = ((i < 4 ? cb8.x : cb8.y) >> ((i & 3) * 8)) & 255;
+                    const int cr = ((i < 4 ? cr8.x : cr8.y) >> ((i & 3) * 8)) & 255;
+                    int r, g, b; ycc_to_rgb(Y, cb, cr, r, g, b);
+                    const int p = h * 8 + i;
+                    if (rc == 1) px[p] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
+                    else if (rc == 3) { px[p * 3] = (uint8_t)r; px[p * 3 + 1] = (uint8_t)g; px[p * 3 + 2] = (uint8_t)b; }
+                    else { px[p * 4] = (uint8_t)r; px[p * 4 + 1] = (uint8_t)g; px[p * 4 + 2] = (uint8_t)b; px[p * 4 + 3] = 255; }
+                }
+            }
+            uint8_t* d = im.out + ((size_t)y * W + x) * rc;
+            if (n == 16 && (((uintptr_t)d) & 15) == 0) {
+#define IC_PACK(o) ((uint32_t)px[o] | ((uint32_t)px[(o) + 1] << 8) | ((uint32_t)px[(o) + 2] << 16) | ((uint32_t)px[(o) + 3] << 24))
+#define IC_ST(q) ((uint4*)d)[q] = make_uint4(IC_PACK((q) * 16), IC_PACK((q) * 16 + 4), IC_PACK((q) * 16 + 8), IC_PACK((q) * 16 + 12))
+                if (rc == 1) { IC_ST(0); }
+                else if (rc == 3) { IC_ST(0); IC_ST(1); IC_ST(2); }
+                else { IC_ST(0); IC_ST(1); IC_ST(2); IC_ST(3); }
+#undef IC_ST
+#undef IC_PACK
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (i < n) {
+                        if (rc == 1) d[i] = px[i];
+                        else if (rc == 3) { d[i * 3] = px[i * 3]; d[i * 3 + 1] = px[i * 3 + 1]; d[i * 3 + 2] = px[i * 3 + 2]; }
+                        else { d[i * 4] = px[i * 4]; d[i * 4 + 1] = px[i * 4 + 1]; d[i * 4 + 2] = px[i * 4 + 2]; d[i * 4 + 3] = 255; }
+                    }
+                }
+            }
+        }
+    } else {
+        const int mw = st == YH2V1 ? 16 : 8, mh = st == YH1V2 ? 16 : 8;
+        const int rw = nm * mw;
+        for (int p = tid; p < rw * mh; p += IC_THREADS) {
+            const int row = p / rw, xx = p - row * rw;
+            const int y = mrow * mh + row, x = g0 * mw + xx;
+            if (y >= H || x >= W) continue;
+            int Y, cb = 128, cr = 128;
+            const uint8_t* tb;
+            switch (st) {
+            case GRAYSCALE: tb = s_tiles + (xx >> 3) * 64; Y = tb[row * 8 + (xx & 7)]; break;
+            case YH1V1: { tb = s_tiles + (xx >> 3) * 192; const int o = row * 8 + (xx & 7); Y = tb[o]; cb = tb[64 + o]; cr = tb[128 + o]; break; }
+            case YH2V1: { tb = s_tiles + (xx >> 4) * 256; const int lx = xx & 15;
+                Y = tb[(lx >> 3) * 64 + row * 8 + (lx & 7)]; cb = tb[128 + row * 8 + (lx >> 1)]; cr = tb[192 + row * 8 + (lx >> 1)]; break; }
+            default: { tb = s_tiles + (xx >> 3) * 256; const int lx = xx & 7;      // YH1V2
+                Y = tb[(row >> 3) * 64 + (row & 7) * 8 + lx]; cb = tb[128 + (row >> 1) * 8 + lx]; cr = tb[192 + (row >> 1) * 8 + lx]; break; }
+            }
+            uint8_t* d = im.out + ((size_t)y * W + x) * rc;
+            if (im.comps == 1) {
+                if (rc == 1) d[0] = (uint8_t)Y;
+                else { d[0] = d[1] = d[2] = (uint8_t)Y; if (rc == 4) d[3] = 255; }
+            } else {
+                int r, g, b; ycc_to_rgb(Y, cb, cr, r, g, b);
+                if (rc == 1) d[0] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
+                else { d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b; if (rc == 4) d[3] = 255; }
+            }
+        }
+    }
+}
+
 // ---- host: marker layer ----------------------------------------------------------------------
 struct ByteSrc {    // get_char semantics: past the end yields FF D9 FF D9 ... (jpegload.d:640-655)
     const uint8_t* p; size_t len, pos; int tem;
@@ -668,14 +887,14 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
     std::vector<int> final_ok((size_t)n, 0);
     while (li < live.size()) {
         size_t scratch = 0, lj = li;
-        std::vector<size_t> coef_off, samp_off, file_off;
+        std::vector<size_t> coef_off, file_off;
         size_t file_total = 0;
         while (lj < live.size()) {
             const Parsed& p = P[live[lj]];
             size_t mcus = (size_t)p.mcus_per_row * p.mcus_per_col;
-            size_t need = al(mcus * p.blocks_per_mcu * 128) + al(mcus * p.tiles_per_mcu * 64);
+            size_t need = al(mcus * p.blocks_per_mcu * 128);
             if (lj > li && scratch + need > SCRATCH_BUDGET) break;
-            coef_off.push_back(scratch); samp_off.push_back(scratch + al(mcus * p.blocks_per_mcu * 128));
+            coef_off.push_back(scratch);
             scratch += need;
             file_off.push_back(file_total); file_total += al(lens[live[lj]] + 16);
             ++lj;
@@ -685,11 +904,10 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         if (!d_scratch.p || !d_files.p || !d_status.p) { delete B; return nullptr; }
         std::vector<JpegImage> imgs((size_t)m);
         std::vector<Segment> segs;
-        std::vector<int> block_base((size_t)m + 1, 0);
+        std::vector<uint32_t> cta_base((size_t)m + 1, 0);     // fused IDCT+colour kernel: CTAs per image (prefix)
         uint8_t* h_stage = nullptr;
         if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
         std::vector<int> host_fail((size_t)m, 0);
-        long long max_pixels = 1;
         for (int k = 0; k < m; ++k) {
             const int i = live[li + k];
             const Parsed& p = P[i];
@@ -714,13 +932,15 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
                 }
             }
             J.coefs = (int16_t*)(d_scratch.as<uint8_t>() + coef_off[k]);
-            J.samples = d_scratch.as<uint8_t>() + samp_off[k];
+            J.samples = nullptr;
             J.out = d_out + out_off[i];
             J.req_comps = req_comps_in < 0 ? p.comps : req_comps_in;
             J.restart_interval = p.restart_interval;
             const int total_mcus = p.mcus_per_row * p.mcus_per_col;
-            block_base[k + 1] = block_base[k] + total_mcus * p.blocks_per_mcu;
-            long long px = (long long)p.width * p.height; if (px > max_pixels) max_pixels = px;
+            {
+                const int NM = p.scan_type == YH2V2 ? 16 : 32;
+                cta_base[k + 1] = cta_base[k] + (uint32_t)((p.mcus_per_row + NM - 1) / NM) * (uint32_t)p.mcus_per_col;
+            }
             // segments: the whole scan, or one per restart interval (process_restart, :2335-2402)
             const uint8_t* f = files[i]; const size_t flen = lens[i];
             if (!p.restart_interval) segs.push_back(Segment{k, (uint32_t)p.scan_start, (uint32_t)flen, 0, total_mcus});
@@ -784,7 +1004,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         if (!segs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
         if (nlong) okc &= cuda_ok(cudaMemcpyAsync(d_long.p, longsegs.data(), sizeof(LongSeg) * nlong, cudaMemcpyHostToDevice, st), "longsegs", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_tables.p, tables.data(), sizeof(HuffTable) * tables.size(), cudaMemcpyHostToDevice, st), "tables", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemcpyAsync(d_base.p, block_base.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, st), "base", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemcpyAsync(d_base.p, cta_base.data(), sizeof(uint32_t) * (m + 1), cudaMemcpyHostToDevice, st), "base", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
         // coefficient blocks start zeroed (the reference zero-fills per block, :2459-2510)
         okc &= cuda_ok(cudaMemsetAsync(d_scratch.p, 0, scratch, st), "memset", __FILE__, __LINE__);
@@ -822,16 +1042,9 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
             count_launch(4);
         }
         cudaEventRecord(ev[2], st);
-        const long long total_blocks = block_base[m];
-        jpeg_idct_kernel<<<(unsigned)((total_blocks + 127) / 128), 128, 0, st>>>(d_imgs.as<JpegImage>(), d_base.as<int>(), m, total_blocks, d_status.as<int>());
-        count_launch();
-        {
-            long long bx = (max_pixels + 255) / 256; if (bx > 148 * 8) bx = 148 * 8;
-            for (int base = 0; base < m; base += 65535) {
-                int ny = std::min(65535, m - base);
-                jpeg_colour_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, st>>>(d_imgs.as<JpegImage>() + base, d_status.as<int>() + base);
-                count_launch();
-            }
+        if (cta_base[m]) {
+            jpeg_idct_colour_kernel<<<cta_base[m], IC_THREADS, 0, st>>>(d_imgs.as<JpegImage>(), d_base.as<uint32_t>(), m, d_status.as<int>());
+            count_launch();
         }
         cudaEventRecord(ev[3], st);
         std::vector<int> status((size_t)m);

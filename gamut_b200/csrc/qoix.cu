@@ -77,74 +77,7 @@ done:
     if (!ok && lane == 0) status[J.image] = 0;
 }
 
-// MSB-first bit reader; reads past the end yield 1-bits (0xFF == END opcode).
-struct BitR {
-    const uint8_t* p; uint32_t size, pos; uint64_t buf; int cnt;
-    __device__ __forceinline__ void init(const uint8_t* d, uint32_t s, uint32_t start) { p = d; size = s; pos = start; buf = 0; cnt = 0; }
-    __device__ __forceinline__ void fill()
-    {
-        while (cnt <= 56) { uint32_t b = pos < size ? p[pos] : 0xFFu; ++pos; buf |= (uint64_t)b << (56 - cnt); cnt += 8; }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
-    __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }
-};
-
-struct PlaneJob { const uint8_t* stream; uint32_t size; uint8_t* out; uint32_t w, h; int channels; int image; };
-
-__device__ __forceinline__ int loco(int left, int top, int topleft)       // qoiplane10.d:84-96
-{
-    const int mx = max(left, top), mn = min(left, top);
-    if (topleft >= mx) return mn;
-    if (topleft <= mn) return mx;
-    return min(max(left + top - topleft, 0), 1023);
-}
-__device__ __forceinline__ int sext(int v, int bits) { return (int)((uint32_t)v << (32 - bits)) >> (32 - bits); }
-
-__global__ void __launch_bounds__(64)
-qoiplane10_kernel(const PlaneJob* __restrict__ jobs, int njobs, const int* __restrict__ status)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
-    const PlaneJob J = jobs[j];
-    if (!status[J.image]) return;
-    BitR r; r.init(J.stream, J.size, QOIX_HEADER_SIZE);
-    const int ch = J.channels;
-    const uint32_t W = J.w, H = J.h;
-    const long long num_pixels = (long long)W * H;
-    long long decoded = 0;
-    int l = 0, a = 1023, run = 0;
-    uint16_t* out = (uint16_t*)J.out;
-    for (uint32_t y = 0; y < H; ++y) {
-        uint16_t* line = out + (size_t)y * W * ch;
-        const uint16_t* above = y ? line - (size_t)W * ch : nullptr;
-        int up_left = 0;    // above[x-1] >> 6, carried to save a load
-        for (uint32_t x = 0; x < W; ++x) {
-            const int ref_l = l, ref_a = a;
-            int up = above ? (above[(size_t)x * ch] >> 6) : 0;
-            if (run > 0) --run;
-            else if (decoded < num_pixels) {
-                const int pred = y == 0 ? ref_l : (x == 0 ? up : loco(ref_l, up, up_left));
-                for (;;) {
-                    r.fill();
-                    const uint32_t op = r.peek(8);
-                    if (op < 0x80) { l = (pred + sext((op >> 4) & 7, 3)) & 1023; r.drop(4); break; }
-                    if (op < 0xc0) { l = (pred + sext(op & 0x3f, 6)) & 1023; r.drop(8); break; }
-                    if (op < 0xe0) { run = (op >> 2) & 7; r.drop(6); if (run == 7) { run = (int)r.peek(8) + 7; r.drop(8); } break; }
-                    if (op < 0xf0) { l = (pred + sext((int)(r.peek(14) & 0x3ff), 10)) & 1023; r.drop(14); break; }
-                    if (op < 0xf8) { l = (pred + sext((int)(r.peek(12) & 0x7f), 7)) & 1023; r.drop(12); break; }
-                    if (op < 0xfc) { a = (ref_a + sext((int)(r.peek(12) & 0x3f), 6)) & 1023; r.drop(12); continue; }
-                    if (op == 0xfe) { const uint32_t v = r.peek(28); l = (v >> 10) & 1023; a = v & 1023; r.drop(28); break; }
-                    return;     // END (0xff) or reserved 0xfc/0xfd: stop; the rest of the output stays zero
-                }
-                ++decoded;
-            }
-            const uint16_t l16 = (uint16_t)((l << 6) | (l >> 4));
-            if (ch == 1) line[x] = l16;
-            else { *(ushort2*)(line + 2 * (size_t)x) = make_ushort2(l16, (uint16_t)((a << 6) | (a >> 4))); }
-            up_left = up;
-        }
-    }
-}
+#include "qoiplane10.cuh"
 
 struct QoiJob { const uint8_t* bytes; uint32_t size; uint8_t* out; uint32_t w, h; int channels; int image; };
 
@@ -277,7 +210,8 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!d_files.p || !d_lz.p || !d_status.p) { delete B; return nullptr; }
     uint8_t* h_stage = nullptr;
     if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
-    std::vector<Lz4Job> lz; std::vector<PlaneJob> pj;
+    std::vector<Lz4Job> lz; std::vector<P10Image> pj;
+    size_t rec_total = 0, row_total = 0; uint32_t total_chunks = 0;
     for (int i : live) {
         const uint8_t* dev = files_dev ? files_dev[i] : d_files.as<uint8_t>() + file_off[i];
         if (!files_dev) memcpy(h_stage + file_off[i], files[i], lens[i]);
@@ -287,9 +221,19 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
             lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, (uint32_t)(lens[i] - QOIX_HEADER_SIZE - 4), dec + QOIX_HEADER_SIZE, P[i].orig, i});
             stream = dec; ssize = QOIX_HEADER_SIZE + P[i].orig;
         }
-        pj.push_back(PlaneJob{stream, ssize, d_out + out_off[i], P[i].w, P[i].h, P[i].channels, i});
+        P10Image J;
+        J.stream = stream; J.size = ssize; J.w = P[i].w; J.h = P[i].h; J.wp = (P[i].w + 7u) & ~7u; J.channels = P[i].channels; J.image = i;
+        J.chunk_base = total_chunks; J.nchunks = std::max(1u, (ssize - QOIX_HEADER_SIZE + P10_CHUNK_BYTES - 1) / P10_CHUNK_BYTES);
+        J.recs = (uint32_t*)rec_total; J.rowinfo = (uint32_t*)row_total;      // offsets, rebased below
+        J.out = d_out + out_off[i];
+        total_chunks += J.nchunks; rec_total += al((size_t)J.wp * J.h * 4); row_total += al((size_t)J.h * 4);
+        pj.push_back(J);
     }
-    DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(PlaneJob) * (pj.size() + 1));
+    DevBuf d_recs(rec_total), d_rows(row_total), d_chunks(sizeof(P10Chunk) * ((size_t)total_chunks + 1)),
+           d_entries(sizeof(P10Entry) * ((size_t)total_chunks + 1)), d_dirty(2 * al(total_chunks) + 256), d_misc(256 + 4 * pj.size());
+    if (!d_recs.p || !d_rows.p || !d_chunks.p || !d_entries.p || !d_dirty.p || !d_misc.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+    for (auto& J : pj) { J.recs = (uint32_t*)(d_recs.as<uint8_t>() + (size_t)J.recs); J.rowinfo = (uint32_t*)(d_rows.as<uint8_t>() + (size_t)J.rowinfo); }
+    DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(P10Image) * (pj.size() + 1));
     if (!d_lzj.p || !d_pj.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
     std::vector<int> ones((size_t)n, 1);
     cudaEvent_t ev[4];
@@ -299,13 +243,34 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!files_dev) okc &= cuda_ok(cudaMemcpyAsync(d_files.p, h_stage, file_total, cudaMemcpyHostToDevice, st), "files", __FILE__, __LINE__);
     okc &= cuda_ok(cudaMemcpyAsync(d_status.p, ones.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
     if (!lz.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_lzj.p, lz.data(), sizeof(Lz4Job) * lz.size(), cudaMemcpyHostToDevice, st), "lz", __FILE__, __LINE__);
-    okc &= cuda_ok(cudaMemcpyAsync(d_pj.p, pj.data(), sizeof(PlaneJob) * pj.size(), cudaMemcpyHostToDevice, st), "pj", __FILE__, __LINE__);
-    okc &= cuda_ok(cudaMemsetAsync(d_out, 0, out_total, st), "memset", __FILE__, __LINE__);   // pixels after END stay zero
+    okc &= cuda_ok(cudaMemcpyAsync(d_pj.p, pj.data(), sizeof(P10Image) * pj.size(), cudaMemcpyHostToDevice, st), "pj", __FILE__, __LINE__);
     cudaEventRecord(ev[1], st);
     if (!lz.empty()) { lz4_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(d_lzj.as<Lz4Job>(), (int)lz.size(), d_status.as<int>()); count_launch(); }
     cudaEventRecord(ev[2], st);
-    qoiplane10_kernel<<<(unsigned)((pj.size() + 63) / 64), 64, 0, st>>>(d_pj.as<PlaneJob>(), (int)pj.size(), d_status.as<int>());
-    count_launch();
+    {
+        // QOI-Plane10: chunk-parallel parse (self-synchronising), scan, per-pixel records, wavefront reconstruction
+        const P10Image* dI = d_pj.as<P10Image>(); const int ni = (int)pj.size();
+        P10Chunk* chunks = d_chunks.as<P10Chunk>(); P10Entry* entries = d_entries.as<P10Entry>();
+        uint8_t* dirty[2] = {d_dirty.as<uint8_t>(), d_dirty.as<uint8_t>() + al(total_chunks)};
+        uint32_t* changed = d_misc.as<uint32_t>(); uint32_t* ndec = changed + 64;
+        const unsigned cg = (total_chunks + 127) / 128;
+        p10_sync_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, dirty[1], dirty[0], 0, changed);
+        count_launch();
+        for (int pass = 1;; ++pass) {
+            uint32_t h_changed = 0;
+            okc &= cuda_ok(cudaMemsetAsync(changed, 0, 4, st), "changed", __FILE__, __LINE__);
+            p10_sync_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, dirty[(pass + 1) & 1], dirty[pass & 1], pass, changed);
+            count_launch();
+            okc &= cuda_ok(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, st), "changed back", __FILE__, __LINE__);
+            okc &= cuda_ok(cudaStreamSynchronize(st), "sync pass", __FILE__, __LINE__);
+            if (!okc || h_changed == 0) break;
+        }
+        p10_scan_kernel<<<ni, 256, 0, st>>>(dI, chunks, entries, ndec);
+        p10_write_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, entries);
+        p10_recon_kernel<1><<<ni, 32, 0, st>>>(dI, ndec, d_status.as<int>());
+        p10_recon_kernel<2><<<ni, 32, 0, st>>>(dI, ndec, d_status.as<int>());
+        count_launch(4);
+    }
     cudaEventRecord(ev[3], st);
     std::vector<int> status((size_t)n);
     okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);

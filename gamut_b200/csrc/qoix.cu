@@ -78,6 +78,7 @@ done:
 }
 
 #include "qoiplane10.cuh"
+#include "qoix_sub.cuh"
 
 struct QoiJob { const uint8_t* bytes; uint32_t size; uint8_t* out; uint32_t w, h; int channels; int image; };
 
@@ -170,7 +171,19 @@ bool plan_qoix(const uint8_t* d, size_t size, int flags, QoixPlan& P)
         if (payload < (size_t)QOIX_HEADER_SIZE + 5) return false;
         if (P.colorspace > 1 || P.version != 2) return false;      // qoiplane10.d:341-343 (premul streams are rejected)
         P.out_bytes = (size_t)P.w * P.h * P.channels * 2;
-    } else return false;     // remaining sub-codecs: see DESIGN.md (not built in this round)
+    } else if (P.codec == 1) {   // qoi10b.d:510-541
+        if (payload < (size_t)QOIX_HEADER_SIZE + 5) return false;
+        if (P.colorspace > 2 || P.version > 2) return false;
+        P.out_bytes = (size_t)P.w * P.h * P.channels * 2;
+    } else if (P.codec == 2) {   // qoiplane.d:379-411
+        if (payload < (size_t)QOIX_HEADER_SIZE + 4) return false;
+        if (P.colorspace > 1 || P.version > 1) return false;
+        P.out_bytes = (size_t)P.w * P.h * P.channels;
+    } else {                     // qoi2avg.d:634-665
+        if (payload < (size_t)QOIX_HEADER_SIZE + 4) return false;
+        if (P.colorspace > 2 || P.version > 1) return false;
+        P.out_bytes = (size_t)P.w * P.h * P.channels;
+    }
     P.ok = true;
     return true;
 }
@@ -212,6 +225,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
     std::vector<Lz4Job> lz; std::vector<P10Image> pj;
     size_t rec_total = 0, row_total = 0; uint32_t total_chunks = 0;
+    std::vector<SubJob> sub[4]; size_t sub_rows_total = 0;
     for (int i : live) {
         const uint8_t* dev = files_dev ? files_dev[i] : d_files.as<uint8_t>() + file_off[i];
         if (!files_dev) memcpy(h_stage + file_off[i], files[i], lens[i]);
@@ -220,6 +234,15 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
             uint8_t* dec = d_lz.as<uint8_t>() + lz_off[i];
             lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, (uint32_t)(lens[i] - QOIX_HEADER_SIZE - 4), dec + QOIX_HEADER_SIZE, P[i].orig, i});
             stream = dec; ssize = QOIX_HEADER_SIZE + P[i].orig;
+        }
+        if (P[i].codec != 0) {
+            SubJob S;
+            S.stream = stream; S.size = ssize; S.out = d_out + out_off[i]; S.w = P[i].w; S.h = P[i].h;
+            S.channels = P[i].channels; S.version = P[i].version; S.image = i;
+            S.rows = (uint8_t*)sub_rows_total;                     // offset, rebased below
+            sub_rows_total += al((size_t)P[i].w * 2 * (P[i].codec == 1 ? 8 : 4));
+            sub[P[i].codec].push_back(S);
+            continue;
         }
         P10Image J;
         J.stream = stream; J.size = ssize; J.w = P[i].w; J.h = P[i].h; J.wp = (P[i].w + 7u) & ~7u; J.channels = P[i].channels; J.image = i;
@@ -232,6 +255,11 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     DevBuf d_recs(rec_total), d_rows(row_total), d_chunks(sizeof(P10Chunk) * ((size_t)total_chunks + 1)),
            d_entries(sizeof(P10Entry) * ((size_t)total_chunks + 1)), d_dirty(2 * al(total_chunks) + 256), d_misc(256 + 4 * pj.size());
     if (!d_recs.p || !d_rows.p || !d_chunks.p || !d_entries.p || !d_dirty.p || !d_misc.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+    DevBuf d_subrows(sub_rows_total + 256), d_subjobs(sizeof(SubJob) * (sub[1].size() + sub[2].size() + sub[3].size() + 1));
+    if (!d_subrows.p || !d_subjobs.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+    std::vector<SubJob> suball;
+    size_t sub_first[4] = {0, 0, 0, 0};
+    for (int c = 1; c < 4; ++c) { sub_first[c] = suball.size(); for (auto& S : sub[c]) { S.rows = d_subrows.as<uint8_t>() + (size_t)S.rows; suball.push_back(S); } }
     for (auto& J : pj) { J.recs = (uint32_t*)(d_recs.as<uint8_t>() + (size_t)J.recs); J.rowinfo = (uint32_t*)(d_rows.as<uint8_t>() + (size_t)J.rowinfo); }
     DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(P10Image) * (pj.size() + 1));
     if (!d_lzj.p || !d_pj.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
@@ -243,11 +271,23 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!files_dev) okc &= cuda_ok(cudaMemcpyAsync(d_files.p, h_stage, file_total, cudaMemcpyHostToDevice, st), "files", __FILE__, __LINE__);
     okc &= cuda_ok(cudaMemcpyAsync(d_status.p, ones.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
     if (!lz.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_lzj.p, lz.data(), sizeof(Lz4Job) * lz.size(), cudaMemcpyHostToDevice, st), "lz", __FILE__, __LINE__);
-    okc &= cuda_ok(cudaMemcpyAsync(d_pj.p, pj.data(), sizeof(P10Image) * pj.size(), cudaMemcpyHostToDevice, st), "pj", __FILE__, __LINE__);
+    if (!pj.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_pj.p, pj.data(), sizeof(P10Image) * pj.size(), cudaMemcpyHostToDevice, st), "pj", __FILE__, __LINE__);
+    if (!suball.empty()) {
+        okc &= cuda_ok(cudaMemcpyAsync(d_subjobs.p, suball.data(), sizeof(SubJob) * suball.size(), cudaMemcpyHostToDevice, st), "subjobs", __FILE__, __LINE__);
+        okc &= cuda_ok(cudaMemsetAsync(d_subrows.p, 0, sub_rows_total, st), "subrows", __FILE__, __LINE__);
+    }
     cudaEventRecord(ev[1], st);
     if (!lz.empty()) { lz4_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(d_lzj.as<Lz4Job>(), (int)lz.size(), d_status.as<int>()); count_launch(); }
     cudaEventRecord(ev[2], st);
-    {
+    for (int c = 1; c < 4; ++c) {
+        if (sub[c].empty()) continue;
+        const SubJob* dj = d_subjobs.as<SubJob>() + sub_first[c]; const int nj = (int)sub[c].size();
+        if (c == 1) qoi10b_kernel<<<(nj + 31) / 32, 32, 0, st>>>(dj, nj, d_status.as<int>());
+        else if (c == 2) qoiplane8_kernel<<<(nj + 31) / 32, 32, 0, st>>>(dj, nj, d_status.as<int>());
+        else qoi2avg_kernel<<<(nj + 31) / 32, 32, 0, st>>>(dj, nj, d_status.as<int>());
+        count_launch();
+    }
+    if (!pj.empty()) {
         // QOI-Plane10: chunk-parallel parse (self-synchronising), scan, per-pixel records, wavefront reconstruction
         const P10Image* dI = d_pj.as<P10Image>(); const int ni = (int)pj.size();
         P10Chunk* chunks = d_chunks.as<P10Chunk>(); P10Entry* entries = d_entries.as<P10Entry>();

@@ -83,3 +83,69 @@ def test_plane10_3x1_kat_and_rejects(oracle):
     cut = enc[:25] + b"\xff" * 8
     px = oracle.qoix_decode(cut, 0)[0]
     assert (px == 0).all()
+
+
+# ---- QOIX sub-codecs without a restated reference encoder (qoi2avg.d, qoiplane.d, qoi10b.d) ----
+def _rand_img(h, w, c, seed, hi=256):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, hi, (h, w, c))
+    img[h // 3: h // 2, :, :] = img[h // 3, 0, :]          # flat band
+    if c >= 3:
+        img[:, w // 2:, 1] = img[:, w // 2:, 0]
+        img[:, w // 2:, 2] = img[:, w // 2:, 0]            # grey half
+    if c in (2, 4):
+        img[: h // 2, :, c - 1] = hi - 1                     # constant alpha on top
+    return img
+
+
+@pytest.mark.parametrize("c", [3, 4])
+def test_qoi2avg_literal_roundtrip_and_fuzz(oracle, c):
+    import qoixsynth as qs
+    for (h, w) in [(1, 1), (9, 13), (40, 31)]:
+        img = _rand_img(h, w, c, h * w + c).astype(np.uint8)
+        for wrap in (False, True):
+            data = qs.encode_qoi2avg(img, par=2.0, dpi=72.0)
+            if wrap:
+                data = qs.lz4_wrap(data, oracle)
+            px, d, t = oracle.qoix_decode(data, 0)
+            assert np.array_equal(px, img) and t == (9 if c == 3 else 12)
+            assert (d.width, d.height, d.pitchBytes, d.pixelAspectRatio, d.resolutionY) == (w, h, w * c, 2.0, 72.0)
+        r = oracle.qoix_decode(qs.fuzz_qoi2avg(w, h, c, 5), 0)
+        assert r is not None and r[0].shape == (h, w, c)
+
+
+@pytest.mark.parametrize("c", [1, 2])
+def test_qoiplane_literal_roundtrip_and_fuzz(oracle, c):
+    import qoixsynth as qs
+    for (h, w) in [(1, 1), (9, 13), (40, 31)]:
+        img = _rand_img(h, w, c, h * w + c).astype(np.uint8)
+        px, d, t = oracle.qoix_decode(qs.encode_qoiplane(img), 0)
+        assert np.array_equal(px, img) and t == (0 if c == 1 else 3)
+        r = oracle.qoix_decode(qs.fuzz_qoiplane(w, h, c, 6), 0)
+        assert r is not None and r[0].shape == (h, w, c)
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+@pytest.mark.parametrize("version", [1, 2])
+def test_qoi10b_literal_roundtrip_and_fuzz(oracle, c, version):
+    import qoixsynth as qs
+    if version == 2 and c <= 2:
+        pytest.skip("10-bit L/LA version 2 streams are QOI-Plane10 (plugins/qoix.d:438-447)")
+    for (h, w) in [(1, 1), (9, 13), (40, 31)]:
+        v = _rand_img(h, w, c, h * w + c, 1024)
+        exp = ((v << 6) | (v >> 4)).astype(np.uint16)
+        px, d, t = oracle.qoix_decode(qs.encode_qoi10b(v, version), 0)
+        assert np.array_equal(px, exp) and t == {1: 1, 2: 4, 3: 10, 4: 13}[c]
+        r = oracle.qoix_decode(qs.fuzz_qoi10b(w, h, c, 7, version), 0)
+        assert r is not None and r[0].shape == (h, w, c)
+
+
+def test_sub_codec_rejects(oracle):
+    import qoixsynth as qs
+    img = _rand_img(4, 4, 3, 1).astype(np.uint8)
+    good = qs.encode_qoi2avg(img)
+    assert oracle.qoix_decode(good, 0) is not None
+    for off, val in ((12, 2), (15, 3), (0, 0x70), (16, 2)):
+        bad = bytearray(good); bad[off] = val
+        assert oracle.qoix_decode(bytes(bad), 0) is None
+    assert oracle.qoix_decode(good[:27], 0) is None

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from qoixutil import depth_map_la, qoi_bytes, qoi_test_image
+import qoixsynth  # noqa: F401  (tests/ is on sys.path)
 
 pytestmark = pytest.mark.gpu
 
@@ -106,3 +107,74 @@ def test_config5_shape_2048(codecs, oracle):
     data = oracle.qoix_encode(img, 10, force_lz4=True)
     got = check_qoix(codecs, oracle, data)
     assert np.array_equal(got[0], img)
+
+
+# ---- remaining QOIX sub-codecs: QOI2AVG (8-bit RGB/RGBA), QOI-Plane (8-bit L/LA), QOI-10b ----
+SIZES = [(1, 1), (3, 2), (9, 13), (40, 31), (64, 128)]
+
+
+@pytest.mark.parametrize("c", [3, 4])
+def test_qoi2avg(codecs, oracle, c):
+    import qoixsynth as qs
+    rng = np.random.default_rng(c)
+    for (h, w) in SIZES:
+        img = rng.integers(0, 256, (h, w, c)).astype(np.uint8)
+        got = check_qoix(codecs, oracle, qs.encode_qoi2avg(img, par=1.25, dpi=300.0))
+        assert np.array_equal(got[0], img)
+        for seed in range(4):
+            s = qs.fuzz_qoi2avg(w, h, c, 100 * seed + h)
+            assert check_qoix(codecs, oracle, s) is not None
+            assert check_qoix(codecs, oracle, qs.lz4_wrap(s, oracle)) is not None
+    check_qoix(codecs, oracle, s[:40] + b"\xff" * 4)                # truncated: stream ends early
+    check_qoix(codecs, oracle, s[:30] + b"\xff\xff" + s[32:])      # END opcode in the middle of a row
+
+
+@pytest.mark.parametrize("c", [1, 2])
+def test_qoiplane8(codecs, oracle, c):
+    import qoixsynth as qs
+    rng = np.random.default_rng(c)
+    for (h, w) in SIZES:
+        img = rng.integers(0, 256, (h, w, c)).astype(np.uint8)
+        got = check_qoix(codecs, oracle, qs.encode_qoiplane(img))
+        assert np.array_equal(got[0], img)
+        for seed in range(4):
+            s = qs.fuzz_qoiplane(w, h, c, 100 * seed + h)
+            assert check_qoix(codecs, oracle, s) is not None
+            assert check_qoix(codecs, oracle, qs.lz4_wrap(s, oracle)) is not None
+    check_qoix(codecs, oracle, s[:40] + b"\xff" * 4)
+
+
+@pytest.mark.parametrize("c,version", [(1, 1), (2, 1), (3, 1), (4, 1), (3, 2), (4, 2), (1, 0)])
+def test_qoi10b(codecs, oracle, c, version):
+    import qoixsynth as qs
+    rng = np.random.default_rng(c + 10 * version)
+    for (h, w) in SIZES:
+        v = rng.integers(0, 1024, (h, w, c))
+        got = check_qoix(codecs, oracle, qs.encode_qoi10b(v, version))
+        assert np.array_equal(got[0], ((v << 6) | (v >> 4)).astype(np.uint16))
+        for seed in range(4):
+            s = qs.fuzz_qoi10b(w, h, c, 100 * seed + h, version)
+            assert check_qoix(codecs, oracle, s) is not None
+            assert check_qoix(codecs, oracle, qs.lz4_wrap(s, oracle)) is not None
+    check_qoix(codecs, oracle, s[:60] + b"\xff" * 5)               # early END: remaining rows stay zero
+
+
+def test_sub_codec_batch_and_rejects(codecs, oracle):
+    import qoixsynth as qs
+    files = [qs.fuzz_qoi2avg(33, 17, 4, 1), qs.fuzz_qoiplane(20, 50, 2, 2), qs.fuzz_qoi10b(31, 9, 3, 3, 2),
+             oracle.qoix_encode(depth_map_la(40, 50, 1, 2), 10, force_lz4=True), qs.fuzz_qoi10b(8, 8, 1, 4, 1)]
+    bad = bytearray(files[0]); bad[12] = 2
+    files.append(bytes(bad))                                          # version 2 of an 8-bit stream: rejected
+    bad = bytearray(files[1]); bad[15] = 2
+    files.append(bytes(bad))                                          # premultiplied QOI-Plane: rejected
+    b = codecs.qoix_decode_batch(files, 0)
+    try:
+        for i, f in enumerate(files):
+            exp = oracle.qoix_decode(f, 0)
+            got = b.to_host(i)
+            if exp is None:
+                assert got is None
+            else:
+                assert np.array_equal(got, exp[0]) and b.images[i].pixel_type == exp[2]
+    finally:
+        b.free()

@@ -54,7 +54,8 @@ class ConvertWorkload:
     default_e2e_steps = 3
     W = H = 8192
     bytes_per_px = 20            # 4 B rgba8 + 16 B rgbaf32 per direction
-    e2e_api = "gb200_scanlines_convert (host pointers, pinned)"
+    e2e_api = ("gb200_scanlines_convert (host pointers, pinned); forward and reverse issued concurrently from two "
+               "host threads (the entry point is thread-safe), each call pipelines H2D/kernel/D2H over row bands")
 
     def __init__(self, rank, world, args):
         import torch
@@ -116,16 +117,34 @@ class ConvertWorkload:
             raise RuntimeError("pinned alloc failed")
         a = np.ctypeslib.as_array(C.cast(self.h_u8, C.POINTER(C.c_uint8)), shape=(W * H * 4,))
         a[:] = np.random.default_rng(1).integers(0, 256, W * H * 4, dtype=np.uint8)
+        # second pair of buffers for the reverse direction so that both directions can run concurrently
+        self.h_f32_in = L.gb200_host_alloc(W * H * 16)
+        self.h_u8_out = L.gb200_host_alloc(W * H * 4)
+        if not self.h_f32_in or not self.h_u8_out:
+            raise RuntimeError("pinned alloc failed")
+        assert L.gb200_scanlines_convert(PT_rgba8(), self.h_u8, W * 4, PT_rgbaf32(), self.h_f32_in, W * 16, W, H)
         self.h2d = W * H * 4 + W * H * 16
         self.d2h = W * H * 16 + W * H * 4
 
     def e2e_step(self):
         from gamut_b200.types import PixelType as PT
         W, H, L = self.W, self.H, self.L
-        ok1 = L.gb200_scanlines_convert(PT.rgba8, self.h_u8, W * 4, PT.rgbaf32, self.h_f32, W * 16, W, H)
-        ok2 = L.gb200_scanlines_convert(PT.rgbaf32, self.h_f32, W * 16, PT.rgba8, self.h_u8, W * 4, W, H)
-        if not (ok1 and ok2):
-            raise RuntimeError(L.gb200_last_error().decode())
+        ok = [0, 0]
+
+        def run(t):
+            if t == 0:
+                ok[0] = L.gb200_scanlines_convert(PT.rgba8, self.h_u8, W * 4, PT.rgbaf32, self.h_f32, W * 16, W, H)
+            else:
+                ok[1] = L.gb200_scanlines_convert(PT.rgbaf32, self.h_f32_in, W * 16, PT.rgba8, self.h_u8_out, W * 4, W, H)
+
+        _threads_run(run, 2)
+        if not (ok[0] and ok[1]):
+            raise RuntimeError("gb200_scanlines_convert failed")
+        if not getattr(self, "_e2e_checked", False):
+            a = np.ctypeslib.as_array(C.cast(self.h_u8, C.POINTER(C.c_uint8)), shape=(W * H * 4,))
+            b = np.ctypeslib.as_array(C.cast(self.h_u8_out, C.POINTER(C.c_uint8)), shape=(W * H * 4,))
+            assert np.array_equal(a, b), "e2e round trip rgba8 -> rgbaf32 -> rgba8 is not the identity"
+            self._e2e_checked = True
 
     @staticmethod
     def cpu_run(threads, reps, full):
@@ -207,7 +226,7 @@ class PngWorkload:
     default_e2e_steps = 1
     W, H = 1920, 1080
     DISTINCT = 16
-    e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back)"
+    e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back to pinned host memory with gb200_batch_download)"
 
     def __init__(self, rank, world, args):
         import torch
@@ -334,14 +353,13 @@ class PngWorkload:
     def e2e_setup(self):
         self.h2d = int(self.comp_bytes * self.e2e_n)
         self.d2h = self.e2e_n * self.out_stride
-        self.h_out = np.empty(self.e2e_n * self.out_stride, np.uint8)
+        self.h_out = self.codecs._L().gb200_host_alloc(self.e2e_n * self.out_stride)
+        assert self.h_out
 
     def e2e_step(self):
         b = self.codecs.png_decode_batch(self.host_files[:self.e2e_n], 0, 0)
-        L = self.codecs._L()
-        for i, d in enumerate(b.images):
-            assert d.status
-            L.gb200_copy_to_host(self.h_out.ctypes.data + i * self.out_stride, d.pixels, self.out_stride)
+        assert all(d.status for d in b.images)
+        b.download(self.h_out, self.out_stride)
         b.free()
 
     @staticmethod
@@ -411,14 +429,13 @@ class _BatchDecodeWorkload:
     def e2e_setup(self):
         self.h2d = int(self.comp_bytes * self.e2e_n)
         self.d2h = self.e2e_n * self.out_bytes
-        self.h_out = np.empty(self.e2e_n * self.out_bytes, np.uint8)
+        self.h_out = self.codecs._L().gb200_host_alloc(self.e2e_n * self.out_bytes)
+        assert self.h_out
 
     def e2e_step(self):
         b = self.decode(self.host_files[:self.e2e_n], None, 0)
-        L = self.codecs._L()
-        for i, d in enumerate(b.images):
-            assert d.status
-            L.gb200_copy_to_host(self.h_out.ctypes.data + i * self.out_bytes, d.pixels, self.out_bytes)
+        assert all(d.status for d in b.images)
+        b.download(self.h_out, self.out_bytes)
         b.free()
 
     def roofline(self, peak, peak_kind):
@@ -440,7 +457,7 @@ class JpegWorkload(_BatchDecodeWorkload):
     """BASELINE configs[3]: JPEG baseline decode (Huffman+IDCT+YCbCr), 3840x2160 4:2:0 q90, batch sharded over ranks."""
     name = "JPEG baseline decode (Huffman+IDCT+YCbCr) 3840x2160 4:2:0 q90, batch sharded 1/2/4/8 GPU (BASELINE configs[3])"
     W, H = 3840, 2160
-    e2e_api = "gb200_jpeg_decode_batch (host file bytes staged through pinned memory; rgb8 pixels copied back)"
+    e2e_api = "gb200_jpeg_decode_batch (host file bytes staged through pinned memory; rgb8 pixels copied back to pinned host memory with gb200_batch_download)"
     kernel_names = {1: "jpeg_huffman_kernel", 2: "jpeg_idct_kernel+jpeg_colour_kernel"}
 
     def __init__(self, rank, world, args):
@@ -495,7 +512,7 @@ class QoixWorkload(_BatchDecodeWorkload):
     name = "QOIX 10-bit LA + LZ4 decode 2048x2048, batch 2048 sharded over ranks (BASELINE configs[4])"
     dtype = "u16"
     W, H = 2048, 2048
-    e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back)"
+    e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back to pinned host memory with gb200_batch_download)"
     kernel_names = {1: "lz4_kernel", 2: "qoiplane10_kernel"}
 
     def __init__(self, rank, world, args):
@@ -546,6 +563,16 @@ class QoixWorkload(_BatchDecodeWorkload):
             _threads_run(work, threads)
             times.append(time.perf_counter() - t0)
         return nimg * W * H, times, f"{nimg} images 2048x2048 la16 + LZ4, {threads} thread(s), one image per worker"
+
+
+def PT_rgba8():
+    from gamut_b200.types import PixelType as PT
+    return PT.rgba8
+
+
+def PT_rgbaf32():
+    from gamut_b200.types import PixelType as PT
+    return PT.rgbaf32
 
 
 def sys_path_tests():

@@ -44,6 +44,7 @@ def _L():
         L.gb200_batch_images.restype = C.POINTER(ImageDesc)
         L.gb200_batch_images.argtypes = [vp]
         L.gb200_batch_free.argtypes = [vp]
+        L.gb200_batch_download.argtypes = [vp, vp, sz]
         L.gb200_batch_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.gb200_png_is16.argtypes = [C.c_char_p, sz]
         L.gb200_png_load.restype = vp
@@ -124,6 +125,10 @@ class Batch:
         _lib.check(_L().gb200_copy_to_host(out.ctypes.data, d.pixels, n), "copy_to_host")
         a = out.view(np.uint16) if d.bits == 16 else out
         return a.reshape(d.height, d.width, d.channels)
+
+    def download(self, dst_host: int, stride: int) -> None:
+        """All decoded images to (pinned) host memory, image i at dst_host + i*stride."""
+        _lib.check(_L().gb200_batch_download(self.handle, dst_host, stride), "batch_download")
 
     def timing(self):
         ph = (C.c_float * 8)()

@@ -144,14 +144,15 @@ void  dev_trim()
 void* pinned_alloc(size_t bytes) { return pool_alloc(hpool(), bytes, true); }
 void  pinned_free(void* p) { pool_free(hpool(), p); }
 
-cudaStream_t thread_stream()
+cudaStream_t thread_stream(int idx)
 {
-    static thread_local cudaStream_t s = nullptr;
-    if (!s) {
+    static thread_local cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+    idx &= 3;
+    if (!s[idx]) {
         if (!ensure_device()) return nullptr;
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { s = nullptr; }
+        if (cudaStreamCreateWithFlags(&s[idx], cudaStreamNonBlocking) != cudaSuccess) { s[idx] = nullptr; }
     }
-    return s;
+    return s[idx];
 }
 
 } // namespace gb

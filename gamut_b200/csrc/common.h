@@ -38,8 +38,9 @@ void  dev_trim();
 void* pinned_alloc(size_t bytes);
 void  pinned_free(void* p);
 
-// The library's own non-blocking stream for host-pointer entry points (one per thread).
-cudaStream_t thread_stream();
+// The library's own non-blocking streams for host-pointer entry points (four per thread; index 0 is
+// the default, the others are used to overlap H2D / kernel / D2H of consecutive bands).
+cudaStream_t thread_stream(int idx = 0);
 
 struct DevBuf {
     void* p = nullptr;

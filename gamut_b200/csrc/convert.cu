@@ -415,22 +415,35 @@ GB_API int gb200_scanlines_convert(int srcType, const uint8_t* src, int srcPitch
     const size_t sdp = (srow + 15) & ~(size_t)15, ddp = (drow + 15) & ~(size_t)15;
     gb::DevBuf ds(sdp * height), dd(ddp * height);
     if (!ds.p || !dd.p) return 0;
-    cudaStream_t st = gb::thread_stream();
     // negative pitches: address the lowest row first and flip on the device side
     const uint8_t* slo = srcPitch >= 0 ? src : src + (long long)(height - 1) * srcPitch;
     uint8_t* dlo = dstPitch >= 0 ? dst : dst + (long long)(height - 1) * dstPitch;
     size_t sap = (size_t)(srcPitch >= 0 ? srcPitch : -(long long)srcPitch);
     size_t dap = (size_t)(dstPitch >= 0 ? dstPitch : -(long long)dstPitch);
     if (height == 1) { sap = srow; dap = drow; }
-    if (sap == srow && sdp == srow) GB_CUDA(cudaMemcpyAsync(ds.p, slo, srow * height, cudaMemcpyHostToDevice, st));
-    else GB_CUDA(cudaMemcpy2DAsync(ds.p, sdp, slo, sap, srow, height, cudaMemcpyHostToDevice, st));
     const uint8_t* dsrc = ds.as<uint8_t>(); long long dsp = (long long)sdp;
     uint8_t* ddst = dd.as<uint8_t>(); long long ddpp = (long long)ddp;
     if (srcPitch < 0) { dsrc += (size_t)(height - 1) * sdp; dsp = -dsp; }
     if (dstPitch < 0) { ddst += (size_t)(height - 1) * ddp; ddpp = -ddpp; }
-    if (!gb::convert_device(srcType, dsrc, dsp, dstType, ddst, ddpp, width, height, st)) return 0;
-    if (dap == drow && ddp == drow) GB_CUDA(cudaMemcpyAsync(dlo, dd.p, drow * height, cudaMemcpyDeviceToHost, st));
-    else GB_CUDA(cudaMemcpy2DAsync(dlo, dap, dd.p, ddp, drow, height, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaStreamSynchronize(st));
+    // Bands of logical rows go round-robin over three streams so that the H2D copy of band k+1, the
+    // kernel of band k and the D2H copy of band k-1 overlap (PCIe is full duplex; a whole-image
+    // H2D -> kernel -> D2H sequence leaves one direction idle at any time).
+    const size_t big = srow > drow ? srow : drow;
+    int band = (int)((16u << 20) / (big ? big : 1));
+    if (band < 1) band = 1;
+    if (band >= height) band = height;
+    int k = 0;
+    for (int i0 = 0; i0 < height; i0 += band, ++k) {
+        const int i1 = i0 + band < height ? i0 + band : height, nr = i1 - i0;
+        cudaStream_t st = gb::thread_stream(k % 3);
+        const size_t sm0 = srcPitch >= 0 ? (size_t)i0 : (size_t)(height - i1);   // first memory row of the band
+        const size_t dm0 = dstPitch >= 0 ? (size_t)i0 : (size_t)(height - i1);
+        if (sap == srow && sdp == srow) GB_CUDA(cudaMemcpyAsync(ds.as<uint8_t>() + sm0 * sdp, slo + sm0 * sap, srow * nr, cudaMemcpyHostToDevice, st));
+        else GB_CUDA(cudaMemcpy2DAsync(ds.as<uint8_t>() + sm0 * sdp, sdp, slo + sm0 * sap, sap, srow, nr, cudaMemcpyHostToDevice, st));
+        if (!gb::convert_device(srcType, dsrc + (long long)i0 * dsp, dsp, dstType, ddst + (long long)i0 * ddpp, ddpp, width, nr, st)) return 0;
+        if (dap == drow && ddp == drow) GB_CUDA(cudaMemcpyAsync(dlo + dm0 * dap, dd.as<uint8_t>() + dm0 * ddp, drow * nr, cudaMemcpyDeviceToHost, st));
+        else GB_CUDA(cudaMemcpy2DAsync(dlo + dm0 * dap, dap, dd.as<uint8_t>() + dm0 * ddp, ddp, drow, nr, cudaMemcpyDeviceToHost, st));
+    }
+    for (int q = 0; q < 3 && q < k; ++q) GB_CUDA(cudaStreamSynchronize(gb::thread_stream(q)));
     return 1;
 }

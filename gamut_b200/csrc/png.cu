@@ -420,6 +420,22 @@ GB_API void gb200_batch_timing(const gb200_batch* b, float* phase_ms8, double* h
     if (host_parse_ms) *host_parse_ms = b->host_parse_ms;
 }
 
+GB_API int gb200_batch_download(const gb200_batch* b, uint8_t* dst_host, size_t stride)
+{
+    gb::clear_error();
+    if (!b) return 0;
+    if (!gb::ensure_device()) return 0;
+    // one asynchronous copy per decoded image on the batch's stream, one synchronisation for all of them
+    // (dst_host should be pinned -- gb200_host_alloc -- for the copies to run at PCIe speed)
+    for (size_t i = 0; i < b->images.size(); ++i) {
+        const gb200_image_desc& D = b->images[i];
+        if (!D.status || !D.pixels) continue;
+        GB_CUDA(cudaMemcpyAsync(dst_host + i * stride, D.pixels, (size_t)D.pitch * D.height, cudaMemcpyDeviceToHost, b->stream));
+    }
+    GB_CUDA(cudaStreamSynchronize(b->stream));
+    return 1;
+}
+
 GB_API int gb200_png_is16(const uint8_t* data, size_t len)
 {
     PngHeader H;

@@ -91,6 +91,10 @@ typedef struct gb200_image_desc {
 int                     gb200_batch_count(const gb200_batch* b);
 const gb200_image_desc* gb200_batch_images(const gb200_batch* b);
 void                    gb200_batch_free(gb200_batch* b);
+/* Copies every decoded image to host memory: image i lands at dst_host + i*stride (gapless rows). One
+ * asynchronous copy per image on the batch's stream and one synchronisation; dst_host should come from
+ * gb200_host_alloc (pinned) for PCIe-speed copies. Failed images are skipped. Returns 1 / 0. */
+int                     gb200_batch_download(const gb200_batch* b, uint8_t* dst_host, size_t stride);
 /* Device time of each phase of the call (CUDA events on the call's stream), ms. PNG: [0] IDAT gather /
  * H2D, [1] inflate, [2] unfilter, [3] finish. JPEG: [0] upload, [1] Huffman, [2] IDCT+colour. QOIX: [0] upload,
  * [1] LZ4, [2] opcode decode. */

@@ -54,6 +54,8 @@ def _L():
         L.gb200_png_unfilter_device.argtypes = [vp, sz, vp, sz, i32, i32, i32, i32, vp, vp]
         L.gb200_inflate_device.argtypes = [i32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp),
                                            C.POINTER(C.c_uint32), i32, vp, vp, vp]
+        L.gb200_inflate_set_mode.argtypes = [i32]
+        L.gb200_inflate_set_mode.restype = None
         L.gb200_jpeg_load.restype = vp
         L.gb200_jpeg_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp]
         L.gb200_jpeg_decode_batch.restype = vp
@@ -163,6 +165,37 @@ def png_decode_batch(files: Sequence[bytes], req_comp: int = 0, want16: int = -1
     if not h:
         raise _lib.GamutB200Error("png_decode_batch: " + _lib.last_error())
     return Batch(h)
+
+
+def inflate_set_mode(parallel: bool) -> None:
+    _L().gb200_inflate_set_mode(1 if parallel else 0)
+
+
+def inflate_device(streams: Sequence[bytes], caps: Sequence[int], parse_header: bool = True):
+    """Kernel-level inflate (replaces miniz mz_uncompress3 as called from stbdec.d:1267-1321) of device-resident
+    streams. Returns [(status, out_len, bytes)] -- status 0 ok, 1 output buffer too small, 2 corrupt."""
+    import torch
+    L = _L()
+    n = len(streams)
+    ins, outs = [], []
+    for s, cap in zip(streams, caps):
+        t = torch.zeros(((len(s) + 3) // 4) * 4 + 32, dtype=torch.uint8, device="cuda")
+        if len(s):
+            t[:len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+        ins.append(t)
+        outs.append(torch.zeros(cap + 32, dtype=torch.uint8, device="cuda"))
+    lens_d = torch.zeros(n, dtype=torch.int32, device="cuda")
+    st_d = torch.zeros(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    inp = (C.c_void_p * n)(*[t.data_ptr() for t in ins])
+    outp = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+    il = (C.c_uint32 * n)(*[len(s) for s in streams])
+    oc = (C.c_uint32 * n)(*caps)
+    _lib.check(L.gb200_inflate_device(n, inp, il, outp, oc, 1 if parse_header else 0, lens_d.data_ptr(), st_d.data_ptr(), None),
+               "inflate_device")
+    lens = lens_d.cpu().numpy()
+    sts = st_d.cpu().numpy()
+    return [(int(sts[i]), int(lens[i]), outs[i][:int(lens[i])].cpu().numpy().tobytes()) for i in range(n)]
 
 
 @dataclass

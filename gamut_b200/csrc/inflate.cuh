@@ -180,6 +180,108 @@ __device__ inline void inf_init_sym_entries(InflateSmem& S, int lane)
     }
 }
 
+// Reads the code tables of a Huffman block (btype 1: fixed, 2: dynamic; the 3 header bits are already
+// consumed) and builds the decode tables. Warp-uniform. Returns false on a malformed header.
+__device__ inline bool inf_setup_tables(InflateReader& R, InflateSmem& S, int lane, uint32_t btype)
+{
+    int nlit, ndist;
+    if (btype == 1) {
+        for (int s = lane; s < 288; s += 32) S.lens[s] = (s < 144) ? 8 : (s < 256) ? 9 : (s < 280) ? 7 : 8;
+        S.lens[288 + lane] = 5;
+        nlit = 288; ndist = 32;
+        __syncwarp();
+    } else {
+        R.refill();
+        nlit = (int)R.get(5) + 257;
+        ndist = (int)R.get(5) + 1;
+        int ncl = (int)R.get(4) + 4;
+        // code-length code: 19 symbols, 3 bits each, in the RFC's permuted order
+        uint32_t cl_lens_lo = 0, cl_lens_hi = 0;           // 19 x 3 bits packed (symbol-indexed)
+        for (int i = 0; i < ncl; ++i) {
+            R.refill();
+            uint32_t v = R.get(3);
+            int sidx = inf_cl_order[i];
+            if (sidx < 10) cl_lens_lo |= v << (3 * sidx); else cl_lens_hi |= v << (3 * (sidx - 10));
+        }
+        // tiny canonical decoder for the code-length code (max 7 bits), in registers
+        int cl_count[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) cl_count[l] = 0;
+#pragma unroll
+        for (int s = 0; s < 19; ++s) {
+            int l = (s < 10) ? (cl_lens_lo >> (3 * s)) & 7 : (cl_lens_hi >> (3 * (s - 10))) & 7;
+#pragma unroll
+            for (int q = 1; q < 8; ++q) cl_count[q] += (l == q);
+        }
+        int cl_first[8], cl_fsym[8];
+        {
+            int code = 0, sym = 0, left = 1; bool over = false;
+            cl_first[0] = 0; cl_fsym[0] = 0;
+#pragma unroll
+            for (int l = 1; l < 8; ++l) {
+                left = (left << 1) - cl_count[l];
+                if (left < 0) over = true;
+                code = (code + (l > 1 ? cl_count[l - 1] : 0)) << 1;
+                cl_first[l] = code; cl_fsym[l] = sym; sym += cl_count[l];
+            }
+            if (over) return false;
+        }
+        // sorted symbol list of the code-length code, packed 5 bits each into two 64-bit words
+        uint64_t cl_sorted_lo = 0, cl_sorted_hi = 0;
+        {
+            int k = 0;
+#pragma unroll
+            for (int l = 1; l < 8; ++l) {
+#pragma unroll
+                for (int s = 0; s < 19; ++s) {
+                    int sl = (s < 10) ? (cl_lens_lo >> (3 * s)) & 7 : (cl_lens_hi >> (3 * (s - 10))) & 7;
+                    if (sl == l) {
+                        if (k < 12) cl_sorted_lo |= (uint64_t)s << (5 * k); else cl_sorted_hi |= (uint64_t)s << (5 * (k - 12));
+                        ++k;
+                    }
+                }
+            }
+        }
+        int total = nlit + ndist;
+        int i = 0, prev = 0;
+        while (i < total) {
+            R.refill();
+            uint32_t rev = __brev(R.peek(7)) >> 25;
+            int sym = -1, len = 0;
+#pragma unroll
+            for (int l = 1; l < 8; ++l) {
+                if (sym < 0) {
+                    int c = (int)(rev >> (7 - l));
+                    int d = c - cl_first[l];
+                    if (d >= 0 && d < cl_count[l]) {
+                        int k = cl_fsym[l] + d;
+                        sym = (k < 12) ? (int)((cl_sorted_lo >> (5 * k)) & 31) : (int)((cl_sorted_hi >> (5 * (k - 12))) & 31);
+                        len = l;
+                    }
+                }
+            }
+            if (sym < 0) return false;
+            R.drop(len);
+            int rep = 1, val = sym;
+            if (sym == 16) { if (i == 0) return false; rep = 3 + (int)R.get(2); val = prev; }
+            else if (sym == 17) { rep = 3 + (int)R.get(3); val = 0; }
+            else if (sym == 18) { rep = 11 + (int)R.get(7); val = 0; }
+            if (i + rep > total) return false;
+            // lens[] index: lit/len symbols at 0.., distance symbols at 288..
+            for (int r = lane; r < rep; r += 32) {
+                int idx = i + r;
+                S.lens[idx < nlit ? idx : 288 + (idx - nlit)] = (uint8_t)val;
+            }
+            i += rep;
+            prev = val;
+        }
+        __syncwarp();
+        if (S.lens[256] == 0) return false;
+    }
+    return inf_build(S, 0, nlit, lane) && inf_build(S, 1, ndist, lane);
+
+}
+
 // Decodes one stream. All 32 lanes of the warp must call this with identical arguments.
 __device__ inline void inflate_stream(InflateJob& job, InflateSmem& S, int lane)
 {
@@ -229,101 +331,7 @@ __device__ inline void inflate_stream(InflateJob& job, InflateSmem& S, int lane)
         } else if (btype == 3) {
             status = INF_DATA_ERROR; goto done;
         } else {
-            int nlit, ndist;
-            if (btype == 1) {
-                for (int s = lane; s < 288; s += 32) S.lens[s] = (s < 144) ? 8 : (s < 256) ? 9 : (s < 280) ? 7 : 8;
-                S.lens[288 + lane] = 5;
-                nlit = 288; ndist = 32;
-                __syncwarp();
-            } else {
-                R.refill();
-                nlit = (int)R.get(5) + 257;
-                ndist = (int)R.get(5) + 1;
-                int ncl = (int)R.get(4) + 4;
-                // code-length code: 19 symbols, 3 bits each, in the RFC's permuted order
-                uint32_t cl_lens_lo = 0, cl_lens_hi = 0;           // 19 x 3 bits packed (symbol-indexed)
-                for (int i = 0; i < ncl; ++i) {
-                    R.refill();
-                    uint32_t v = R.get(3);
-                    int sidx = inf_cl_order[i];
-                    if (sidx < 10) cl_lens_lo |= v << (3 * sidx); else cl_lens_hi |= v << (3 * (sidx - 10));
-                }
-                // tiny canonical decoder for the code-length code (max 7 bits), in registers
-                int cl_count[8];
-#pragma unroll
-                for (int l = 0; l < 8; ++l) cl_count[l] = 0;
-#pragma unroll
-                for (int s = 0; s < 19; ++s) {
-                    int l = (s < 10) ? (cl_lens_lo >> (3 * s)) & 7 : (cl_lens_hi >> (3 * (s - 10))) & 7;
-#pragma unroll
-                    for (int q = 1; q < 8; ++q) cl_count[q] += (l == q);
-                }
-                int cl_first[8], cl_fsym[8];
-                {
-                    int code = 0, sym = 0, left = 1; bool over = false;
-                    cl_first[0] = 0; cl_fsym[0] = 0;
-#pragma unroll
-                    for (int l = 1; l < 8; ++l) {
-                        left = (left << 1) - cl_count[l];
-                        if (left < 0) over = true;
-                        code = (code + (l > 1 ? cl_count[l - 1] : 0)) << 1;
-                        cl_first[l] = code; cl_fsym[l] = sym; sym += cl_count[l];
-                    }
-                    if (over) { status = INF_DATA_ERROR; goto done; }
-                }
-                // sorted symbol list of the code-length code, packed 5 bits each into two 64-bit words
-                uint64_t cl_sorted_lo = 0, cl_sorted_hi = 0;
-                {
-                    int k = 0;
-#pragma unroll
-                    for (int l = 1; l < 8; ++l) {
-#pragma unroll
-                        for (int s = 0; s < 19; ++s) {
-                            int sl = (s < 10) ? (cl_lens_lo >> (3 * s)) & 7 : (cl_lens_hi >> (3 * (s - 10))) & 7;
-                            if (sl == l) {
-                                if (k < 12) cl_sorted_lo |= (uint64_t)s << (5 * k); else cl_sorted_hi |= (uint64_t)s << (5 * (k - 12));
-                                ++k;
-                            }
-                        }
-                    }
-                }
-                int total = nlit + ndist;
-                int i = 0, prev = 0;
-                while (i < total) {
-                    R.refill();
-                    uint32_t rev = __brev(R.peek(7)) >> 25;
-                    int sym = -1, len = 0;
-#pragma unroll
-                    for (int l = 1; l < 8; ++l) {
-                        if (sym < 0) {
-                            int c = (int)(rev >> (7 - l));
-                            int d = c - cl_first[l];
-                            if (d >= 0 && d < cl_count[l]) {
-                                int k = cl_fsym[l] + d;
-                                sym = (k < 12) ? (int)((cl_sorted_lo >> (5 * k)) & 31) : (int)((cl_sorted_hi >> (5 * (k - 12))) & 31);
-                                len = l;
-                            }
-                        }
-                    }
-                    if (sym < 0) { status = INF_DATA_ERROR; goto done; }
-                    R.drop(len);
-                    int rep = 1, val = sym;
-                    if (sym == 16) { if (i == 0) { status = INF_DATA_ERROR; goto done; } rep = 3 + (int)R.get(2); val = prev; }
-                    else if (sym == 17) { rep = 3 + (int)R.get(3); val = 0; }
-                    else if (sym == 18) { rep = 11 + (int)R.get(7); val = 0; }
-                    if (i + rep > total) { status = INF_DATA_ERROR; goto done; }
-                    // lens[] index: lit/len symbols at 0.., distance symbols at 288..
-                    for (int r = lane; r < rep; r += 32) {
-                        int idx = i + r;
-                        S.lens[idx < nlit ? idx : 288 + (idx - nlit)] = (uint8_t)val;
-                    }
-                    i += rep;
-                    prev = val;
-                }
-                __syncwarp();
-                if (S.lens[256] == 0) { status = INF_DATA_ERROR; goto done; }
-            }
-            if (!inf_build(S, 0, nlit, lane) || !inf_build(S, 1, ndist, lane)) { status = INF_DATA_ERROR; goto done; }
+            if (!inf_setup_tables(R, S, lane, btype)) { status = INF_DATA_ERROR; goto done; }
 
             // ---- symbol loop ----
             int nl = 0;             // literals batched in registers

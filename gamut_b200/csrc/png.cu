@@ -12,7 +12,6 @@
 #include <chrono>
 
 namespace gb {
-void launch_inflate(InflateJob* d_jobs, int njobs, cudaStream_t st);
 void launch_gather(const void* d_segs, int nsegs, cudaStream_t st);
 void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const InflateJob* d_inf, cudaStream_t st, int rowpar_threads);
 void launch_finish(const FinishJob* d_jobs, int njobs, uint64_t max_pixels, cudaStream_t st);
@@ -350,7 +349,8 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
             okc &= cuda_ok(cudaMemcpyAsync(d_idat.p, h_stage, idat_total, cudaMemcpyHostToDevice, st), "idat", __FILE__, __LINE__);
         }
         cudaEventRecord(ev[1], st);
-        launch_inflate(d_ij.as<InflateJob>(), m, st);
+        InflateWork iwork;
+        okc &= launch_inflate(d_ij.as<InflateJob>(), ijobs.data(), m, st, iwork);
         cudaEventRecord(ev[2], st);
         launch_unfilter(d_uj.as<UnfilterJob>(), (int)ujobs.size(), d_status.as<int>(), d_ij.as<InflateJob>(), st, rowpar_threads);
         cudaEventRecord(ev[3], st);
@@ -502,6 +502,8 @@ GB_API int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint
     return 1;
 }
 
+GB_API void gb200_inflate_set_mode(int parallel) { gb::set_inflate_mode(parallel ? 1 : 0); }
+
 GB_API int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint32_t* in_lens,
                                 uint8_t* const* out_dev, const uint32_t* out_caps, int parse_header,
                                 uint32_t* out_lens_dev, int* statuses_dev, void* stream)
@@ -519,7 +521,8 @@ GB_API int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint3
     gb::DevBuf d_jobs(sizeof(gb::InflateJob) * (size_t)n);
     if (!d_jobs.p) return 0;
     GB_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(gb::InflateJob) * (size_t)n, cudaMemcpyHostToDevice, st));
-    gb::launch_inflate(d_jobs.as<gb::InflateJob>(), n, st);
+    gb::InflateWork iwork;
+    if (!gb::launch_inflate(d_jobs.as<gb::InflateJob>(), jobs.data(), n, st, iwork)) return 0;
     GB_CUDA(cudaGetLastError());
     if (out_lens_dev) GB_CUDA(cudaMemcpy2DAsync(out_lens_dev, 4, (const char*)d_jobs.p + offsetof(gb::InflateJob, out_len), sizeof(gb::InflateJob), 4, n, cudaMemcpyDeviceToDevice, st));
     if (statuses_dev) GB_CUDA(cudaMemcpy2DAsync(statuses_dev, 4, (const char*)d_jobs.p + offsetof(gb::InflateJob, status), sizeof(gb::InflateJob), 4, n, cudaMemcpyDeviceToDevice, st));

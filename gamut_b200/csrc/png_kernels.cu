@@ -1,29 +1,111 @@
 // png_kernels.cu -- PNG device kernels: batched inflate, row unfilter (wavefront), finish.
 #include "common.h"
 #include "png_kernels.cuh"
+#include "inflate_par.cuh"
+#include <vector>
+#include <algorithm>
 
 namespace gb {
 
 // ---------------------------------------------------------------------------------------------
-// Batched inflate: one warp per zlib stream (see inflate.cuh).
+// Batched inflate. Long streams go through the block-parallel pipeline of inflate_par.cuh; every stream that
+// pipeline did not accept (short, odd, corrupt, output buffer too small) is decoded by one warp (inflate.cuh).
 __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
-inflate_batch_kernel(InflateJob* jobs, int njobs)
+inflate_batch_kernel(InflateJob* jobs, int njobs, const InfPar* par)
 {
     __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int j = blockIdx.x * INF_WARPS_PER_CTA + warp;
     if (j >= njobs) return;
+    if (par && par[j].eligible && par[j].ok && !par[j].fail) return;     // accepted by the parallel pipeline
     InflateJob job = jobs[j];
     inflate_stream(job, smem[warp], lane);
     if (lane == 0) { jobs[j].out_len = job.out_len; jobs[j].status = job.status; }
 }
 
-void launch_inflate(InflateJob* d_jobs, int njobs, cudaStream_t st)
+static int g_inflate_mode = -1;      // -1: unset (env GB200_INFLATE: "serial" | "parallel"), 0 serial, 1 parallel
+void set_inflate_mode(int m) { g_inflate_mode = m; }
+
+bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cudaStream_t st, InflateWork& W)
 {
-    if (njobs <= 0) return;
-    int grid = (njobs + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
-    inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs);
-    count_launch();
+    if (njobs <= 0) return true;
+    if (g_inflate_mode < 0) {
+        const char* e = getenv("GB200_INFLATE");
+        g_inflate_mode = (e && !strcmp(e, "serial")) ? 0 : 1;
+    }
+    const int grid = (njobs + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
+    // ---- plan the parallel pipeline
+    std::vector<InfPar> par((size_t)njobs);
+    std::vector<uint32_t> tile_start((size_t)njobs + 1);
+    size_t slots_total = 0, blocks_total = 0, bitmap_total = 0;
+    uint64_t bits_total = 0;
+    uint32_t tiles = 0;
+    int neligible = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const InflateJob& J = h_jobs[j];
+        InfPar& P = par[j];
+        memset(&P, 0, sizeof(P));
+        tile_start[j] = tiles;
+        const bool el = g_inflate_mode == 1 && J.in_len >= 2048 && J.in_len < (1u << 28) && J.out_cap >= 64 &&
+                        J.out_cap < 0xfffffff0u && (((uintptr_t)J.out) & 3) == 0 && (((uintptr_t)J.in) & 3) == 0;
+        if (!el) continue;
+        P.eligible = 1;
+        P.in_bits = J.in_len * 8;
+        P.nslots = (P.in_bits + INFP_SLOT_BITS - 1) / INFP_SLOT_BITS;
+        P.maxblocks = J.in_len / 2048 + 8;
+        // offsets for now; turned into pointers below
+        P.slots = (uint32_t*)(uintptr_t)slots_total;   slots_total += P.nslots;
+        P.blocks = (InfBlock*)(uintptr_t)blocks_total; blocks_total += P.maxblocks;
+        P.bitmap = (uint32_t*)(uintptr_t)bitmap_total; bitmap_total += (size_t)(J.out_cap / 32) + 2;
+        bits_total += P.in_bits;
+        const uint32_t nwords = (J.in_len + 3) / 4;
+        tiles += (nwords + INFP_TILE_WORDS - 1) / INFP_TILE_WORDS;
+        ++neligible;
+    }
+    tile_start[njobs] = tiles;
+    if (neligible == 0) {
+        inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs, nullptr);
+        count_launch();
+        return true;
+    }
+    const uint32_t vq_cap = (uint32_t)std::min<uint64_t>(bits_total / 512 + 4096, 0x7fffffffull);
+    auto al256 = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const size_t o_par = 0, o_tiles = al256(o_par + sizeof(InfPar) * njobs), o_ctr = al256(o_tiles + 4 * ((size_t)njobs + 1)),
+                 o_slots = al256(o_ctr + 64), o_bitmap = al256(o_slots + 4 * slots_total), o_blocks = al256(o_bitmap + 4 * bitmap_total),
+                 o_work = al256(o_blocks + sizeof(InfBlock) * blocks_total), o_vq = al256(o_work + 8 * blocks_total),
+                 total = al256(o_vq + 8 * (size_t)vq_cap);
+    if (!W.buf.alloc(total)) return false;
+    uint8_t* base = W.buf.as<uint8_t>();
+    for (int j = 0; j < njobs; ++j) {
+        InfPar& P = par[j];
+        if (!P.eligible) continue;
+        P.slots = (uint32_t*)(base + o_slots) + (size_t)(uintptr_t)P.slots;
+        P.blocks = (InfBlock*)(base + o_blocks) + (size_t)(uintptr_t)P.blocks;
+        P.bitmap = (uint32_t*)(base + o_bitmap) + (size_t)(uintptr_t)P.bitmap;
+    }
+    // par and tile_start are uploaded from pageable memory: cudaMemcpyAsync returns once they are staged
+    bool ok = true;
+    ok &= cuda_ok(cudaMemcpyAsync(base + o_par, par.data(), sizeof(InfPar) * njobs, cudaMemcpyHostToDevice, st), "inflate par", __FILE__, __LINE__);
+    ok &= cuda_ok(cudaMemcpyAsync(base + o_tiles, tile_start.data(), 4 * ((size_t)njobs + 1), cudaMemcpyHostToDevice, st), "inflate tiles", __FILE__, __LINE__);
+    ok &= cuda_ok(cudaMemsetAsync(base + o_ctr, 0, 64, st), "inflate ctr", __FILE__, __LINE__);
+    ok &= cuda_ok(cudaMemsetAsync(base + o_slots, 0xff, 4 * slots_total, st), "inflate slots", __FILE__, __LINE__);
+    ok &= cuda_ok(cudaMemsetAsync(base + o_bitmap, 0, 4 * bitmap_total, st), "inflate bitmap", __FILE__, __LINE__);
+    if (!ok) return false;
+    InfPar* d_par = (InfPar*)(base + o_par);
+    uint32_t* d_ctr = (uint32_t*)(base + o_ctr);
+    uint2* d_work = (uint2*)(base + o_work);
+    uint2* d_vq = (uint2*)(base + o_vq);
+    const int persistent = sm_count() * 6;
+    infp_find_kernel<<<tiles, 256, 0, st>>>(d_jobs, d_par, (const uint32_t*)(base + o_tiles), njobs, d_vq, vq_cap, d_ctr);
+    infp_verify_kernel<<<sm_count() * 8, 128, 0, st>>>(d_jobs, d_par, d_vq, vq_cap, d_ctr);
+    infp_compact_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_par, njobs, d_work, d_ctr);
+    infp_count_kernel<<<persistent, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
+    infp_walk_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, njobs);
+    infp_write_kernel<<<persistent, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
+    infp_resolve_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, d_par, njobs);
+    inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs, d_par);
+    count_launch(8);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------

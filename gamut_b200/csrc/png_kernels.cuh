@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include "inflate.cuh"
+#include "common.h"
 
 namespace gb {
 
@@ -40,5 +41,12 @@ struct FinishJob {
     uint16_t tc16[3];
     uint8_t palette[1024];
 };
+
+// Scratch of one launch_inflate call; must stay alive until the stream has run the launch.
+struct InflateWork { DevBuf buf; };
+
+// h_jobs: host copy of the job table (sizes plan the scratch). Returns false when scratch allocation fails.
+bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cudaStream_t st, InflateWork& W);
+void set_inflate_mode(int m);
 
 } // namespace gb

@@ -127,6 +127,9 @@ int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint8_t* ou
 int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint32_t* in_lens,
                          uint8_t* const* out_dev, const uint32_t* out_caps, int parse_header,
                          uint32_t* out_lens_dev, int* statuses_dev, void* stream);
+/* Inflate engine selection for tests and profiling: 1 = block-parallel pipeline with the one-warp-per-stream
+ * decoder for whatever it does not accept (default), 0 = one warp per stream only. Results are identical. */
+void gb200_inflate_set_mode(int parallel);
 
 /* ---- JPEG: source/gamut/codecs/jpegload.d (jpgd port), baseline / extended-sequential Huffman ---- */
 /* decompress_jpeg_image_from_stream (jpegload.d:3720-3808) over a memory buffer. req_comps: -1 keep,

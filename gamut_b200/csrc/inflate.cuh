@@ -39,19 +39,34 @@ constexpr int INF_WARPS_PER_CTA = 4;
 struct InflateSmem {
     uint32_t lit_tab[1 << INF_LIT_BITS];
     uint32_t dist_tab[1 << INF_DIST_BITS];
-    uint32_t sym_entry[320];      // per-symbol decode entry (without code length)
-    uint16_t sorted[320];         // symbols sorted by (length, symbol) -- canonical order
-    uint16_t code_of[320];        // canonical code of each symbol
+    uint32_t sorted_entry[320];   // decode entry | code length, in canonical (length, symbol) order
     uint8_t  lens[320];           // code lengths: 0..287 lit/len, 288..319 distance
+    uint16_t rank[320];           // rank of a symbol among the symbols of its length (build scratch)
     uint16_t count[2][16];
     uint16_t first_code[2][16];
     uint16_t first_sym[2][16];
+    uint32_t lj_end[2][16];       // left-justified (15-bit) end of the codes of each length
     int      err;
 };
 
 // entry layout: [3:0] code length (0 = take the slow path), [7:4] extra-bit count,
 // [9:8] kind (0 literal, 1 length/distance base, 2 end-of-block, 3 invalid), [31:16] value/base
 __device__ __forceinline__ uint32_t inf_entry(int kind, int extra, int value) { return (uint32_t)(extra << 4) | (uint32_t)(kind << 8) | ((uint32_t)value << 16); }
+
+// decode entry (without code length) of symbol s; s >= 288: distance symbol s - 288 (RFC 1951 3.2.5)
+__device__ __forceinline__ uint32_t inf_sym_entry(int s)
+{
+    if (s < 256) return inf_entry(0, 0, s);
+    if (s == 256) return inf_entry(2, 0, 0);
+    if (s < 265) return inf_entry(1, 0, s - 257 + 3);
+    if (s < 285) { const int x = (s - 261) >> 2; return inf_entry(1, x, 3 + ((4 + ((s - 265) & 3)) << x)); }
+    if (s == 285) return inf_entry(1, 0, 258);
+    if (s < 288) return inf_entry(3, 0, 0);
+    const int d = s - 288;
+    if (d < 4) return inf_entry(1, 0, d + 1);
+    if (d < 30) { const int x = (d >> 1) - 1; return inf_entry(1, x, 1 + ((2 + (d & 1)) << x)); }
+    return inf_entry(3, 0, 0);
+}
 
 struct InflateReader {
     const uint32_t* words;   // input as aligned words
@@ -93,7 +108,8 @@ struct InflateReader {
 };
 
 // Builds decode tables for one code (which = 0 lit/len with n<=288 symbols at lens[0..], 1 distance
-// at lens[288..]). Warp-cooperative. Returns false on an over-subscribed code.
+// at lens[288..]). Warp-cooperative: ranks by __match_any_sync, 16-step canonical prefix on lane 0, table fill
+// by all lanes. Returns false on an over-subscribed code.
 __device__ inline bool inf_build(InflateSmem& S, int which, int n, int lane)
 {
     const int off = which ? 288 : 0;
@@ -102,12 +118,21 @@ __device__ inline bool inf_build(InflateSmem& S, int which, int n, int lane)
     for (int i = lane; i < (1 << FAST); i += 32) tab[i] = 0;
     if (lane < 16) S.count[which][lane] = 0;
     __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        const int l = s < n ? S.lens[off + s] : 0;
+        const uint32_t m = __match_any_sync(0xffffffffu, l);
+        const int before = S.count[which][l];
+        __syncwarp();
+        if (s < n) S.rank[off + s] = (uint16_t)(before + __popc(m & ((1u << lane) - 1)));
+        if ((int)(__ffs(m) - 1) == lane) S.count[which][l] = (uint16_t)(before + __popc(m));
+        __syncwarp();
+    }
     if (lane == 0) {
-        // canonical code assignment (serial: <= 288 symbols, once per block)
-        for (int s = 0; s < n; ++s) S.count[which][S.lens[off + s]]++;
         S.count[which][0] = 0;
         int code = 0, sym = 0, left = 1;
         bool over = false;
+        S.lj_end[which][0] = 0;
         for (int l = 1; l < 16; ++l) {
             left <<= 1;
             left -= S.count[which][l];
@@ -116,27 +141,22 @@ __device__ inline bool inf_build(InflateSmem& S, int which, int n, int lane)
             S.first_code[which][l] = (uint16_t)code;
             S.first_sym[which][l] = (uint16_t)sym;
             sym += S.count[which][l];
+            S.lj_end[which][l] = (uint32_t)(code + S.count[which][l]) << (15 - l);
         }
         S.err = over ? 1 : 0;
-        uint16_t next[16];
-        for (int l = 0; l < 16; ++l) next[l] = 0;
-        for (int s = 0; s < n; ++s) {
-            int l = S.lens[off + s];
-            if (l) {
-                int r = next[l]++;
-                S.code_of[off + s] = (uint16_t)(S.first_code[which][l] + r);
-                S.sorted[off + S.first_sym[which][l] + r] = (uint16_t)s;
-            }
-        }
     }
     __syncwarp();
     if (S.err) return false;
     for (int s = lane; s < n; s += 32) {
-        int l = S.lens[off + s];
-        if (l > 0 && l <= FAST) {
-            uint32_t rev = __brev((uint32_t)S.code_of[off + s]) >> (32 - l);
-            uint32_t e = S.sym_entry[off + s] | (uint32_t)l;
-            for (uint32_t k = rev; k < (1u << FAST); k += (1u << l)) tab[k] = e;
+        const int l = S.lens[off + s];
+        if (l > 0) {
+            const uint32_t r = S.rank[off + s];
+            const uint32_t e = inf_sym_entry(off + s) | (uint32_t)l;
+            S.sorted_entry[off + S.first_sym[which][l] + r] = e;
+            if (l <= FAST) {
+                const uint32_t rev = __brev((uint32_t)S.first_code[which][l] + r) >> (32 - l);
+                for (uint32_t k = rev; k < (1u << FAST); k += (1u << l)) tab[k] = e;
+            }
         }
     }
     __syncwarp();
@@ -144,40 +164,16 @@ __device__ inline bool inf_build(InflateSmem& S, int which, int n, int lane)
 }
 
 // Slow path: canonical decode of a code longer than FAST bits. Returns entry|len or 0 (invalid).
+// Codes of length l, left-justified to 15 bits, fill [lj_end[l-1], lj_end[l]).
 __device__ __forceinline__ uint32_t inf_slow(const InflateSmem& S, int which, uint32_t bits15, int FAST)
 {
-    const int off = which ? 288 : 0;
-    uint32_t rev = __brev(bits15) >> 17;   // 15 bits, first-read bit is the MSB
-    for (int l = FAST + 1; l <= 15; ++l) {
-        uint32_t c = rev >> (15 - l);
-        uint32_t d = c - S.first_code[which][l];
-        if (d < S.count[which][l]) {
-            int s = S.sorted[off + S.first_sym[which][l] + d];
-            return S.sym_entry[off + s] | (uint32_t)l;
-        }
-    }
-    return 0;
-}
-
-__device__ inline void inf_init_sym_entries(InflateSmem& S, int lane)
-{
-    // RFC 1951 3.2.5
-    for (int s = lane; s < 320; s += 32) {
-        uint32_t e;
-        if (s < 256) e = inf_entry(0, 0, s);
-        else if (s == 256) e = inf_entry(2, 0, 0);
-        else if (s < 265) e = inf_entry(1, 0, s - 257 + 3);
-        else if (s < 285) { int x = (s - 261) >> 2; int base = 3 + ((4 + ((s - 265) & 3)) << x); e = inf_entry(1, x, base); }
-        else if (s == 285) e = inf_entry(1, 0, 258);
-        else if (s < 288) e = inf_entry(3, 0, 0);
-        else {
-            int d = s - 288;
-            if (d < 4) e = inf_entry(1, 0, d + 1);
-            else if (d < 30) { int x = (d >> 1) - 1; int base = 1 + ((2 + (d & 1)) << x); e = inf_entry(1, x, base); }
-            else e = inf_entry(3, 0, 0);
-        }
-        S.sym_entry[s] = e;
-    }
+    const uint32_t rev = __brev(bits15) >> 17;   // 15 bits, first-read bit is the MSB
+    int l = FAST + 1;
+#pragma unroll
+    for (int k = 10; k < 15; ++k) if (k > FAST) l += rev >= S.lj_end[which][k];
+    if (rev >= S.lj_end[which][l]) return 0;
+    const uint32_t d = (rev - S.lj_end[which][l - 1]) >> (15 - l);
+    return S.sorted_entry[(which ? 288 : 0) + S.first_sym[which][l] + d];
 }
 
 // Reads the code tables of a Huffman block (btype 1: fixed, 2: dynamic; the 3 header bits are already
@@ -295,9 +291,6 @@ __device__ inline void inflate_stream(InflateJob& job, InflateSmem& S, int lane)
     uint32_t pos = 0;
     int status = INF_OK;
     uint32_t start = 0;
-
-    inf_init_sym_entries(S, lane);
-    __syncwarp();
 
     if (job.parse_header) {
         if (in_len < 2) { status = INF_DATA_ERROR; goto done; }

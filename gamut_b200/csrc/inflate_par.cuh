@@ -59,19 +59,29 @@ struct InfPar {
     uint32_t eligible;    // host: the fast path is attempted for this stream
 };
 
-// Independent bit reader of one lane.
+// Independent bit reader of one lane. The input is fetched as 16-byte vectors one vector ahead of use, so that the
+// load latency (the L1 is mostly shared memory here; a miss goes to L2) never sits on the decode chain.
 struct LaneReader {
-    const uint32_t* w; uint32_t nwords; uint64_t buf; int cnt; uint32_t widx;
-    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < nwords ? __ldg(w + i) : 0u; }
+    const uint4* v; uint32_t nvec; uint4 cur, nxt; uint64_t buf; int cnt; uint32_t widx;
+    __device__ __forceinline__ void bind(const InflateJob& J) { v = (const uint4*)J.in; nvec = (J.in_len + 16) >> 4; }
+    __device__ __forceinline__ uint4 ldv(uint32_t i) const { return i < nvec ? __ldg(v + i) : make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ uint32_t word()
+    {
+        const uint32_t k = widx & 3;
+        const uint32_t w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+        ++widx;
+        if ((widx & 3) == 0) { cur = nxt; nxt = ldv((widx >> 2) + 1); }
+        return w;
+    }
     __device__ __forceinline__ void seek(uint32_t bitpos)
     {
         widx = bitpos >> 5;
-        const uint32_t a = ld(widx), b = ld(widx + 1);
-        widx += 2;
+        cur = ldv(widx >> 2); nxt = ldv((widx >> 2) + 1);
+        const uint32_t a = word(), b = word();
         buf = (((uint64_t)b << 32) | a) >> (bitpos & 31);
         cnt = 64 - (int)(bitpos & 31);
     }
-    __device__ __forceinline__ void refill() { if (cnt <= 32) { buf |= (uint64_t)ld(widx) << cnt; cnt += 32; ++widx; } }
+    __device__ __forceinline__ void refill() { if (cnt <= 32) { buf |= (uint64_t)word() << cnt; cnt += 32; } }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1); }
     __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
     __device__ __forceinline__ uint32_t get(int n) { uint32_t v = peek(n); drop(n); return v; }
@@ -103,55 +113,82 @@ struct LaneWriter {
     __device__ __forceinline__ void skip(uint32_t n) { off += n; acc = 0; k0 = off & 3; }
 };
 
-// Decodes lit/len units from bit `start` while the position is below `limit`; stops after an end-of-block symbol.
-template <bool WRITE>
-__device__ __forceinline__ void lane_decode(const InflateSmem& S, LaneReader& R, uint32_t start, uint32_t limit, LaneRes& res,
-                                            uint8_t* out, uint32_t off, uint32_t* bitmap, uint32_t* fail)
+__device__ __forceinline__ void infp_cp4(uint32_t* smem_dst, const uint32_t* gsrc, uint32_t src_size)
 {
-    R.seek(start);
-    uint32_t nbytes = 0, flags = 0;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gsrc), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void infp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void infp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int INFP_RING = 16;       // input words per lane staged in shared memory
+
+// Decodes from bit `start` while the position is below `limit` (checked between lit/len units); stops after an
+// end-of-block symbol. One Huffman symbol per loop iteration, literal/length and distance symbols through the same
+// code path (the two tables are adjacent), so the 32 lanes of a warp stay converged although each decodes its own
+// sub-chunk. The lane's input words are staged in a shared-memory ring (column `col`, word k at col[(k%16)*32]: bank
+// = lane, conflict-free) by 4-byte cp.async issued at least four iterations ahead of use.
+template <bool WRITE>
+__device__ __forceinline__ void lane_decode(const InflateSmem& S, uint32_t* col, const InflateJob& J, uint32_t start, uint32_t limit,
+                                            LaneRes& res, uint8_t* out, uint32_t off, uint32_t* bitmap, uint32_t* fail)
+{
+    const uint32_t* words = (const uint32_t*)J.in;
+    const uint32_t nwords = (J.in_len + 8 + 3) >> 2;
+    uint32_t pos = start;
+    uint32_t fetched = (pos >> 5) & ~3u;
+    auto fetch4 = [&]() {
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t idx = fetched + q;
+            infp_cp4(col + (idx & (INFP_RING - 1)) * 32, words + (idx < nwords ? idx : 0), idx < nwords ? 4u : 0u);
+        }
+        fetched += 4;
+    };
+    fetch4(); fetch4(); fetch4();
+    infp_commit();
+    infp_wait<0>();
+    const uint32_t* tab = S.lit_tab;                        // dist_tab follows at +1024
+    uint32_t nbytes = 0, flags = 0, want_dist = 0, mlen = 0;
     LaneWriter W;
     if (WRITE) W.init(out, off);
-    while (R.pos() < limit) {
-        R.refill();
-        uint32_t e = S.lit_tab[(uint32_t)R.buf & ((1u << INF_LIT_BITS) - 1)];
+    while (pos < limit || want_dist) {
+        const uint32_t wi = pos >> 5;
+        if (fetched - wi <= 8) fetch4();
+        infp_commit();
+        infp_wait<4>();
+        const uint32_t w0 = col[(wi & (INFP_RING - 1)) * 32], w1 = col[((wi + 1) & (INFP_RING - 1)) * 32];
+        const uint32_t bits = __funnelshift_r(w0, w1, pos);
+        uint32_t e = tab[(want_dist ? (1u << INF_LIT_BITS) : 0u) + (bits & (want_dist ? (1u << INF_DIST_BITS) - 1 : (1u << INF_LIT_BITS) - 1))];
         if ((e & 15) == 0) {
-            e = inf_slow(S, 0, (uint32_t)R.buf & 0x7fffu, INF_LIT_BITS);
+            e = inf_slow(S, (int)want_dist, bits & 0x7fffu, want_dist ? INF_DIST_BITS : INF_LIT_BITS);
             if (e == 0) { flags = 2; break; }
         }
-        R.drop(e & 15);
-        const uint32_t kind = (e >> 8) & 3;
-        if (kind == 0) {
-            ++nbytes;
-            if (WRITE) W.put(e >> 16);
-            continue;
-        }
-        if (kind == 2) { flags = 1; break; }
+        const uint32_t len = e & 15, xb = (e >> 4) & 15, kind = (e >> 8) & 3;
+        const uint32_t val = (e >> 16) + ((bits >> len) & ((1u << xb) - 1));
+        pos += len + xb;
         if (kind == 3) { flags = 2; break; }
-        const uint32_t len = (e >> 16) + R.get((e >> 4) & 15);
-        R.refill();
-        uint32_t de = S.dist_tab[(uint32_t)R.buf & ((1u << INF_DIST_BITS) - 1)];
-        if ((de & 15) == 0) {
-            de = inf_slow(S, 1, (uint32_t)R.buf & 0x7fffu, INF_DIST_BITS);
-            if (de == 0) { flags = 2; break; }
-        }
-        R.drop(de & 15);
-        if (((de >> 8) & 3) == 3) { flags = 2; break; }
-        const uint32_t dist = (de >> 16) + R.get((de >> 4) & 15);
-        nbytes += len;
-        if (WRITE) {
-            W.flush();
-            const uint32_t at = W.off;
-            if (dist > at) *fail = 1;                       // reaches before the start of the output
-            out[at] = (uint8_t)(len - 3);
-            out[at + 1] = (uint8_t)((dist - 1) & 255);
-            out[at + 2] = (uint8_t)((dist - 1) >> 8);
-            atomicOr(bitmap + (at >> 5), 1u << (at & 31));
-            W.skip(len);
-        }
+        if (want_dist) {
+            want_dist = 0;
+            if (WRITE) {
+                W.flush();
+                const uint32_t at = W.off;
+                if (val > at) *fail = 1;                    // reaches before the start of the output
+                out[at] = (uint8_t)(mlen - 3);
+                out[at + 1] = (uint8_t)((val - 1) & 255);
+                out[at + 2] = (uint8_t)((val - 1) >> 8);
+                atomicOr(bitmap + (at >> 5), 1u << (at & 31));
+                W.skip(mlen);
+            }
+        } else if (kind == 0) {
+            ++nbytes;
+            if (WRITE) W.put(val);
+        } else if (kind == 1) {
+            nbytes += val; mlen = val; want_dist = 1;
+        } else { flags = 1; break; }
     }
+    infp_wait<0>();
     if (WRITE) W.flush();
-    res.end = R.pos(); res.nbytes = nbytes; res.flags = flags;
+    res.end = pos; res.nbytes = nbytes; res.flags = flags;
 }
 
 __device__ __forceinline__ void infp_reader(InflateReader& R, const InflateJob& J, int lane)
@@ -238,7 +275,7 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
         const uint2 c = vq[q];
         const InflateJob& J = jobs[c.x];
         LaneReader R;
-        R.w = (const uint32_t*)J.in; R.nwords = (J.in_len + 8 + 3) >> 2;
+        R.bind(J);
         R.seek(c.y + 3);
         const int nlit = (int)R.get(5) + 257, ndist = (int)R.get(5) + 1, ncl = (int)R.get(4) + 4;
         uint32_t cl_lens_lo = 0, cl_lens_hi = 0;
@@ -313,6 +350,7 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
                 const uint32_t wgt = 32768u >> val;
                 const int a = i < nlit ? min(rep, nlit - i) : 0, b = rep - a;
                 kl += (uint32_t)a * wgt; kd += (uint32_t)b * wgt; nd += b;
+                if (kl > 32768u || kd > 32768u) { good = false; break; }     // over-subscribed: most random headers end here
                 if (i <= 256 && 256 < i + rep) has256 = true;
             }
             i += rep; prev = val;
@@ -376,10 +414,9 @@ __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
 infp_count_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32_t* ctr)
 {
     __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
+    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     InflateSmem& S = smem[warp];
-    inf_init_sym_entries(S, lane);
-    __syncwarp();
     const uint32_t nwork = ctr[INFP_CTR_WORK];
     for (;;) {
         uint32_t i = 0;
@@ -401,11 +438,10 @@ infp_count_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
         const uint32_t body = infp_bitpos(R), e = B.seg_end;
         uint32_t g, limit;
         infp_chunks(body, e, lane, g, limit);
-        LaneReader LR;
-        LR.w = R.words; LR.nwords = R.nwords;
+        uint32_t* col = &ring[warp][0][lane];
         uint32_t start = lane == 0 ? body : g;
         LaneRes res; res.end = start; res.nbytes = 0; res.flags = 0;
-        if (start != INFP_NONE) lane_decode<false>(S, LR, start, limit, res, nullptr, 0, nullptr, nullptr);
+        if (start != INFP_NONE) lane_decode<false>(S, col, J, start, limit, res, nullptr, 0, nullptr, nullptr);
         for (int round = 0; round < 40; ++round) {
             const uint32_t pend = __shfl_up_sync(0xffffffffu, res.end, 1);
             const uint32_t pfl = __shfl_up_sync(0xffffffffu, res.flags, 1);
@@ -417,7 +453,7 @@ infp_count_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
             if (changed) {
                 start = ns;
                 res.end = start; res.nbytes = 0; res.flags = 0;
-                if (start != INFP_NONE) lane_decode<false>(S, LR, start, limit, res, nullptr, 0, nullptr, nullptr);
+                if (start != INFP_NONE) lane_decode<false>(S, col, J, start, limit, res, nullptr, 0, nullptr, nullptr);
             }
         }
         const bool alive = start != INFP_NONE;
@@ -449,6 +485,7 @@ __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
 infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
 {
     __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
+    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * INF_WARPS_PER_CTA + warp;
     if (j >= njobs) return;
@@ -459,7 +496,6 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
     const uint32_t in_bits = P.in_bits, cap = J.out_cap;
     uint32_t pos = 0, out_off = 0;
     bool ok = false;
-    bool tables_ready = false;
     if (J.parse_header) {
         if (J.in_len < 2) return;
         const uint32_t cmf = J.in[0], flg = J.in[1];
@@ -504,15 +540,13 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
         } else if (btype == 3) {
             break;
         } else {
-            if (!tables_ready) { inf_init_sym_entries(S, lane); tables_ready = true; }
             __syncwarp();
             if (!inf_setup_tables(R, S, lane, btype)) break;
             const uint32_t body = infp_bitpos(R);
-            LaneReader LR;
-            LR.w = R.words; LR.nwords = R.nwords;
+            uint32_t* col = &ring[warp][0][lane];
             LaneRes res; res.end = body; res.nbytes = 0; res.flags = 0;
             const uint32_t lim = in_bits + 64 > in_bits ? in_bits + 64 : 0xffffffffu;
-            if (lane == 0) lane_decode<false>(S, LR, body, lim, res, nullptr, 0, nullptr, nullptr);
+            if (lane == 0) lane_decode<false>(S, col, J, body, lim, res, nullptr, 0, nullptr, nullptr);
             res.end = __shfl_sync(0xffffffffu, res.end, 0);
             res.nbytes = __shfl_sync(0xffffffffu, res.nbytes, 0);
             res.flags = __shfl_sync(0xffffffffu, res.flags, 0);
@@ -520,7 +554,7 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
             if (res.nbytes > cap - out_off) break;
             if (lane == 0) {
                 LaneRes r2;
-                lane_decode<true>(S, LR, body, lim, r2, J.out, out_off, P.bitmap, &P.fail);
+                lane_decode<true>(S, col, J, body, lim, r2, J.out, out_off, P.bitmap, &P.fail);
             }
             __syncwarp();
             out_off += res.nbytes;
@@ -541,10 +575,9 @@ __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
 infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32_t* ctr)
 {
     __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
+    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     InflateSmem& S = smem[warp];
-    inf_init_sym_entries(S, lane);
-    __syncwarp();
     const uint32_t nwork = ctr[INFP_CTR_WORK];
     for (;;) {
         uint32_t i = 0;
@@ -572,10 +605,8 @@ infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
         for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
         const uint32_t off = B.out_off + incl - nb;
         if (start != INFP_NONE) {
-            LaneReader LR;
-            LR.w = R.words; LR.nwords = R.nwords;
             LaneRes res;
-            lane_decode<true>(S, LR, start, limit, res, J.out, off, P.bitmap, &P.fail);
+            lane_decode<true>(S, &ring[warp][0][lane], J, start, limit, res, J.out, off, P.bitmap, &P.fail);
             if (res.nbytes != nb) P.fail = 1;
         }
         __syncwarp();

@@ -47,7 +47,7 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
         memset(&P, 0, sizeof(P));
         tile_start[j] = tiles;
         const bool el = g_inflate_mode == 1 && J.in_len >= 2048 && J.in_len < (1u << 28) && J.out_cap >= 64 &&
-                        J.out_cap < 0xfffffff0u && (((uintptr_t)J.out) & 3) == 0 && (((uintptr_t)J.in) & 3) == 0;
+                        J.out_cap < 0xfffffff0u && (((uintptr_t)J.out) & 3) == 0 && (((uintptr_t)J.in) & 15) == 0;
         if (!el) continue;
         P.eligible = 1;
         P.in_bits = J.in_len * 8;
@@ -95,7 +95,7 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
     uint32_t* d_ctr = (uint32_t*)(base + o_ctr);
     uint2* d_work = (uint2*)(base + o_work);
     uint2* d_vq = (uint2*)(base + o_vq);
-    const int persistent = sm_count() * 6;
+    const int persistent = sm_count() * 5;
     infp_find_kernel<<<tiles, 256, 0, st>>>(d_jobs, d_par, (const uint32_t*)(base + o_tiles), njobs, d_vq, vq_cap, d_ctr);
     infp_verify_kernel<<<sm_count() * 8, 128, 0, st>>>(d_jobs, d_par, d_vq, vq_cap, d_ctr);
     infp_compact_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_par, njobs, d_work, d_ctr);

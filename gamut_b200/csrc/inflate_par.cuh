@@ -122,16 +122,32 @@ __device__ __forceinline__ void infp_commit() { asm volatile("cp.async.commit_gr
 template <int N> __device__ __forceinline__ void infp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 constexpr int INFP_RING = 16;       // input words per lane staged in shared memory
+constexpr int INFP_MARK_WORDS = 8;  // self-synchronisation window: 256 bits after a lane's guessed start
+constexpr int INFP_WARPS = 3;       // warps per CTA of the count / walk / write kernels
+
+struct InfpWarp {                   // shared memory of one warp
+    InflateSmem S;
+    uint32_t ring[INFP_RING][32];
+    uint32_t marks[INFP_MARK_WORDS][32];
+};
+
+// Decode modes: PLAIN counts; MARK also records the unit boundaries inside the window after `mark_base`;
+// MERGE stops at the first unit boundary that is recorded in the window; STOPAT stops exactly at `stop_at`.
+enum { LD_PLAIN = 0, LD_MARK = 1, LD_MERGE = 2, LD_STOPAT = 3, LD_WRITE = 4 };
 
 // Decodes from bit `start` while the position is below `limit` (checked between lit/len units); stops after an
 // end-of-block symbol. One Huffman symbol per loop iteration, literal/length and distance symbols through the same
 // code path (the two tables are adjacent), so the 32 lanes of a warp stay converged although each decodes its own
 // sub-chunk. The lane's input words are staged in a shared-memory ring (column `col`, word k at col[(k%16)*32]: bank
-// = lane, conflict-free) by 4-byte cp.async issued at least four iterations ahead of use.
-template <bool WRITE>
+// = lane, conflict-free) by 4-byte cp.async; every lane tops its ring up in the same iteration (one in four), so the
+// refill is a warp-uniform branch, and the data is needed no earlier than four iterations after it was requested.
+// res.flags: 1 end-of-block, 2 invalid code, 4 (MERGE) merged with the recorded path at res.end.
+template <int MODE>
 __device__ __forceinline__ void lane_decode(const InflateSmem& S, uint32_t* col, const InflateJob& J, uint32_t start, uint32_t limit,
-                                            LaneRes& res, uint8_t* out, uint32_t off, uint32_t* bitmap, uint32_t* fail)
+                                            LaneRes& res, uint32_t* mcol, uint32_t mark_base, uint32_t stop_at,
+                                            uint8_t* out, uint32_t off, uint32_t* bitmap, uint32_t* fail)
 {
+    constexpr bool WRITE = MODE == LD_WRITE;
     const uint32_t* words = (const uint32_t*)J.in;
     const uint32_t nwords = (J.in_len + 8 + 3) >> 2;
     uint32_t pos = start;
@@ -151,11 +167,22 @@ __device__ __forceinline__ void lane_decode(const InflateSmem& S, uint32_t* col,
     uint32_t nbytes = 0, flags = 0, want_dist = 0, mlen = 0;
     LaneWriter W;
     if (WRITE) W.init(out, off);
-    while (pos < limit || want_dist) {
+    for (uint32_t it = 0; pos < limit || want_dist; ++it) {
         const uint32_t wi = pos >> 5;
-        if (fetched - wi <= 8) fetch4();
-        infp_commit();
-        infp_wait<4>();
+        if ((it & 3) == 0) {
+            if (fetched - wi <= 8) fetch4();
+            infp_commit();
+            infp_wait<1>();
+        }
+        if (MODE == LD_MARK || MODE == LD_MERGE) {
+            const uint32_t d = pos - mark_base;
+            if (!want_dist && d < INFP_MARK_WORDS * 32) {
+                uint32_t* m = mcol + (d >> 5) * 32;
+                if (MODE == LD_MARK) *m |= 1u << (d & 31);
+                else if ((*m >> (d & 31)) & 1u) { flags = 4; break; }
+            }
+        }
+        if (MODE == LD_STOPAT) { if (!want_dist && pos == stop_at) break; }
         const uint32_t w0 = col[(wi & (INFP_RING - 1)) * 32], w1 = col[((wi + 1) & (INFP_RING - 1)) * 32];
         const uint32_t bits = __funnelshift_r(w0, w1, pos);
         uint32_t e = tab[(want_dist ? (1u << INF_LIT_BITS) : 0u) + (bits & (want_dist ? (1u << INF_DIST_BITS) - 1 : (1u << INF_LIT_BITS) - 1))];
@@ -409,14 +436,85 @@ __device__ __forceinline__ void infp_chunks(uint32_t body, uint32_t e, int lane,
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4. count
-__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+// 4. count. Block B of stream J with its segment end B.seg_end: builds the tables, finds every lane's true start and
+// byte count. Round 0 decodes every sub-chunk from its guessed start and records the unit boundaries of the first 256
+// bits; later rounds decode from the previous lane's end only until they land on a recorded boundary (Huffman codes
+// self-synchronise within a few symbols), and take the rest of the sub-chunk from round 0.
+__device__ inline void infp_count_block(const InflateJob& J, InfBlock& B, InfpWarp& M, int lane)
+{
+    InflateSmem& S = M.S;
+    InflateReader R;
+    infp_reader(R, J, lane);
+    infp_seek_bit(R, B.bitpos);
+    const uint32_t bfinal = R.get(1), btype = R.get(2);
+    __syncwarp();
+    if (btype != 2 || !inf_setup_tables(R, S, lane, btype)) {
+        if (lane == 0) B.status = BLK_ERR;
+        return;
+    }
+    const uint32_t body = infp_bitpos(R), e = B.seg_end;
+    uint32_t g, limit;
+    infp_chunks(body, e, lane, g, limit);
+    uint32_t* col = &M.ring[0][lane];
+    uint32_t* mcol = &M.marks[0][lane];
+#pragma unroll
+    for (int k = 0; k < INFP_MARK_WORDS; ++k) mcol[k * 32] = 0;
+    const uint32_t g0 = lane == 0 ? body : g;              // round-0 start
+    LaneRes r0; r0.end = g0; r0.nbytes = 0; r0.flags = 0;
+    if (g0 != INFP_NONE) lane_decode<LD_MARK>(S, col, J, g0, limit, r0, mcol, g0, 0, nullptr, 0, nullptr, nullptr);
+    uint32_t start = g0;
+    LaneRes res = r0;
+    for (int round = 0; round < 40; ++round) {
+        const uint32_t pend = __shfl_up_sync(0xffffffffu, res.end, 1);
+        const uint32_t pfl = __shfl_up_sync(0xffffffffu, res.flags, 1);
+        const uint32_t pst = __shfl_up_sync(0xffffffffu, start, 1);
+        uint32_t ns = (pst != INFP_NONE && pfl == 0 && pend < e) ? pend : INFP_NONE;
+        if (lane == 0) ns = body;
+        const bool changed = ns != start;
+        if (!__any_sync(0xffffffffu, changed)) break;
+        if (changed) {
+            start = ns;
+            res.end = start; res.nbytes = 0; res.flags = 0;
+            if (start == g0) res = r0;
+            else if (start != INFP_NONE) {
+                LaneRes a;
+                lane_decode<LD_MERGE>(S, col, J, start, limit, a, mcol, g0, 0, nullptr, 0, nullptr, nullptr);
+                if (a.flags == 4) {
+                    // merged with the round-0 path at a.end: bytes = mine up to there + round 0's from there on
+                    LaneRes c;
+                    lane_decode<LD_STOPAT>(S, col, J, g0, limit, c, nullptr, 0, a.end, nullptr, 0, nullptr, nullptr);
+                    res.end = r0.end; res.flags = r0.flags; res.nbytes = a.nbytes + (r0.nbytes - c.nbytes);
+                } else res = a;
+            }
+        }
+    }
+    const bool alive = start != INFP_NONE;
+    const uint32_t stopm = __ballot_sync(0xffffffffu, alive && res.flags != 0);
+    const uint32_t alivem = __ballot_sync(0xffffffffu, alive);
+    int status = BLK_NOEOB;
+    int last = 31 - __clz(alivem);            // alive lanes form a prefix (lane 0 is always alive)
+    if (stopm) {
+        last = __ffs(stopm) - 1;
+        status = (__shfl_sync(0xffffffffu, res.flags, last) == 1) ? BLK_EOB : BLK_ERR;
+    }
+    uint32_t nb = lane <= last ? res.nbytes : 0;
+    uint32_t tot = nb;
+    bool ovf = false;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, tot, d); ovf |= (tot + o) < tot; tot += o; }
+    if (__any_sync(0xffffffffu, ovf) && status == BLK_EOB) status = BLK_ERR;
+    B.lane_start[lane] = lane <= last ? start : INFP_NONE;
+    B.lane_bytes[lane] = nb;
+    const uint32_t endb = __shfl_sync(0xffffffffu, res.end, last);
+    if (lane == 0) { B.end_bit = endb; B.nbytes = tot; B.bfinal = (uint8_t)bfinal; B.status = (uint8_t)status; }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(INFP_WARPS * 32)
 infp_count_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32_t* ctr)
 {
-    __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
-    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
+    __shared__ InfpWarp smem[INFP_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    InflateSmem& S = smem[warp];
     const uint32_t nwork = ctr[INFP_CTR_WORK];
     for (;;) {
         uint32_t i = 0;
@@ -424,74 +522,23 @@ infp_count_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= nwork) break;
         const uint2 wk = work[i];
-        const InflateJob& J = jobs[wk.x];
-        InfBlock& B = par[wk.x].blocks[wk.y];
-        InflateReader R;
-        infp_reader(R, J, lane);
-        infp_seek_bit(R, B.bitpos);
-        const uint32_t bfinal = R.get(1), btype = R.get(2);
-        __syncwarp();
-        if (btype != 2 || !inf_setup_tables(R, S, lane, btype)) {
-            if (lane == 0) B.status = BLK_ERR;
-            continue;
-        }
-        const uint32_t body = infp_bitpos(R), e = B.seg_end;
-        uint32_t g, limit;
-        infp_chunks(body, e, lane, g, limit);
-        uint32_t* col = &ring[warp][0][lane];
-        uint32_t start = lane == 0 ? body : g;
-        LaneRes res; res.end = start; res.nbytes = 0; res.flags = 0;
-        if (start != INFP_NONE) lane_decode<false>(S, col, J, start, limit, res, nullptr, 0, nullptr, nullptr);
-        for (int round = 0; round < 40; ++round) {
-            const uint32_t pend = __shfl_up_sync(0xffffffffu, res.end, 1);
-            const uint32_t pfl = __shfl_up_sync(0xffffffffu, res.flags, 1);
-            const uint32_t pst = __shfl_up_sync(0xffffffffu, start, 1);
-            uint32_t ns = (pst != INFP_NONE && pfl == 0 && pend < e) ? pend : INFP_NONE;
-            if (lane == 0) ns = body;
-            const bool changed = ns != start;
-            if (!__any_sync(0xffffffffu, changed)) break;
-            if (changed) {
-                start = ns;
-                res.end = start; res.nbytes = 0; res.flags = 0;
-                if (start != INFP_NONE) lane_decode<false>(S, col, J, start, limit, res, nullptr, 0, nullptr, nullptr);
-            }
-        }
-        const bool alive = start != INFP_NONE;
-        const uint32_t stopm = __ballot_sync(0xffffffffu, alive && res.flags != 0);
-        const uint32_t alivem = __ballot_sync(0xffffffffu, alive);
-        int status = BLK_NOEOB;
-        int last = 31 - __clz(alivem);            // alive lanes form a prefix (lane 0 is always alive)
-        if (stopm) {
-            last = __ffs(stopm) - 1;
-            status = (__shfl_sync(0xffffffffu, res.flags, last) == 1) ? BLK_EOB : BLK_ERR;
-        }
-        uint32_t nb = lane <= last ? res.nbytes : 0;
-        uint32_t tot = nb;
-        bool ovf = false;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, tot, d); ovf |= (tot + o) < tot; tot += o; }
-        if (__any_sync(0xffffffffu, ovf) && status == BLK_EOB) status = BLK_ERR;
-        B.lane_start[lane] = lane <= last ? start : INFP_NONE;
-        B.lane_bytes[lane] = nb;
-        const uint32_t endb = __shfl_sync(0xffffffffu, res.end, last);
-        if (lane == 0) { B.end_bit = endb; B.nbytes = tot; B.bfinal = (uint8_t)bfinal; B.status = (uint8_t)status; }
-        __syncwarp();
+        infp_count_block(jobs[wk.x], par[wk.x].blocks[wk.y], smem[warp], lane);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // 5. walk
-__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(INFP_WARPS * 32)
 infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
 {
-    __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
-    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
+    __shared__ InfpWarp smem[INFP_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * INF_WARPS_PER_CTA + warp;
+    const int j = blockIdx.x * INFP_WARPS + warp;
     if (j >= njobs) return;
     InfPar& P = par[j];
     if (!P.eligible) return;
-    InflateSmem& S = smem[warp];
+    InflateSmem& S = smem[warp].S;
+    uint32_t* col = &smem[warp].ring[0][lane];
     const InflateJob J = jobs[j];
     const uint32_t in_bits = P.in_bits, cap = J.out_cap;
     uint32_t pos = 0, out_off = 0;
@@ -510,15 +557,25 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
         const uint32_t bi = slot < P.nslots ? P.slots[slot] : INFP_NONE;
         if (bi < P.nblocks) {
             InfBlock& B = P.blocks[bi];
-            if (B.bitpos == pos && B.status == BLK_EOB) {
-                const uint32_t nb = B.nbytes;
-                if (nb > cap - out_off) break;
-                const uint32_t e = B.end_bit;
-                const uint32_t fin = B.bfinal;
-                if (lane == 0) { B.out_off = out_off; B.is_true = 1; }
-                out_off += nb; pos = e;
-                if (fin) { ok = true; break; }
-                continue;
+            if (B.bitpos == pos) {
+                // a false candidate inside this block cut its segment short: count it again with a later segment end
+                for (uint32_t k = bi + 2; B.status == BLK_NOEOB && k <= bi + 4 && k <= P.nblocks; ++k) {
+                    __syncwarp();
+                    if (lane == 0) B.seg_end = k < P.nblocks ? P.blocks[k].bitpos : in_bits;
+                    __syncwarp();
+                    infp_count_block(J, B, smem[warp], lane);
+                }
+                if (B.status == BLK_EOB) {
+                    const uint32_t nb = B.nbytes;
+                    if (nb > cap - out_off) break;
+                    const uint32_t e = B.end_bit;
+                    const uint32_t fin = B.bfinal;
+                    __syncwarp();
+                    if (lane == 0) { B.out_off = out_off; B.is_true = 1; }
+                    out_off += nb; pos = e;
+                    if (fin) { ok = true; break; }
+                    continue;
+                }
             }
         }
         // not a counted candidate: decode this block here
@@ -543,10 +600,9 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
             __syncwarp();
             if (!inf_setup_tables(R, S, lane, btype)) break;
             const uint32_t body = infp_bitpos(R);
-            uint32_t* col = &ring[warp][0][lane];
             LaneRes res; res.end = body; res.nbytes = 0; res.flags = 0;
             const uint32_t lim = in_bits + 64 > in_bits ? in_bits + 64 : 0xffffffffu;
-            if (lane == 0) lane_decode<false>(S, col, J, body, lim, res, nullptr, 0, nullptr, nullptr);
+            if (lane == 0) lane_decode<LD_PLAIN>(S, col, J, body, lim, res, nullptr, 0, 0, nullptr, 0, nullptr, nullptr);
             res.end = __shfl_sync(0xffffffffu, res.end, 0);
             res.nbytes = __shfl_sync(0xffffffffu, res.nbytes, 0);
             res.flags = __shfl_sync(0xffffffffu, res.flags, 0);
@@ -554,7 +610,7 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
             if (res.nbytes > cap - out_off) break;
             if (lane == 0) {
                 LaneRes r2;
-                lane_decode<true>(S, col, J, body, lim, r2, J.out, out_off, P.bitmap, &P.fail);
+                lane_decode<LD_WRITE>(S, col, J, body, lim, r2, nullptr, 0, 0, J.out, out_off, P.bitmap, &P.fail);
             }
             __syncwarp();
             out_off += res.nbytes;
@@ -571,13 +627,12 @@ infp_walk_kernel(InflateJob* jobs, InfPar* par, int njobs)
 
 // ---------------------------------------------------------------------------------------------
 // 6. write
-__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(INFP_WARPS * 32)
 infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32_t* ctr)
 {
-    __shared__ InflateSmem smem[INF_WARPS_PER_CTA];
-    __shared__ uint32_t ring[INF_WARPS_PER_CTA][INFP_RING][32];
+    __shared__ InfpWarp smem[INFP_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    InflateSmem& S = smem[warp];
+    InflateSmem& S = smem[warp].S;
     const uint32_t nwork = ctr[INFP_CTR_WORK];
     for (;;) {
         uint32_t i = 0;
@@ -606,7 +661,7 @@ infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
         const uint32_t off = B.out_off + incl - nb;
         if (start != INFP_NONE) {
             LaneRes res;
-            lane_decode<true>(S, &ring[warp][0][lane], J, start, limit, res, J.out, off, P.bitmap, &P.fail);
+            lane_decode<LD_WRITE>(S, &smem[warp].ring[0][lane], J, start, limit, res, nullptr, 0, 0, J.out, off, P.bitmap, &P.fail);
             if (res.nbytes != nb) P.fail = 1;
         }
         __syncwarp();

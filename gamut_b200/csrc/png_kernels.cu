@@ -95,13 +95,13 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
     uint32_t* d_ctr = (uint32_t*)(base + o_ctr);
     uint2* d_work = (uint2*)(base + o_work);
     uint2* d_vq = (uint2*)(base + o_vq);
-    const int persistent = sm_count() * 5;
+    const int persistent = sm_count() * 6;
     infp_find_kernel<<<tiles, 256, 0, st>>>(d_jobs, d_par, (const uint32_t*)(base + o_tiles), njobs, d_vq, vq_cap, d_ctr);
     infp_verify_kernel<<<sm_count() * 8, 128, 0, st>>>(d_jobs, d_par, d_vq, vq_cap, d_ctr);
     infp_compact_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_par, njobs, d_work, d_ctr);
-    infp_count_kernel<<<persistent, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
-    infp_walk_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, njobs);
-    infp_write_kernel<<<persistent, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
+    infp_count_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
+    infp_walk_kernel<<<(njobs + INFP_WARPS - 1) / INFP_WARPS, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, njobs);
+    infp_write_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
     infp_resolve_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, d_par, njobs);
     inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs, d_par);
     count_launch(8);

@@ -37,7 +37,7 @@ constexpr uint32_t INFP_SLOT_BITS = 1024;
 constexpr uint32_t INFP_FINAL_WINDOW = 1u << 19;    // BFINAL=1 headers are searched only this close to the end (bits)
 constexpr uint32_t INFP_MIN_CHUNK = 256;            // minimum sub-chunk (bits)
 constexpr uint32_t INFP_TILE_WORDS = 1024;          // input words per CTA of the find kernel
-enum { INFP_CTR_WORK = 0, INFP_CTR_A = 1, INFP_CTR_B = 2, INFP_CTR_Q = 3 };
+enum { INFP_CTR_WORK = 0, INFP_CTR_A = 1, INFP_CTR_B = 2, INFP_CTR_Q = 3, INFP_CTR_Q2 = 4 };
 enum { BLK_NEW = 0, BLK_EOB = 1, BLK_NOEOB = 2, BLK_ERR = 3 };
 
 struct InfBlock {
@@ -90,27 +90,37 @@ struct LaneReader {
 
 struct LaneRes { uint32_t end, nbytes, flags; };     // flags: 1 end-of-block seen, 2 invalid code
 
-// Output side of one lane in write mode: literals are gathered into aligned 32-bit words.
+// Output side of one lane in write mode. Literals (and the 3-byte record of a match) are gathered into aligned 32-bit
+// words. The bytes of a match after its record are a hole that the resolve pass overwrites, so they may receive
+// anything: once a hole has crossed into a new word the lane owns every byte of that word that matters, and all
+// stores but those of the first and last word of the lane's region are full-word stores.
 struct LaneWriter {
     uint8_t* out; uint32_t off, acc, k0;
     __device__ __forceinline__ void init(uint8_t* o, uint32_t at) { out = o; off = at; acc = 0; k0 = at & 3; }
+    __device__ __forceinline__ void store_word(uint32_t base, uint32_t e)        // bytes [k0, e) of the word at base
+    {
+        if (k0 == 0) *(uint32_t*)(out + base) = acc;
+        else for (uint32_t q = k0; q < e; ++q) out[base + q] = (uint8_t)(acc >> (8 * q));
+    }
     __device__ __forceinline__ void put(uint32_t b)
     {
         acc |= b << (8 * (off & 3));
         ++off;
-        if ((off & 3) == 0) {
-            if (k0 == 0) *(uint32_t*)(out + off - 4) = acc;
-            else for (uint32_t q = k0; q < 4; ++q) out[off - 4 + q] = (uint8_t)(acc >> (8 * q));
-            acc = 0; k0 = 0;
-        }
+        if ((off & 3) == 0) { store_word(off - 4, 4); acc = 0; k0 = 0; }
     }
-    __device__ __forceinline__ void flush()
+    __device__ __forceinline__ void skip(uint32_t n)
+    {
+        const uint32_t e = off & 3;
+        if (n < 4 - e) { off += n; return; }                 // the hole ends inside the current word
+        if (e) store_word(off - e, 4);
+        off += n; acc = 0; k0 = 0;
+    }
+    __device__ __forceinline__ void flush()                  // end of the lane's region: only bytes below off are mine
     {
         const uint32_t e = off & 3, base = off & ~3u;
         for (uint32_t q = k0; q < e; ++q) out[base + q] = (uint8_t)(acc >> (8 * q));
         acc = 0; k0 = e;
     }
-    __device__ __forceinline__ void skip(uint32_t n) { off += n; acc = 0; k0 = off & 3; }
 };
 
 __device__ __forceinline__ void infp_cp4(uint32_t* smem_dst, const uint32_t* gsrc, uint32_t src_size)
@@ -197,14 +207,11 @@ __device__ __forceinline__ void lane_decode(const InflateSmem& S, uint32_t* col,
         if (want_dist) {
             want_dist = 0;
             if (WRITE) {
-                W.flush();
                 const uint32_t at = W.off;
                 if (val > at) *fail = 1;                    // reaches before the start of the output
-                out[at] = (uint8_t)(mlen - 3);
-                out[at + 1] = (uint8_t)((val - 1) & 255);
-                out[at + 2] = (uint8_t)((val - 1) >> 8);
+                W.put(mlen - 3); W.put((val - 1) & 255); W.put((val - 1) >> 8);
                 atomicOr(bitmap + (at >> 5), 1u << (at & 31));
-                W.skip(mlen);
+                W.skip(mlen - 3);
             }
         } else if (kind == 0) {
             ++nbytes;
@@ -294,9 +301,10 @@ infp_find_kernel(const InflateJob* jobs, const InfPar* par, const uint32_t* tile
 // ---------------------------------------------------------------------------------------------
 // 2. verify: the code lengths of the header must give complete literal/length and distance codes.
 __global__ void __launch_bounds__(128)
-infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, uint32_t vq_cap, const uint32_t* ctr)
+infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, uint32_t vq_cap, const uint32_t* qcount,
+                   int max_syms, uint2* vq_next, uint32_t vq_next_cap, uint32_t* qcount_next)
 {
-    uint32_t n = ctr[INFP_CTR_Q];
+    uint32_t n = *qcount;
     if (n > vq_cap) n = vq_cap;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const uint2 c = vq[q];
@@ -350,7 +358,9 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
         int i = 0, prev = 0, nd = 0;
         uint32_t kl = 0, kd = 0;
         bool good = true, has256 = false;
+        int nsym = 0;
         while (i < total) {
+            if (++nsym > max_syms) break;
             R.refill();
             const uint32_t rev = __brev(R.peek(7)) >> 25;
             int sym = -1, len = 0;
@@ -382,7 +392,10 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
             }
             i += rep; prev = val;
         }
-        if (good && has256 && kl == 32768u && (kd == 32768u || nd <= 1))
+        if (good && i < total) {                // ran out of this pass's symbol budget: the next pass finishes it
+            const uint32_t q2 = atomicAdd(qcount_next, 1u);
+            if (q2 < vq_next_cap) vq_next[q2] = c;
+        } else if (good && has256 && kl == 32768u && (kd == 32768u || nd <= 1))
             atomicMin(par[c.x].slots + c.y / INFP_SLOT_BITS, c.y);
     }
 }
@@ -685,6 +698,72 @@ __device__ __forceinline__ void infp_copy_lane(uint8_t* out, uint32_t dst, uint3
     }
 }
 
+// One warp per stream. The bitmap is scanned 4096 output bytes (128 words, 4 per lane) at a time; the matches found
+// are taken 32 at a time (one per lane). The records of the next 32 matches are loaded before the current 32 are
+// copied, so that only the source loads sit on the critical path. Inside a batch, a maximal prefix of matches whose
+// sources end before the first destination of the prefix is copied in parallel (lane per match up to 32 bytes, the
+// whole warp for longer ones); then the next prefix.
+struct InfpMatch { uint32_t dst, len, dist; };
+
+__device__ __forceinline__ InfpMatch infp_locate(const uint8_t* out, const uint32_t (&w)[4], uint32_t incl, uint32_t wb,
+                                                 uint32_t m, bool valid, int lane)
+{
+    uint32_t lo = 0;
+#pragma unroll
+    for (int step = 16; step; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
+        if (v <= m) lo += step;
+    }
+    uint32_t excl = __shfl_sync(0xffffffffu, incl, (int)((lo + 31) & 31));
+    if (lo == 0) excl = 0;
+    const uint32_t x0 = __shfl_sync(0xffffffffu, w[0], (int)lo), x1 = __shfl_sync(0xffffffffu, w[1], (int)lo);
+    const uint32_t x2 = __shfl_sync(0xffffffffu, w[2], (int)lo), x3 = __shfl_sync(0xffffffffu, w[3], (int)lo);
+    InfpMatch M; M.dst = 0; M.len = 0; M.dist = 1;
+    if (valid) {
+        uint32_t r = m - excl, k = 0, x = x0;
+        const uint32_t c0 = __popc(x0), c1 = __popc(x1), c2 = __popc(x2);
+        if (r >= c0) { r -= c0; k = 1; x = x1; if (r >= c1) { r -= c1; k = 2; x = x2; if (r >= c2) { r -= c2; k = 3; x = x3; } } }
+        const uint32_t bit = __fns(x, 0, (int)(r + 1));
+        M.dst = (wb + lo * 4 + k) * 32 + bit;
+        M.len = (uint32_t)out[M.dst] + 3;
+        M.dist = ((uint32_t)out[M.dst + 1] | ((uint32_t)out[M.dst + 2] << 8)) + 1;
+    }
+    return M;
+}
+
+__device__ __forceinline__ void infp_copy_batch(uint8_t* out, const InfpMatch& M, bool valid, int lane)
+{
+    const uint32_t dst = M.dst, len = M.len, dist = M.dist;
+    const uint32_t src = dst - dist;
+    const uint32_t send = src + (len < dist ? len : dist);
+    uint32_t rem = __ballot_sync(0xffffffffu, valid);
+    while (rem) {
+        const int first = __ffs(rem) - 1;
+        const uint32_t D0 = __shfl_sync(0xffffffffu, dst, first);
+        const bool okl = ((rem >> lane) & 1) && (lane == first || send <= D0);
+        const uint32_t okm = __ballot_sync(0xffffffffu, okl);
+        const uint32_t bad = rem & ~okm;
+        const uint32_t grp = bad ? (rem & ((1u << (__ffs(bad) - 1)) - 1)) : rem;
+        const bool mine = (grp >> lane) & 1;
+        if (mine && len <= 32) infp_copy_lane(out, dst, src, len, dist);
+        uint32_t longm = __ballot_sync(0xffffffffu, mine && len > 32);
+        while (longm) {
+            const int l = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const uint32_t d = __shfl_sync(0xffffffffu, dst, l), s = __shfl_sync(0xffffffffu, src, l);
+            const uint32_t ln = __shfl_sync(0xffffffffu, len, l), di = __shfl_sync(0xffffffffu, dist, l);
+            const bool ov = di < ln;
+            uint8_t t[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) t[k] = out[s + (ov ? x % di : x)]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) out[d + x] = t[k]; }
+        }
+        __syncwarp();
+        rem &= ~grp;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 infp_resolve_kernel(const InflateJob* jobs, const InfPar* par, int njobs)
 {
@@ -695,62 +774,43 @@ infp_resolve_kernel(const InflateJob* jobs, const InfPar* par, int njobs)
     if (!P.eligible || !P.ok || P.fail) return;
     uint8_t* out = jobs[j].out;
     const uint32_t n = jobs[j].out_len;
-    const uint32_t* bm = P.bitmap;
+    const uint32_t* bm = P.bitmap;                      // 16-byte aligned, padded past the last word
     const uint32_t nw = (n + 31) >> 5;
-    for (uint32_t wb = 0; wb < nw; wb += 32) {
-        const uint32_t wv = wb + lane < nw ? bm[wb + lane] : 0u;
-        uint32_t incl = __popc(wv);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        for (uint32_t m0 = 0; m0 < total; m0 += 32) {
-            const uint32_t m = m0 + lane;
-            const bool valid = m < total;
-            uint32_t lo = 0;
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
-                if (v <= m) lo += step;
+    auto load_window = [&](uint32_t wb, uint32_t (&w)[4]) {
+        const uint4 v = wb + lane * 4 < nw ? *(const uint4*)(bm + wb + lane * 4) : make_uint4(0, 0, 0, 0);
+        const uint32_t i0 = wb + lane * 4;
+        w[0] = i0 < nw ? v.x : 0; w[1] = i0 + 1 < nw ? v.y : 0; w[2] = i0 + 2 < nw ? v.z : 0; w[3] = i0 + 3 < nw ? v.w : 0;
+    };
+    // software pipeline over (window, batch): `cur` is copied while `nxt`'s records are in flight
+    uint32_t w[4], incl = 0, total = 0, wb = 0, m0 = 0;
+    bool have = false;
+    InfpMatch cur; bool curv = false;
+    // advance to the next batch: returns false when the stream is exhausted
+    auto next_batch = [&](InfpMatch& M, bool& v) -> bool {
+        for (;;) {
+            if (have && m0 < total) {
+                const uint32_t m = m0 + lane;
+                v = m < total;
+                M = infp_locate(out, w, incl, wb, m, v, lane);
+                m0 += 32;
+                return true;
             }
-            uint32_t excl = __shfl_sync(0xffffffffu, incl, (int)((lo + 31) & 31));
-            if (lo == 0) excl = 0;
-            const uint32_t word = __shfl_sync(0xffffffffu, wv, (int)lo);
-            uint32_t dst = 0, len = 0, dist = 1;
-            if (valid) {
-                const uint32_t bit = __fns(word, 0, (int)(m - excl + 1));
-                dst = (wb + lo) * 32 + bit;
-                len = (uint32_t)out[dst] + 3;
-                dist = ((uint32_t)out[dst + 1] | ((uint32_t)out[dst + 2] << 8)) + 1;
-            }
-            const uint32_t src = dst - dist;
-            const uint32_t send = src + (len < dist ? len : dist);
-            uint32_t rem = __ballot_sync(0xffffffffu, valid);
-            while (rem) {
-                const int first = __ffs(rem) - 1;
-                const uint32_t D0 = __shfl_sync(0xffffffffu, dst, first);
-                const bool okl = ((rem >> lane) & 1) && (lane == first || send <= D0);
-                const uint32_t okm = __ballot_sync(0xffffffffu, okl);
-                const uint32_t bad = rem & ~okm;
-                const uint32_t grp = bad ? (rem & ((1u << (__ffs(bad) - 1)) - 1)) : rem;
-                const bool mine = (grp >> lane) & 1;
-                if (mine && len <= 32) infp_copy_lane(out, dst, src, len, dist);
-                uint32_t longm = __ballot_sync(0xffffffffu, mine && len > 32);
-                while (longm) {
-                    const int l = __ffs(longm) - 1;
-                    longm &= longm - 1;
-                    const uint32_t d = __shfl_sync(0xffffffffu, dst, l), s = __shfl_sync(0xffffffffu, src, l);
-                    const uint32_t ln = __shfl_sync(0xffffffffu, len, l), di = __shfl_sync(0xffffffffu, dist, l);
-                    const bool ov = di < ln;
-                    uint8_t t[9];
+            if (have) wb += 128;
+            if (wb >= nw) return false;
+            load_window(wb, w);
+            incl = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) t[k] = out[s + (ov ? x % di : x)]; }
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) out[d + x] = t[k]; }
-                }
-                __syncwarp();
-                rem &= ~grp;
-            }
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            m0 = 0; have = true;
         }
+    };
+    bool more = next_batch(cur, curv);
+    while (more) {
+        InfpMatch nxt; bool nxtv = false;
+        more = next_batch(nxt, nxtv);
+        infp_copy_batch(out, cur, curv, lane);
+        cur = nxt; curv = nxtv;
     }
 }
 

@@ -56,7 +56,7 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
         // offsets for now; turned into pointers below
         P.slots = (uint32_t*)(uintptr_t)slots_total;   slots_total += P.nslots;
         P.blocks = (InfBlock*)(uintptr_t)blocks_total; blocks_total += P.maxblocks;
-        P.bitmap = (uint32_t*)(uintptr_t)bitmap_total; bitmap_total += (size_t)(J.out_cap / 32) + 2;
+        P.bitmap = (uint32_t*)(uintptr_t)bitmap_total; bitmap_total += ((size_t)(J.out_cap / 32) + 2 + 3) & ~(size_t)3;
         bits_total += P.in_bits;
         const uint32_t nwords = (J.in_len + 3) / 4;
         tiles += (nwords + INFP_TILE_WORDS - 1) / INFP_TILE_WORDS;
@@ -69,11 +69,12 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
         return true;
     }
     const uint32_t vq_cap = (uint32_t)std::min<uint64_t>(bits_total / 512 + 4096, 0x7fffffffull);
+    const uint32_t vq2_cap = vq_cap / 4 + 1024;
     auto al256 = [](size_t n) { return (n + 255) & ~(size_t)255; };
     const size_t o_par = 0, o_tiles = al256(o_par + sizeof(InfPar) * njobs), o_ctr = al256(o_tiles + 4 * ((size_t)njobs + 1)),
-                 o_slots = al256(o_ctr + 64), o_bitmap = al256(o_slots + 4 * slots_total), o_blocks = al256(o_bitmap + 4 * bitmap_total),
+                 o_slots = al256(o_ctr + 64), o_bitmap = al256(o_slots + 4 * slots_total), o_blocks = al256(o_bitmap + 4 * bitmap_total + 1024),
                  o_work = al256(o_blocks + sizeof(InfBlock) * blocks_total), o_vq = al256(o_work + 8 * blocks_total),
-                 total = al256(o_vq + 8 * (size_t)vq_cap);
+                 o_vq2 = al256(o_vq + 8 * (size_t)vq_cap), o_vq3 = al256(o_vq2 + 8 * (size_t)vq2_cap), total = al256(o_vq3 + 8 * (size_t)vq2_cap);
     if (!W.buf.alloc(total)) return false;
     uint8_t* base = W.buf.as<uint8_t>();
     for (int j = 0; j < njobs; ++j) {
@@ -95,16 +96,31 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
     uint32_t* d_ctr = (uint32_t*)(base + o_ctr);
     uint2* d_work = (uint2*)(base + o_work);
     uint2* d_vq = (uint2*)(base + o_vq);
+    uint2* d_vq2 = (uint2*)(base + o_vq2);
+    uint2* d_vq3 = (uint2*)(base + o_vq3);
     const int persistent = sm_count() * 6;
     infp_find_kernel<<<tiles, 256, 0, st>>>(d_jobs, d_par, (const uint32_t*)(base + o_tiles), njobs, d_vq, vq_cap, d_ctr);
-    infp_verify_kernel<<<sm_count() * 8, 128, 0, st>>>(d_jobs, d_par, d_vq, vq_cap, d_ctr);
+    // several passes with a growing symbol budget: most random headers over-subscribe their code within a few
+    // symbols; whatever outlives a pass's budget is queued for the next pass and decoded again from its start
+    // (keeps the lanes of a warp in step: without the budget a warp runs as long as its longest header)
+    {
+        const int budgets[4] = {12, 40, 120, 1 << 20};
+        uint2* qin = d_vq; uint32_t qin_cap = vq_cap; uint32_t* cin = d_ctr + INFP_CTR_Q;
+        for (int pass = 0; pass < 4; ++pass) {
+            uint2* qout = (pass & 1) ? d_vq3 : d_vq2;
+            uint32_t* cout = d_ctr + INFP_CTR_Q2 + pass;
+            infp_verify_kernel<<<sm_count() * (pass == 0 ? 8 : 4), 128, 0, st>>>(d_jobs, d_par, qin, qin_cap, cin, budgets[pass],
+                                                                                 pass < 3 ? qout : nullptr, vq2_cap, pass < 3 ? cout : nullptr);
+            qin = qout; qin_cap = vq2_cap; cin = cout;
+        }
+    }
     infp_compact_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_par, njobs, d_work, d_ctr);
     infp_count_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
     infp_walk_kernel<<<(njobs + INFP_WARPS - 1) / INFP_WARPS, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, njobs);
     infp_write_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
     infp_resolve_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, d_par, njobs);
     inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs, d_par);
-    count_launch(8);
+    count_launch(11);
     return true;
 }
 
@@ -116,9 +132,27 @@ struct Segment { const uint8_t* src; uint8_t* dst; uint32_t len; };
 __global__ void __launch_bounds__(256)
 gather_segments_kernel(const Segment* segs, int nsegs)
 {
+    // 16-byte destination vectors; the source is read as aligned words and realigned with a funnel shift (the up to
+    // 3 bytes read past a segment are the chunk's CRC, inside the file)
     for (int s = blockIdx.x; s < nsegs; s += gridDim.x) {
-        Segment g = segs[s];
-        for (uint32_t i = threadIdx.x; i < g.len; i += 256) g.dst[i] = g.src[i];
+        const Segment g = segs[s];
+        uint32_t head = (16u - (uint32_t)((uintptr_t)g.dst & 15u)) & 15u;
+        if (head > g.len) head = g.len;
+        const uint32_t nvec = (g.len - head) >> 4;
+        const uint32_t tail0 = head + (nvec << 4);
+        if (threadIdx.x < head) g.dst[threadIdx.x] = g.src[threadIdx.x];
+        if (tail0 + threadIdx.x < g.len) g.dst[tail0 + threadIdx.x] = g.src[tail0 + threadIdx.x];
+        for (uint32_t v = threadIdx.x; v < nvec; v += 256) {
+            const uint8_t* sp = g.src + head + ((size_t)v << 4);
+            const uint32_t m = (uint32_t)((uintptr_t)sp & 3u), sh = m * 8;
+            const uint32_t* wp = (const uint32_t*)(sp - m);
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+            const uint32_t w4 = m ? __ldg(wp + 4) : 0u;
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+            *(uint4*)(g.dst + head + ((size_t)v << 4)) = o;
+        }
     }
 }
 void launch_gather(const void* d_segs, int nsegs, cudaStream_t st)

@@ -29,6 +29,7 @@
 // path only ever accepts streams it decoded completely, so accepted results are identical to the serial decoder's.
 #pragma once
 #include "inflate.cuh"
+#include "lz_resolve.cuh"
 
 namespace gb {
 
@@ -682,88 +683,7 @@ infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// 7. resolve
-__device__ __forceinline__ void infp_copy_lane(uint8_t* out, uint32_t dst, uint32_t src, uint32_t len, uint32_t dist)
-{
-    const bool overlap = dist < len;
-    for (uint32_t i = 0; i < len; i += 8) {
-        uint8_t t[8];
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            const uint32_t x = i + k;
-            if (x < len) t[k] = out[src + (overlap ? x % dist : x)];
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) if (i + k < len) out[dst + i + k] = t[k];
-    }
-}
-
-// One warp per stream. The bitmap is scanned 4096 output bytes (128 words, 4 per lane) at a time; the matches found
-// are taken 32 at a time (one per lane). The records of the next 32 matches are loaded before the current 32 are
-// copied, so that only the source loads sit on the critical path. Inside a batch, a maximal prefix of matches whose
-// sources end before the first destination of the prefix is copied in parallel (lane per match up to 32 bytes, the
-// whole warp for longer ones); then the next prefix.
-struct InfpMatch { uint32_t dst, len, dist; };
-
-__device__ __forceinline__ InfpMatch infp_locate(const uint8_t* out, const uint32_t (&w)[4], uint32_t incl, uint32_t wb,
-                                                 uint32_t m, bool valid, int lane)
-{
-    uint32_t lo = 0;
-#pragma unroll
-    for (int step = 16; step; step >>= 1) {
-        const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
-        if (v <= m) lo += step;
-    }
-    uint32_t excl = __shfl_sync(0xffffffffu, incl, (int)((lo + 31) & 31));
-    if (lo == 0) excl = 0;
-    const uint32_t x0 = __shfl_sync(0xffffffffu, w[0], (int)lo), x1 = __shfl_sync(0xffffffffu, w[1], (int)lo);
-    const uint32_t x2 = __shfl_sync(0xffffffffu, w[2], (int)lo), x3 = __shfl_sync(0xffffffffu, w[3], (int)lo);
-    InfpMatch M; M.dst = 0; M.len = 0; M.dist = 1;
-    if (valid) {
-        uint32_t r = m - excl, k = 0, x = x0;
-        const uint32_t c0 = __popc(x0), c1 = __popc(x1), c2 = __popc(x2);
-        if (r >= c0) { r -= c0; k = 1; x = x1; if (r >= c1) { r -= c1; k = 2; x = x2; if (r >= c2) { r -= c2; k = 3; x = x3; } } }
-        const uint32_t bit = __fns(x, 0, (int)(r + 1));
-        M.dst = (wb + lo * 4 + k) * 32 + bit;
-        M.len = (uint32_t)out[M.dst] + 3;
-        M.dist = ((uint32_t)out[M.dst + 1] | ((uint32_t)out[M.dst + 2] << 8)) + 1;
-    }
-    return M;
-}
-
-__device__ __forceinline__ void infp_copy_batch(uint8_t* out, const InfpMatch& M, bool valid, int lane)
-{
-    const uint32_t dst = M.dst, len = M.len, dist = M.dist;
-    const uint32_t src = dst - dist;
-    const uint32_t send = src + (len < dist ? len : dist);
-    uint32_t rem = __ballot_sync(0xffffffffu, valid);
-    while (rem) {
-        const int first = __ffs(rem) - 1;
-        const uint32_t D0 = __shfl_sync(0xffffffffu, dst, first);
-        const bool okl = ((rem >> lane) & 1) && (lane == first || send <= D0);
-        const uint32_t okm = __ballot_sync(0xffffffffu, okl);
-        const uint32_t bad = rem & ~okm;
-        const uint32_t grp = bad ? (rem & ((1u << (__ffs(bad) - 1)) - 1)) : rem;
-        const bool mine = (grp >> lane) & 1;
-        if (mine && len <= 32) infp_copy_lane(out, dst, src, len, dist);
-        uint32_t longm = __ballot_sync(0xffffffffu, mine && len > 32);
-        while (longm) {
-            const int l = __ffs(longm) - 1;
-            longm &= longm - 1;
-            const uint32_t d = __shfl_sync(0xffffffffu, dst, l), s = __shfl_sync(0xffffffffu, src, l);
-            const uint32_t ln = __shfl_sync(0xffffffffu, len, l), di = __shfl_sync(0xffffffffu, dist, l);
-            const bool ov = di < ln;
-            uint8_t t[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) t[k] = out[s + (ov ? x % di : x)]; }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { const uint32_t x = (uint32_t)k * 32 + lane; if (x < ln) out[d + x] = t[k]; }
-        }
-        __syncwarp();
-        rem &= ~grp;
-    }
-}
-
+// 7. resolve (lz_resolve.cuh)
 __global__ void __launch_bounds__(128)
 infp_resolve_kernel(const InflateJob* jobs, const InfPar* par, int njobs)
 {
@@ -772,46 +692,7 @@ infp_resolve_kernel(const InflateJob* jobs, const InfPar* par, int njobs)
     if (j >= njobs) return;
     const InfPar& P = par[j];
     if (!P.eligible || !P.ok || P.fail) return;
-    uint8_t* out = jobs[j].out;
-    const uint32_t n = jobs[j].out_len;
-    const uint32_t* bm = P.bitmap;                      // 16-byte aligned, padded past the last word
-    const uint32_t nw = (n + 31) >> 5;
-    auto load_window = [&](uint32_t wb, uint32_t (&w)[4]) {
-        const uint4 v = wb + lane * 4 < nw ? *(const uint4*)(bm + wb + lane * 4) : make_uint4(0, 0, 0, 0);
-        const uint32_t i0 = wb + lane * 4;
-        w[0] = i0 < nw ? v.x : 0; w[1] = i0 + 1 < nw ? v.y : 0; w[2] = i0 + 2 < nw ? v.z : 0; w[3] = i0 + 3 < nw ? v.w : 0;
-    };
-    // software pipeline over (window, batch): `cur` is copied while `nxt`'s records are in flight
-    uint32_t w[4], incl = 0, total = 0, wb = 0, m0 = 0;
-    bool have = false;
-    InfpMatch cur; bool curv = false;
-    // advance to the next batch: returns false when the stream is exhausted
-    auto next_batch = [&](InfpMatch& M, bool& v) -> bool {
-        for (;;) {
-            if (have && m0 < total) {
-                const uint32_t m = m0 + lane;
-                v = m < total;
-                M = infp_locate(out, w, incl, wb, m, v, lane);
-                m0 += 32;
-                return true;
-            }
-            if (have) wb += 128;
-            if (wb >= nw) return false;
-            load_window(wb, w);
-            incl = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-            total = __shfl_sync(0xffffffffu, incl, 31);
-            m0 = 0; have = true;
-        }
-    };
-    bool more = next_batch(cur, curv);
-    while (more) {
-        InfpMatch nxt; bool nxtv = false;
-        more = next_batch(nxt, nxtv);
-        infp_copy_batch(out, cur, curv, lane);
-        cur = nxt; curv = nxtv;
-    }
+    lz_resolve_stream<LZR_DEFLATE>(jobs[j].out, jobs[j].out_len, P.bitmap, lane);
 }
 
 } // namespace gb

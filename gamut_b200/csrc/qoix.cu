@@ -4,8 +4,8 @@
 // (source/gamut/plugins/qoix.d:350-473) with its sub-decoders qoiplane10_decode
 // (codecs/qoiplane10.d:317-515), LZ4_decompress_fast (codecs/lz4.d:976 -> :760-963).
 // The 14/25-byte headers are parsed on the host; all byte-stream and pixel work runs on the GPU:
-//   lz4_kernel          one warp per LZ4 block: the token walk is warp-uniform, literal runs and
-//                       matches are copied 32 bytes per step by the whole warp
+//   lz4_parse_kernel +  one warp per LZ4 block walks the sequences and copies literal runs; matches are parked as
+//   lz4_resolve_kernel  records and copied by a second pass, 32 at a time (see below and lz_resolve.cuh)
 //   qoiplane10_kernel   QOI-Plane10 opcode stream -> 10-bit L/LA expanded to 16 bit (one thread per
 //                       image: the MED predictor makes every pixel depend on its left/top/top-left)
 //   qoi_kernel          QOI opcode stream (value-hashed index => serial per image)
@@ -13,6 +13,7 @@
 // a corrupt stream fails that image only.
 #include "common.h"
 #include "batch.h"
+#include "lz_resolve.cuh"
 #include <vector>
 #include <chrono>
 
@@ -20,61 +21,159 @@ namespace {
 
 constexpr int QOIX_HEADER_SIZE = 25;
 
-struct Lz4Job { const uint8_t* in; uint32_t in_len; uint8_t* out; uint32_t orig; int image; };
+struct Lz4Job { const uint8_t* in; uint32_t in_len; uint8_t* out; uint32_t orig; int image; uint32_t* bitmap; };
 
-// LZ4 block decode with endOnOutputSize semantics (lz4.d:760-963): stops when exactly `orig` bytes
-// have been produced by a final literal run.
+__device__ __forceinline__ void lz4_cp16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
+// LZ4 block decode with endOnOutputSize semantics (lz4.d:760-963): stops when exactly `orig` bytes have been
+// produced by a final literal run. Two kernels:
+//   lz4_parse_kernel    one warp per block walks the sequences (warp-uniform; the input is staged through a 4 KB
+//                       shared-memory ring by 16-byte cp.async, 2 KB ahead of the walk, so no global-memory latency
+//                       sits on the serial token chain), copies the literal runs to their final positions, and
+//                       parks every match as a 4-byte record (length, offset) in the hole it will fill, flagged in
+//                       a bitmap;
+//   lz4_resolve_kernel  performs the match copies in stream order, 32 at a time where independent (lz_resolve.cuh).
+constexpr int LZ4_RING = 8192;
+constexpr int LZ4_WARPS = 2;
+
+// The walk is done in bursts of up to 32 sequences: all lanes execute the (warp-uniform) token chain -- one shared-
+// memory broadcast load for the token, two for the offset, a dozen integer instructions -- and lane k keeps the k-th
+// sequence (literal source, literal length, output position, match length, offset) in registers; then the warp copies
+// the literal runs of the burst together (flattened over the 32 lanes with a prefix sum) and lane k parks match k.
+// Header bytes beyond the staged window are read from global memory (rare); a literal run that is not completely
+// staged is copied global -> global after the burst.
+__global__ void __launch_bounds__(LZ4_WARPS * 32)
+lz4_parse_kernel(const Lz4Job* __restrict__ jobs, int njobs, int* status)
+{
+    __shared__ uint4 ring_all[LZ4_WARPS][LZ4_RING / 16];
+    const int wslot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * LZ4_WARPS + wslot;
+    if (warp >= njobs) return;
+    const Lz4Job J = jobs[warp];
+    uint4* ring = ring_all[wslot];
+    const uint8_t* ring8 = (const uint8_t*)ring;
+    const uint8_t* gbase = (const uint8_t*)((uintptr_t)J.in & ~(uintptr_t)15);
+    const uint32_t a0 = (uint32_t)(J.in - gbase);
+    const uint32_t in_len = J.in_len, orig = J.orig;
+    const uint32_t nvec = (a0 + in_len + 15) >> 4;            // 16-byte vectors that hold the block
+    uint32_t fetched = 0;                                     // vectors [.., fetched) are staged and complete
+    uint32_t safe = 0;                                        // block bytes [p, safe) are in the ring
+    uint32_t p = 0, o = 0;                                    // input / output positions
+    bool ok = true, done = false;
+    auto rbx = [&](uint32_t k) -> uint32_t { return k < safe ? (uint32_t)ring8[(a0 + k) & (LZ4_RING - 1)] : (uint32_t)J.in[k]; };
+    // stage input up to LZ4_RING - 256 bytes beyond position p (everything before p may be overwritten)
+    auto stage = [&]() {
+        const uint32_t v0 = (a0 + p) >> 4;
+        if (fetched < v0) fetched = v0;                       // skipped by a long literal run
+        const uint32_t lim = v0 + (LZ4_RING - 256) / 16;
+        const uint32_t hi = lim < nvec ? lim : nvec;
+        for (uint32_t v = fetched + lane; v < hi; v += 32) lz4_cp16(ring + (v & (LZ4_RING / 16 - 1)), gbase + (size_t)v * 16);
+        if (hi > fetched) fetched = hi;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        safe = fetched * 16 > a0 ? fetched * 16 - a0 : 0;
+    };
+    if (in_len == 0) ok = false;
+    else if (orig == 0) ok = J.in[0] == 0;
+    else while (!done && ok) {
+        stage();
+        // ---- burst: up to 32 sequences
+        uint32_t d_lit = 0, d_len = 0, d_out = 0, d_mlen = 0, d_off = 0, d_big = 0;   // this lane's sequence
+        int nseq = 0;
+        while (nseq < 32) {
+            if (p >= in_len) { ok = false; break; }
+            const uint32_t token = rbx(p++);
+            uint32_t L = token >> 4;
+            if (L == 15) {
+                uint32_t s2;
+                do { if (p >= in_len) { ok = false; break; } s2 = rbx(p++); L += s2; } while (s2 == 255 && L < 0x7fffff00u);
+                if (!ok) break;
+            }
+            if (L > orig - o || L > in_len - p) { ok = false; break; }
+            const bool last = (uint64_t)o + L + 8 > orig;     // cpy > oend - COPYLENGTH
+            if (last && o + L != orig) { ok = false; break; }
+            const uint32_t lit = p, oo = o;
+            const uint32_t big = p + L > safe ? 1u : 0u;      // literal run not completely staged
+            p += L; o += L;
+            uint32_t M = 0, off = 0;
+            if (last) done = true;
+            else {
+                if (in_len - p < 2) { ok = false; break; }
+                off = rbx(p) | (rbx(p + 1) << 8);
+                p += 2;
+                if (off == 0 || off > o) { ok = false; break; }
+                M = token & 15;
+                if (M == 15) {
+                    uint32_t s2;
+                    do { if (p >= in_len) { ok = false; break; } s2 = rbx(p++); M += s2; } while (s2 == 255 && M < 0x7fffff00u);
+                    if (!ok) break;
+                }
+                M += 4;
+                if (M > orig - o || (uint64_t)o + M + 5 > orig) { ok = false; break; }   // last 5 bytes are literals
+            }
+            if (lane == nseq) { d_lit = lit; d_len = L; d_out = oo; d_mlen = M; d_off = off; d_big = big; }
+            o += M;
+            ++nseq;
+            if (done || big || (p + 64 > safe && safe < in_len)) break;
+        }
+        // ---- literal runs of the burst, flattened over the lanes
+        {
+            const uint32_t mylen = (lane < nseq && !d_big) ? d_len : 0;
+            uint32_t incl = mylen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t excl = incl - mylen;
+            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                uint32_t lo = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
+                    if (v <= t) lo += step;
+                }
+                const uint32_t ex = __shfl_sync(0xffffffffu, excl, (int)lo);
+                const uint32_t sl = __shfl_sync(0xffffffffu, d_lit, (int)lo), so = __shfl_sync(0xffffffffu, d_out, (int)lo);
+                if (t < total) J.out[so + (t - ex)] = ring8[(a0 + sl + (t - ex)) & (LZ4_RING - 1)];
+            }
+            uint32_t bigm = __ballot_sync(0xffffffffu, lane < nseq && d_big);
+            while (bigm) {
+                const int l = __ffs(bigm) - 1;
+                bigm &= bigm - 1;
+                const uint32_t sl = __shfl_sync(0xffffffffu, d_lit, l), so = __shfl_sync(0xffffffffu, d_out, l), ln = __shfl_sync(0xffffffffu, d_len, l);
+                for (uint32_t i = lane; i < ln; i += 32) J.out[so + i] = J.in[sl + i];
+            }
+        }
+        // ---- matches of the burst: 4-byte record + bitmap flag; pieces of at most 65535 bytes, each at least 4
+        if (lane < nseq && d_mlen) {
+            uint32_t at = d_out + d_len, left = d_mlen;
+            while (left) {
+                uint32_t n = left > 65535 ? 65531 : left;
+                if (left - n > 0 && left - n < 4) n -= 4;
+                J.out[at] = (uint8_t)n; J.out[at + 1] = (uint8_t)(n >> 8);
+                J.out[at + 2] = (uint8_t)d_off; J.out[at + 3] = (uint8_t)(d_off >> 8);
+                atomicOr(J.bitmap + (at >> 5), 1u << (at & 31));
+                at += n; left -= n;
+            }
+        }
+        __syncwarp();
+    }
+    if (!ok && lane == 0) status[J.image] = 0;
+}
+
 __global__ void __launch_bounds__(128)
-lz4_kernel(const Lz4Job* __restrict__ jobs, int njobs, int* status)
+lz4_resolve_kernel(const Lz4Job* __restrict__ jobs, int njobs, const int* status)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= njobs) return;
     const Lz4Job J = jobs[warp];
-    const uint8_t* ip = J.in; const uint8_t* const iend = J.in + J.in_len;
-    uint8_t* op = J.out; uint8_t* const oend = J.out + J.orig;
-    bool ok = true;
-    if (J.orig == 0) { ok = J.in_len >= 1 && ip[0] == 0; goto done; }
-    for (;;) {
-        if (ip >= iend) { ok = false; break; }
-        const uint32_t token = *ip++;
-        size_t length = token >> 4;
-        if (length == 15) {
-            uint32_t s;
-            do { if (ip >= iend) { ok = false; break; } s = *ip++; length += s; } while (s == 255);
-            if (!ok) break;
-        }
-        if (length > (size_t)(oend - op) || length > (size_t)(iend - ip)) { ok = false; break; }
-        const bool last = (op + length) + 8 > oend;          // cpy > oend - COPYLENGTH
-        if (last && op + length != oend) { ok = false; break; }
-        for (size_t i = lane; i < length; i += 32) op[i] = ip[i];
-        ip += length; op += length;
-        if (last) break;
-        if (iend - ip < 2) { ok = false; break; }
-        const size_t offset = (size_t)ip[0] | ((size_t)ip[1] << 8); ip += 2;
-        if (offset == 0 || offset > (size_t)(op - J.out)) { ok = false; break; }
-        length = token & 15;
-        if (length == 15) {
-            uint32_t s;
-            do { if (ip >= iend) { ok = false; break; } s = *ip++; length += s; } while (s == 255);
-            if (!ok) break;
-        }
-        length += 4;
-        if (length > (size_t)(oend - op) || op + length + 5 > oend) { ok = false; break; }   // last 5 bytes are literals
-        __syncwarp();
-        if (offset >= 32) {
-            for (size_t b = 0; b < length; b += 32) {
-                size_t i = b + lane;
-                if (i < length) op[i] = op[i - offset];
-                __syncwarp();
-            }
-        } else {
-            for (size_t i = lane; i < length; i += 32) op[i] = (op - offset)[i % offset];
-            __syncwarp();
-        }
-        op += length;
-    }
-done:
-    if (!ok && lane == 0) status[J.image] = 0;
+    if (!status[J.image]) return;                           // the parse failed: the image fails as a whole
+    gb::lz_resolve_stream<gb::LZR_LZ4>(J.out, J.orig, J.bitmap, lane);
 }
 
 #include "qoiplane10.cuh"
@@ -224,6 +323,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     uint8_t* h_stage = nullptr;
     if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
     std::vector<Lz4Job> lz; std::vector<P10Image> pj;
+    size_t lzbm_total = 0;
     size_t rec_total = 0, row_total = 0; uint32_t total_chunks = 0;
     std::vector<SubJob> sub[4]; size_t sub_rows_total = 0;
     for (int i : live) {
@@ -232,7 +332,8 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         const uint8_t* stream = dev; uint32_t ssize = (uint32_t)lens[i];
         if (P[i].compression == 1) {
             uint8_t* dec = d_lz.as<uint8_t>() + lz_off[i];
-            lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, (uint32_t)(lens[i] - QOIX_HEADER_SIZE - 4), dec + QOIX_HEADER_SIZE, P[i].orig, i});
+            lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, (uint32_t)(lens[i] - QOIX_HEADER_SIZE - 4), dec + QOIX_HEADER_SIZE, P[i].orig, i, (uint32_t*)lzbm_total});
+            lzbm_total += (((size_t)P[i].orig / 32 + 2 + 3) & ~(size_t)3) * 4;
             stream = dec; ssize = QOIX_HEADER_SIZE + P[i].orig;
         }
         if (P[i].codec != 0) {
@@ -261,8 +362,9 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     size_t sub_first[4] = {0, 0, 0, 0};
     for (int c = 1; c < 4; ++c) { sub_first[c] = suball.size(); for (auto& S : sub[c]) { S.rows = d_subrows.as<uint8_t>() + (size_t)S.rows; suball.push_back(S); } }
     for (auto& J : pj) { J.recs = (uint32_t*)(d_recs.as<uint8_t>() + (size_t)J.recs); J.rowinfo = (uint32_t*)(d_rows.as<uint8_t>() + (size_t)J.rowinfo); }
-    DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(P10Image) * (pj.size() + 1));
-    if (!d_lzj.p || !d_pj.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+    DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(P10Image) * (pj.size() + 1)), d_lzbm(lzbm_total + 1024);
+    for (auto& L : lz) L.bitmap = (uint32_t*)(d_lzbm.as<uint8_t>() + (size_t)L.bitmap);
+    if (!d_lzj.p || !d_pj.p || !d_lzbm.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
     std::vector<int> ones((size_t)n, 1);
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
@@ -277,7 +379,13 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         okc &= cuda_ok(cudaMemsetAsync(d_subrows.p, 0, sub_rows_total, st), "subrows", __FILE__, __LINE__);
     }
     cudaEventRecord(ev[1], st);
-    if (!lz.empty()) { lz4_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(d_lzj.as<Lz4Job>(), (int)lz.size(), d_status.as<int>()); count_launch(); }
+    if (!lz.empty()) {
+        okc &= cuda_ok(cudaMemsetAsync(d_lzbm.p, 0, lzbm_total + 1024, st), "lz4 bitmap", __FILE__, __LINE__);
+        const unsigned g = (unsigned)((lz.size() + LZ4_WARPS - 1) / LZ4_WARPS);
+        lz4_parse_kernel<<<g, LZ4_WARPS * 32, 0, st>>>(d_lzj.as<Lz4Job>(), (int)lz.size(), d_status.as<int>());
+        lz4_resolve_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(d_lzj.as<Lz4Job>(), (int)lz.size(), d_status.as<int>());
+        count_launch(2);
+    }
     cudaEventRecord(ev[2], st);
     for (int c = 1; c < 4; ++c) {
         if (sub[c].empty()) continue;

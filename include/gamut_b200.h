@@ -110,7 +110,9 @@ uint8_t* gb200_png_load(const uint8_t* data, size_t len, int req_comp, int want1
                         int* width, int* height, int* comp, float* ppmX, float* ppmY, float* pixelRatio);
 /* Batched PNG decode: files[i]/lens[i] are HOST copies of the files (chunk headers are walked on the
  * host); files_dev, if not NULL, holds device-resident copies of the same bytes (no H2D copy is made
- * then). want16: 0 / 1 as above, -1 = auto per file (what loadPNG does, plugins/png.d:77-79). */
+ * then; every device copy must be followed by >= 16 readable bytes -- the kernels fetch whole 16-byte vectors;
+ * the same holds for the JPEG and QOIX batch entry points). want16: 0 / 1 as above, -1 = auto per file (what
+ * loadPNG does, plugins/png.d:77-79). */
 gb200_batch* gb200_png_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                     const uint8_t* const* files_dev, int req_comp, int want16, void* stream);
 /* Kernel-level entry for the row unfilter alone (stbi__create_png_image_raw, stbdec.d:1406-1547,

@@ -210,10 +210,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # units processed by all ranks (ranges are balanced by bytes, so the per-rank counts may differ by one image)
+    px_all, e2e_px_all = wl.px_per_step * world, wl.e2e_px_per_step * world
+    if world > 1:
+        t = torch.tensor([wl.px_per_step, wl.e2e_px_per_step], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        px_all, e2e_px_all = float(t[0].item()), float(t[1].item())
     if rank == 0:
-        total_px = wl.px_per_step * args.steps * world
+        total_px = px_all * args.steps
         value = total_px / (ms * 1e-3) / 1e6
-        e2e_v = wl.e2e_px_per_step * args.e2e_steps * world / e2e_s / 1e6
+        e2e_v = e2e_px_all * args.e2e_steps / e2e_s / 1e6
         cfg = {"workload": wl.name, "sharding": "units sharded across ranks, no collective on the data path"}
         cfg.update(wl.config())
         out = {"metric": "Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world,

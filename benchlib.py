@@ -324,7 +324,7 @@ class PngWorkload:
         # dominant kernel: inflate. algorithmic bytes per launch = compressed in + raw out, per image * n
         alg = (self.comp_bytes + self.raw_len) * self.n
         ach = alg / (ph[1] * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "inflate_batch_kernel", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+        return {"bound": "hbm", "kernel": "inflate pipeline (infp_find/verify/compact/count/walk/write/resolve kernels)", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": None,
                 "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(float(ph[1]), 3)}
 
@@ -400,12 +400,18 @@ class _BatchDecodeWorkload:
         self.torch, self.codecs = torch, codecs
         total = args.batch or total_default
         self.world = world
-        self.n = max(1, total // world)                      # strong scaling: the batch is sharded across ranks
-        self.total = self.n * world
-        self.files = self.make_files(1000 + 100 * rank)
-        self.host_files = [self.files[i % len(self.files)] for i in range(self.n)]
+        # strong scaling: ONE batch of `total` images (image k = distinct file k % DISTINCT, same on every rank) is cut
+        # into contiguous index ranges balanced by compressed bytes (gamut_b200/shard.py); no collective
+        from gamut_b200 import shard
+        self.total = max(total, world)
+        self.files = self.make_files(1000)
+        nd = len(self.files)
+        self.range = shard.my_range([len(self.files[k % nd]) for k in range(self.total)], rank, world)
+        idx = list(range(*self.range))
+        self.n = len(idx)
+        self.host_files = [self.files[k % nd] for k in idx]
         base = [torch.frombuffer(bytearray(f + b"\0" * 64), dtype=torch.uint8).cuda() for f in self.files]
-        self.dev_bufs = [base[i % len(base)].clone() for i in range(self.n)]
+        self.dev_bufs = [base[k % nd].clone() for k in idx]
         self.dev_ptrs = [t.data_ptr() for t in self.dev_bufs]
         self.px_per_step = self.n * self.W * self.H
         self.e2e_n = min(self.n, 64)
@@ -513,7 +519,7 @@ class QoixWorkload(_BatchDecodeWorkload):
     dtype = "u16"
     W, H = 2048, 2048
     e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back to pinned host memory with gb200_batch_download)"
-    kernel_names = {1: "lz4_kernel", 2: "qoiplane10_kernel"}
+    kernel_names = {1: "lz4_parse_kernel+lz4_resolve_kernel", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
 
     def __init__(self, rank, world, args):
         self._setup(rank, world, args, 256)

@@ -242,9 +242,11 @@ __device__ void unfilter_warp(const UnfilterJob& J, int* status, int lane)
 //    the producer has published the chunk in a shared progress counter.
 // Shared-memory bank = (step - lane) mod 32 for every ring access: conflict-free by construction.
 constexpr int U4_NW = 4;
-constexpr int U4_INW = 128;
-constexpr int U4_OUTW = 64;
-struct U4Smem { uint32_t in[33][U4_INW]; uint32_t out[32][U4_OUTW]; };
+constexpr int U4_CH = 16;           // wavefront steps (= skewed columns) per chunk
+constexpr int U4_INW = 64;          // input ring: chunk in use + the next one (complete) + one in flight, of 16 columns
+constexpr int U4_OUTW = 32;         // output ring: two chunks
+// rows are padded by one word: every lane reads the same column in a step, so the row stride must be odd (bank = lane + column)
+struct U4Smem { uint32_t in[33][U4_INW + 1]; uint32_t out[32][U4_OUTW + 1]; };     // 12.5 KB per warp => 16 warps per SM
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 {
@@ -285,8 +287,8 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
 {
     const uint32_t rb = J.row_bytes, H = J.height, npx = rb >> 2;
     const int nbands = (int)((H + 31) / 32);
-    const int NCH = (int)((npx + 31) / 32);            // pixel chunks per row
-    const int NSC = (int)((npx + 31 + 31) / 32);       // step chunks per band (31 steps of skew)
+    const int NSC = (int)((npx + 31 + U4_CH - 1) / U4_CH);   // step chunks per band (31 steps of skew)
+    // flushed[w] = (bands finished by warp w) * npx + pixels of the current band's last row that are in memory
     const int pw = (warp + U4_NW - 1) % U4_NW;         // producer of the row above my bands
     const bool out16 = ((J.out_pitch & 15) == 0) && ((((uintptr_t)J.out) & 15) == 0);
     int kband = 0;
@@ -302,29 +304,6 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
         const uint8_t* raw0 = J.raw + (size_t)r0 * (rb + 1) + 1;
         const uint8_t* bnd = band > 0 ? J.out + (size_t)(r0 - 1) * J.out_pitch : nullptr;
         const uint32_t nrows = min(32u, H - r0);
-
-        // ---- staging shared by both modes: chunk c = aligned 16-byte vectors [8c, 8c+8) of every row of the
-        // band (+ 4-byte words [32c, 32c+32) of the row above the band), issued two chunks ahead of use
-        const int NCHW = (int)((npx + 4 + 31) / 32);       // 16-byte aligned staging may need up to 4 extra words
-        auto load_chunk = [&](int c) {
-            if (c < NCHW) {
-                const uint32_t vi = (uint32_t)c * 8 + (lane & 7);       // 16-byte vector index within the row
-                const uint8_t* p = raw0 + (size_t)(lane >> 3) * (rb + 1);
-                for (uint32_t rr = lane >> 3; rr < nrows; rr += 4, p += 4 * (size_t)(rb + 1)) {
-                    const uint32_t m = (uint32_t)(uintptr_t)p & 15u;
-                    const uint32_t nv = (m + rb + 15) >> 4;
-                    if (vi < nv) cp_async16(&S->in[rr][(vi * 4) & (U4_INW - 1)], (p - m) + (size_t)vi * 16);
-                }
-                if (bnd && c < NCH) {
-                    // the producer must have flushed chunk c of its band's last row
-                    const int need = kprev * NCH + c + 1;
-                    while (flushed[pw] < need) __nanosleep(64);
-                    const uint32_t wi = (uint32_t)c * 32 + lane;
-                    if (wi < npx) cp_async4(&S->in[32][wi & (U4_INW - 1)], bnd + (size_t)wi * 4);
-                }
-            }
-            cp_async_commit();
-        };
 
         if (!anyP && !anyA) {
             // ---- row-parallel mode: only None/Sub/Up rows => no serial dependency except Sub's prefix sum.
@@ -360,7 +339,7 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
                 if (y0 == 0) {                                // block start: the row above the band
                     up0 = up1 = up2 = up3 = 0;
                     if (bnd) {
-                        const int need = kprev * NCH + min(4 * xb + 4, NCH);
+                        const int need = kprev * (int)npx + (int)min(128u * (uint32_t)(xb + 1), npx);
                         while (flushed[pw] < need) __nanosleep(32);
                         const uint32_t* bp = (const uint32_t*)(bnd + (size_t)px * 4);
                         if (px + 3 < npx && out16) { const uint4 t = __ldcg((const uint4*)bp); up0 = t.x; up1 = t.y; up2 = t.z; up3 = t.w; }
@@ -417,7 +396,7 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
                 if ((int)(y0 / 4) == ngroups - 1) {           // block end: publish it for the band below
                     __threadfence_block();
                     __syncwarp();
-                    if (lane == 0) flushed[warp] = kband * NCH + min(4 * xb + 4, NCH);
+                    if (lane == 0) flushed[warp] = kband * (int)npx + (int)min(128u * (uint32_t)(xb + 1), npx);
                 }
             };
 
@@ -429,61 +408,120 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
             continue;
         }
 
-        // ---- wavefront mode
-        const uint32_t mis16 = (uint32_t)(uintptr_t)rowaddr & 15u;
-        const uint32_t woff = mis16 >> 2, sh = (mis16 & 3u) * 8u;
+        // ---- wavefront mode. Step t: lane l works on pixel x = t - l of its row. Both rings are indexed by the
+        // *skewed* column t (row l's pixel x sits in column x + l), so every lane touches the same column in a step
+        // (one shared address computation, bank = lane) and the rings only need to hold the chunk in use and the next.
+        const uint32_t mis = (uint32_t)(uintptr_t)rowaddr & 3u, sh = mis * 8u;
         const uint32_t mS = f == 1 ? ~0u : 0u, mU = f == 2 ? ~0u : 0u, mA = f == 3 ? ~0u : 0u, mP = f == 4 ? ~0u : 0u;
-        auto flush_chunk = [&](int fc) {
-            if (out16) {
-                const uint32_t px = (uint32_t)fc * 32 + (lane & 7) * 4;
-                uint8_t* o = J.out + (size_t)(r0 + (lane >> 3)) * J.out_pitch + (size_t)px * 4;
-                for (uint32_t rr = lane >> 3; rr < nrows; rr += 4, o += 4 * (size_t)J.out_pitch) {
-                    if (px + 3 < npx) *(uint4*)o = *(const uint4*)&S->out[rr][px & (U4_OUTW - 1)];
-                    else for (uint32_t k = 0; k < 4 && px + k < npx; ++k) ((uint32_t*)o)[k] = S->out[rr][(px + k) & (U4_OUTW - 1)];
+        // staging / flushing: instruction k of a chunk handles rows 2k and 2k+1, 16 columns each (64-byte segments).
+        // Row rr starts at raw0 + rr*(rb+1); rb is a multiple of 4, so its misalignment is (m0 + rr) & 3 and the
+        // aligned word address of (row 2k+h, column col) is base[k&1] + k*kstep + 4*col with two lane constants.
+        const uint32_t hrow = lane >> 4, jcol = lane & 15;
+        const uint32_t m0 = (uint32_t)(uintptr_t)raw0 & 3u;
+        const uint32_t e0 = (m0 + hrow) & 3u;
+        const uint8_t* sbase0 = raw0 + (size_t)hrow * (rb + 1) - 4 * (size_t)hrow + 4 * (size_t)jcol - e0;
+        const uint8_t* sbase1 = sbase0 + e0 - (e0 ^ 2u);
+        const size_t kstep = 2 * (size_t)(rb + 1) - 8;
+        uint32_t* const sdst = &S->in[hrow][jcol];
+        uint8_t* const fbase = J.out + (size_t)(r0 + hrow) * J.out_pitch - 4 * (size_t)hrow + 4 * (size_t)jcol;
+        const size_t fstep = 2 * (size_t)J.out_pitch - 8;
+        const uint32_t* const fsrc = &S->out[hrow][jcol];
+        auto stage = [&](int c) {
+            if (c <= NSC) {                                   // one chunk past the last: the funnel reads column t + 1
+                const int xb = c * U4_CH + (int)jcol - (int)hrow;             // pixel index for k = 0
+                const uint32_t col = (uint32_t)(c * U4_CH) & (U4_INW - 1);
+                const uint8_t* p0 = sbase0 + (size_t)c * (4 * U4_CH);
+                const uint8_t* p1 = sbase1 + (size_t)c * (4 * U4_CH);
+                const bool interior = c * U4_CH >= 32 && (uint32_t)((c + 1) * U4_CH) <= npx && nrows == 32;
+                if (interior) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 16; ++k)
+                        cp_async4(sdst + 2 * k * (U4_INW + 1) + col, ((k & 1) ? p1 : p0) + k * kstep);
+                } else {
+#pragma unroll
+                    for (uint32_t k = 0; k < 16; ++k) {
+                        const int x = xb - 2 * (int)k;
+                        if (2 * k + hrow < nrows && x >= 0 && (uint32_t)x <= npx)
+                            cp_async4(sdst + 2 * k * (U4_INW + 1) + col, ((k & 1) ? p1 : p0) + k * kstep);
+                    }
                 }
+                if (bnd) {
+                    // the row above the band (skew 0): its producer must have it in memory up to this chunk
+                    const uint32_t xe = min((uint32_t)(c + 1) * U4_CH, npx);
+                    const int need = kprev * (int)npx + (int)xe;
+                    while (flushed[pw] < need) __nanosleep(64);
+                    const uint32_t x = (uint32_t)c * U4_CH + lane;
+                    if (lane < U4_CH && x < npx) cp_async4(&S->in[32][x & (U4_INW - 1)], bnd + (size_t)x * 4);
+                }
+            }
+            cp_async_commit();
+        };
+        auto flush = [&](int c) {
+            const int xb = c * U4_CH + (int)jcol - (int)hrow;
+            const uint32_t col = (uint32_t)(c * U4_CH) & (U4_OUTW - 1);
+            uint8_t* p = fbase + (size_t)c * (4 * U4_CH);
+            const bool interior = c * U4_CH >= 32 && (uint32_t)((c + 1) * U4_CH) <= npx && nrows == 32;
+            if (interior) {
+                uint32_t v[16];
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) v[k] = fsrc[2 * k * (U4_OUTW + 1) + col];
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) *(uint32_t*)(p + k * fstep) = v[k];
             } else {
-                const uint32_t px = (uint32_t)fc * 32 + lane;
-                if (px < npx) {
-                    uint8_t* o = J.out + (size_t)r0 * J.out_pitch + (size_t)px * 4;
-                    for (uint32_t rr = 0; rr < nrows; ++rr, o += J.out_pitch) *(uint32_t*)o = S->out[rr][px & (U4_OUTW - 1)];
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) {
+                    const int x = xb - 2 * (int)k;
+                    if (2 * k + hrow < nrows && x >= 0 && (uint32_t)x < npx) *(uint32_t*)(p + k * fstep) = fsrc[2 * k * (U4_OUTW + 1) + col];
                 }
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) flushed[warp] = kband * NCH + fc + 1;
+            // the band's last row (lane nrows-1) is in memory up to pixel 16(c+1) - (nrows-1)
+            const int done = (c + 1) * U4_CH - (int)(nrows - 1);
+            if (lane == 0) flushed[warp] = kband * (int)npx + (done < 0 ? 0 : done > (int)npx ? (int)npx : done);
         };
 
-        load_chunk(0);
-        load_chunk(1);
+        stage(0);
+        stage(1);
         uint32_t cur = 0, left = 0, upleft = 0;
-        for (int j = 0; j < NSC; ++j) {
-            load_chunk(j + 2);
+        const uint32_t* const inrow = &S->in[lane][0];
+        const uint32_t* const inbnd = &S->in[32][0];
+        uint32_t* const outrow = &S->out[lane][0];
+        const bool hasb = bnd != nullptr;
+        for (int c = 0; c < NSC; ++c) {
+            stage(c + 2);
             cp_async_wait<1>();
             __syncwarp();
-#pragma unroll 4
-            for (int s = 0; s < 32; ++s) {
-                const int x = j * 32 + s - lane;
+            const uint32_t cb = (uint32_t)(c * U4_CH) & (U4_INW - 1);
+            const uint32_t* const ip = inrow + cb;
+            const uint32_t* const bp = inbnd + cb;
+            uint32_t* const op = outrow + ((uint32_t)(c * U4_CH) & (U4_OUTW - 1));
+            const int x0 = c * U4_CH - lane;
+            uint32_t w0 = ip[0];
+#pragma unroll
+            for (int s2 = 0; s2 < U4_CH; ++s2) {
+                const int x = x0 + s2;
                 const uint32_t upsh = __shfl_up_sync(0xffffffffu, cur, 1);
-                const uint32_t bv = S->in[32][x & (U4_INW - 1)];
-                const uint32_t up = lane ? upsh : (bnd ? bv : 0u);
-                const bool active = valid && (uint32_t)x < npx;
-                const uint32_t w0 = S->in[lane][(x + woff) & (U4_INW - 1)];
-                const uint32_t w1 = S->in[lane][(x + woff + 1) & (U4_INW - 1)];
+                const uint32_t bv = bp[s2];
+                const uint32_t up = lane ? upsh : (hasb ? bv : 0u);
+                const uint32_t w1 = s2 + 1 < U4_CH ? ip[s2 + 1] : inrow[(cb + U4_CH) & (U4_INW - 1)];
                 const uint32_t raw = __funnelshift_r(w0, w1, sh);
+                w0 = w1;
                 const uint32_t L = x == 0 ? 0u : left, UL = x == 0 ? 0u : upleft;
                 uint32_t pred = (L & mS) | (up & mU);
                 if (anyA) pred |= __vhaddu4(L, up) & mA;
                 if (anyP) pred |= paeth4(L, up, UL) & mP;
                 const uint32_t nv = __vadd4(raw, pred);
-                if (active) { cur = nv; left = nv; S->out[lane][x & (U4_OUTW - 1)] = nv; }
+                if (valid && (uint32_t)x < npx) { cur = nv; left = nv; }
+                op[s2] = nv;
                 upleft = up;
             }
             __syncwarp();
-            if (j - 1 >= 0 && j - 1 < NCH) flush_chunk(j - 1);
+            flush(c);
         }
-        for (int fc = max(NSC - 1, 0); fc < NCH; ++fc) flush_chunk(fc);     // chunks not yet flushed by the loop above
         cp_async_wait<0>();
         __syncwarp();
+        if (lane == 0) flushed[warp] = (kband + 1) * (int)npx;
     }
 }
 
@@ -578,7 +616,7 @@ unfilter_rowpar_kernel(const UnfilterJob* jobs, int njobs, const InflateJob* inf
 // no shared-memory rings => 2x the resident warps), <false> handles every other image. Each CTA classifies its
 // image by scanning the filter bytes first.
 template <bool ROWPAR_ONLY>
-__global__ void __launch_bounds__(U4_NW * 32, ROWPAR_ONLY ? 6 : 2)
+__global__ void __launch_bounds__(U4_NW * 32, ROWPAR_ONLY ? 6 : 4)
 unfilter_kernel(const UnfilterJob* jobs, int njobs, int* status, const InflateJob* inf, int rowpar_warps)
 {
     extern __shared__ __align__(16) uint8_t u4_smem[];

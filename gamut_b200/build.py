@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-fmad=false",            # float bit-exactness with the reference's separate mul/add (scanline.d)
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    *(["-DLZ4_DEBUG"] if os.environ.get("LZ4_DEBUG") else []),
 ]
 
 

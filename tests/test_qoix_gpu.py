@@ -178,3 +178,22 @@ def test_sub_codec_batch_and_rejects(codecs, oracle):
                 assert np.array_equal(got, exp[0]) and b.images[i].pixel_type == exp[2]
     finally:
         b.free()
+
+
+def test_lz4_long_blocks_parallel_walk(codecs, oracle):
+    """Blocks long enough (>= 64 KB of LZ4 bytes) for the sub-chunk-parallel walk (lz4_spec/merge/scan/pwrite), plus
+    damaged copies that must fail -- or decode identically -- in both implementations."""
+    rng = np.random.default_rng(5)
+    for (h, w, seed) in [(768, 1024, 1), (600, 900, 2)]:
+        img = depth_map_la(h, w, seed, 2)
+        data = oracle.qoix_encode(img, 10, force_lz4=True)
+        assert len(data) > 4 * 16384 + 29
+        got = check_qoix(codecs, oracle, data)
+        assert np.array_equal(got[0], img)
+        for _ in range(6):
+            b = bytearray(data)
+            i = int(rng.integers(40, len(b) - 8))
+            b[i] ^= 1 << int(rng.integers(0, 8))
+            check_qoix(codecs, oracle, bytes(b))
+        check_qoix(codecs, oracle, data[:len(data) // 2])
+        check_qoix(codecs, oracle, data + b"\0" * 37)          # trailing bytes after the final sequence

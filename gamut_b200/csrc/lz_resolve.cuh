@@ -5,9 +5,10 @@
 // start is flagged in a bitmap (1 bit per output byte). One warp per stream then performs the copies in stream order:
 // the bitmap is scanned 4096 output bytes (128 words, 4 per lane) at a time; the matches found are taken 32 at a
 // time (one per lane); the records of the next 32 matches are loaded before the current 32 are copied, so that only
-// the source loads sit on the critical path. Inside a batch, a maximal prefix of matches whose sources end before
-// the first destination of the prefix is copied in parallel (lane per match up to 32 bytes, the whole warp for
-// longer ones); then the next prefix.
+// the source loads sit on the critical path. Inside a batch the short matches are copied together, one per lane: a
+// source byte that is itself produced by a match of the batch is traced back (by address arithmetic over warp
+// shuffles) to a byte that is already final, so the batch needs one memory round trip whatever its inner
+// dependencies; long matches are copied by the whole warp.
 #pragma once
 #include <stdint.h>
 
@@ -65,29 +66,63 @@ __device__ __forceinline__ void lzr_copy_lane(uint8_t* out, uint32_t dst, uint32
     }
 }
 
+constexpr uint32_t LZR_SHORT = 16;      // matches up to this length are copied one per lane, longer ones by the whole warp
+
+// One run of consecutive short matches (lanes lo..hi-1 of the batch, ascending destinations). A source byte that lies
+// inside the destination of an earlier match of the run (or of the match itself: overlapping copy) is not in memory
+// yet -- but its value is known to equal the byte `dist` further back, so the source ADDRESS is chased back through
+// the matches of the run (warp shuffles only) until it reaches a byte that is final: before the run's first
+// destination, or in a literal gap. All loads of the run are then independent: one memory round trip per run.
+__device__ __forceinline__ void lzr_copy_run(uint8_t* out, uint32_t dst, uint32_t len, uint32_t dist, uint32_t runm, int lane)
+{
+    const bool mine = (runm >> lane) & 1;
+    const int lo0 = __ffs(runm) - 1;
+    const uint32_t D0 = __shfl_sync(0xffffffffu, dst, lo0);
+    // search key, ascending over the lanes: 0 below the run (matches already copied), the destinations, ~0 above
+    const uint32_t key = mine ? dst : (lane < lo0 ? 0u : 0xffffffffu);
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, mine ? len : 0u);
+    uint8_t t[LZR_SHORT];
+#pragma unroll
+    for (uint32_t k = 0; k < LZR_SHORT; ++k) {
+        if (k < maxlen) {                                       // warp-uniform
+            const bool act = mine && k < len;
+            uint32_t a = dst - dist + k;
+            bool chasing = act && a >= D0;
+            while (__any_sync(0xffffffffu, chasing)) {
+                // largest lane i of the run with dst_i <= a
+                uint32_t i = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, key, (int)((i + step) & 31));
+                    if (i + step < 32 && v <= a) i += step;
+                }
+                const uint32_t di = __shfl_sync(0xffffffffu, key, (int)i), li = __shfl_sync(0xffffffffu, len, (int)i);
+                const uint32_t ti = __shfl_sync(0xffffffffu, dist, (int)i);
+                if (chasing) {
+                    if (((runm >> i) & 1) && di <= a && a - di < li) { a -= ti; chasing = a >= D0; }   // inside match i: same byte, dist_i back
+                    else chasing = false;                                           // a literal byte: final
+                }
+            }
+            if (act) t[k] = out[a];
+        }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < LZR_SHORT; ++k) if (mine && k < len) out[dst + k] = t[k];
+}
+
 __device__ __forceinline__ void lzr_copy_batch(uint8_t* out, const LzMatch& M, bool valid, int lane)
 {
     const uint32_t dst = M.dst, len = M.len, dist = M.dist;
-    const uint32_t src = dst - dist;
-    const uint32_t send = src + (len < dist ? len : dist);
     uint32_t rem = __ballot_sync(0xffffffffu, valid);
+    const uint32_t longm = __ballot_sync(0xffffffffu, valid && len > LZR_SHORT);
     while (rem) {
         const int first = __ffs(rem) - 1;
-        const uint32_t D0 = __shfl_sync(0xffffffffu, dst, first);
-        const bool okl = ((rem >> lane) & 1) && (lane == first || send <= D0);
-        const uint32_t okm = __ballot_sync(0xffffffffu, okl);
-        const uint32_t bad = rem & ~okm;
-        const uint32_t grp = bad ? (rem & ((1u << (__ffs(bad) - 1)) - 1)) : rem;
-        const bool mine = (grp >> lane) & 1;
-        if (mine && len <= 32) lzr_copy_lane(out, dst, src, len, dist);
-        uint32_t longm = __ballot_sync(0xffffffffu, mine && len > 32);
-        while (longm) {
-            const int l = __ffs(longm) - 1;
-            longm &= longm - 1;
-            const uint32_t d = __shfl_sync(0xffffffffu, dst, l), s = __shfl_sync(0xffffffffu, src, l);
-            const uint32_t ln = __shfl_sync(0xffffffffu, len, l), di = __shfl_sync(0xffffffffu, dist, l);
+        if ((longm >> first) & 1) {
+            // a long match: the whole warp copies it (x % dist: every byte comes from the dist bytes before the
+            // destination, so no chunk depends on another)
+            const uint32_t d = __shfl_sync(0xffffffffu, dst, first), ln = __shfl_sync(0xffffffffu, len, first);
+            const uint32_t di = __shfl_sync(0xffffffffu, dist, first), s = d - di;
             const bool ov = di < ln;
-            // with x % di every byte comes from the di bytes before the destination: no chunk depends on another
             for (uint32_t c = 0; c < ln; c += 256) {
                 uint8_t t[8];
 #pragma unroll
@@ -95,9 +130,15 @@ __device__ __forceinline__ void lzr_copy_batch(uint8_t* out, const LzMatch& M, b
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { const uint32_t x = c + (uint32_t)k * 32 + lane; if (x < ln) out[d + x] = t[k]; }
             }
+            rem &= ~(1u << first);
+        } else {
+            // the run of short matches up to the next long one
+            const uint32_t ahead = longm & rem;
+            const uint32_t runm = ahead ? (rem & ((1u << (__ffs(ahead) - 1)) - 1)) : rem;
+            lzr_copy_run(out, dst, len, dist, runm, lane);
+            rem &= ~runm;
         }
         __syncwarp();
-        rem &= ~grp;
     }
 }
 

@@ -249,22 +249,31 @@ __device__ __forceinline__ int p10_out_l(const uint8_t* out, uint32_t W, uint32_
     return (int)(__ldcg((const uint16_t*)out + ((size_t)y * W + x) * CH) >> 6);
 }
 
+constexpr int P10_RECON_WARPS = 8;     // warps per image: warp w owns bands w, w+8, ...; a band follows the band above
+                                       // as soon as that band's last row is two blocks ahead (progress counters)
 template <int CH>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * P10_RECON_WARPS)
 p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__ ndecoded, const int* __restrict__ status)
 {
+    __shared__ volatile uint32_t prog[P10_RECON_WARPS];     // (bands finished by the warp) * (nblocks+1) + blocks of the current band's last row in memory
     const P10Image& im = imgs[blockIdx.x];
     if (im.channels != CH || !status[im.image]) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < P10_RECON_WARPS) prog[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t W = im.w, H = im.h, WP = im.wp;
     const uint32_t nblocks = WP >> 3;
     const unsigned long long ndec = ndecoded[blockIdx.x];
     uint16_t* out16 = (uint16_t*)im.out;
     const bool vec_ok = (W & 7) == 0 && (((uintptr_t)im.out) & 15) == 0;
 
-    for (uint32_t y0 = 0; y0 < H; y0 += 32) {
+    const int pw = (warp + P10_RECON_WARPS - 1) % P10_RECON_WARPS;      // the warp that owns the band above mine
+    uint32_t kband = 0;
+    for (uint32_t y0 = (uint32_t)warp * 32; y0 < H; y0 += 32 * P10_RECON_WARPS, ++kband) {
         const uint32_t y = y0 + lane;
         const bool row_ok = y < H;
+        const int lastlane = (int)min(31u, H - 1 - y0);
+        const uint32_t kprev_base = (y0 ? (y0 / 32 - 1) / P10_RECON_WARPS : 0) * (nblocks + 1);
         // start block of every lane: one block behind the lane above, later when the row starts inside a run
         const uint32_t info = (row_ok && (unsigned long long)y * W < ndec) ? im.rowinfo[y] : 0u;
         const bool wrap = info != 0;
@@ -296,6 +305,12 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) up[i] = __shfl_up_sync(0xffffffffu, prevres[i], 1);
             if (active) {
+                if (lane == 0 && y0 > 0) {
+                    // the row above belongs to another warp: wait until it is in memory as far as this step reads it
+                    uint32_t need = min(blk + 2, nblocks);
+                    if (blk == 0 && wrap) need = max(need, min((uint32_t)(max(xn, 0) >> 3) + 1u, nblocks));
+                    while (prog[pw] < kprev_base + need) __nanosleep(40);
+                }
                 if (blk == 0) {
                     ra = __ldg((const uint4*)rrow); rb = __ldg((const uint4*)rrow + 1);
                     if (frommem) {
@@ -357,9 +372,11 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
                     }
                 }
                 ra = na; rb = nb;
+                if (lane == lastlane) { __threadfence_block(); prog[warp] = kband * (nblocks + 1) + blk + 1; }
             }
             __syncwarp();       // orders this block's stores before the loads of the lanes that read rows from memory
         }
         __syncwarp();
+        if (lane == 0) { __threadfence_block(); prog[warp] = (kband + 1) * (nblocks + 1); }
     }
 }

@@ -682,8 +682,8 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         }
         p10_scan_kernel<<<ni, 256, 0, st>>>(dI, chunks, entries, ndec);
         p10_write_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, entries);
-        p10_recon_kernel<1><<<ni, 32, 0, st>>>(dI, ndec, d_status.as<int>());
-        p10_recon_kernel<2><<<ni, 32, 0, st>>>(dI, ndec, d_status.as<int>());
+        p10_recon_kernel<1><<<ni, 32 * P10_RECON_WARPS, 0, st>>>(dI, ndec, d_status.as<int>());
+        p10_recon_kernel<2><<<ni, 32 * P10_RECON_WARPS, 0, st>>>(dI, ndec, d_status.as<int>());
         count_launch(4);
     }
     cudaEventRecord(ev[3], st);

@@ -301,10 +301,14 @@ infp_find_kernel(const InflateJob* jobs, const InfPar* par, const uint32_t* tile
 
 // ---------------------------------------------------------------------------------------------
 // 2. verify: the code lengths of the header must give complete literal/length and distance codes.
+// USE_LUT: the code-length code is decoded through a 128-entry per-thread table in shared memory (worth its set-up
+// cost for the headers that survive the first, short pass) instead of the canonical compare chain in registers.
+template <bool USE_LUT>
 __global__ void __launch_bounds__(128)
 infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, uint32_t vq_cap, const uint32_t* qcount,
                    int max_syms, uint2* vq_next, uint32_t vq_next_cap, uint32_t* qcount_next)
 {
+    __shared__ uint8_t lut[USE_LUT ? 128 : 1][128];          // [7 code bits][thread]: symbol << 3 | length
     uint32_t n = *qcount;
     if (n > vq_cap) n = vq_cap;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
@@ -341,7 +345,24 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
             }
         }
         uint64_t cl_sorted_lo = 0, cl_sorted_hi = 0;
-        {
+        if (USE_LUT) {
+            // canonical codes in symbol order; the code is complete (checked by the find kernel), so every one of the
+            // 128 patterns is covered and the table needs no clearing
+            int nxt[8];
+#pragma unroll
+            for (int l = 0; l < 8; ++l) nxt[l] = cl_first[l];
+#pragma unroll
+            for (int sy = 0; sy < 19; ++sy) {
+                const int l = (sy < 10) ? (cl_lens_lo >> (3 * sy)) & 7 : (cl_lens_hi >> (3 * (sy - 10))) & 7;
+                if (l) {
+                    int code = 0;
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) if (l == k) { code = nxt[k]; nxt[k] = code + 1; }
+                    const uint32_t rev = __brev((uint32_t)code) >> (32 - l);
+                    for (uint32_t k = rev; k < 128; k += (1u << l)) lut[k][threadIdx.x] = (uint8_t)((sy << 3) | l);
+                }
+            }
+        } else {
             int k = 0;
 #pragma unroll
             for (int l = 1; l < 8; ++l) {
@@ -363,17 +384,22 @@ infp_verify_kernel(const InflateJob* jobs, const InfPar* par, const uint2* vq, u
         while (i < total) {
             if (++nsym > max_syms) break;
             R.refill();
-            const uint32_t rev = __brev(R.peek(7)) >> 25;
             int sym = -1, len = 0;
+            if (USE_LUT) {
+                const uint32_t e = lut[R.peek(7)][threadIdx.x];
+                len = (int)(e & 7); sym = len ? (int)(e >> 3) : -1;
+            } else {
+                const uint32_t rev = __brev(R.peek(7)) >> 25;
 #pragma unroll
-            for (int l = 1; l < 8; ++l) {
-                if (sym < 0) {
-                    const int cc = (int)(rev >> (7 - l));
-                    const int d = cc - cl_first[l];
-                    if (d >= 0 && d < cl_count[l]) {
-                        const int k = cl_fsym[l] + d;
-                        sym = (k < 12) ? (int)((cl_sorted_lo >> (5 * k)) & 31) : (int)((cl_sorted_hi >> (5 * (k - 12))) & 31);
-                        len = l;
+                for (int l = 1; l < 8; ++l) {
+                    if (sym < 0) {
+                        const int cc = (int)(rev >> (7 - l));
+                        const int d = cc - cl_first[l];
+                        if (d >= 0 && d < cl_count[l]) {
+                            const int k = cl_fsym[l] + d;
+                            sym = (k < 12) ? (int)((cl_sorted_lo >> (5 * k)) & 31) : (int)((cl_sorted_hi >> (5 * (k - 12))) & 31);
+                            len = l;
+                        }
                     }
                 }
             }

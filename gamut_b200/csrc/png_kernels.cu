@@ -109,8 +109,11 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
         for (int pass = 0; pass < 4; ++pass) {
             uint2* qout = (pass & 1) ? d_vq3 : d_vq2;
             uint32_t* cout = d_ctr + INFP_CTR_Q2 + pass;
-            infp_verify_kernel<<<sm_count() * (pass == 0 ? 8 : 4), 128, 0, st>>>(d_jobs, d_par, qin, qin_cap, cin, budgets[pass],
-                                                                                 pass < 3 ? qout : nullptr, vq2_cap, pass < 3 ? cout : nullptr);
+            if (pass == 0)
+                infp_verify_kernel<false><<<sm_count() * 8, 128, 0, st>>>(d_jobs, d_par, qin, qin_cap, cin, budgets[pass], qout, vq2_cap, cout);
+            else
+                infp_verify_kernel<true><<<sm_count() * 4, 128, 0, st>>>(d_jobs, d_par, qin, qin_cap, cin, budgets[pass],
+                                                                         pass < 3 ? qout : nullptr, vq2_cap, pass < 3 ? cout : nullptr);
             qin = qout; qin_cap = vq2_cap; cin = cout;
         }
     }

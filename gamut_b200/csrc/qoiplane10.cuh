@@ -249,7 +249,7 @@ __device__ __forceinline__ int p10_out_l(const uint8_t* out, uint32_t W, uint32_
     return (int)(__ldcg((const uint16_t*)out + ((size_t)y * W + x) * CH) >> 6);
 }
 
-constexpr int P10_RECON_WARPS = 8;     // warps per image: warp w owns bands w, w+8, ...; a band follows the band above
+constexpr int P10_RECON_WARPS = 8;  // warps per image: warp w owns bands w, w+8, ...; a band follows the band above
                                        // as soon as that band's last row is two blocks ahead (progress counters)
 template <int CH>
 __global__ void __launch_bounds__(32 * P10_RECON_WARPS)

@@ -51,7 +51,7 @@ class ConvertWorkload:
     name = "PixelType convert rgba8<->rgbaf32 8192x8192 (BASELINE configs[1])"
     dtype = "f32"
     default_steps = 100
-    default_e2e_steps = 3
+    default_e2e_steps = 9
     W = H = 8192
     bytes_per_px = 20            # 4 B rgba8 + 16 B rgbaf32 per direction
     e2e_api = ("gb200_scanlines_convert (host pointers, pinned); forward and reverse issued concurrently from two "
@@ -223,7 +223,7 @@ class PngWorkload:
     name = "PNG 8-bit RGBA decode + unfilter, batch 1024 images 1920x1080 (BASELINE configs[2])"
     dtype = "u8"
     default_steps = 3
-    default_e2e_steps = 1
+    default_e2e_steps = 5
     W, H = 1920, 1080
     DISTINCT = 16
     e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back to pinned host memory with gb200_batch_download)"
@@ -391,7 +391,7 @@ class _BatchDecodeWorkload:
     dtype = "u8"
     scaling = "strong"
     default_steps = 3
-    default_e2e_steps = 1
+    default_e2e_steps = 5
     DISTINCT = 8
 
     def _setup(self, rank, world, args, total_default):

@@ -1,5 +1,7 @@
 // common.cu -- error state, device init, caching allocator, launch counter.
 #include "common.h"
+#include <thread>
+#include <vector>
 #include <stdarg.h>
 #include <mutex>
 #include <map>
@@ -7,6 +9,7 @@
 #include <atomic>
 
 namespace gb {
+
 
 static thread_local char t_err[512] = {0};
 static std::atomic<long long> g_launches{0};
@@ -153,6 +156,31 @@ cudaStream_t thread_stream(int idx)
         if (cudaStreamCreateWithFlags(&s[idx], cudaStreamNonBlocking) != cudaSuccess) { s[idx] = nullptr; }
     }
     return s[idx];
+}
+
+void host_copy_parallel(const HostCopy* copies, size_t count)
+{
+    size_t total = 0;
+    for (size_t i = 0; i < count; ++i) total += copies[i].n;
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = total < (8u << 20) ? 1u : (hw >= 16 ? 8u : hw >= 4 ? hw / 2 : 1u);
+    if (nt <= 1) { for (size_t i = 0; i < count; ++i) memcpy(copies[i].dst, copies[i].src, copies[i].n); return; }
+    // thread t takes the byte range [t, t+1) * total / nt of the concatenated copies
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+        th.emplace_back([=]() {
+            const size_t lo = total * t / nt, hi = total * (t + 1) / nt;
+            size_t pos = 0;
+            for (size_t i = 0; i < count && pos < hi; ++i) {
+                const size_t a = pos, b = pos + copies[i].n;
+                pos = b;
+                if (b <= lo) continue;
+                const size_t s0 = a < lo ? lo - a : 0, s1 = (b > hi ? hi : b) - a;
+                if (s1 > s0) memcpy((char*)copies[i].dst + s0, (const char*)copies[i].src + s0, s1 - s0);
+            }
+        });
+    }
+    for (auto& x : th) x.join();
 }
 
 } // namespace gb

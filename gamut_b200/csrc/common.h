@@ -38,6 +38,11 @@ void  dev_trim();
 void* pinned_alloc(size_t bytes);
 void  pinned_free(void* p);
 
+// Host-side staging copies (pageable caller memory -> pinned staging) of a batch, spread over a few threads: one
+// memcpy thread moves ~10 GB/s, which would otherwise dominate the end-to-end time of a batch decode.
+struct HostCopy { void* dst; const void* src; size_t n; };
+void host_copy_parallel(const HostCopy* copies, size_t count);
+
 // The library's own non-blocking streams for host-pointer entry points (four per thread; index 0 is
 // the default, the others are used to overlap H2D / kernel / D2H of consecutive bands).
 cudaStream_t thread_stream(int idx = 0);

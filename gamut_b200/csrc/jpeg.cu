@@ -908,13 +908,14 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         uint8_t* h_stage = nullptr;
         if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
         std::vector<int> host_fail((size_t)m, 0);
+        std::vector<HostCopy> hcopies;
         for (int k = 0; k < m; ++k) {
             const int i = live[li + k];
             const Parsed& p = P[i];
             JpegImage& J = imgs[k];
             memset(&J, 0, sizeof(J));
             if (files_dev) J.data = files_dev[i];
-            else { memcpy(h_stage + file_off[k], files[i], lens[i]); J.data = d_files.as<uint8_t>() + file_off[k]; }
+            else { hcopies.push_back(HostCopy{h_stage + file_off[k], files[i], lens[i]}); J.data = d_files.as<uint8_t>() + file_off[k]; }
             J.data_len = (uint32_t)lens[i];
             J.width = p.width; J.height = p.height; J.scan_type = p.scan_type; J.comps = p.comps;
             J.mcus_per_row = p.mcus_per_row; J.mcus_per_col = p.mcus_per_col; J.blocks_per_mcu = p.blocks_per_mcu; J.tiles_per_mcu = p.tiles_per_mcu;
@@ -999,6 +1000,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         for (auto& e : ev) cudaEventCreate(&e);
         bool okc = true;
         cudaEventRecord(ev[0], st);
+        host_copy_parallel(hcopies.data(), hcopies.size());
         if (!files_dev) okc &= cuda_ok(cudaMemcpyAsync(d_files.p, h_stage, file_total, cudaMemcpyHostToDevice, st), "files", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_imgs.p, imgs.data(), sizeof(JpegImage) * m, cudaMemcpyHostToDevice, st), "imgs", __FILE__, __LINE__);
         if (!segs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);

@@ -283,6 +283,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(idat_total); if (!h_stage) { delete B; return nullptr; } }
         uint64_t max_pixels = 1;
         int rowpar_threads = 32;
+        std::vector<HostCopy> hcopies;
         for (int k = 0; k < m; ++k) {
             const int i = pending[k];
             Plan& P = plans[i];
@@ -290,7 +291,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
             size_t o = 0;
             for (auto& sg : P.H.idat) {
                 if (files_dev) segs.push_back(Segment{files_dev[i] + sg.first, idat + o, sg.second});
-                else memcpy(h_stage + idat_off[k] + o, files[i] + sg.first, sg.second);
+                else hcopies.push_back(HostCopy{h_stage + idat_off[k] + o, files[i] + sg.first, sg.second});
                 o += sg.second;
             }
             if (!files_dev) memset(h_stage + idat_off[k] + o, 0, al(P.H.ioff + 32) - o);
@@ -329,6 +330,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
                 uint64_t px = (uint64_t)P.H.w * P.H.h; if (px > max_pixels) max_pixels = px;
             }
         }
+        host_copy_parallel(hcopies.data(), hcopies.size());
         DevBuf d_ij(sizeof(InflateJob) * (size_t)m), d_uj(sizeof(UnfilterJob) * (ujobs.size() + 1)),
                d_fj(sizeof(FinishJob) * (fjobs.size() + 1)), d_sg(sizeof(Segment) * (segs.size() + 1));
         if (!d_ij.p || !d_uj.p || !d_fj.p || !d_sg.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }

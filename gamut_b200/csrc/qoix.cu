@@ -572,13 +572,14 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     uint8_t* h_stage = nullptr;
     if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
     std::vector<Lz4Job> lz; std::vector<P10Image> pj;
+    std::vector<HostCopy> hcopies;
     size_t lzbm_total = 0;
     uint32_t lz_chunks = 0;
     size_t rec_total = 0, row_total = 0; uint32_t total_chunks = 0;
     std::vector<SubJob> sub[4]; size_t sub_rows_total = 0;
     for (int i : live) {
         const uint8_t* dev = files_dev ? files_dev[i] : d_files.as<uint8_t>() + file_off[i];
-        if (!files_dev) memcpy(h_stage + file_off[i], files[i], lens[i]);
+        if (!files_dev) hcopies.push_back(HostCopy{h_stage + file_off[i], files[i], lens[i]});
         const uint8_t* stream = dev; uint32_t ssize = (uint32_t)lens[i];
         if (P[i].compression == 1) {
             uint8_t* dec = d_lz.as<uint8_t>() + lz_off[i];
@@ -608,6 +609,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         total_chunks += J.nchunks; rec_total += al((size_t)J.wp * J.h * 4); row_total += al((size_t)J.h * 4);
         pj.push_back(J);
     }
+    host_copy_parallel(hcopies.data(), hcopies.size());
     DevBuf d_recs(rec_total), d_rows(row_total), d_chunks(sizeof(P10Chunk) * ((size_t)total_chunks + 1)),
            d_entries(sizeof(P10Entry) * ((size_t)total_chunks + 1)), d_dirty(2 * al(total_chunks) + 256), d_misc(256 + 4 * pj.size());
     if (!d_recs.p || !d_rows.p || !d_chunks.p || !d_entries.p || !d_dirty.p || !d_misc.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }

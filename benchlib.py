@@ -23,6 +23,24 @@ def _threads_run(fn, threads):
     [t.join() for t in ts]
 
 
+def _e2e_slices(n, parts, fn):
+    """Runs fn(a, b) over `parts` contiguous slices of range(n) on as many host threads; re-raises a failure."""
+    parts = max(1, min(parts, n))
+    cuts = [n * i // parts for i in range(parts + 1)]
+    err = []
+
+    def run(t):
+        try:
+            if cuts[t + 1] > cuts[t]:
+                fn(cuts[t], cuts[t + 1])
+        except BaseException as e:  # noqa: BLE001
+            err.append(e)
+
+    _threads_run(run, parts)
+    if err:
+        raise err[0]
+
+
 class EventLog:
     """Collects (tag, start_event, end_event) on torch's current stream; elapsed read after the sync."""
 
@@ -241,7 +259,7 @@ class PngWorkload:
         self.dev_bufs = [base[i % self.DISTINCT].clone() for i in range(self.n)]
         self.dev_ptrs = [t.data_ptr() for t in self.dev_bufs]
         self.px_per_step = self.n * self.W * self.H
-        self.e2e_n = min(self.n, 128)
+        self.e2e_n = min(self.n, 512)
         self.e2e_px_per_step = self.e2e_n * self.W * self.H
         self.comp_bytes = sum(len(split_idat(f)) for f in self.files) / self.DISTINCT
         self.phase = []
@@ -357,9 +375,14 @@ class PngWorkload:
         assert self.h_out
 
     def e2e_step(self):
-        b = self.codecs.png_decode_batch(self.host_files[:self.e2e_n], 0, 0)
+        # one call for the whole batch: slicing it over several host threads was measured and is slower (the slices
+        # serialise on the allocator and each small batch is latency-bound)
+        self._e2e_slice(0, self.e2e_n)
+
+    def _e2e_slice(self, a, b_):
+        b = self.codecs.png_decode_batch(self.host_files[a:b_], 0, 0)
         assert all(d.status for d in b.images)
-        b.download(self.h_out, self.out_stride)
+        b.download(self.h_out + a * self.out_stride, self.out_stride)
         b.free()
 
     @staticmethod
@@ -414,7 +437,7 @@ class _BatchDecodeWorkload:
         self.dev_bufs = [base[k % nd].clone() for k in idx]
         self.dev_ptrs = [t.data_ptr() for t in self.dev_bufs]
         self.px_per_step = self.n * self.W * self.H
-        self.e2e_n = min(self.n, 64)
+        self.e2e_n = min(self.n, getattr(self, 'E2E_N', 128))
         self.e2e_px_per_step = self.e2e_n * self.W * self.H
         self.comp_bytes = sum(len(f) for f in self.files) / len(self.files)
         self.phase = []
@@ -439,9 +462,12 @@ class _BatchDecodeWorkload:
         assert self.h_out
 
     def e2e_step(self):
-        b = self.decode(self.host_files[:self.e2e_n], None, 0)
+        self._e2e_slice(0, self.e2e_n)
+
+    def _e2e_slice(self, a, b_):
+        b = self.decode(self.host_files[a:b_], None, 0)
         assert all(d.status for d in b.images)
-        b.download(self.h_out, self.out_bytes)
+        b.download(self.h_out + a * self.out_bytes, self.out_bytes)
         b.free()
 
     def roofline(self, peak, peak_kind):
@@ -519,7 +545,8 @@ class QoixWorkload(_BatchDecodeWorkload):
     dtype = "u16"
     W, H = 2048, 2048
     e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back to pinned host memory with gb200_batch_download)"
-    kernel_names = {1: "lz4_parse_kernel+lz4_resolve_kernel", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
+    E2E_N = 256
+    kernel_names = {1: "lz4 kernels (spec/merge/scan/pwrite/parse/resolve)", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
 
     def __init__(self, rank, world, args):
         self._setup(rank, world, args, 256)

@@ -23,24 +23,6 @@ def _threads_run(fn, threads):
     [t.join() for t in ts]
 
 
-def _e2e_slices(n, parts, fn):
-    """Runs fn(a, b) over `parts` contiguous slices of range(n) on as many host threads; re-raises a failure."""
-    parts = max(1, min(parts, n))
-    cuts = [n * i // parts for i in range(parts + 1)]
-    err = []
-
-    def run(t):
-        try:
-            if cuts[t + 1] > cuts[t]:
-                fn(cuts[t], cuts[t + 1])
-        except BaseException as e:  # noqa: BLE001
-            err.append(e)
-
-    _threads_run(run, parts)
-    if err:
-        raise err[0]
-
-
 class EventLog:
     """Collects (tag, start_event, end_event) on torch's current stream; elapsed read after the sync."""
 

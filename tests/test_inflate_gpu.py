@@ -60,6 +60,11 @@ def corpus():
         "tiny": deflate(b"abc", 6),
         "empty": deflate(b"", 6),
         "level0": deflate(big[:300_000], 0),
+        # memLevel 1 / 2: blocks of ~128 / ~256 symbols, i.e. several block headers per 1024-bit candidate slot --
+        # most blocks are then found by the stream walker itself, not by the candidate search
+        "tinyblocks1": deflate(big[:600_000], 6, mem=1),
+        "tinyblocks2": deflate(texty(700_000, 9), 9, mem=2),
+        "zeros_then_photo": deflate(bytes(1_000_000) + big[:1_000_000], 4, mem=3),
     }
     return items
 

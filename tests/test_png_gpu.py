@@ -150,3 +150,20 @@ def test_config3_shape_1080p_rgba(codecs, oracle):
     img = synth(1080, 1920, 4, 8, 42)
     data = write_png(img, 6, 8, filters=(4, 4, 3, 1, 2, 4, 0, 3), level=6, idat_split=65536)
     check(codecs, oracle, data)
+
+
+def test_rgba8_wavefront_geometry(codecs, oracle):
+    """Widths/heights around every boundary of the 4-byte-pixel wavefront kernel (16-column chunks, 32-row bands,
+    31 steps of skew, misaligned row starts): RGBA8 and LA16 with every filter mix, bit-exact against the oracle."""
+    rng = np.random.default_rng(77)
+    shapes = [(1, 1), (1, 40), (2, 15), (3, 16), (5, 17), (31, 31), (32, 32), (33, 33), (34, 47), (40, 48), (63, 49),
+              (64, 64), (65, 65), (97, 95), (100, 129), (130, 481), (37, 1000)]
+    mixes = [4, 3, (4, 3), (0, 1, 2, 3, 4), (2, 4, 4, 1, 3, 0, 4), (4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+             0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3)]
+    for (h, w) in shapes:
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[:, :, 3] = (img[:, :, 3] // 64) * 64 + 63            # long flat runs in one channel
+        filt = mixes[(h * 7 + w) % len(mixes)]
+        check(codecs, oracle, write_png(img, 6, 8, filters=filt))
+        la = rng.integers(0, 65536, (h, w, 2)).astype(np.uint16)
+        check(codecs, oracle, write_png(la, 4, 16, filters=mixes[(h + w) % len(mixes)]), 0, 1)

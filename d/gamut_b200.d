@@ -88,6 +88,20 @@ extern(C)
     gb200_batch* gb200_qoix_decode_batch(int n, const(ubyte*)* files, const(size_t)* lens,
                                          const(ubyte*)* files_dev, int flags, void* stream);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
+    int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
+    void* gb200_device_alloc(size_t bytes);
+    void gb200_device_free(void* p);
+    void gb200_device_trim();
+    int gb200_sm_count();
+    int gb200_batch_download(const(gb200_batch)* b, ubyte* dst_host, size_t stride);
+    void gb200_batch_timing(const(gb200_batch)* b, float* phase_ms8, double* host_parse_ms);
+
+    // kernel-level entries (device-resident data): row unfilter and inflate on their own
+    int gb200_png_unfilter_device(const(ubyte)* raw, size_t raw_stride, ubyte* out_, size_t out_stride,
+                                  int n_images, int row_bytes, int height, int bpp, int* status_dev, void* stream);
+    int gb200_inflate_device(int n, const(ubyte*)* in_dev, const(uint)* in_lens, ubyte** out_dev, const(uint)* out_caps,
+                             int parse_header, uint* out_lens_dev, int* statuses_dev, void* stream);
+    void gb200_inflate_set_mode(int parallel);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,195 @@
+"""CPU models of the ideas behind the parallel device decoders (no GPU, no product code on the path): they pin the
+*properties* the CUDA kernels rely on, with independent libraries (zlib via ctypes, liblz4) as the judges.
+
+ * paeth: the 26-instruction packed-byte Paeth of csrc/png_kernels.cu is a re-derivation (two compares instead of
+   five); checked against the PNG/stb formula (stbdec.d:1390-1401) for all 2^24 (a, b, c);
+ * deflate: every dynamic-Huffman block of a zlib stream is found by the brute-force header search of
+   csrc/inflate_par.cuh (BTYPE = 2, HLIT/HDIST <= 29, complete code-length code, complete literal/length and distance
+   codes), judged by zlib's own block boundaries (inflate with Z_BLOCK);
+ * lz4: the token chain of an LZ4 block synchronises itself: a walk started at an arbitrary byte meets the true chain
+   (csrc/qoix.cu lz4_spec / lz4_merge kernels)."""
+import ctypes as C
+import ctypes.util
+import zlib
+
+import numpy as np
+import pytest
+
+
+def test_paeth_two_compare_identity():
+    a, b, c = np.meshgrid(np.arange(256, dtype=np.int32), np.arange(256, dtype=np.int32), np.arange(256, dtype=np.int32), indexing="ij")
+    a, b, c = a.ravel(), b.ravel(), c.ravel()
+    p = a + b - c
+    pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+    ref = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+    PA, PB, T = np.abs(b - c), np.abs(a - c), np.abs(a - b)
+    U = np.abs(PA - PB)
+    le = PA <= PB
+    q = np.where(le, PA, PB)
+    V = np.where(T == U, 255, U)            # same sign of a-c and b-c  <=>  |a-b| == ||b-c| - |a-c||
+    got = np.where(q <= V, np.where(le, a, b), c)
+    assert np.array_equal(got, ref)
+
+
+# ---- deflate block boundaries from zlib itself ---------------------------------------------------------------
+class _ZStream(C.Structure):
+    _fields_ = [("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in", C.c_ulong), ("next_out", C.c_void_p),
+                ("avail_out", C.c_uint), ("total_out", C.c_ulong), ("msg", C.c_char_p), ("state", C.c_void_p),
+                ("zalloc", C.c_void_p), ("zfree", C.c_void_p), ("opaque", C.c_void_p), ("data_type", C.c_int),
+                ("adler", C.c_ulong), ("reserved", C.c_ulong)]
+
+
+def _block_starts(z: bytes):
+    """Bit positions at which zlib's inflate reports a block boundary (Z_BLOCK), i.e. where block headers start."""
+    name = ctypes.util.find_library("z")
+    if not name:
+        pytest.skip("libz not found")
+    L = C.CDLL(name)
+    s = _ZStream()
+    L.zlibVersion.restype = C.c_char_p
+    assert L.inflateInit_(C.byref(s), L.zlibVersion(), C.sizeof(_ZStream)) == 0
+    src = C.create_string_buffer(z, len(z))
+    out = C.create_string_buffer(1 << 20)
+    s.next_in = C.cast(src, C.c_void_p); s.avail_in = len(z)
+    starts, last = [], []
+    while True:
+        s.next_out = C.cast(out, C.c_void_p); s.avail_out = len(out)
+        r = L.inflate(C.byref(s), 5)                      # Z_BLOCK
+        if s.data_type & 128:
+            starts.append(int(s.total_in) * 8 - (s.data_type & 63))
+            last.append(bool(s.data_type & 64))
+        if r == 1 or r < 0:
+            break
+    L.inflateEnd(C.byref(s))
+    assert r == 1
+    # the first report is the end of the zlib header = start of block 0; the final one is the end of the stream
+    return starts[:-1]
+
+
+_ORDER = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+
+
+def _header_ok(bits: np.ndarray, p: int) -> bool:
+    """The find + verify filters of inflate_par.cuh at bit position p (bits: one uint8 per stream bit)."""
+    def get(q, n):
+        v = 0
+        for i in range(n):
+            v |= int(bits[q + i]) << i
+        return v
+    if p + 17 + 57 > len(bits) or get(p + 1, 2) != 2:
+        return False
+    hlit, hdist, hclen = get(p + 3, 5), get(p + 8, 5), get(p + 13, 4)
+    if hlit > 29 or hdist > 29:
+        return False
+    cl = [0] * 19
+    q = p + 17
+    for i in range(hclen + 4):
+        cl[_ORDER[i]] = get(q, 3); q += 3
+    if sum(128 >> l for l in cl if l) != 128:
+        return False
+    # canonical code of the code-length code
+    codes, code = {}, 0
+    for l in range(1, 8):
+        for sym in range(19):
+            if cl[sym] == l:
+                codes[(l, code)] = sym; code += 1
+        code <<= 1
+    total, nlit = hlit + 257 + hdist + 1, hlit + 257
+    lens, prev = [], 0
+    while len(lens) < total:
+        code = 0; sym = None
+        for l in range(1, 8):
+            if q >= len(bits):
+                return False
+            code = (code << 1) | int(bits[q]); q += 1
+            if (l, code) in codes:
+                sym = codes[(l, code)]; break
+        if sym is None:
+            return False
+        if sym < 16:
+            lens.append(sym); prev = sym; continue
+        if sym == 16:
+            if not lens:
+                return False
+            rep, val = 3 + get(q, 2), prev; q += 2
+        elif sym == 17:
+            rep, val = 3 + get(q, 3), 0; q += 3
+        else:
+            rep, val = 11 + get(q, 7), 0; q += 7
+        if len(lens) + rep > total:
+            return False
+        lens += [val] * rep; prev = val
+    lit, dist = lens[:nlit], lens[nlit:]
+    if lit[256] == 0 or sum(32768 >> l for l in lit if l) != 32768:
+        return False
+    nd = sum(1 for l in dist if l)
+    return sum(32768 >> l for l in dist if l) == 32768 or nd <= 1
+
+
+def test_deflate_dynamic_headers_are_found():
+    rng = np.random.default_rng(3)
+    x = np.arange(400_000)
+    data = ((128 + 70 * np.sin(x / 29.0) + rng.normal(0, 6, x.size)).clip(0, 255)).astype(np.uint8).tobytes()
+    data += bytes(20_000) + rng.integers(0, 256, 30_000, dtype=np.uint8).tobytes()      # + a run, + a stored block
+    z = zlib.compress(data, 6)
+    bits = np.unpackbits(np.frombuffer(z + bytes(16), np.uint8), bitorder="little")
+    starts = _block_starts(z)
+    assert len(starts) >= 10
+    dyn = [p for p in starts if int(bits[p + 1]) | (int(bits[p + 2]) << 1) == 2]
+    assert len(dyn) >= len(starts) - 4                     # level 6 emits dynamic blocks except for the stored part
+    for p in dyn:
+        assert _header_ok(bits, p), p
+    # and the filter is selective: none of a few thousand other positions passes
+    other = [int(q) for q in rng.integers(16, len(z) * 8 - 4000, 3000) if int(q) not in set(starts)]
+    assert sum(_header_ok(bits, q) for q in other) == 0
+
+
+# ---- LZ4 token chain self-synchronisation --------------------------------------------------------------------
+def _lz4_step(b, x):
+    tok = b[x]; x += 1
+    L = tok >> 4
+    if L == 15:
+        while True:
+            s = b[x]; x += 1; L += s
+            if s != 255:
+                break
+    x += L
+    if x >= len(b):
+        return len(b)
+    x += 2
+    M = tok & 15
+    if M == 15:
+        while True:
+            s = b[x]; x += 1
+            if s != 255:
+                break
+    return x
+
+
+def test_lz4_token_chain_self_synchronises():
+    from qoixutil import liblz4
+    L = liblz4()
+    if L is None:
+        pytest.skip("liblz4 not found")
+    rng = np.random.default_rng(9)
+    words = [bytes(rng.integers(0, 256, int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(500)]
+    src = b"".join(words[int(i)] for i in rng.integers(0, 500, 60_000)) + rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
+    cap = L.LZ4_compressBound(len(src))
+    dst = C.create_string_buffer(cap)
+    n = L.LZ4_compress_default(src, dst, len(src), cap)
+    b = dst.raw[:n]
+    true_pos, x = set(), 0
+    while x < len(b):
+        true_pos.add(x); x = _lz4_step(b, x)
+    met = 0
+    starts = [int(q) for q in rng.integers(1, len(b) - 4096, 200)]
+    for q in starts:
+        x, steps = q, 0
+        while x < len(b) and x not in true_pos and x < q + 4096:
+            try:
+                x = _lz4_step(b, x)
+            except IndexError:
+                break
+            steps += 1
+        met += x in true_pos and x < len(b)
+    assert met >= 0.97 * len(starts)        # the rare miss is what the merge kernel's true-walk fallback is for

@@ -4,6 +4,7 @@
 #include "inflate_par.cuh"
 #include <vector>
 #include <algorithm>
+#include <atomic>
 
 namespace gb {
 
@@ -23,15 +24,17 @@ inflate_batch_kernel(InflateJob* jobs, int njobs, const InfPar* par)
     if (lane == 0) { jobs[j].out_len = job.out_len; jobs[j].status = job.status; }
 }
 
-static int g_inflate_mode = -1;      // -1: unset (env GB200_INFLATE: "serial" | "parallel"), 0 serial, 1 parallel
-void set_inflate_mode(int m) { g_inflate_mode = m; }
+static std::atomic<int> g_inflate_mode{-1};      // -1: unset (env GB200_INFLATE: "serial" | "parallel"), 0 serial, 1 parallel
+void set_inflate_mode(int m) { g_inflate_mode.store(m); }
 
 bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cudaStream_t st, InflateWork& W)
 {
     if (njobs <= 0) return true;
-    if (g_inflate_mode < 0) {
+    int mode = g_inflate_mode.load();
+    if (mode < 0) {
         const char* e = getenv("GB200_INFLATE");
-        g_inflate_mode = (e && !strcmp(e, "serial")) ? 0 : 1;
+        mode = (e && !strcmp(e, "serial")) ? 0 : 1;
+        g_inflate_mode.store(mode);
     }
     const int grid = (njobs + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
     // ---- plan the parallel pipeline
@@ -46,7 +49,7 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
         InfPar& P = par[j];
         memset(&P, 0, sizeof(P));
         tile_start[j] = tiles;
-        const bool el = g_inflate_mode == 1 && J.in_len >= 2048 && J.in_len < (1u << 28) && J.out_cap >= 64 &&
+        const bool el = mode == 1 && J.in_len >= 2048 && J.in_len < (1u << 28) && J.out_cap >= 64 &&
                         J.out_cap < 0xfffffff0u && (((uintptr_t)J.out) & 3) == 0 && (((uintptr_t)J.in) & 15) == 0;
         if (!el) continue;
         P.eligible = 1;

@@ -23,6 +23,26 @@ def _threads_run(fn, threads):
     [t.join() for t in ts]
 
 
+def _e2e_threads(n, fn):
+    """fn(a, b) over GB200_E2E_THREADS (default 1) contiguous slices of range(n), one host thread each."""
+    parts = max(1, min(int(os.environ.get("GB200_E2E_THREADS", "1")), n))
+    if parts == 1:
+        fn(0, n)
+        return
+    cuts = [n * i // parts for i in range(parts + 1)]
+    err = []
+
+    def run(t):
+        try:
+            fn(cuts[t], cuts[t + 1])
+        except BaseException as e:  # noqa: BLE001
+            err.append(e)
+
+    _threads_run(run, parts)
+    if err:
+        raise err[0]
+
+
 class EventLog:
     """Collects (tag, start_event, end_event) on torch's current stream; elapsed read after the sync."""
 
@@ -358,8 +378,8 @@ class PngWorkload:
 
     def e2e_step(self):
         # one call for the whole batch: slicing it over several host threads was measured and is slower (the slices
-        # serialise on the allocator and each small batch is latency-bound)
-        self._e2e_slice(0, self.e2e_n)
+        # serialise on the allocator and each small batch is latency-bound); GB200_E2E_THREADS=k re-measures it
+        _e2e_threads(self.e2e_n, self._e2e_slice)
 
     def _e2e_slice(self, a, b_):
         b = self.codecs.png_decode_batch(self.host_files[a:b_], 0, 0)
@@ -444,7 +464,7 @@ class _BatchDecodeWorkload:
         assert self.h_out
 
     def e2e_step(self):
-        self._e2e_slice(0, self.e2e_n)
+        _e2e_threads(self.e2e_n, self._e2e_slice)
 
     def _e2e_slice(self, a, b_):
         b = self.decode(self.host_files[a:b_], None, 0)

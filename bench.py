@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- hot-path throughput on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload convert|png|jpeg|qoix] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload jpeg|png|qoix|convert|qoi]
+                    [--impl reference] [--only]
 
-A "step" is one pass of the hot path over one batch of synthetic input. Default workload is
-BASELINE.json configs[1]: PixelType convert rgba8<->rgbaf32 on one 8192x8192 image (forward +
-reverse = 2 launches, 134.2 Mpixels per step). One process per GPU (torchrun for N>1), batch units
-sharded across ranks with no data-path collective ("weak" scaling: every rank converts its own image).
-Workload classes live in benchlib.py.
+A "step" is one pass of the hot path over one batch of synthetic input. The DEFAULT workload is the decode
+headline of BASELINE.json, configs[3]: JPEG baseline decode (Huffman + IDCT + YCbCr) of a TOTAL batch of 4096
+3840x2160 4:2:0 images, strong-scaled: the batch is cut into contiguous index ranges over the ranks
+(gamut_b200/shard.py), one process per GPU (torchrun for N>1), no collective on the data path. Every rank
+walks its share in sub-batches so that outputs (102 GB for the whole batch) fit HBM.
 
-Prints ONE JSON line on rank 0.
+With no --workload/--only the line of the primary workload also carries, under detail.workloads, full lines
+(value, roofline, cpu_baseline, e2e) of the other configs that run on a GPU: configs[1] convert 8192x8192,
+configs[2] PNG 1024x1080p, configs[4] QOIX 10-bit + LZ4 (256 images per GPU) and configs[0] QOI 512x512.
+
+Prints ONE JSON line on rank 0. Workload classes live in benchlib.py.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -25,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+T_BEGIN = time.perf_counter()
+SECONDARY_BUDGET_S = float(os.environ.get("GB200_BENCH_BUDGET_S", "420"))   # stop adding secondary workloads after this
 
 
 def load_peaks():
@@ -64,8 +71,7 @@ class ClockSampler:
                     pass
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
             def run():
                 while not self.stop_flag:
@@ -98,10 +104,10 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
-
 def reference_arm(args, WORKLOADS):
-    """--impl reference: the reference's CPU implementation of the path (the C oracle port -- the D
-    reference cannot be compiled in this image) on all host threads."""
+    """--impl reference: the reference's CPU implementation of the path on all host threads. The D reference
+    cannot be compiled in this image (no D toolchain), so this is the C restatement under oracle/ (kind "port").
+    Each step decodes/converts a bounded sample of the workload (one unit per host thread)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -113,12 +119,139 @@ def reference_arm(args, WORKLOADS):
     v = px / t / 1e6
     out = {"metric": "Mpixels/s", "value": round(v, 1), "unit": "Mpixels/s", "impl": "reference",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3),
-           "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-           "config": {"workload": wl.name},
+           "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype,
+           "data": "synthetic", "config": {"workload": wl.name},
            "cpu_baseline": {"value": round(v, 1), "unit": "Mpixels/s", "cores": cores, "kind": "port",
                             "sample": sample + " (C restatement of the reference; no D toolchain in the image)"},
            "e2e": {"value": round(v, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
+
+
+class Ctx:
+    """Process-wide state shared by the workloads of one bench run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        from gamut_b200 import _lib
+        self.L = _lib.lib()
+        if not self.L.gb200_init():
+            raise SystemExit("bench.py: " + self.L.gb200_last_error().decode())
+        self.peak, self.peak_kind = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def allsum(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+
+def run_workload(WL, ctx: Ctx, args, steps, warmup, e2e_steps, cpu_baseline=True):
+    """Measures one workload on all ranks; returns the JSON line (rank 0) or None."""
+    torch, L = ctx.torch, ctx.L
+    wl = WL(ctx.rank, ctx.world, args)
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        wl.step(stream, timed=False)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    launches0 = L.gb200_launch_count()
+    ctx.barrier()
+    t_start.record(stream)
+    for _ in range(steps):
+        wl.step(stream, timed=True)
+    t_end.record(stream)
+    ctx.barrier()
+    launches = L.gb200_launch_count() - launches0
+    ms = t_start.elapsed_time(t_end)
+    wl.finish_timing()
+    ms = ctx.allmax([ms])[0]
+    clocks = sampler.stop() if ctx.rank == 0 else None
+
+    # ---- end to end through the host-pointer C ABI: every step starts with its inputs in (pinned) host memory
+    # and ends with its results in host memory (H2D and D2H inside the timed region)
+    e2e = None
+    if e2e_steps > 0:
+        wl.e2e_setup()
+        wl.e2e_step()                      # warm-up (allocates the cached device / pinned buffers)
+        wl.e2e_step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        step_ms = []
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            wl.e2e_step()
+            step_ms.append(round((time.perf_counter() - t1) * 1e3, 2))
+        torch.cuda.synchronize()
+        total_s = time.perf_counter() - t0
+        median_s = float(np.median(step_ms)) * 1e-3 * e2e_steps
+        median_s, total_s = ctx.allmax([median_s, total_s])
+        e2e = (median_s, total_s, step_ms)
+        wl.e2e_teardown()
+
+    px_all, e2e_px_all = ctx.allsum([wl.px_per_step, wl.e2e_px_per_step])
+    line = None
+    if ctx.rank == 0:
+        value = px_all * steps / (ms * 1e-3) / 1e6
+        cfg = {"workload": wl.name, "sharding": "units sharded across ranks, no collective on the data path"}
+        cfg.update(wl.config())
+        line = {"metric": "Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": ctx.world,
+                "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4),
+                "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None,
+                "dtype": wl.dtype, "data": "synthetic", "config": cfg,
+                "roofline": wl.roofline(ctx.peak, ctx.peak_kind)}
+        if e2e:
+            median_s, total_s, step_ms = e2e
+            line["e2e"] = {"value": round(e2e_px_all * e2e_steps / total_s / 1e6, 1), "unit": "Mpixels/s",
+                           "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps,
+                           "timing": "mean over the steps (wall clock around the whole loop, max over ranks)",
+                           "value_median": round(e2e_px_all * e2e_steps / median_s / 1e6, 1),
+                           "step_ms": step_ms, "api": wl.e2e_api}
+        line["gpu_launches"] = int(launches)
+        line["clocks"] = clocks
+        extra = wl.extra()
+        if extra:
+            line["detail"] = extra
+        if cpu_baseline:
+            px, times, sample = wl.cpu_run(1, 6, full=False)
+            times = times[1:]
+            line["cpu_baseline"] = {"value": round(px / float(np.median(times)) / 1e6, 1), "unit": "Mpixels/s",
+                                    "cores": 1, "kind": "port", "timing": "1 warm-up, median of 5",
+                                    "sample": sample + " (C restatement of the reference, which is single-threaded)"}
+    wl.release()
+    del wl
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    L.gb200_device_trim()
+    return line
 
 
 def main():
@@ -127,129 +260,55 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="convert", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--batch", type=int, default=None, help="images per rank for the batched decode workloads")
+    ap.add_argument("--batch", type=int, default=None, help="TOTAL images of the batched decode workloads")
+    ap.add_argument("--sub-batch", type=int, default=None, help="images per decode call inside a step")
+    ap.add_argument("--only", action="store_true", help="primary workload only (no detail.workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    secondary = args.workload is None and not args.only
+    if args.workload is None:
+        args.workload = "jpeg"
     WL = WORKLOADS[args.workload]
     if args.steps is None:
         args.steps = WL.default_steps if args.impl == "b200" else 3
-    if args.e2e_steps is None:
-        args.e2e_steps = WL.default_e2e_steps
-
     if args.impl == "reference":
         reference_arm(args, WORKLOADS)
         return
-    args.warmup = max(args.warmup, 3)
+    if args.warmup < 3:
+        sys.stderr.write("bench.py: --warmup %d raised to 3 (timing rules: >= 3 warm-up steps)\n" % args.warmup)
+        args.warmup = 3
 
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    from gamut_b200 import _lib
-    L = _lib.lib()
-    if not L.gb200_init():
-        raise SystemExit("bench.py: " + L.gb200_last_error().decode())
-
-    wl = WL(rank, world, args)
-    stream = torch.cuda.current_stream()
-    peak, peak_kind = load_peaks()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        wl.step(stream, timed=False)
-    barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    launches0 = L.gb200_launch_count()
-    barrier()
-    t_start.record(stream)
-    for i in range(args.steps):
-        wl.step(stream, timed=True)
-    t_end.record(stream)
-    barrier()
-    launches = L.gb200_launch_count() - launches0
-    ms = t_start.elapsed_time(t_end)
-    wl.finish_timing()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- end to end through the host-pointer C ABI
-    wl.e2e_setup()
-    wl.e2e_step()  # warm-up (allocates the cached device buffers)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_step_ms = []
-    for _ in range(args.e2e_steps):
-        t1 = time.perf_counter()
-        wl.e2e_step()
-        e2e_step_ms.append(round((time.perf_counter() - t1) * 1e3, 2))
-    torch.cuda.synchronize()
-    e2e_total_s = time.perf_counter() - t0
-    # every e2e step ends with its results in host memory (the C ABI calls synchronise), so steps are timed one by
-    # one and the median step is reported (median of >= 5): a fresh box shows occasional 2-3x spikes from
-    # host-side noise, visible in "step_ms"; "value_mean" keeps the plain total/steps figure
-    e2e_s = float(np.median(e2e_step_ms)) * 1e-3 * args.e2e_steps if e2e_step_ms else e2e_total_s
-    if world > 1:
-        t = torch.tensor([e2e_s, e2e_total_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_total_s = float(t[0].item()), float(t[1].item())
-
-    # units processed by all ranks (ranges are balanced by bytes, so the per-rank counts may differ by one image)
-    px_all, e2e_px_all = wl.px_per_step * world, wl.e2e_px_per_step * world
-    if world > 1:
-        t = torch.tensor([wl.px_per_step, wl.e2e_px_per_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        px_all, e2e_px_all = float(t[0].item()), float(t[1].item())
-    if rank == 0:
-        total_px = px_all * args.steps
-        value = total_px / (ms * 1e-3) / 1e6
-        e2e_v = e2e_px_all * args.e2e_steps / e2e_s / 1e6
-        cfg = {"workload": wl.name, "sharding": "units sharded across ranks, no collective on the data path"}
-        cfg.update(wl.config())
-        out = {"metric": "Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
-               "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype,
-               "data": "synthetic", "config": cfg,
-               "roofline": wl.roofline(peak, peak_kind),
-               "e2e": {"value": round(e2e_v, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": wl.h2d,
-                       "d2h_bytes_per_step": wl.d2h, "steps": args.e2e_steps, "timing": "median step",
-                       "value_mean": round(e2e_px_all * args.e2e_steps / e2e_total_s / 1e6, 1), "step_ms": e2e_step_ms, "api": wl.e2e_api},
-               "gpu_launches": int(launches), "clocks": clocks}
-        extra = wl.extra()
-        if extra:
-            out["detail"] = extra
-        if not args.no_cpu_baseline:
-            px, times, sample = wl.cpu_run(1, 3, full=False)
-            out["cpu_baseline"] = {"value": round(px / float(np.mean(times)) / 1e6, 1), "unit": "Mpixels/s",
-                                   "cores": 1, "kind": "port",
-                                   "sample": sample + " (C restatement of the reference, which is single-threaded)"}
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx = Ctx(args)
+    line = run_workload(WL, ctx, args, args.steps, args.warmup,
+                        WL.default_e2e_steps if args.e2e_steps is None else args.e2e_steps,
+                        cpu_baseline=not args.no_cpu_baseline)
+    if secondary:
+        others = {}
+        # at N > 1 only the workload whose BASELINE config is multi-GPU (QOIX, configs[4]) rides along
+        for name in (("convert", "png", "qoix", "qoi") if ctx.world == 1 else ("qoix",)):
+            if ctx.allmax([time.perf_counter() - T_BEGIN])[0] > SECONDARY_BUDGET_S:
+                others[name] = {"skipped": "time budget of the default run (%.0f s) used up" % SECONDARY_BUDGET_S}
+                continue
+            W2 = WORKLOADS[name]
+            a2 = argparse.Namespace(**vars(args))
+            a2.batch = None
+            a2.sub_batch = None
+            try:
+                l2 = run_workload(W2, ctx, a2, W2.default_steps, 3, W2.default_e2e_steps, cpu_baseline=not args.no_cpu_baseline)
+            except Exception as e:  # noqa: BLE001 -- a secondary workload never costs the primary line
+                l2 = {"error": "%s: %s" % (type(e).__name__, e)}
+            others[name] = l2
+        if line is not None:
+            line.setdefault("detail", {})["workloads"] = others
+    if ctx.rank == 0:
+        line["bench_wall_s"] = round(time.perf_counter() - T_BEGIN, 1)
+        print(json.dumps(line), flush=True)
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

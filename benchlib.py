@@ -14,6 +14,69 @@ import time
 import numpy as np
 
 
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_traffic():
+    """Per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of THIS build, captured by
+    scripts/capture_traffic.py (one ncu pass per workload) into profiles/traffic.json; None when not captured."""
+    import json
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def hbm_peak():
+    import json
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0      # fallback of B200_PROFILING.md
+
+
+def traffic_for(kernel_key, units):
+    """(bytes per launch at `units` units per launch, source string) for a kernel of profiles/traffic.json."""
+    t = load_traffic().get(kernel_key)
+    if not t:
+        return None, "not captured for this build (scripts/capture_traffic.py)"
+    return int(t["bytes_per_unit"] * units), t.get("source", "profiles/traffic.json")
+
+
+class _WorkloadBase:
+    scaling = "weak"
+
+    def finish_timing(self):
+        pass
+
+    def extra(self):
+        return None
+
+    def e2e_teardown(self):
+        """Returns the pinned host buffers of the e2e leg."""
+        for name in list(getattr(self, "_pinned", [])):
+            self.L_free(name)
+        self._pinned = []
+
+    def pin(self, nbytes):
+        from gamut_b200 import _lib
+        p = _lib.lib().gb200_host_alloc(nbytes)
+        if not p:
+            raise RuntimeError("pinned alloc of %d bytes failed" % nbytes)
+        self.__dict__.setdefault("_pinned", []).append(p)
+        return p
+
+    def L_free(self, p):
+        from gamut_b200 import _lib
+        _lib.lib().gb200_host_free(p)
+
+    def release(self):
+        """Drops device tensors so that the next workload of the same process starts with an empty HBM."""
+        for k, v in list(self.__dict__.items()):
+            if k not in ("px_per_step", "e2e_px_per_step", "h2d", "d2h"):
+                self.__dict__.pop(k, None)
+
+
 def _threads_run(fn, threads):
     if threads == 1:
         fn(0)
@@ -66,7 +129,7 @@ class EventLog:
 
 
 # ----------------------------------------------------------------------------------------------
-class ConvertWorkload:
+class ConvertWorkload(_WorkloadBase):
     """BASELINE configs[1]: PixelType convert rgba8 <-> rgbaf32, 8192x8192, 1 GPU (HBM roofline probe)."""
     name = "PixelType convert rgba8<->rgbaf32 8192x8192 (BASELINE configs[1])"
     dtype = "f32"
@@ -121,27 +184,19 @@ class ConvertWorkload:
         ach = alg / (avg[k] * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "peak_kind": peak_kind,
-                "traffic": 1283941000 if "rgba8,rgbaf32" in k else 1317897000,
-                "traffic_source": "profiles/r1_convert_ncu_full.txt (dram read+write per launch, one ncu --set full capture)",
+                "traffic": traffic_for(k, 1)[0], "traffic_source": traffic_for(k, 1)[1],
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": round(avg[k], 4),
                 "all_kernels_GBps": {kk: round(alg / (vv * 1e-3) / 1e9, 1) for kk, vv in avg.items()}}
 
-    def extra(self):
-        return None
-
     def e2e_setup(self):
         W, H, L = self.W, self.H, self.L
-        self.h_u8 = L.gb200_host_alloc(W * H * 4)
-        self.h_f32 = L.gb200_host_alloc(W * H * 16)
-        if not self.h_u8 or not self.h_f32:
-            raise RuntimeError("pinned alloc failed")
+        self.h_u8 = self.pin(W * H * 4)
+        self.h_f32 = self.pin(W * H * 16)
         a = np.ctypeslib.as_array(C.cast(self.h_u8, C.POINTER(C.c_uint8)), shape=(W * H * 4,))
         a[:] = np.random.default_rng(1).integers(0, 256, W * H * 4, dtype=np.uint8)
         # second pair of buffers for the reverse direction so that both directions can run concurrently
-        self.h_f32_in = L.gb200_host_alloc(W * H * 16)
-        self.h_u8_out = L.gb200_host_alloc(W * H * 4)
-        if not self.h_f32_in or not self.h_u8_out:
-            raise RuntimeError("pinned alloc failed")
+        self.h_f32_in = self.pin(W * H * 16)
+        self.h_u8_out = self.pin(W * H * 4)
         assert L.gb200_scanlines_convert(PT_rgba8(), self.h_u8, W * 4, PT_rgbaf32(), self.h_f32_in, W * 16, W, H)
         self.h2d = W * H * 4 + W * H * 16
         self.d2h = W * H * 16 + W * H * 4
@@ -215,15 +270,75 @@ def synth_photo(h, w, c, seed):
     return (np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8)
 
 
+def synth_photo_mixed(h, w, c, seed):
+    """Photo-like synthetic image with varied content: a smooth base plus bands of different structure (noisy smooth
+    areas, vertical and horizontal structures, clean diagonal edges, clean blobs, fine texture). Which PNG filter
+    wins a row depends on the structure, so an adaptive encoder emits Sub, Up, Avg and Paeth rows like it does on
+    photographs (synth_photo alone makes every row pick the same filter)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    nc = min(c, 3)
+    img = np.zeros((h, w, c), np.float32)
+    for k in range(nc):
+        a = np.zeros((h, w), np.float32)
+        for _ in range(4):
+            fx, fy, ph = rng.uniform(0.002, 0.03), rng.uniform(0.002, 0.03), rng.uniform(0, 6.28)
+            a += np.sin(xx * fx + yy * fy + ph) * rng.uniform(0.1, 0.3)
+        img[:, :, k] = 0.5 + a * 0.4
+    y = 0
+    while y < h:
+        bh = int(rng.integers(24, 120))
+        kind = int(rng.integers(0, 6))
+        sl = slice(y, min(h, y + bh))
+        X, Y = xx[sl], yy[sl]
+        amp = rng.uniform(0.08, 0.25)
+        sigma = [0.008, 0.004, 0.004, 0.0, 0.0, 0.0][kind]
+        for k in range(nc):
+            if kind == 0:
+                t = 0
+            elif kind == 1:      # vertical structures: constant down the rows
+                col = np.cumsum(rng.normal(0, 0.6, w)).astype(np.float32)
+                t = np.sign(np.sin(col))[None, :] * amp
+            elif kind == 2:      # horizontal structures: constant along the row
+                row = np.cumsum(rng.normal(0, 0.6, X.shape[0])).astype(np.float32)
+                t = np.sign(np.sin(row))[:, None] * amp
+            elif kind == 3:      # clean diagonal hard edges
+                f = rng.uniform(0.05, 0.2)
+                t = np.sign(np.sin((X + Y * rng.choice([-1.0, 1.0])) * f + k)) * amp
+            elif kind == 4:      # clean blobs: curved edges in every direction
+                t = np.zeros_like(X)
+                for _ in range(12):
+                    cx, cy, r = rng.uniform(0, w), rng.uniform(y, y + bh), rng.uniform(10, 60)
+                    t += (np.hypot(X - cx, Y - cy) < r) * rng.uniform(-amp, amp)
+            else:                # fine isotropic texture
+                t = rng.normal(0, amp * 0.6, X.shape).astype(np.float32)
+            img[sl, :, k] += t
+        if sigma:
+            img[sl, :, :nc] += rng.normal(0, sigma, (X.shape[0], w, nc)).astype(np.float32)
+        y += bh
+    if c in (2, 4):
+        img[:, :, c - 1] = np.clip((xx + yy) / (h + w) * 1.3, 0, 1)
+    return (np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8)
+
+
 def make_png_files(distinct, w, h, seed0=1000):
-    from PIL import Image as PILImage
-    files = []
-    for i in range(distinct):
-        img = synth_photo(h, w, 4, seed0 + i)
-        bio = io.BytesIO()
-        PILImage.fromarray(img, "RGBA").save(bio, format="PNG", compress_level=6)
-        files.append(bio.getvalue())
-    return files
+    """RGBA8 PNG files of mixed-content images, filters chosen per row by libpng's minimum-sum-of-absolute-
+    differences heuristic (tests/pngwriter.py), zlib level 6."""
+    sys_path_tests()
+    from pngwriter import write_png
+    return [write_png(synth_photo_mixed(h, w, 4, seed0 + i), 6, 8, filters="adaptive", level=6) for i in range(distinct)]
+
+
+def png_filter_histogram(files):
+    """Rows per filter type (None, Sub, Up, Avg, Paeth) over the given PNG files."""
+    import struct
+    import zlib
+    hist = np.zeros(5, np.int64)
+    for f in files:
+        w, h = struct.unpack(">II", f[16:24])
+        raw = np.frombuffer(zlib.decompress(split_idat(f)), np.uint8).reshape(h, -1)
+        hist += np.bincount(raw[:, 0], minlength=5)[:5]
+    return [int(x) for x in hist]
 
 
 def split_idat(png: bytes):
@@ -238,14 +353,14 @@ def split_idat(png: bytes):
     return out
 
 
-class PngWorkload:
+class PngWorkload(_WorkloadBase):
     """BASELINE configs[2]: PNG 8-bit RGBA decode (inflate + unfilter), batch of 1920x1080 images, 1 GPU."""
     name = "PNG 8-bit RGBA decode + unfilter, batch 1024 images 1920x1080 (BASELINE configs[2])"
     dtype = "u8"
     default_steps = 3
     default_e2e_steps = 5
     W, H = 1920, 1080
-    DISTINCT = 16
+    DISTINCT = 8
     e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back to pinned host memory with gb200_batch_download)"
 
     def __init__(self, rank, world, args):
@@ -334,7 +449,8 @@ class PngWorkload:
         self.variant_ms = {k: c.get("unfilter_" + k, []) for k in self.variants}
 
     def config(self):
-        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} RGBA8 ({self.DISTINCT} distinct, PIL level 6, adaptive filters)",
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} RGBA8 ({self.DISTINCT} distinct, zlib level 6, libpng-style adaptive filters)",
+                "filter_rows_none_sub_up_avg_paeth": png_filter_histogram(self.files),
                 "compressed_idat_bytes_per_image": int(self.comp_bytes),
                 "l2": "inputs larger than L2 (every image has its own device copy; batch >> 126 MB)",
                 "note": "value = whole decode (gather+inflate+unfilter); the unfilter-only leg is timed separately and excluded"}
@@ -345,7 +461,8 @@ class PngWorkload:
         alg = (self.comp_bytes + self.raw_len) * self.n
         ach = alg / (ph[1] * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "inflate pipeline (infp_find/verify/compact/count/walk/write/resolve kernels)", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": None,
+                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": traffic_for("inflate", self.n)[0],
+                "traffic_source": traffic_for("inflate", self.n)[1],
                 "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(float(ph[1]), 3)}
 
     def extra(self):
@@ -358,23 +475,22 @@ class PngWorkload:
         if self.unf_ms:
             ms = float(np.mean(self.unf_ms))
             alg = (self.raw_len + self.out_stride) * self.n
-            d["unfilter_only"] = {"filters": "PIL adaptive (None/Sub/Up rows on this data)",
+            d["unfilter_only"] = {"filters": "the workload's own files (adaptive: Sub/Up/Avg/Paeth rows, see config)",
                                   "Mpixels_s": round(px / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 3),
                                   "algorithmic_bytes": int(alg), "GBps": round(alg / (ms * 1e-3) / 1e9, 1),
-                                  "frac_of_measured_hbm": round(alg / (ms * 1e-3) / 1e9 / 6534.8, 4)}
+                                  "frac_of_measured_hbm": round(alg / (ms * 1e-3) / 1e9 / hbm_peak(), 4)}
             for k, v in getattr(self, "variant_ms", {}).items():
                 if v:
                     m2 = float(np.mean(v))
                     d["unfilter_only_" + k] = {"Mpixels_s": round(px / (m2 * 1e-3) / 1e6, 1), "ms": round(m2, 3),
                                                "GBps": round(alg / (m2 * 1e-3) / 1e9, 1),
-                                               "frac_of_measured_hbm": round(alg / (m2 * 1e-3) / 1e9 / 6534.8, 4)}
+                                               "frac_of_measured_hbm": round(alg / (m2 * 1e-3) / 1e9 / hbm_peak(), 4)}
         return d
 
     def e2e_setup(self):
         self.h2d = int(self.comp_bytes * self.e2e_n)
         self.d2h = self.e2e_n * self.out_stride
-        self.h_out = self.codecs._L().gb200_host_alloc(self.e2e_n * self.out_stride)
-        assert self.h_out
+        self.h_out = self.pin(self.e2e_n * self.out_stride)
 
     def e2e_step(self):
         # one call for the whole batch: slicing it over several host threads was measured and is slower (the slices
@@ -411,7 +527,7 @@ class PngWorkload:
 
 
 # ----------------------------------------------------------------------------------------------
-class _BatchDecodeWorkload:
+class _BatchDecodeWorkload(_WorkloadBase):
     """Shared plumbing of the batched decode workloads (JPEG, QOIX): files resident in HBM, one call per step."""
     dtype = "u8"
     scaling = "strong"
@@ -442,26 +558,31 @@ class _BatchDecodeWorkload:
         self.e2e_n = min(self.n, getattr(self, 'E2E_N', 128))
         self.e2e_px_per_step = self.e2e_n * self.W * self.H
         self.comp_bytes = sum(len(f) for f in self.files) / len(self.files)
+        self.sub = min(self.n, args.sub_batch or getattr(self, 'SUB_BATCH', self.n))
         self.phase = []
 
     def step(self, stream, timed):
-        b = self.decode(self.host_files, self.dev_ptrs, stream.cuda_stream)
+        # the rank's share is walked in sub-batches of `sub` images (one decode call each) so that the decoded
+        # pixels of a call fit HBM; every call's phase times (CUDA events on the call's stream) are summed
+        ph_sum = None
+        for a in range(0, self.n, self.sub):
+            e = min(self.n, a + self.sub)
+            b = self.decode(self.host_files[a:e], self.dev_ptrs[a:e], stream.cuda_stream)
+            if timed:
+                ph, hp = b.timing()
+                row = np.array(ph[:8] + [hp])
+                ph_sum = row if ph_sum is None else ph_sum + row
+            bad = sum(1 for d in b.images if not d.status)
+            b.free()
+            if bad:
+                raise RuntimeError(f"{bad} images failed to decode")
         if timed:
-            ph, hp = b.timing()
-            self.phase.append(ph[:3] + [hp])
-        bad = sum(1 for d in b.images if not d.status)
-        b.free()
-        if bad:
-            raise RuntimeError(f"{bad} images failed to decode")
-
-    def finish_timing(self):
-        pass
+            self.phase.append(ph_sum)
 
     def e2e_setup(self):
         self.h2d = int(self.comp_bytes * self.e2e_n)
         self.d2h = self.e2e_n * self.out_bytes
-        self.h_out = self.codecs._L().gb200_host_alloc(self.e2e_n * self.out_bytes)
-        assert self.h_out
+        self.h_out = self.pin(self.e2e_n * self.out_bytes)
 
     def e2e_step(self):
         _e2e_threads(self.e2e_n, self._e2e_slice)
@@ -473,18 +594,33 @@ class _BatchDecodeWorkload:
         b.free()
 
     def roofline(self, peak, peak_kind):
+        """The dominant kernel (group) of the step: the phase with the largest device time, measured live with CUDA
+        events on the launching stream inside the library (gb200_batch_timing). A "launch" is one decode call of
+        `sub` images; achieved = algorithmic bytes of that phase for `sub` images / its average duration per call."""
         ph = np.mean(np.array(self.phase), axis=0)
-        k = 1 if ph[1] >= ph[2] else 2
-        alg = self.kernel_bytes[k] * self.n
-        ach = alg / (ph[k] * 1e-3) / 1e9
+        calls = (self.n + self.sub - 1) // self.sub
+        k = max(self.kernel_names, key=lambda q: ph[q])
+        per_call_ms = float(ph[k]) / calls
+        units = self.n / calls
+        alg = self.kernel_bytes[k] * units
+        ach = alg / (per_call_ms * 1e-3) / 1e9
+        tr, src = traffic_for(self.traffic_keys.get(k, ""), units)
         return {"bound": "hbm", "kernel": self.kernel_names[k], "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": None,
-                "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(float(ph[k]), 3)}
+                "frac": round(ach / peak, 4), "peak_kind": peak_kind, "traffic": tr, "traffic_source": src,
+                "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": round(per_call_ms, 3),
+                "launch": f"one decode call of {units:.0f} images",
+                "all_phases": {self.kernel_names[q]: {"ms_per_call": round(float(ph[q]) / calls, 3),
+                                                      "GBps": round(self.kernel_bytes[q] * units / (float(ph[q]) / calls * 1e-3) / 1e9, 1),
+                                                      "frac": round(self.kernel_bytes[q] * units / (float(ph[q]) / calls * 1e-3) / 1e9 / peak, 4)}
+                               for q in self.kernel_names if ph[q] > 0}}
 
     def extra(self):
         ph = np.mean(np.array(self.phase), axis=0)
-        return {"phase_ms": {"upload": round(float(ph[0]), 3), self.kernel_names[1]: round(float(ph[1]), 3),
-                             self.kernel_names[2]: round(float(ph[2]), 3), "host_parse": round(float(ph[3]), 3)}}
+        d = {"upload": round(float(ph[0]), 3)}
+        for q, name in self.kernel_names.items():
+            d[name] = round(float(ph[q]), 3)
+        d["host_parse"] = round(float(ph[8]), 3)
+        return {"phase_ms_per_step": d, "decode_calls_per_step": (self.n + self.sub - 1) // self.sub}
 
 
 class JpegWorkload(_BatchDecodeWorkload):
@@ -492,13 +628,17 @@ class JpegWorkload(_BatchDecodeWorkload):
     name = "JPEG baseline decode (Huffman+IDCT+YCbCr) 3840x2160 4:2:0 q90, batch sharded 1/2/4/8 GPU (BASELINE configs[3])"
     W, H = 3840, 2160
     e2e_api = "gb200_jpeg_decode_batch (host file bytes staged through pinned memory; rgb8 pixels copied back to pinned host memory with gb200_batch_download)"
-    kernel_names = {1: "jpeg_huffman_kernel", 2: "jpeg_idct_kernel+jpeg_colour_kernel"}
+    kernel_names = {1: "jpeg entropy stage (unstuff/sync/scan/write kernels)", 2: "jpeg_idct_colour_kernel"}
+    traffic_keys = {1: "jpeg_entropy", 2: "jpeg_idct_colour_kernel"}
+    SUB_BATCH = 512
+    E2E_N = 128
 
     def __init__(self, rank, world, args):
-        self._setup(rank, world, args, 1024)
+        self._setup(rank, world, args, 4096)
         self.out_bytes = self.W * self.H * 3
         coef = self.W * self.H * 3      # int16 coefficients, 1.5 samples per pixel
-        self.kernel_bytes = {1: self.comp_bytes + coef, 2: coef + self.W * self.H * 3 * 2 + self.out_bytes}
+        # algorithmic bytes per image: entropy stage = file in + coefficients out; IDCT+colour = coefficients in + rgb8 out
+        self.kernel_bytes = {1: self.comp_bytes + coef, 2: coef + self.out_bytes}
 
     def make_files(self, seed0):
         from PIL import Image as PILImage
@@ -515,6 +655,7 @@ class JpegWorkload(_BatchDecodeWorkload):
 
     def config(self):
         return {"units_per_rank": f"{self.n} images {self.W}x{self.H} (total batch {self.total}, {self.DISTINCT} distinct, PIL q90 4:2:0, no DRI)",
+                "total_batch": self.total, "sub_batch": self.sub,
                 "compressed_bytes_per_image": int(self.comp_bytes), "scaling_note": "strong: total batch fixed, sharded by image index",
                 "l2": "inputs larger than L2 (every image has its own device copy)"}
 
@@ -549,6 +690,7 @@ class QoixWorkload(_BatchDecodeWorkload):
     e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back to pinned host memory with gb200_batch_download)"
     E2E_N = 256
     kernel_names = {1: "lz4 kernels (spec/merge/scan/pwrite/parse/resolve)", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
+    traffic_keys = {1: "lz4", 2: "qoiplane10"}
 
     def __init__(self, rank, world, args):
         self._setup(rank, world, args, 256)
@@ -600,6 +742,90 @@ class QoixWorkload(_BatchDecodeWorkload):
         return nimg * W * H, times, f"{nimg} images 2048x2048 la16 + LZ4, {threads} thread(s), one image per worker"
 
 
+class QoiWorkload(_WorkloadBase):
+    """BASELINE configs[0]: QOI decode of one 512x512 RGBA8 image, the plumbing case of examples/convert
+    (load with LAYOUT_VERT_STRAIGHT | LAYOUT_GAPLESS; `python -m gamut_b200.convert` is the CLI equivalent).
+    Plain QOI has a value-hashed index (qoi.d:536), so one image is one serial chain: this line measures the
+    call path, not a throughput kernel. There is no device-resident entry point for QOI: `value` and `e2e` both go
+    through gb200_qoi_decode / Image.loadFromMemory with host buffers."""
+    name = "QOI decode one 512x512 RGBA8 image via the convert-equivalent path (BASELINE configs[0])"
+    dtype = "u8"
+    default_steps = 20
+    default_e2e_steps = 9
+    W = H = 512
+    e2e_api = "Image.loadFromMemory(bytes, LAYOUT_VERT_STRAIGHT | LAYOUT_GAPLESS) -> gb200_qoi_decode (host bytes in, malloc'd host pixels out)"
+
+    def __init__(self, rank, world, args):
+        import torch
+        from gamut_b200 import codecs
+        self.torch, self.codecs = torch, codecs
+        self.file, self.pixels = make_qoi_file(self.W, self.H)
+        self.px_per_step = self.e2e_px_per_step = self.W * self.H
+        self.ms = []
+
+    def step(self, stream, timed):
+        a = self.torch.cuda.Event(enable_timing=True)
+        b = self.torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        r = self.codecs.qoi_decode(self.file, 0)
+        b.record(stream)
+        if r is None:
+            raise RuntimeError("qoi_decode failed")
+        if not getattr(self, "_checked", False):
+            assert np.array_equal(r[0], self.pixels), "QOI decode differs from the encoded pixels"
+            self._checked = True
+
+    def config(self):
+        return {"units_per_rank": "1 image 512x512 RGBA8 (seeded gradient + noise + flat rectangles + alpha ramp)",
+                "file_bytes": len(self.file), "l2": "single small image: L2-resident by nature of the config",
+                "note": "value and e2e use the same host-pointer call (no device-resident QOI entry point)"}
+
+    def roofline(self, peak, peak_kind):
+        return {"bound": "hbm", "kernel": "qoi_kernel (one thread per image: serial by the format's value-hashed index)",
+                "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_kind": peak_kind, "traffic": None,
+                "note": "latency-bound plumbing case; no roofline claim"}
+
+    def e2e_setup(self):
+        self.h2d = len(self.file)
+        self.d2h = self.W * self.H * 4
+
+    def e2e_step(self):
+        from gamut_b200.image import Image
+        from gamut_b200.types import LAYOUT_VERT_STRAIGHT, LAYOUT_GAPLESS
+        im = Image()
+        im.loadFromMemory(self.file, LAYOUT_VERT_STRAIGHT | LAYOUT_GAPLESS)
+        if im.isError():
+            raise RuntimeError(im.errorMessage())
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        f, _ = make_qoi_file(QoiWorkload.W, QoiWorkload.H)
+        n = threads if full else 1
+
+        def work(t):
+            for _ in range(8):
+                assert pyoracle.qoi_decode(f, 0) is not None
+
+        _threads_run(work, n)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, n)
+            times.append(time.perf_counter() - t0)
+        return 8 * n * QoiWorkload.W * QoiWorkload.H, times, f"8 decodes of the 512x512 image per thread, {n} thread(s)"
+
+
+def make_qoi_file(w, h):
+    """SURVEY 8d cfg 1: seeded gradient + low-amplitude noise + flat rectangles + alpha ramp (tests/qoixutil.py),
+    encoded by PIL's QOI writer (an implementation independent of the reference and of this repo).
+    Returns (file, pixels)."""
+    sys_path_tests()
+    from qoixutil import qoi_bytes, qoi_test_image
+    px = qoi_test_image(h, w, 4, 1234)
+    return qoi_bytes(px), px
+
+
 def PT_rgba8():
     from gamut_b200.types import PixelType as PT
     return PT.rgba8
@@ -617,4 +843,4 @@ def sys_path_tests():
         sys.path.insert(0, p)
 
 
-WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload}
+WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload, "qoi": QoiWorkload}

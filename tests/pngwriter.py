@@ -46,6 +46,32 @@ def filter_rows(rows: np.ndarray, bpp: int, filters) -> bytes:
     return bytes(out)
 
 
+def filter_rows_adaptive(rows: np.ndarray, bpp: int):
+    """libpng's default heuristic (PNG spec 12.8): per row, the filter whose residuals, read as signed bytes, have
+    the smallest sum of absolute values. Vectorised over the whole image. Returns (raw bytes, per-row filter types)."""
+    h, rb = rows.shape
+    cur = rows.astype(np.int16)
+    left = np.zeros_like(cur)
+    left[:, bpp:] = cur[:, :-bpp]
+    up = np.zeros_like(cur)
+    up[1:] = cur[:-1]
+    ul = np.zeros_like(cur)
+    ul[1:, bpp:] = cur[:-1, :-bpp]
+    p = left + up - ul
+    pa, pb, pc = np.abs(p - left), np.abs(p - up), np.abs(p - ul)
+    paeth = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+    cands = [cur, cur - left, cur - up, cur - ((left + up) >> 1), cur - paeth]
+    res = [(c & 255).astype(np.uint8) for c in cands]
+    cost = np.stack([np.minimum(r.astype(np.int32), 256 - r.astype(np.int32)).sum(axis=1) for r in res])   # (5, h)
+    choice = np.argmin(cost, axis=0).astype(np.uint8)
+    out = np.empty((h, rb + 1), np.uint8)
+    out[:, 0] = choice
+    for f in range(5):
+        m = choice == f
+        out[m, 1:] = res[f][m]
+    return out.tobytes(), choice
+
+
 def pack_samples(img: np.ndarray, depth: int) -> np.ndarray:
     """img: (h, w, c) integer samples (values < 2**depth). Returns (h, rowbytes) uint8, PNG byte order."""
     h, w, c = img.shape
@@ -74,7 +100,9 @@ def write_png(img: np.ndarray, color: int, depth: int, filters=0, interlace: boo
     """img: (h, w, c) samples, c = channels stored in the file (1 for palette)."""
     h, w, c = img.shape
     bpp = max(1, c * depth // 8)
-    if not interlace:
+    if not interlace and isinstance(filters, str) and filters == "adaptive":
+        raw = filter_rows_adaptive(pack_samples(img, depth), bpp)[0]
+    elif not interlace:
         raw = filter_rows(pack_samples(img, depth), bpp, filters)
     else:
         raw = b""

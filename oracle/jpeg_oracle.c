@@ -583,6 +583,29 @@ static void calc_mcu_block_order(jd* d)
     }
 }
 
+/* create_look_ups (jpegload.d:2080-2094); FIX!(x) = (int)(x * 65536 + 0.5f) */
+static void create_look_ups(jd* d)
+{
+    const int F140200 = (int)(1.40200f * 65536 + 0.5f), F177200 = (int)(1.77200f * 65536 + 0.5f);
+    const int F071414 = (int)(0.71414f * 65536 + 0.5f), F034414 = (int)(0.34414f * 65536 + 0.5f);
+    for (int i = 0; i <= 255; ++i) {
+        int k = i - 128;
+        d->crr[i] = (F140200 * k + 32768) >> 16;
+        d->cbb[i] = (F177200 * k + 32768) >> 16;
+        d->crg[i] = (-F071414) * k;
+        d->cbg[i] = (-F034414) * k + 32768;
+    }
+}
+/* the pixel expression of H1V1Convert / H2V1Convert / H1V2Convert / expanded_convert (jpegload.d:2536-2549 ...):
+ * saturating packs == clamp for these ranges */
+static inline void ycc(jd* d, int y, int cb, int cr, uint8_t* o)
+{
+    o[0] = CLAMP(y + d->crr[cr]);
+    o[1] = CLAMP(y + ((d->crg[cr] + d->cbg[cb]) >> 16));
+    o[2] = CLAMP(y + d->cbb[cb]);
+    o[3] = 255;
+}
+
 /* init_frame (jpegload.d:3130-3268) */
 static int init_frame(jd* d)
 {
@@ -616,17 +639,38 @@ static int init_frame(jd* d)
     d->pSample_buf = (uint8_t*)calloc(nb + 64, 1);
     d->total_lines_left = d->image_y_size;
     d->mcu_lines_left = 0;
-    /* create_look_ups (jpegload.d:2080-2094); FIX!(x) = (int)(x * 65536 + 0.5f) */
-    const int F140200 = (int)(1.40200f * 65536 + 0.5f), F177200 = (int)(1.77200f * 65536 + 0.5f);
-    const int F071414 = (int)(0.71414f * 65536 + 0.5f), F034414 = (int)(0.34414f * 65536 + 0.5f);
-    for (int i = 0; i <= 255; ++i) {
-        int k = i - 128;
-        d->crr[i] = (F140200 * k + 32768) >> 16;
-        d->cbb[i] = (F177200 * k + 32768) >> 16;
-        d->crg[i] = (-F071414) * k;
-        d->cbg[i] = (-F034414) * k + 32768;
-    }
+    create_look_ups(d);
     return 1;
+}
+
+/* ---- test hooks (tests/test_oracle_reference_text.py): the arithmetic kernels of this file, callable on
+ * single blocks so that they can be compared with vectors generated from the reference's source text
+ * (tests/golden/gen_from_reference.py). ---- */
+void or_test_jpeg_idct(const int16_t* src, int max_zag, uint8_t* dst) { idct(src, dst, max_zag); }
+void or_test_jpeg_upsample(const int16_t* src, uint8_t* dst256)          /* chroma half of transform_mcu_expand */
+{
+    Matrix44 P, Q, R, S, a, bb, c, dd;
+    jpgd_block_t temp_block[64];
+    memset(temp_block, 0, sizeof(temp_block));
+    pq_rs_calc(&P, &Q, &R, &S, src);
+    for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) {
+        a.v[r][q] = P.v[r][q] + Q.v[r][q]; bb.v[r][q] = P.v[r][q] - Q.v[r][q];
+        c.v[r][q] = R.v[r][q] + S.v[r][q]; dd.v[r][q] = R.v[r][q] - S.v[r][q];
+    }
+    addsub_store(temp_block, &a, &c, 0);  idct_4x4(temp_block, dst256);
+    addsub_store(temp_block, &a, &c, 1);  idct_4x4(temp_block, dst256 + 64);
+    addsub_store(temp_block, &bb, &dd, 0); idct_4x4(temp_block, dst256 + 128);
+    addsub_store(temp_block, &bb, &dd, 1); idct_4x4(temp_block, dst256 + 192);
+}
+void or_test_jpeg_ycc(int y, int cb, int cr, uint8_t* rgb, int* tables /* crr, cbb, crg, cbg: 4 x 256, may be NULL */)
+{
+    jd* d = (jd*)calloc(1, sizeof(jd));
+    uint8_t o[4];
+    create_look_ups(d);
+    ycc(d, y, cb, cr, o);
+    rgb[0] = o[0]; rgb[1] = o[1]; rgb[2] = o[2];
+    if (tables) { memcpy(tables, d->crr, 1024); memcpy(tables + 256, d->cbb, 1024); memcpy(tables + 512, d->crg, 1024); memcpy(tables + 768, d->cbg, 1024); }
+    free(d);
 }
 
 /* fix_in_buffer + init_scan (jpegload.d:2098-2118, 3093-3127) */
@@ -758,14 +802,7 @@ static int decode_next_row(jd* d)
     return 1;
 }
 
-/* colour conversion (jpegload.d:2528-2823); saturating packs == clamp for these ranges */
-static inline void ycc(jd* d, int y, int cb, int cr, uint8_t* o)
-{
-    o[0] = CLAMP(y + d->crr[cr]);
-    o[1] = CLAMP(y + ((d->crg[cr] + d->cbg[cb]) >> 16));
-    o[2] = CLAMP(y + d->cbb[cb]);
-    o[3] = 255;
-}
+/* colour conversion (jpegload.d:2528-2823) */
 static void H1V1Convert(jd* d)
 {
     int row = d->max_mcu_y_size - d->mcu_lines_left;

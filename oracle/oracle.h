@@ -95,6 +95,15 @@ int or_lz4_decompress_fast(const uint8_t* src, uint8_t* dst, int originalSize); 
 int or_lz4_compress(const uint8_t* src, uint8_t* dst, int srcSize);              /* lz4.d:544 */
 int or_lz4_compress_bound(int isize);                                            /* lz4.d:68 */
 
+/* test hooks: single arithmetic kernels, compared with vectors generated from the reference's source text
+ * (tests/golden/gen_from_reference.py, tests/test_oracle_reference_text.py) */
+void or_test_jpeg_idct(const int16_t* src, int max_zag, uint8_t* dst);           /* idct, jpegload.d:308-376 */
+void or_test_jpeg_upsample(const int16_t* src, uint8_t* dst256);                 /* transform_mcu_expand chroma, :2150-2251 */
+void or_test_jpeg_ycc(int y, int cb, int cr, uint8_t* rgb, int* tables);         /* create_look_ups + H1V1Convert pixel */
+int  or_test_loco_predict10(int left, int top, int topleft);                     /* locoPredict, qoiplane10.d:84-96 */
+int  or_test_loco8(int a, int b, int c);                                         /* qoi2avg.d:863-897, one lane */
+int  or_test_loco10(int a, int b, int c);                                        /* qoi10b.d:871-903, one lane */
+
 void or_free(void* p);
 
 #ifdef __cplusplus

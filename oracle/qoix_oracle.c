@@ -208,6 +208,8 @@ static void outputBits(bitw* w, uint32_t x, int nbits)      /* qoiplane10.d:139-
 }
 
 /* qoiplane10.d:99-314 */
+int or_test_loco_predict10(int left, int top, int topleft) { return locoPredict(left, top, topleft); }   /* test hook */
+
 uint8_t* or_qoiplane10_encode(const uint8_t* data, const or_qoix_desc* desc, int* out_len)
 {
     if ((desc->channels != 1 && desc->channels != 2) || desc->width == 0 || desc->height == 0 ||

@@ -55,6 +55,8 @@ static int loco8(int a, int b, int c)
     return clamp255(p);
 }
 
+int or_test_loco8(int a, int b, int c) { return loco8(a, b, c); }          /* test hook */
+
 uint8_t* or_qoix_decode(const uint8_t* data, int size, or_qoix_desc* desc, int channels)   /* qoi2avg.d:625 */
 {
     if (!data || !desc || (channels != 0 && channels != 3 && channels != 4) || size < QOIX_HEADER_SIZE + 4) return NULL;
@@ -220,6 +222,7 @@ static int loco10(int a, int b, int c)                            /* qoi10b.d:87
     if (c <= mn) p = mx;
     return clamp1023(p);
 }
+int or_test_loco10(int a, int b, int c) { return loco10(a, b, c); }        /* test hook */
 
 uint8_t* or_qoi10b_decode(const uint8_t* data, int size, or_qoix_desc* desc, int channels)   /* qoi10b.d:504 */
 {

@@ -106,3 +106,24 @@ def test_config2_full_size_properties(gb, oracle):
     exp = np.zeros(64 * W * 16, np.uint8)
     oracle.scanlines_convert(PT.rgba8, band, W * 4, PT.rgbaf32, exp, W * 16, W, 64)
     assert np.array_equal(f[1000:1064].cpu().numpy().reshape(-1).view(np.uint8), exp)
+
+
+def test_reference_text_vectors(gb):
+    """The CUDA converters against vectors generated from the reference's source text (tests/golden/
+    gen_from_reference.py: the 46 scanline_convert_* bodies of scanline.d executed with IEEE-single semantics) --
+    no oracle in between. Single-stage pairs: the source or the destination is the intermediate type."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_scanline.npz"))
+    w = int(d["width"])
+    n = 0
+    for name in [str(x) for x in d["names"]]:
+        src_t, dst_t = name.split("_to_")
+        if src_t not in PT.__members__ or dst_t not in PT.__members__ or (src_t, dst_t) == ("l8", "rgb8"):
+            continue                     # bgra8 / bgr8 / l8->rgb8 helpers are outside scanlinesConvert (scanline.d:139,812,826)
+        x = np.ascontiguousarray(d["in_" + name]).view(np.uint8)
+        exp = np.ascontiguousarray(d["out_" + name]).view(np.uint8)
+        got = np.zeros_like(exp)
+        assert gb.scanlinesConvert(PT[src_t], x, x.size, PT[dst_t], got, got.size, w, 1), name
+        assert np.array_equal(got, exp), name
+        n += 1
+    assert n >= 40

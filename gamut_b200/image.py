@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import codecs
-from .scanline import scanlinesConvert
+from .scanline import scanlinesConvert, scanlinesInterType
 from .types import *  # noqa: F401,F403
 from .types import (PixelType, ImageFormat, pixelTypeSize, LOAD_GREYSCALE, LOAD_ALPHA, LOAD_NO_ALPHA, LOAD_RGB,
                     LOAD_8BIT, LOAD_16BIT, LOAD_FP32, LOAD_PREMUL, LOAD_NO_PREMUL, LAYOUT_GAPLESS,
@@ -377,7 +377,9 @@ class Image:
         if (self._width == 0 or self._height == 0) and compatible:
             self._layoutConstraints = layoutConstraints
             return True
-        st = allocatePixelStorage(targetType, self._width, self._height, layoutConstraints)
+        # image.d:1233-1236: the allocation also holds one intermediate scanline when the type changes
+        bonus = self._width * pixelTypeSize(scanlinesInterType(self._type, targetType)) if targetType != self._type else 0
+        st = allocatePixelStorage(targetType, self._width, self._height, layoutConstraints, bonus)
         if st is None:
             self.error(kStrOutOfMemory)
             return False
@@ -392,3 +394,19 @@ class Image:
         self._layoutConstraints = layoutConstraints
         self._error = None
         return True
+
+    # -- the convertTo family (image.d:1086-1172): each is convertTo(<type algebra>(_type), layoutConstraints)
+    def setLayout(self, layoutConstraints: int) -> bool: return self.convertTo(self._type, layoutConstraints)
+    def convertToGreyscale(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToGreyscale(self._type), lc)
+    def convertToGreyscaleAlpha(self, lc: int = 0) -> bool:
+        return self.convertTo(convertPixelTypeToAddAlphaChannel(convertPixelTypeToGreyscale(self._type)), lc)
+    def convertToRGB(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToRGB(self._type), lc)
+    def convertToRGBA(self, lc: int = 0) -> bool:
+        return self.convertTo(convertPixelTypeToAddAlphaChannel(convertPixelTypeToRGB(self._type)), lc)
+    def addAlphaChannel(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToAddAlphaChannel(self._type), lc)
+    def dropAlphaChannel(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToDropAlphaChannel(self._type), lc)
+    def premultiply(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToPremul(self._type), lc)
+    def unpremultiply(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToNoPremul(self._type), lc)
+    def convertTo8Bit(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeTo8Bit(self._type), lc)
+    def convertTo16Bit(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeTo16Bit(self._type), lc)
+    def convertToFP32(self, lc: int = 0) -> bool: return self.convertTo(convertPixelTypeToFP32(self._type), lc)

@@ -1,38 +1,65 @@
 // jpeg_sync.cuh -- intra-image parallel Huffman decoding for long entropy segments (included by jpeg.cu).
 //
 // A baseline JPEG scan without restart markers is one serial bit stream (decode_next_row,
-// jpegload.d:2405-2525). Huffman codes self-synchronise, so the stream is cut into fixed-size chunks and
-// decoded by one thread per chunk:
-//   1. jpeg_unstuff_kernel   removes FF00 byte stuffing and stops at the first marker, giving a plain bit
-//                            stream (padded with 1-bits: the reference reads all-ones past a marker,
-//                            jpegload.d:683-743);
-//   2. jpeg_sync_kernel      pass 0: every thread decodes its chunk from a guessed state (block 0 of the MCU,
-//                            DC next) and records the decoder state (bit position, block-in-MCU, zig-zag
-//                            index) at the first symbol that starts in the next chunk. Passes 1..n: a thread
-//                            whose predecessor's exit state changed re-decodes from that state; the host
-//                            repeats until no exit state changes. Chunk 0 starts from the true state, so the
-//                            fixed point is the serial decode (induction over chunks);
-//   3. jpeg_scan_kernel      exclusive scan over chunks: first block index and DC running sums per chunk;
-//   4. jpeg_sync_kernel<W>   final pass: decode again and write dequantised AC coefficients and DC differences;
-//   5. jpeg_dcfix_kernel     DC prediction: per-chunk walk adding the scanned base, dequantise DC.
+// jpegload.d:2405-2525). Huffman codes self-synchronise, so the stream is cut into 128-byte chunks, one
+// thread each, and the whole stage runs without a host round trip:
+//   1. jpeg_unstuff_kernel  removes FF00 byte stuffing and stops at the first marker, giving a plain bit
+//                           stream padded with 1-bits (the reference reads all-ones past a marker,
+//                           jpegload.d:683-743);
+//   2. jpeg_sync_kernel     one CTA = 248 consecutive chunks of one segment (+ 8 warm-up chunks borrowed from
+//                           its predecessor). Every thread decodes its chunk from a guessed state, then the CTA
+//                           relaxes in shared memory: a thread whose predecessor's exit state differs from the
+//                           entry state it used decodes again, until nothing changes (chunk 0 of a segment starts
+//                           from the true state, so the fixed point is the serial decode, by induction). Per chunk
+//                           it leaves the exit state, the number of blocks completed and the sum of the DC
+//                           differences per component;
+//   3. jpeg_repair_kernel   the only unverified assumption is the state at each CTA's first own chunk (taken from
+//                           its warm-up chunks). One thread per CTA boundary compares it with the true exit state
+//                           of the previous CTA and, if they differ (rare), walks forward re-decoding chunks until
+//                           the states meet again. jpeg_check_kernel counts boundaries that still disagree; the
+//                           host reads that count with the statuses at the very end and only then repeats;
+//   4. jpeg_scan_kernel     per segment: exclusive scans of the block counts and of the three DC sums;
+//   5. jpeg_write_kernel    every chunk is decoded once more from its true state. A block belongs to the chunk
+//                           its DC symbol starts in: that thread decodes it to its end (running into the next
+//                           chunk if need be), zero-fills the 128 bytes, scatters the dequantised coefficients
+//                           with the DC prediction already applied, and records the block's zig-zag extent.
 #pragma once
 
 constexpr int JS_CHUNK_BYTES = 128;
 constexpr int JS_CHUNK_BITS = JS_CHUNK_BYTES * 8;
 constexpr uint32_t JS_LONG_MIN = 1024;           // shorter segments are decoded by one thread each (jpeg_huffman_kernel)
+constexpr int JS_CTA = 256;                      // threads (= chunks) per CTA of the sync kernel
+constexpr int JS_WARM = 8;                       // of which warm-up chunks that belong to the previous CTA
+constexpr int JS_OWN = JS_CTA - JS_WARM;
+constexpr int JS_PAD_BYTES = 256;                // 1-bits after the unstuffed data (a block may run past the end)
 
 struct LongSeg {
     int image;
     uint32_t in_start, in_end;      // raw (stuffed) byte range in the file
     uint32_t chunk_base, nchunks;   // this segment's slice of the per-chunk arrays (nchunks from the stuffed length)
+    uint32_t cta_base;              // first sync CTA of this segment (JS_OWN chunks per CTA)
     int first_mcu, num_mcus;
     unsigned long long clean_off;   // offset of the unstuffed stream in the clean arena (16-byte aligned)
 };
 
-struct ChunkState { uint32_t bitpos; uint16_t bi; uint16_t k; };   // k: 0 = DC next, 1..63 = next AC index
-__device__ __forceinline__ ChunkState js_load(const ChunkState* p) { const uint2 v = __ldcg((const uint2*)p); ChunkState s; s.bitpos = v.x; s.bi = (uint16_t)(v.y & 0xffff); s.k = (uint16_t)(v.y >> 16); return s; }
-__device__ __forceinline__ void js_store(ChunkState* p, ChunkState s) { __stcg((uint2*)p, make_uint2(s.bitpos, (uint32_t)s.bi | ((uint32_t)s.k << 16))); }
-__device__ __forceinline__ uint32_t js_find_seg(const LongSeg* __restrict__ segs, int nsegs, uint32_t c)
+// decoder state between two symbols: bit position, block-in-MCU, zig-zag index (0 = DC next)
+struct ChunkState { uint32_t bitpos; uint32_t bik; };               // bik = bi | k << 16
+struct __align__(16) ChunkRec { uint32_t bitpos, bik, nblk; int dc0, dc1, dc2; uint32_t pad0, pad1; };   // 32 B
+struct __align__(16) ChunkBase { uint32_t blk; int dc0, dc1, dc2; };                                     // 16 B
+
+// The two-level tables of HuffTable (l1 / l2) of the up to six tables of one image, in shared memory.
+struct __align__(16) FastTables {                           // [comp * 2 + (0 = DC, 1 = AC)]
+    uint16_t l1[6][1 << HT_L1_BITS];
+    uint16_t l2[6][HT_SUBS << HT_L2_BITS];
+};
+
+__device__ __forceinline__ uint32_t js_find_seg(const LongSeg* __restrict__ segs, int nsegs, uint32_t cta)
+{
+    int lo = 0, hi = nsegs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].cta_base <= cta) lo = mid; else hi = mid - 1; }
+    return (uint32_t)lo;
+}
+__device__ __forceinline__ uint32_t js_find_seg_chunk(const LongSeg* __restrict__ segs, int nsegs, uint32_t c)
 {
     int lo = 0, hi = nsegs - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].chunk_base <= c) lo = mid; else hi = mid - 1; }
@@ -45,12 +72,12 @@ jpeg_unstuff_kernel(const JpegImage* __restrict__ images, const LongSeg* __restr
                     uint32_t* __restrict__ clean_len)
 {
     __shared__ uint32_t warp_sums[8];
-    __shared__ uint32_t s_base, s_end;
+    __shared__ uint32_t s_end;
     const LongSeg sg = segs[blockIdx.x];
     const uint8_t* in = images[sg.image].data;
     uint8_t* out = clean + sg.clean_off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_base = 0; s_end = 0xffffffffu; }
+    if (tid == 0) s_end = 0xffffffffu;
     __syncthreads();
     uint32_t base = 0;
     for (uint32_t t0 = sg.in_start; t0 < sg.in_end; t0 += 256 * 16) {
@@ -103,233 +130,422 @@ jpeg_unstuff_kernel(const JpegImage* __restrict__ images, const LongSeg* __restr
         if (endp != 0xffffffffu) break;
     }
     // pad with 1-bits: reads past the end of the data return FF (jpegload.d:683-696)
-    for (uint32_t i = tid; i < 64; i += 256) out[base + i] = 0xFF;
+    for (uint32_t i = tid; i < JS_PAD_BYTES; i += 256) out[base + i] = 0xFF;
     if (tid == 0) clean_len[blockIdx.x] = base;
 }
 
-// ---- 2/4. chunk decode ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t js_peek32(const uint32_t* __restrict__ words, uint32_t bitpos)
+// ---- bit reader over the unstuffed stream (big-endian bit order) -----------------------------------------------
+struct JsBits {
+    const uint32_t* __restrict__ w; uint32_t next; uint64_t buf; int cnt;      // cnt valid bits, MSB-aligned
+    __device__ __forceinline__ static uint32_t be(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+    __device__ __forceinline__ void init(const uint32_t* words, uint32_t bitpos)
+    {
+        w = words; next = bitpos >> 5;
+        buf = ((uint64_t)be(__ldg(w + next)) << 32) | be(__ldg(w + next + 1));
+        next += 2;
+        const int sh = bitpos & 31;
+        buf <<= sh; cnt = 64 - sh;
+    }
+    __device__ __forceinline__ void refill() { if (cnt <= 32) { buf |= (uint64_t)be(__ldg(w + next)) << (32 - cnt); ++next; cnt += 32; } }
+    __device__ __forceinline__ uint32_t pos() const { return next * 32u - (uint32_t)cnt; }
+    __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }
+};
+
+struct JsImageCtx {            // per-CTA copy of what the decoders need from JpegImage
+    int bpm; int comp_of[10]; int tab[6];     // tab[comp * 2 + (is AC)] = index into the global HuffTable array
+};
+
+// One Huffman symbol at the head of the bit buffer (>= 32 valid bits): code length, run and size. A bit pattern that
+// is no code word (or a DC symbol > 15) yields bad = true with len = 1, run = size = 0, so that speculative decoders
+// keep moving. `t` = comp * 2 + (is AC).
+__device__ __forceinline__ void js_symbol(const FastTables& ft, int t, const JsImageCtx& cx, const HuffTable* __restrict__ tables,
+                                          uint32_t top, int& len, int& run, int& size, bool& bad)
 {
-    const uint32_t idx = bitpos >> 5, sh = bitpos & 31;
-    const uint32_t w0 = __byte_perm(words[idx], 0, 0x0123), w1 = __byte_perm(words[idx + 1], 0, 0x0123);
-    return __funnelshift_l(w1, w0, sh);
+    uint32_t e = ft.l1[t][top >> (32 - HT_L1_BITS)];
+    if (e & HT_LONG) e = ft.l2[t][((e & 7) << HT_L2_BITS) | ((top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1 << HT_L2_BITS) - 1))];
+    bad = false;
+    len = e & 31; size = (e >> 5) & 15; run = (e >> 9) & 15;
+    if (len && !(e & HT_SLOW)) return;
+    const HuffTable* slow = tables + cx.tab[t];
+    int sym = -1; len = 1;
+    if (e & HT_SLOW) {       // more long-code prefixes than sub-tables: canonical decode of the 10..16-bit codes
+        const uint32_t top16 = top >> 16;
+#pragma unroll 1
+        for (int l = HT_L1_BITS + 1; l <= 16; ++l) {
+            const int code = (int)(top16 >> (16 - l));
+            if (code <= slow->maxcode[l] && code >= slow->mincode[l]) { len = l; sym = slow->val[slow->valptr[l] + code - slow->mincode[l]]; break; }
+        }
+        if (sym >= 0 && slow->is_dc && sym > 15) { sym = -1; len = 1; }
+    }
+    if (sym < 0) { bad = true; size = 0; run = 0; return; }
+    size = sym & 15; run = slow->is_dc ? 0 : sym >> 4;
 }
 
-// Decodes the symbols that start in [st.bitpos, limit). Returns false on a stream error (only meaningful
-// when the entry state is the true state). WRITE: store coefficients of blocks [blk0, blk_end).
-template <bool WRITE>
-__device__ __forceinline__ bool js_decode(const uint32_t* __restrict__ words, ChunkState& st, uint32_t limit,
-                                          const JpegImage& im, const HuffTable* __restrict__ tables,
-                                          uint32_t& nblocks, int16_t* coef_seg, uint32_t blk0, uint32_t blk_end, int dcsum[3])
+// Same symbol through the two-level tables in global memory (used where threads of one CTA serve different images).
+__device__ __forceinline__ void js_symbol_global(const HuffTable* __restrict__ h, uint32_t top, int& len, int& run, int& size, bool& bad)
 {
-    uint32_t bitpos = st.bitpos; int bi = st.bi, k = st.k;
-    const int bpm = im.blocks_per_mcu;
+    uint32_t e = h->l1[top >> (32 - HT_L1_BITS)];
+    if (e & HT_LONG) e = h->l2[e & 7][(top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1 << HT_L2_BITS) - 1)];
+    bad = false;
+    if ((e & 31) && !(e & HT_SLOW)) { len = e & 31; size = (e >> 5) & 15; run = (e >> 9) & 15; return; }
+    int sym = -1; len = 1;
+    if (e & HT_SLOW) {
+        const uint32_t top16 = top >> 16;
+#pragma unroll 1
+        for (int l = HT_L1_BITS + 1; l <= 16; ++l) {
+            const int code = (int)(top16 >> (16 - l));
+            if (code <= h->maxcode[l] && code >= h->mincode[l]) { len = l; sym = h->val[h->valptr[l] + code - h->mincode[l]]; break; }
+        }
+        if (sym >= 0 && h->is_dc && sym > 15) { sym = -1; len = 1; }
+    }
+    if (sym < 0) { bad = true; size = 0; run = 0; return; }
+    size = sym & 15; run = h->is_dc ? 0 : sym >> 4;
+}
+
+__device__ __forceinline__ void js_load_tables(FastTables& ft, JsImageCtx& cx, const JpegImage& im, const HuffTable* __restrict__ tables, int tid, int nthreads)
+{
+    if (tid == 0) {
+        cx.bpm = im.blocks_per_mcu;
+        for (int b = 0; b < 10; ++b) cx.comp_of[b] = b < im.blocks_per_mcu ? im.mcu_org[b] : 0;
+        for (int c = 0; c < 3; ++c) { cx.tab[c * 2] = im.dc_tab[c < im.comps ? c : 0]; cx.tab[c * 2 + 1] = im.ac_tab[c < im.comps ? c : 0]; }
+    }
+    // 16-byte copies of l1 (1 KB) and l2 (2 KB) of every table in use; unused slots are never indexed
+    const int comps = im.comps;
+    constexpr int V1 = (int)(sizeof(uint16_t) << HT_L1_BITS) / 16, V2 = (int)(sizeof(uint16_t) * HT_SUBS << HT_L2_BITS) / 16;
+    for (int i = tid; i < 6 * (V1 + V2); i += nthreads) {
+        const int t = i / (V1 + V2), r = i - t * (V1 + V2);
+        const int c = t >> 1;
+        if (c >= comps) continue;
+        const HuffTable* h = tables + ((t & 1) ? im.ac_tab[c] : im.dc_tab[c]);
+        if (r < V1) ((uint4*)ft.l1[t])[r] = __ldg((const uint4*)h->l1 + r);
+        else ((uint4*)ft.l2[t])[r - V1] = __ldg((const uint4*)h->l2 + (r - V1));
+    }
+}
+
+// Decodes the symbols that START in [st.bitpos, limit) without storing anything: exit state, blocks completed, and
+// the sum of the DC differences per component. One straight-line body for DC and AC symbols (the lanes of a warp are
+// at different symbols), the component of the current block lives in a register.
+__device__ __forceinline__ void js_scan_chunk(const uint32_t* __restrict__ words, ChunkState& st, uint32_t limit,
+                                              const FastTables& ft, const JsImageCtx& cx, const HuffTable* __restrict__ tables,
+                                              uint32_t& nblocks, int dcs[3])
+{
+    int bi = st.bik & 0xffff, k = st.bik >> 16;
+    const int bpm = cx.bpm;
+    int comp = cx.comp_of[bi];
     uint32_t nb = 0;
-    bool ok = true;          // errors count only while the current block lies inside [blk0, blk_end)
-#define JS_ERR() do { if (blk0 + nb < blk_end) ok = false; } while (0)
-    while (bitpos < limit) {
-        const int comp = im.mcu_org[bi];
-        const HuffTable* h = tables + (k == 0 ? im.dc_tab[comp] : im.ac_tab[comp]);
-        const uint32_t v = js_peek32(words, bitpos);
-        const uint32_t top = v >> 16;
-        uint32_t e = h->fast[top >> (16 - HUFF_FAST)];
-        int len, sym;
-        if (e) { len = (int)(e >> 8); sym = (int)(e & 255); }
-        else {
-            len = 0; sym = -1;
-            for (int l = HUFF_FAST + 1; l <= 16; ++l) {
-                const int code = (int)(top >> (16 - l));
-                if (code <= h->maxcode[l] && code >= h->mincode[l]) { len = l; sym = h->val[h->valptr[l] + code - h->mincode[l]]; break; }
-            }
-            if (sym < 0) { JS_ERR(); len = 1; sym = 0; }      // invalid code word: speculative decoders just move on
-        }
-        const int s = sym & 15;
-        const uint32_t extra = s ? ((v << len) >> (32 - s)) : 0u;
-        bitpos += (uint32_t)(len + s);
-        if (k == 0) {
-            if (sym > 15) JS_ERR();
-            const int diff = huff_extend((int)extra, s);
-            if (WRITE) { const uint32_t b = blk0 + nb; if (b < blk_end) coef_seg[(size_t)b * 64] = (int16_t)diff; dcsum[comp] += diff; }
-            k = 1;
-        } else {
-            const int r = sym >> 4;
-            if (s) {
-                if (r) { if (k + r > 63) { JS_ERR(); k = 63; } else k += r; }
-                if (WRITE) { const uint32_t b = blk0 + nb; if (b < blk_end) coef_seg[(size_t)b * 64 + c_zag[k]] = (int16_t)(huff_extend((int)extra, s) * im.quant[comp][k]); }
-                k += 1;
-            } else if (r == 15) { if (k + 16 > 64) { JS_ERR(); k = 64; } else k += 16; }
-            else k = 64;
-        }
-        if (k >= 64) { k = 0; ++nb; bi = bi + 1 == bpm ? 0 : bi + 1; }
+    int d0 = 0, d1 = 0, d2 = 0;
+    JsBits br; br.init(words, st.bitpos);
+    uint32_t pos = st.bitpos;
+    while (pos < limit) {
+        br.refill();
+        const bool is_dc = k == 0;
+        const uint32_t top = br.top32();
+        int len, run, size; bool bad;
+        js_symbol(ft, comp * 2 + (is_dc ? 0 : 1), cx, tables, top, len, run, size, bad);
+        const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
+        const int diff = is_dc ? huff_extend((int)extra, size) : 0;
+        d0 += comp == 0 ? diff : 0; d1 += comp == 1 ? diff : 0; d2 += comp == 2 ? diff : 0;
+        k = is_dc ? 1 : (size ? k + run + 1 : (run == 15 ? k + 16 : 64));
+        br.drop(len + size);
+        pos += (uint32_t)(len + size);
+        if (k >= 64) { k = 0; ++nb; bi = bi + 1 == bpm ? 0 : bi + 1; comp = cx.comp_of[bi]; }
     }
-#undef JS_ERR
-    st.bitpos = bitpos; st.bi = (uint16_t)bi; st.k = (uint16_t)k;
-    nblocks = nb;
-    return ok;
+    st.bitpos = pos; st.bik = (uint32_t)bi | ((uint32_t)k << 16);
+    nblocks = nb; dcs[0] = d0; dcs[1] = d1; dcs[2] = d2;
 }
 
-// pass: 0 = speculative first pass, >0 = relaxation. exit/nblk are updated in place; `changed` counts updates.
-__global__ void __launch_bounds__(128)
+// ---- 2. sync: CTA-local relaxation ------------------------------------------------------------------------------
+// After the first pass only the chunks whose entry state is stale decode again. They are compacted every round so that
+// the stale chunks of the whole CTA fill as few warps as possible (a warp costs a full chunk decode however few of
+// its lanes work).
+__global__ void __launch_bounds__(JS_CTA)
 jpeg_sync_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict__ segs, int nsegs,
-                 uint32_t total_chunks, const uint8_t* __restrict__ clean, const uint32_t* __restrict__ clean_len,
-                 const HuffTable* __restrict__ tables, ChunkState* exitst, uint32_t* nblk,
-                 const uint8_t* __restrict__ dirty_in, uint8_t* __restrict__ dirty_out, int pass, uint32_t* changed)
+                 const uint8_t* __restrict__ clean, const uint32_t* __restrict__ clean_len,
+                 const HuffTable* __restrict__ tables, ChunkRec* __restrict__ recs, ChunkState* __restrict__ entry_used)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_chunks) return;
-    const uint32_t si = js_find_seg(segs, nsegs, c);
+    __shared__ FastTables ft;
+    __shared__ JsImageCtx cx;
+    __shared__ uint2 s_entry[JS_CTA], s_exit[JS_CTA], s_todo_entry[JS_CTA];
+    __shared__ uint4 s_res[JS_CTA];                 // blocks completed, DC sums
+    __shared__ uint16_t s_todo[JS_CTA];
+    __shared__ uint32_t s_wcount[JS_CTA / 32];
+    const uint32_t si = js_find_seg(segs, nsegs, blockIdx.x);
     const LongSeg sg = segs[si];
-    const uint32_t lc = c - sg.chunk_base;             // chunk index inside the segment
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    js_load_tables(ft, cx, images[sg.image], tables, tid, JS_CTA);
+    const uint32_t local_cta = blockIdx.x - sg.cta_base;
+    // chunk of slot s: the first JS_WARM slots re-decode the tail of the previous CTA's range
+    const long long lc_first = (long long)local_cta * JS_OWN - JS_WARM;
     const uint32_t total_bits = clean_len[si] * 8;
-    // chunks are laid out for the stuffed length; those wholly behind the unstuffed data take no part
-    if (lc > 0 && lc * (uint32_t)JS_CHUNK_BITS >= total_bits) {
-        if (pass == 0) { ChunkState z; z.bitpos = total_bits; z.bi = 0; z.k = 0; js_store(exitst + c, z); nblk[c] = 0; }
-        dirty_out[c] = 0;
-        return;
+    const uint32_t* words = (const uint32_t*)(clean + sg.clean_off);
+    // chunks are laid out for the stuffed length; those wholly behind the unstuffed data hold nothing
+    auto slot_active = [&](int s) {
+        const long long l = lc_first + s;
+        return l >= 0 && l < (long long)sg.nchunks && (l == 0 || (uint32_t)l * (uint32_t)JS_CHUNK_BITS < total_bits);
+    };
+    __syncthreads();
+
+    {   // first pass: every chunk from the guessed state "a block starts at the first bit of the chunk"
+        const bool active = slot_active(tid);
+        const uint32_t lc = active ? (uint32_t)(lc_first + tid) : 0;
+        ChunkState st; st.bitpos = lc * JS_CHUNK_BITS; st.bik = 0;
+        s_entry[tid] = make_uint2(st.bitpos, st.bik);
+        uint32_t nb = 0; int dcs[3] = {0, 0, 0};
+        if (active) js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), ft, cx, tables, nb, dcs);
+        else { st.bitpos = total_bits; st.bik = 0; }
+        s_exit[tid] = make_uint2(st.bitpos, st.bik);
+        s_res[tid] = make_uint4(nb, (uint32_t)dcs[0], (uint32_t)dcs[1], (uint32_t)dcs[2]);
     }
-    if (pass > 0) {
-        dirty_out[c] = 0;
-        if (lc == 0 || !dirty_in[c - 1]) return;       // my entry state did not change
+    // a chunk takes its predecessor's exit state unless it sits in slot 0 (whose guess stands) or is chunk 0 of the
+    // segment (whose "guess" is the true start state)
+    const bool chained = tid > 0 && slot_active(tid) && lc_first + tid > 0;
+    for (;;) {
+        __syncthreads();
+        bool stale = false;
+        uint2 prev = make_uint2(0, 0);
+        if (chained) { prev = s_exit[tid - 1]; const uint2 mine = s_entry[tid]; stale = prev.x != mine.x || prev.y != mine.y; }
+        const uint32_t bal = __ballot_sync(0xffffffffu, stale);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < JS_CTA / 32; ++w) { const uint32_t c = s_wcount[w]; off += w < warp ? c : 0; total += c; }
+        if (total == 0) break;
+        if (stale) { const uint32_t p = off + __popc(bal & ((1u << lane) - 1)); s_todo[p] = (uint16_t)tid; s_todo_entry[p] = prev; }
+        __syncthreads();
+        if ((uint32_t)tid < total) {
+            const int s = s_todo[tid];
+            const uint2 e = s_todo_entry[tid];
+            const uint32_t lc = (uint32_t)(lc_first + s);
+            ChunkState st; st.bitpos = e.x; st.bik = e.y;
+            uint32_t nb = 0; int dcs[3];
+            js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), ft, cx, tables, nb, dcs);
+            s_entry[s] = e;
+            s_exit[s] = make_uint2(st.bitpos, st.bik);
+            s_res[s] = make_uint4(nb, (uint32_t)dcs[0], (uint32_t)dcs[1], (uint32_t)dcs[2]);
+        }
     }
+    const long long lc_s = lc_first + tid;
+    if (tid >= JS_WARM && lc_s < (long long)sg.nchunks) {
+        const uint2 x = s_exit[tid]; const uint4 r = s_res[tid];
+        ChunkRec* dst = recs + sg.chunk_base + (uint32_t)lc_s;
+        ((uint4*)dst)[0] = make_uint4(x.x, x.y, r.x, r.y);
+        ((uint4*)dst)[1] = make_uint4(r.z, r.w, 0u, 0u);
+    }
+    if (tid == JS_WARM) { ChunkState e; const uint2 v = s_entry[tid]; e.bitpos = v.x; e.bik = v.y; entry_used[blockIdx.x] = e; }   // the state assumed at the first own chunk
+}
+
+// ---- 3. repair / check of the CTA boundaries --------------------------------------------------------------------
+// mode 0: repair (walk forward from a wrong boundary); mode 1: count boundaries that still disagree.
+__global__ void __launch_bounds__(64)
+jpeg_repair_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict__ segs, int nsegs, uint32_t total_ctas,
+                   const uint8_t* __restrict__ clean, const uint32_t* __restrict__ clean_len,
+                   const HuffTable* __restrict__ tables, ChunkRec* recs, ChunkState* entry_used, int mode, uint32_t* unconverged)
+{
+    const uint32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cta >= total_ctas) return;
+    const uint32_t si = js_find_seg(segs, nsegs, cta);
+    const LongSeg sg = segs[si];
+    const uint32_t local_cta = cta - sg.cta_base;
+    if (local_cta == 0) return;                                  // starts from the true state
+    const uint32_t lc0 = local_cta * JS_OWN;
+    const uint32_t total_bits = clean_len[si] * 8;
+    if (lc0 >= sg.nchunks || lc0 * (uint32_t)JS_CHUNK_BITS >= total_bits) return;     // nothing of its own to decode
+    const ChunkRec* pr = recs + sg.chunk_base + lc0 - 1;
+    const uint2 truth = __ldcg((const uint2*)pr);
+    ChunkState used = entry_used[cta];
+    if (truth.x == used.bitpos && truth.y == used.bik) return;
+    if (mode == 1) { atomicAdd(unconverged, 1u); return; }
+    // walk: taken by very few threads, through the global tables (threads of one CTA here serve different images)
     const JpegImage& im = images[sg.image];
-    const uint32_t limit = min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits);
-    ChunkState st;
-    if (pass == 0 || lc == 0) { st.bitpos = lc * JS_CHUNK_BITS; st.bi = 0; st.k = 0; }
-    if (pass > 0 && lc > 0) st = js_load(exitst + c - 1);
-    uint32_t nb = 0; int dummy[3];
-    js_decode<false>((const uint32_t*)(clean + sg.clean_off), st, limit, im, tables, nb, nullptr, 0, 0, dummy);
-    if (pass == 0) { js_store(exitst + c, st); nblk[c] = nb; dirty_out[c] = 1; }
-    else {
-        const ChunkState old = js_load(exitst + c);
-        const bool ch = old.bitpos != st.bitpos || old.bi != st.bi || old.k != st.k;
-        js_store(exitst + c, st); nblk[c] = nb;
-        if (ch) { dirty_out[c] = 1; atomicAdd(changed, 1u); }
+    const uint32_t* words = (const uint32_t*)(clean + sg.clean_off);
+    ChunkState st; st.bitpos = truth.x; st.bik = truth.y;
+    entry_used[cta] = st;
+    const uint32_t lc_end = min(lc0 + (uint32_t)JS_OWN, sg.nchunks);
+    for (uint32_t lc = lc0; lc < lc_end; ++lc) {
+        if (lc * (uint32_t)JS_CHUNK_BITS >= total_bits) break;
+        const uint32_t limit = min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits);
+        // plain decode through the global tables (same symbol semantics as js_scan_chunk)
+        int bi = st.bik & 0xffff, k = st.bik >> 16;
+        uint32_t nb = 0; int d[3] = {0, 0, 0};
+        JsBits br; br.init(words, st.bitpos);
+        uint32_t pos = st.bitpos;
+        while (pos < limit) {
+            br.refill();
+            const int comp = im.mcu_org[bi];
+            const bool is_dc = k == 0;
+            const uint32_t top = br.top32();
+            int len, run, size; bool bad;
+            js_symbol_global(tables + (is_dc ? im.dc_tab[comp] : im.ac_tab[comp]), top, len, run, size, bad);
+            if (is_dc) {
+                const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
+                d[comp] += huff_extend((int)extra, size);
+                k = 1;
+            } else k = size ? k + run + 1 : (run == 15 ? k + 16 : 64);
+            br.drop(len + size); pos += (uint32_t)(len + size);
+            if (k >= 64) { k = 0; ++nb; bi = bi + 1 == im.blocks_per_mcu ? 0 : bi + 1; }
+        }
+        st.bitpos = pos; st.bik = (uint32_t)bi | ((uint32_t)k << 16);
+        ChunkRec* dst = recs + sg.chunk_base + lc;
+        const uint2 old = __ldcg((const uint2*)dst);
+        ((uint4*)dst)[0] = make_uint4(st.bitpos, st.bik, nb, (uint32_t)d[0]);
+        ((uint4*)dst)[1] = make_uint4((uint32_t)d[1], (uint32_t)d[2], 0u, 0u);
+        if (old.x == st.bitpos && old.y == st.bik) break;        // met the old chain: everything after is already right
     }
 }
 
-// ---- 3. scan over the chunks of each segment: block base (exclusive) -----------------------------------
+// ---- 4. scan over the chunks of each segment: block base and DC bases (exclusive) -------------------------------
 __global__ void __launch_bounds__(256)
-jpeg_scan_kernel(const LongSeg* __restrict__ segs, const uint32_t* __restrict__ vals, uint32_t* __restrict__ excl)
+jpeg_scan_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict__ segs, const ChunkRec* __restrict__ recs,
+                 ChunkBase* __restrict__ bases, int* status)
 {
-    __shared__ uint32_t ws[8];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t ws[8][4];
+    __shared__ uint32_t carry[4];
     const LongSeg sg = segs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid < 4) carry[tid] = 0;
     __syncthreads();
     for (uint32_t t0 = 0; t0 < sg.nchunks; t0 += 256) {
         const uint32_t i = t0 + tid;
-        const uint32_t v = i < sg.nchunks ? vals[sg.chunk_base + i] : 0;
-        uint32_t inc = v;
+        uint32_t v[4] = {0, 0, 0, 0}, inc[4];
+        if (i < sg.nchunks) {
+            const ChunkRec* r = recs + sg.chunk_base + i;
+            const uint4 a = ((const uint4*)r)[0]; const uint4 b = ((const uint4*)r)[1];
+            v[0] = a.z; v[1] = a.w; v[2] = b.x; v[3] = b.y;
+        }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
-        if (lane == 31) ws[warp] = inc;
-        __syncthreads();
-        uint32_t off = carry;
-        for (int w = 0; w < warp; ++w) off += ws[w];
-        if (i < sg.nchunks) excl[sg.chunk_base + i] = off + inc - v;
-        __syncthreads();
-        if (tid == 255) carry = off + inc;
-        __syncthreads();
-    }
-}
-// same for the three DC sums (int32, wrap-around like the reference's uint accumulation)
-__global__ void __launch_bounds__(256)
-jpeg_scan3_kernel(const LongSeg* __restrict__ segs, const int* __restrict__ vals /* [chunk][3] */, int* __restrict__ excl)
-{
-    __shared__ int ws[8][3];
-    __shared__ int carry[3];
-    const LongSeg sg = segs[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 3) carry[tid] = 0;
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < sg.nchunks; t0 += 256) {
-        const uint32_t i = t0 + tid;
-        int v[3], inc[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { v[q] = i < sg.nchunks ? vals[(size_t)(sg.chunk_base + i) * 3 + q] : 0; inc[q] = v[q]; }
+        for (int q = 0; q < 4; ++q) inc[q] = v[q];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const int n = __shfl_up_sync(0xffffffffu, inc[q], d); if (lane >= d) inc[q] += n; }
+            for (int q = 0; q < 4; ++q) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc[q], d); if (lane >= d) inc[q] += n; }
         }
-        if (lane == 31) { ws[warp][0] = inc[0]; ws[warp][1] = inc[1]; ws[warp][2] = inc[2]; }
+        if (lane == 31) { ws[warp][0] = inc[0]; ws[warp][1] = inc[1]; ws[warp][2] = inc[2]; ws[warp][3] = inc[3]; }
         __syncthreads();
+        uint32_t ex[4];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            int off = carry[q];
+        for (int q = 0; q < 4; ++q) {
+            uint32_t off = carry[q];
             for (int w = 0; w < warp; ++w) off += ws[w][q];
-            if (i < sg.nchunks) excl[(size_t)(sg.chunk_base + i) * 3 + q] = off + inc[q] - v[q];
+            ex[q] = off + inc[q] - v[q];
             inc[q] += off;
         }
+        if (i < sg.nchunks) *(uint4*)(bases + sg.chunk_base + i) = make_uint4(ex[0], ex[1], ex[2], ex[3]);
         __syncthreads();
-        if (tid == 255) { carry[0] = inc[0]; carry[1] = inc[1]; carry[2] = inc[2]; }
+        if (tid == 255) { carry[0] = inc[0]; carry[1] = inc[1]; carry[2] = inc[2]; carry[3] = inc[3]; }
         __syncthreads();
     }
+    // the stream must hold every block of the segment
+    if (tid == 0 && carry[0] < (uint32_t)sg.num_mcus * (uint32_t)images[sg.image].blocks_per_mcu) status[sg.image] = 0;
 }
 
-// ---- 4. write pass ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// ---- 5. write pass ------------------------------------------------------------------------------------------------
+// Every lane assembles the block it is decoding in shared memory (64 int16 = 32 words; word w of lane l sits at
+// [l][(w + l) & 31], so the lanes' scatters and the flush below are both free of bank conflicts). When a lane
+// completes a block the whole warp writes it out -- one coalesced 128-byte row per block, zeros included -- and clears
+// the lane's buffer: the coefficient array is written exactly once, in full sectors, with no zero-fill pass.
+constexpr int JW_CTA = 256;
+__global__ void __launch_bounds__(JW_CTA)
 jpeg_write_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict__ segs, int nsegs,
-                  uint32_t total_chunks, const uint8_t* __restrict__ clean, const uint32_t* __restrict__ clean_len,
-                  const HuffTable* __restrict__ tables, const ChunkState* exitst, const uint32_t* __restrict__ blkbase,
-                  int* __restrict__ dcsum, int* status)
+                  const uint8_t* __restrict__ clean, const uint32_t* __restrict__ clean_len,
+                  const HuffTable* __restrict__ tables, const ChunkRec* __restrict__ recs, const ChunkBase* __restrict__ bases,
+                  int* status)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_chunks) return;
-    const uint32_t si = js_find_seg(segs, nsegs, c);
+    __shared__ FastTables ft;
+    __shared__ JsImageCtx cx;
+    __shared__ int16_t s_quant[3][64];
+    __shared__ uint8_t s_zag[64];
+    __shared__ uint32_t s_blk[JW_CTA][32];
+    // CTA -> (segment, JW_CTA consecutive chunks): chunk_base of every segment is a multiple of JW_CTA (host)
+    const uint32_t si = js_find_seg_chunk(segs, nsegs, blockIdx.x * JW_CTA);
     const LongSeg sg = segs[si];
-    const uint32_t lc = c - sg.chunk_base;
     const JpegImage& im = images[sg.image];
+    const int tid = threadIdx.x, lane = tid & 31;
+    js_load_tables(ft, cx, im, tables, tid, JW_CTA);
+    for (int i = tid; i < 192; i += JW_CTA) s_quant[i >> 6][i & 63] = (i >> 6) < im.comps ? im.quant[i >> 6][i & 63] : (int16_t)0;
+    if (tid < 64) s_zag[tid] = c_zag[tid];
+#pragma unroll
+    for (int w = 0; w < 32; ++w) s_blk[tid][(w + lane) & 31] = 0;
+    __syncthreads();
+    const uint32_t lc = blockIdx.x * JW_CTA + tid - sg.chunk_base;
     const uint32_t total_bits = clean_len[si] * 8;
+    bool alive = lc < sg.nchunks && (lc == 0 || lc * (uint32_t)JS_CHUNK_BITS < total_bits);      // else: behind the data
     const uint32_t limit = min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits);
-    if (lc > 0 && lc * (uint32_t)JS_CHUNK_BITS >= total_bits) {      // behind the data
-        dcsum[(size_t)c * 3 + 0] = 0; dcsum[(size_t)c * 3 + 1] = 0; dcsum[(size_t)c * 3 + 2] = 0;
-        return;
+    const uint32_t hard_limit = total_bits + (JS_PAD_BYTES - 16) * 8;            // never read past the padding
+    ChunkState st; st.bitpos = 0; st.bik = 0;
+    uint4 bs = make_uint4(0, 0, 0, 0);
+    if (alive) {
+        if (lc > 0) { const uint2 v = __ldg((const uint2*)(recs + sg.chunk_base + lc - 1)); st.bitpos = v.x; st.bik = v.y; }
+        bs = __ldg((const uint4*)(bases + sg.chunk_base + lc));
     }
-    ChunkState st;
-    if (lc == 0) { st.bitpos = 0; st.bi = 0; st.k = 0; } else st = js_load(exitst + c - 1);
-    const uint32_t seg_blocks = (uint32_t)sg.num_mcus * im.blocks_per_mcu;
-    const uint32_t b0 = blkbase[c];
-    int ds[3] = {0, 0, 0};
-    uint32_t nb = 0;
-    int16_t* coef_seg = im.coefs + (size_t)sg.first_mcu * im.blocks_per_mcu * 64;
-    if (b0 < seg_blocks) {
-        // symbols after the segment's last block (padding bits) are decoded but neither stored nor checked
-        if (!js_decode<true>((const uint32_t*)(clean + sg.clean_off), st, limit, im, tables, nb, coef_seg, b0, seg_blocks, ds))
-            status[sg.image] = 0;
+    const int bpm = cx.bpm;
+    const uint32_t seg_blocks = (uint32_t)sg.num_mcus * (uint32_t)bpm;
+    int bi = st.bik & 0xffff, k = st.bik >> 16;
+    int comp = cx.comp_of[bi];
+    uint32_t b = bs.x;                              // index of the block in progress / about to start
+    int dc0 = (int)bs.y, dc1 = (int)bs.z, dc2 = (int)bs.w;
+    int16_t* const coef_seg = im.coefs + (size_t)sg.first_mcu * bpm * 64;
+    uint8_t* const zag_seg = im.blk_zag + (size_t)sg.first_mcu * bpm;
+    const uint32_t* words = (const uint32_t*)(clean + sg.clean_off);
+    JsBits br; br.init(words, alive ? st.bitpos : 0);
+    uint32_t pos = st.bitpos;
+    bool mine = k == 0;                             // a block in progress at the entry belongs to an earlier chunk
+    int last_k = 0;
+    bool ok = true;
+    uint32_t* const myrow = s_blk[tid];
+    const uint32_t* const wrow = s_blk[tid & ~31];  // first row of my warp
+    alive = alive && b < seg_blocks && pos < limit;
+    // symbols of my blocks may run past `limit`; a new block is only started before it
+    while (__any_sync(0xffffffffu, alive)) {
+        bool flush = false;
+        if (alive) {
+            br.refill();
+            const bool is_dc = k == 0;
+            const uint32_t top = br.top32();
+            int len, run, size; bool bad;
+            js_symbol(ft, comp * 2 + (is_dc ? 0 : 1), cx, tables, top, len, run, size, bad);
+            const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
+            int val = huff_extend((int)extra, size);
+            if (is_dc) {
+                mine = true;
+                val += comp == 0 ? dc0 : comp == 1 ? dc1 : dc2;
+                dc0 = comp == 0 ? val : dc0; dc1 = comp == 1 ? val : dc1; dc2 = comp == 2 ? val : dc2;
+                last_k = 0;
+            } else if (size) {
+                k += run;
+                if (k > 63) { bad = true; k = 63; }
+            } else if (run == 15 && k + 16 > 64) bad = true;
+            if (mine && bad) ok = false;
+            if (mine && (is_dc || size)) {
+                const int zz = s_zag[k];
+                ((int16_t*)(myrow + (((zz >> 1) + lane) & 31)))[zz & 1] = (int16_t)(val * s_quant[comp][k]);
+                last_k = k;
+            }
+            k = is_dc ? 1 : (size ? k + 1 : (run == 15 ? k + 16 : 64));
+            br.drop(len + size);
+            pos += (uint32_t)(len + size);
+            flush = k >= 64 && mine;
+        }
+        // whole-warp flush of the blocks completed in this round
+        uint32_t fb = __ballot_sync(0xffffffffu, flush);
+        if (fb) {
+            __syncwarp();
+            while (fb) {
+                const int l = __ffs(fb) - 1; fb &= fb - 1;
+                const uint32_t blk = __shfl_sync(0xffffffffu, b, l);
+                uint32_t* row = (uint32_t*)wrow + l * 32 + ((lane + l) & 31);
+                ((uint32_t*)(coef_seg + (size_t)blk * 64))[lane] = *row;
+                *row = 0;
+            }
+            __syncwarp();
+        }
+        if (alive && k >= 64) {
+            if (mine) zag_seg[b] = (uint8_t)(last_k + 1);
+            k = 0; ++b; bi = bi + 1 == bpm ? 0 : bi + 1; comp = cx.comp_of[bi];
+            if (pos >= limit) alive = false;        // the next block starts in a later chunk
+        }
+        alive = alive && (pos < limit || (mine && k != 0)) && pos < hard_limit && b < seg_blocks;
     }
-    dcsum[(size_t)c * 3 + 0] = ds[0]; dcsum[(size_t)c * 3 + 1] = ds[1]; dcsum[(size_t)c * 3 + 2] = ds[2];
-    // the last chunk checks that the stream held all the blocks
-    if ((lc + 1) * (uint32_t)JS_CHUNK_BITS >= total_bits && b0 + nb < seg_blocks) status[sg.image] = 0;
-}
-
-// ---- 5. DC prediction ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-jpeg_dcfix_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict__ segs, int nsegs,
-                  uint32_t total_chunks, const ChunkState* exitst, const uint32_t* __restrict__ blkbase,
-                  const uint32_t* __restrict__ nblk, const int* __restrict__ dcbase)
-{
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_chunks) return;
-    const uint32_t si = js_find_seg(segs, nsegs, c);
-    const LongSeg sg = segs[si];
-    const uint32_t lc = c - sg.chunk_base;
-    const JpegImage& im = images[sg.image];
-    const uint32_t seg_blocks = (uint32_t)sg.num_mcus * im.blocks_per_mcu;
-    // blocks whose DC symbol was decoded by this chunk: from the first block that starts here ...
-    const int entry_k = lc == 0 ? 0 : js_load(exitst + c - 1).k;
-    const int exit_k = js_load(exitst + c).k;
-    uint32_t b = blkbase[c] + (entry_k != 0 ? 1u : 0u);
-    uint32_t e = blkbase[c] + nblk[c] + (exit_k != 0 ? 1u : 0u);      // ... to the one still open at the exit
-    if (e > seg_blocks) e = seg_blocks;
-    int dc[3] = {dcbase[(size_t)c * 3], dcbase[(size_t)c * 3 + 1], dcbase[(size_t)c * 3 + 2]};
-    int16_t* coef_seg = im.coefs + (size_t)sg.first_mcu * im.blocks_per_mcu * 64;
-    const int bpm = im.blocks_per_mcu;
-    for (; b < e; ++b) {
-        const int comp = im.mcu_org[b % bpm];
-        int16_t* p = coef_seg + (size_t)b * 64;
-        dc[comp] += (int)p[0];
-        p[0] = (int16_t)(dc[comp] * im.quant[comp][0]);
-    }
+    if (!ok) status[sg.image] = 0;
 }

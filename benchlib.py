@@ -361,7 +361,7 @@ class PngWorkload(_WorkloadBase):
     default_e2e_steps = 5
     W, H = 1920, 1080
     DISTINCT = 8
-    e2e_api = "gb200_png_decode_batch (host file bytes; IDAT staged through pinned memory; pixels copied back to pinned host memory with gb200_batch_download)"
+    e2e_api = "gb200_decode_batch_host(PNG): host file bytes in, rgba8 pixels in pinned host memory out; sub-batches pipelined (download of k overlaps upload + kernels of k+1)"
 
     def __init__(self, rank, world, args):
         import torch
@@ -498,10 +498,8 @@ class PngWorkload(_WorkloadBase):
         _e2e_threads(self.e2e_n, self._e2e_slice)
 
     def _e2e_slice(self, a, b_):
-        b = self.codecs.png_decode_batch(self.host_files[a:b_], 0, 0)
-        assert all(d.status for d in b.images)
-        b.download(self.h_out + a * self.out_stride, self.out_stride)
-        b.free()
+        descs = self.codecs.decode_batch_host(1, self.host_files[a:b_], 0, 0, self.h_out + a * self.out_stride, self.out_stride)
+        assert all(d.status for d in descs)
 
     @staticmethod
     def cpu_run(threads, reps, full):
@@ -588,10 +586,9 @@ class _BatchDecodeWorkload(_WorkloadBase):
         _e2e_threads(self.e2e_n, self._e2e_slice)
 
     def _e2e_slice(self, a, b_):
-        b = self.decode(self.host_files[a:b_], None, 0)
-        assert all(d.status for d in b.images)
-        b.download(self.h_out + a * self.out_bytes, self.out_bytes)
-        b.free()
+        descs = self.codecs.decode_batch_host(self.FORMAT, self.host_files[a:b_], self.E2E_ARG, 0,
+                                              self.h_out + a * self.out_bytes, self.out_bytes)
+        assert all(d.status for d in descs)
 
     def roofline(self, peak, peak_kind):
         """The dominant kernel (group) of the step: the phase with the largest device time, measured live with CUDA
@@ -627,11 +624,12 @@ class JpegWorkload(_BatchDecodeWorkload):
     """BASELINE configs[3]: JPEG baseline decode (Huffman+IDCT+YCbCr), 3840x2160 4:2:0 q90, batch sharded over ranks."""
     name = "JPEG baseline decode (Huffman+IDCT+YCbCr) 3840x2160 4:2:0 q90, batch sharded 1/2/4/8 GPU (BASELINE configs[3])"
     W, H = 3840, 2160
-    e2e_api = "gb200_jpeg_decode_batch (host file bytes staged through pinned memory; rgb8 pixels copied back to pinned host memory with gb200_batch_download)"
+    e2e_api = "gb200_decode_batch_host(JPEG): host file bytes in, rgb8 pixels in pinned host memory out; sub-batches pipelined (download of k overlaps upload + kernels of k+1)"
+    FORMAT, E2E_ARG = 0, -1
     kernel_names = {1: "jpeg entropy stage (unstuff/sync/scan/write kernels)", 2: "jpeg_idct_colour_kernel"}
     traffic_keys = {1: "jpeg_entropy", 2: "jpeg_idct_colour_kernel"}
     SUB_BATCH = 512
-    E2E_N = 128
+    E2E_N = 256
 
     def __init__(self, rank, world, args):
         self._setup(rank, world, args, 4096)
@@ -687,7 +685,8 @@ class QoixWorkload(_BatchDecodeWorkload):
     name = "QOIX 10-bit LA + LZ4 decode 2048x2048, batch 2048 sharded over ranks (BASELINE configs[4])"
     dtype = "u16"
     W, H = 2048, 2048
-    e2e_api = "gb200_qoix_decode_batch (host file bytes staged through pinned memory; la16 pixels copied back to pinned host memory with gb200_batch_download)"
+    e2e_api = "gb200_decode_batch_host(QOIX): host file bytes in, la16 pixels in pinned host memory out; sub-batches pipelined (download of k overlaps upload + kernels of k+1)"
+    FORMAT, E2E_ARG = 3, 0
     E2E_N = 256
     kernel_names = {1: "lz4 kernels (spec/merge/scan/pwrite/parse/resolve)", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
     traffic_keys = {1: "lz4", 2: "qoiplane10"}

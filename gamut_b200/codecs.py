@@ -66,6 +66,8 @@ def _L():
         L.gb200_qoix_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoixDesc), i32, ip]
         L.gb200_qoix_decode_batch.restype = vp
         L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
+        L.gb200_decode_batch_host.argtypes = [i32, i32, C.POINTER(C.c_char_p), C.POINTER(sz), i32, i32, vp, sz,
+                                              C.POINTER(ImageDesc), i32]
         _declared = True
     return L
 
@@ -260,3 +262,14 @@ def qoix_decode_batch(files: Sequence[bytes], flags: int = 0, files_dev: Optiona
     if not h:
         raise _lib.GamutB200Error("qoix_decode_batch: " + _lib.last_error())
     return Batch(h)
+
+
+def decode_batch_host(fmt: int, files: Sequence[bytes], arg: int, want16: int, dst_host: int, dst_stride: int,
+                      sub_batch: int = 0):
+    """gb200_decode_batch_host: host files in, pixels in host memory at dst_host + i*dst_stride, transfers overlapped
+    with the decode of the next sub-batch. Returns the list of descriptors (pixels = host address, 0 if failed)."""
+    n, arr, lens, _ = _batch_args(files, None)
+    descs = (ImageDesc * max(n, 1))()
+    _lib.check(_L().gb200_decode_batch_host(int(fmt), n, arr, lens, arg, want16, dst_host, dst_stride, descs, sub_batch),
+               "decode_batch_host")
+    return [descs[i] for i in range(n)]

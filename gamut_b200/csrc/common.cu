@@ -7,6 +7,7 @@
 #include <map>
 #include <vector>
 #include <atomic>
+#include <array>
 
 namespace gb {
 
@@ -31,35 +32,37 @@ bool cuda_ok(cudaError_t e, const char* what, const char* file, int line)
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static std::once_flag g_once;
-static bool g_dev_ok = false;
-static int g_sms = 0;
+// Per-device state: a process may drive several devices (cudaSetDevice between calls); everything cached is keyed by
+// the current device.
+constexpr int MAX_DEV = 64;
+static std::mutex g_dev_m;
+static int g_dev_state[MAX_DEV];       // 0 unknown, 1 usable, -1 unusable
+static int g_sms[MAX_DEV];
+
+static int current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; } return d; }
 
 bool ensure_device()
 {
-    std::call_once(g_once, [] {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n <= 0) {
-            set_error("gamut_b200: no CUDA device available (%s); there is no CPU fallback",
-                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-            return;
+    const int dev = current_device();
+    if (dev < 0 || dev >= MAX_DEV) {
+        set_error("gamut_b200: no CUDA device available; there is no CPU fallback");
+        return false;
+    }
+    {
+        std::lock_guard<std::mutex> g(g_dev_m);
+        if (g_dev_state[dev] == 0) {
+            cudaDeviceProp p;
+            if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); g_dev_state[dev] = -1; }
+            else if (p.major != 10) { set_error("gamut_b200: built for sm_100a only, found sm_%d%d", p.major, p.minor); g_dev_state[dev] = -1; }
+            else { g_sms[dev] = p.multiProcessorCount; g_dev_state[dev] = 1; }
         }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return; }
-        if (p.major != 10) {
-            set_error("gamut_b200: built for sm_100a only, found sm_%d%d", p.major, p.minor);
-            return;
-        }
-        g_sms = p.multiProcessorCount;
-        g_dev_ok = true;
-    });
-    if (!g_dev_ok && t_err[0] == 0) set_error("gamut_b200: no usable sm_100 CUDA device; there is no CPU fallback");
-    return g_dev_ok;
+        if (g_dev_state[dev] == 1) return true;
+    }
+    if (t_err[0] == 0) set_error("gamut_b200: no usable sm_100 CUDA device; there is no CPU fallback");
+    return false;
 }
-int sm_count() { return g_sms > 0 ? g_sms : 148; }
+int sm_count() { const int d = current_device(); return d >= 0 && d < MAX_DEV && g_sms[d] > 0 ? g_sms[d] : 148; }
+int device_index() { return current_device(); }
 
 // ---------------------------------------------------------------------------------------------
 // Caching allocator: power-of-two-ish buckets (round up to 1/8 octave above 1 MiB, 512 B below).
@@ -149,13 +152,16 @@ void  pinned_free(void* p) { pool_free(hpool(), p); }
 
 cudaStream_t thread_stream(int idx)
 {
-    static thread_local cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+    // four streams per (thread, device): a stream belongs to the device that was current when it was created
+    static thread_local std::map<int, std::array<cudaStream_t, 4>> per_dev;
     idx &= 3;
-    if (!s[idx]) {
-        if (!ensure_device()) return nullptr;
-        if (cudaStreamCreateWithFlags(&s[idx], cudaStreamNonBlocking) != cudaSuccess) { s[idx] = nullptr; }
-    }
-    return s[idx];
+    if (!ensure_device()) return nullptr;
+    const int dev = current_device();
+    auto it = per_dev.find(dev);
+    if (it == per_dev.end()) it = per_dev.emplace(dev, std::array<cudaStream_t, 4>{nullptr, nullptr, nullptr, nullptr}).first;
+    cudaStream_t& st = it->second[idx];
+    if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st = nullptr; }
+    return st;
 }
 
 void host_copy_parallel(const HostCopy* copies, size_t count)

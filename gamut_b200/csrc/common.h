@@ -27,6 +27,7 @@ void count_launch(int n = 1);
 // Lazy one-time context init on the current device; fails loudly when there is no GPU.
 bool ensure_device();
 int  sm_count();
+int  device_index();     // current CUDA device (-1 if none); cached state is keyed by it
 
 // Size-bucketed caching device allocator (cudaMalloc is ~100 us; the host-pointer entry points
 // are called once per image). Thread-safe.

@@ -202,8 +202,13 @@ __device__ __forceinline__ void idct8(const int in[8], int out[8])
     const int z1 = (z2 + z3) * FIX_0_541196100;
     const int tmp2 = z1 + z3 * (-FIX_1_847759065);
     const int tmp3 = z1 + z2 * FIX_0_765366865;
-    const int tmp0 = (int)((unsigned)(in[0] + in[4]) << CONST_BITS);
-    const int tmp1 = (int)((unsigned)(in[0] - in[4]) << CONST_BITS);
+    // The descale rounding term (and the +128 level shift of the final pass) is added to the even part once instead of
+    // to each of the eight outputs: int32 addition is associative modulo 2^32, so every output is the same integer as
+    // DESCALE / DESCALE_ZEROSHIFT of the reference (jpegload.d:137-145).
+    constexpr int RND = FINAL ? (128 << (CONST_BITS + PASS1_BITS + 3)) + (1 << (CONST_BITS + PASS1_BITS + 2)) : (1 << (CONST_BITS - PASS1_BITS - 1));
+    constexpr int SH = FINAL ? CONST_BITS + PASS1_BITS + 3 : CONST_BITS - PASS1_BITS;
+    const int tmp0 = (int)((unsigned)(in[0] + in[4]) * (1u << CONST_BITS) + (unsigned)RND);     // unsigned: wraps like the reference's int
+    const int tmp1 = (int)((unsigned)(in[0] - in[4]) * (1u << CONST_BITS) + (unsigned)RND);
     const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     const int atmp0 = in[7], atmp1 = in[5], atmp2 = in[3], atmp3 = in[1];
     const int bz1 = atmp0 + atmp3, bz2 = atmp1 + atmp2, bz3 = atmp0 + atmp2, bz4 = atmp1 + atmp3;
@@ -218,10 +223,7 @@ __device__ __forceinline__ void idct8(const int in[8], int out[8])
     const int btmp3 = atmp3 * FIX_1_501321110 + az1 + az4;
     const int s[8] = {tmp10 + btmp3, tmp11 + btmp2, tmp12 + btmp1, tmp13 + btmp0, tmp13 - btmp0, tmp12 - btmp1, tmp11 - btmp2, tmp10 - btmp3};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (FINAL) out[i] = clamp255((s[i] + (128 << (CONST_BITS + PASS1_BITS + 3)) + (1 << (CONST_BITS + PASS1_BITS + 2))) >> (CONST_BITS + PASS1_BITS + 3));
-        else out[i] = (s[i] + (1 << (CONST_BITS - PASS1_BITS - 1))) >> (CONST_BITS - PASS1_BITS);
-    }
+    for (int i = 0; i < 8; ++i) out[i] = FINAL ? clamp255(s[i] >> SH) : (s[i] >> SH);
 }
 
 // Full 8x8 IDCT of a block held as blk[row*8+col] (NR rows x NC columns may be non-zero) -> 64 bytes.
@@ -426,7 +428,7 @@ __device__ __forceinline__ void ycc_to_rgb(int Y, int cb, int cr, int& r, int& g
     b = clamp255(Y + ((F177200 * cb + (32768 - 128 * F177200)) >> 16));
 }
 
-__global__ void __launch_bounds__(IC_THREADS)
+__global__ void __launch_bounds__(IC_THREADS, 4)
 jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __restrict__ cta_base, int nimages,
                         const int* __restrict__ status)
 {

@@ -667,9 +667,16 @@ void launch_unfilter(const UnfilterJob* d_jobs, int njobs, int* d_status, const 
     if (njobs <= 0) return;
     if (rowpar_threads < 32) rowpar_threads = 32;
     if (rowpar_threads > RP_MAX_WARPS * 32) rowpar_threads = RP_MAX_WARPS * 32;
-    static bool attr_set = false;
+    // function attributes are per device: one flag per device, set once each (a process may switch devices)
+    static std::atomic<unsigned long long> attr_mask{0};
     const int smem = (int)sizeof(U4Smem) * U4_NW;
-    if (!attr_set) { cudaFuncSetAttribute(unfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    const int dev = device_index();
+    const unsigned long long bit = dev >= 0 && dev < 64 ? 1ull << dev : 0;
+    if (!bit || !(attr_mask.load(std::memory_order_acquire) & bit)) {
+        if (cudaFuncSetAttribute(unfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess)
+            attr_mask.fetch_or(bit, std::memory_order_release);
+        else cudaGetLastError();
+    }
     unfilter_rowpar_kernel<<<njobs, rowpar_threads, 0, st>>>(d_jobs, njobs, d_inf);
     unfilter_kernel<false><<<njobs, U4_NW * 32, smem, st>>>(d_jobs, njobs, d_status, d_inf, rowpar_threads / 32);
     count_launch(2);

@@ -100,6 +100,17 @@ int                     gb200_batch_download(const gb200_batch* b, uint8_t* dst_
  * [1] LZ4, [2] opcode decode. */
 void                    gb200_batch_timing(const gb200_batch* b, float* phase_ms8, double* host_parse_ms);
 
+/* Host-to-host batched decode with the transfers overlapped: files[i]/lens[i] in host memory, image i delivered to
+ * dst_host + i*dst_stride (gapless rows; dst_host should be pinned -- gb200_host_alloc -- or the copies are staged by
+ * the driver). The batch is cut into sub-batches (sub_batch images each, 0 = automatic); the pixels of one sub-batch
+ * travel back while the next one is uploaded and decoded. format: GB200_FORMAT_JPEG (arg = req_comps, -1 keep),
+ * GB200_FORMAT_PNG (arg = req_comp, want16 as in gb200_png_decode_batch), GB200_FORMAT_QOIX (arg = LoadFlags).
+ * descs[i] is filled like gb200_batch_images() except that `pixels` is the HOST address of the image (NULL = failed; an
+ * image larger than dst_stride fails). Synchronous, thread-safe. This is the batch form of the reference's codec
+ * calls -- bytes in, pixels out (plugins/png.d:108, jpeg.d:62, qoix.d:116). Returns 1 / 0. */
+int gb200_decode_batch_host(int format, int n, const uint8_t* const* files, const size_t* lens, int arg, int want16,
+                            uint8_t* dst_host, size_t dst_stride, gb200_image_desc* descs, int sub_batch);
+
 /* ---- PNG: source/gamut/codecs/stbdec.d (stb_image PNG path) + miniz inflate ---- */
 /* stbi__png_is16 (stbdec.d:2090-2110): 1 if the file stores 16-bit samples. Host-only header scan. */
 int gb200_png_is16(const uint8_t* data, size_t len);
@@ -157,7 +168,8 @@ typedef struct gb200_qoix_desc {        /* qoi_desc, qoi2avg.d:276-287 */
 } gb200_qoix_desc;
 /* qoix_lz4_decode (plugins/qoix.d:350-473): container + optional LZ4 + sub-codec dispatch. `flags` are
  * LoadFlags (only validated, as in the reference); *decodedType receives the stream's own PixelType.
- * Built in this round: QOI-Plane10 (10-bit L/LA, version 2) with and without LZ4. */
+ * All four sub-codecs are built: QOI-Plane10 (10-bit L/LA), QOI-10b (10-bit RGB/RGBA), QOI-Plane (8-bit L/LA) and
+ * QOI2AVG (8-bit RGB/RGBA), each with and without the LZ4 wrapper. */
 uint8_t* gb200_qoix_decode(const uint8_t* data, int size, gb200_qoix_desc* desc, int flags, int* decodedType);
 gb200_batch* gb200_qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int flags, void* stream);

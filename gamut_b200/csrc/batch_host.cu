@@ -29,10 +29,11 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
         gb::set_error("gb200_decode_batch_host: format %d has no batched decoder", format); return 0;
     }
     if (sub_batch <= 0) {
-        // enough sub-batches for the overlap to matter, each large enough to fill the GPU
-        sub_batch = n / 8;
-        if (sub_batch < 8) sub_batch = 8;
-        if (sub_batch > 64) sub_batch = 64;
+        // JPEG decode time scales with the number of images, so many small sub-batches overlap well. The PNG and QOIX
+        // pipelines have per-stream serial stages (LZ77 resolve, chain walks) whose duration hardly depends on how
+        // many streams run side by side: cutting those batches only adds latency, so they stay whole up to 1024 images.
+        if (format == GB200_FORMAT_JPEG) { sub_batch = n / 8; if (sub_batch < 8) sub_batch = 8; if (sub_batch > 64) sub_batch = 64; }
+        else sub_batch = 1024;
     }
     cudaStream_t s_decode = gb::thread_stream(0), s_copy = gb::thread_stream(1);
     if (!s_decode || !s_copy) return 0;

@@ -183,4 +183,305 @@ __device__ inline void lz_resolve_stream(uint8_t* out, uint32_t n, const uint32_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Chunked resolver (round 2). The stream is walked in 4 KB chunks that live in shared memory while their matches are
+// resolved: the chunk (literals in place, match records parked in their holes) is loaded with coalesced vectors, the
+// matches that start in it are taken 32 at a time, one per lane, and the chunk is written back once. Inside a batch a
+// match may copy as soon as its source ends before the first destination that is still open (everything before that
+// point is final): independent matches -- the common case on photographic data, where distances are spread over the
+// whole window -- all copy in the first round, chains of dependent matches take one round per link, with the data in
+// shared memory instead of a DRAM round trip per link. Sources before the chunk are read from the output buffer
+// (final: earlier chunks were written back by this same warp). Matches longer than 32 bytes are copied by the whole
+// warp (x % dist: every byte comes from the dist bytes before the destination).
+constexpr uint32_t LZC_BYTES = 4096, LZC_EXTRA = 320, LZC_SPAN = LZC_BYTES + LZC_EXTRA, LZC_BUF = LZC_SPAN + 16;
+
+template <int FMT>
+__device__ inline void lz_resolve_stream_chunked(uint8_t* out, uint32_t n, const uint32_t* bm, int lane, uint8_t* buf0 /* LZC_BUF bytes, 16-aligned */)
+{
+    const uint32_t nw = (n + 31) >> 5;
+    for (uint32_t c0 = 0; c0 < n; c0 += LZC_BYTES) {
+        const uint32_t cend = min(c0 + LZC_SPAN, n);                // bytes of the stream held in the buffer: [c0, cend)
+        // the buffer starts at the 16-byte boundary at or below out + c0, so that global accesses are aligned vectors
+        // whatever the alignment of `out`; the up to 15 bytes before c0 are final bytes of the previous chunk (or, for
+        // c0 = 0, bytes of the allocation before `out`: device allocations are 256-byte aligned)
+        const uint32_t mis = (uint32_t)((uintptr_t)(out + c0) & 15);
+        uint8_t* const buf = buf0 + mis;                             // buf[x - c0] for stream position x >= c0 - mis
+        uint8_t* const gbase = out + c0 - mis;                       // 16-byte aligned
+        const uint32_t span = cend - c0 + mis;
+        // ---- bitmap window of the chunk: 128 words, 4 per lane
+        uint32_t w[4];
+        {
+            const uint32_t i0 = (c0 >> 5) + lane * 4;
+            const uint4 v = i0 < nw ? *(const uint4*)(bm + i0) : make_uint4(0, 0, 0, 0);
+            w[0] = i0 < nw ? v.x : 0; w[1] = i0 + 1 < nw ? v.y : 0; w[2] = i0 + 2 < nw ? v.z : 0; w[3] = i0 + 3 < nw ? v.w : 0;
+        }
+        uint32_t incl = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;                                   // nothing starts here: the chunk is final as it stands
+        // ---- load
+        for (uint32_t i = lane * 16; i < span; i += 512) *(uint4*)(buf0 + i) = __ldcg((const uint4*)(gbase + i));   // reads <= 15 bytes past n: slack
+        __syncwarp();
+        for (uint32_t m0 = 0; m0 < total; m0 += 32) {
+            const uint32_t m = m0 + lane;
+            const bool valid = m < total;
+            // locate match m of the window (same search as lzr_locate) and read its record from the buffer
+            uint32_t lo = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
+                if (v <= m) lo += step;
+            }
+            uint32_t excl = __shfl_sync(0xffffffffu, incl, (int)((lo + 31) & 31));
+            if (lo == 0) excl = 0;
+            const uint32_t x0 = __shfl_sync(0xffffffffu, w[0], (int)lo), x1 = __shfl_sync(0xffffffffu, w[1], (int)lo);
+            const uint32_t x2 = __shfl_sync(0xffffffffu, w[2], (int)lo), x3 = __shfl_sync(0xffffffffu, w[3], (int)lo);
+            uint32_t dst = 0xffffffffu, len = 0, dist = 1;
+            if (valid) {
+                uint32_t r = m - excl, k = 0, x = x0;
+                const uint32_t p0 = __popc(x0), p1 = __popc(x1), p2 = __popc(x2);
+                if (r >= p0) { r -= p0; k = 1; x = x1; if (r >= p1) { r -= p1; k = 2; x = x2; if (r >= p2) { r -= p2; k = 3; x = x3; } } }
+                const uint32_t bit = __fns(x, 0, (int)(r + 1));
+                dst = c0 + (lo * 4 + k) * 32 + bit;
+                const uint8_t* rec = buf + (dst - c0);
+                if (FMT == LZR_DEFLATE) { len = (uint32_t)rec[0] + 3; dist = ((uint32_t)rec[1] | ((uint32_t)rec[2] << 8)) + 1; }
+                else { len = (uint32_t)rec[0] | ((uint32_t)rec[1] << 8); dist = (uint32_t)rec[2] | ((uint32_t)rec[3] << 8); }
+            }
+            // a record that would read before the stream or write past it cannot come from an accepted stream: skip it
+            bool done = !valid || dist == 0 || dist > dst || dst + len > n;
+            __syncwarp();
+            for (;;) {
+                const uint32_t F = __reduce_min_sync(0xffffffffu, done ? 0xffffffffu : dst);
+                if (F == 0xffffffffu) break;
+                const int fl = __ffs(__ballot_sync(0xffffffffu, !done && dst == F)) - 1;
+                const uint32_t flen = __shfl_sync(0xffffffffu, len, fl);
+                if (flen > 32) {
+                    // the first open match is long: the whole warp copies it
+                    const uint32_t d = F, di = __shfl_sync(0xffffffffu, dist, fl), s = d - di;
+                    const bool ov = di < flen;
+                    if (d + flen <= c0 + LZC_SPAN) {
+                        for (uint32_t x = lane; x < flen; x += 32) {
+                            const uint32_t a = s + (ov ? x % di : x);
+                            buf[d - c0 + x] = a >= c0 ? buf[a - c0] : __ldcg(out + a);
+                        }
+                    } else {
+                        // longer than the buffer's slack (LZ4 only): through the output buffer. Everything resolved so
+                        // far goes back first, the part of the destination that the buffer covers is reloaded after.
+                        __syncwarp();
+                        for (uint32_t i = lane; i < cend - c0; i += 32) out[c0 + i] = buf[i];
+                        __threadfence_block();
+                        __syncwarp();
+                        for (uint32_t c = 0; c < flen; c += 256) {
+                            uint8_t t[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { const uint32_t x = c + (uint32_t)q * 32 + lane; if (x < flen) t[q] = __ldcg(out + s + (ov ? x % di : x)); }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { const uint32_t x = c + (uint32_t)q * 32 + lane; if (x < flen) out[d + x] = t[q]; }
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        for (uint32_t i = d - c0 + lane; i < cend - c0; i += 32) buf[i] = __ldcg(out + c0 + i);
+                    }
+                    if (lane == fl) done = true;
+                    __syncwarp();
+                    continue;
+                }
+                // short matches whose source ends before the first open destination copy now, one per lane
+                const uint32_t s = dst - dist;
+                const bool ready = !done && len <= 32 && (s + min(len, dist) <= F || dst == F);
+                if (ready) {
+                    uint8_t* d8 = buf + (dst - c0);
+                    if (s + len <= c0) {
+                        // source entirely before the chunk: independent loads from the output buffer
+                        uint8_t t[32];
+#pragma unroll
+                        for (uint32_t k = 0; k < 32; ++k) if (k < len) t[k] = __ldcg(out + s + k);
+#pragma unroll
+                        for (uint32_t k = 0; k < 32; ++k) if (k < len) d8[k] = t[k];
+                    } else {
+                        // byte by byte in stream order (an overlapping copy reads what it has just written)
+                        for (uint32_t k = 0; k < len; ++k) { const uint32_t a = s + k; d8[k] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+                    }
+                    done = true;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- write back [c0, cend): resolved bytes, untouched literals, and the still-parked records of the next chunk
+        __syncwarp();
+        {
+            const uint32_t nfull = span & ~15u;
+            for (uint32_t i = lane * 16; i < nfull; i += 512) *(uint4*)(gbase + i) = *(const uint4*)(buf0 + i);
+            if (nfull + lane < span) gbase[nfull + lane] = buf0[nfull + lane];       // at most 15 tail bytes, never past n
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-wide resolver: one thread per match, exact dependencies. Used where a batch has FEW streams (QOIX: one LZ4 block
+// per image, 256 images per GPU), so that a stream gets 16 warps instead of one.
+// The chunk sits in shared memory with a finality bit per byte (literals final, match destinations open); the matches
+// are taken LZB_THREADS at a time, one per thread; every open match checks the bits of its source range and copies in
+// the round in which they are all set, then sets its own. The number of rounds is the depth of the longest dependency
+// chain inside the batch, each round costs one barrier; the copies of a round are independent by construction.
+// Measured (round 2): LZ4 of 256 x 2048^2 QOIX images 16.4 ms (round-1 resolver) -> 4.3 ms. PNG, 1024 x 1080p with
+// 1.1 M matches per image (mean length 6.4, three quarters of the sources more than 4 KB back): round-1 resolver 249
+// ms, lz_resolve_stream_chunked (one warp per stream, all streams resident) 112 ms, this one 135-139 ms (it executes
+// ~20 k warp instructions per chunk -- every warp runs every round -- and becomes throughput-bound once all 1024
+// streams are resident), warps spinning on the bits without barriers 189 ms, a lane-owned-region variant with a
+// 16 KB window in shared memory 300 ms (a lone warp issues one dependent instruction every 6-10 cycles). PNG
+// therefore uses lz_resolve_stream_chunked.
+constexpr int LZB_THREADS = 512;
+constexpr uint32_t LZB_FINW = (LZC_SPAN + 31) / 32 + 1;
+
+struct LzbShared {
+    __align__(16) uint8_t buf[LZC_BUF];
+    uint32_t start[128];                    // match-start bits of the chunk
+    uint32_t pref[129];                     // exclusive prefix of their popcounts
+    uint32_t wsum[4];
+    uint32_t fin[LZB_FINW];                 // finality bits, relative to c0
+};
+
+__device__ __forceinline__ bool lzb_range_final(const volatile uint32_t* fin, uint32_t a, uint32_t b)      // bits [a, b), a < b
+{
+    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (uint32_t w = w0; w <= w1; ++w) {
+        uint32_t mask = 0xffffffffu;
+        if (w == w0) mask &= 0xffffffffu << (a & 31);
+        if (w == w1) mask &= 0xffffffffu >> (31 - ((b - 1) & 31));
+        if ((fin[w] & mask) != mask) return false;
+    }
+    return true;
+}
+template <bool SET>
+__device__ __forceinline__ void lzb_range_mark(uint32_t* fin, uint32_t a, uint32_t b)
+{
+    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (uint32_t w = w0; w <= w1; ++w) {
+        uint32_t mask = 0xffffffffu;
+        if (w == w0) mask &= 0xffffffffu << (a & 31);
+        if (w == w1) mask &= 0xffffffffu >> (31 - ((b - 1) & 31));
+        if (SET) atomicOr(fin + w, mask); else atomicAnd(fin + w, ~mask);
+    }
+}
+
+// All LZB_THREADS threads of one CTA. `bm` must be 16-byte aligned and readable up to the next multiple of 128 words.
+template <int FMT>
+__device__ inline void lz_resolve_stream_cta(uint8_t* out, uint32_t n, const uint32_t* bm, LzbShared& S)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t nw = (n + 31) >> 5;
+    for (uint32_t c0 = 0; c0 < n; c0 += LZC_BYTES) {
+        const uint32_t cend = min(c0 + LZC_SPAN, n);
+        const uint32_t mis = (uint32_t)((uintptr_t)(out + c0) & 15);
+        uint8_t* const buf = S.buf + mis;                            // buf[x - c0] for stream position x >= c0 - mis
+        uint8_t* const gbase = out + c0 - mis;                       // 16-byte aligned
+        const uint32_t span = cend - c0 + mis;
+        // ---- match starts of the chunk and the prefix of their counts
+        __syncthreads();
+        if (tid < 128) {
+            const uint32_t i = (c0 >> 5) + tid;
+            uint32_t w = i < nw ? bm[i] : 0;
+            const uint32_t lim = n - min(n, c0 + (uint32_t)tid * 32);             // bits at or beyond n are not matches
+            if (lim < 32) w &= lim ? (0xffffffffu >> (32 - lim)) : 0u;
+            S.start[tid] = w;
+            uint32_t inc = __popc(w);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+            if (lane == 31) S.wsum[tid >> 5] = inc;
+            S.pref[tid + 1] = inc;                                    // warp-local inclusive; the warp bases are added below
+        }
+        __syncthreads();
+        if (tid < 128) {
+            uint32_t base = 0;
+            for (int w4 = 0; w4 < (tid >> 5); ++w4) base += S.wsum[w4];
+            S.pref[tid + 1] += base;
+            if (tid == 0) S.pref[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t total = S.pref[128];
+        if (total == 0) continue;                                     // nothing starts here: the chunk is final as it stands
+        // ---- load the chunk, all bytes final until a match claims them
+        for (uint32_t i = tid * 16; i < span; i += LZB_THREADS * 16) *(uint4*)(S.buf + i) = __ldcg((const uint4*)(gbase + i));
+        for (uint32_t i = tid; i < LZB_FINW; i += LZB_THREADS) S.fin[i] = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t m0 = 0; m0 < total; m0 += LZB_THREADS) {
+            const uint32_t m = m0 + tid;
+            bool open = false;
+            uint32_t dst = 0, len = 0, dist = 1;
+            if (m < total) {
+                // word that holds set bit number m: largest wi with pref[wi] <= m
+                uint32_t wi = 0;
+#pragma unroll
+                for (int step = 64; step; step >>= 1) if (S.pref[wi + step] <= m) wi += step;
+                const uint32_t bit = __fns(S.start[wi], 0, (int)(m - S.pref[wi] + 1));
+                dst = c0 + wi * 32 + bit;
+                const uint8_t* rec = buf + (dst - c0);
+                if (FMT == LZR_DEFLATE) { len = (uint32_t)rec[0] + 3; dist = ((uint32_t)rec[1] | ((uint32_t)rec[2] << 8)) + 1; }
+                else { len = (uint32_t)rec[0] | ((uint32_t)rec[1] << 8); dist = (uint32_t)rec[2] | ((uint32_t)rec[3] << 8); }
+                // a record that would read before the stream or write past it cannot come from an accepted stream: skip it
+                open = len != 0 && dist != 0 && dist <= dst && dst + len <= n;
+            }
+            if (open) lzb_range_mark<false>(S.fin, dst - c0, min(dst + len, c0 + LZC_SPAN) - c0);
+            __syncthreads();
+            const uint32_t s = dst - dist;
+            const uint32_t src_end = s + min(len, dist);
+            const uint32_t need_a = max(s, c0) - c0, need_b = src_end > c0 ? src_end - c0 : 0;   // source bits to check
+            for (;;) {
+                const bool ready = open && (need_b <= need_a || lzb_range_final(S.fin, need_a, need_b));
+                if (ready && len <= 32) {
+                    uint8_t* d8 = buf + (dst - c0);
+                    if (dist >= len) {
+                        // no self-overlap: independent loads (buffer, or output before the chunk), 8 at a time
+                        for (uint32_t k0 = 0; k0 < len; k0 += 8) {
+                            uint8_t t[8];
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < len) { const uint32_t a = s + k0 + k; t[k] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < len) d8[k0 + k] = t[k];
+                        }
+                    } else {
+                        // overlapping copy: byte k equals source byte k mod dist
+                        uint32_t j = 0;
+                        for (uint32_t k = 0; k < len; ++k) { const uint32_t a = s + j; d8[k] = a >= c0 ? buf[a - c0] : __ldcg(out + a); j = j + 1 == dist ? 0 : j + 1; }
+                    }
+                }
+                // long matches: the warp copies them one after the other (x % dist: every byte comes from the dist bytes
+                // before the destination). The part of a destination beyond the buffer (LZ4 only) goes straight to the
+                // output: no later match of this chunk can start there, and later chunks load it as final bytes.
+                uint32_t lm = __ballot_sync(0xffffffffu, ready && len > 32);
+                while (lm) {
+                    const int l = __ffs(lm) - 1; lm &= lm - 1;
+                    const uint32_t d = __shfl_sync(0xffffffffu, dst, l), ln = __shfl_sync(0xffffffffu, len, l);
+                    const uint32_t di = __shfl_sync(0xffffffffu, dist, l), ss = d - di;
+                    const bool ov = di < ln;
+                    for (uint32_t x = lane; x < ln; x += 32) {
+                        const uint32_t a = ss + (ov ? x % di : x);
+                        const uint8_t v = a >= c0 ? buf[a - c0] : __ldcg(out + a);
+                        if (d + x < c0 + LZC_SPAN) buf[d - c0 + x] = v; else out[d + x] = v;
+                    }
+                    __syncwarp();
+                }
+                if (ready) {
+                    __threadfence_block();                            // the bytes are visible before the bits that announce them
+                    lzb_range_mark<true>(S.fin, dst - c0, min(dst + len, c0 + LZC_SPAN) - c0);
+                    open = false;
+                }
+                if (!__syncthreads_or(open ? 1 : 0)) break;
+            }
+        }
+        // ---- write back [c0, cend): resolved bytes, untouched literals, and the still-parked records of the next chunk
+        {
+            const uint32_t nfull = span & ~15u;
+            for (uint32_t i = tid * 16; i < nfull; i += LZB_THREADS * 16) *(uint4*)(gbase + i) = *(const uint4*)(S.buf + i);
+            if (tid < 16 && nfull + tid < span) gbase[nfull + tid] = S.buf[nfull + tid];       // at most 15 tail bytes, never past n
+        }
+        __threadfence_block();
+    }
+    __syncthreads();
+}
+
 } // namespace gb

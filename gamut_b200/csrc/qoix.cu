@@ -415,14 +415,14 @@ lz4_parse_kernel(const Lz4Job* __restrict__ jobs, int njobs, int* status, const 
     if (!lz4_write_walk(J, ring_all[wslot], lane, 0, 0, 0xffffffffu) && lane == 0) status[J.image] = 0;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(gb::LZB_THREADS, 2)
 lz4_resolve_kernel(const Lz4Job* __restrict__ jobs, int njobs, const int* status)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= njobs) return;
-    const Lz4Job J = jobs[warp];
+    __shared__ gb::LzbShared S;
+    if ((int)blockIdx.x >= njobs) return;
+    const Lz4Job J = jobs[blockIdx.x];
     if (!status[J.image]) return;                           // the parse failed: the image fails as a whole
-    gb::lz_resolve_stream<gb::LZR_LZ4>(J.out, J.orig, J.bitmap, lane);
+    gb::lz_resolve_stream_cta<gb::LZR_LZ4>(J.out, J.orig, J.bitmap, S);
 }
 
 #include "qoiplane10.cuh"
@@ -652,7 +652,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
             count_launch(6);
         }
         lz4_parse_kernel<<<g, LZ4_WARPS * 32, 0, st>>>(dj, nj, d_status.as<int>(), d_lzok.as<int>());
-        lz4_resolve_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(dj, nj, d_status.as<int>());
+        lz4_resolve_kernel<<<(unsigned)lz.size(), gb::LZB_THREADS, 0, st>>>(dj, nj, d_status.as<int>());
         count_launch(2);
     }
     cudaEventRecord(ev[2], st);

@@ -94,6 +94,9 @@ extern(C)
     void gb200_device_trim();
     int gb200_sm_count();
     int gb200_batch_download(const(gb200_batch)* b, ubyte* dst_host, size_t stride);
+    int gb200_jpeg_probe(const(ubyte)* data, size_t len);
+    struct gb200_image { void* alloc; size_t alloc_bytes; ubyte* data; int width, height, type, pitch, layout; float pixelAspectRatio, resolutionY; const(char)* error; }
+    int gb200_image_load(const(ubyte)* data, size_t len, int flags, gb200_image* out_);
     int gb200_decode_batch_host(int format, int n, const(ubyte*)* files, const(size_t)* lens, int arg, int want16,
                                 ubyte* dst_host, size_t dst_stride, gb200_image_desc* descs, int sub_batch);
     void gb200_batch_timing(const(gb200_batch)* b, float* phase_ms8, double* host_parse_ms);

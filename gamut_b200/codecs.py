@@ -20,6 +20,12 @@ class ImageDesc(C.Structure):
                 ("status", C.c_int), ("ppmX", C.c_float), ("ppmY", C.c_float), ("pixelAspectRatio", C.c_float)]
 
 
+class LoadedImage(C.Structure):     # gb200_image
+    _fields_ = [("alloc", C.c_void_p), ("alloc_bytes", C.c_size_t), ("data", C.c_void_p), ("width", C.c_int),
+                ("height", C.c_int), ("type", C.c_int), ("pitch", C.c_int), ("layout", C.c_int),
+                ("pixelAspectRatio", C.c_float), ("resolutionY", C.c_float), ("error", C.c_char_p)]
+
+
 class QoiDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint8), ("colorspace", C.c_uint8)]
 
@@ -66,6 +72,8 @@ def _L():
         L.gb200_qoix_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoixDesc), i32, ip]
         L.gb200_qoix_decode_batch.restype = vp
         L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
+        L.gb200_jpeg_probe.argtypes = [C.c_char_p, sz]
+        L.gb200_image_load.argtypes = [C.c_char_p, sz, i32, C.POINTER(LoadedImage)]
         L.gb200_decode_batch_host.argtypes = [i32, i32, C.POINTER(C.c_char_p), C.POINTER(sz), i32, i32, vp, sz,
                                               C.POINTER(ImageDesc), i32]
         _declared = True
@@ -223,6 +231,11 @@ def jpeg_load(data: bytes, req_comps: int = -1) -> Optional[JpegResult]:
     return JpegResult(a.reshape(h.value, w.value, c), w.value, h.value, ac.value, par.value, dpi.value)
 
 
+def jpeg_probe(data: bytes) -> int:
+    """0 decodable here, 1 progressive (SOF2), 2 non-interleaved multi-scan, -1 not a JPEG (gb200_jpeg_probe)."""
+    return int(_L().gb200_jpeg_probe(data, len(data)))
+
+
 def jpeg_decode_batch(files: Sequence[bytes], req_comps: int = -1, files_dev: Optional[Sequence[int]] = None,
                       stream: int = 0) -> Batch:
     n, arr, lens, dev = _batch_args(files, files_dev)
@@ -273,3 +286,11 @@ def decode_batch_host(fmt: int, files: Sequence[bytes], arg: int, want16: int, d
     _lib.check(_L().gb200_decode_batch_host(int(fmt), n, arr, lens, arg, want16, dst_host, dst_stride, descs, sub_batch),
                "decode_batch_host")
     return [descs[i] for i in range(n)]
+
+
+def image_load(data: bytes, flags: int) -> LoadedImage:
+    """gb200_image_load: decode + conversion into the requested PixelType / LayoutConstraints on the GPU, one copy back.
+    The caller owns `alloc` (gb200_free)."""
+    im = LoadedImage()
+    _L().gb200_image_load(data, len(data), int(flags), C.byref(im))
+    return im

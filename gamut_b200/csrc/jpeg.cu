@@ -670,6 +670,7 @@ struct HostHuff { bool valid = false; uint8_t num[17]; uint8_t val[256]; };
 
 struct Parsed {
     bool ok = false;
+    int unsupported = 0;         // 1 progressive (SOF2), 2 non-interleaved multi-scan sequential: valid JPEG, not on this path
     int width = 0, height = 0, comps = 0;
     int h_samp[4] = {0}, v_samp[4] = {0}, quant_sel[4] = {0}, ident[4] = {0};
     HostHuff huff[8];
@@ -682,7 +683,7 @@ struct Parsed {
     int scan_type = 0, mcus_per_row = 0, mcus_per_col = 0, blocks_per_mcu = 0, tiles_per_mcu = 0, mcu_org[10];
 };
 
-float inches_to_meters(float x) { return x * 0.0254f; }
+float inches_to_meters(float x) { return x / 39.37007874f; }      // convertInchesToMeters, types.d:127 (a division there too)
 uint16_t rd16(const uint8_t* p, bool le) { return le ? (uint16_t)(p[0] | (p[1] << 8)) : (uint16_t)((p[0] << 8) | p[1]); }
 uint32_t rd32(const uint8_t* p, bool le) { return le ? ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24))
                                                       : (((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]); }
@@ -772,7 +773,9 @@ int walk_markers(ByteSrc& s, Parsed& P)
                 if (rd16(tiff + 2, le) != 42) return -1;
                 uint32_t off = rd32(tiff + 4, le);
                 double rx = 72, ry = 72; int unit = 2;
+                int ifds = 0;
                 while (off != 0) {
+                    if (++ifds > 64) return -1;          // a next-IFD offset that points back at itself would spin forever (the reference does)
                     if (off > left || (uint64_t)off + 2 > tlen) return -1;
                     const uint8_t* q = tiff + off;
                     uint32_t ne = rd16(q, le); q += 2;
@@ -824,6 +827,7 @@ bool parse_jpeg(const uint8_t* data, size_t len, Parsed& P)
         if (nx != 0xFF) return false;
     }
     int c = walk_markers(s, P);
+    if (c == 0xC2) P.unsupported = 1;
     if (c != 0xC0 && c != 0xC1) return false;      // SOF2 (progressive) and the rest: not on this path
     // read_sof_marker (:1343-1405)
     uint32_t left = s.u16();
@@ -868,7 +872,7 @@ bool parse_jpeg(const uint8_t* data, size_t len, Parsed& P)
     left -= 3;
     while (left) { s.next(); --left; }
     if (s.pos > len) return false;
-    if (P.comps_in_scan != P.comps) return false;  // non-interleaved multi-scan baseline: unsupported
+    if (P.comps_in_scan != P.comps) { P.unsupported = 2; return false; }  // non-interleaved multi-scan baseline: unsupported
     // calc_mcu_block_order (:3038-3090)
     int max_h = P.h_samp[0], max_v = P.v_samp[0];
     if (P.comps == 1) { P.mcus_per_row = (P.width + 7) / 8; P.mcus_per_col = (P.height + 7) / 8; P.blocks_per_mcu = 1; P.mcu_org[0] = P.comp_list[0]; }
@@ -1194,6 +1198,15 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
 
 } // namespace gb
 
+/* 0 = decodable here (baseline / extended sequential, one interleaved scan), 1 = progressive (SOF2), 2 = sequential but
+ * non-interleaved multi-scan, -1 = not a JPEG this parser accepts. Header walk on the host, no GPU work. */
+GB_API int gb200_jpeg_probe(const uint8_t* data, size_t len)
+{
+    Parsed pp;
+    if (data && parse_jpeg(data, len, pp)) return 0;
+    return pp.unsupported ? pp.unsupported : -1;
+}
+
 GB_API gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                             const uint8_t* const* files_dev, int req_comps, void* stream)
 {
@@ -1213,7 +1226,15 @@ GB_API uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, 
     gb200_batch* B = gb::jpeg_decode_batch(1, f, l, nullptr, req_comps, st);
     if (!B) return nullptr;
     const gb200_image_desc& D = B->images[0];
-    if (!D.status) { gb::set_error("JPEG decoding failed"); delete B; return nullptr; }
+    if (!D.status) {
+        // a valid file of a kind this path does not decode is reported as such, so that callers can route it elsewhere
+        Parsed pp;
+        parse_jpeg(data, len, pp);
+        if (pp.unsupported == 1) gb::set_error("unsupported: progressive JPEG (SOF2) -- the GPU path decodes baseline / extended sequential Huffman only");
+        else if (pp.unsupported == 2) gb::set_error("unsupported: non-interleaved multi-scan sequential JPEG -- the GPU path decodes single-scan interleaved files only");
+        else gb::set_error("JPEG decoding failed");
+        delete B; return nullptr;
+    }
     size_t bytes = (size_t)D.pitch * D.height;
     uint8_t* out = (uint8_t*)malloc(bytes ? bytes : 1);
     if (!out) { delete B; return nullptr; }

@@ -749,30 +749,54 @@ GB_API uint8_t* gb200_qoix_decode(const uint8_t* data, int size, gb200_qoix_desc
     return out;
 }
 
+// qoi_decode (qoi.d:448-550) into a one-image device batch (shared by gb200_qoi_decode and gb200_image_load).
+namespace gb {
+gb200_batch* qoi_decode_batch1(const uint8_t* data, int size, int channels, int* file_channels, cudaStream_t st)
+{
+    if (!ensure_device()) return nullptr;
+    if ((channels != 0 && channels != 3 && channels != 4) || !data || size < 14 + 8) return nullptr;
+    const uint32_t magic = be32(data), w = be32(data + 4), h = be32(data + 8);
+    const int fch = data[12], cs = data[13];
+    if (file_channels) *file_channels = fch;
+    if (w == 0 || h == 0 || fch < 3 || fch > 4 || cs > 1 || magic != 0x716F6966u || h >= 400000000u / w) return nullptr;
+    if (channels == 0) channels = fch;
+    const size_t bytes = (size_t)w * h * channels;
+    DevBuf d_in((size_t)size + 16), d_job(sizeof(QoiJob));
+    uint8_t* d_out = (uint8_t*)dev_alloc(bytes ? bytes : 1);
+    if (!d_in.p || !d_out || !d_job.p) { if (d_out) dev_free(d_out); return nullptr; }
+    gb200_batch* B = new gb200_batch;
+    B->stream = st; B->device_allocs.push_back(d_out);
+    B->images.resize(1);
+    gb200_image_desc& D = B->images[0];
+    memset(&D, 0, sizeof(D));
+    QoiJob J{d_in.as<uint8_t>(), (uint32_t)size, d_out, w, h, channels, 0};
+    bool ok = cuda_ok(cudaMemcpyAsync(d_in.p, data, (size_t)size, cudaMemcpyHostToDevice, st), "h2d", __FILE__, __LINE__) &&
+              cuda_ok(cudaMemcpyAsync(d_job.p, &J, sizeof(J), cudaMemcpyHostToDevice, st), "job", __FILE__, __LINE__);
+    if (ok) { qoi_kernel<<<1, 64, 0, st>>>(d_job.as<QoiJob>(), 1); count_launch(); }
+    ok = ok && cuda_ok(cudaGetLastError(), "qoi_kernel", __FILE__, __LINE__) && cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+    if (!ok) { cudaStreamSynchronize(st); delete B; return nullptr; }
+    D.pixels = d_out; D.width = (int)w; D.height = (int)h; D.channels = channels; D.file_channels = fch; D.bits = 8;
+    D.pixel_type = channels == 3 ? GB200_rgb8 : GB200_rgba8; D.pitch = (int)w * channels; D.status = 1;
+    D.ppmX = D.ppmY = D.pixelAspectRatio = -1;
+    return B;
+}
+}
+
 // qoi_decode (qoi.d:448-550). channels: 0 = as stored, 3 or 4.
 GB_API uint8_t* gb200_qoi_decode(const uint8_t* data, int size, gb200_qoi_desc* desc, int channels)
 {
     gb::clear_error();
     if (!gb::ensure_device()) return nullptr;
-    if ((channels != 0 && channels != 3 && channels != 4) || size < 14 + 8) return nullptr;
-    const uint32_t magic = be32(data), w = be32(data + 4), h = be32(data + 8);
-    const int fch = data[12], cs = data[13];
-    if (desc) { desc->width = w; desc->height = h; desc->channels = (uint8_t)fch; desc->colorspace = (uint8_t)cs; }
-    if (w == 0 || h == 0 || fch < 3 || fch > 4 || cs > 1 || magic != 0x716F6966u || h >= 400000000u / w) return nullptr;
-    if (channels == 0) channels = fch;
-    const size_t bytes = (size_t)w * h * channels;
+    if (data && size >= 14 && desc) { desc->width = be32(data + 4); desc->height = be32(data + 8); desc->channels = data[12]; desc->colorspace = data[13]; }
     cudaStream_t st = gb::thread_stream();
-    gb::DevBuf d_in((size_t)size + 16), d_out(bytes), d_job(sizeof(QoiJob));
-    if (!d_in.p || !d_out.p || !d_job.p) return nullptr;
-    QoiJob J{d_in.as<uint8_t>(), (uint32_t)size, d_out.as<uint8_t>(), w, h, channels, 0};
+    gb200_batch* B = gb::qoi_decode_batch1(data, size, channels, nullptr, st);
+    if (!B) return nullptr;
+    const gb200_image_desc& D = B->images[0];
+    const size_t bytes = (size_t)D.pitch * D.height;
     uint8_t* out = (uint8_t*)malloc(bytes ? bytes : 1);
-    if (!out) return nullptr;
-    bool ok = gb::cuda_ok(cudaMemcpyAsync(d_in.p, data, (size_t)size, cudaMemcpyHostToDevice, st), "h2d", __FILE__, __LINE__) &&
-              gb::cuda_ok(cudaMemcpyAsync(d_job.p, &J, sizeof(J), cudaMemcpyHostToDevice, st), "job", __FILE__, __LINE__);
-    if (ok) { qoi_kernel<<<1, 64, 0, st>>>(d_job.as<QoiJob>(), 1); gb::count_launch(); }
-    ok = ok && gb::cuda_ok(cudaGetLastError(), "qoi_kernel", __FILE__, __LINE__) &&
-         gb::cuda_ok(cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) &&
-         gb::cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+    bool ok = out && gb::cuda_ok(cudaMemcpyAsync(out, D.pixels, bytes, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) &&
+              gb::cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+    delete B;
     if (!ok) { free(out); return nullptr; }
     return out;
 }

@@ -186,6 +186,22 @@ def allocatePixelStorage(type_, width, height, constraints, bonusBytes=0):
     return area, off, pitch
 
 
+class _MallocOwner:
+    """Owns a malloc()'d pixel area returned by the C library (Image._allocArea); freed with gb200_free."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                from . import _lib
+                _lib.lib().gb200_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class Image:
     """The fields and the two hot-path methods of gamut.Image (image.d). `_area` is the owned allocation
     (numpy bytes), `_offset` the byte offset of the first scanline inside it, `_pitch` is signed."""
@@ -201,6 +217,7 @@ class Image:
         self._pixelAspectRatio = GAMUT_UNKNOWN_ASPECT_RATIO
         self._resolutionY = GAMUT_UNKNOWN_RESOLUTION
         self._layerCount = 0
+        self._owner = None
         self._error = kStrImageNotInitialized
 
     # -- status (image.d:372-400)
@@ -250,7 +267,29 @@ class Image:
         self._layerCount = 1
 
     def loadFromMemory(self, data: bytes, flags: int = 0) -> bool:
-        """image.d:886-901 + loadFromStreamInternal (:1751-1772)."""
+        """image.d:886-901 + loadFromStreamInternal (:1751-1772). One call into the CUDA library: gb200_image_load
+        decodes, converts into the PixelType / LayoutConstraints that `flags` ask for and copies the finished image
+        back once; the allocation it returns is adopted like the plugins adopt the codec's buffer."""
+        self.__init__()
+        self._error = None
+        r = codecs.image_load(bytes(data), flags)
+        if r.error is not None or not r.alloc:
+            self.error(r.error.decode() if r.error else kStrImageDecodingFailed)
+            return False
+        import ctypes as C
+        area = np.ctypeslib.as_array((C.c_uint8 * r.alloc_bytes).from_address(r.alloc))
+        self._owner = _MallocOwner(r.alloc)         # frees the area when the image lets go of it
+        self._area, self._offset = area, r.data - r.alloc
+        self._width, self._height, self._pitch = r.width, r.height, r.pitch
+        self._type, self._layoutConstraints = PixelType(r.type), r.layout
+        self._pixelAspectRatio, self._resolutionY = r.pixelAspectRatio, r.resolutionY
+        self._layerCount = 1
+        return True
+
+    def loadFromMemoryStaged(self, data: bytes, flags: int = 0) -> bool:
+        """The same load composed from the codec-level entry points the way the reference's plugins do it (decode to a
+        gapless buffer, then convertTo): kept as the executable description of the plugin epilogues and to cross-check
+        gb200_image_load in the tests."""
         self.__init__()
         self._error = None
         fif = self.identifyFormatFromMemory(data)
@@ -293,7 +332,8 @@ class Image:
             req = -1
         r = codecs.jpeg_load(data, req)
         if r is None:
-            return self.error(kStrImageDecodingFailed)
+            # a valid progressive / multi-scan file is a kind this build cannot decode, not a broken one
+            return self.error(kStrImageFormatNoLoadSupport if codecs.jpeg_probe(data) > 0 else kStrImageDecodingFailed)
         if r.actual_comps not in (1, 3, 4):
             return self.error(kStrImageWrongComponents)
         if not imageIsValidSize(1, r.width, r.height):

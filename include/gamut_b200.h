@@ -153,6 +153,12 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
                          int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
+/* Classifies a file without decoding it (host-only marker walk): 0 = decodable by this path (baseline / extended
+ * sequential Huffman, one interleaved scan), 1 = progressive (SOF2; the reference decodes these, jpegload.d:3299-3683
+ * -- SURVEY 8(f3), not built), 2 = sequential but non-interleaved multi-scan, -1 = not a valid JPEG. gb200_jpeg_load
+ * sets gb200_last_error() to a message starting with "unsupported:" for 1 and 2, so that callers can route those files
+ * to another decoder. */
+int gb200_jpeg_probe(const uint8_t* data, size_t len);
 
 /* ---- QOI: source/gamut/codecs/qoi.d ---- */
 typedef struct gb200_qoi_desc { uint32_t width, height; uint8_t channels, colorspace; } gb200_qoi_desc;  /* qoi.d:215-222 minus pitchBytes */
@@ -173,6 +179,29 @@ typedef struct gb200_qoix_desc {        /* qoi_desc, qoi2avg.d:276-287 */
 uint8_t* gb200_qoix_decode(const uint8_t* data, int size, gb200_qoix_desc* desc, int flags, int* decodedType);
 gb200_batch* gb200_qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int flags, void* stream);
+
+/* ---- Image.loadFromMemory in one call (image.d:886-901 -> loadPNG/JPEG/QOI/QOIX -> convertTo) ----
+ * Replaces the body of the four LoadImageProc plugins (plugin.d:30; plugins/png.d:44, jpeg.d:42, qoi.d:48, qoix.d:64)
+ * INCLUDING their closing image.convertTo(applyLoadFlags(type, flags), cast(LayoutConstraints) flags): the file is
+ * decoded on the GPU, converted on the GPU straight into the PixelType and LayoutConstraints that `flags` ask for
+ * (pitch, scanline alignment, border, trailing pixels, vertical flip as allocatePixelStorage lays them out,
+ * internals/types.d:355-540) and copied to the host once -- the fusion the reference's PERF note at plugins/qoix.d:134
+ * asks for. `flags` = LoadFlags | LayoutConstraints exactly as passed to Image.loadFromMemory.
+ * On success (1): alloc = malloc()'d area of alloc_bytes to adopt as Image._allocArea (free with gb200_free), data = first scanline
+ * (Image._data), pitch signed (negative when flipped), type = gb200_pixel_type, layout = flags & 0xFFFF, plus the
+ * resolution fields. On failure (0): error = the static string the reference would set with image.error(kStr...). */
+typedef struct gb200_image {
+    void*    alloc;
+    size_t   alloc_bytes;
+    uint8_t* data;
+    int      width, height;
+    int      type;
+    int      pitch;
+    int      layout;
+    float    pixelAspectRatio, resolutionY;
+    const char* error;
+} gb200_image;
+int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_image* out);
 
 #ifdef __cplusplus
 }

@@ -434,7 +434,7 @@ static int next_marker(jd* d)
     } while (c == 0);
     return (int)c;
 }
-static float inches_to_meters_x(float x) { return x * 0.0254f; }   /* convertInchesToMeters (types.d) */
+static float inches_to_meters_x(float x) { return x / 39.37007874f; }   /* convertInchesToMeters, types.d:127 */
 
 static uint16_t rd16(const uint8_t* p, int le) { return le ? (uint16_t)(p[0] | (p[1] << 8)) : (uint16_t)((p[0] << 8) | p[1]); }
 static uint32_t rd32(const uint8_t* p, int le) { return le ? ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24))

@@ -204,6 +204,25 @@ def test_convert_after_load_chain(Image, pyimage):
             same(im, o, (name, t.name, lay))
 
 
+def test_single_pass_load_equals_staged_load(Image):
+    """gb200_image_load (decode + convert on the GPU into the final layout, one copy back) against the same load
+    composed from the codec entry points + convertTo, the way the reference's plugins do it."""
+    files = _files()
+    for name, data in files.items():
+        for f in FLAG_SETS[:12]:
+            for lay in (0, LAYOUT_VERT_FLIPPED | LAYOUT_BORDER_1, LAYOUT_SCANLINE_ALIGNED_32 | LAYOUT_TRAILING_3):
+                a, b = Image(), Image()
+                a.loadFromMemory(data, f | lay)
+                b.loadFromMemoryStaged(data, f | lay)
+                assert a.isError() == b.isError() and a.errorMessage() == b.errorMessage(), (name, hex(f), lay)
+                if a.isError():
+                    continue
+                assert (a.type(), a.width(), a.height(), a.pitchInBytes(), a.layoutConstraints()) == \
+                       (b.type(), b.width(), b.height(), b.pitchInBytes(), b.layoutConstraints()), (name, hex(f), lay)
+                for y in range(a.height()):
+                    assert np.array_equal(a.scanline(y), b.scanline(y)), (name, hex(f), lay, y)
+
+
 def test_unidentified_and_garbage(Image, pyimage):
     for data in (b"", b"abc", b"\x89PNG\r\n\x1a\n", b"qoif", b"qoix" + b"\0" * 30, b"\xff\xd8\xff"):
         im, o = load_both(Image, pyimage, data, 0)

@@ -111,6 +111,26 @@ def test_failures(codecs, oracle):
     check(codecs, oracle, b"\xff\xd8\xff\xd9")
 
 
+def test_progressive_is_reported_as_unsupported(codecs, gb):
+    """A valid progressive (SOF2) file is not on this path: the load fails with a message that starts
+    with "unsupported:", gb200_jpeg_probe classifies it, and Image.loadFromMemory reports "Cannot decode this image
+    format in this build" instead of "Image decoding failed" -- callers can route such files elsewhere."""
+    from gamut_b200 import _lib
+    from gamut_b200.image import Image, kStrImageFormatNoLoadSupport, kStrImageDecodingFailed
+    img = photo(40, 40, 3, 2)
+    b = io.BytesIO()
+    PILImage.fromarray(img).save(b, "JPEG", progressive=True)
+    prog = b.getvalue()
+    assert codecs.jpeg_probe(prog) == 1 and codecs.jpeg_probe(encode(img, 90, 2)) == 0 and codecs.jpeg_probe(b"nope") == -1
+    assert codecs.jpeg_load(prog, -1) is None
+    assert _lib.last_error().startswith("unsupported: progressive JPEG")
+    im = Image()
+    im.loadFromMemory(prog)
+    assert im.isError() and im.errorMessage() == kStrImageFormatNoLoadSupport
+    im.loadFromMemory(b"\xff\xd8\xff\xd9")
+    assert im.isError() and im.errorMessage() == kStrImageDecodingFailed
+
+
 def test_batch_mixed(codecs, oracle):
     files = [encode(photo(64, 48, 3, 1), 90, 2), b"nope", encode(photo(33, 65, 1, 2), 70),
              encode(photo(80, 80, 3, 3), 95, 0, restart_rows=1), encode(photo(50, 70, 3, 4), 60, 1)]

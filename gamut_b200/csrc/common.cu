@@ -122,19 +122,26 @@ static void* pool_alloc(Pool& P, size_t bytes, bool pinned)
     P.live_[p] = {dev, b};
     return p;
 }
-static void pool_free(Pool& P, void* p)
+// Cached (free) bytes are capped: beyond the cap a block goes back to the driver instead of the cache. The caps are
+// generous for the batch workloads (their scratch is reused call after call) and bound what an idle process holds.
+static const size_t DEV_CACHE_CAP = (size_t)64 << 30, PINNED_CACHE_CAP = (size_t)16 << 30;
+static void pool_free(Pool& P, void* p, bool pinned)
 {
     if (!p) return;
-    std::lock_guard<std::mutex> g(P.m);
-    auto it = P.live_.find(p);
-    if (it == P.live_.end()) return;
-    P.free_.insert({it->second, p});
-    P.cached_bytes += it->second.second;
-    P.live_.erase(it);
+    bool release = false;
+    {
+        std::lock_guard<std::mutex> g(P.m);
+        auto it = P.live_.find(p);
+        if (it == P.live_.end()) return;
+        if (P.cached_bytes + it->second.second > (pinned ? PINNED_CACHE_CAP : DEV_CACHE_CAP)) release = true;
+        else { P.free_.insert({it->second, p}); P.cached_bytes += it->second.second; }
+        P.live_.erase(it);
+    }
+    if (release) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
 }
 
 void* dev_alloc(size_t bytes) { return pool_alloc(dpool(), bytes, false); }
-void  dev_free(void* p) { pool_free(dpool(), p); }
+void  dev_free(void* p) { pool_free(dpool(), p, false); }
 void  dev_trim()
 {
     Pool& P = dpool();
@@ -148,7 +155,7 @@ void  dev_trim()
     for (void* p : v) cudaFree(p);
 }
 void* pinned_alloc(size_t bytes) { return pool_alloc(hpool(), bytes, true); }
-void  pinned_free(void* p) { pool_free(hpool(), p); }
+void  pinned_free(void* p) { pool_free(hpool(), p, true); }
 
 cudaStream_t thread_stream(int idx)
 {

@@ -443,18 +443,23 @@ GB_API int gb200_scanlines_convert(int srcType, const uint8_t* src, int srcPitch
     int band = (int)((16u << 20) / (big ? big : 1));
     if (band < 1) band = 1;
     if (band >= height) band = height;
+    // a failure after work was queued must not release ds / dd (DevBuf destructors) while copies or kernels still
+    // touch them: every exit goes through the synchronisation below
+#define GB_TRY(x) if (!gb::cuda_ok((x), #x, __FILE__, __LINE__)) { ok = false; break; }
+    bool ok = true;
     int k = 0;
     for (int i0 = 0; i0 < height; i0 += band, ++k) {
         const int i1 = i0 + band < height ? i0 + band : height, nr = i1 - i0;
         cudaStream_t st = gb::thread_stream(k % 3);
         const size_t sm0 = srcPitch >= 0 ? (size_t)i0 : (size_t)(height - i1);   // first memory row of the band
         const size_t dm0 = dstPitch >= 0 ? (size_t)i0 : (size_t)(height - i1);
-        if (sap == srow && sdp == srow) GB_CUDA(cudaMemcpyAsync(ds.as<uint8_t>() + sm0 * sdp, slo + sm0 * sap, srow * nr, cudaMemcpyHostToDevice, st));
-        else GB_CUDA(cudaMemcpy2DAsync(ds.as<uint8_t>() + sm0 * sdp, sdp, slo + sm0 * sap, sap, srow, nr, cudaMemcpyHostToDevice, st));
-        if (!gb::convert_device(srcType, dsrc + (long long)i0 * dsp, dsp, dstType, ddst + (long long)i0 * ddpp, ddpp, width, nr, st)) return 0;
-        if (dap == drow && ddp == drow) GB_CUDA(cudaMemcpyAsync(dlo + dm0 * dap, dd.as<uint8_t>() + dm0 * ddp, drow * nr, cudaMemcpyDeviceToHost, st));
-        else GB_CUDA(cudaMemcpy2DAsync(dlo + dm0 * dap, dap, dd.as<uint8_t>() + dm0 * ddp, ddp, drow, nr, cudaMemcpyDeviceToHost, st));
+        if (sap == srow && sdp == srow) { GB_TRY(cudaMemcpyAsync(ds.as<uint8_t>() + sm0 * sdp, slo + sm0 * sap, srow * nr, cudaMemcpyHostToDevice, st)); }
+        else { GB_TRY(cudaMemcpy2DAsync(ds.as<uint8_t>() + sm0 * sdp, sdp, slo + sm0 * sap, sap, srow, nr, cudaMemcpyHostToDevice, st)); }
+        if (!gb::convert_device(srcType, dsrc + (long long)i0 * dsp, dsp, dstType, ddst + (long long)i0 * ddpp, ddpp, width, nr, st)) { ok = false; break; }
+        if (dap == drow && ddp == drow) { GB_TRY(cudaMemcpyAsync(dlo + dm0 * dap, dd.as<uint8_t>() + dm0 * ddp, drow * nr, cudaMemcpyDeviceToHost, st)); }
+        else { GB_TRY(cudaMemcpy2DAsync(dlo + dm0 * dap, dap, dd.as<uint8_t>() + dm0 * ddp, ddp, drow, nr, cudaMemcpyDeviceToHost, st)); }
     }
-    for (int q = 0; q < 3 && q < k; ++q) GB_CUDA(cudaStreamSynchronize(gb::thread_stream(q)));
-    return 1;
+#undef GB_TRY
+    for (int q = 0; q < 3 && q <= k; ++q) if (!gb::cuda_ok(cudaStreamSynchronize(gb::thread_stream(q)), "sync", __FILE__, __LINE__)) ok = false;
+    return ok ? 1 : 0;
 }

@@ -410,7 +410,7 @@ jpeg_colour_kernel(const JpegImage* __restrict__ images, const int* __restrict__
 // block (thread = row, then thread = column, transposing through shared memory), sample tiles stay in shared
 // memory in the reference's m_pSample_buf tile order, and the colour pass writes whole output rows of the run
 // with 16-byte stores. Coefficients are read once (16 B per thread, 128 B per group) and pixels written once.
-constexpr int IC_THREADS = 256, IC_GROUPS = 32, IC_GSTRIDE = 264, IC_MAX_TILES = 192;
+constexpr int IC_THREADS = 256, IC_GROUPS = 32, IC_GSTRIDE = 264, IC_MAX_TILES = 192, IC_MCU420 = 12 * 64 + 16;
 
 __device__ __forceinline__ void unpack8(const int4 v, int in[8])
 {
@@ -428,11 +428,45 @@ __device__ __forceinline__ void ycc_to_rgb(int Y, int cb, int cr, int& r, int& g
     b = clamp255(Y + ((F177200 * cb + (32768 - 128 * F177200)) >> 16));
 }
 
+// 16 pixels of one row of a 4:2:0 MCU: Y from two luma tiles, Cb / Cr from the frequency-domain-upsampled tiles
+// (expanded_convert, jpegload.d:2731-2823) -> RC bytes per pixel (final channel adaptation :3763-3801).
+template <int RC>
+__device__ __forceinline__ void colour420(const uint8_t* __restrict__ tb, uint8_t* __restrict__ d, int n)
+{
+    uint32_t wds[RC * 4];           // 16 pixels * RC bytes
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint2 y8 = *(const uint2*)(tb + h * 64), cb8 = *(const uint2*)(tb + 256 + h * 64), cr8 = *(const uint2*)(tb + 512 + h * 64);
+        uint8_t px[8 * RC];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int Y = ((i < 4 ? y8.x : y8.y) >> ((i & 3) * 8)) & 255;
+            const int cb = ((i < 4 ? cb8.x : cb8.y) >> ((i & 3) * 8)) & 255;
+            const int cr = ((i < 4 ? cr8.x : cr8.y) >> ((i & 3) * 8)) & 255;
+            int r, g, b; ycc_to_rgb(Y, cb, cr, r, g, b);
+            if (RC == 1) px[i] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
+            else { px[i * RC] = (uint8_t)r; px[i * RC + 1] = (uint8_t)g; px[i * RC + 2] = (uint8_t)b; if (RC == 4) px[i * 4 + 3] = 255; }
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * RC; ++q)
+            wds[h * 2 * RC + q] = (uint32_t)px[q * 4] | ((uint32_t)px[q * 4 + 1] << 8) | ((uint32_t)px[q * 4 + 2] << 16) | ((uint32_t)px[q * 4 + 3] << 24);
+    }
+    if (n == 16 && (((uintptr_t)d) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < RC; ++q) ((uint4*)d)[q] = make_uint4(wds[q * 4], wds[q * 4 + 1], wds[q * 4 + 2], wds[q * 4 + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16 * RC; ++i) if (i < n * RC) d[i] = (uint8_t)(wds[i >> 2] >> ((i & 3) * 8));
+    }
+}
+
 __global__ void __launch_bounds__(IC_THREADS, 4)
 jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __restrict__ cta_base, int nimages,
                         const int* __restrict__ status)
 {
-    __shared__ __align__(16) uint8_t s_tiles[IC_MAX_TILES * 64];
+    // 4:2:0: the 12 tiles of an MCU are IC_MCU420 = 784 bytes apart (768 + 16): the colour pass reads 8-byte rows of 16
+    // MCUs at once, and a 768-byte stride would put them all in the same banks
+    __shared__ __align__(16) uint8_t s_tiles[IC_MAX_TILES * 64 + 16 * 16];
     __shared__ __align__(16) int s_tmp[IC_GROUPS * IC_GSTRIDE];
     int lo = 0, hi = nimages - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cta_base[mid] <= blockIdx.x) lo = mid; else hi = mid - 1; }
@@ -462,7 +496,7 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
         if (active) { m = task / npm; bi = task - m * npm; zag = zags[m * bpm + bi]; }
         const int zmax = __reduce_max_sync(0xffffffffu, zag);
         const int4* __restrict__ src = (const int4*)(coefs + ((size_t)m * bpm + bi) * 64);
-        uint8_t* dst = s_tiles + (m * tpm + bi) * 64;
+        uint8_t* dst = s_tiles + (st == YH2V2 ? m * IC_MCU420 + bi * 64 : (m * tpm + bi) * 64);
         if (zmax <= 1) {
             // idct with block_max_zag <= 1 (jpegload.d:312-326): all 64 samples are ((dc + 4) >> 3) + 128, clamped
             if (active) {
@@ -514,7 +548,7 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
                     const int dcv = (int)__ldg(coefs + ((size_t)m * 6 + 4 + ch) * 64);
                     const int t4 = (int)(short)dcv;          // add_and_store keeps a short
                     const uint32_t v = (uint32_t)clamp255((((t4 << 2) + (128 << 5) + 16) >> 5)) * 0x01010101u;
-                    uint8_t* dstc = s_tiles + (m * 12 + 4 + ch * 4) * 64;
+                    uint8_t* dstc = s_tiles + m * IC_MCU420 + (4 + ch * 4) * 64;
 #pragma unroll
                     for (int tt = 0; tt < 4; ++tt) *(uint2*)(dstc + tt * 64 + t * 8) = make_uint2(v, v);
                 }
@@ -568,7 +602,7 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
             }
             __syncwarp();
             if (active) {   // D: column pass, thread = column
-                uint8_t* dst = s_tiles + (m * 12 + 4 + ch * 4) * 64;
+                uint8_t* dst = s_tiles + m * IC_MCU420 + (4 + ch * 4) * 64;
 #pragma unroll
                 for (int tt = 0; tt < 4; ++tt) {
                     int in[8], out[8];
@@ -591,43 +625,10 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
         const int row = tid >> 4, m = tid & 15;
         const int y = mrow * 16 + row, x = (g0 + m) * 16;
         if (m < nm && y < H && x < W) {
-            const uint8_t* tb = s_tiles + m * 768 + (row >> 3) * 128 + (row & 7) * 8;
-            uint8_t px[64];
-            const int n = min(16, W - x);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint2 y8 = *(const uint2*)(tb + h * 64), cb8 = *(const uint2*)(tb + 256 + h * 64), cr8 = *(const uint2*)(tb + 512 + h * 64);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int Y = ((i < 4 ? y8.x : y8.y) >> ((i & 3) * 8)) & 255;
-                    const int cb = ((i < 4 ? cb8.x : cb8.y) >> ((i & 3) * 8)) & 255;
-                    const int cr = ((i < 4 ? cr8.x : cr8.y) >> ((i & 3) * 8)) & 255;
-                    int r, g, b; ycc_to_rgb(Y, cb, cr, r, g, b);
-                    const int p = h * 8 + i;
-                    if (rc == 1) px[p] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
-                    else if (rc == 3) { px[p * 3] = (uint8_t)r; px[p * 3 + 1] = (uint8_t)g; px[p * 3 + 2] = (uint8_t)b; }
-                    else { px[p * 4] = (uint8_t)r; px[p * 4 + 1] = (uint8_t)g; px[p * 4 + 2] = (uint8_t)b; px[p * 4 + 3] = 255; }
-                }
-            }
-            uint8_t* d = im.out + ((size_t)y * W + x) * rc;
-            if (n == 16 && (((uintptr_t)d) & 15) == 0) {
-#define IC_PACK(o) ((uint32_t)px[o] | ((uint32_t)px[(o) + 1] << 8) | ((uint32_t)px[(o) + 2] << 16) | ((uint32_t)px[(o) + 3] << 24))
-#define IC_ST(q) ((uint4*)d)[q] = make_uint4(IC_PACK((q) * 16), IC_PACK((q) * 16 + 4), IC_PACK((q) * 16 + 8), IC_PACK((q) * 16 + 12))
-                if (rc == 1) { IC_ST(0); }
-                else if (rc == 3) { IC_ST(0); IC_ST(1); IC_ST(2); }
-                else { IC_ST(0); IC_ST(1); IC_ST(2); IC_ST(3); }
-#undef IC_ST
-#undef IC_PACK
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (i < n) {
-                        if (rc == 1) d[i] = px[i];
-                        else if (rc == 3) { d[i * 3] = px[i * 3]; d[i * 3 + 1] = px[i * 3 + 1]; d[i * 3 + 2] = px[i * 3 + 2]; }
-                        else { d[i * 4] = px[i * 4]; d[i * 4 + 1] = px[i * 4 + 1]; d[i * 4 + 2] = px[i * 4 + 2]; d[i * 4 + 3] = 255; }
-                    }
-                }
-            }
+            const uint8_t* tb = s_tiles + m * IC_MCU420 + (row >> 3) * 128 + (row & 7) * 8;
+            if (rc == 3) colour420<3>(tb, im.out + ((size_t)y * W + x) * 3, min(16, W - x));
+            else if (rc == 4) colour420<4>(tb, im.out + ((size_t)y * W + x) * 4, min(16, W - x));
+            else colour420<1>(tb, im.out + ((size_t)y * W + x), min(16, W - x));
         }
     } else {
         const int mw = st == YH2V1 ? 16 : 8, mh = st == YH1V2 ? 16 : 8;
@@ -1177,7 +1178,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
             cudaEventElapsedTime(&ms, ev[5], ev[2]); B->phase_ms[5] += ms;      // scan + write
         }
         for (auto& e : ev) cudaEventDestroy(e);
-        if (!okc) { delete B; return nullptr; }
+        if (!okc) { cudaStreamSynchronize(st); delete B; return nullptr; }     // nothing in flight may outlive the scratch it uses
         for (int k = 0; k < m; ++k) final_ok[live[li + k]] = status[k];
         li = lj;
     }

@@ -366,7 +366,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         if (h_stage) pinned_free(h_stage);
         if (okc) for (int q = 0; q < 4; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }
         for (auto& e : ev) cudaEventDestroy(e);
-        if (!okc) { delete B; return nullptr; }
+        if (!okc) { cudaStreamSynchronize(st); delete B; return nullptr; }     // nothing in flight may outlive the scratch it uses
 
         std::vector<int> next;
         for (int k = 0; k < m; ++k) {
@@ -492,7 +492,12 @@ GB_API int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint
         u.image = i; u.inflate_idx = -1; u.need_len = 0;
     }
     // persistent per-thread scratch: the launch is asynchronous, so the job table must outlive the call
+    //  the previous launch that read the table may still be running, possibly on another stream: wait for it
+    // before the table is overwritten or regrown
     static thread_local gb::Scratch s_jobs, s_dummy;
+    static thread_local cudaEvent_t s_done = nullptr;
+    if (s_done) GB_CUDA(cudaEventSynchronize(s_done));
+    else GB_CUDA(cudaEventCreateWithFlags(&s_done, cudaEventDisableTiming));
     gb::UnfilterJob* d_jobs = (gb::UnfilterJob*)s_jobs.get(sizeof(gb::UnfilterJob) * (size_t)n_images);
     int* d_dummy = (int*)s_dummy.get(sizeof(int) * (size_t)n_images);
     if (!d_jobs || !d_dummy) return 0;
@@ -500,6 +505,7 @@ GB_API int gb200_png_unfilter_device(const uint8_t* raw, size_t raw_stride, uint
     int rp = bpp == 4 ? (int)(((row_bytes / 4 + 127) / 128) * 32) : 32;
     gb::launch_unfilter(d_jobs, n_images, status_dev ? status_dev : d_dummy, nullptr, st, rp <= 1024 ? rp : 32);
     GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaEventRecord(s_done, st));
     // jobs were copied from pageable memory: the copy has completed on return
     return 1;
 }

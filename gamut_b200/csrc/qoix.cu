@@ -696,7 +696,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (h_stage) pinned_free(h_stage);
     if (okc) for (int q = 0; q < 3; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }
     for (auto& e : ev) cudaEventDestroy(e);
-    if (!okc) { delete B; return nullptr; }
+    if (!okc) { cudaStreamSynchronize(st); delete B; return nullptr; }     // nothing in flight may outlive the scratch it uses
     for (int i : live) {
         if (!status[i]) continue;
         gb200_image_desc& D = B->images[i];

@@ -169,6 +169,34 @@ class Ctx:
         return [float(x) for x in t.tolist()]
 
 
+def pcie_probe(ctx: Ctx):
+    """What the platform gives a plain pinned copy, all ranks at once: the ceiling of any end-to-end number.
+    {"d2h": aggregate GB/s, "h2d": aggregate GB/s} over 1 GiB per rank and direction (best of 3)."""
+    torch = ctx.torch
+    n = 1 << 30
+    try:
+        h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+        out = {}
+        for name, (dst, src) in (("d2h", (h, d)), ("h2d", (d, h))):
+            best = 1e9
+            for _ in range(3):
+                ctx.barrier()
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                dst.copy_(src, non_blocking=True)
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            best = ctx.allmax([best])[0]
+            out[name] = round(n * ctx.world / (best * 1e-3) / 1e9, 1)
+        del h, d
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:100]}
+
+
 def run_workload(WL, ctx: Ctx, args, steps, warmup, e2e_steps, cpu_baseline=True):
     """Measures one workload on all ranks; returns the JSON line (rank 0) or None."""
     torch, L = ctx.torch, ctx.L
@@ -198,7 +226,9 @@ def run_workload(WL, ctx: Ctx, args, steps, warmup, e2e_steps, cpu_baseline=True
     # ---- end to end through the host-pointer C ABI: every step starts with its inputs in (pinned) host memory
     # and ends with its results in host memory (H2D and D2H inside the timed region)
     e2e = None
+    pcie = None
     if e2e_steps > 0:
+        pcie = pcie_probe(ctx)
         wl.e2e_setup()
         wl.e2e_step()                      # warm-up (allocates the cached device / pinned buffers)
         wl.e2e_step()
@@ -233,7 +263,7 @@ def run_workload(WL, ctx: Ctx, args, steps, warmup, e2e_steps, cpu_baseline=True
                            "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps,
                            "timing": "mean over the steps (wall clock around the whole loop, max over ranks)",
                            "value_median": round(e2e_px_all * e2e_steps / median_s / 1e6, 1),
-                           "step_ms": step_ms, "api": wl.e2e_api}
+                           "step_ms": step_ms, "api": wl.e2e_api, "platform_copy_GBps": pcie}
         line["gpu_launches"] = int(launches)
         line["clocks"] = clocks
         extra = wl.extra()

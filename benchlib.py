@@ -691,8 +691,10 @@ class QoixWorkload(_BatchDecodeWorkload):
     kernel_names = {1: "lz4 kernels (spec/merge/scan/pwrite/parse/resolve)", 2: "qoiplane10 kernels (p10_sync/scan/write/recon)"}
     traffic_keys = {1: "lz4", 2: "qoiplane10"}
 
+    scaling = "weak"                # BASELINE configs[4]: batch 2048 on 8 GPUs = 256 images per GPU at every N
+
     def __init__(self, rank, world, args):
-        self._setup(rank, world, args, 256)
+        self._setup(rank, world, args, 256 * world)
         self.out_bytes = self.W * self.H * 4
         self.kernel_bytes = {1: self.comp_bytes + self.payload, 2: self.payload + self.out_bytes}
 
@@ -716,7 +718,7 @@ class QoixWorkload(_BatchDecodeWorkload):
     def config(self):
         return {"units_per_rank": f"{self.n} images {self.W}x{self.H} la16 (total batch {self.total}, {self.DISTINCT} distinct, LZ4 forced on)",
                 "file_bytes_per_image": int(self.comp_bytes), "opcode_payload_bytes_per_image": int(self.payload),
-                "scaling_note": "strong: total batch fixed, sharded by image index",
+                "scaling_note": "weak: 256 images per GPU (the batch of 2048 of configs[4] on 8 GPUs), sharded by image index",
                 "l2": "inputs larger than L2 (every image has its own device copy)"}
 
     @staticmethod

@@ -710,16 +710,15 @@ infp_write_kernel(const InflateJob* jobs, InfPar* par, const uint2* work, uint32
 
 // ---------------------------------------------------------------------------------------------
 // 7. resolve (lz_resolve.cuh)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LZ4C_NT)
 infp_resolve_kernel(const InflateJob* jobs, const InfPar* par, int njobs)
 {
-    __shared__ __align__(16) uint8_t s_chunk[4][LZC_BUF];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 4 + warp;
+    __shared__ Lz4cShared S;
+    const int j = blockIdx.x;
     if (j >= njobs) return;
     const InfPar& P = par[j];
     if (!P.eligible || !P.ok || P.fail) return;
-    lz_resolve_stream_chunked<LZR_DEFLATE>(jobs[j].out, jobs[j].out_len, P.bitmap, lane, s_chunk[warp]);
+    lz_resolve_stream_jump<LZR_DEFLATE>(jobs[j].out, jobs[j].out_len, P.bitmap, S);
 }
 
 } // namespace gb

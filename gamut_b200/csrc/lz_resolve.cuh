@@ -321,6 +321,419 @@ __device__ inline void lz_resolve_stream_chunked(uint8_t* out, uint32_t n, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Chunked resolver, second form (round 2, PNG). Same 4 KB chunks in shared memory, but the work of a chunk is ordered
+// by what it waits for instead of by stream position:
+//   1. enumerate  every lane walks the set bits of its 4 bitmap words and writes (offset, length, distance) of its
+//                 matches to a list in shared memory (the lane's slot range comes from the popcount scan);
+//   2. far        matches whose whole source lies before the chunk (three quarters of them on photographic PNG data:
+//                 the row above is 7681 bytes back) depend on nothing that is still open: all of them are copied at
+//                 once, four per lane in flight, each as two or three aligned 8-byte loads realigned with a shift --
+//                 one L2 round trip per 128 matches instead of one per dependency round of 32;
+//   3. near       the remaining matches (source inside the chunk, or longer than 16 bytes) are taken in stream order,
+//                 32 at a time, exactly like lz_resolve_stream_chunked: a match copies as soon as its source ends
+//                 before the first destination that is still open; all the data involved is in shared memory.
+constexpr uint32_t LZ3_MAXM = LZC_BYTES / 3 + 3;
+constexpr uint32_t LZ3_FAR_LEN = 16;
+constexpr int LZ3_G = 4;
+
+struct Lz3Shared {
+    __align__(16) uint8_t buf[LZC_BUF];
+    uint2 list[LZ3_MAXM];                   // x: offset in the chunk | length << 12 (0: skip), y: distance
+    uint16_t near_idx[LZ3_MAXM + 1];
+};
+
+template <int FMT>
+__device__ inline void lz_resolve_stream_v3(uint8_t* out, uint32_t n, const uint32_t* bm, int lane, Lz3Shared& S)
+{
+    const uint32_t nw = (n + 31) >> 5;
+    for (uint32_t c0 = 0; c0 < n; c0 += LZC_BYTES) {
+        const uint32_t cend = min(c0 + LZC_SPAN, n);
+        const uint32_t mis = (uint32_t)((uintptr_t)(out + c0) & 15);
+        uint8_t* const buf = S.buf + mis;                            // buf[x - c0] for stream position x >= c0 - mis
+        uint8_t* const gbase = out + c0 - mis;                       // 16-byte aligned
+        const uint32_t span = cend - c0 + mis;
+        uint32_t w[4];
+        {
+            const uint32_t i0 = (c0 >> 5) + lane * 4;
+            const uint4 v = i0 < nw ? *(const uint4*)(bm + i0) : make_uint4(0, 0, 0, 0);
+            w[0] = i0 < nw ? v.x : 0; w[1] = i0 + 1 < nw ? v.y : 0; w[2] = i0 + 2 < nw ? v.z : 0; w[3] = i0 + 3 < nw ? v.w : 0;
+        }
+        const uint32_t cnt = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const uint32_t total = min(__shfl_sync(0xffffffffu, incl, 31), LZ3_MAXM);
+        if (total == 0) continue;                                   // nothing starts here: the chunk is final as it stands
+        for (uint32_t i = lane * 16; i < span; i += 512) *(uint4*)(S.buf + i) = __ldcg((const uint4*)(gbase + i));
+        __syncwarp();
+        // ---- 1. enumerate
+        {
+            uint32_t idx = incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t x = w[k];
+                const uint32_t base = ((uint32_t)lane * 4 + (uint32_t)k) * 32;
+                while (x) {
+                    const uint32_t p = base + (uint32_t)__ffs(x) - 1;
+                    x &= x - 1;
+                    const uint8_t* rec = buf + p;
+                    uint32_t len, dist;
+                    if (FMT == LZR_DEFLATE) { len = (uint32_t)rec[0] + 3; dist = ((uint32_t)rec[1] | ((uint32_t)rec[2] << 8)) + 1; }
+                    else { len = (uint32_t)rec[0] | ((uint32_t)rec[1] << 8); dist = (uint32_t)rec[2] | ((uint32_t)rec[3] << 8); }
+                    const uint32_t dst = c0 + p;
+                    // a record that would read before the stream or write past it cannot come from an accepted stream: skip it
+                    if (dist == 0 || dist > dst || dst + len > n) len = 0;
+                    if (idx < LZ3_MAXM) S.list[idx] = make_uint2(p | (len << 12), dist);
+                    ++idx;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- 2. far matches, LZ3_G per lane in flight; the others are queued in stream order for step 3
+        uint32_t nnear = 0;
+        for (uint32_t m0 = 0; m0 < total; m0 += 32 * LZ3_G) {
+            uint32_t p[LZ3_G], len[LZ3_G];
+            uint64_t q0[LZ3_G], q1[LZ3_G], q2[LZ3_G];
+            bool far[LZ3_G], nearf[LZ3_G];
+            uint32_t sh[LZ3_G];
+#pragma unroll
+            for (int g = 0; g < LZ3_G; ++g) {
+                const uint32_t m = m0 + (uint32_t)g * 32 + (uint32_t)lane;
+                const uint2 e = m < total ? S.list[m] : make_uint2(0, 1);
+                p[g] = e.x & 4095; len[g] = e.x >> 12;
+                const uint32_t s = c0 + p[g] - e.y;
+                far[g] = len[g] != 0 && len[g] <= LZ3_FAR_LEN && s + len[g] <= c0;
+                nearf[g] = len[g] != 0 && !far[g];
+                q0[g] = q1[g] = q2[g] = 0; sh[g] = 0;
+                if (far[g]) {
+                    const uintptr_t a = (uintptr_t)(out + s);
+                    const uint64_t* a8 = (const uint64_t*)(a & ~(uintptr_t)7);
+                    const uint32_t o = (uint32_t)(a & 7);
+                    sh[g] = o * 8;
+                    q0[g] = __ldcg(a8);
+                    if (o + len[g] > 8) q1[g] = __ldcg(a8 + 1);
+                    if (o + len[g] > 16) q2[g] = __ldcg(a8 + 2);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < LZ3_G; ++g) {
+                if (far[g]) {
+                    uint64_t lo = q0[g] >> sh[g], hi = q1[g] >> sh[g];
+                    if (sh[g]) { lo |= q1[g] << (64 - sh[g]); hi |= q2[g] << (64 - sh[g]); }
+                    uint8_t* d8 = buf + p[g];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) if (k < len[g]) d8[k] = (uint8_t)(lo >> (8 * k));
+                    if (len[g] > 8) {
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; ++k) if (8 + k < len[g]) d8[8 + k] = (uint8_t)(hi >> (8 * k));
+                    }
+                }
+                const uint32_t nm = __ballot_sync(0xffffffffu, nearf[g]);
+                if (nearf[g]) S.near_idx[nnear + __popc(nm & ((1u << lane) - 1))] = (uint16_t)(m0 + (uint32_t)g * 32 + (uint32_t)lane);
+                nnear += __popc(nm);
+            }
+        }
+        __syncwarp();
+        // ---- 3. near matches in stream order
+        for (uint32_t b0 = 0; b0 < nnear; b0 += 32) {
+            const bool valid = b0 + lane < nnear;
+            const uint2 e = valid ? S.list[S.near_idx[b0 + lane]] : make_uint2(0, 1);
+            const uint32_t dst = valid ? c0 + (e.x & 4095) : 0xffffffffu, len = e.x >> 12, dist = e.y;
+            bool done = !valid;
+            for (;;) {
+                const uint32_t F = __reduce_min_sync(0xffffffffu, done ? 0xffffffffu : dst);
+                if (F == 0xffffffffu) break;
+                const int fl = __ffs(__ballot_sync(0xffffffffu, !done && dst == F)) - 1;
+                const uint32_t flen = __shfl_sync(0xffffffffu, len, fl);
+                if (flen > 32) {
+                    // the first open match is long: the whole warp copies it
+                    const uint32_t d = F, di = __shfl_sync(0xffffffffu, dist, fl), s = d - di;
+                    const bool ov = di < flen;
+                    if (d + flen <= c0 + LZC_SPAN) {
+                        if (!ov) {
+                            for (uint32_t x = lane; x < flen; x += 32) { const uint32_t a = s + x; buf[d - c0 + x] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+                        } else {
+                            // periodic: byte x equals source byte x mod di; all sources lie before d (final)
+                            for (uint32_t x = lane; x < flen; x += 32) { const uint32_t a = s + x % di; buf[d - c0 + x] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+                        }
+                    } else {
+                        // longer than the buffer's slack (LZ4 only): through the output buffer. Everything resolved so
+                        // far goes back first, the part of the destination that the buffer covers is reloaded after.
+                        __syncwarp();
+                        for (uint32_t i = lane; i < cend - c0; i += 32) out[c0 + i] = buf[i];
+                        __threadfence_block();
+                        __syncwarp();
+                        for (uint32_t c = 0; c < flen; c += 256) {
+                            uint8_t t[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { const uint32_t x = c + (uint32_t)q * 32 + lane; if (x < flen) t[q] = __ldcg(out + s + (ov ? x % di : x)); }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { const uint32_t x = c + (uint32_t)q * 32 + lane; if (x < flen) out[d + x] = t[q]; }
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        for (uint32_t i = d - c0 + lane; i < cend - c0; i += 32) buf[i] = __ldcg(out + c0 + i);
+                    }
+                    if (lane == fl) done = true;
+                    __syncwarp();
+                    continue;
+                }
+                // short matches whose source ends before the first open destination copy now, one per lane
+                const uint32_t s = dst - dist;
+                const bool ready = !done && len <= 32 && (s + min(len, dist) <= F || dst == F);
+                if (ready) {
+                    uint8_t* d8 = buf + (dst - c0);
+                    if (dist >= len) {
+                        // no self-overlap: independent loads, 8 at a time
+                        for (uint32_t k0 = 0; k0 < len; k0 += 8) {
+                            uint8_t t[8];
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < len) { const uint32_t a = s + k0 + k; t[k] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < len) d8[k0 + k] = t[k];
+                        }
+                    } else {
+                        // overlapping copy: the first `dist` bytes come from the source, the rest repeats them
+                        uint8_t t[8];
+                        for (uint32_t k0 = 0; k0 < dist; k0 += 8) {
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < dist) { const uint32_t a = s + k0 + k; t[k] = a >= c0 ? buf[a - c0] : __ldcg(out + a); }
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if (k0 + k < dist) d8[k0 + k] = t[k];
+                        }
+                        for (uint32_t k = dist; k < len; ++k) d8[k] = d8[k - dist];
+                    }
+                    done = true;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- write back [c0, cend): resolved bytes, untouched literals, and the still-parked records of the next chunk
+        __syncwarp();
+        {
+            const uint32_t nfull = span & ~15u;
+            for (uint32_t i = lane * 16; i < nfull; i += 512) *(uint4*)(gbase + i) = *(const uint4*)(S.buf + i);
+            if (nfull + lane < span) gbase[nfull + lane] = S.buf[nfull + lane];       // at most 15 tail bytes, never past n
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Chunked resolver, CTA form with pointer jumping (round 2, PNG; matches of at most LZC_EXTRA bytes, i.e. DEFLATE).
+// Profiles of the one-warp chunked resolver on the adaptive-filter PNG workload (profiles/r2_resolve_*): a lone warp runs
+// 13.6 k warp instructions per 4 KB chunk at one instruction every ~10 cycles (143 ms per stream whatever the batch
+// size), 60 % of them in ordered rounds with 3.4 of 32 lanes active -- the matches of filtered image rows form long
+// dependency chains (a match copies what the match before it has just produced; distances of 4-8 bytes), and every
+// link of a chain was a round. A first CTA version that chased source addresses back through the open matches (one
+// hop per link) removed the ordering but paid one hop per link and byte: 15.7 k instructions per chunk, 90 ms.
+// This version resolves the chains in O(log depth) uniform passes instead:
+//   * NT threads per stream; the chunk and a pointer per byte (16 bits, chunk-relative) sit in shared memory; a byte
+//     that is final points to itself;
+//   * far matches (whole source before the chunk: final data) are copied at once, with aligned 8-byte loads (<= 32
+//     bytes, one match per thread, two in flight) or by the whole warp (longer ones, two in flight);
+//   * every byte x of any other match gets ptr[x] = x - dist (a source byte before the chunk is fetched on the spot
+//     and the byte becomes final); for an overlapping match this chains through the match itself;
+//   * pointer jumping, ptr[x] = ptr[ptr[x]], in place, until nothing changes: every pass at least doubles the distance
+//     a pointer has travelled, so <= 13 passes whatever the input and 3-5 on image data (in-place updates in ascending
+//     order compress most of a chain in one pass); all lanes busy, no divergence, one barrier per pass;
+//   * one pass copies buf[x] = buf[ptr[x]]: sources are roots (final bytes), destinations are not -- no hazards.
+constexpr int LZ4C_NT = 128;
+constexpr uint32_t LZ4C_PTRS = (LZC_SPAN + 32 + 7) & ~7u;
+
+struct Lz4cShared {
+    __align__(16) uint8_t buf[LZC_BUF];
+    __align__(16) uint16_t ptr[LZ4C_PTRS];  // chunk-relative position of the byte this byte is a copy of (itself: final)
+    uint2 list[LZ3_MAXM];                   // x: offset in the chunk | length << 12 (0: skip), y: distance
+    uint32_t wsum[LZ4C_NT / 32];
+};
+
+template <int FMT>
+__device__ inline void lz_resolve_stream_jump(uint8_t* out, uint32_t n, const uint32_t* bm, Lz4cShared& S)
+{
+    constexpr int NT = LZ4C_NT, NWARP = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nw = (n + 31) >> 5;
+    for (uint32_t c0 = 0; c0 < n; c0 += LZC_BYTES) {
+        const uint32_t cend = min(c0 + LZC_SPAN, n);
+        const uint32_t mis = (uint32_t)((uintptr_t)(out + c0) & 15);
+        uint8_t* const buf = S.buf + mis;                            // buf[x - c0] for stream position x >= c0 - mis
+        uint8_t* const gbase = out + c0 - mis;                       // 16-byte aligned
+        const uint32_t span = cend - c0 + mis;
+        __syncthreads();                                             // the previous chunk's write-back has read S.buf
+        // ---- match starts: one bitmap word per thread (NT * 32 = LZC_BYTES)
+        uint32_t w;
+        {
+            const uint32_t i = (c0 >> 5) + (uint32_t)tid;
+            w = i < nw ? bm[i] : 0u;
+            const uint32_t lim = n - min(n, c0 + (uint32_t)tid * 32);             // bits at or beyond n are not matches
+            if (lim < 32) w &= lim ? (0xffffffffu >> (32 - lim)) : 0u;
+        }
+        const uint32_t cnt = __popc(w);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        if (lane == 31) S.wsum[warp] = incl;
+        for (uint32_t i = tid * 16; i < span; i += NT * 16) *(uint4*)(S.buf + i) = __ldcg((const uint4*)(gbase + i));
+        // every byte final: ptr[x] = x
+        for (uint32_t i = tid * 8; i < LZ4C_PTRS; i += NT * 8) {
+            const uint32_t a = i | ((i + 1) << 16);
+            *(uint4*)(S.ptr + i) = make_uint4(a, a + 0x00020002u, a + 0x00040004u, a + 0x00060006u);
+        }
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < NWARP; ++q) { const uint32_t t = S.wsum[q]; base += q < warp ? t : 0u; total += t; }
+        if (total == 0) continue;                                    // nothing starts here: the chunk is final as it stands
+        total = min(total, LZ3_MAXM);
+        // ---- 1. enumerate
+        {
+            uint32_t idx = base + incl - cnt;
+            uint32_t x = w;
+            while (x) {
+                const uint32_t p = (uint32_t)tid * 32 + (uint32_t)__ffs(x) - 1;
+                x &= x - 1;
+                const uint8_t* rec = buf + p;
+                uint32_t len, dist;
+                if (FMT == LZR_DEFLATE) { len = (uint32_t)rec[0] + 3; dist = ((uint32_t)rec[1] | ((uint32_t)rec[2] << 8)) + 1; }
+                else { len = (uint32_t)rec[0] | ((uint32_t)rec[1] << 8); dist = (uint32_t)rec[2] | ((uint32_t)rec[3] << 8); }
+                const uint32_t dst = c0 + p;
+                // a record that would read before the stream or write past it (or past the buffer's slack) cannot come
+                // from an accepted stream: skip it
+                if (dist == 0 || dist > dst || dst + len > n || len > LZC_EXTRA) len = 0;
+                if (idx < LZ3_MAXM) S.list[idx] = make_uint2(p | (len << 12), dist);
+                ++idx;
+            }
+        }
+        __syncthreads();
+        // ---- 2. far matches copy; the bytes of the others point dist back
+        bool any_open = false;
+        for (uint32_t m0 = 0; m0 < total; m0 += NT * 2) {
+            uint32_t p[2], len[2], sh[2], srcpos[2];
+            uint64_t q[2][5];
+            bool far[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t m = m0 + (uint32_t)g * NT + (uint32_t)tid;
+                const uint2 e = m < total ? S.list[m] : make_uint2(0, 1);
+                p[g] = e.x & 4095; len[g] = e.x >> 12;
+                const uint32_t s = c0 + p[g] - e.y;
+                srcpos[g] = s;
+                far[g] = len[g] != 0 && s + len[g] <= c0;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) q[g][i] = 0;
+                sh[g] = 0;
+                if (far[g] && len[g] <= 32) {
+                    const uintptr_t a = (uintptr_t)(out + s);
+                    const uint64_t* a8 = (const uint64_t*)(a & ~(uintptr_t)7);
+                    const uint32_t o = (uint32_t)(a & 7);
+                    sh[g] = o * 8;
+                    q[g][0] = __ldcg(a8);
+#pragma unroll
+                    for (int i = 1; i < 5; ++i) if (o + len[g] > 8u * i) q[g][i] = __ldcg(a8 + i);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const bool open = len[g] != 0 && !far[g];
+                any_open |= open;
+                if (open && len[g] <= 32) {
+                    // x - dist, or the byte itself when its source lies before the chunk (a straddling match)
+                    const uint32_t back = p[g] + c0 - srcpos[g];         // = dist
+                    for (uint32_t k = 0; k < len[g]; ++k) {
+                        const uint32_t x = p[g] + k;
+                        if (x >= back) S.ptr[x] = (uint16_t)(x - back);
+                        else buf[x] = __ldcg(out + srcpos[g] + k);
+                    }
+                }
+                uint32_t lm = __ballot_sync(0xffffffffu, open && len[g] > 32);
+                while (lm) {
+                    const int l = __ffs(lm) - 1; lm &= lm - 1;
+                    const uint32_t pp = __shfl_sync(0xffffffffu, p[g], l), ll = __shfl_sync(0xffffffffu, len[g], l);
+                    const uint32_t ss = __shfl_sync(0xffffffffu, srcpos[g], l);
+                    const uint32_t back = pp + c0 - ss;
+                    for (uint32_t k = lane; k < ll; k += 32) {
+                        const uint32_t x = pp + k;
+                        if (x >= back) S.ptr[x] = (uint16_t)(x - back);
+                        else buf[x] = __ldcg(out + ss + k);
+                    }
+                }
+                if (far[g] && len[g] <= 32) {
+                    uint8_t* d8 = buf + p[g];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if ((uint32_t)i * 8 < len[g]) {
+                            uint64_t v = q[g][i] >> sh[g];
+                            if (sh[g]) v |= q[g][i + 1] << (64 - sh[g]);
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) if ((uint32_t)i * 8 + k < len[g]) d8[i * 8 + k] = (uint8_t)(v >> (8 * k));
+                        }
+                    }
+                }
+                // long far matches of this warp, two at a time
+                uint32_t fm = __ballot_sync(0xffffffffu, far[g] && len[g] > 32);
+                while (fm) {
+                    const int l0 = __ffs(fm) - 1; fm &= fm - 1;
+                    const int l1 = fm ? __ffs(fm) - 1 : l0;
+                    const bool two = fm != 0; fm &= fm - 1;
+                    const uint32_t pa = __shfl_sync(0xffffffffu, p[g], l0), la = __shfl_sync(0xffffffffu, len[g], l0), sa = __shfl_sync(0xffffffffu, srcpos[g], l0);
+                    const uint32_t pb = __shfl_sync(0xffffffffu, p[g], l1), lb = two ? __shfl_sync(0xffffffffu, len[g], l1) : 0u, sb = __shfl_sync(0xffffffffu, srcpos[g], l1);
+                    uint8_t ta[LZC_EXTRA / 32], tb[LZC_EXTRA / 32];
+#pragma unroll
+                    for (uint32_t i = 0; i < LZC_EXTRA / 32; ++i) {
+                        const uint32_t x = i * 32 + (uint32_t)lane;
+                        if (x < la) ta[i] = __ldcg(out + sa + x);
+                        if (x < lb) tb[i] = __ldcg(out + sb + x);
+                    }
+#pragma unroll
+                    for (uint32_t i = 0; i < LZC_EXTRA / 32; ++i) {
+                        const uint32_t x = i * 32 + (uint32_t)lane;
+                        if (x < la) buf[pa + x] = ta[i];
+                        if (x < lb) buf[pb + x] = tb[i];
+                    }
+                }
+            }
+        }
+        if (__syncthreads_or(any_open ? 1 : 0)) {
+            // ---- 3. pointer jumping over the chunk, two positions per 32-bit word, in place
+            const uint32_t npair = (min(cend - c0, LZC_SPAN) + 1) >> 1;
+            uint32_t* const ptr32 = (uint32_t*)S.ptr;
+            for (int pass = 0; pass < 16; ++pass) {
+                bool changed = false;
+                for (uint32_t i = tid; i < npair; i += NT) {
+                    const uint32_t v = ptr32[i];
+                    uint32_t p0 = v & 0xffffu, p1 = v >> 16;
+                    if (v != ((2 * i) | ((2 * i + 1) << 16))) {     // at least one of the two is not final
+                        const uint32_t q0 = S.ptr[p0], q1 = S.ptr[p1];
+                        if (q0 != p0 || q1 != p1) { ptr32[i] = q0 | (q1 << 16); changed = true; }
+                    }
+                }
+                if (!__syncthreads_or(changed ? 1 : 0)) break;
+            }
+            // ---- 4. copy: every open byte from its root
+            for (uint32_t i = tid; i < npair; i += NT) {
+                const uint32_t v = ptr32[i];
+                if (v != ((2 * i) | ((2 * i + 1) << 16))) {
+                    const uint32_t p0 = v & 0xffffu, p1 = v >> 16;
+                    const uint8_t b0 = buf[p0], b1 = buf[p1];
+                    buf[2 * i] = b0; buf[2 * i + 1] = b1;            // a final byte is rewritten with itself
+                }
+            }
+            __syncthreads();
+        }
+        // ---- write back [c0, cend): resolved bytes, untouched literals, and the still-parked records of the next chunk
+        {
+            const uint32_t nfull = span & ~15u;
+            for (uint32_t i = tid * 16; i < nfull; i += NT * 16) *(uint4*)(gbase + i) = *(const uint4*)(S.buf + i);
+            if (tid < 16 && nfull + tid < span) gbase[nfull + tid] = S.buf[nfull + tid];       // at most 15 tail bytes, never past n
+        }
+        __threadfence_block();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // CTA-wide resolver: one thread per match, exact dependencies. Used where a batch has FEW streams (QOIX: one LZ4 block
 // per image, 256 images per GPU), so that a stream gets 16 warps instead of one.
 // The chunk sits in shared memory with a finality bit per byte (literals final, match destinations open); the matches

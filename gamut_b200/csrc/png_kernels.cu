@@ -124,7 +124,7 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
     infp_count_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
     infp_walk_kernel<<<(njobs + INFP_WARPS - 1) / INFP_WARPS, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, njobs);
     infp_write_kernel<<<persistent, INFP_WARPS * 32, 0, st>>>(d_jobs, d_par, d_work, d_ctr);
-    infp_resolve_kernel<<<(njobs + 3) / 4, 128, 0, st>>>(d_jobs, d_par, njobs);
+    infp_resolve_kernel<<<njobs, LZ4C_NT, 0, st>>>(d_jobs, d_par, njobs);
     inflate_batch_kernel<<<grid, INF_WARPS_PER_CTA * 32, 0, st>>>(d_jobs, njobs, d_par);
     count_launch(11);
     return true;

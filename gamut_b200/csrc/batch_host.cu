@@ -9,6 +9,9 @@
 #include "batch.h"
 #include <vector>
 #include <memory>
+#include <chrono>
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace gb {
 gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
@@ -29,33 +32,59 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
         gb::set_error("gb200_decode_batch_host: format %d has no batched decoder", format); return 0;
     }
     if (sub_batch <= 0) {
-        // JPEG decode time scales with the number of images, so many small sub-batches overlap well. The PNG and QOIX
-        // pipelines have per-stream serial stages (LZ77 resolve, chain walks) whose duration hardly depends on how
-        // many streams run side by side: cutting those batches only adds latency, so they stay whole up to 1024 images.
-        if (format == GB200_FORMAT_JPEG) { sub_batch = n / 8; if (sub_batch < 8) sub_batch = 8; if (sub_batch > 64) sub_batch = 64; }
-        else sub_batch = 1024;
+        // The download of sub-batch k overlaps the upload + kernels of sub-batch k+1, so the call costs about one
+        // (small) first decode plus the larger of the two sums. Sizes measured on B200 + PCIe 5 (profiles/r2_e2e_*):
+        // JPEG 4K: 32 images (6 ms of decode against 15 ms of download); PNG / QOIX: their LZ77 stages need a few
+        // hundred streams to fill the machine, so the sub-batches are larger. GB200_E2E_SUB overrides (measurement).
+        const char* e = getenv("GB200_E2E_SUB");
+        const int env = e ? atoi(e) : 0;
+        if (env > 0) sub_batch = env;
+        else if (format == GB200_FORMAT_JPEG) { sub_batch = n / 8; if (sub_batch < 8) sub_batch = 8; if (sub_batch > 32) sub_batch = 32; }
+        else if (format == GB200_FORMAT_PNG) sub_batch = 128;
+        else sub_batch = 64;
     }
     cudaStream_t s_decode = gb::thread_stream(0), s_copy = gb::thread_stream(1);
     if (!s_decode || !s_copy) return 0;
-    struct InFlight { gb200_batch* B = nullptr; cudaEvent_t done = nullptr; };
+    struct InFlight { gb200_batch* B = nullptr; cudaEvent_t done = nullptr; cudaEvent_t start = nullptr; double t_dec0 = 0, t_dec1 = 0; int a = 0; };
+    const bool trace = getenv("GB200_E2E_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_base = now();
+    cudaEvent_t ev_base = nullptr;
+    if (trace) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, s_copy); }
     InFlight fly[2];
     bool ok = true;
     auto retire = [&](InFlight& f) {
         if (!f.B) return;
-        if (f.done) { if (cudaEventSynchronize(f.done) != cudaSuccess) ok = false; cudaEventDestroy(f.done); f.done = nullptr; }
+        if (f.done) {
+            if (cudaEventSynchronize(f.done) != cudaSuccess) ok = false;
+            if (trace && f.start) {
+                float c0 = 0, c1 = 0;
+                cudaEventElapsedTime(&c0, ev_base, f.start); cudaEventElapsedTime(&c1, ev_base, f.done);
+                fprintf(stderr, "[e2e] sub-batch at %d: decode call %.2f..%.2f ms (host clock), download %.2f..%.2f ms (device clock from the first record), retired at %.2f\n",
+                        f.a, f.t_dec0 - t_base, f.t_dec1 - t_base, c0, c1, now() - t_base);
+                cudaEventDestroy(f.start); f.start = nullptr;
+            }
+            cudaEventDestroy(f.done); f.done = nullptr;
+        }
         delete f.B; f.B = nullptr;
     };
     int slot = 0;
-    for (int a = 0; a < n && ok; a += sub_batch, slot ^= 1) {
-        const int m = n - a < sub_batch ? n - a : sub_batch;
+    // the first sub-batch is the only one whose decode nothing hides: a quarter of the others
+    int m = 0;
+    for (int a = 0; a < n && ok; a += m, slot ^= 1) {
+        const int want = a == 0 && n > sub_batch ? (sub_batch + 3) / 4 : sub_batch;
+        m = n - a < want ? n - a : want;
         retire(fly[slot]);                       // the sub-batch before the previous one: its pixels have long arrived
         gb200_batch* B = nullptr;
+        const double td0 = now();
         switch (format) {
         case GB200_FORMAT_JPEG: B = gb::jpeg_decode_batch(m, files + a, lens + a, nullptr, arg, s_decode); break;
         case GB200_FORMAT_PNG:  B = gb::png_decode_batch(m, files + a, lens + a, nullptr, arg, want16, s_decode); break;
         default:                B = gb::qoix_decode_batch(m, files + a, lens + a, nullptr, arg, s_decode); break;
         }
         if (!B) { ok = false; break; }
+        fly[slot].t_dec0 = td0; fly[slot].t_dec1 = now(); fly[slot].a = a;
+        if (trace) { cudaEventCreate(&fly[slot].start); cudaEventRecord(fly[slot].start, s_copy); }
         // the decode call returns with its work complete (it reads the statuses back), so the copies can be queued on
         // the other stream right away; they overlap the next sub-batch's upload and kernels
         for (int i = 0; i < m; ++i) {
@@ -70,7 +99,7 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
             descs[a + i] = D;
         }
         fly[slot].B = B;
-        if (cudaEventCreateWithFlags(&fly[slot].done, cudaEventDisableTiming) != cudaSuccess ||
+        if (cudaEventCreateWithFlags(&fly[slot].done, trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
             cudaEventRecord(fly[slot].done, s_copy) != cudaSuccess) ok = false;
     }
     retire(fly[0]); retire(fly[1]);

@@ -171,6 +171,48 @@ cudaStream_t thread_stream(int idx)
     return st;
 }
 
+__global__ void __launch_bounds__(256) fill_kernel(uint8_t* p, size_t n, uint32_t v4)
+{
+    // head bytes up to the first 16-byte boundary, 16-byte vectors, tail bytes
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)p & 15)) & 15));
+    const size_t nvec = (n - head) >> 4, tail0 = head + (nvec << 4);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (tid < head) p[tid] = (uint8_t)v4;
+    uint4* v = (uint4*)(p + head);
+    for (size_t i = tid; i < nvec; i += nth) v[i] = make_uint4(v4, v4, v4, v4);
+    if (tid < n - tail0) p[tail0 + tid] = (uint8_t)v4;
+}
+__global__ void __launch_bounds__(256) read_back_kernel(uint8_t* dst, const uint8_t* src, size_t n)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 3) == 0) {
+        const size_t nw = n >> 2;
+        for (size_t i = tid; i < nw; i += nth) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+        if (tid < (n & 3)) dst[(nw << 2) + tid] = src[(nw << 2) + tid];
+    } else for (size_t i = tid; i < n; i += nth) dst[i] = src[i];
+}
+bool dev_fill_async(void* p, int byte, size_t n, cudaStream_t st)
+{
+    if (n == 0) return true;
+    const uint32_t b = (uint32_t)byte & 255u;
+    size_t blocks = (n / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    fill_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint8_t*)p, n, b * 0x01010101u);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "fill_kernel", __FILE__, __LINE__);
+}
+bool dev_read_back_async(void* pinned_dst, const void* dev_src, size_t n, cudaStream_t st)
+{
+    if (n == 0) return true;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 64) blocks = 64;
+    read_back_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint8_t*)pinned_dst, (const uint8_t*)dev_src, n);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "read_back_kernel", __FILE__, __LINE__);
+}
+
 void host_copy_parallel(const HostCopy* copies, size_t count)
 {
     size_t total = 0;

@@ -39,6 +39,15 @@ void  dev_trim();
 void* pinned_alloc(size_t bytes);
 void  pinned_free(void* p);
 
+// Fill and small read-back WITHOUT the copy engines. On this platform a cudaMemsetAsync or a device-to-host
+// cudaMemcpyAsync queues behind every download already issued on ANY stream (one FIFO per engine; measured: a 64 KB
+// read-back issued after a 1 GiB download starts when that download ends), which serialised the decode of sub-batch
+// k+1 behind the download of sub-batch k in gb200_decode_batch_host. These two run as kernels: dev_fill_async sets n
+// bytes, dev_read_back_async copies n bytes of device memory into PINNED host memory (mapped under UVA) with a store
+// from the SMs; the caller synchronises the stream before reading it.
+bool dev_fill_async(void* p, int byte, size_t n, cudaStream_t st);
+bool dev_read_back_async(void* pinned_dst, const void* dev_src, size_t n, cudaStream_t st);
+
 // Host-side staging copies (pageable caller memory -> pinned staging) of a batch, spread over a few threads: one
 // memcpy thread moves ~10 GB/s, which would otherwise dominate the end-to-end time of a batch decode.
 struct HostCopy { void* dst; const void* src; size_t n; };
@@ -55,6 +64,14 @@ struct DevBuf {
     ~DevBuf() { if (p) dev_free(p); }
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     bool alloc(size_t n) { if (p) dev_free(p); p = dev_alloc(n); return p != nullptr; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    explicit PinnedBuf(size_t n) { p = pinned_alloc(n ? n : 1); }
+    ~PinnedBuf() { if (p) pinned_free(p); }
+    PinnedBuf(const PinnedBuf&) = delete; PinnedBuf& operator=(const PinnedBuf&) = delete;
     template <class T> T* as() const { return (T*)p; }
 };
 

@@ -240,7 +240,7 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
         gb::DevBuf d_img(block);
         if (!d_img.p) { free(area); delete B; return fail(kOutOfMemory); }
         uint8_t* d_first = d_img.as<uint8_t>() + (data_off - first_off);      // device address of scanline 0
-        ok = gb::cuda_ok(cudaMemsetAsync(d_img.p, 0, block, st), "clear", __FILE__, __LINE__);
+        ok = gb::dev_fill_async(d_img.p, 0, block, st);
         // scanlinesConvert / scanlinesCopy (image.d:1262-1300) on the device, straight into the final geometry
         ok = ok && gb200_scanlines_convert_device(type, D.pixels, D.pitch, target, d_first, final_pitch, W, H, st);
         ok = ok && gb::cuda_ok(cudaMemcpyAsync(area + first_off, d_img.p, block, cudaMemcpyDeviceToHost, st), "image to host", __FILE__, __LINE__);

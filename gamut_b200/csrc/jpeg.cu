@@ -1100,12 +1100,12 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         okc &= cuda_ok(cudaMemcpyAsync(d_tables.p, tables.data(), sizeof(HuffTable) * tables.size(), cudaMemcpyHostToDevice, st), "tables", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_base.p, cta_base.data(), sizeof(uint32_t) * (m + 1), cudaMemcpyHostToDevice, st), "base", __FILE__, __LINE__);
         okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemsetAsync(d_unconv.p, 0, 4, st), "unconv", __FILE__, __LINE__);
+        okc &= dev_fill_async(d_unconv.p, 0, 4, st);
         // images with one-thread segments scatter into zero-filled blocks (the reference zero-fills per block, :2459-2510);
         // the chunk-parallel writer zero-fills its own blocks
         for (int k = 0; k < m; ++k) if (needs_zero[k]) {
             const size_t bytes = (k + 1 < m ? coef_off[k + 1] : scratch) - coef_off[k];
-            okc &= cuda_ok(cudaMemsetAsync(d_scratch.as<uint8_t>() + coef_off[k], 0, bytes, st), "memset", __FILE__, __LINE__);
+            okc &= dev_fill_async(d_scratch.as<uint8_t>() + coef_off[k], 0, bytes, st);
         }
         cudaEventRecord(ev[1], st);
         const int nsegs = (int)segs.size();
@@ -1145,25 +1145,31 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         };
         run_idct();
         cudaEventRecord(ev[3], st);
-        std::vector<int> status((size_t)m);
-        okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemcpyAsync(&h_unconv, unconv, 4, cudaMemcpyDeviceToHost, st), "unconverged back", __FILE__, __LINE__);
+        // results come back through pinned memory written by a kernel, not through the copy engine (common.h)
+        PinnedBuf h_back(sizeof(int) * ((size_t)m + 1));
+        if (!h_back.p) okc = false;
+        int* const status = h_back.as<int>();
+        volatile uint32_t* const h_unconv_p = (volatile uint32_t*)(status + m);
+        okc = okc && dev_read_back_async(status, d_status.p, sizeof(int) * m, st);
+        okc = okc && dev_read_back_async((void*)h_unconv_p, unconv, 4, st);
         okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+        if (okc) h_unconv = *h_unconv_p;
         // A CTA boundary of the sync kernel was still wrong after two repair rounds (a run of > 248 chunks that never
         // re-synchronises: not seen on real streams): repair until the chain is consistent, then redo the dependent passes.
         for (int round = 0; okc && h_unconv && round < 1 << 16; ++round) {
-            okc &= cuda_ok(cudaMemsetAsync(unconv, 0, 4, st), "unconv", __FILE__, __LINE__);
+            okc &= dev_fill_async(unconv, 0, 4, st);
             jpeg_repair_kernel<<<rg, 64, 0, st>>>(dI, dL, nlong, total_sync_ctas, clean, clen, dT, recs, entry, 0, unconv);
             jpeg_repair_kernel<<<rg, 64, 0, st>>>(dI, dL, nlong, total_sync_ctas, clean, clen, dT, recs, entry, 1, unconv);
             count_launch(2);
-            okc &= cuda_ok(cudaMemcpyAsync(&h_unconv, unconv, 4, cudaMemcpyDeviceToHost, st), "unconverged back", __FILE__, __LINE__);
+            okc = okc && dev_read_back_async((void*)h_unconv_p, unconv, 4, st);
             okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+            if (okc) h_unconv = *h_unconv_p;
             if (!h_unconv) {
                 okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
                 if (nsegs) { jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>()); count_launch(); }
                 finish_entropy();
                 run_idct();
-                okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
+                okc = okc && dev_read_back_async(status, d_status.p, sizeof(int) * m, st);
                 okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
             }
         }

@@ -696,28 +696,43 @@ __device__ inline void lz_resolve_stream_jump(uint8_t* out, uint32_t n, const ui
             }
         }
         if (__syncthreads_or(any_open ? 1 : 0)) {
-            // ---- 3. pointer jumping over the chunk, two positions per 32-bit word, in place
+            // ---- 3. pointer jumping over the chunk, two positions per 32-bit word, in place. A thread owns the pairs tid,
+            // tid + NT, ... and keeps one bit per pair: set while one of the two bytes does not point at a root yet. A
+            // pair whose two targets are roots is done for good (roots never change), so the passes get shorter.
             const uint32_t npair = (min(cend - c0, LZC_SPAN) + 1) >> 1;
             uint32_t* const ptr32 = (uint32_t*)S.ptr;
+            uint32_t act = 0;
+            {
+                uint32_t it = 0;
+                for (uint32_t i = tid; i < npair; i += NT, ++it)
+                    if (ptr32[i] != ((2 * i) | ((2 * i + 1) << 16))) act |= 1u << it;
+            }
+            const uint32_t open0 = act;
             for (int pass = 0; pass < 16; ++pass) {
                 bool changed = false;
-                for (uint32_t i = tid; i < npair; i += NT) {
+                uint32_t a = act;
+                while (a) {
+                    const uint32_t it = (uint32_t)__ffs(a) - 1;
+                    a &= a - 1;
+                    const uint32_t i = (uint32_t)tid + it * NT;
                     const uint32_t v = ptr32[i];
-                    uint32_t p0 = v & 0xffffu, p1 = v >> 16;
-                    if (v != ((2 * i) | ((2 * i + 1) << 16))) {     // at least one of the two is not final
-                        const uint32_t q0 = S.ptr[p0], q1 = S.ptr[p1];
-                        if (q0 != p0 || q1 != p1) { ptr32[i] = q0 | (q1 << 16); changed = true; }
-                    }
+                    const uint32_t p0 = v & 0xffffu, p1 = v >> 16;
+                    const uint32_t q0 = S.ptr[p0], q1 = S.ptr[p1];
+                    if (q0 != p0 || q1 != p1) { ptr32[i] = q0 | (q1 << 16); changed = true; }
+                    else act &= ~(1u << it);
                 }
                 if (!__syncthreads_or(changed ? 1 : 0)) break;
             }
-            // ---- 4. copy: every open byte from its root
-            for (uint32_t i = tid; i < npair; i += NT) {
-                const uint32_t v = ptr32[i];
-                if (v != ((2 * i) | ((2 * i + 1) << 16))) {
-                    const uint32_t p0 = v & 0xffffu, p1 = v >> 16;
-                    const uint8_t b0 = buf[p0], b1 = buf[p1];
-                    buf[2 * i] = b0; buf[2 * i + 1] = b1;            // a final byte is rewritten with itself
+            // ---- 4. copy: every open byte from its root (a final byte of an open pair is rewritten with itself)
+            {
+                uint32_t a = open0;
+                while (a) {
+                    const uint32_t it = (uint32_t)__ffs(a) - 1;
+                    a &= a - 1;
+                    const uint32_t i = (uint32_t)tid + it * NT;
+                    const uint32_t v = ptr32[i];
+                    const uint8_t b0 = buf[v & 0xffffu], b1 = buf[v >> 16];
+                    buf[2 * i] = b0; buf[2 * i + 1] = b1;
                 }
             }
             __syncthreads();

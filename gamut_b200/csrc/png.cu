@@ -344,7 +344,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         for (auto& e : ev) cudaEventCreate(&e);
         cudaEventRecord(ev[0], st);
         if (files_dev) {
-            okc &= cuda_ok(cudaMemsetAsync(d_idat.p, 0, idat_total, st), "memset", __FILE__, __LINE__);
+            okc &= dev_fill_async(d_idat.p, 0, idat_total, st);
             if (!segs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_sg.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st), "segs", __FILE__, __LINE__);
             launch_gather(d_sg.p, (int)segs.size(), st);
         } else {
@@ -359,9 +359,16 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
         launch_finish(d_fj.as<FinishJob>(), (int)fjobs.size(), max_pixels, st);
         cudaEventRecord(ev[4], st);
         std::vector<int> status((size_t)m);
-        okc &= cuda_ok(cudaMemcpyAsync(ijobs.data(), d_ij.p, sizeof(InflateJob) * m, cudaMemcpyDeviceToHost, st), "ijobs back", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+        {
+            // results come back through pinned memory written by a kernel, not through the copy engine (common.h)
+            const size_t ij_bytes = (sizeof(InflateJob) * (size_t)m + 15) & ~(size_t)15;
+            PinnedBuf h_back(ij_bytes + sizeof(int) * (size_t)m);
+            if (!h_back.p) okc = false;
+            okc = okc && dev_read_back_async(h_back.p, d_ij.p, sizeof(InflateJob) * m, st);
+            okc = okc && dev_read_back_async(h_back.as<uint8_t>() + ij_bytes, d_status.p, sizeof(int) * m, st);
+            okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+            if (okc) { memcpy(ijobs.data(), h_back.p, sizeof(InflateJob) * m); memcpy(status.data(), h_back.as<uint8_t>() + ij_bytes, sizeof(int) * m); }
+        }
         okc &= cuda_ok(cudaGetLastError(), "kernels", __FILE__, __LINE__);
         if (h_stage) pinned_free(h_stage);
         if (okc) for (int q = 0; q < 4; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }

@@ -91,9 +91,9 @@ bool launch_inflate(InflateJob* d_jobs, const InflateJob* h_jobs, int njobs, cud
     bool ok = true;
     ok &= cuda_ok(cudaMemcpyAsync(base + o_par, par.data(), sizeof(InfPar) * njobs, cudaMemcpyHostToDevice, st), "inflate par", __FILE__, __LINE__);
     ok &= cuda_ok(cudaMemcpyAsync(base + o_tiles, tile_start.data(), 4 * ((size_t)njobs + 1), cudaMemcpyHostToDevice, st), "inflate tiles", __FILE__, __LINE__);
-    ok &= cuda_ok(cudaMemsetAsync(base + o_ctr, 0, 64, st), "inflate ctr", __FILE__, __LINE__);
-    ok &= cuda_ok(cudaMemsetAsync(base + o_slots, 0xff, 4 * slots_total, st), "inflate slots", __FILE__, __LINE__);
-    ok &= cuda_ok(cudaMemsetAsync(base + o_bitmap, 0, 4 * bitmap_total, st), "inflate bitmap", __FILE__, __LINE__);
+    ok &= dev_fill_async(base + o_ctr, 0, 64, st);
+    ok &= dev_fill_async(base + o_slots, 0xff, 4 * slots_total, st);
+    ok &= dev_fill_async(base + o_bitmap, 0, 4 * bitmap_total, st);
     if (!ok) return false;
     InfPar* d_par = (InfPar*)(base + o_par);
     uint32_t* d_ctr = (uint32_t*)(base + o_ctr);

@@ -634,14 +634,14 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!pj.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_pj.p, pj.data(), sizeof(P10Image) * pj.size(), cudaMemcpyHostToDevice, st), "pj", __FILE__, __LINE__);
     if (!suball.empty()) {
         okc &= cuda_ok(cudaMemcpyAsync(d_subjobs.p, suball.data(), sizeof(SubJob) * suball.size(), cudaMemcpyHostToDevice, st), "subjobs", __FILE__, __LINE__);
-        okc &= cuda_ok(cudaMemsetAsync(d_subrows.p, 0, sub_rows_total, st), "subrows", __FILE__, __LINE__);
+        okc &= dev_fill_async(d_subrows.p, 0, sub_rows_total, st);
     }
     cudaEventRecord(ev[1], st);
     if (!lz.empty()) {
-        okc &= cuda_ok(cudaMemsetAsync(d_lzbm.p, 0, lzbm_total + 1024, st), "lz4 bitmap", __FILE__, __LINE__);
+        okc &= dev_fill_async(d_lzbm.p, 0, lzbm_total + 1024, st);
         const unsigned g = (unsigned)((lz.size() + LZ4_WARPS - 1) / LZ4_WARPS);
         const Lz4Job* dj = d_lzj.as<Lz4Job>(); const int nj = (int)lz.size();
-        okc &= cuda_ok(cudaMemsetAsync(d_lzok.p, 0, sizeof(int) * (lz.size() + 1), st), "lz4 ok", __FILE__, __LINE__);
+        okc &= dev_fill_async(d_lzok.p, 0, sizeof(int) * (lz.size() + 1), st);
         if (lz_chunks) {
             const unsigned gc = (lz_chunks + LZ4_WARPS - 1) / LZ4_WARPS;
             lz4_spec_kernel<<<gc, LZ4_WARPS * 32, 0, st>>>(dj, nj, d_lzch.as<Lz4Chunk>(), lz_chunks);
@@ -673,14 +673,15 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         const unsigned cg = (total_chunks + 127) / 128;
         p10_sync_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, dirty[1], dirty[0], 0, changed);
         count_launch();
-        for (int pass = 1;; ++pass) {
-            uint32_t h_changed = 0;
-            okc &= cuda_ok(cudaMemsetAsync(changed, 0, 4, st), "changed", __FILE__, __LINE__);
+        PinnedBuf h_chg(64);
+        if (!h_chg.p) okc = false;
+        for (int pass = 1; okc; ++pass) {
+            okc &= dev_fill_async(changed, 0, 4, st);
             p10_sync_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, dirty[(pass + 1) & 1], dirty[pass & 1], pass, changed);
             count_launch();
-            okc &= cuda_ok(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, st), "changed back", __FILE__, __LINE__);
+            okc = okc && dev_read_back_async(h_chg.p, changed, 4, st);       // a kernel store into pinned memory (common.h)
             okc &= cuda_ok(cudaStreamSynchronize(st), "sync pass", __FILE__, __LINE__);
-            if (!okc || h_changed == 0) break;
+            if (!okc || *(volatile uint32_t*)h_chg.p == 0) break;
         }
         p10_scan_kernel<<<ni, 256, 0, st>>>(dI, chunks, entries, ndec);
         p10_write_kernel<<<cg, 128, 0, st>>>(dI, ni, total_chunks, chunks, entries);
@@ -690,8 +691,13 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     }
     cudaEventRecord(ev[3], st);
     std::vector<int> status((size_t)n);
-    okc &= cuda_ok(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st), "status back", __FILE__, __LINE__);
-    okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+    {
+        PinnedBuf h_back(sizeof(int) * (size_t)n);
+        if (!h_back.p) okc = false;
+        okc = okc && dev_read_back_async(h_back.p, d_status.p, sizeof(int) * n, st);
+        okc &= cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
+        if (okc) memcpy(status.data(), h_back.p, sizeof(int) * n);
+    }
     okc &= cuda_ok(cudaGetLastError(), "kernels", __FILE__, __LINE__);
     if (h_stage) pinned_free(h_stage);
     if (okc) for (int q = 0; q < 3; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); B->phase_ms[q] += ms; }

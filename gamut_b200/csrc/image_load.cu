@@ -159,7 +159,7 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
         B = gb::jpeg_decode_batch(1, f, l, nullptr, req, st);
         if (!B || !B->images[0].status) {
             delete B;
-            return fail(gb200_jpeg_probe(data, len) > 0 ? kNoLoadSupport : kDecodingFailed);   // progressive: SURVEY 8(f3)
+            return fail(gb200_jpeg_probe(data, len) > 0 ? kNoLoadSupport : kDecodingFailed);   // non-interleaved multi-scan sequential: a valid file this path does not decode
         }
         const gb200_image_desc& D = B->images[0];
         if (D.file_channels != 1 && D.file_channels != 3 && D.file_channels != 4) { delete B; return fail(kWrongComponents); }

@@ -162,6 +162,182 @@ jpeg_huffman_kernel(const JpegImage* __restrict__ images, const Segment* __restr
     }
 }
 
+// ---- progressive (SOF2) ---------------------------------------------------------------------------------------------
+// init_progressive / decode_scan / decode_block_* (jpegload.d:3299-3684): every scan of the file refines whole-image
+// coefficient planes (one per component, DC in element 0 of each 64-coefficient block: the reference keeps DC and AC
+// in two buffers and joins them in load_next_row, :2280-2284); scans must run in file order (a refinement scan reads
+// what earlier scans wrote), and a scan is one serial bit stream, so one thread walks all the scans of one image.
+// Parallelism is across the images of a batch; the dequantisation, IDCT and colour stages are the batch-parallel
+// kernels of the sequential path (jpeg_prog_gather_kernel puts the planes into the MCU order they read).
+struct ProgImage {
+    int image;                 // index into JpegImage[]
+    int16_t* plane[3];         // [block_y][block_x][64]
+    int num_x[3], num_y[3], h[3], v[3];
+    int first_scan, nscans;
+};
+struct ProgScan {
+    int ncomp, comp[3], dc_tab[3], ac_tab[3];      // indices into the global HuffTable array
+    int ss, se, ah, al;
+    int mcus_per_row;
+    int first_seg, nsegs;      // Segment[]: one per restart interval (image = index of the ProgImage)
+};
+
+// one block of a scan; kind = (AC scan ? 2 : 0) + (refinement ? 1 : 0). Returns false on a decode error.
+__device__ __forceinline__ bool prog_block(BitReader& br, const HuffTable* __restrict__ dct, const HuffTable* __restrict__ act,
+                                           const ProgScan& sc, int kind, int16_t* __restrict__ p, int& last_dc, int& eob_run)
+{
+    const int al = sc.al;
+    if (kind == 0) {                                    // decode_block_dc_first (:3299-3320)
+        int s = huff_decode(br, dct);
+        if (s < 0 || s > 15) return false;
+        if (s != 0) { br.fill(); const int r = (int)br.get(s); s = huff_extend(r, s); }
+        last_dc = (s += last_dc);
+        p[0] = (int16_t)((uint32_t)s << al);
+        return true;
+    }
+    if (kind == 1) {                                    // decode_block_dc_refine (:3322-3333)
+        br.fill();
+        if (br.get(1)) p[0] = (int16_t)(p[0] | (1 << al));
+        return true;
+    }
+    if (kind == 2) {                                    // decode_block_ac_first (:3335-3398)
+        if (eob_run) { --eob_run; return true; }
+        for (int k = sc.ss; k <= sc.se; ++k) {
+            const int rs = huff_decode(br, act);
+            if (rs < 0) return false;
+            int r = rs >> 4, s = rs & 15;
+            if (s) {
+                if ((k += r) > 63) return false;
+                br.fill();
+                r = (int)br.get(s);
+                s = huff_extend(r, s);
+                p[c_zag[k]] = (int16_t)((uint32_t)s << al);
+            } else if (r == 15) {
+                if ((k += 15) > 63) return false;
+            } else {
+                eob_run = 1 << r;
+                if (r) { br.fill(); eob_run += (int)br.get(r); }
+                --eob_run;
+                break;
+            }
+        }
+        return true;
+    }
+    // decode_block_ac_refine (:3400-3519)
+    const int p1 = 1 << al, m1 = (int)(0xFFFFFFFFu << al);
+    int k = sc.ss;
+    if (eob_run == 0) {
+        for (; k <= sc.se; ++k) {
+            const int rs = huff_decode(br, act);
+            if (rs < 0) return false;
+            int r = rs >> 4, s = rs & 15;
+            if (s) {
+                if (s != 1) return false;
+                br.fill();
+                s = br.get(1) ? p1 : m1;
+            } else if (r != 15) {
+                eob_run = 1 << r;
+                if (r) { br.fill(); eob_run += (int)br.get(r); }
+                break;
+            }
+            do {
+                int16_t* tc = p + c_zag[k & 63];
+                if (*tc != 0) {
+                    br.fill();
+                    if (br.get(1)) { if ((*tc & p1) == 0) *tc = (int16_t)(*tc + (*tc >= 0 ? p1 : m1)); }
+                } else if (--r < 0) break;
+                ++k;
+            } while (k <= sc.se);
+            if (s && k < 64) p[c_zag[k]] = (int16_t)s;
+        }
+    }
+    if (eob_run > 0) {
+        for (; k <= sc.se; ++k) {
+            int16_t* tc = p + c_zag[k & 63];
+            if (*tc != 0) {
+                br.fill();
+                if (br.get(1)) { if ((*tc & p1) == 0) *tc = (int16_t)(*tc + (*tc >= 0 ? p1 : m1)); }
+            }
+        }
+        --eob_run;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32)
+jpeg_prog_kernel(const JpegImage* __restrict__ images, const ProgImage* __restrict__ prog, int nprog,
+                 const ProgScan* __restrict__ scans, const Segment* __restrict__ segs,
+                 const HuffTable* __restrict__ tables, int* status)
+{
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= nprog) return;
+    const ProgImage& P = prog[pi];
+    if (!status[P.image]) return;
+    const uint8_t* data = images[P.image].data;
+    for (int si = 0; si < P.nscans; ++si) {
+        const ProgScan& sc = scans[P.first_scan + si];
+        const int kind = (sc.ss ? 2 : 0) + (sc.ah ? 1 : 0);
+        for (int g = 0; g < sc.nsegs; ++g) {
+            const Segment sg = segs[sc.first_seg + g];
+            BitReader br; br.init(data, sg.start, sg.end);
+            int dc[3] = {0, 0, 0};
+            int eob_run = 0;                            // process_restart clears it with the DC predictors (:2380-2386)
+            for (int m = sg.first_mcu; m < sg.first_mcu + sg.num_mcus; ++m) {
+                const int mx = m % sc.mcus_per_row, my = m / sc.mcus_per_row;
+                for (int i = 0; i < sc.ncomp; ++i) {
+                    const int c = sc.comp[i];
+                    const int hh = sc.ncomp == 1 ? 1 : P.h[c], vv = sc.ncomp == 1 ? 1 : P.v[c];
+                    const HuffTable* dct = tables + sc.dc_tab[i];
+                    const HuffTable* act = tables + sc.ac_tab[i];
+                    for (int yo = 0; yo < vv; ++yo) {
+                        for (int xo = 0; xo < hh; ++xo) {
+                            const int bx = mx * hh + xo, by = my * vv + yo;
+                            if (bx >= P.num_x[c] || by >= P.num_y[c]) { status[P.image] = 0; return; }     // the reference asserts
+                            int16_t* p = P.plane[c] + ((size_t)by * P.num_x[c] + bx) * 64;
+                            if (!prog_block(br, dct, act, sc, kind, p, dc[c], eob_run)) { status[P.image] = 0; return; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// load_next_row (jpegload.d:2259-2332) for the whole image: one warp per block of the interleaved MCU grid copies the
+// block out of its component plane, dequantises it (quant tables in zig-zag order, products kept as 16-bit like the
+// reference's cast) and records the zig-zag extent the IDCT stage uses to pick its sparse variant.
+__global__ void __launch_bounds__(128)
+jpeg_prog_gather_kernel(const JpegImage* __restrict__ images, const ProgImage* __restrict__ prog, const uint32_t* __restrict__ blk_base,
+                        int nprog, const int* __restrict__ status)
+{
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= blk_base[nprog]) return;
+    int lo = 0, hi = nprog - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_base[mid] <= gw) lo = mid; else hi = mid - 1; }
+    const ProgImage& P = prog[lo];
+    if (!status[P.image]) return;
+    const JpegImage& im = images[P.image];
+    const uint32_t lb = gw - blk_base[lo];
+    const int bpm = im.blocks_per_mcu;
+    const int m = (int)(lb / (uint32_t)bpm), b = (int)(lb - (uint32_t)m * bpm);
+    const int c = im.mcu_org[b];
+    int j = 0;
+    for (int t = 0; t < b; ++t) j += im.mcu_org[t] == c ? 1 : 0;
+    const int mx = m % im.mcus_per_row, my = m / im.mcus_per_row;
+    const int bx = mx * P.h[c] + j % P.h[c], by = my * P.v[c] + j / P.h[c];
+    const int16_t* __restrict__ src = P.plane[c] + ((size_t)by * P.num_x[c] + bx) * 64;
+    const int k0 = lane, k1 = lane + 32;
+    const int n0 = c_zag[k0], n1 = c_zag[k1];
+    const int v0 = src[n0], v1 = src[n1];
+    const uint32_t z0 = __ballot_sync(0xffffffffu, v0 != 0) & ~1u, z1 = __ballot_sync(0xffffffffu, v1 != 0);
+    const int last = z1 ? 63 - __clz(z1) : (z0 ? 31 - __clz(z0) : 0);
+    int16_t* __restrict__ dst = im.coefs + ((size_t)m * bpm + b) * 64;
+    dst[n0] = (int16_t)(v0 * im.quant[c][k0]);
+    dst[n1] = (int16_t)(v1 * im.quant[c][k1]);
+    if (lane == 0) im.blk_zag[(size_t)m * bpm + b] = (uint8_t)(last + 1);
+}
+
 #include "jpeg_sync.cuh"
 
 // ---- IDCT -------------------------------------------------------------------------------------
@@ -669,9 +845,19 @@ struct ByteSrc {    // get_char semantics: past the end yields FF D9 FF D9 ... (
 
 struct HostHuff { bool valid = false; uint8_t num[17]; uint8_t val[256]; };
 
+struct HostScan {                // one scan of a progressive file (init_progressive, jpegload.d:3609-3671)
+    int ncomp = 0, comp[4] = {0}, dc_tab[4] = {0}, ac_tab[4] = {0};      // tables: indices into `huff` below
+    int ss = 0, se = 0, ah = 0, al = 0, restart_interval = 0;
+    int mcus_per_row = 0, mcus_per_col = 0;
+    size_t data_start = 0, data_end = 0;
+    HostHuff huff[8];            // the tables as they stood at this SOS (DHT may redefine them between scans)
+};
+
 struct Parsed {
     bool ok = false;
-    int unsupported = 0;         // 1 progressive (SOF2), 2 non-interleaved multi-scan sequential: valid JPEG, not on this path
+    int unsupported = 0;         // 2 non-interleaved multi-scan sequential: a valid JPEG that is not on this path
+    bool progressive = false;
+    std::vector<HostScan> scans;
     int width = 0, height = 0, comps = 0;
     int h_samp[4] = {0}, v_samp[4] = {0}, quant_sel[4] = {0}, ident[4] = {0};
     HostHuff huff[8];
@@ -828,8 +1014,8 @@ bool parse_jpeg(const uint8_t* data, size_t len, Parsed& P)
         if (nx != 0xFF) return false;
     }
     int c = walk_markers(s, P);
-    if (c == 0xC2) P.unsupported = 1;
-    if (c != 0xC0 && c != 0xC1) return false;      // SOF2 (progressive) and the rest: not on this path
+    if (c == 0xC2) P.progressive = true;            // locate_sof_marker (:1921-1924)
+    else if (c != 0xC0 && c != 0xC1) return false;
     // read_sof_marker (:1343-1405)
     uint32_t left = s.u16();
     if (s.next() != 8) return false;
@@ -851,6 +1037,85 @@ bool parse_jpeg(const uint8_t* data, size_t len, Parsed& P)
     {
         static const int bpm[5] = {1, 3, 4, 4, 6};
         if ((P.width + (P.scan_type == YH2V1 || P.scan_type == YH2V2 ? 15 : 7)) / (P.scan_type == YH2V1 || P.scan_type == YH2V2 ? 16 : 8) * bpm[P.scan_type] > 8192) return false;
+    }
+    if (P.progressive) {
+        // init_progressive (:3587-3684): every scan up to EOI; the geometry of the output stage is that of one
+        // interleaved scan over all components (:3675-3681)
+        const int max_h = P.h_samp[0], max_v = P.v_samp[0];
+        int h_blocks[4], v_blocks[4];
+        for (int ci = 0; ci < P.comps; ++ci) {
+            h_blocks[ci] = (((P.width * P.h_samp[ci]) + (max_h - 1)) / max_h + 7) / 8;
+            v_blocks[ci] = (((P.height * P.v_samp[ci]) + (max_v - 1)) / max_v + 7) / 8;
+        }
+        const int full_mpr = (((P.width + 7) / 8) + (max_h - 1)) / max_h, full_mpc = (((P.height + 7) / 8) + (max_v - 1)) / max_v;
+        for (;;) {
+            c = walk_markers(s, P);
+            if (c == 0xD9) break;
+            if (c != 0xDA) return false;
+            HostScan S;
+            uint32_t l2 = s.u16();
+            const int n = (int)s.next();
+            S.ncomp = n;
+            l2 -= 3;
+            if (l2 != (uint32_t)(n * 2 + 3) || n < 1 || n > 4) return false;
+            for (int i = 0; i < n; ++i) {
+                const int cc = (int)s.next(), tc = (int)s.next();
+                int ci = 0;
+                for (; ci < P.comps; ++ci) if (cc == P.ident[ci]) break;
+                if (ci >= P.comps) return false;
+                S.comp[i] = ci; S.dc_tab[i] = (tc >> 4) & 15; S.ac_tab[i] = (tc & 15) + 4;
+                l2 -= 2;
+            }
+            S.ss = (int)s.next(); S.se = (int)s.next();
+            { const uint32_t a = s.next(); S.ah = (int)(a >> 4); S.al = (int)(a & 15); }
+            l2 -= 3;
+            while (l2) { s.next(); --l2; }
+            if (s.pos > len) return false;
+            // calc_mcu_block_order for this scan (:3038-3090)
+            if (n == 1) { S.mcus_per_row = h_blocks[S.comp[0]]; S.mcus_per_col = v_blocks[S.comp[0]]; }
+            else {
+                S.mcus_per_row = full_mpr; S.mcus_per_col = full_mpc;
+                int nb = 0;
+                for (int i = 0; i < n; ++i) nb += P.h_samp[S.comp[i]] * P.v_samp[S.comp[i]];
+                if (nb > 10) return false;
+            }
+            // check_huff_tables / check_quant_tables (:2990-3035)
+            for (int i = 0; i < n; ++i) {
+                if (S.ss == 0 && (S.dc_tab[i] >= 8 || !P.huff[S.dc_tab[i]].valid)) return false;
+                if (S.se > 0 && (S.ac_tab[i] >= 8 || !P.huff[S.ac_tab[i]].valid)) return false;
+                if (P.quant_sel[S.comp[i]] >= 4 || !P.quant_valid[P.quant_sel[S.comp[i]]]) return false;
+            }
+            // the scan's own checks (:3620-3645)
+            if (S.ss > S.se || S.se > 63) return false;
+            if (S.ss == 0) { if (S.se) return false; }
+            else if (n != 1) return false;
+            if (S.ah != 0 && S.al != S.ah - 1) return false;
+            if (S.al > 13) return false;            // shifts of a 16-bit coefficient (T.81 allows 0..13)
+            for (int t = 0; t < 8; ++t) S.huff[t] = P.huff[t];
+            S.restart_interval = P.restart_interval;
+            S.data_start = s.pos;
+            // the entropy data runs up to the next marker that is neither a stuffed FF00 nor RSTn
+            size_t e = s.pos;
+            while (e + 1 < len && !(data[e] == 0xFF && data[e + 1] != 0x00 && !(data[e + 1] >= 0xD0 && data[e + 1] <= 0xD7))) ++e;
+            if (e + 1 >= len) e = len;
+            S.data_end = e;
+            s.pos = e;
+            P.scans.push_back(S);
+            if (P.scans.size() > 1024) return false;
+        }
+        // the output stage: one interleaved MCU grid over all components
+        P.comps_in_scan = P.comps;
+        for (int i = 0; i < P.comps; ++i) P.comp_list[i] = i;
+        if (P.comps == 1) { P.mcus_per_row = h_blocks[0]; P.mcus_per_col = v_blocks[0]; P.blocks_per_mcu = 1; P.mcu_org[0] = 0; }
+        else {
+            P.mcus_per_row = full_mpr; P.mcus_per_col = full_mpc;
+            P.blocks_per_mcu = 0;
+            for (int ci = 0; ci < P.comps; ++ci) { int nb = P.h_samp[ci] * P.v_samp[ci]; while (nb--) { if (P.blocks_per_mcu >= 10) return false; P.mcu_org[P.blocks_per_mcu++] = ci; } }
+        }
+        P.tiles_per_mcu = P.scan_type == YH2V2 ? 12 : P.blocks_per_mcu;
+        for (int ci = 0; ci < P.comps; ++ci) if (P.quant_sel[ci] >= 4 || !P.quant_valid[P.quant_sel[ci]]) return false;
+        P.ok = true;
+        return true;
     }
     // init_scan (:3093-3127): next SOS
     c = walk_markers(s, P);
@@ -975,20 +1240,35 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         size_t scratch = 0, lj = li;
         std::vector<size_t> coef_off, zag_off, file_off;
         size_t file_total = 0, zag_total = 0;
+        std::vector<size_t> plane_off;            // progressive images: whole-image coefficient planes after the MCU-ordered ones
+        size_t plane_total = 0;
+        auto plane_bytes = [](const Parsed& p) {
+            if (!p.progressive) return (size_t)0;
+            const int mw = p.scan_type == YH2V1 || p.scan_type == YH2V2 ? 16 : 8, mh = p.scan_type == YH1V2 || p.scan_type == YH2V2 ? 16 : 8;
+            const size_t mr = (size_t)(p.width + mw - 1) / mw, mc = (size_t)(p.height + mh - 1) / mh;   // m_max_mcus_per_row / col
+            size_t t = 0;
+            for (int c = 0; c < p.comps; ++c) t += al(mr * p.h_samp[c] * mc * p.v_samp[c] * 128);
+            return t;
+        };
         while (lj < live.size()) {
             const Parsed& p = P[live[lj]];
             size_t mcus = (size_t)p.mcus_per_row * p.mcus_per_col;
             size_t need = al(mcus * p.blocks_per_mcu * 128);
-            if (lj > li && scratch + need > SCRATCH_BUDGET) break;
+            const size_t pneed = plane_bytes(p);
+            if (lj > li && scratch + plane_total + need + pneed > SCRATCH_BUDGET) break;
             coef_off.push_back(scratch);
+            plane_off.push_back(plane_total); plane_total += pneed;
             scratch += need;
             zag_off.push_back(zag_total); zag_total += al(mcus * p.blocks_per_mcu);
             file_off.push_back(file_total); file_total += al(lens[live[lj]] + 16);
             ++lj;
         }
         const int m = (int)(lj - li);
-        DevBuf d_scratch(scratch), d_zag(zag_total + 256), d_files(files_dev ? 256 : file_total), d_status(sizeof(int) * (size_t)m);
-        if (!d_scratch.p || !d_zag.p || !d_files.p || !d_status.p) { delete B; return nullptr; }
+        DevBuf d_scratch(scratch), d_zag(zag_total + 256), d_files(files_dev ? 256 : file_total), d_status(sizeof(int) * (size_t)m),
+               d_planes(plane_total + 256);
+        if (!d_scratch.p || !d_zag.p || !d_files.p || !d_status.p || !d_planes.p) { delete B; return nullptr; }
+        std::vector<ProgImage> pimgs; std::vector<ProgScan> pscans; std::vector<Segment> psegs;
+        std::vector<uint32_t> pblk_base(1, 0);
         std::vector<JpegImage> imgs((size_t)m);
         std::vector<Segment> segs;
         std::vector<uint32_t> cta_base((size_t)m + 1, 0);     // fused IDCT+colour kernel: CTAs per image (prefix)
@@ -1007,17 +1287,19 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
             J.width = p.width; J.height = p.height; J.scan_type = p.scan_type; J.comps = p.comps;
             J.mcus_per_row = p.mcus_per_row; J.mcus_per_col = p.mcus_per_col; J.blocks_per_mcu = p.blocks_per_mcu; J.tiles_per_mcu = p.tiles_per_mcu;
             for (int b = 0; b < p.blocks_per_mcu; ++b) J.mcu_org[b] = p.mcu_org[b];
+            auto table_id = [&](const HostHuff& hh, bool is_ac) {
+                std::string key((const char*)hh.num, 17); key.append((const char*)hh.val, 256); key.push_back(is_ac ? 'A' : 'D');
+                auto it = table_ids.find(key);
+                if (it != table_ids.end()) return it->second;
+                const int id = (int)tables.size();
+                tables.emplace_back(); build_table(hh, tables.back(), !is_ac); table_ids[key] = id;
+                return id;
+            };
             for (int c = 0; c < p.comps; ++c) {
                 memcpy(J.quant[c], p.quant[p.quant_sel[c]], 128);
-                for (int which = 0; which < 2; ++which) {
-                    const HostHuff& hh = p.huff[which ? p.ac_tab[c] : p.dc_tab[c]];
-                    std::string key((const char*)hh.num, 17); key.append((const char*)hh.val, 256); key.push_back(which ? 'A' : 'D');
-                    auto it = table_ids.find(key);
-                    int id;
-                    if (it == table_ids.end()) { id = (int)tables.size(); tables.emplace_back(); build_table(hh, tables.back(), which == 0); table_ids[key] = id; }
-                    else id = it->second;
-                    (which ? J.ac_tab[c] : J.dc_tab[c]) = id;
-                }
+                if (p.progressive) continue;                  // tables belong to the scans
+                for (int which = 0; which < 2; ++which)
+                    (which ? J.ac_tab[c] : J.dc_tab[c]) = table_id(p.huff[which ? p.ac_tab[c] : p.dc_tab[c]], which != 0);
             }
             J.coefs = (int16_t*)(d_scratch.as<uint8_t>() + coef_off[k]);
             J.blk_zag = d_zag.as<uint8_t>() + zag_off[k];
@@ -1030,8 +1312,58 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
                 const int NM = p.scan_type == YH2V2 ? 16 : 32;
                 cta_base[k + 1] = cta_base[k] + (uint32_t)((p.mcus_per_row + NM - 1) / NM) * (uint32_t)p.mcus_per_col;
             }
-            // segments: the whole scan, or one per restart interval (process_restart, :2335-2402)
             const uint8_t* f = files[i]; const size_t flen = lens[i];
+            if (p.progressive) {
+                // whole-image coefficient planes (coeff_buf_open, :3601-3604) and the scans that fill them
+                ProgImage PI; memset(&PI, 0, sizeof(PI));
+                PI.image = k; PI.first_scan = (int)pscans.size(); PI.nscans = (int)p.scans.size();
+                const int mw = p.scan_type == YH2V1 || p.scan_type == YH2V2 ? 16 : 8, mh = p.scan_type == YH1V2 || p.scan_type == YH2V2 ? 16 : 8;
+                const int mr = (p.width + mw - 1) / mw, mc = (p.height + mh - 1) / mh;
+                size_t off = plane_off[k];
+                for (int c = 0; c < p.comps; ++c) {
+                    PI.h[c] = p.h_samp[c]; PI.v[c] = p.v_samp[c];
+                    PI.num_x[c] = mr * p.h_samp[c]; PI.num_y[c] = mc * p.v_samp[c];
+                    PI.plane[c] = (int16_t*)(d_planes.as<uint8_t>() + off);
+                    off += al((size_t)PI.num_x[c] * PI.num_y[c] * 128);
+                }
+                for (const HostScan& hs : p.scans) {
+                    ProgScan S; memset(&S, 0, sizeof(S));
+                    S.ncomp = hs.ncomp; S.ss = hs.ss; S.se = hs.se; S.ah = hs.ah; S.al = hs.al; S.mcus_per_row = hs.mcus_per_row;
+                    for (int q = 0; q < hs.ncomp && q < 3; ++q) {
+                        S.comp[q] = hs.comp[q];
+                        S.dc_tab[q] = hs.ss == 0 ? table_id(hs.huff[hs.dc_tab[q]], false) : 0;
+                        S.ac_tab[q] = hs.se > 0 ? table_id(hs.huff[hs.ac_tab[q]], true) : 0;
+                    }
+                    S.first_seg = (int)psegs.size();
+                    // one segment per restart interval (process_restart, :2335-2402), the whole scan without DRI
+                    const int scan_mcus = hs.mcus_per_row * hs.mcus_per_col;
+                    if (!hs.restart_interval) psegs.push_back(Segment{(int)pimgs.size(), (uint32_t)hs.data_start, (uint32_t)hs.data_end, 0, scan_mcus});
+                    else {
+                        size_t pos = hs.data_start; int mcu = 0, expect = 0; bool bad = false;
+                        while (mcu < scan_mcus) {
+                            const int cnt = std::min(hs.restart_interval, scan_mcus - mcu);
+                            size_t e = pos;
+                            while (e + 1 < hs.data_end && !(f[e] == 0xFF && f[e + 1] != 0x00)) ++e;
+                            if (e + 1 >= hs.data_end) e = hs.data_end;
+                            psegs.push_back(Segment{(int)pimgs.size(), (uint32_t)pos, (uint32_t)e, mcu, cnt});
+                            mcu += cnt;
+                            if (mcu >= scan_mcus) break;
+                            size_t q = e;
+                            while (q < hs.data_end && f[q] == 0xFF) ++q;
+                            if (q >= hs.data_end || q == e || f[q] != (uint8_t)(0xD0 + expect)) { bad = true; break; }
+                            expect = (expect + 1) & 7;
+                            pos = q + 1;
+                        }
+                        if (bad) host_fail[k] = 1;
+                    }
+                    S.nsegs = (int)psegs.size() - S.first_seg;
+                    pscans.push_back(S);
+                }
+                pimgs.push_back(PI);
+                pblk_base.push_back(pblk_base.back() + (uint32_t)total_mcus * (uint32_t)p.blocks_per_mcu);
+                continue;
+            }
+            // segments: the whole scan, or one per restart interval (process_restart, :2335-2402)
             if (!p.restart_interval) segs.push_back(Segment{k, (uint32_t)p.scan_start, (uint32_t)flen, 0, total_mcus});
             else {
                 size_t pos = p.scan_start; int mcu = 0, expect = 0; bool bad = false;
@@ -1107,7 +1439,29 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
             const size_t bytes = (k + 1 < m ? coef_off[k + 1] : scratch) - coef_off[k];
             okc &= dev_fill_async(d_scratch.as<uint8_t>() + coef_off[k], 0, bytes, st);
         }
+        // progressive images: scan tables up, planes cleared, one thread per image through all its scans, then the
+        // planes are dequantised into the MCU order of the sequential path
+        const int nprog = (int)pimgs.size();
+        DevBuf d_pimgs(sizeof(ProgImage) * ((size_t)nprog + 1)), d_pscans(sizeof(ProgScan) * (pscans.size() + 1)),
+               d_psegs(sizeof(Segment) * (psegs.size() + 1)), d_pblk(sizeof(uint32_t) * ((size_t)nprog + 2));
+        if (!d_pimgs.p || !d_pscans.p || !d_psegs.p || !d_pblk.p) okc = false;
+        if (nprog && okc) {
+            okc &= cuda_ok(cudaMemcpyAsync(d_pimgs.p, pimgs.data(), sizeof(ProgImage) * nprog, cudaMemcpyHostToDevice, st), "prog images", __FILE__, __LINE__);
+            if (!pscans.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_pscans.p, pscans.data(), sizeof(ProgScan) * pscans.size(), cudaMemcpyHostToDevice, st), "prog scans", __FILE__, __LINE__);
+            if (!psegs.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_psegs.p, psegs.data(), sizeof(Segment) * psegs.size(), cudaMemcpyHostToDevice, st), "prog segments", __FILE__, __LINE__);
+            okc &= cuda_ok(cudaMemcpyAsync(d_pblk.p, pblk_base.data(), sizeof(uint32_t) * pblk_base.size(), cudaMemcpyHostToDevice, st), "prog blocks", __FILE__, __LINE__);
+        }
+        auto run_prog = [&]() {
+            if (!nprog || !okc) return;
+            okc &= dev_fill_async(d_planes.p, 0, plane_total, st);
+            jpeg_prog_kernel<<<(nprog + 31) / 32, 32, 0, st>>>(d_imgs.as<JpegImage>(), d_pimgs.as<ProgImage>(), nprog, d_pscans.as<ProgScan>(),
+                                                             d_psegs.as<Segment>(), d_tables.as<HuffTable>(), d_status.as<int>());
+            const uint32_t nwarps = pblk_base.back();
+            if (nwarps) jpeg_prog_gather_kernel<<<(nwarps + 3) / 4, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_pimgs.as<ProgImage>(), d_pblk.as<uint32_t>(), nprog, d_status.as<int>());
+            count_launch(2);
+        };
         cudaEventRecord(ev[1], st);
+        run_prog();
         const int nsegs = (int)segs.size();
         if (nsegs) {
             jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>());
@@ -1166,6 +1520,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
             if (okc) h_unconv = *h_unconv_p;
             if (!h_unconv) {
                 okc &= cuda_ok(cudaMemcpyAsync(d_status.p, st_init.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st), "status", __FILE__, __LINE__);
+                run_prog();
                 if (nsegs) { jpeg_huffman_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(d_imgs.as<JpegImage>(), d_segs.as<Segment>(), nsegs, d_tables.as<HuffTable>(), d_status.as<int>()); count_launch(); }
                 finish_entropy();
                 run_idct();
@@ -1205,8 +1560,9 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
 
 } // namespace gb
 
-/* 0 = decodable here (baseline / extended sequential, one interleaved scan), 1 = progressive (SOF2), 2 = sequential but
- * non-interleaved multi-scan, -1 = not a JPEG this parser accepts. Header walk on the host, no GPU work. */
+/* 0 = decodable here (baseline / extended sequential with one interleaved scan, or progressive SOF2), 2 = sequential but
+ * non-interleaved multi-scan (not on this path), -1 = not a JPEG this parser accepts. (1 used to mean "progressive,
+ * unsupported" and is no longer returned.) Header walk on the host, no GPU work. */
 GB_API int gb200_jpeg_probe(const uint8_t* data, size_t len)
 {
     Parsed pp;
@@ -1237,8 +1593,7 @@ GB_API uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, 
         // a valid file of a kind this path does not decode is reported as such, so that callers can route it elsewhere
         Parsed pp;
         parse_jpeg(data, len, pp);
-        if (pp.unsupported == 1) gb::set_error("unsupported: progressive JPEG (SOF2) -- the GPU path decodes baseline / extended sequential Huffman only");
-        else if (pp.unsupported == 2) gb::set_error("unsupported: non-interleaved multi-scan sequential JPEG -- the GPU path decodes single-scan interleaved files only");
+        if (pp.unsupported == 2) gb::set_error("unsupported: non-interleaved multi-scan sequential JPEG -- the GPU path decodes single-scan interleaved files only");
         else gb::set_error("JPEG decoding failed");
         delete B; return nullptr;
     }

@@ -332,7 +332,7 @@ class Image:
             req = -1
         r = codecs.jpeg_load(data, req)
         if r is None:
-            # a valid progressive / multi-scan file is a kind this build cannot decode, not a broken one
+            # a valid non-interleaved multi-scan sequential file is a kind this build cannot decode, not a broken one
             return self.error(kStrImageFormatNoLoadSupport if codecs.jpeg_probe(data) > 0 else kStrImageDecodingFailed)
         if r.actual_comps not in (1, 3, 4):
             return self.error(kStrImageWrongComponents)

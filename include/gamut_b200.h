@@ -154,10 +154,10 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
 /* Classifies a file without decoding it (host-only marker walk): 0 = decodable by this path (baseline / extended
- * sequential Huffman, one interleaved scan), 1 = progressive (SOF2; the reference decodes these, jpegload.d:3299-3683
- * -- SURVEY 8(f3), not built), 2 = sequential but non-interleaved multi-scan, -1 = not a valid JPEG. gb200_jpeg_load
- * sets gb200_last_error() to a message starting with "unsupported:" for 1 and 2, so that callers can route those files
- * to another decoder. */
+ * sequential Huffman with one interleaved scan, or progressive SOF2 -- init_progressive, jpegload.d:3299-3683), 2 =
+ * sequential but non-interleaved multi-scan, -1 = not a valid JPEG. gb200_jpeg_load sets gb200_last_error() to a message
+ * starting with "unsupported:" for 2, so that callers can route those files to another decoder. (1 used to mean
+ * "progressive, unsupported" and is no longer returned.) */
 int gb200_jpeg_probe(const uint8_t* data, size_t len);
 
 /* ---- QOI: source/gamut/codecs/qoi.d ---- */

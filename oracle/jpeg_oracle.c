@@ -17,7 +17,7 @@
  *    tree entry (garbage on corrupt streams only);
  *  - the sparse Row!N/Col!N IDCT instantiations and P_Q!(R,C)/R_S!(R,C) are evaluated densely on the
  *    zero-filled block (algebraically identical integer expressions);
- *  - progressive (SOF2) streams are rejected (out of scope);
+ *  - progressive (SOF2) streams: restated in round 2 (init_progressive, decode_scan, load_next_row);
  *  - find_eoi (:2826-2848) is not restated (it cannot change pixels of a successful decode).
  *
  * parity: pixel values are UNPINNED by the reference (its only JPEG assertion is "issue35.jpg loads,
@@ -233,6 +233,11 @@ typedef struct {
     uint8_t *pScan_line_0, *pScan_line_1;
     int error;
     float ppiX, ppiY, par;
+    /* progressive (jpegload.d:440,470-476,3299-3683) */
+    int spectral_start, spectral_end, successive_low, successive_high, eob_run;
+    jpgd_block_t* dc_coeffs[MAX_COMPONENTS]; jpgd_block_t* ac_coeffs[MAX_COMPONENTS];
+    int coef_num_x[MAX_COMPONENTS], coef_num_y[MAX_COMPONENTS];
+    int block_y_mcu[MAX_COMPONENTS];
 } jd;
 
 /* get_char (jpegload.d:640-655): past the end, FF D9 FF D9 ... */
@@ -420,7 +425,11 @@ static int read_sos_marker(jd* d)
         d->comp_dc_tab[ci] = (c >> 4) & 15;
         d->comp_ac_tab[ci] = (c & 15) + (MAX_HUFF_TABLES >> 1);
     }
-    get_bits(d, 8); get_bits(d, 8); get_bits(d, 4); get_bits(d, 4);     /* spectral / successive: ignored when sequential */
+    d->spectral_start = (int)get_bits(d, 8);
+    d->spectral_end = (int)get_bits(d, 8);
+    d->successive_high = (int)get_bits(d, 4);
+    d->successive_low = (int)get_bits(d, 4);
+    if (!d->progressive) { d->spectral_start = 0; d->spectral_end = 63; }       /* :1526-1530 */
     num_left -= 3;
     while (num_left) { get_bits(d, 8); num_left--; }
     return 1;
@@ -674,27 +683,32 @@ void or_test_jpeg_ycc(int y, int cb, int cr, uint8_t* rgb, int* tables /* crr, c
 }
 
 /* fix_in_buffer + init_scan (jpegload.d:2098-2118, 3093-3127) */
-static int init_scan(jd* d)
+/* init_scan (jpegload.d:3090-3128): 1 = a scan is ready, 0 = EOI (no further scan), -1 = error */
+static int init_scan3(jd* d)
 {
     int c = process_markers(d, 0);
-    if (c < 0 || c == M_EOI || c != M_SOS) return 0;
-    if (!read_sos_marker(d)) return 0;
+    if (c < 0) return -1;
+    if (c == M_EOI) return 0;
+    if (c != M_SOS) return -1;
+    if (!read_sos_marker(d)) return -1;
     calc_mcu_block_order(d);
-    if (d->error) return 0;
-    /* check_huff_tables / check_quant_tables (:2990-3035) */
+    if (d->error) return -1;
+    /* check_huff_tables / check_quant_tables (:2990-3035): a DC table is needed when the scan covers coefficient 0,
+     * an AC table when it covers any other (the reference records the error and fails later; here: at once) */
     for (int i = 0; i < d->comps_in_scan; ++i) {
         int ci = d->comp_list[i];
-        if (d->comp_dc_tab[ci] >= MAX_HUFF_TABLES || !d->huff[d->comp_dc_tab[ci]].valid) return 0;
-        if (d->comp_ac_tab[ci] >= MAX_HUFF_TABLES || !d->huff[d->comp_ac_tab[ci]].valid) return 0;
-        if (d->comp_quant[ci] >= MAX_QUANT_TABLES || !d->quant_valid[d->comp_quant[ci]]) return 0;
+        if (d->spectral_start == 0 && (d->comp_dc_tab[ci] >= MAX_HUFF_TABLES || !d->huff[d->comp_dc_tab[ci]].valid)) return -1;
+        if (d->spectral_end > 0 && (d->comp_ac_tab[ci] >= MAX_HUFF_TABLES || !d->huff[d->comp_ac_tab[ci]].valid)) return -1;
+        if (d->comp_quant[ci] >= MAX_QUANT_TABLES || !d->quant_valid[d->comp_quant[ci]]) return -1;
     }
     for (int i = 0; i < MAX_HUFF_TABLES; ++i) if (d->huff[i].valid) make_huff_table(&d->huff[i]);
     memset(d->last_dc_val, 0, sizeof(d->last_dc_val));
+    d->eob_run = 0;
     if (d->restart_interval) { d->restarts_left = d->restart_interval; d->next_restart_num = 0; }
     /* fix_in_buffer: un-read what the marker scanner pre-fetched, then prime with marker-aware reads */
     {
         size_t n = 2 + (d->bits_left >= 8) + (d->bits_left == 16);
-        if (d->pos < n || d->pos > d->len) return 0;      /* SOS at the very end of the data */
+        if (d->pos < n || d->pos > d->len) return -1;     /* SOS at the very end of the data */
         d->pos -= n;
     }
     d->bits_left = 16;
@@ -702,6 +716,7 @@ static int init_scan(jd* d)
     get_bits_nm(d, 16);
     return 1;
 }
+static int init_scan(jd* d) { return init_scan3(d) == 1; }
 
 /* process_restart (jpegload.d:2335-2402) */
 static int process_restart(jd* d)
@@ -713,6 +728,7 @@ static int process_restart(jd* d)
     if (i == 0) return 0;
     if (c != (d->next_restart_num + M_RST0)) return 0;
     memset(d->last_dc_val, 0, (size_t)d->comps_in_frame * sizeof(uint32_t));
+    d->eob_run = 0;
     d->restarts_left = d->restart_interval;
     d->next_restart_num = (d->next_restart_num + 1) & 7;
     d->bits_left = 16;
@@ -802,6 +818,194 @@ static int decode_next_row(jd* d)
     return 1;
 }
 
+/* ---- progressive (SOF2): every scan decoded into whole-image coefficient buffers, then one MCU row at a time is
+ * dequantised and transformed (jpegload.d:3274-3683, :2259-2332) ---- */
+static jpgd_block_t* dc_getp(jd* d, int c, int bx, int by) { return d->dc_coeffs[c] + ((size_t)by * d->coef_num_x[c] + bx); }
+static jpgd_block_t* ac_getp(jd* d, int c, int bx, int by) { return d->ac_coeffs[c] + ((size_t)by * d->coef_num_x[c] + bx) * 64; }
+static inline int shl(int v, int n) { return (int)((unsigned)v << n); }
+
+/* decode_block_dc_first (:3299-3320) */
+static int decode_block_dc_first(jd* d, int c, int bx, int by)
+{
+    jpgd_block_t* p = dc_getp(d, c, bx, by);
+    int s = huff_decode(d, &d->huff[d->comp_dc_tab[c]]);
+    if (s < 0 || s > 15) return 0;
+    if (s != 0) { int r = (int)get_bits_nm(d, s); s = huff_extend(r, s); }
+    d->last_dc_val[c] = (uint32_t)(s += (int)d->last_dc_val[c]);
+    p[0] = (jpgd_block_t)shl(s, d->successive_low);
+    return 1;
+}
+/* decode_block_dc_refine (:3322-3333) */
+static int decode_block_dc_refine(jd* d, int c, int bx, int by)
+{
+    if (get_bits_nm(d, 1)) { jpgd_block_t* p = dc_getp(d, c, bx, by); p[0] = (jpgd_block_t)(p[0] | (1 << d->successive_low)); }
+    return 1;
+}
+/* decode_block_ac_first (:3335-3398) */
+static int decode_block_ac_first(jd* d, int c, int bx, int by)
+{
+    if (d->eob_run) { d->eob_run--; return 1; }
+    jpgd_block_t* p = ac_getp(d, c, bx, by);
+    for (int k = d->spectral_start; k <= d->spectral_end; k++) {
+        int s = huff_decode(d, &d->huff[d->comp_ac_tab[c]]);
+        if (s < 0) return 0;
+        int r = s >> 4;
+        s &= 15;
+        if (s) {
+            if ((k += r) > 63) return 0;
+            r = (int)get_bits_nm(d, s);
+            s = huff_extend(r, s);
+            p[g_ZAG[k]] = (jpgd_block_t)shl(s, d->successive_low);
+        } else {
+            if (r == 15) { if ((k += 15) > 63) return 0; }
+            else {
+                d->eob_run = 1 << r;
+                if (r) d->eob_run += (int)get_bits_nm(d, r);
+                d->eob_run--;
+                break;
+            }
+        }
+    }
+    return 1;
+}
+/* decode_block_ac_refine (:3400-3519) */
+static int decode_block_ac_refine(jd* d, int c, int bx, int by)
+{
+    const int p1 = 1 << d->successive_low, m1 = shl(-1, d->successive_low);
+    jpgd_block_t* p = ac_getp(d, c, bx, by);
+    int k = d->spectral_start;
+    if (d->eob_run == 0) {
+        for (; k <= d->spectral_end; k++) {
+            int s = huff_decode(d, &d->huff[d->comp_ac_tab[c]]);
+            if (s < 0) return 0;
+            int r = s >> 4;
+            s &= 15;
+            if (s) {
+                if (s != 1) return 0;
+                s = get_bits_nm(d, 1) ? p1 : m1;
+            } else if (r != 15) {
+                d->eob_run = 1 << r;
+                if (r) d->eob_run += (int)get_bits_nm(d, r);
+                break;
+            }
+            do {
+                jpgd_block_t* this_coef = p + g_ZAG[k & 63];
+                if (*this_coef != 0) {
+                    if (get_bits_nm(d, 1)) {
+                        if ((*this_coef & p1) == 0) *this_coef = (jpgd_block_t)(*this_coef + (*this_coef >= 0 ? p1 : m1));
+                    }
+                } else if (--r < 0) break;
+                k++;
+            } while (k <= d->spectral_end);
+            if (s && k < 64) p[g_ZAG[k]] = (jpgd_block_t)s;
+        }
+    }
+    if (d->eob_run > 0) {
+        for (; k <= d->spectral_end; k++) {
+            jpgd_block_t* this_coef = p + g_ZAG[k & 63];
+            if (*this_coef != 0) {
+                if (get_bits_nm(d, 1)) {
+                    if ((*this_coef & p1) == 0) *this_coef = (jpgd_block_t)(*this_coef + (*this_coef >= 0 ? p1 : m1));
+                }
+            }
+        }
+        d->eob_run--;
+    }
+    return 1;
+}
+typedef int (*decode_block_fn)(jd*, int, int, int);
+/* decode_scan (:3521-3585) */
+static int decode_scan(jd* d, decode_block_fn fn)
+{
+    int block_x_mcu[MAX_COMPONENTS], block_y_mcu[MAX_COMPONENTS];
+    memset(block_y_mcu, 0, sizeof(block_y_mcu));
+    for (int mcu_col = 0; mcu_col < d->mcus_per_col; mcu_col++) {
+        memset(block_x_mcu, 0, sizeof(block_x_mcu));
+        for (int mcu_row = 0; mcu_row < d->mcus_per_row; mcu_row++) {
+            int xo = 0, yo = 0;
+            if (d->restart_interval && d->restarts_left == 0) { if (!process_restart(d)) return 0; }
+            for (int mcu_block = 0; mcu_block < d->blocks_per_mcu; mcu_block++) {
+                const int c = d->mcu_org[mcu_block];
+                if (block_x_mcu[c] + xo >= d->coef_num_x[c] || block_y_mcu[c] + yo >= d->coef_num_y[c]) return 0;   /* the reference asserts */
+                if (!fn(d, c, block_x_mcu[c] + xo, block_y_mcu[c] + yo)) return 0;
+                if (d->comps_in_scan == 1) block_x_mcu[c]++;
+                else if (++xo == d->comp_h_samp[c]) {
+                    xo = 0;
+                    if (++yo == d->comp_v_samp[c]) { yo = 0; block_x_mcu[c] += d->comp_h_samp[c]; }
+                }
+            }
+            d->restarts_left--;
+        }
+        if (d->comps_in_scan == 1) block_y_mcu[d->comp_list[0]]++;
+        else for (int n = 0; n < d->comps_in_scan; n++) { const int c = d->comp_list[n]; block_y_mcu[c] += d->comp_v_samp[c]; }
+    }
+    return 1;
+}
+/* init_progressive (:3587-3684) */
+static int init_progressive(jd* d)
+{
+    if (d->comps_in_frame == 4) return 0;
+    for (int i = 0; i < d->comps_in_frame; i++) {
+        d->coef_num_x[i] = d->max_mcus_per_row * d->comp_h_samp[i];
+        d->coef_num_y[i] = d->max_mcus_per_col * d->comp_v_samp[i];
+        const size_t nb = (size_t)d->coef_num_x[i] * d->coef_num_y[i];
+        d->dc_coeffs[i] = (jpgd_block_t*)calloc(nb, sizeof(jpgd_block_t));
+        d->ac_coeffs[i] = (jpgd_block_t*)calloc(nb * 64, sizeof(jpgd_block_t));
+        if (!d->dc_coeffs[i] || !d->ac_coeffs[i]) return 0;
+    }
+    for (;;) {
+        const int si = init_scan3(d);
+        if (si < 0) return 0;
+        if (!si) break;
+        const int dc_only_scan = d->spectral_start == 0, refinement_scan = d->successive_high != 0;
+        if (d->spectral_start > d->spectral_end || d->spectral_end > 63) return 0;
+        if (dc_only_scan) { if (d->spectral_end) return 0; }
+        else if (d->comps_in_scan != 1) return 0;
+        if (refinement_scan && d->successive_low != d->successive_high - 1) return 0;
+        decode_block_fn fn = dc_only_scan ? (refinement_scan ? decode_block_dc_refine : decode_block_dc_first)
+                                          : (refinement_scan ? decode_block_ac_refine : decode_block_ac_first);
+        if (!decode_scan(d, fn)) return 0;
+        d->bits_left = 16;
+        get_bits(d, 16);
+        get_bits(d, 16);
+    }
+    d->comps_in_scan = d->comps_in_frame;
+    for (int i = 0; i < d->comps_in_frame; i++) d->comp_list[i] = i;
+    calc_mcu_block_order(d);
+    return !d->error;
+}
+/* load_next_row (:2259-2332) */
+static void load_next_row(jd* d)
+{
+    int block_x_mcu[MAX_COMPONENTS];
+    memset(block_x_mcu, 0, sizeof(block_x_mcu));
+    for (int mcu_row = 0; mcu_row < d->mcus_per_row; mcu_row++) {
+        int xo = 0, yo = 0;
+        for (int mcu_block = 0; mcu_block < d->blocks_per_mcu; mcu_block++) {
+            const int c = d->mcu_org[mcu_block];
+            const jpgd_quant_t* q = d->quant[d->comp_quant[c]];
+            jpgd_block_t* p = d->pMCU_coefficients + 64 * mcu_block;
+            const jpgd_block_t* pAC = ac_getp(d, c, block_x_mcu[c] + xo, d->block_y_mcu[c] + yo);
+            const jpgd_block_t* pDC = dc_getp(d, c, block_x_mcu[c] + xo, d->block_y_mcu[c] + yo);
+            p[0] = pDC[0];
+            memcpy(&p[1], &pAC[1], 63 * sizeof(jpgd_block_t));
+            int i;
+            for (i = 63; i > 0; i--) if (p[g_ZAG[i]]) break;
+            d->mcu_block_max_zag[mcu_block] = i + 1;
+            for (; i >= 0; i--) if (p[g_ZAG[i]]) p[g_ZAG[i]] = (jpgd_block_t)(p[g_ZAG[i]] * q[i]);
+            if (d->comps_in_scan == 1) block_x_mcu[c]++;
+            else if (++xo == d->comp_h_samp[c]) {
+                xo = 0;
+                if (++yo == d->comp_v_samp[c]) { yo = 0; block_x_mcu[c] += d->comp_h_samp[c]; }
+            }
+        }
+        if (d->freq_domain_chroma_upsample) transform_mcu_expand(d, mcu_row);
+        else transform_mcu(d, mcu_row);
+    }
+    if (d->comps_in_scan == 1) d->block_y_mcu[d->comp_list[0]]++;
+    else for (int n = 0; n < d->comps_in_scan; n++) { const int c = d->comp_list[n]; d->block_y_mcu[c] += d->comp_v_samp[c]; }
+}
+
 /* colour conversion (jpegload.d:2528-2823) */
 static void H1V1Convert(jd* d)
 {
@@ -871,7 +1075,8 @@ static int decode_line(jd* d, const uint8_t** pScan_line)
 {
     if (d->total_lines_left == 0) return 1;
     if (d->mcu_lines_left == 0) {
-        if (!decode_next_row(d)) return -1;
+        if (d->progressive) load_next_row(d);              /* decode (:555-563) */
+        else if (!decode_next_row(d)) return -1;
         d->mcu_lines_left = d->max_mcu_y_size;
     }
     if (d->freq_domain_chroma_upsample) { expanded_convert(d); *pScan_line = d->pScan_line_0; }
@@ -890,7 +1095,11 @@ static int decode_line(jd* d, const uint8_t** pScan_line)
     return 0;
 }
 
-static void jd_free(jd* d) { free(d->pScan_line_0); free(d->pScan_line_1); free(d->pMCU_coefficients); free(d->pSample_buf); }
+static void jd_free(jd* d)
+{
+    free(d->pScan_line_0); free(d->pScan_line_1); free(d->pMCU_coefficients); free(d->pSample_buf);
+    for (int i = 0; i < MAX_COMPONENTS; ++i) { free(d->dc_coeffs[i]); free(d->ac_coeffs[i]); }
+}
 
 /* decompress_jpeg_image_from_stream (jpegload.d:3720-3808) */
 uint8_t* or_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* width, int* height,
@@ -910,15 +1119,18 @@ uint8_t* or_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* width
     if (!locate_soi_marker(d)) goto fail;
     {
         int c = process_markers(d, 0);
-        if (c == M_SOF2) goto fail;                         /* progressive: out of scope */
-        if (c != M_SOF0 && c != M_SOF1) goto fail;
+        if (c == M_SOF2) d->progressive = 1;                /* locate_sof_marker (:1921-1924) */
+        else if (c != M_SOF0 && c != M_SOF1) goto fail;
         if (!read_sof_marker(d)) goto fail;
     }
     *width = d->image_x_size; *height = d->image_y_size; *actual_comps = d->comps_in_frame;
     if (req_comps < 0) req_comps = d->comps_in_frame;
     if (!init_frame(d)) goto fail;
-    if (!init_scan(d)) goto fail;
-    if (d->comps_in_scan != d->comps_in_frame) goto fail;   /* non-interleaved multi-scan baseline: unsupported */
+    if (d->progressive) { if (!init_progressive(d)) goto fail; }     /* decode_start (:3696-3706) */
+    else {
+        if (!init_scan(d)) goto fail;
+        if (d->comps_in_scan != d->comps_in_frame) goto fail;   /* non-interleaved multi-scan baseline: unsupported */
+    }
     {
         const int W = d->image_x_size, H = d->image_y_size;
         const int dst_bpl = W * req_comps;

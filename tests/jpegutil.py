@@ -22,10 +22,12 @@ def photo(h, w, c, seed):
     return (np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8)
 
 
-def encode(img, quality=90, subsampling=0, restart_rows=0, restart_blocks=0, optimize=False, dpi=None):
+def encode(img, quality=90, subsampling=0, restart_rows=0, restart_blocks=0, optimize=False, dpi=None, progressive=False):
     b = io.BytesIO()
     im = PILImage.fromarray(img if img.shape[2] != 1 else img[:, :, 0])
     kw = dict(quality=quality, optimize=optimize)
+    if progressive:
+        kw["progressive"] = True
     if img.shape[2] == 3:
         kw["subsampling"] = subsampling
     if restart_rows:

@@ -103,32 +103,58 @@ def test_optimized_huffman_and_density(codecs, oracle):
 
 def test_failures(codecs, oracle):
     img = photo(40, 40, 3, 2)
-    b = io.BytesIO()
-    PILImage.fromarray(img).save(b, "JPEG", progressive=True)
-    check(codecs, oracle, b.getvalue())
     data = encode(img, 90, 2)
     check(codecs, oracle, data[:200])
     check(codecs, oracle, b"\xff\xd8\xff\xd9")
 
 
-def test_progressive_is_reported_as_unsupported(codecs, gb):
-    """A valid progressive (SOF2) file is not on this path: the load fails with a message that starts
-    with "unsupported:", gb200_jpeg_probe classifies it, and Image.loadFromMemory reports "Cannot decode this image
-    format in this build" instead of "Image decoding failed" -- callers can route such files elsewhere."""
-    from gamut_b200 import _lib
-    from gamut_b200.image import Image, kStrImageFormatNoLoadSupport, kStrImageDecodingFailed
-    img = photo(40, 40, 3, 2)
-    b = io.BytesIO()
-    PILImage.fromarray(img).save(b, "JPEG", progressive=True)
-    prog = b.getvalue()
-    assert codecs.jpeg_probe(prog) == 1 and codecs.jpeg_probe(encode(img, 90, 2)) == 0 and codecs.jpeg_probe(b"nope") == -1
-    assert codecs.jpeg_load(prog, -1) is None
-    assert _lib.last_error().startswith("unsupported: progressive JPEG")
+def test_progressive(codecs, oracle):
+    """Progressive files (SOF2; init_progressive / decode_scan / load_next_row, jpegload.d:3299-3683, :2259-2332):
+    bit-exact against the oracle for every subsampling, grey, optimised tables, restart intervals inside the scans,
+    every req_comps; the probe classifies them as decodable."""
+    for (h, w, c, ss, q, kw) in ((48, 64, 3, 2, 90, {}), (77, 130, 3, 0, 75, {}), (150, 200, 3, 1, 85, {}), (61, 97, 1, 0, 90, {}),
+                                  (250, 333, 3, 2, 95, {"optimize": True}), (256, 256, 3, 2, 50, {"restart_blocks": 7}),
+                                  (173, 211, 3, 1, 80, {"restart_rows": 2}), (9, 7, 3, 2, 60, {}), (8, 8, 1, 0, 100, {})):
+        data = encode(photo(h, w, c, 3 + h), q, ss, progressive=True, **kw)
+        assert data.count(b"\xff\xda") > 1 and codecs.jpeg_probe(data) == 0
+        check(codecs, oracle, data)
+    data = encode(photo(40, 56, 3, 9), 85, 2, progressive=True)
+    for rc in (1, 3, 4):
+        check(codecs, oracle, data, rc)
+    assert codecs.jpeg_probe(b"nope") == -1
+
+
+def test_progressive_corrupt(codecs, oracle):
+    """Truncated and inconsistent progressive files: same accept / reject decision and the same pixels as the oracle."""
+    prog = encode(photo(40, 40, 3, 2), 90, 2, progressive=True)
+    for cut in (200, len(prog) // 2, len(prog) - 3):
+        check(codecs, oracle, prog[:cut])
+    i = prog.rindex(b"\xff\xda")
+    n = int.from_bytes(prog[i + 2:i + 4], "big")
+    bad = bytearray(prog)
+    bad[i + 2 + n - 1] = 0x31
+    check(codecs, oracle, bytes(bad))
+
+
+def test_progressive_batch_and_image(codecs, oracle, gb):
+    """A batch that mixes progressive and sequential files, and Image.loadFromMemory on a progressive file."""
+    from gamut_b200.image import Image
+    files = [encode(photo(64, 48, 3, 1), 90, 2, progressive=True), encode(photo(64, 48, 3, 1), 90, 2),
+             encode(photo(33, 65, 1, 2), 70, progressive=True), b"nope", encode(photo(120, 90, 3, 4), 80, 1, progressive=True)]
+    b = codecs.jpeg_decode_batch(files, 4)
+    try:
+        for i, f in enumerate(files):
+            exp = oracle.jpeg_load(f, 4)
+            got = b.to_host(i)
+            if exp is None:
+                assert got is None and b.images[i].status == 0
+            else:
+                assert np.array_equal(got, exp[0])
+    finally:
+        b.free()
     im = Image()
-    im.loadFromMemory(prog)
-    assert im.isError() and im.errorMessage() == kStrImageFormatNoLoadSupport
-    im.loadFromMemory(b"\xff\xd8\xff\xd9")
-    assert im.isError() and im.errorMessage() == kStrImageDecodingFailed
+    im.loadFromMemory(files[0])
+    assert not im.isError() and im.width() == 48 and im.height() == 64
 
 
 def test_batch_mixed(codecs, oracle):

@@ -79,10 +79,52 @@ def test_density_and_nan_without_jfif(oracle):
     assert math.isnan(par) and math.isnan(dpi)
 
 
-def test_progressive_and_truncated(oracle):
+def test_progressive_equals_baseline(oracle):
+    """Progressive (SOF2, jpegload.d:3299-3683) and sequential files written by libjpeg from the same pixels with the
+    same quality hold the same quantised coefficients (progressive mode only changes the entropy coding), so the
+    restated progressive path (10 scans: DC first/refine, AC first/refine with EOB runs) must reproduce the pixels of
+    the sequential path -- which is pinned to the reference's source text -- exactly. Every subsampling, grey,
+    optimised tables, restart intervals inside the scans."""
+    for (h, w, c, ss, q, kw) in ((48, 64, 3, 2, 90, {}), (77, 130, 3, 0, 75, {}), (150, 200, 3, 1, 85, {}), (61, 97, 1, 0, 90, {}),
+                                  (250, 333, 3, 2, 95, {"optimize": True}), (256, 256, 3, 2, 50, {"restart_blocks": 7}),
+                                  (173, 211, 3, 1, 80, {"restart_rows": 2}), (9, 7, 3, 2, 60, {}), (8, 8, 1, 0, 100, {})):
+        img = photo(h, w, c, 3 + h)
+        base = oracle.jpeg_load(encode(img, q, ss, **kw), -1)
+        prog_file = encode(img, q, ss, progressive=True, **kw)
+        assert prog_file.count(b"\xff\xda") > 1
+        prog = oracle.jpeg_load(prog_file, -1)
+        assert base is not None and prog is not None
+        assert prog[1:] == base[1:]
+        assert np.array_equal(np.asarray(prog[0]), np.asarray(base[0])), (h, w, c, ss)
+    # channel adaptation on the progressive path
+    f = encode(photo(40, 56, 3, 9), 85, 2, progressive=True)
+    for rc in (1, 3, 4):
+        assert np.array_equal(np.asarray(oracle.jpeg_load(f, rc)[0]), np.asarray(oracle.jpeg_load(encode(photo(40, 56, 3, 9), 85, 2), rc)[0]))
+
+
+def test_progressive_against_libjpeg(oracle):
+    """Independent sanity check of the progressive entropy layer: libjpeg-turbo's own decode of the same file (it runs
+    the same LL&M IDCT in the other pass order; 4:2:0 chroma is upsampled differently)."""
+    for (c, ss, tol) in ((1, 0, 1), (3, 0, 4), (3, 2, 60)):
+        data = encode(photo(72, 88, c, 5), 90, ss, progressive=True)
+        px = np.asarray(oracle.jpeg_load(data, -1)[0])
+        ref = np.asarray(PILImage.open(io.BytesIO(data)))
+        assert np.abs(px.reshape(ref.shape).astype(int) - ref.astype(int)).max() <= tol
+
+
+def test_progressive_corrupt_and_truncated(oracle):
     img = photo(40, 40, 3, 2)
-    b = io.BytesIO()
-    PILImage.fromarray(img).save(b, "JPEG", progressive=True)
-    assert oracle.jpeg_load(b.getvalue(), -1) is None           # SOF2: out of scope on this path
+    prog = encode(img, 90, 2, progressive=True)
+    # cut inside the first scan: the missing scans simply never refine the coefficients; the data that is there runs
+    # into the FF D9 padding of get_char (jpegload.d:640-655) and decodes as 1-bits -- an image comes back or the
+    # decode fails, but nothing crashes
+    for cut in (200, len(prog) // 2, len(prog) - 3):
+        oracle.jpeg_load(prog[:cut], -1)
+    # a refinement scan whose successive-approximation pair is inconsistent is rejected (:3637-3641)
+    i = prog.rindex(b"\xff\xda")
+    n = int.from_bytes(prog[i + 2:i + 4], "big")
+    bad = bytearray(prog)
+    bad[i + 2 + n - 1] = 0x31                 # Ah = 3, Al = 1
+    assert oracle.jpeg_load(bytes(bad), -1) is None
     data = encode(img, 90, 2)
     assert oracle.jpeg_load(data[:200], -1) is None

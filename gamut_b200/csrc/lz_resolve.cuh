@@ -749,6 +749,14 @@ __device__ inline void lz_resolve_stream_jump(uint8_t* out, uint32_t n, const ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Measured and not kept (round 2): the same resolver with the chunk traffic on the TMA -- cp.async.bulk + mbarrier
+// prefetch of chunk c+1 into a second buffer while chunk c jumps pointers, one cp.async.bulk.global.shared write-back
+// per chunk, far sources of the previous chunk served from shared memory. 49.0 ms against 45.0 ms per 1024 streams:
+// the kernel is bound by instruction issue (57 % issue-active with all 1024 CTAs resident, profiles/r2_resolve_*), not
+// by the latency of the chunk load, so hiding that latency buys nothing and the second buffer costs a resident CTA
+// per SM.
+
+// ---------------------------------------------------------------------------------------------------------------------
 // CTA-wide resolver: one thread per match, exact dependencies. Used where a batch has FEW streams (QOIX: one LZ4 block
 // per image, 256 images per GPU), so that a stream gets 16 warps instead of one.
 // The chunk sits in shared memory with a finality bit per byte (literals final, match destinations open); the matches

@@ -489,7 +489,8 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
 
         stage(0);
         stage(1);
-        uint32_t cur = 0, left = 0, upleft = 0;
+        uint32_t cur = 0, upleft = 0;
+        const uint32_t npx_live = valid ? npx : 0u;
         const uint32_t* const inrow = &S->in[lane][0];
         const uint32_t* const inbnd = &S->in[32][0];
         uint32_t* const outrow = &S->out[lane][0];
@@ -513,12 +514,15 @@ __device__ void unfilter4_cta(const UnfilterJob& J, int* status, U4Smem* S, vola
                 const uint32_t w1 = s2 + 1 < U4_CH ? ip[s2 + 1] : inrow[(cb + U4_CH) & (U4_INW - 1)];
                 const uint32_t raw = __funnelshift_r(w0, w1, sh);
                 w0 = w1;
-                const uint32_t L = x == 0 ? 0u : left, UL = x == 0 ? 0u : upleft;
-                uint32_t pred = (L & mS) | (up & mU);
-                if (anyA) pred |= __vhaddu4(L, up) & mA;
-                if (anyP) pred |= paeth4(L, up, UL) & mP;
+                // no special case for the first pixel of a row: `cur` (= the pixel to the left, and what the lane below
+                // receives as its pixel above) only changes on a lane's active steps and starts the band at 0, so at
+                // x == 0 both the left and the upper-left pixel read 0, as stbi__create_png_image_raw has it
+                // (stbdec.d:1444-1466); one unsigned compare covers x < 0, x >= npx and rows past the image
+                uint32_t pred = (cur & mS) | (up & mU);
+                if (anyA) pred |= __vhaddu4(cur, up) & mA;
+                if (anyP) pred |= paeth4(cur, up, upleft) & mP;
                 const uint32_t nv = __vadd4(raw, pred);
-                if (valid && (uint32_t)x < npx) { cur = nv; left = nv; }
+                if ((uint32_t)x < npx_live) cur = nv;
                 op[s2] = nv;
                 upleft = up;
             }

@@ -73,6 +73,11 @@ def _L():
         L.gb200_qoix_decode_batch.restype = vp
         L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         L.gb200_jpeg_probe.argtypes = [C.c_char_p, sz]
+        L.gb200_bmp_load.restype = vp
+        L.gb200_bmp_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp, fp]
+        L.gb200_bmp_decode_batch.restype = vp
+        L.gb200_bmp_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
+        L.gb200_identify_format.argtypes = [C.c_char_p, sz]
         L.gb200_image_load.argtypes = [C.c_char_p, sz, i32, C.POINTER(LoadedImage)]
         L.gb200_decode_batch_host.argtypes = [i32, i32, C.POINTER(C.c_char_p), C.POINTER(sz), i32, i32, vp, sz,
                                               C.POINTER(ImageDesc), i32]
@@ -286,6 +291,33 @@ def decode_batch_host(fmt: int, files: Sequence[bytes], arg: int, want16: int, d
     _lib.check(_L().gb200_decode_batch_host(int(fmt), n, arr, lens, arg, want16, dst_host, dst_stride, descs, sub_batch),
                "decode_batch_host")
     return [descs[i] for i in range(n)]
+
+
+def bmp_load(data: bytes, req_comp: int = 0) -> Optional[PngResult]:
+    """stbi_load_from_callbacks on a BMP file (stbdec.d:2263), as plugins/bmp.d:112 calls it."""
+    L = _L()
+    w, h, comp = C.c_int(), C.c_int(), C.c_int()
+    px, py, pr = C.c_float(), C.c_float(), C.c_float()
+    p = L.gb200_bmp_load(data, len(data), req_comp, C.byref(w), C.byref(h), C.byref(comp), C.byref(px), C.byref(py), C.byref(pr))
+    if not p:
+        return None
+    c = req_comp if req_comp else comp.value
+    a = _take_host(p, w.value * h.value * c)
+    return PngResult(a.reshape(h.value, w.value, c), w.value, h.value, comp.value, px.value, py.value, pr.value)
+
+
+def bmp_decode_batch(files: Sequence[bytes], req_comp: int = 0, files_dev: Optional[Sequence[int]] = None,
+                     stream: int = 0) -> Batch:
+    n, arr, lens, dev = _batch_args(files, files_dev)
+    h = _L().gb200_bmp_decode_batch(n, arr, lens, dev, req_comp, stream)
+    if not h:
+        raise _lib.GamutB200Error("bmp_decode_batch: " + _lib.last_error())
+    return Batch(h)
+
+
+def identify_format(data: bytes) -> int:
+    """Image.identifyFormatFromMemory (image.d:1037-1061): ImageFormat value or -1."""
+    return int(_L().gb200_identify_format(data, len(data)))
 
 
 def image_load(data: bytes, flags: int) -> LoadedImage:

@@ -20,6 +20,8 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
                               int req_comp, int want16, cudaStream_t st);
 gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
                                int req_comps, cudaStream_t st);
+gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
+                              int req_comp, cudaStream_t st);
 gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
                                int flags, cudaStream_t st);
 gb200_batch* qoi_decode_batch1(const uint8_t* data, int size, int channels, int* file_channels, cudaStream_t st);
@@ -125,13 +127,12 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
     memset(out, 0, sizeof(*out));
     out->type = -1; out->pixelAspectRatio = -1; out->resolutionY = -1;
     auto fail = [&](const char* msg) { out->error = msg; gb::set_error("%s", msg); return 0; };
-    // ---- identifyFormatFromMemory (image.d:1037-1061; the detect procs compare magic numbers)
-    int fmt = -1;
-    if (data && len >= 2 && data[0] == 0xFF && data[1] == 0xD8) fmt = GB200_FORMAT_JPEG;
-    else if (data && len >= 8 && !memcmp(data, "\x89PNG\r\n\x1a\n", 8)) fmt = GB200_FORMAT_PNG;
-    else if (data && len >= 4 && !memcmp(data, "qoif", 4)) fmt = GB200_FORMAT_QOI;
-    else if (data && len >= 4 && !memcmp(data, "qoix", 4)) fmt = GB200_FORMAT_QOIX;
+    // ---- identifyFormatFromMemory (image.d:1037-1061) + loadFromStreamInternal (:1751-1772): an unknown format and a
+    // format without a loader are different errors
+    const int fmt = gb200_identify_format(data, len);
     if (fmt < 0) return fail(kUnidentified);
+    if (fmt != GB200_FORMAT_JPEG && fmt != GB200_FORMAT_PNG && fmt != GB200_FORMAT_QOI && fmt != GB200_FORMAT_QOIX && fmt != GB200_FORMAT_BMP)
+        return fail(kNoLoadSupport);            // DDS / TGA / GIF / JXL / SQZ: detected, no decoder in this build
     if (len > 0x7fffffffu) return fail(kDecodingFailed);
     int req = requested_components(flags);
     if (req == 0) return fail(kInvalidFlags);
@@ -173,6 +174,15 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
         B = gb::qoi_decode_batch1(data, (int)len, req, &fch, st);
         if (!B || !B->images[0].status) { delete B; return fail(kDecodingFailed); }
         type = (req ? req : fch) == 3 ? GB200_rgb8 : GB200_rgba8;
+    } else if (fmt == GB200_FORMAT_BMP) {       // plugins/bmp.d:93-163
+        if (req == -1) req = 0;
+        B = gb::bmp_decode_batch(1, f, l, nullptr, req, st);
+        if (!B || !B->images[0].status) { delete B; return fail(kDecodingFailed); }
+        const gb200_image_desc& D = B->images[0];
+        static const int t8[5] = {-1, GB200_l8, GB200_la8, GB200_rgb8, GB200_rgba8};
+        type = t8[req ? req : D.file_channels];
+        par = D.pixelAspectRatio == -1 ? -1.0f : D.pixelAspectRatio;
+        resY = D.ppmY == -1 ? -1.0f : D.ppmY / 39.37007874f;            // convertInchesToMeters(ppmY), bmp.d:134
     } else {                                    // plugins/qoix.d:64-146
         B = gb::qoix_decode_batch(1, f, l, nullptr, flags, st);
         if (!B || !B->images[0].status) { delete B; return fail(kDecodingFailed); }

@@ -231,6 +231,13 @@ class Image:
     def height(self): return self._height
     def pitchInBytes(self): return self._pitch
     def layoutConstraints(self): return self._layoutConstraints
+    def pixelAspectRatio(self): return self._pixelAspectRatio
+    def dotsPerInchY(self): return self._resolutionY            # image.d:324
+
+    def dotsPerInchX(self):                                     # image.d:314
+        if self._resolutionY == GAMUT_UNKNOWN_RESOLUTION or self._pixelAspectRatio == GAMUT_UNKNOWN_ASPECT_RATIO:
+            return GAMUT_UNKNOWN_RESOLUTION
+        return float(np.float32(self._resolutionY) * np.float32(self._pixelAspectRatio))
 
     def scanline(self, y: int) -> np.ndarray:
         """Bytes of scanline y (image.d scanptr)."""
@@ -244,18 +251,10 @@ class Image:
         dt = (np.uint8, np.uint16, np.float32)[int(self._type) % 3]
         return rows.view(dt).reshape(self._height, self._width, -1)
 
-    # -- identifyFormatFromMemory (image.d:1037-1061; detect procs plugins/*.d)
+    # -- identifyFormatFromMemory (image.d:1037-1061; the detect procs of all ten plugins, TGA last)
     @staticmethod
     def identifyFormatFromMemory(data: bytes) -> ImageFormat:
-        if data[:2] == b"\xff\xd8":
-            return ImageFormat.JPEG
-        if data[:8] == b"\x89PNG\r\n\x1a\n":
-            return ImageFormat.PNG
-        if data[:4] == b"qoif":
-            return ImageFormat.QOI
-        if data[:4] == b"qoix":
-            return ImageFormat.QOIX
-        return ImageFormat.unknown
+        return ImageFormat(codecs.identify_format(bytes(data)))
 
     def _adopt(self, px: np.ndarray, type_, pitch: int, layout: int, par: float, resY: float):
         a = np.ascontiguousarray(px).view(np.uint8).reshape(-1)
@@ -296,9 +295,31 @@ class Image:
         if fif == ImageFormat.unknown:
             self.error(kStrImageFormatUnidentified)
             return False
-        {ImageFormat.PNG: self._loadPNG, ImageFormat.JPEG: self._loadJPEG, ImageFormat.QOI: self._loadQOI,
-         ImageFormat.QOIX: self._loadQOIX}[fif](data, flags)
+        loaders = {ImageFormat.PNG: self._loadPNG, ImageFormat.JPEG: self._loadJPEG, ImageFormat.QOI: self._loadQOI,
+                   ImageFormat.QOIX: self._loadQOIX, ImageFormat.BMP: self._loadBMP}
+        if fif not in loaders:                       # plugin.loadProc is null (image.d:1766-1770)
+            self.error(kStrImageFormatNoLoadSupport)
+            return False
+        loaders[fif](data, flags)
         return self.isValid()
+
+    def _loadBMP(self, data, flags):  # plugins/bmp.d:93-163
+        req = computeRequestedImageComponents(flags)
+        if req == 0:
+            return self.error(kStrInvalidFlags)
+        if req == -1:
+            req = 0
+        r = codecs.bmp_load(data, req)
+        if r is None:
+            return self.error(kStrImageDecodingFailed)
+        comps = req if req else r.file_channels
+        if not imageIsValidSize(1, r.width, r.height):
+            return self.error(kStrImageTooLarge)
+        t = (None, _P.l8, _P.la8, _P.rgb8, _P.rgba8)[comps]
+        par = GAMUT_UNKNOWN_ASPECT_RATIO if r.pixelRatio == -1 else r.pixelRatio
+        resY = GAMUT_UNKNOWN_RESOLUTION if r.ppmY == -1 else float(np.float32(r.ppmY) / np.float32(39.37007874))  # convertInchesToMeters
+        self._adopt(r.pixels, t, r.width * comps, 0, par, resY)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
 
     def _loadPNG(self, data, flags):  # plugins/png.d:44-163
         is16 = codecs.png_is16(data)

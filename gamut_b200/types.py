@@ -54,6 +54,12 @@ class ImageFormat(enum.IntEnum):  # types.d:14-28
     PNG = 1
     QOI = 2
     QOIX = 3
+    DDS = 4
+    TGA = 5
+    GIF = 6
+    BMP = 7
+    JXL = 8
+    SQZ = 9
 
 
 # LoadFlags, types.d:141-197

@@ -38,7 +38,8 @@ enum gb200_pixel_type {
 };
 
 /* ImageFormat (types.d:14-28), only the four formats on the hot path. */
-enum gb200_image_format { GB200_FORMAT_JPEG = 0, GB200_FORMAT_PNG = 1, GB200_FORMAT_QOI = 2, GB200_FORMAT_QOIX = 3 };
+enum gb200_image_format { GB200_FORMAT_JPEG = 0, GB200_FORMAT_PNG = 1, GB200_FORMAT_QOI = 2, GB200_FORMAT_QOIX = 3,    /* ImageFormat, types.d:14-28 */
+                          GB200_FORMAT_DDS = 4, GB200_FORMAT_TGA = 5, GB200_FORMAT_GIF = 6, GB200_FORMAT_BMP = 7, GB200_FORMAT_JXL = 8, GB200_FORMAT_SQZ = 9 };
 
 /* ---- library ---- */
 int         gb200_init(void);               /* 1 if an sm_100 device is usable */
@@ -153,6 +154,19 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
                          int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
+/* ---- BMP ----
+ * stbi_load_from_callbacks on a BMP file (codecs/stbdec.d:725 -> stbi__bmp_load :2263-2466), as loadBMP calls it
+ * (plugins/bmp.d:112): 1/4/8-bit palettes, 16/32-bit bit fields, 24/32-bit BGR(A), bottom-up and top-down, OS/2 and
+ * V3/V4/V5 headers; req_comp 0 (as stored: 3 or 4) or 1..4. Returns malloc'd pixels (gb200_free) or NULL; *comp = the
+ * file's own channel count; ppm values are the header's pixels per metre (-1 unknown). */
+uint8_t* gb200_bmp_load(const uint8_t* data, size_t len, int req_comp, int* width, int* height, int* comp,
+                        float* ppmX, float* ppmY, float* pixelRatio);
+gb200_batch* gb200_bmp_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                    const uint8_t* const* files_dev, int req_comp, void* stream);
+/* Image.identifyFormatFromMemory (image.d:1037-1061): the detect procs of all ten plugins in ImageFormat order, TGA
+ * last. Returns a gb200_image_format value or -1 (unknown). Host only. */
+int gb200_identify_format(const uint8_t* data, size_t len);
+
 /* Classifies a file without decoding it (host-only marker walk): 0 = decodable by this path (baseline / extended
  * sequential Huffman with one interleaved scan, or progressive SOF2 -- init_progressive, jpegload.d:3299-3683), 2 =
  * sequential but non-interleaved multi-scan, -1 = not a valid JPEG. gb200_jpeg_load sets gb200_last_error() to a message

@@ -27,6 +27,7 @@ VERT_FLIPPED, VERT_STRAIGHT, GAPLESS, BORDER_MASK = 512, 1024, 2048, 384
 
 E_DECODE = "Image decoding failed"
 E_UNIDENT = "Unidentified image format"
+E_NOLOAD = "Cannot decode this image format in this build"
 E_FLAGS = "Invalid image decoding flags"
 E_COMPONENTS = "Invalid number of component for image"
 E_CONV = "Unsupported image pixel type conversion"
@@ -265,6 +266,23 @@ def load_from_memory(data: bytes, flags: int = 0) -> OImage:
             return im
         px, desc, t = r
         _adopt(im, px, t, desc.pitchBytes, desc.pixelAspectRatio, desc.resolutionY)
+    elif pyoracle.identify_format(data) == 7:              # plugins/bmp.d:93-163
+        if req == 0:
+            im.error = E_FLAGS
+            return im
+        if req == -1:
+            req = 0
+        r = pyoracle.bmp_load(data, req)
+        if r is None:
+            im.error = E_DECODE
+            return im
+        px, comp, ppmX, ppmY, ratio = r
+        comps = req if req else comp
+        resY = -1.0 if ppmY == -1 else float(np.float32(ppmY) / np.float32(39.37007874))
+        _adopt(im, px, (None, L8, LA8, RGB8, RGBA8)[comps], px.shape[1] * comps, -1.0 if ratio == -1 else ratio, resY)
+    elif pyoracle.identify_format(data) >= 0:              # detected, but the build has no loader for it (image.d:1766-1770)
+        im.error = E_NOLOAD
+        return im
     else:
         im.error = E_UNIDENT
         return im

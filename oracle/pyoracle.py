@@ -70,6 +70,9 @@ def lib():
         L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.or_lz4_compress_bound.argtypes = [C.c_int]
         L.or_lz4_decompress_fast.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        L.or_bmp_load.restype = C.c_void_p
+        L.or_bmp_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_float)] * 3
+        L.or_identify_format.argtypes = [C.c_char_p, C.c_size_t]
         L.or_zlib_decode.restype = C.c_void_p
         L.or_zlib_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
     return _lib
@@ -186,3 +189,21 @@ def lz4_decompress(data: bytes, orig: int):
     out = np.zeros(orig + 1, np.uint8)
     r = lib().or_lz4_decompress_fast(data + b"\0" * 16, out.ctypes.data, orig)
     return out[:orig] if r >= 0 else None
+
+
+def bmp_load(data: bytes, req_comp: int = 0):
+    """stbi_load_from_callbacks on a BMP (stbdec.d:2263): (pixels[h, w, c], file_comp, ppmX, ppmY, pixelRatio) or None."""
+    x, y, comp = C.c_int(), C.c_int(), C.c_int()
+    px, py, pr = C.c_float(), C.c_float(), C.c_float()
+    p = lib().or_bmp_load(data, len(data), req_comp, C.byref(x), C.byref(y), C.byref(comp), C.byref(px), C.byref(py), C.byref(pr))
+    if not p:
+        return None
+    c = req_comp if req_comp else comp.value
+    n = x.value * y.value * c
+    a = np.ctypeslib.as_array((C.c_uint8 * max(n, 1)).from_address(p))[:n].copy().reshape(y.value, x.value, c)
+    lib().or_free(p)
+    return a, comp.value, px.value, py.value, pr.value
+
+
+def identify_format(data: bytes) -> int:
+    return int(lib().or_identify_format(data, len(data)))

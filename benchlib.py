@@ -680,6 +680,64 @@ class JpegWorkload(_BatchDecodeWorkload):
         return nimg * W * H, times, f"{nimg} images 3840x2160 4:2:0, {threads} thread(s), one image per worker"
 
 
+class BmpWorkload(_BatchDecodeWorkload):
+    """SURVEY 8(f4), first "next" decoder: 24-bit bottom-up BMP (the common case of stbi__bmp_load's easy path),
+    3840x2160, decoded to rgb8. Not a BASELINE config: a widening row measured to the same bar."""
+    name = "BMP 24-bit decode (BGR swap + vertical flip) 3840x2160, batch 256 (SURVEY 8(f4), not a BASELINE config)"
+    W, H = 3840, 2160
+    e2e_api = "gb200_decode_batch_host(BMP): host file bytes in, rgb8 pixels in pinned host memory out; sub-batches pipelined"
+    FORMAT, E2E_ARG = 7, 0
+    kernel_names = {1: "bmp_decode_kernel"}
+    traffic_keys = {1: "bmp_decode_kernel"}
+    DISTINCT = 4
+    E2E_N = 64
+    scaling = "weak"
+
+    def __init__(self, rank, world, args):
+        self._setup(rank, world, args, 256 * world)
+        self.out_bytes = self.W * self.H * 3
+        self.kernel_bytes = {1: self.comp_bytes + self.out_bytes}      # the file in, rgb8 out
+
+    def make_files(self, seed0):
+        from PIL import Image as PILImage
+        out = []
+        for i in range(self.DISTINCT):
+            bio = io.BytesIO()
+            PILImage.fromarray(synth_photo(self.H, self.W, 3, seed0 + i), "RGB").save(bio, format="BMP")
+            out.append(bio.getvalue())
+        return out
+
+    def decode(self, files, dev, stream):
+        return self.codecs.bmp_decode_batch(files, 0, files_dev=dev, stream=stream)
+
+    def config(self):
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} 24-bit BMP (total batch {self.total}, {self.DISTINCT} distinct)",
+                "file_bytes_per_image": int(self.comp_bytes), "scaling_note": "weak: 256 images per GPU",
+                "l2": "inputs larger than L2 (every image has its own device copy)"}
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        W, H = BmpWorkload.W, BmpWorkload.H
+        w = BmpWorkload.__new__(BmpWorkload)
+        w.DISTINCT = 2
+        files = w.make_files(1000)
+        nimg = max(threads, 2) if full else 2
+        pyoracle.lib()
+
+        def work(t):
+            for i in range(t, nimg, threads):
+                assert pyoracle.bmp_load(files[i % len(files)], 0) is not None
+
+        _threads_run(work, threads)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, threads)
+            times.append(time.perf_counter() - t0)
+        return nimg * W * H, times, f"{nimg} images 3840x2160 24-bit BMP, {threads} thread(s), one image per worker"
+
+
 class QoixWorkload(_BatchDecodeWorkload):
     """BASELINE configs[4]: QOIX 10-bit LA + LZ4 decode, 2048x2048 images, batch sharded over ranks."""
     name = "QOIX 10-bit LA + LZ4 decode 2048x2048, batch 2048 sharded over ranks (BASELINE configs[4])"
@@ -844,4 +902,5 @@ def sys_path_tests():
         sys.path.insert(0, p)
 
 
-WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload, "qoi": QoiWorkload}
+WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload, "qoi": QoiWorkload,
+             "bmp": BmpWorkload}

@@ -20,6 +20,8 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
                                int req_comps, cudaStream_t st);
 gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
                                int flags, cudaStream_t st);
+gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
+                              int req_comp, cudaStream_t st);
 }
 
 GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* files, const size_t* lens, int arg, int want16,
@@ -28,7 +30,7 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
     gb::clear_error();
     if (!gb::ensure_device()) return 0;
     if (n < 0 || (n > 0 && (!files || !lens || !dst_host || !descs))) { gb::set_error("gb200_decode_batch_host: bad arguments"); return 0; }
-    if (format != GB200_FORMAT_JPEG && format != GB200_FORMAT_PNG && format != GB200_FORMAT_QOIX) {
+    if (format != GB200_FORMAT_JPEG && format != GB200_FORMAT_PNG && format != GB200_FORMAT_QOIX && format != GB200_FORMAT_BMP) {
         gb::set_error("gb200_decode_batch_host: format %d has no batched decoder", format); return 0;
     }
     if (sub_batch <= 0) {
@@ -40,6 +42,7 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
         const int env = e ? atoi(e) : 0;
         if (env > 0) sub_batch = env;
         else if (format == GB200_FORMAT_JPEG) { sub_batch = n / 8; if (sub_batch < 8) sub_batch = 8; if (sub_batch > 32) sub_batch = 32; }
+        else if (format == GB200_FORMAT_BMP) sub_batch = 16;
         else if (format == GB200_FORMAT_PNG) sub_batch = 256;
         else sub_batch = 128;
     }
@@ -80,6 +83,7 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
         switch (format) {
         case GB200_FORMAT_JPEG: B = gb::jpeg_decode_batch(m, files + a, lens + a, nullptr, arg, s_decode); break;
         case GB200_FORMAT_PNG:  B = gb::png_decode_batch(m, files + a, lens + a, nullptr, arg, want16, s_decode); break;
+        case GB200_FORMAT_BMP:  B = gb::bmp_decode_batch(m, files + a, lens + a, nullptr, arg, s_decode); break;
         default:                B = gb::qoix_decode_batch(m, files + a, lens + a, nullptr, arg, s_decode); break;
         }
         if (!B) { ok = false; break; }

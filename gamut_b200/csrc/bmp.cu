@@ -277,6 +277,78 @@ bmp_decode_kernel(const BmpJob* __restrict__ jobs, int njobs, uint32_t total_pix
     }
 }
 
+// The two "easy" layouts of stbi__bmp_load (:2396-2420: 24-bit BGR and 32-bit BGRA with the default masks) are a
+// byte shuffle with a vertical flip, i.e. a copy: four pixels per thread, the source read as aligned 32-bit words
+// realigned with a funnel shift (rows start at data_off + j * row_bytes, usually 2 mod 4), B and R swapped with one
+// PRMT per pixel, whole words stored. A warp reads and writes 384 (or 512) contiguous bytes per instruction.
+// grid = (ceil(w / 1024), h, images); SB = source bytes per pixel, DB = destination bytes per pixel.
+template <int SB, int DB>
+__global__ void __launch_bounds__(256)
+bmp_easy_kernel(const BmpJob* __restrict__ jobs)
+{
+    const BmpJob& J = jobs[blockIdx.z];
+    const uint32_t j = blockIdx.y;
+    if (j >= (uint32_t)J.h) return;
+    const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    const bool live = i0 < (uint32_t)J.w;
+    uint32_t aor = 0;
+    if (live) {
+        const uint32_t npx = min(4u, (uint32_t)J.w - i0);
+        const uint32_t o = J.data_off + j * (uint32_t)J.row_bytes + i0 * SB;
+        uint32_t px[4];                                  // B | G << 8 | R << 16 | A << 24
+        if ((uint64_t)o + 4 * SB + 4 <= J.len) {
+            const uint8_t* p = J.data + o;
+            const uint32_t mis = (uint32_t)((uintptr_t)p & 3u), sh = mis * 8u;
+            const uint32_t* w = (const uint32_t*)(p - mis);
+            uint32_t x[SB + 1], v[SB];
+#pragma unroll
+            for (int k = 0; k <= SB; ++k) x[k] = __ldg(w + k);
+#pragma unroll
+            for (int k = 0; k < SB; ++k) v[k] = __funnelshift_r(x[k], x[k + 1], sh);
+            if (SB == 3) {
+                px[0] = v[0] & 0x00ffffffu; px[1] = __funnelshift_r(v[0], v[1], 24) & 0x00ffffffu;
+                px[2] = __funnelshift_r(v[1], v[2], 16) & 0x00ffffffu; px[3] = v[2] >> 8;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[k] = v[k % SB];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                px[k] = 0;
+#pragma unroll
+                for (int c = 0; c < SB; ++c) px[k] |= rd8(J, o + k * SB + c) << (8 * c);
+            }
+        }
+        uint32_t q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = SB == 4 ? px[k] >> 24 : 255u;
+            if (k < (int)npx) aor |= a;
+            q[k] = (__byte_perm(px[k], 0, 0x3012) & 0x00ffffffu) | (a << 24);       // R | G << 8 | B << 16 | A << 24
+        }
+        const uint32_t row = J.flip ? (uint32_t)J.h - 1u - j : j;
+        uint8_t* d = J.out + ((size_t)row * J.w + i0) * DB;
+        if (DB == 4) {
+            if (npx == 4 && (((uintptr_t)d) & 15) == 0) *(uint4*)d = make_uint4(q[0], q[1], q[2], q[3]);
+            else for (uint32_t k = 0; k < npx; ++k) ((uint32_t*)d)[k] = q[k];
+        } else {
+            if (npx == 4 && (((uintptr_t)d) & 3) == 0) {
+                uint32_t* d32 = (uint32_t*)d;
+                d32[0] = (q[0] & 0x00ffffffu) | (q[1] << 24);
+                d32[1] = ((q[1] >> 8) & 0x0000ffffu) | (q[2] << 16);
+                d32[2] = ((q[2] >> 16) & 0x000000ffu) | (q[3] << 8);
+            } else {
+                for (uint32_t k = 0; k < npx; ++k) { d[k * 3] = (uint8_t)q[k]; d[k * 3 + 1] = (uint8_t)(q[k] >> 8); d[k * 3 + 2] = (uint8_t)(q[k] >> 16); }
+            }
+        }
+    }
+    if (SB == 4) {                                       // all_a |= a (:2418)
+        const uint32_t m = __reduce_or_sync(0xffffffffu, aor);
+        if ((threadIdx.x & 31) == 0 && m) atomicOr(J.all_a, m);
+    }
+}
+
 __device__ __forceinline__ uint8_t bmp_compute_y(int r, int g, int b) { return (uint8_t)(((r * 77) + (g * 150) + (29 * b)) >> 8); }   // :911
 
 __global__ void __launch_bounds__(256)
@@ -340,12 +412,19 @@ gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* 
     if (!d_files.p || !d_tmp.p || !d_jobs.p || !d_fix.p || !d_flags.p) { delete B; return nullptr; }
     uint8_t* h_stage = nullptr;
     if (!files_dev) { h_stage = (uint8_t*)pinned_alloc(file_total); if (!h_stage) { delete B; return nullptr; } }
+    // jobs[0 .. ngen) go to the per-pixel kernel, then four groups for the easy layouts (source 3|4 bytes x target 3|4)
     std::vector<BmpJob> jobs((size_t)m); std::vector<BmpFix> fix; std::vector<uint32_t> flags((size_t)m);
     std::vector<HostCopy> hcopies;
+    auto group_of = [&](const BmpPlan& p) { return p.easy && p.h <= 65535 && (p.target == 3 || p.target == 4) ? 1 + (p.easy - 1) * 2 + (p.target - 3) : 0; };
+    int gcount[5] = {0, 0, 0, 0, 0}, gfirst[6] = {0, 0, 0, 0, 0, 0}, gmaxw[5] = {0, 0, 0, 0, 0}, gmaxh[5] = {0, 0, 0, 0, 0};
+    for (int i : live) { const int g = group_of(P[i]); ++gcount[g]; gmaxw[g] = std::max(gmaxw[g], P[i].w); gmaxh[g] = std::max(gmaxh[g], P[i].h); }
+    for (int g = 0; g < 5; ++g) gfirst[g + 1] = gfirst[g] + gcount[g];
+    int gnext[5]; for (int g = 0; g < 5; ++g) gnext[g] = gfirst[g];
     uint32_t pix = 0, fixpix = 0;
-    for (int k = 0; k < m; ++k) {
-        const int i = live[k];
+    for (int i : live) {
         const BmpPlan& p = P[i];
+        const int g = group_of(p);
+        const int k = gnext[g]++;
         BmpJob& J = jobs[k];
         memset(&J, 0, sizeof(J));
         if (files_dev) J.data = files_dev[i];
@@ -360,9 +439,8 @@ gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* 
         const bool convert = outc != p.target;
         J.out = convert ? d_tmp.as<uint8_t>() + tmp_off[i] : d_out + out_off[i];
         J.all_a = d_flags.as<uint32_t>() + k;
-        J.pix_base = pix;
         flags[k] = p.all_a0;
-        pix += (uint32_t)p.w * (uint32_t)p.h;
+        if (g == 0) { J.pix_base = pix; pix += (uint32_t)p.w * (uint32_t)p.h; }
         if (convert || (p.target == 4 && p.all_a0 == 0)) {
             BmpFix F; F.src = J.out; F.dst = d_out + out_off[i]; F.w = p.w; F.h = p.h; F.target = p.target; F.req = outc;
             F.all_a = J.all_a; F.pix_base = fixpix;
@@ -381,8 +459,18 @@ gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* 
     if (!fix.empty()) okc &= cuda_ok(cudaMemcpyAsync(d_fix.p, fix.data(), sizeof(BmpFix) * fix.size(), cudaMemcpyHostToDevice, st), "fix", __FILE__, __LINE__);
     cudaEventRecord(ev[1], st);
     if (okc) {
-        bmp_decode_kernel<<<(pix + 255) / 256, 256, 0, st>>>(d_jobs.as<BmpJob>(), m, pix);
-        count_launch();
+        if (gcount[0]) { bmp_decode_kernel<<<(pix + 255) / 256, 256, 0, st>>>(d_jobs.as<BmpJob>(), gcount[0], pix); count_launch(); }
+        for (int g = 1; g < 5; ++g) {
+            for (int z0 = 0; z0 < gcount[g]; z0 += 65535) {
+                const dim3 grid((unsigned)((gmaxw[g] + 1023) / 1024), (unsigned)gmaxh[g], (unsigned)std::min(65535, gcount[g] - z0));
+                const BmpJob* dj = d_jobs.as<BmpJob>() + gfirst[g] + z0;
+                if (g == 1) bmp_easy_kernel<3, 3><<<grid, 256, 0, st>>>(dj);
+                else if (g == 2) bmp_easy_kernel<3, 4><<<grid, 256, 0, st>>>(dj);
+                else if (g == 3) bmp_easy_kernel<4, 3><<<grid, 256, 0, st>>>(dj);
+                else bmp_easy_kernel<4, 4><<<grid, 256, 0, st>>>(dj);
+                count_launch();
+            }
+        }
         if (!fix.empty()) { bmp_fix_kernel<<<(fixpix + 255) / 256, 256, 0, st>>>(d_fix.as<BmpFix>(), (int)fix.size(), fixpix); count_launch(); }
     }
     cudaEventRecord(ev[2], st);

@@ -105,7 +105,8 @@ void                    gb200_batch_timing(const gb200_batch* b, float* phase_ms
  * dst_host + i*dst_stride (gapless rows; dst_host should be pinned -- gb200_host_alloc -- or the copies are staged by
  * the driver). The batch is cut into sub-batches (sub_batch images each, 0 = automatic); the pixels of one sub-batch
  * travel back while the next one is uploaded and decoded. format: GB200_FORMAT_JPEG (arg = req_comps, -1 keep),
- * GB200_FORMAT_PNG (arg = req_comp, want16 as in gb200_png_decode_batch), GB200_FORMAT_QOIX (arg = LoadFlags).
+ * GB200_FORMAT_PNG (arg = req_comp, want16 as in gb200_png_decode_batch), GB200_FORMAT_QOIX (arg = LoadFlags),
+ * GB200_FORMAT_BMP (arg = req_comp).
  * descs[i] is filled like gb200_batch_images() except that `pixels` is the HOST address of the image (NULL = failed; an
  * image larger than dst_stride fails). Synchronous, thread-safe. This is the batch form of the reference's codec
  * calls -- bytes in, pixels out (plugins/png.d:108, jpeg.d:62, qoix.d:116). Returns 1 / 0. */

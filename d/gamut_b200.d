@@ -95,6 +95,13 @@ extern(C)
     int gb200_sm_count();
     int gb200_batch_download(const(gb200_batch)* b, ubyte* dst_host, size_t stride);
     int gb200_jpeg_probe(const(ubyte)* data, size_t len);
+    /// stbi_load_from_callbacks on a BMP (stbdec.d:725 -> :2263), as loadBMP calls it (plugins/bmp.d:112)
+    ubyte* gb200_bmp_load(const(ubyte)* data, size_t len, int req_comp, int* width, int* height, int* comp,
+                          float* ppmX, float* ppmY, float* pixelRatio);
+    gb200_batch* gb200_bmp_decode_batch(int n, const(ubyte*)* files, const(size_t)* lens,
+                                        const(ubyte*)* files_dev, int req_comp, void* stream);
+    /// Image.identifyFormatFromMemory (image.d:1037-1061): ImageFormat value or -1
+    int gb200_identify_format(const(ubyte)* data, size_t len);
     struct gb200_image { void* alloc; size_t alloc_bytes; ubyte* data; int width, height, type, pitch, layout; float pixelAspectRatio, resolutionY; const(char)* error; }
     int gb200_image_load(const(ubyte)* data, size_t len, int flags, gb200_image* out_);
     int gb200_decode_batch_host(int format, int n, const(ubyte*)* files, const(size_t)* lens, int arg, int want16,
@@ -172,6 +179,40 @@ void loadPNG_b200(ref Image image, IOStream* io, IOHandle handle, int page, int 
     static immutable PixelType[5] t8  = [PixelType.unknown, PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8];
     static immutable PixelType[5] t16 = [PixelType.unknown, PixelType.l16, PixelType.la16, PixelType.rgb16, PixelType.rgba16];
     image._type = decodeTo16bit ? t16[components] : t8[components];
+    image.convertTo(applyLoadFlags(image._type, flags), cast(LayoutConstraints) flags);
+}
+
+/// Replaces loadBMP (plugins/bmp.d:93-163).
+void loadBMP_b200(ref Image image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    int len;
+    ubyte* buf = slurp(io, handle, len, image);
+    if (buf is null) return;
+    scope(exit) free(buf);
+
+    int requestedComp = computeRequestedImageComponents(flags);
+    if (requestedComp == 0) { image.error(kStrInvalidFlags); return; }
+    if (requestedComp == -1) requestedComp = 0;
+
+    int width, height, components;
+    float ppmX = -1, ppmY = -1, pixelRatio = -1;
+    ubyte* decoded = gb200_bmp_load(buf, len, requestedComp, &width, &height, &components, &ppmX, &ppmY, &pixelRatio);
+    if (requestedComp != 0) components = requestedComp;
+    if (decoded is null) { image.error(kStrImageDecodingFailed); return; }
+    if (!imageIsValidSize(1, width, height)) { image.error(kStrImageTooLarge); free(decoded); return; }
+
+    image._allocArea = decoded;
+    image._width = width;
+    image._height = height;
+    image._data = decoded;
+    image._pitch = width * components;
+    image._pixelAspectRatio = (pixelRatio == -1) ? GAMUT_UNKNOWN_ASPECT_RATIO : pixelRatio;
+    image._resolutionY = (ppmY == -1) ? GAMUT_UNKNOWN_RESOLUTION : convertInchesToMeters(ppmY);
+    image._layoutConstraints = LAYOUT_DEFAULT;
+    image._layerCount = 1;
+    image._layerOffset = 0;
+    static immutable PixelType[5] t8 = [PixelType.unknown, PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8];
+    image._type = t8[components];
     image.convertTo(applyLoadFlags(image._type, flags), cast(LayoutConstraints) flags);
 }
 

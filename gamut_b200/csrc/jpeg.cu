@@ -669,6 +669,12 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
     const uint8_t* __restrict__ zags = im.blk_zag + ((size_t)mrow * im.mcus_per_row + g0) * bpm;
     // the coefficient row and the extent of the NEXT task are fetched while the current one is transformed (the two
     // dependent global loads at the top of an iteration were 16 % of the kernel's stall samples)
+    // 4:2:0: the chroma row of this group's (single) upsampling task is requested now and used after the luma blocks
+    int4 chroma_v = make_int4(0, 0, 0, 0); int chroma_zag = 0;
+    if (st == YH2V2 && grp < nm * 2) {
+        chroma_zag = zags[(grp >> 1) * 6 + 4 + (grp & 1)];
+        chroma_v = __ldg((const int4*)(coefs + ((size_t)(grp >> 1) * 6 + 4 + (grp & 1)) * 64) + t);
+    }
     int4 nv = make_int4(0, 0, 0, 0); int nzag = 0;
     auto fetch = [&](int task, int4& v, int& zag) {
         v = make_int4(0, 0, 0, 0); zag = 0;
@@ -732,12 +738,14 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
             const int task = base + grp;
             const bool active = task < nup;
             const int m = task >> 1, ch = task & 1;
-            const int czag = active ? (int)zags[m * 6 + 4 + ch] : 0;
+            const bool first = base == 0;                // nm <= 16: the only iteration; kept general
+            const int czag = !active ? 0 : first ? chroma_zag : (int)zags[m * 6 + 4 + ch];
+            const int4 cv4 = first ? chroma_v : (active ? __ldg((const int4*)(coefs + ((size_t)m * 6 + 4 + ch) * 64) + t) : make_int4(0, 0, 0, 0));
             if (__reduce_max_sync(0xffffffffu, czag) <= 1) {
                 // P_Q!(1,1) / R_S!(1,1): only P[0][0] = DC is non-zero, the four tiles are the DC-only idct_4x4:
                 // Row!4 gives DC << 2 along row 0, Col!4 then ((t + 128*32 + 16) >> 5) = ((DC + 4) >> 3) + 128
+                const int dcv = __shfl_sync(0xffffffffu, cv4.x, (threadIdx.x & 31) & ~7);
                 if (active) {
-                    const int dcv = (int)__ldg(coefs + ((size_t)m * 6 + 4 + ch) * 64);
                     const int t4 = (int)(short)dcv;          // add_and_store keeps a short
                     const uint32_t v = (uint32_t)clamp255((((t4 << 2) + (128 << 5) + 16) >> 5)) * 0x01010101u;
                     uint8_t* dstc = s_tiles + m * IC_MCU420 + (4 + ch * 4) * 64;
@@ -749,7 +757,7 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
             }
             if (active) {   // A: thread j = source row j -> X0[0..3][j], X1[0..3][j]
                 int s[8];
-                unpack8(__ldg((const int4*)(coefs + ((size_t)m * 6 + 4 + ch) * 64) + t), s);
+                unpack8(cv4, s);
                 tmp[0 * 8 + t] = s[0];
                 tmp[1 * 8 + t] = UD(a1[0] * s[1] + a1[1] * s[3] + a1[2] * s[5] + a1[3] * s[7]);
                 tmp[2 * 8 + t] = s[4];

@@ -89,6 +89,7 @@ extern(C)
                                          const(ubyte*)* files_dev, int flags, void* stream);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
     int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
+    int gb200_download_by_kernel(void* dst_pinned, const(void)* src_dev, size_t bytes, void* stream);
     void* gb200_device_alloc(size_t bytes);
     void gb200_device_free(void* p);
     void gb200_device_trim();

@@ -259,6 +259,24 @@ GB_API int gb200_copy_to_host(void* dst_host, const void* src_dev, size_t bytes)
     GB_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
     return 1;
 }
+/* Download by the SMs instead of a copy engine: a grid-stride 16-byte copy whose stores land in PINNED host memory
+ * (mapped under UVA). Asynchronous on `stream`. dst_pinned, src_dev and bytes must be multiples of 16. */
+namespace gb {
+__global__ void __launch_bounds__(256) sm_download_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcs(src + i);
+}
+}
+GB_API int gb200_download_by_kernel(void* dst_pinned, const void* src_dev, size_t bytes, void* stream)
+{
+    if (!gb::ensure_device()) return 0;
+    if ((((uintptr_t)dst_pinned | (uintptr_t)src_dev | bytes) & 15) != 0) { gb::set_error("gb200_download_by_kernel: 16-byte alignment"); return 0; }
+    if (!bytes) return 1;
+    gb::sm_download_kernel<<<gb::sm_count() * 8, 256, 0, (cudaStream_t)stream>>>((uint4*)dst_pinned, (const uint4*)src_dev, bytes / 16);
+    gb::count_launch();
+    GB_CUDA(cudaGetLastError());
+    return 1;
+}
 GB_API int gb200_copy_to_device(void* dst_dev, const void* src_host, size_t bytes)
 {
     if (!gb::ensure_device()) return 0;

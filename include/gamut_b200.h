@@ -55,6 +55,9 @@ void        gb200_host_free(void* p);
 void        gb200_free(void* p);               /* free() for pixels returned by host decoders */
 int         gb200_copy_to_host(void* dst_host, const void* src_dev, size_t bytes);    /* synchronous */
 int         gb200_copy_to_device(void* dst_dev, const void* src_host, size_t bytes);  /* synchronous */
+/* Download by the SMs instead of a copy engine: 16-byte stores straight into PINNED host memory (gb200_host_alloc),
+ * asynchronous on `stream`; pointers and size multiples of 16. */
+int         gb200_download_by_kernel(void* dst_pinned, const void* src_dev, size_t bytes, void* stream);
 
 /* ---- PixelType converters: source/gamut/scanline.d ---- */
 int gb200_pixel_type_size(int type);                       /* pixelTypeSize, types.d:62 */

@@ -24,7 +24,12 @@
 
 constexpr int P10_CHUNK_BYTES = 128;
 constexpr int P10_CHUNK_BITS = P10_CHUNK_BYTES * 8;
+constexpr int P10_CHUNK_WORDS = P10_CHUNK_BYTES / 4;
 constexpr uint32_t P10_KIND_DIFF = 0u, P10_KIND_COPY = 1u << 20, P10_KIND_LIT = 2u << 20;
+constexpr int P10_CTA = 256;                     // threads (= chunk slots) per CTA of the sync and write kernels
+constexpr int P10_WARM = 8;                      // sync: slots that re-parse the tail of the previous CTA's range
+constexpr int P10_OWN = P10_CTA - P10_WARM;
+constexpr int P10_STAGE_WORDS = P10_CTA * P10_CHUNK_WORDS + 32;     // the CTA's slice of the stream + what a parse may read past it
 
 struct P10Image {
     const uint8_t* stream;      // payload with its 25-byte header
@@ -33,115 +38,245 @@ struct P10Image {
     int channels;
     int image;                  // index into status[]
     uint32_t chunk_base, nchunks;
+    uint32_t scta_base, wcta_base;      // first CTA of this image in the sync grid (P10_OWN chunks each) / write grid (P10_CTA)
     uint32_t* recs;             // [h][wp]
     uint32_t* rowinfo;          // [h]: 0 = row starts normally, x+2 = first pixel copies column x of the row above (x = -1: any)
     uint8_t* out;
 };
 
 struct P10Chunk {               // per-chunk parse summary
-    uint32_t exit_bit;          // position of the first opcode group that starts at or after the chunk's end
-    uint32_t npix;              // pixels produced by the groups that start in this chunk
+    uint32_t exit_bit;          // position of the first opcode that starts at or after the chunk's end
+    uint32_t npix;              // pixels produced by the opcodes that start in this chunk
     uint32_t alpha;             // bit 31: ended, bit 30: set, bits 0-9: value (set) or delta (add)
 };
 struct P10Entry { uint32_t pix; uint32_t alpha; };     // alpha bit 31: the stream ended before this chunk
 
+template <int WHICH>            // 0: chunk_base, 1: scta_base, 2: wcta_base
 __device__ __forceinline__ uint32_t p10_find_image(const P10Image* __restrict__ imgs, int n, uint32_t c)
 {
     int lo = 0, hi = n - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (imgs[mid].chunk_base <= c) lo = mid; else hi = mid - 1; }
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const uint32_t b = WHICH == 0 ? imgs[mid].chunk_base : WHICH == 1 ? imgs[mid].scta_base : imgs[mid].wcta_base;
+        if (b <= c) lo = mid; else hi = mid - 1;
+    }
     return (uint32_t)lo;
 }
 
-// 32 bits of the opcode stream starting at bit `bp` (MSB first). Bytes past the end read as 0xFF (== END).
-struct P10Bits {
-    const uint32_t* words; uint32_t adj, total_bits;
+// The opcode stream as big-endian 32-bit words: word k = payload bits [32k, 32k + 32). Bytes past the end read as
+// 0xFF (== END), like the restated bit reader of the oracle.
+struct P10Global {
+    const uint32_t* words; uint32_t adj, nbytes;
     __device__ __forceinline__ void init(const uint8_t* stream, uint32_t size)
     {
         const uintptr_t a = (uintptr_t)(stream + 25);
         words = (const uint32_t*)(a & ~(uintptr_t)3); adj = (uint32_t)(a & 3) * 8;
-        total_bits = (size - 25) * 8;
+        nbytes = size - 25;
     }
-    __device__ __forceinline__ uint32_t peek32(uint32_t bp) const
+    __device__ __forceinline__ uint32_t operator()(long long k) const
     {
-        if (bp + 64 <= total_bits) {
-            const uint32_t b = bp + adj, idx = b >> 5, sh = b & 31;
-            const uint32_t w0 = __byte_perm(words[idx], 0, 0x0123), w1 = __byte_perm(words[idx + 1], 0, 0x0123);
-            return __funnelshift_l(w1, w0, sh);
+        if (k < 0) return 0xffffffffu;
+        const unsigned long long b = (unsigned long long)k * 4;
+        if (b + 8 <= nbytes) {
+            const uint32_t w0 = __byte_perm(__ldg(words + k), 0, 0x0123), w1 = __byte_perm(__ldg(words + k + 1), 0, 0x0123);
+            return __funnelshift_l(w1, w0, adj);
         }
         const uint8_t* p = (const uint8_t*)words + (adj >> 3);
-        uint64_t v = 0;
-        const uint32_t byte0 = bp >> 3;
+        uint32_t v = 0;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { const uint32_t bi = byte0 + i; v = (v << 8) | (bi * 8 < total_bits ? p[bi] : 0xFFu); }
-        return (uint32_t)(v >> (8 - (bp & 7)));
+        for (int i = 0; i < 4; ++i) v = (v << 8) | (b + i < nbytes ? (uint32_t)p[b + i] : 0xFFu);
+        return v;
     }
 };
-
-__device__ __forceinline__ int p10_sext(uint32_t v, int bits) { return (int)(v << (32 - bits)) >> (32 - bits); }
-
-// Parses the opcode groups that start in [bitpos, limit). EMIT receives every group:
-//   emit(kind_and_value, alpha_changed, alpha_is_literal, alpha_value_or_delta, npixels)
-template <class Emit>
-__device__ __forceinline__ bool p10_parse(const P10Bits& B, uint32_t& bitpos, uint32_t limit, Emit&& emit)
+// The CTA's slice of the stream in shared memory: word k of the slice at [k / 32][(k + k / 32) % 32], so that the
+// lanes of a warp, each reading its own 128-byte chunk, hit different banks.
+struct P10Shared {
+    const uint32_t* s;
+    __device__ __forceinline__ static uint32_t swz(uint32_t k) { return (k & ~31u) | ((k + (k >> 5)) & 31u); }
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return s[swz(k)]; }
+};
+__device__ __forceinline__ void p10_stage(uint32_t* s_words, const P10Global& G, long long first_word, int tid)
 {
-    uint32_t bp = bitpos;
-    bool ended = false;
-    while (bp < limit) {
-        bool achg = false; int adelta = 0;
-        for (;;) {
-            const uint32_t v = B.peek32(bp);
-            const uint32_t op = v >> 24;
-            if (op < 0x80) { emit(P10_KIND_DIFF | ((uint32_t)p10_sext((op >> 4) & 7, 3) & 1023u), achg, false, adelta, 1u); bp += 4; break; }
-            if (op < 0xc0) { emit(P10_KIND_DIFF | ((uint32_t)p10_sext(op & 0x3f, 6) & 1023u), achg, false, adelta, 1u); bp += 8; break; }
-            if (op < 0xe0) {
-                uint32_t run = (op >> 2) & 7, len = 6;
-                if (run == 7) { run = ((v >> 18) & 0xff) + 7; len = 14; }
-                emit(P10_KIND_COPY, achg, false, adelta, run + 1); bp += len; break;
-            }
-            if (op < 0xf0) { emit(P10_KIND_DIFF | ((v >> 18) & 1023u), achg, false, adelta, 1u); bp += 14; break; }
-            if (op < 0xf8) { emit(P10_KIND_DIFF | ((uint32_t)p10_sext((v >> 20) & 0x7f, 7) & 1023u), achg, false, adelta, 1u); bp += 12; break; }
-            if (op < 0xfc) { achg = true; adelta = p10_sext((v >> 20) & 0x3f, 6); bp += 12; continue; }
-            if (op == 0xfe) { emit(P10_KIND_LIT | ((v >> 14) & 1023u), true, true, (int)((v >> 4) & 1023u), 1u); bp += 28; break; }
-            ended = true; break;     // END (0xff) or the reserved 0xfc/0xfd
-        }
-        if (ended) break;
+    for (int k = tid; k < P10_STAGE_WORDS; k += P10_CTA) s_words[P10Shared::swz((uint32_t)k)] = G(first_word + k);
+}
+
+// One table lookup per opcode instead of a chain of data-dependent branches (the lanes of a warp are at different
+// opcodes): length, pixels produced, and where the value sits in the 32 bits at the opcode's start.
+//   bits 0-4 length | 5-8 pixels | 9 extended run | 10 alpha opcode (ADIFF; with pixels = 1: LA) | 11 END / reserved
+//   | 12-16, 17-21 the left / arithmetic right shift that extract the sign-extended value | 20-21 (<< 2) kind
+constexpr uint32_t P10L_EXT = 1u << 9, P10L_ALPHA = 1u << 10, P10L_END = 1u << 11, P10L_NPIX = 15u << 5;
+__device__ __forceinline__ uint32_t p10_lut_entry(uint32_t op)      // opcode table, qoiplane10.d:43-52
+{
+    auto val = [](int shift, int bits) { return (uint32_t)(32 - shift - bits) << 12 | (uint32_t)(32 - bits) << 17; };
+    if (op < 0x80) return 4u | 1u << 5 | val(28, 3);                                   // DIFF1
+    if (op < 0xc0) return 8u | 1u << 5 | val(24, 6);                                   // DIFF2
+    if (op < 0xe0) {                                                                   // RUN
+        const uint32_t run = (op >> 2) & 7;
+        return run == 7 ? (14u | P10L_EXT | 1u << 22) : (6u | (run + 1) << 5 | 1u << 22);
     }
-    bitpos = bp;
+    if (op < 0xf0) return 14u | 1u << 5 | val(18, 10);                                 // DIFF4
+    if (op < 0xf8) return 12u | 1u << 5 | val(20, 7);                                  // DIFF3
+    if (op < 0xfc) return 12u | P10L_ALPHA;                                            // ADIFF (the pixel's own opcode follows)
+    if (op == 0xfe) return 28u | 1u << 5 | P10L_ALPHA | val(14, 10) | 2u << 22;        // LA
+    return P10L_END;                                                                   // END (0xff), reserved 0xfc / 0xfd
+}
+
+// Bit reader over a word accessor: 64-bit window, MSB first, refilled one word at a time.
+template <class Words>
+struct P10Reader {
+    Words W; uint32_t next; uint64_t buf; int cnt;
+    __device__ __forceinline__ void init(uint32_t bitpos)
+    {
+        next = bitpos >> 5;
+        buf = ((uint64_t)W(next) << 32) | W(next + 1);
+        next += 2;
+        const int sh = bitpos & 31;
+        buf <<= sh; cnt = 64 - sh;
+    }
+    __device__ __forceinline__ uint32_t peek() { if (cnt <= 32) { buf |= (uint64_t)W(next) << (32 - cnt); ++next; cnt += 32; } return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }
+};
+
+// Parses the opcode groups that START in [bitpos, limit) without storing anything (positions are relative to the word
+// accessor's origin): exit position, pixels produced, effect on the running alpha. A group is a pixel's opcode with
+// the ADIFFs before it; an ADIFF adds to the alpha of the PREVIOUS pixel (qoiplane10.d:463-470), so of several
+// ADIFFs in one group only the last counts, and a group belongs to the chunk it starts in.
+template <class Words>
+__device__ __forceinline__ bool p10_count(const Words& W, const uint32_t* __restrict__ lut, uint32_t& bitpos, uint32_t limit,
+                                          uint32_t& npix, uint32_t& alpha_fx)
+{
+    P10Reader<Words> R{W}; R.init(bitpos);
+    uint32_t p = bitpos, np = 0;
+    bool aset = false, ended = false, ing = false; int aval = 0, gd = 0;
+    while (p < limit || ing) {
+        const uint32_t v = R.peek();
+        const uint32_t e = lut[v >> 24];
+        const uint32_t len = e & 31u;
+        if ((e & (P10L_ALPHA | P10L_END)) || ing) {              // rare: the alpha plane of the workload is mostly flat
+            if (e & P10L_END) { ended = true; break; }
+            if ((e & (P10L_ALPHA | P10L_NPIX)) == P10L_ALPHA) { gd = (int)(v << 6) >> 26; ing = true; p += len; R.drop((int)len); continue; }
+            if (e & P10L_ALPHA) { aset = true; aval = (int)((v >> 4) & 1023u); }
+            else aval += gd;
+            ing = false;
+        }
+        np += (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
+        p += len; R.drop((int)len);
+    }
+    bitpos = p; npix = np;
+    alpha_fx = (aset ? 0x40000000u : 0u) | ((uint32_t)aval & 1023u);
     return ended;
 }
 
-// ---- A1. speculative parse + relaxation ---------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-p10_sync_kernel(const P10Image* __restrict__ imgs, int nimgs, uint32_t total_chunks, P10Chunk* chunks,
-                const uint8_t* __restrict__ dirty_in, uint8_t* __restrict__ dirty_out, int pass, uint32_t* changed)
+// ---- A1. speculative parse + CTA-local relaxation ----------------------------------------------------------------
+// One CTA = 248 consecutive chunks of one image plus 8 warm-up chunks of its predecessor, the slice of the stream in
+// shared memory. Every thread parses its chunk from its first bit, then the CTA relaxes: chunks whose predecessor's
+// exit differs from the entry they used are compacted into as few warps as possible and parse again, until nothing
+// changes. Chunk 0 starts at the true position, so the fixed point is the serial parse. The one unverified
+// assumption, the entry of the CTA's first own chunk, is checked by p10_repair_kernel.
+__global__ void __launch_bounds__(P10_CTA)
+p10_sync_kernel(const P10Image* __restrict__ imgs, int nimgs, P10Chunk* __restrict__ chunks, uint32_t* __restrict__ entry_used)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_chunks) return;
-    const uint32_t ii = p10_find_image(imgs, nimgs, c);
-    const P10Image& im = imgs[ii];
-    const uint32_t lc = c - im.chunk_base;
-    if (pass > 0) {
-        dirty_out[c] = 0;
-        if (lc == 0 || !dirty_in[c - 1]) return;
+    __shared__ uint32_t s_words[P10_STAGE_WORDS];
+    __shared__ uint32_t s_lut[256];
+    __shared__ uint32_t s_entry[P10_CTA], s_exit[P10_CTA], s_npix[P10_CTA], s_alpha[P10_CTA], s_todo_entry[P10_CTA];
+    __shared__ uint16_t s_todo[P10_CTA];
+    __shared__ uint32_t s_wcount[P10_CTA / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const P10Image& im = imgs[p10_find_image<1>(imgs, nimgs, blockIdx.x)];
+    const uint32_t local_cta = blockIdx.x - im.scta_base;
+    const int lc_first = (int)(local_cta * P10_OWN) - P10_WARM;            // chunk of slot 0 (negative in the first CTA)
+    P10Global G; G.init(im.stream, im.size);
+    const uint32_t total_bits = G.nbytes * 8;
+    s_lut[tid] = p10_lut_entry((uint32_t)tid);
+    p10_stage(s_words, G, (long long)lc_first * P10_CHUNK_WORDS, tid);
+    const P10Shared W{s_words};
+    const int origin = lc_first * P10_CHUNK_BITS;                           // stream position of bit 0 of the slice
+    const int lc = lc_first + tid;
+    const bool active = lc >= 0 && (uint32_t)lc < im.nchunks;
+    const uint32_t limit = min((uint32_t)(lc + 1) * (uint32_t)P10_CHUNK_BITS, total_bits);
+    auto parse = [&](uint32_t entry, uint32_t& exit_bit, uint32_t& npix, uint32_t& alpha) {
+        uint32_t rel = entry - (uint32_t)origin;
+        const bool ended = p10_count(W, s_lut, rel, limit - (uint32_t)origin, npix, alpha) || rel + (uint32_t)origin >= total_bits;
+        // A parse that stopped at END leaves a neutral exit (the next chunk's own first bit): after a true END the later
+        // chunks do not matter, and after a false one (a speculative parse on garbage) the successor keeps its own guess.
+        exit_bit = ended ? (uint32_t)(lc + 1) * (uint32_t)P10_CHUNK_BITS : rel + (uint32_t)origin;
+        if (ended) alpha |= 0x80000000u;
+    };
+    __syncthreads();
+    {
+        const uint32_t entry = active ? (uint32_t)lc * (uint32_t)P10_CHUNK_BITS : 0u;
+        uint32_t x = total_bits, np = 0, al = 0;
+        if (active) parse(entry, x, np, al);
+        s_entry[tid] = entry; s_exit[tid] = x; s_npix[tid] = np; s_alpha[tid] = al;
     }
-    P10Bits B; B.init(im.stream, im.size);
-    const uint32_t limit = min((lc + 1) * (uint32_t)P10_CHUNK_BITS, B.total_bits);
-    uint32_t bp = lc * (uint32_t)P10_CHUNK_BITS;
-    if (pass > 0) bp = __ldcg(&chunks[c - 1].exit_bit);
-    uint32_t npix = 0; bool aset = false; int aval = 0;
-    const bool ended = p10_parse(B, bp, limit, [&](uint32_t, bool achg, bool alit, int av, uint32_t n) {
-        npix += n;
-        if (alit) { aset = true; aval = av; } else if (achg) aval += av;
-    }) || bp >= B.total_bits;
-    // A parse that stopped at END leaves a neutral exit position (the next chunk's own first bit): after a true END
-    // the later chunks do not matter, and after a false one (a speculative parse on garbage) the successor keeps
-    // its own guess instead of inheriting a stuck position.
-    if (ended) bp = (lc + 1) * (uint32_t)P10_CHUNK_BITS;
-    const uint32_t alpha = (ended ? 0x80000000u : 0u) | (aset ? 0x40000000u : 0u) | ((uint32_t)aval & 1023u);
-    const uint32_t old = __ldcg(&chunks[c].exit_bit);
-    __stcg(&chunks[c].exit_bit, bp); chunks[c].npix = npix; chunks[c].alpha = alpha;
-    if (pass == 0) dirty_out[c] = 1;
-    else if (old != bp) { dirty_out[c] = 1; atomicAdd(changed, 1u); }
+    const bool chained = tid > 0 && active && lc > 0;
+    for (;;) {
+        __syncthreads();
+        bool stale = false; uint32_t prev = 0;
+        if (chained) { prev = s_exit[tid - 1]; stale = prev != s_entry[tid]; }
+        const uint32_t bal = __ballot_sync(0xffffffffu, stale);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < P10_CTA / 32; ++w) { const uint32_t c = s_wcount[w]; off += w < warp ? c : 0; total += c; }
+        if (total == 0) break;
+        if (stale) { const uint32_t q = off + __popc(bal & ((1u << lane) - 1)); s_todo[q] = (uint16_t)tid; s_todo_entry[q] = prev; }
+        __syncthreads();
+        if ((uint32_t)tid < total) {
+            const int s = s_todo[tid];
+            const uint32_t entry = s_todo_entry[tid];
+            const int slc = lc_first + s;
+            uint32_t rel = entry - (uint32_t)origin, np = 0, al = 0;
+            const uint32_t lim = min((uint32_t)(slc + 1) * (uint32_t)P10_CHUNK_BITS, total_bits);
+            const bool ended = p10_count(W, s_lut, rel, lim - (uint32_t)origin, np, al) || rel + (uint32_t)origin >= total_bits;
+            s_entry[s] = entry;
+            s_exit[s] = ended ? (uint32_t)(slc + 1) * (uint32_t)P10_CHUNK_BITS : rel + (uint32_t)origin;
+            s_npix[s] = np; s_alpha[s] = al | (ended ? 0x80000000u : 0u);
+        }
+    }
+    if (tid >= P10_WARM && active) {
+        P10Chunk* dst = chunks + im.chunk_base + (uint32_t)lc;
+        dst->exit_bit = s_exit[tid]; dst->npix = s_npix[tid]; dst->alpha = s_alpha[tid];
+    }
+    if (tid == P10_WARM) entry_used[blockIdx.x] = s_entry[tid];
+}
+
+// ---- A1b. repair / check of the CTA boundaries --------------------------------------------------------------------
+// One thread per sync CTA compares the entry its first own chunk used with the true exit of the chunk before it and,
+// where they differ (rare), parses forward through its own range until it meets the old chain. mode 1 only counts
+// the boundaries that still disagree; the host reads that count with the statuses at the very end.
+__global__ void __launch_bounds__(64)
+p10_repair_kernel(const P10Image* __restrict__ imgs, int nimgs, uint32_t total_ctas, P10Chunk* chunks, uint32_t* entry_used,
+                  int mode, uint32_t* unconverged)
+{
+    __shared__ uint32_t s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += 64) s_lut[i] = p10_lut_entry((uint32_t)i);
+    __syncthreads();
+    const uint32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cta >= total_ctas) return;
+    const P10Image& im = imgs[p10_find_image<1>(imgs, nimgs, cta)];
+    const uint32_t local_cta = cta - im.scta_base;
+    if (local_cta == 0) return;                                  // starts from the true position
+    const uint32_t lc0 = local_cta * P10_OWN;
+    if (lc0 >= im.nchunks) return;
+    P10Chunk* const ch = chunks + im.chunk_base;
+    const uint32_t truth = __ldcg(&ch[lc0 - 1].exit_bit);
+    if (truth == entry_used[cta]) return;
+    if (mode == 1) { atomicAdd(unconverged, 1u); return; }
+    entry_used[cta] = truth;
+    P10Global G; G.init(im.stream, im.size);
+    const uint32_t total_bits = G.nbytes * 8;
+    const uint32_t lc_end = min(lc0 + (uint32_t)P10_OWN, im.nchunks);
+    uint32_t bp = truth;
+    for (uint32_t lc = lc0; lc < lc_end; ++lc) {
+        uint32_t np = 0, al = 0;
+        const bool ended = p10_count(G, s_lut, bp, min((lc + 1) * (uint32_t)P10_CHUNK_BITS, total_bits), np, al) || bp >= total_bits;
+        if (ended) { bp = (lc + 1) * (uint32_t)P10_CHUNK_BITS; al |= 0x80000000u; }
+        const uint32_t old = __ldcg(&ch[lc].exit_bit);
+        __stcg(&ch[lc].exit_bit, bp); ch[lc].npix = np; ch[lc].alpha = al;
+        if (old == bp) break;                                    // met the old chain: everything after is already right
+    }
 }
 
 // ---- A2. scan over the chunks of an image ----------------------------------------------------------------
@@ -193,46 +328,133 @@ p10_scan_kernel(const P10Image* __restrict__ imgs, const P10Chunk* __restrict__ 
 }
 
 // ---- A3. per-pixel records -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, uint32_t total_chunks, const P10Chunk* __restrict__ chunks,
+// Every chunk is parsed once more from its true entry state. A lane collects the records of the 32-record (128-byte)
+// segment of the record array it is in (word w of lane l at [l][(w + l) % 32]); when the next record belongs to another
+// segment the whole warp writes the finished one out as one coalesced row -- records reach memory in full lines
+// although every lane walks its own part of the image.
+constexpr size_t P10_WRITE_SMEM = sizeof(uint32_t) * (P10_STAGE_WORDS + 256 + P10_CTA * 32);
+__global__ void __launch_bounds__(P10_CTA)
+p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* __restrict__ chunks,
                  const P10Entry* __restrict__ entries)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_chunks) return;
-    const uint32_t ii = p10_find_image(imgs, nimgs, c);
-    const P10Image& im = imgs[ii];
-    const uint32_t lc = c - im.chunk_base;
-    const P10Entry e = entries[c];
-    if (e.alpha & 0x80000000u) return;
-    P10Bits B; B.init(im.stream, im.size);
-    const uint32_t limit = min((lc + 1) * (uint32_t)P10_CHUNK_BITS, B.total_bits);
-    uint32_t bp = lc ? chunks[c - 1].exit_bit : 0u;
-    const unsigned long long np = (unsigned long long)im.w * im.h;
-    unsigned long long i = e.pix;
-    if (i >= np) return;
-    uint32_t y = (uint32_t)(i / im.w), x = (uint32_t)(i - (unsigned long long)y * im.w);
-    uint32_t a = e.alpha & 1023u;
-    uint32_t* __restrict__ rec = im.recs + (size_t)y * im.wp + x;
-    const uint32_t W = im.w, skip = im.wp - im.w;
-    p10_parse(B, bp, limit, [&](uint32_t kv, bool achg, bool alit, int av, uint32_t n) {
-        if (alit) a = (uint32_t)av; else if (achg) a = (a + (uint32_t)av) & 1023u;
-        const uint32_t r = kv | (a << 10);
-        const unsigned long long p0 = i;
-        for (uint32_t q = 0; q < n && i < np; ++q, ++i) {
-            if (x == 0) {
-                uint32_t info = 0;
-                if (y > 0 && (kv & (3u << 20)) == P10_KIND_COPY) {
-                    // the pixel copies pixel p0-1 (and everything between is a copy of it too)
-                    const unsigned long long dist = i - (p0 - 1);
-                    info = dist <= W ? (W - (uint32_t)dist) + 2u : 1u;
-                }
-                im.rowinfo[y] = info;
-            }
-            *rec++ = r;
-            if (++x == W) { x = 0; ++y; rec += skip; }
+    extern __shared__ __align__(16) uint32_t p10w_smem[];
+    uint32_t* const s_words = p10w_smem;                          // [P10_STAGE_WORDS]
+    uint32_t* const s_lut = s_words + P10_STAGE_WORDS;            // [256]
+    uint32_t (*const s_rows)[32] = (uint32_t (*)[32])(s_lut + 256);   // [P10_CTA][32]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const P10Image& im = imgs[p10_find_image<2>(imgs, nimgs, blockIdx.x)];
+    const uint32_t lc0 = (blockIdx.x - im.wcta_base) * P10_CTA;
+    P10Global G; G.init(im.stream, im.size);
+    const uint32_t total_bits = G.nbytes * 8;
+    s_lut[tid] = p10_lut_entry((uint32_t)tid);
+    p10_stage(s_words, G, (long long)lc0 * P10_CHUNK_WORDS, tid);
+    const P10Shared W{s_words};
+    const uint32_t origin = lc0 * (uint32_t)P10_CHUNK_BITS;
+    const uint32_t lc = lc0 + tid;
+    const uint32_t np = im.w * im.h;                              // < 400e6 (header check)
+    bool alive = lc < im.nchunks;
+    uint32_t i = 0, a = 0, bp = 0;
+    if (alive) {
+        const P10Entry e = entries[im.chunk_base + lc];
+        i = e.pix; a = e.alpha & 1023u;
+        bp = lc ? chunks[im.chunk_base + lc - 1].exit_bit : 0u;
+        alive = !(e.alpha & 0x80000000u) && i < np;
+    }
+    const uint32_t limit = min((lc + 1) * (uint32_t)P10_CHUNK_BITS, total_bits);
+    alive = alive && bp < limit;
+    const uint32_t Wd = im.w, skip = im.wp - im.w;
+    uint32_t y = alive ? i / Wd : 0u, x = alive ? i - y * Wd : 0u;
+    uint32_t addr = y * im.wp + x;                                // index into the record array
+    uint32_t seg = addr >> 5, lo = 32, hi = 0;                    // my segment and the part of it I have written
+    uint32_t pend_n = 0, pend_rec = 0, pend_p0 = 0;               // records of the current opcode not yet placed
+    uint32_t a_pend = 0; bool ing = false;                        // inside a group: alpha an ADIFF has announced
+    uint32_t* const myrow = s_rows[tid];
+    const uint32_t* const wrow = s_rows[tid & ~31];
+    uint32_t* const recs = im.recs; uint32_t* const rowinfo = im.rowinfo; const uint32_t WP = im.wp;
+    P10Reader<P10Shared> R{W};
+    __syncthreads();
+    R.init(alive ? bp - origin : 0u);
+    // what the first pixel of row yy records when it is pixel ii of a COPY run that started at pixel p0
+    auto row_info = [&](uint32_t rec, uint32_t ii, uint32_t yy, uint32_t p0) {
+        uint32_t info = 0;
+        if (yy > 0 && (rec & (3u << 20)) == P10_KIND_COPY) {
+            // the pixel copies pixel p0-1 (and everything between is a copy of it too)
+            const uint32_t dist = ii - (p0 - 1);
+            info = dist <= Wd ? (Wd - dist) + 2u : 1u;
         }
-    });
+        return info;
+    };
+    for (;;) {
+        if (alive && pend_n == 0) {
+            const uint32_t v = R.peek();
+            const uint32_t e = s_lut[v >> 24];
+            const uint32_t len = e & 31u;
+            if (e & P10L_END) alive = false;
+            else if ((e & (P10L_ALPHA | P10L_NPIX)) == P10L_ALPHA) {      // ADIFF: the pixel's own opcode follows
+                a_pend = (a + (uint32_t)((int)(v << 6) >> 26)) & 1023u; ing = true;
+                bp += len; R.drop((int)len);
+            } else {
+                if (e & P10L_ALPHA) a = (v >> 4) & 1023u;                  // LA
+                else if (ing) a = a_pend;
+                ing = false;
+                const uint32_t n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
+                const uint32_t kind = ((e >> 22) & 3u) << 20;
+                const uint32_t val = kind == P10_KIND_COPY ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
+                pend_rec = kind | val | (a << 10);
+                pend_n = min(n, np - i); pend_p0 = i;
+                bp += len; R.drop((int)len);
+                if (bp >= limit) alive = false;                   // the next group starts in a later chunk
+            }
+        }
+        // long runs: the whole warp places the records of one lane's run straight into memory, 32 per step (a lane
+        // on its own would keep the other 31 waiting for up to 262 steps)
+        uint32_t big = __ballot_sync(0xffffffffu, pend_n >= 8);
+        while (big) {
+            const int l = __ffs(big) - 1; big &= big - 1;
+            const uint32_t rn = __shfl_sync(0xffffffffu, pend_n, l), rrec = __shfl_sync(0xffffffffu, pend_rec, l);
+            const uint32_t ri = __shfl_sync(0xffffffffu, i, l), rx = __shfl_sync(0xffffffffu, x, l), ry = __shfl_sync(0xffffffffu, y, l);
+            const uint32_t rp0 = __shfl_sync(0xffffffffu, pend_p0, l);
+            const uint32_t sg = __shfl_sync(0xffffffffu, seg, l), flo = __shfl_sync(0xffffffffu, lo, l), fhi = __shfl_sync(0xffffffffu, hi, l);
+            __syncwarp();
+            if ((uint32_t)lane >= flo && (uint32_t)lane < fhi) recs[(size_t)sg * 32 + lane] = wrow[l * 32 + ((lane + l) & 31)];
+            for (uint32_t j = lane; j < rn; j += 32) {
+                const uint32_t xx0 = rx + j, dy = xx0 / Wd, xx = xx0 - dy * Wd, yy = ry + dy;
+                recs[(size_t)yy * WP + xx] = rrec;
+                if (xx == 0) rowinfo[yy] = row_info(rrec, ri + j, yy, rp0);
+            }
+            __syncwarp();
+            if (lane == l) {
+                const uint32_t xx0 = x + pend_n, dy = xx0 / Wd;
+                i += pend_n; x = xx0 - dy * Wd; y += dy; addr = y * WP + x;
+                pend_n = 0; seg = addr >> 5; lo = 32; hi = 0;
+            }
+        }
+        while (pend_n && (addr >> 5) == seg) {
+            if (x == 0) rowinfo[y] = row_info(pend_rec, i, y, pend_p0);
+            const uint32_t w = addr & 31u;
+            myrow[(w + lane) & 31] = pend_rec;
+            lo = min(lo, w); hi = w + 1;
+            --pend_n; ++i; ++addr;
+            if (++x == Wd) { x = 0; ++y; addr += skip; }
+        }
+        if (i >= np) { alive = false; pend_n = 0; }
+        const bool flush = hi > lo && ((addr >> 5) != seg || (!alive && pend_n == 0));
+        uint32_t fb = __ballot_sync(0xffffffffu, flush);
+        if (!__any_sync(0xffffffffu, alive || pend_n)) { if (!fb) break; }
+        if (fb) {
+            __syncwarp();
+            while (fb) {
+                const int l = __ffs(fb) - 1; fb &= fb - 1;
+                const uint32_t sg = __shfl_sync(0xffffffffu, seg, l), flo = __shfl_sync(0xffffffffu, lo, l), fhi = __shfl_sync(0xffffffffu, hi, l);
+                if ((uint32_t)lane >= flo && (uint32_t)lane < fhi) recs[(size_t)sg * 32 + lane] = wrow[l * 32 + ((lane + l) & 31)];
+            }
+            __syncwarp();
+            if (flush) { seg = addr >> 5; lo = 32; hi = 0; }
+        }
+    }
 }
+
+__device__ __forceinline__ int p10_sext(uint32_t v, int bits) { return (int)(v << (32 - bits)) >> (32 - bits); }
 
 // ---- B. reconstruction -------------------------------------------------------------------------------------
 __device__ __forceinline__ int p10_med(int left, int top, int topleft)       // locoPredict, qoiplane10.d:84-96

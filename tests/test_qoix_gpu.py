@@ -197,3 +197,16 @@ def test_lz4_long_blocks_parallel_walk(codecs, oracle):
             check_qoix(codecs, oracle, bytes(b))
         check_qoix(codecs, oracle, data[:len(data) // 2])
         check_qoix(codecs, oracle, data + b"\0" * 37)          # trailing bytes after the final sequence
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_plane10_boundary_repair_paths(codecs, oracle, monkeypatch, mode):
+    """The entry of every sync CTA's first own chunk is declared wrong (test hook): mode 1 sends every boundary
+    through p10_repair_kernel's forward walk, mode 2 leaves that to the host loop that runs when the device-side
+    check still counts disagreeing boundaries. Both must end at the serial parse."""
+    monkeypatch.setenv("GB200_P10_FORCE_REPAIR", mode)
+    for (h, w, c) in [(700, 901, 2), (512, 768, 1)]:
+        img = depth_map_la(h, w, 7, c)
+        for force in (False, True):
+            got = check_qoix(codecs, oracle, oracle.qoix_encode(img, 10, force_lz4=force))
+            assert np.array_equal(got[0], img)

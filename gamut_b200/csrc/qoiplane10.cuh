@@ -25,7 +25,9 @@
 constexpr int P10_CHUNK_BYTES = 128;
 constexpr int P10_CHUNK_BITS = P10_CHUNK_BYTES * 8;
 constexpr int P10_CHUNK_WORDS = P10_CHUNK_BYTES / 4;
-constexpr uint32_t P10_KIND_DIFF = 0u, P10_KIND_COPY = 1u << 20, P10_KIND_LIT = 2u << 20;
+// per-pixel record: bits 0-9 residual (LIT: the value itself), bit 10 COPY of the previous pixel, bit 11 LIT,
+// bits 16-31 the pixel's alpha already expanded to 16 bits
+constexpr uint32_t P10_REC_COPY = 1u << 10, P10_REC_LIT = 1u << 11;
 constexpr int P10_CTA = 256;                     // threads (= chunk slots) per CTA of the sync and write kernels
 constexpr int P10_WARM = 8;                      // sync: slots that re-parse the tail of the previous CTA's range
 constexpr int P10_OWN = P10_CTA - P10_WARM;
@@ -377,7 +379,7 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
     // what the first pixel of row yy records when it is pixel ii of a COPY run that started at pixel p0
     auto row_info = [&](uint32_t rec, uint32_t ii, uint32_t yy, uint32_t p0) {
         uint32_t info = 0;
-        if (yy > 0 && (rec & (3u << 20)) == P10_KIND_COPY) {
+        if (yy > 0 && (rec & P10_REC_COPY)) {
             // the pixel copies pixel p0-1 (and everything between is a copy of it too)
             const uint32_t dist = ii - (p0 - 1);
             info = dist <= Wd ? (Wd - dist) + 2u : 1u;
@@ -398,9 +400,9 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
                 else if (ing) a = a_pend;
                 ing = false;
                 const uint32_t n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
-                const uint32_t kind = ((e >> 22) & 3u) << 20;
-                const uint32_t val = kind == P10_KIND_COPY ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
-                pend_rec = kind | val | (a << 10);
+                const uint32_t kind = ((e >> 22) & 3u) << 10;
+                const uint32_t val = (kind & P10_REC_COPY) ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
+                pend_rec = kind | val | (((a << 6) | (a >> 4)) << 16);
                 pend_n = min(n, np - i); pend_p0 = i;
                 bp += len; R.drop((int)len);
                 if (bp >= limit) alive = false;                   // the next group starts in a later chunk
@@ -518,6 +520,25 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
         int upm[8];                                                      // row above from memory (next block, prefetched)
 #pragma unroll
         for (int i = 0; i < 8; ++i) upm[i] = 0;
+        // l of 8 pixels of the finished row above, from memory (written by another warp or another lane: L2 loads)
+        auto load_up = [&](uint32_t xx0, int* dst) {
+            if (vec_ok) {
+                if (CH == 2) {
+                    const uint4 a = __ldcg((const uint4*)(out16 + ((size_t)(y - 1) * W + xx0) * 2)), b = __ldcg((const uint4*)(out16 + ((size_t)(y - 1) * W + xx0) * 2) + 1);
+                    const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = (int)((wv[i] & 0xffffu) >> 6);
+                } else {
+                    const uint4 a = __ldcg((const uint4*)(out16 + (size_t)(y - 1) * W + xx0));
+                    const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = (int)(((wv[i >> 1] >> ((i & 1) * 16)) & 0xffffu) >> 6);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = xx0 + i < W ? p10_out_l<CH>(im.out, W, y - 1, xx0 + i) : 0;
+            }
+        };
 
         for (uint32_t T = 0; T < total; ++T) {
             const bool active = row_ok && T >= start && T < start + nblocks;
@@ -536,8 +557,7 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
                 if (blk == 0) {
                     ra = __ldg((const uint4*)rrow); rb = __ldg((const uint4*)rrow + 1);
                     if (frommem) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) upm[i] = (uint32_t)i < W ? p10_out_l<CH>(im.out, W, y - 1, i) : 0;
+                        load_up(0, upm);
                         if (wrap) left = p10_out_l<CH>(im.out, W, y - 1, (uint32_t)max(xn, 0));
                     }
                 }
@@ -545,39 +565,45 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
 #pragma unroll
                     for (int i = 0; i < 8; ++i) up[i] = upm[i];
                 }
+                if (y == 0) {                       // row 0 predicts from the left neighbour alone: median(left, 0, left + 0 - 0)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) up[i] = 0;
+                }
                 // prefetch the next block
                 uint4 na = ra, nb = rb;
                 if (blk + 1 < nblocks) {
                     na = __ldg((const uint4*)(rrow + x0 + 8)); nb = __ldg((const uint4*)(rrow + x0 + 12));
-                    if (frommem) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) upm[i] = x0 + 8 + i < W ? p10_out_l<CH>(im.out, W, y - 1, x0 + 8 + i) : 0;
-                    }
+                    if (frommem) load_up(x0 + 8, upm);
                 }
+                // The first pixel of a row is predicted by the pixel above it (a COPY keeps the previous pixel in
+                // raster order, which `left` holds when the row starts inside a run): median(up, up, up).
+                if (blk == 0) { upleft = up[0]; if (!(ra.x & P10_REC_COPY)) left = up[0]; }
                 const uint32_t recs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                 uint32_t o[8];
-                const unsigned long long gi0 = (unsigned long long)y * W + x0;
+                // locoPredict (qoiplane10.d:84-96) is the median of left, top and left + top - topleft; one straight-line
+                // body per pixel: a COPY record zeroes top - topleft (the median of left, top, left is left) and
+                // carries residual 0, a LIT record masks the prediction away.
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t r = recs[i];
-                    const int val = (int)(r & 1023u);
-                    const uint32_t kind = r & (3u << 20);
-                    int pred;
-                    if (y == 0) pred = left;
-                    else if (x0 + i == 0) pred = up[0];
-                    else pred = p10_med(left, up[i], i ? up[i - 1] : upleft);
-                    int l = (pred + p10_sext((uint32_t)val, 10)) & 1023;
-                    if (kind == P10_KIND_COPY) l = left;
-                    if (kind == P10_KIND_LIT) l = val;
-                    const bool dec = gi0 + i < ndec;
-                    if (!dec) l = 0;
-                    const uint32_t a = dec ? (r >> 10) & 1023u : 0u;
+                    const uint32_t keep = (((r >> 11) & 1u) - 1u) & 1023u;       // 0 for LIT, else 1023
+                    const uint32_t res = r & 1023u;
+                    const int d = (r & P10_REC_COPY) ? 0 : up[i] - (i ? up[i - 1] : upleft);
+                    const int t = left + d, mn = min(left, up[i]), mx = max(left, up[i]);
+                    const int pred = max(mn, min(mx, t));
+                    const int l = (int)((((uint32_t)pred + (res & keep)) & keep) | (res & ~keep));
                     left = l;
                     prevres[i] = l;
-                    const uint32_t l16 = (uint32_t)((l << 6) | (l >> 4)), a16 = (a << 6) | (a >> 4);
-                    o[i] = CH == 2 ? (l16 | (a16 << 16)) : l16;
+                    const uint32_t l16 = (uint32_t)((l << 6) | (l >> 4));
+                    o[i] = CH == 2 ? __byte_perm(l16, r, 0x7610) : l16;
                 }
                 upleft = up[7];
+                const unsigned long long gi0 = (unsigned long long)y * W + x0;
+                if (gi0 + 8 > ndec) {               // the stream ended inside or before this block: the rest stays zero
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (gi0 + i >= ndec) { o[i] = 0; prevres[i] = 0; }
+                    left = prevres[7];
+                }
                 if (CH == 2) {
                     uint32_t* d = (uint32_t*)(out16 + ((size_t)y * W + x0) * 2);
                     if (vec_ok) { ((uint4*)d)[0] = make_uint4(o[0], o[1], o[2], o[3]); ((uint4*)d)[1] = make_uint4(o[4], o[5], o[6], o[7]); }

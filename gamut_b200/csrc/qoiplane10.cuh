@@ -547,13 +547,21 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
             // the row above: shuffle the previous block results of the lane above, or memory
 #pragma unroll
             for (int i = 0; i < 8; ++i) up[i] = __shfl_up_sync(0xffffffffu, prevres[i], 1);
-            if (active) {
-                if (lane == 0 && y0 > 0) {
+            // memory phase. The wait for the warp that owns the band above is taken by the whole warp on lane 0's
+            // behalf (one uniform loop instead of one lane leaving the others behind).
+            uint4 na = ra, nb = rb;
+            if (y0 > 0) {
+                uint32_t need = 0;
+                if (lane == 0 && active) {
                     // the row above belongs to another warp: wait until it is in memory as far as this step reads it
-                    uint32_t need = min(blk + 2, nblocks);
+                    need = min(blk + 2, nblocks);
                     if (blk == 0 && wrap) need = max(need, min((uint32_t)(max(xn, 0) >> 3) + 1u, nblocks));
-                    while (prog[pw] < kprev_base + need) __nanosleep(40);
+                    need += kprev_base;
                 }
+                need = __shfl_sync(0xffffffffu, need, 0);
+                while (prog[pw] < need) __nanosleep(20);
+            }
+            if (active) {
                 if (blk == 0) {
                     ra = __ldg((const uint4*)rrow); rb = __ldg((const uint4*)rrow + 1);
                     if (frommem) {
@@ -565,19 +573,23 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
 #pragma unroll
                     for (int i = 0; i < 8; ++i) up[i] = upm[i];
                 }
-                if (y == 0) {                       // row 0 predicts from the left neighbour alone: median(left, 0, left + 0 - 0)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) up[i] = 0;
-                }
                 // prefetch the next block
-                uint4 na = ra, nb = rb;
                 if (blk + 1 < nblocks) {
                     na = __ldg((const uint4*)(rrow + x0 + 8)); nb = __ldg((const uint4*)(rrow + x0 + 12));
                     if (frommem) load_up(x0 + 8, upm);
                 }
+            }
+            __syncwarp();
+            // arithmetic phase: every lane, converged (lanes outside their row work on stale registers; nothing of
+            // theirs is stored, and a lane's registers are set up again at its block 0)
+            {
+                if (y == 0) {                       // row 0 predicts from the left neighbour alone: median(left, 0, left + 0 - 0)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) up[i] = 0;
+                }
                 // The first pixel of a row is predicted by the pixel above it (a COPY keeps the previous pixel in
                 // raster order, which `left` holds when the row starts inside a run): median(up, up, up).
-                if (blk == 0) { upleft = up[0]; if (!(ra.x & P10_REC_COPY)) left = up[0]; }
+                if (blk == 0) { upleft = up[0]; left = (ra.x & P10_REC_COPY) ? left : up[0]; }
                 const uint32_t recs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                 uint32_t o[8];
                 // locoPredict (qoiplane10.d:84-96) is the median of left, top and left + top - topleft; one straight-line
@@ -599,28 +611,30 @@ p10_recon_kernel(const P10Image* __restrict__ imgs, const uint32_t* __restrict__
                 }
                 upleft = up[7];
                 const unsigned long long gi0 = (unsigned long long)y * W + x0;
-                if (gi0 + 8 > ndec) {               // the stream ended inside or before this block: the rest stays zero
+                if (active && gi0 + 8 > ndec) {     // the stream ended inside or before this block: the rest stays zero
 #pragma unroll
                     for (int i = 0; i < 8; ++i) if (gi0 + i >= ndec) { o[i] = 0; prevres[i] = 0; }
                     left = prevres[7];
                 }
-                if (CH == 2) {
-                    uint32_t* d = (uint32_t*)(out16 + ((size_t)y * W + x0) * 2);
-                    if (vec_ok) { ((uint4*)d)[0] = make_uint4(o[0], o[1], o[2], o[3]); ((uint4*)d)[1] = make_uint4(o[4], o[5], o[6], o[7]); }
-                    else {
+                if (active) {
+                    if (CH == 2) {
+                        uint32_t* d = (uint32_t*)(out16 + ((size_t)y * W + x0) * 2);
+                        if (vec_ok) { ((uint4*)d)[0] = make_uint4(o[0], o[1], o[2], o[3]); ((uint4*)d)[1] = make_uint4(o[4], o[5], o[6], o[7]); }
+                        else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) if (x0 + i < W) d[i] = o[i];
-                    }
-                } else {
-                    uint16_t* d = out16 + (size_t)y * W + x0;
-                    if (vec_ok) *(uint4*)d = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
-                    else {
+                            for (int i = 0; i < 8; ++i) if (x0 + i < W) d[i] = o[i];
+                        }
+                    } else {
+                        uint16_t* d = out16 + (size_t)y * W + x0;
+                        if (vec_ok) *(uint4*)d = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+                        else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) if (x0 + i < W) d[i] = (uint16_t)o[i];
+                            for (int i = 0; i < 8; ++i) if (x0 + i < W) d[i] = (uint16_t)o[i];
+                        }
                     }
+                    ra = na; rb = nb;
+                    if (lane == lastlane) { __threadfence_block(); prog[warp] = kband * (nblocks + 1) + blk + 1; }
                 }
-                ra = na; rb = nb;
-                if (lane == lastlane) { __threadfence_block(); prog[warp] = kband * (nblocks + 1) + blk + 1; }
             }
             __syncwarp();       // orders this block's stores before the loads of the lanes that read rows from memory
         }

@@ -23,7 +23,8 @@ namespace {
 constexpr int QOIX_HEADER_SIZE = 25;
 
 struct Lz4Job { const uint8_t* in; uint32_t in_len; uint8_t* out; uint32_t orig; int image; uint32_t* bitmap;
-                uint32_t chunk_base, nchunks; };      // chunk records of the sub-chunk-parallel walk (lz4_spec_kernel ...)
+                uint32_t chunk_base, nchunks;         // chunk records of the chunk-parallel walk (lz4_par.cuh)
+                uint32_t scta_base, wcta_base; };     // first CTA of this block in the sync / write grids
 
 __device__ __forceinline__ void lz4_cp16(void* smem_dst, const void* gsrc)
 {
@@ -167,235 +168,7 @@ __device__ bool lz4_write_walk(const Lz4Job& J, uint4* ring, int lane, uint32_t 
 }
 
 
-// ---- sub-chunk-parallel walk. One LZ4 block per image leaves one warp per image on the machine, so the block is cut
-// into 16 KB chunks of input and every chunk gets a warp. The position of the first token of a chunk is not known,
-// but the token chain synchronises itself: a walk started on an arbitrary byte soon lands on a true token position
-// and follows the true chain from there. So (spec) every chunk is walked from its first byte, recording where the
-// walk crosses into the next chunk and how many bytes it produces; (merge) the true chain of chunk c (from where chunk
-// c-1's walk crossed over) and its speculative chain are advanced side by side until they meet; (scan) output offsets; (write) every chunk is walked from its true start with its output
-// offset, through the same code as the one-warp walk. Anything inconsistent (chains that still disagree after three repair rounds, totals that do
-// not add up, trailing bytes after the final sequence, ...) sends the image to the one-warp walk, which owns the
-// reference's semantics (LZ4_decompress_fast, lz4.d:760-963).
-constexpr uint32_t LZ4_CHUNK = 16384;
-enum { LZ4F_FINAL = 1, LZ4F_ERR = 2, LZ4F_MERGED = 4 };
-struct Lz4Chunk { uint32_t end, nout, flags;                      // speculative walk from the chunk's first byte
-                  uint32_t start_true, end_true, n_true, flags_true, valid, out_off; };   // true walk
-
-// Counting walk (no output) from token position p0 until the position reaches `limit`. All lanes execute the same
-// chain over the shared-memory input ring.
-__device__ void lz4_count_walk(const Lz4Job& J, uint4* ring, int lane, uint32_t p0, uint32_t limit,
-                               uint32_t& p_out, uint32_t& nout_out, uint32_t& flags_out)
-{
-    const uint8_t* ring8 = (const uint8_t*)ring;
-    const uint8_t* gbase = (const uint8_t*)((uintptr_t)J.in & ~(uintptr_t)15);
-    const uint32_t a0 = (uint32_t)(J.in - gbase);
-    const uint32_t in_len = J.in_len;
-    const uint32_t nvec = (a0 + in_len + 15) >> 4;
-    uint32_t fetched = 0, safe = 0, p = p0, nout = 0, flags = 0;
-    auto rbx = [&](uint32_t k) -> uint32_t { return k < safe ? (uint32_t)ring8[(a0 + k) & (LZ4_RING - 1)] : (uint32_t)J.in[k]; };
-    auto stage = [&]() {
-        const uint32_t v0 = (a0 + p) >> 4;
-        if (fetched < v0) fetched = v0;
-        const uint32_t lim = v0 + (LZ4_RING - 256) / 16;
-        const uint32_t hi = lim < nvec ? lim : nvec;
-        for (uint32_t v = fetched + lane; v < hi; v += 32) lz4_cp16(ring + (v & (LZ4_RING / 16 - 1)), gbase + (size_t)v * 16);
-        if (hi > fetched) fetched = hi;
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        safe = fetched * 16 > a0 ? fetched * 16 - a0 : 0;
-    };
-    for (;;) {
-        if (p >= limit) break;
-        if (p >= in_len) { flags |= LZ4F_ERR; break; }
-        if (p + 64 > safe && safe < in_len) stage();
-        const uint32_t token = rbx(p++);
-        uint32_t L = token >> 4;
-        if (L == 15) {
-            uint32_t s2;
-            do { if (p >= in_len) { flags |= LZ4F_ERR; break; } s2 = rbx(p++); L += s2; } while (s2 == 255 && L < 0x7fffff00u);
-            if (flags & LZ4F_ERR) break;
-        }
-        if (L > in_len - p) { flags |= LZ4F_ERR; break; }
-        p += L; nout += L;
-        if (p == in_len) { flags |= LZ4F_FINAL; break; }      // the final sequence has no match part
-        if (in_len - p < 2) { flags |= LZ4F_ERR; break; }
-        p += 2;
-        uint32_t M = token & 15;
-        if (M == 15) {
-            uint32_t s2;
-            do { if (p >= in_len) { flags |= LZ4F_ERR; break; } s2 = rbx(p++); M += s2; } while (s2 == 255 && M < 0x7fffff00u);
-            if (flags & LZ4F_ERR) break;
-        }
-        nout += M + 4;
-        if (nout > 0x7fffffffu) { flags |= LZ4F_ERR; break; }
-    }
-    p_out = p; nout_out = nout; flags_out = flags;
-}
-
-__device__ __forceinline__ bool lz4_chunk_of(const Lz4Job* jobs, int njobs, uint32_t gchunk, int& j, uint32_t& c)
-{
-    int lo = 0, hi = njobs;                         // last job with chunk_base <= gchunk
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jobs[mid].chunk_base <= gchunk) lo = mid; else hi = mid; }
-    j = lo; c = gchunk - jobs[lo].chunk_base;
-    return c < jobs[lo].nchunks;
-}
-
-__global__ void __launch_bounds__(LZ4_WARPS * 32)
-lz4_spec_kernel(const Lz4Job* __restrict__ jobs, int njobs, Lz4Chunk* chunks, uint32_t total_chunks)
-{
-    __shared__ uint4 ring_all[LZ4_WARPS][LZ4_RING / 16];
-    const int wslot = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * LZ4_WARPS + wslot;
-    if (g >= total_chunks) return;
-    int j; uint32_t c;
-    if (!lz4_chunk_of(jobs, njobs, g, j, c)) return;
-    const Lz4Job J = jobs[j];
-    Lz4Chunk& C = chunks[g];
-    const uint32_t q = c * LZ4_CHUNK;
-    const uint64_t lim64 = (uint64_t)q + LZ4_CHUNK;
-    const uint32_t limit = lim64 < J.in_len ? (uint32_t)lim64 : 0xffffffffu;     // the last chunk runs to the final sequence
-    uint32_t pe, no, fl;
-    lz4_count_walk(J, ring_all[wslot], lane, q, limit, pe, no, fl);
-    if (lane == 0) { C.end = pe; C.nout = no; C.flags = fl; C.start_true = q; C.end_true = pe; C.n_true = no; C.flags_true = fl; C.valid = c == 0; C.out_off = 0; }
-}
-
-// One sequence of the token chain at position x, read straight from global memory (merge walks are short).
-// Returns false on a malformed sequence; fin = the literal run ended the block (final sequence).
-__device__ __forceinline__ bool lz4_step(const uint8_t* in, uint32_t in_len, uint32_t& x, uint32_t& nout, bool& fin)
-{
-    fin = false;
-    if (x >= in_len) return false;
-    const uint32_t token = in[x++];
-    uint32_t L = token >> 4;
-    if (L == 15) {
-        uint32_t s2;
-        do { if (x >= in_len) return false; s2 = in[x++]; L += s2; } while (s2 == 255 && L < 0x7fffff00u);
-    }
-    if (L > in_len - x) return false;
-    x += L; nout += L;
-    if (x == in_len) { fin = true; return true; }
-    if (in_len - x < 2) return false;
-    x += 2;
-    uint32_t M = token & 15;
-    if (M == 15) {
-        uint32_t s2;
-        do { if (x >= in_len) return false; s2 = in[x++]; M += s2; } while (s2 == 255 && M < 0x7fffff00u);
-    }
-    nout += M + 4;
-    return true;
-}
-
-// merge: one thread per chunk c >= 1 walks the true chain (from where chunk c-1's true walk crossed over) and chunk
-// c's own speculative chain (from its first byte) side by side, always advancing the one that is behind, until they
-// meet; from there on chunk c's speculative walk is the true one: bytes = mine up to the meeting point + its bytes
-// after. If they never meet inside the chunk the true walk has covered the whole chunk by itself and its result is
-// taken; the next chunk then starts somewhere else than assumed, which the next round of this kernel repairs.
-__global__ void __launch_bounds__(128)
-lz4_merge_kernel(const Lz4Job* __restrict__ jobs, int njobs, Lz4Chunk* chunks, uint32_t total_chunks)
-{
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_chunks) return;
-    int j; uint32_t c;
-    if (!lz4_chunk_of(jobs, njobs, g, j, c) || c == 0) return;
-    const Lz4Job& J = jobs[j];
-    Lz4Chunk& C = chunks[g];
-    const volatile Lz4Chunk& P = chunks[g - 1];
-    const uint32_t q = c * LZ4_CHUNK;
-    const uint32_t pfl = P.flags_true, s0 = (pfl & (LZ4F_FINAL | LZ4F_ERR)) ? 0xffffffffu : P.end_true;
-    if (C.valid && C.start_true == s0) return;                 // consistent with the previous chunk already
-    C.start_true = s0;
-    if (s0 == 0xffffffffu) {
-        // if chunk c-1 is on the true chain the block ends (or breaks) there: the scan kernel decides
-        C.n_true = 0; C.end_true = 0xffffffffu; C.flags_true = 0; C.valid = 1;
-        return;
-    }
-    if (s0 == q) { C.n_true = C.nout; C.end_true = C.end; C.flags_true = C.flags; C.valid = 1; return; }
-    const uint64_t lim64 = (uint64_t)q + LZ4_CHUNK;
-    const uint32_t lim = lim64 < J.in_len ? (uint32_t)lim64 : 0xffffffffu;
-    uint32_t pa = s0, na = 0, pb = q, nb = 0, fa = 0;
-    bool b_alive = true;
-    for (;;) {
-        if (b_alive && pa == pb) {
-            C.n_true = na + (C.nout - nb); C.end_true = C.end; C.flags_true = C.flags; C.valid = 1;
-            return;
-        }
-        bool fin;
-        if (!b_alive || pa < pb) {
-            if (pa >= lim) break;                              // the true walk crossed into the next chunk
-            if (!lz4_step(J.in, J.in_len, pa, na, fin)) { fa = LZ4F_ERR; break; }
-            if (fin) { fa = LZ4F_FINAL; break; }
-        } else {
-            if (pb >= C.end) { b_alive = false; continue; }
-            if (!lz4_step(J.in, J.in_len, pb, nb, fin) || fin) b_alive = false;
-        }
-    }
-    C.n_true = na; C.end_true = pa; C.flags_true = fa; C.valid = 1;
-}
-
-// one warp per image: the chain ends at the first chunk whose walk saw the final sequence (or an error); chunks
-// after it are dead. Output offsets of the live chunks; the image takes the parallel path only if everything adds up.
-__global__ void __launch_bounds__(128)
-lz4_scan_kernel(const Lz4Job* __restrict__ jobs, int njobs, Lz4Chunk* chunks, int* par_ok)
-{
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= njobs) return;
-    const Lz4Job J = jobs[warp];
-    Lz4Chunk* C = chunks + J.chunk_base;
-    uint32_t run = 0;
-    bool good = true, ended = false, final_ok = false;
-    for (uint32_t base = 0; base < J.nchunks; base += 32) {
-        const uint32_t i = base + lane;
-        const bool in = i < J.nchunks;
-        const uint32_t fl = in ? C[i].flags_true : 0u;
-        const uint32_t stopm = __ballot_sync(0xffffffffu, in && (fl & (LZ4F_FINAL | LZ4F_ERR)) != 0);
-        // lanes up to and including the first stopping chunk of this group are live (if the chain has not ended yet)
-        const int firststop = stopm ? __ffs(stopm) - 1 : 32;
-        const bool live = in && !ended && lane <= firststop;
-        const uint32_t n = live ? C[i].n_true : 0u;
-        // a live chunk must be valid and start exactly where the previous live chunk's true walk ended
-        const uint32_t st = in ? C[i].start_true : 0u, prev_end = (in && i > 0) ? C[i - 1].end_true : 0u;
-        if (__any_sync(0xffffffffu, live && (C[i].valid == 0 || st == 0xffffffffu || st != prev_end))) good = false;
-        uint32_t incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-        if (in) {
-            if (live) C[i].out_off = run + incl - n;
-            else C[i].start_true = 0xffffffffu;
-        }
-        run += __shfl_sync(0xffffffffu, incl, 31);
-        if (!ended && stopm) {
-            ended = true;
-            final_ok = (__shfl_sync(0xffffffffu, fl, firststop) & (LZ4F_FINAL | LZ4F_ERR)) == LZ4F_FINAL;
-        }
-    }
-    if (lane == 0) par_ok[warp] = (good && ended && final_ok && run == J.orig && J.orig != 0) ? 1 : 0;
-#ifdef LZ4_DEBUG
-    if (lane == 0 && warp == 0) {
-        printf("lz4 scan: good %d ended %d final_ok %d run %u orig %u nchunks %u\n", (int)good, (int)ended, (int)final_ok, run, J.orig, J.nchunks);
-        int shown = 0;
-        for (uint32_t i = 0; i < J.nchunks && shown < 8; ++i)
-            if (!C[i].valid || (C[i].flags_true & 2) || (i && C[i].start_true != C[i - 1].end_true)) { printf("  chunk %u: valid %u flags %u/%u start_true %u end %u/%u nout %u n_true %u\n", i, C[i].valid, C[i].flags, C[i].flags_true, C[i].start_true, C[i].end, C[i].end_true, C[i].nout, C[i].n_true); ++shown; }
-    }
-#endif
-}
-
-__global__ void __launch_bounds__(LZ4_WARPS * 32)
-lz4_pwrite_kernel(const Lz4Job* __restrict__ jobs, int njobs, const Lz4Chunk* chunks, uint32_t total_chunks, int* par_ok)
-{
-    __shared__ uint4 ring_all[LZ4_WARPS][LZ4_RING / 16];
-    const int wslot = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * LZ4_WARPS + wslot;
-    if (g >= total_chunks) return;
-    int j; uint32_t c;
-    if (!lz4_chunk_of(jobs, njobs, g, j, c)) return;
-    if (!par_ok[j]) return;
-    const Lz4Chunk& C = chunks[g];
-    if (C.start_true == 0xffffffffu) return;                    // past the final sequence
-    const Lz4Job J = jobs[j];
-    const uint32_t p_end = (C.flags_true & LZ4F_FINAL) ? 0xffffffffu : C.end_true;
-    if (!lz4_write_walk(J, ring_all[wslot], lane, C.start_true, C.out_off, p_end) && lane == 0) par_ok[j] = 0;
-}
+#include "lz4_par.cuh"
 
 // the one-warp walk: every image the parallel path did not take (par_ok == nullptr: all images)
 __global__ void __launch_bounds__(LZ4_WARPS * 32)
@@ -541,6 +314,18 @@ bool plan_qoix(const uint8_t* d, size_t size, int flags, QoixPlan& P)
 
 namespace gb {
 
+static bool lz4_par_attr()          // function attributes are per device: one flag per device, set once each
+{
+    static std::atomic<unsigned long long> attr_mask{0};
+    const int dev = device_index();
+    const unsigned long long bit = dev >= 0 && dev < 64 ? 1ull << dev : 0;
+    if (bit && (attr_mask.load(std::memory_order_acquire) & bit)) return true;
+    if (!cuda_ok(cudaFuncSetAttribute(lz4_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZP_SMEM), "lz4 attr", __FILE__, __LINE__) ||
+        !cuda_ok(cudaFuncSetAttribute(lz4_pwrite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZP_SMEM), "lz4 attr", __FILE__, __LINE__)) return false;
+    attr_mask.fetch_or(bit, std::memory_order_release);
+    return true;
+}
+
 static bool p10_write_attr()        // function attributes are per device: one flag per device, set once each
 {
     static std::atomic<unsigned long long> attr_mask{0};
@@ -586,7 +371,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     std::vector<Lz4Job> lz; std::vector<P10Image> pj;
     std::vector<HostCopy> hcopies;
     size_t lzbm_total = 0;
-    uint32_t lz_chunks = 0;
+    uint32_t lz_chunks = 0, lz_sctas = 0, lz_wctas = 0;
     size_t rec_total = 0, row_total = 0; uint32_t total_chunks = 0, p10_sctas = 0, p10_wctas = 0;
     std::vector<SubJob> sub[4]; size_t sub_rows_total = 0;
     for (int i : live) {
@@ -597,9 +382,9 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
             uint8_t* dec = d_lz.as<uint8_t>() + lz_off[i];
             {
                 const uint32_t ilen = (uint32_t)(lens[i] - QOIX_HEADER_SIZE - 4);
-                const uint32_t nch = ilen >= 4 * LZ4_CHUNK ? (ilen + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;     // short blocks: one warp
-                lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, ilen, dec + QOIX_HEADER_SIZE, P[i].orig, i, (uint32_t*)lzbm_total, lz_chunks, nch});
-                lz_chunks += nch;
+                const uint32_t nch = ilen >= LZP_MIN_LEN ? (ilen + LZP_CHUNK - 1) / LZP_CHUNK : 0;     // short blocks: one warp
+                lz.push_back(Lz4Job{dev + QOIX_HEADER_SIZE + 4, ilen, dec + QOIX_HEADER_SIZE, P[i].orig, i, (uint32_t*)lzbm_total, lz_chunks, nch, lz_sctas, lz_wctas});
+                lz_chunks += nch; lz_sctas += (nch + LZP_OWN - 1) / LZP_OWN; lz_wctas += (nch + LZP_CTA - 1) / LZP_CTA;
             }
             lzbm_total += (((size_t)P[i].orig / 32 + 2 + 3) & ~(size_t)3) * 4;
             stream = dec; ssize = QOIX_HEADER_SIZE + P[i].orig;
@@ -634,9 +419,10 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     for (int c = 1; c < 4; ++c) { sub_first[c] = suball.size(); for (auto& S : sub[c]) { S.rows = d_subrows.as<uint8_t>() + (size_t)S.rows; suball.push_back(S); } }
     for (auto& J : pj) { J.recs = (uint32_t*)(d_recs.as<uint8_t>() + (size_t)J.recs); J.rowinfo = (uint32_t*)(d_rows.as<uint8_t>() + (size_t)J.rowinfo); }
     DevBuf d_lzj(sizeof(Lz4Job) * (lz.size() + 1)), d_pj(sizeof(P10Image) * (pj.size() + 1)), d_lzbm(lzbm_total + 1024),
-           d_lzch(sizeof(Lz4Chunk) * ((size_t)lz_chunks + 1)), d_lzok(sizeof(int) * (lz.size() + 1));
+           d_lzch(sizeof(Lz4Chunk) * ((size_t)lz_chunks + 1)), d_lzok(sizeof(int) * 2 * (lz.size() + 1)),
+           d_lzentry(4 * ((size_t)lz_sctas + 1));
     for (auto& L : lz) L.bitmap = (uint32_t*)(d_lzbm.as<uint8_t>() + (size_t)L.bitmap);
-    if (!d_lzj.p || !d_pj.p || !d_lzbm.p || !d_lzch.p || !d_lzok.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
+    if (!d_lzj.p || !d_pj.p || !d_lzbm.p || !d_lzch.p || !d_lzok.p || !d_lzentry.p) { if (h_stage) pinned_free(h_stage); delete B; return nullptr; }
     std::vector<int> ones((size_t)n, 1);
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
@@ -655,14 +441,19 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         okc &= dev_fill_async(d_lzbm.p, 0, lzbm_total + 1024, st);
         const unsigned g = (unsigned)((lz.size() + LZ4_WARPS - 1) / LZ4_WARPS);
         const Lz4Job* dj = d_lzj.as<Lz4Job>(); const int nj = (int)lz.size();
-        okc &= dev_fill_async(d_lzok.p, 0, sizeof(int) * (lz.size() + 1), st);
+        okc &= dev_fill_async(d_lzok.p, 0, sizeof(int) * 2 * (lz.size() + 1), st);
+        int* const par_ok = d_lzok.as<int>(); int* const par_bad = par_ok + lz.size() + 1;
         if (lz_chunks) {
-            const unsigned gc = (lz_chunks + LZ4_WARPS - 1) / LZ4_WARPS;
-            lz4_spec_kernel<<<gc, LZ4_WARPS * 32, 0, st>>>(dj, nj, d_lzch.as<Lz4Chunk>(), lz_chunks);
-            for (int round = 0; round < 3; ++round)       // later rounds only touch chunks whose predecessor's end moved
-                lz4_merge_kernel<<<(lz_chunks + 127) / 128, 128, 0, st>>>(dj, nj, d_lzch.as<Lz4Chunk>(), lz_chunks);
-            lz4_scan_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(dj, nj, d_lzch.as<Lz4Chunk>(), d_lzok.as<int>());
-            lz4_pwrite_kernel<<<gc, LZ4_WARPS * 32, 0, st>>>(dj, nj, d_lzch.as<Lz4Chunk>(), lz_chunks, d_lzok.as<int>());
+            // chunk-parallel walk (lz4_par.cuh): no host round trip; whatever does not add up goes to the one-warp walk
+            okc &= lz4_par_attr();
+            Lz4Chunk* ch = d_lzch.as<Lz4Chunk>(); uint32_t* entry = d_lzentry.as<uint32_t>();
+            const unsigned rg = (lz_sctas + 63) / 64;
+            lz4_sync_kernel<<<lz_sctas, LZP_CTA, LZP_SMEM, st>>>(dj, nj, ch, entry);
+            lz4_repair_kernel<<<rg, 64, 0, st>>>(dj, nj, lz_sctas, ch, entry, 0, par_bad);
+            lz4_repair_kernel<<<rg, 64, 0, st>>>(dj, nj, lz_sctas, ch, entry, 0, par_bad);
+            lz4_repair_kernel<<<rg, 64, 0, st>>>(dj, nj, lz_sctas, ch, entry, 1, par_bad);
+            lz4_scan_kernel<<<(unsigned)((lz.size() * 32 + 127) / 128), 128, 0, st>>>(dj, nj, ch, par_bad, par_ok);
+            lz4_pwrite_kernel<<<lz_wctas, LZP_CTA, LZP_SMEM, st>>>(dj, nj, ch, par_ok);
             count_launch(6);
         }
         lz4_parse_kernel<<<g, LZ4_WARPS * 32, 0, st>>>(dj, nj, d_status.as<int>(), d_lzok.as<int>());

@@ -330,19 +330,15 @@ p10_scan_kernel(const P10Image* __restrict__ imgs, const P10Chunk* __restrict__ 
 }
 
 // ---- A3. per-pixel records -------------------------------------------------------------------------------
-// Every chunk is parsed once more from its true entry state. A lane collects the records of the 32-record (128-byte)
-// segment of the record array it is in (word w of lane l at [l][(w + l) % 32]); when the next record belongs to another
-// segment the whole warp writes the finished one out as one coalesced row -- records reach memory in full lines
-// although every lane walks its own part of the image.
-constexpr size_t P10_WRITE_SMEM = sizeof(uint32_t) * (P10_STAGE_WORDS + 256 + P10_CTA * 32);
+// Every chunk is parsed once more from its true entry state. A lane collects its records four at a time in
+// registers and stores them as one aligned 16-byte vector (single records only at the two ends of its part of the
+// image); long runs are placed by the whole warp, 32 records per step, straight into memory.
 __global__ void __launch_bounds__(P10_CTA)
 p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* __restrict__ chunks,
                  const P10Entry* __restrict__ entries)
 {
-    extern __shared__ __align__(16) uint32_t p10w_smem[];
-    uint32_t* const s_words = p10w_smem;                          // [P10_STAGE_WORDS]
-    uint32_t* const s_lut = s_words + P10_STAGE_WORDS;            // [256]
-    uint32_t (*const s_rows)[32] = (uint32_t (*)[32])(s_lut + 256);   // [P10_CTA][32]
+    __shared__ uint32_t s_words[P10_STAGE_WORDS];
+    __shared__ uint32_t s_lut[256];
     const int tid = threadIdx.x, lane = tid & 31;
     const P10Image& im = imgs[p10_find_image<2>(imgs, nimgs, blockIdx.x)];
     const uint32_t lc0 = (blockIdx.x - im.wcta_base) * P10_CTA;
@@ -364,15 +360,12 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
     }
     const uint32_t limit = min((lc + 1) * (uint32_t)P10_CHUNK_BITS, total_bits);
     alive = alive && bp < limit;
-    const uint32_t Wd = im.w, skip = im.wp - im.w;
+    const uint32_t Wd = im.w, WP = im.wp, skip = im.wp - im.w;
     uint32_t y = alive ? i / Wd : 0u, x = alive ? i - y * Wd : 0u;
-    uint32_t addr = y * im.wp + x;                                // index into the record array
-    uint32_t seg = addr >> 5, lo = 32, hi = 0;                    // my segment and the part of it I have written
-    uint32_t pend_n = 0, pend_rec = 0, pend_p0 = 0;               // records of the current opcode not yet placed
+    uint32_t addr = y * WP + x;                                   // index into the record array
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, qmask = 0;           // records of the aligned group of four `addr` is in
     uint32_t a_pend = 0; bool ing = false;                        // inside a group: alpha an ADIFF has announced
-    uint32_t* const myrow = s_rows[tid];
-    const uint32_t* const wrow = s_rows[tid & ~31];
-    uint32_t* const recs = im.recs; uint32_t* const rowinfo = im.rowinfo; const uint32_t WP = im.wp;
+    uint32_t* const recs = im.recs; uint32_t* const rowinfo = im.rowinfo;
     P10Reader<P10Shared> R{W};
     __syncthreads();
     R.init(alive ? bp - origin : 0u);
@@ -386,8 +379,20 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
         }
         return info;
     };
-    for (;;) {
-        if (alive && pend_n == 0) {
+    auto flush_group = [&]() {           // the group that ends just before (or contains) addr - 1
+        uint32_t* g = recs + ((addr - 1) & ~3u);
+        if (qmask == 15u) *(uint4*)g = make_uint4(q0, q1, q2, q3);
+        else {
+            if (qmask & 1u) g[0] = q0;
+            if (qmask & 2u) g[1] = q1;
+            if (qmask & 4u) g[2] = q2;
+            if (qmask & 8u) g[3] = q3;
+        }
+        qmask = 0;
+    };
+    while (__any_sync(0xffffffffu, alive)) {
+        uint32_t n = 0, rec = 0;
+        if (alive) {
             const uint32_t v = R.peek();
             const uint32_t e = s_lut[v >> 24];
             const uint32_t len = e & 31u;
@@ -399,60 +404,46 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
                 if (e & P10L_ALPHA) a = (v >> 4) & 1023u;                  // LA
                 else if (ing) a = a_pend;
                 ing = false;
-                const uint32_t n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
+                n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
                 const uint32_t kind = ((e >> 22) & 3u) << 10;
                 const uint32_t val = (kind & P10_REC_COPY) ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
-                pend_rec = kind | val | (((a << 6) | (a >> 4)) << 16);
-                pend_n = min(n, np - i); pend_p0 = i;
+                rec = kind | val | (((a << 6) | (a >> 4)) << 16);
+                n = min(n, np - i);
                 bp += len; R.drop((int)len);
                 if (bp >= limit) alive = false;                   // the next group starts in a later chunk
             }
         }
         // long runs: the whole warp places the records of one lane's run straight into memory, 32 per step (a lane
         // on its own would keep the other 31 waiting for up to 262 steps)
-        uint32_t big = __ballot_sync(0xffffffffu, pend_n >= 8);
+        uint32_t big = __ballot_sync(0xffffffffu, n >= 8);
+        if (n >= 8 && qmask) flush_group();
         while (big) {
             const int l = __ffs(big) - 1; big &= big - 1;
-            const uint32_t rn = __shfl_sync(0xffffffffu, pend_n, l), rrec = __shfl_sync(0xffffffffu, pend_rec, l);
+            const uint32_t rn = __shfl_sync(0xffffffffu, n, l), rrec = __shfl_sync(0xffffffffu, rec, l);
             const uint32_t ri = __shfl_sync(0xffffffffu, i, l), rx = __shfl_sync(0xffffffffu, x, l), ry = __shfl_sync(0xffffffffu, y, l);
-            const uint32_t rp0 = __shfl_sync(0xffffffffu, pend_p0, l);
-            const uint32_t sg = __shfl_sync(0xffffffffu, seg, l), flo = __shfl_sync(0xffffffffu, lo, l), fhi = __shfl_sync(0xffffffffu, hi, l);
-            __syncwarp();
-            if ((uint32_t)lane >= flo && (uint32_t)lane < fhi) recs[(size_t)sg * 32 + lane] = wrow[l * 32 + ((lane + l) & 31)];
             for (uint32_t j = lane; j < rn; j += 32) {
                 const uint32_t xx0 = rx + j, dy = xx0 / Wd, xx = xx0 - dy * Wd, yy = ry + dy;
                 recs[(size_t)yy * WP + xx] = rrec;
-                if (xx == 0) rowinfo[yy] = row_info(rrec, ri + j, yy, rp0);
+                if (xx == 0) rowinfo[yy] = row_info(rrec, ri + j, yy, ri);
             }
-            __syncwarp();
             if (lane == l) {
-                const uint32_t xx0 = x + pend_n, dy = xx0 / Wd;
-                i += pend_n; x = xx0 - dy * Wd; y += dy; addr = y * WP + x;
-                pend_n = 0; seg = addr >> 5; lo = 32; hi = 0;
+                const uint32_t xx0 = x + n, dy = xx0 / Wd;
+                i += n; x = xx0 - dy * Wd; y += dy; addr = y * WP + x;
+                n = 0;
             }
         }
-        while (pend_n && (addr >> 5) == seg) {
-            if (x == 0) rowinfo[y] = row_info(pend_rec, i, y, pend_p0);
-            const uint32_t w = addr & 31u;
-            myrow[(w + lane) & 31] = pend_rec;
-            lo = min(lo, w); hi = w + 1;
-            --pend_n; ++i; ++addr;
-            if (++x == Wd) { x = 0; ++y; addr += skip; }
+        const uint32_t p0 = i;
+        while (n) {
+            if (x == 0) rowinfo[y] = row_info(rec, i, y, p0);
+            const uint32_t k = addr & 3u;
+            q0 = k == 0 ? rec : q0; q1 = k == 1 ? rec : q1; q2 = k == 2 ? rec : q2; q3 = k == 3 ? rec : q3;
+            qmask |= 1u << k;
+            --n; ++i; ++addr;
+            if (k == 3) flush_group();
+            if (++x == Wd) { x = 0; ++y; if (skip) { if (qmask) flush_group(); addr += skip; } }
         }
-        if (i >= np) { alive = false; pend_n = 0; }
-        const bool flush = hi > lo && ((addr >> 5) != seg || (!alive && pend_n == 0));
-        uint32_t fb = __ballot_sync(0xffffffffu, flush);
-        if (!__any_sync(0xffffffffu, alive || pend_n)) { if (!fb) break; }
-        if (fb) {
-            __syncwarp();
-            while (fb) {
-                const int l = __ffs(fb) - 1; fb &= fb - 1;
-                const uint32_t sg = __shfl_sync(0xffffffffu, seg, l), flo = __shfl_sync(0xffffffffu, lo, l), fhi = __shfl_sync(0xffffffffu, hi, l);
-                if ((uint32_t)lane >= flo && (uint32_t)lane < fhi) recs[(size_t)sg * 32 + lane] = wrow[l * 32 + ((lane + l) & 31)];
-            }
-            __syncwarp();
-            if (flush) { seg = addr >> 5; lo = 32; hi = 0; }
-        }
+        if (i >= np) alive = false;
+        if (!alive && qmask) flush_group();
     }
 }
 

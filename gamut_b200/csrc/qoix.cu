@@ -326,17 +326,6 @@ static bool lz4_par_attr()          // function attributes are per device: one f
     return true;
 }
 
-static bool p10_write_attr()        // function attributes are per device: one flag per device, set once each
-{
-    static std::atomic<unsigned long long> attr_mask{0};
-    const int dev = device_index();
-    const unsigned long long bit = dev >= 0 && dev < 64 ? 1ull << dev : 0;
-    if (bit && (attr_mask.load(std::memory_order_acquire) & bit)) return true;
-    if (!cuda_ok(cudaFuncSetAttribute(p10_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P10_WRITE_SMEM), "p10 attr", __FILE__, __LINE__)) return false;
-    attr_mask.fetch_or(bit, std::memory_order_release);
-    return true;
-}
-
 gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                const uint8_t* const* files_dev, int flags, cudaStream_t st)
 {
@@ -474,7 +463,7 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
         const P10Image* dI = d_pj.as<P10Image>(); const int ni = (int)pj.size();
         uint32_t* ndec = d_misc.as<uint32_t>() + 64;
         p10_scan_kernel<<<ni, 256, 0, st>>>(dI, d_chunks.as<P10Chunk>(), d_entries.as<P10Entry>(), ndec);
-        p10_write_kernel<<<p10_wctas, P10_CTA, P10_WRITE_SMEM, st>>>(dI, ni, d_chunks.as<P10Chunk>(), d_entries.as<P10Entry>());
+        p10_write_kernel<<<p10_wctas, P10_CTA, 0, st>>>(dI, ni, d_chunks.as<P10Chunk>(), d_entries.as<P10Entry>());
         p10_recon_kernel<1><<<ni, 32 * P10_RECON_WARPS, 0, st>>>(dI, ndec, d_status.as<int>());
         p10_recon_kernel<2><<<ni, 32 * P10_RECON_WARPS, 0, st>>>(dI, ndec, d_status.as<int>());
         count_launch(4);
@@ -487,7 +476,6 @@ gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t*
     if (!pj.empty()) {
         // QOI-Plane10: chunk-parallel parse (self-synchronising, relaxed inside the CTA), boundary repair, scan,
         // per-pixel records, wavefront reconstruction -- no host round trip
-        okc &= p10_write_attr();
         okc &= dev_fill_async(p10_unconv, 0, 4, st);
         p10_sync_kernel<<<p10_sctas, P10_CTA, 0, st>>>(d_pj.as<P10Image>(), (int)pj.size(), d_chunks.as<P10Chunk>(), d_sentry.as<uint32_t>());
         count_launch();

@@ -28,16 +28,19 @@ enum { GRAYSCALE = 0, YH1V1, YH2V1, YH1V2, YH2V2 };
 constexpr int HUFF_FAST = 10;
 constexpr int HT_L1_BITS = 9, HT_L2_BITS = 7, HT_SUBS = 6;
 static_assert(true, "");
-constexpr uint16_t HT_LONG = 0x8000, HT_SLOW = 0x4000, HT_DC = 0x2000;
+constexpr uint16_t HT_LONG = 0x8000;
+constexpr int HT_KINC_EOB = 63;      // zig-zag advance that ends the block from any AC position (k >= 1)
 struct alignas(16) HuffTable {   // canonical JPEG code (Annex C) + 10-bit lookahead
     uint16_t fast[1 << HUFF_FAST];   // (len << 8) | symbol, 0 = longer than HUFF_FAST bits / invalid
     int32_t maxcode[18];             // maxcode[l] for l = 1..16, -1 if none
     int32_t mincode[18];
     int32_t valptr[18];
     uint8_t val[256];
-    // two-level table of the chunk-parallel decoders (copied to shared memory): entry = len (bits 0-4, 0 = no code) |
-    // size << 5 | run << 9 | HT_DC. An l1 entry with HT_LONG set points at the l2 sub-table (bits 0-2) indexed by the
-    // next 7 bits; HT_SLOW = more long-code prefixes than sub-tables (decode through maxcode/valptr).
+    // two-level table of the chunk-parallel decoders (copied to shared memory): entry = len (bits 0-4, 0 = not a code
+    // word) | size << 5 | kinc << 9, kinc = how far the symbol moves the zig-zag index: 1 for a DC symbol, run + 1 for
+    // an AC coefficient, 16 for ZRL, HT_KINC_EOB for EOB (jpegload.d:2466-2507) -- one add per symbol instead of a
+    // case distinction. An l1 entry with HT_LONG set points at the l2 sub-table (bits 0-2) indexed by the next 7 bits;
+    // sub-table 7 = more long-code prefixes than sub-tables (decode through maxcode/valptr).
     int32_t is_dc;
     alignas(16) uint16_t l1[1 << HT_L1_BITS];     // 16-byte aligned: copied to shared memory by 16-byte vectors
     uint16_t l2[HT_SUBS][1 << HT_L2_BITS];
@@ -1189,6 +1192,10 @@ void build_table(const HostHuff& h, HuffTable& T, bool is_dc)
     memset(&T, 0, sizeof(T));
     memcpy(T.val, h.val, 256);
     T.is_dc = is_dc ? 1 : 0;
+    // what is not a code word reads as one bit that moves a DC position on and ends the block from an AC position
+    const uint16_t bad_e = (uint16_t)((is_dc ? 1 : HT_KINC_EOB) << 9);
+    for (auto& v : T.l1) v = bad_e;
+    for (auto& sub : T.l2) for (auto& v : sub) v = bad_e;
     int code = 0, k = 0, nsubs = 0;
     int sub_of[1 << HT_L1_BITS];
     for (int& v : sub_of) v = -1;
@@ -1203,14 +1210,16 @@ void build_table(const HostHuff& h, HuffTable& T, bool is_dc)
             }
             // a DC symbol is a size 0..15; anything else is not a code word for the decoders
             const bool valid = !is_dc || sym <= 15;
-            const uint16_t e = valid ? (uint16_t)(l | ((sym & 15) << 5) | ((is_dc ? 0 : (sym >> 4)) << 9) | (is_dc ? HT_DC : 0)) : (uint16_t)0;
+            const int size = sym & 15, run = sym >> 4;
+            const int kinc = is_dc ? 1 : (size ? run + 1 : (run == 15 ? 16 : HT_KINC_EOB));
+            const uint16_t e = valid ? (uint16_t)(l | (size << 5) | (kinc << 9)) : bad_e;
             if (l <= HT_L1_BITS) {
                 const int shift = HT_L1_BITS - l;
                 for (int f = 0; f < (1 << shift); ++f) T.l1[(code << shift) | f] = e;
             } else {
                 const int prefix = code >> (l - HT_L1_BITS);
                 if (sub_of[prefix] < 0) sub_of[prefix] = nsubs < HT_SUBS ? nsubs++ : HT_SUBS;
-                if (sub_of[prefix] == HT_SUBS) { T.l1[prefix] = HT_SLOW; continue; }
+                if (sub_of[prefix] == HT_SUBS) { T.l1[prefix] = (uint16_t)(HT_LONG | 7); continue; }
                 T.l1[prefix] = (uint16_t)(HT_LONG | sub_of[prefix]);
                 const int rest = code & ((1 << (l - HT_L1_BITS)) - 1), shift = HT_L1_BITS + HT_L2_BITS - l;
                 for (int f = 0; f < (1 << shift); ++f) T.l2[sub_of[prefix]][(rest << shift) | f] = e;

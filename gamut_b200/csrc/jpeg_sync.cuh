@@ -47,11 +47,18 @@ struct ChunkState { uint32_t bitpos; uint32_t bik; };               // bik = bi 
 struct __align__(16) ChunkRec { uint32_t bitpos, bik, nblk; int dc0, dc1, dc2; uint32_t pad0, pad1; };   // 32 B
 struct __align__(16) ChunkBase { uint32_t blk; int dc0, dc1, dc2; };                                     // 16 B
 
-// The two-level tables of HuffTable (l1 / l2) of the up to six tables of one image, in shared memory.
-struct __align__(16) FastTables {                           // [comp * 2 + (0 = DC, 1 = AC)]
-    uint16_t l1[6][1 << HT_L1_BITS];
-    uint16_t l2[6][HT_SUBS << HT_L2_BITS];
-};
+// The two-level tables of HuffTable (l1 then l2, contiguous) of the up to six tables of one image, in shared memory:
+// table t = comp * 2 + (0 = DC, 1 = AC) at byte offset t * JS_TBL_BYTES. Addressed through 32-bit shared addresses
+// (ld.shared with a register offset) rather than generic pointers.
+constexpr uint32_t JS_L1_BYTES = sizeof(uint16_t) << HT_L1_BITS, JS_L2_BYTES = sizeof(uint16_t) * (HT_SUBS << HT_L2_BITS);
+constexpr uint32_t JS_TBL_BYTES = JS_L1_BYTES + JS_L2_BYTES;
+struct __align__(16) FastTables { uint8_t b[6 * JS_TBL_BYTES]; };
+static_assert(offsetof(HuffTable, l2) == offsetof(HuffTable, l1) + JS_L1_BYTES, "l1 and l2 are copied as one block");
+
+__device__ __forceinline__ uint32_t js_lds16(uint32_t saddr)
+{
+    uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v;
+}
 
 __device__ __forceinline__ uint32_t js_find_seg(const LongSeg* __restrict__ segs, int nsegs, uint32_t cta)
 {
@@ -154,103 +161,118 @@ struct JsBits {
 
 struct JsImageCtx {            // per-CTA copy of what the decoders need from JpegImage
     int bpm; int comp_of[10]; int tab[6];     // tab[comp * 2 + (is AC)] = index into the global HuffTable array
+    uint32_t comp_packed;                     // comp_of, two bits per block of the MCU
 };
 
-// One Huffman symbol at the head of the bit buffer (>= 32 valid bits): code length, run and size. A bit pattern that
-// is no code word (or a DC symbol > 15) yields bad = true with len = 1, run = size = 0, so that speculative decoders
-// keep moving. `t` = comp * 2 + (is AC).
-__device__ __forceinline__ void js_symbol(const FastTables& ft, int t, const JsImageCtx& cx, const HuffTable* __restrict__ tables,
-                                          uint32_t top, int& len, int& run, int& size, bool& bad)
+// Canonical decode of the 10..16-bit codes of a table with more long-code prefixes than sub-tables; result in the
+// format of a table entry (len 0 = not a code word).
+__device__ __noinline__ uint32_t js_slow_symbol(const HuffTable* __restrict__ h, uint32_t top)
 {
-    uint32_t e = ft.l1[t][top >> (32 - HT_L1_BITS)];
-    if (e & HT_LONG) e = ft.l2[t][((e & 7) << HT_L2_BITS) | ((top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1 << HT_L2_BITS) - 1))];
-    bad = false;
-    len = e & 31; size = (e >> 5) & 15; run = (e >> 9) & 15;
-    if (len && !(e & HT_SLOW)) return;
-    const HuffTable* slow = tables + cx.tab[t];
-    int sym = -1; len = 1;
-    if (e & HT_SLOW) {       // more long-code prefixes than sub-tables: canonical decode of the 10..16-bit codes
-        const uint32_t top16 = top >> 16;
-#pragma unroll 1
-        for (int l = HT_L1_BITS + 1; l <= 16; ++l) {
-            const int code = (int)(top16 >> (16 - l));
-            if (code <= slow->maxcode[l] && code >= slow->mincode[l]) { len = l; sym = slow->val[slow->valptr[l] + code - slow->mincode[l]]; break; }
-        }
-        if (sym >= 0 && slow->is_dc && sym > 15) { sym = -1; len = 1; }
+    const uint32_t top16 = top >> 16;
+    int sym = -1, len = 0;
+    for (int l = HT_L1_BITS + 1; l <= 16; ++l) {
+        const int code = (int)(top16 >> (16 - l));
+        if (code <= h->maxcode[l] && code >= h->mincode[l]) { len = l; sym = h->val[h->valptr[l] + code - h->mincode[l]]; break; }
     }
-    if (sym < 0) { bad = true; size = 0; run = 0; return; }
-    size = sym & 15; run = slow->is_dc ? 0 : sym >> 4;
+    if (sym >= 0 && h->is_dc && sym > 15) sym = -1;
+    if (sym < 0) return (uint32_t)(h->is_dc ? 1 : HT_KINC_EOB) << 9;
+    const int size = sym & 15, run = sym >> 4;
+    return (uint32_t)(len | (size << 5) | ((h->is_dc ? 1 : (size ? run + 1 : (run == 15 ? 16 : HT_KINC_EOB))) << 9));
+}
+
+// One Huffman symbol at the head of the bit buffer (>= 32 valid bits) through table t = comp * 2 + (is AC): the table
+// entry (len | size << 5 | kinc << 9, len 0 = the bits are no code word). The second-level lookup is predicated,
+// not a branch: the lanes of a warp are at different symbols.
+__device__ __forceinline__ uint32_t js_symbol(uint32_t tabs, int t, const JsImageCtx& cx, const HuffTable* __restrict__ tables, uint32_t top)
+{
+    const uint32_t tb = tabs + (uint32_t)t * JS_TBL_BYTES;
+    const uint32_t e1 = js_lds16(tb + ((top >> (32 - HT_L1_BITS)) << 1));
+    uint32_t e = e1;
+    if (e1 & HT_LONG) e = js_lds16(tb + JS_L1_BYTES + (((min(e1 & 7u, (uint32_t)HT_SUBS - 1u) << HT_L2_BITS) | ((top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1u << HT_L2_BITS) - 1u))) << 1));
+    if ((e1 & (HT_LONG | 7u)) == (HT_LONG | 7u)) e = js_slow_symbol(tables + cx.tab[t], top);       // rare
+    return e;
 }
 
 // Same symbol through the two-level tables in global memory (used where threads of one CTA serve different images).
-__device__ __forceinline__ void js_symbol_global(const HuffTable* __restrict__ h, uint32_t top, int& len, int& run, int& size, bool& bad)
+__device__ __forceinline__ uint32_t js_symbol_global(const HuffTable* __restrict__ h, uint32_t top)
 {
     uint32_t e = h->l1[top >> (32 - HT_L1_BITS)];
-    if (e & HT_LONG) e = h->l2[e & 7][(top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1 << HT_L2_BITS) - 1)];
-    bad = false;
-    if ((e & 31) && !(e & HT_SLOW)) { len = e & 31; size = (e >> 5) & 15; run = (e >> 9) & 15; return; }
-    int sym = -1; len = 1;
-    if (e & HT_SLOW) {
-        const uint32_t top16 = top >> 16;
-#pragma unroll 1
-        for (int l = HT_L1_BITS + 1; l <= 16; ++l) {
-            const int code = (int)(top16 >> (16 - l));
-            if (code <= h->maxcode[l] && code >= h->mincode[l]) { len = l; sym = h->val[h->valptr[l] + code - h->mincode[l]]; break; }
-        }
-        if (sym >= 0 && h->is_dc && sym > 15) { sym = -1; len = 1; }
+    if (e & HT_LONG) {
+        if ((e & 7u) == 7u) return js_slow_symbol(h, top);
+        e = h->l2[e & 7][(top >> (32 - HT_L1_BITS - HT_L2_BITS)) & ((1 << HT_L2_BITS) - 1)];
     }
-    if (sym < 0) { bad = true; size = 0; run = 0; return; }
-    size = sym & 15; run = h->is_dc ? 0 : sym >> 4;
+    return e;
+}
+
+// the value of `size` extra bits at the head of x (left-aligned), JPGD_HUFF_EXTEND (jpegload.d:816-822) without a branch:
+// a leading 1 bit means the value is positive
+__device__ __forceinline__ int js_extend(uint32_t x, uint32_t size)
+{
+    const uint32_t v = __funnelshift_l(x, 0u, size);                   // the top `size` bits of x, 0 for size 0
+    return (int)v - (int)(((1u << size) - 1u) & ~(uint32_t)((int)x >> 31));
 }
 
 __device__ __forceinline__ void js_load_tables(FastTables& ft, JsImageCtx& cx, const JpegImage& im, const HuffTable* __restrict__ tables, int tid, int nthreads)
 {
     if (tid == 0) {
         cx.bpm = im.blocks_per_mcu;
-        for (int b = 0; b < 10; ++b) cx.comp_of[b] = b < im.blocks_per_mcu ? im.mcu_org[b] : 0;
+        uint32_t pk = 0;
+        for (int b = 0; b < 10; ++b) { cx.comp_of[b] = b < im.blocks_per_mcu ? im.mcu_org[b] : 0; pk |= (uint32_t)(cx.comp_of[b] & 3) << (2 * b); }
+        cx.comp_packed = pk;
         for (int c = 0; c < 3; ++c) { cx.tab[c * 2] = im.dc_tab[c < im.comps ? c : 0]; cx.tab[c * 2 + 1] = im.ac_tab[c < im.comps ? c : 0]; }
     }
-    // 16-byte copies of l1 (1 KB) and l2 (2 KB) of every table in use; unused slots are never indexed
+    // 16-byte copies of l1 + l2 (2.5 KB) of every table in use; unused slots are never indexed
     const int comps = im.comps;
-    constexpr int V1 = (int)(sizeof(uint16_t) << HT_L1_BITS) / 16, V2 = (int)(sizeof(uint16_t) * HT_SUBS << HT_L2_BITS) / 16;
-    for (int i = tid; i < 6 * (V1 + V2); i += nthreads) {
-        const int t = i / (V1 + V2), r = i - t * (V1 + V2);
+    constexpr int V = (int)(JS_TBL_BYTES / 16);
+    for (int i = tid; i < 6 * V; i += nthreads) {
+        const int t = i / V, r = i - t * V;
         const int c = t >> 1;
         if (c >= comps) continue;
         const HuffTable* h = tables + ((t & 1) ? im.ac_tab[c] : im.dc_tab[c]);
-        if (r < V1) ((uint4*)ft.l1[t])[r] = __ldg((const uint4*)h->l1 + r);
-        else ((uint4*)ft.l2[t])[r - V1] = __ldg((const uint4*)h->l2 + (r - V1));
+        ((uint4*)(ft.b + (size_t)t * JS_TBL_BYTES))[r] = __ldg((const uint4*)h->l1 + r);
     }
 }
 
 // Decodes the symbols that START in [st.bitpos, limit) without storing anything: exit state, blocks completed, and
-// the sum of the DC differences per component. One straight-line body for DC and AC symbols (the lanes of a warp are
-// at different symbols), the component of the current block lives in a register.
+// the sum of the DC differences per component. One straight-line body per symbol whatever its kind (the lanes of a
+// warp are at different symbols): the table entry says how far the zig-zag index moves, a DC difference is kept until
+// its block ends (or the chunk does) and added to its component's sum there.
 __device__ __forceinline__ void js_scan_chunk(const uint32_t* __restrict__ words, ChunkState& st, uint32_t limit,
-                                              const FastTables& ft, const JsImageCtx& cx, const HuffTable* __restrict__ tables,
+                                              uint32_t tabs, const JsImageCtx& cx, const HuffTable* __restrict__ tables,
                                               uint32_t& nblocks, int dcs[3])
 {
     int bi = st.bik & 0xffff, k = st.bik >> 16;
     const int bpm = cx.bpm;
-    int comp = cx.comp_of[bi];
+    const uint32_t cpk = cx.comp_packed;
+    int comp = (int)((cpk >> (2 * bi)) & 3u);
     uint32_t nb = 0;
-    int d0 = 0, d1 = 0, d2 = 0;
+    int d0 = 0, d1 = 0, d2 = 0, cur_dc = 0;
     JsBits br; br.init(words, st.bitpos);
     uint32_t pos = st.bitpos;
     while (pos < limit) {
         br.refill();
         const bool is_dc = k == 0;
         const uint32_t top = br.top32();
-        int len, run, size; bool bad;
-        js_symbol(ft, comp * 2 + (is_dc ? 0 : 1), cx, tables, top, len, run, size, bad);
-        const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
-        const int diff = is_dc ? huff_extend((int)extra, size) : 0;
-        d0 += comp == 0 ? diff : 0; d1 += comp == 1 ? diff : 0; d2 += comp == 2 ? diff : 0;
-        k = is_dc ? 1 : (size ? k + run + 1 : (run == 15 ? k + 16 : 64));
-        br.drop(len + size);
-        pos += (uint32_t)(len + size);
-        if (k >= 64) { k = 0; ++nb; bi = bi + 1 == bpm ? 0 : bi + 1; comp = cx.comp_of[bi]; }
+        const uint32_t e = js_symbol(tabs, comp * 2 + (is_dc ? 0 : 1), cx, tables, top);
+        uint32_t len = e & 31u;
+        const uint32_t size = (e >> 5) & 15u;
+        len += len == 0 ? 1u : 0u;                               // no code word: one bit, and the decoders keep moving
+        const int diff = js_extend(top << len, size);
+        cur_dc = is_dc ? diff : cur_dc;
+        k += (int)((e >> 9) & 63u);
+        br.drop((int)(len + size));
+        pos += len + size;
+        const bool end = k >= 64;
+        d0 += (end && comp == 0) ? cur_dc : 0; d1 += (end && comp == 1) ? cur_dc : 0; d2 += (end && comp == 2) ? cur_dc : 0;
+        cur_dc = end ? 0 : cur_dc;
+        nb += end ? 1u : 0u;
+        k = end ? 0 : k;
+        const int nbi = bi + 1 == bpm ? 0 : bi + 1;
+        bi = end ? nbi : bi;
+        comp = (int)((cpk >> (2 * bi)) & 3u);
     }
+    // the DC difference of a block in progress belongs to this chunk if its DC symbol started here
+    d0 += comp == 0 ? cur_dc : 0; d1 += comp == 1 ? cur_dc : 0; d2 += comp == 2 ? cur_dc : 0;
     st.bitpos = pos; st.bik = (uint32_t)bi | ((uint32_t)k << 16);
     nblocks = nb; dcs[0] = d0; dcs[1] = d1; dcs[2] = d2;
 }
@@ -274,6 +296,7 @@ jpeg_sync_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict
     const LongSeg sg = segs[si];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     js_load_tables(ft, cx, images[sg.image], tables, tid, JS_CTA);
+    const uint32_t tabs = (uint32_t)__cvta_generic_to_shared(ft.b);
     const uint32_t local_cta = blockIdx.x - sg.cta_base;
     // chunk of slot s: the first JS_WARM slots re-decode the tail of the previous CTA's range
     const long long lc_first = (long long)local_cta * JS_OWN - JS_WARM;
@@ -292,7 +315,7 @@ jpeg_sync_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict
         ChunkState st; st.bitpos = lc * JS_CHUNK_BITS; st.bik = 0;
         s_entry[tid] = make_uint2(st.bitpos, st.bik);
         uint32_t nb = 0; int dcs[3] = {0, 0, 0};
-        if (active) js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), ft, cx, tables, nb, dcs);
+        if (active) js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), tabs, cx, tables, nb, dcs);
         else { st.bitpos = total_bits; st.bik = 0; }
         s_exit[tid] = make_uint2(st.bitpos, st.bik);
         s_res[tid] = make_uint4(nb, (uint32_t)dcs[0], (uint32_t)dcs[1], (uint32_t)dcs[2]);
@@ -320,7 +343,7 @@ jpeg_sync_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict
             const uint32_t lc = (uint32_t)(lc_first + s);
             ChunkState st; st.bitpos = e.x; st.bik = e.y;
             uint32_t nb = 0; int dcs[3];
-            js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), ft, cx, tables, nb, dcs);
+            js_scan_chunk(words, st, min((lc + 1) * (uint32_t)JS_CHUNK_BITS, total_bits), tabs, cx, tables, nb, dcs);
             s_entry[s] = e;
             s_exit[s] = make_uint2(st.bitpos, st.bik);
             s_res[s] = make_uint4(nb, (uint32_t)dcs[0], (uint32_t)dcs[1], (uint32_t)dcs[2]);
@@ -376,14 +399,12 @@ jpeg_repair_kernel(const JpegImage* __restrict__ images, const LongSeg* __restri
             const int comp = im.mcu_org[bi];
             const bool is_dc = k == 0;
             const uint32_t top = br.top32();
-            int len, run, size; bool bad;
-            js_symbol_global(tables + (is_dc ? im.dc_tab[comp] : im.ac_tab[comp]), top, len, run, size, bad);
-            if (is_dc) {
-                const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
-                d[comp] += huff_extend((int)extra, size);
-                k = 1;
-            } else k = size ? k + run + 1 : (run == 15 ? k + 16 : 64);
-            br.drop(len + size); pos += (uint32_t)(len + size);
+            const uint32_t e = js_symbol_global(tables + (is_dc ? im.dc_tab[comp] : im.ac_tab[comp]), top);
+            uint32_t len = e & 31u; const uint32_t size = (e >> 5) & 15u;
+            if (len == 0) len = 1;
+            if (is_dc) d[comp] += js_extend(top << len, size);
+            k += (int)((e >> 9) & 63u);
+            br.drop((int)(len + size)); pos += len + size;
             if (k >= 64) { k = 0; ++nb; bi = bi + 1 == im.blocks_per_mcu ? 0 : bi + 1; }
         }
         st.bitpos = pos; st.bik = (uint32_t)bi | ((uint32_t)k << 16);
@@ -463,6 +484,7 @@ jpeg_write_kernel(const JpegImage* __restrict__ images, const LongSeg* __restric
     const JpegImage& im = images[sg.image];
     const int tid = threadIdx.x, lane = tid & 31;
     js_load_tables(ft, cx, im, tables, tid, JW_CTA);
+    const uint32_t tabs = (uint32_t)__cvta_generic_to_shared(ft.b);
     for (int i = tid; i < 192; i += JW_CTA) s_quant[i >> 6][i & 63] = (i >> 6) < im.comps ? im.quant[i >> 6][i & 63] : (int16_t)0;
     if (tid < 64) s_zag[tid] = c_zag[tid];
 #pragma unroll
@@ -503,26 +525,26 @@ jpeg_write_kernel(const JpegImage* __restrict__ images, const LongSeg* __restric
             br.refill();
             const bool is_dc = k == 0;
             const uint32_t top = br.top32();
-            int len, run, size; bool bad;
-            js_symbol(ft, comp * 2 + (is_dc ? 0 : 1), cx, tables, top, len, run, size, bad);
-            const uint32_t extra = size ? ((top << len) >> (32 - size)) : 0u;
-            int val = huff_extend((int)extra, size);
+            const uint32_t e = js_symbol(tabs, comp * 2 + (is_dc ? 0 : 1), cx, tables, top);
+            bool bad = (e & 31u) == 0;
+            const int len = (int)(e & 31u) + (bad ? 1 : 0), size = (int)((e >> 5) & 15u), kinc = (int)((e >> 9) & 63u);
+            int val = js_extend(top << len, (uint32_t)size);
             if (is_dc) {
                 mine = true;
                 val += comp == 0 ? dc0 : comp == 1 ? dc1 : dc2;
                 dc0 = comp == 0 ? val : dc0; dc1 = comp == 1 ? val : dc1; dc2 = comp == 2 ? val : dc2;
                 last_k = 0;
             } else if (size) {
-                k += run;
+                k += kinc - 1;                       // the run of zeros before the coefficient
                 if (k > 63) { bad = true; k = 63; }
-            } else if (run == 15 && k + 16 > 64) bad = true;
+            } else if (kinc == 16 && k + 16 > 64) bad = true;
             if (mine && bad) ok = false;
             if (mine && (is_dc || size)) {
                 const int zz = s_zag[k];
                 ((int16_t*)(myrow + (((zz >> 1) + lane) & 31)))[zz & 1] = (int16_t)(val * s_quant[comp][k]);
                 last_k = k;
             }
-            k = is_dc ? 1 : (size ? k + 1 : (run == 15 ? k + 16 : 64));
+            k = is_dc ? 1 : (size ? k + 1 : (kinc == 16 ? k + 16 : 64));
             br.drop(len + size);
             pos += (uint32_t)(len + size);
             flush = k >= 64 && mine;

@@ -123,20 +123,28 @@ __device__ __forceinline__ uint32_t p10_lut_entry(uint32_t op)      // opcode ta
     return P10L_END;                                                                   // END (0xff), reserved 0xfc / 0xfd
 }
 
-// Bit reader over a word accessor: 64-bit window, MSB first, refilled one word at a time.
+// Bit reader over a word accessor, MSB first: two words of the stream and the bit offset into the first. The refill
+// is straight-line code (the next word is always loaded, selects decide whether it is used): the lanes of a warp
+// cross their word boundaries at different opcodes, and a branch there would run for a handful of lanes at a time.
 template <class Words>
 struct P10Reader {
-    Words W; uint32_t next; uint64_t buf; int cnt;
+    Words W; uint32_t next, hi, lo, sh;
     __device__ __forceinline__ void init(uint32_t bitpos)
     {
         next = bitpos >> 5;
-        buf = ((uint64_t)W(next) << 32) | W(next + 1);
+        hi = W(next); lo = W(next + 1);
         next += 2;
-        const int sh = bitpos & 31;
-        buf <<= sh; cnt = 64 - sh;
+        sh = bitpos & 31;
     }
-    __device__ __forceinline__ uint32_t peek() { if (cnt <= 32) { buf |= (uint64_t)W(next) << (32 - cnt); ++next; cnt += 32; } return (uint32_t)(buf >> 32); }
-    __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, sh); }
+    __device__ __forceinline__ void drop(int n)
+    {
+        sh += (uint32_t)n;
+        const uint32_t nw = W(next);
+        const bool adv = sh >= 32;
+        hi = adv ? lo : hi; lo = adv ? nw : lo;
+        next += adv ? 1u : 0u; sh &= 31u;
+    }
 };
 
 // Parses the opcode groups that START in [bitpos, limit) without storing anything (positions are relative to the word

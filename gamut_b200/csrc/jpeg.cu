@@ -1423,7 +1423,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         // others are decoded by one thread each into zero-filled blocks
         std::vector<LongSeg> longsegs;
         std::vector<char> needs_zero((size_t)m, 0);
-        uint32_t total_chunks = 0, total_sync_ctas = 0; size_t clean_total = 0;
+        uint32_t total_chunks = 0, total_sync_ctas = 0, total_tiles = 0; size_t clean_total = 0;
         {
             std::vector<Segment> shortsegs;
             for (const Segment& sg : segs) {
@@ -1434,6 +1434,7 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
                 L.chunk_base = total_chunks; L.nchunks = (len + JS_CHUNK_BYTES - 1) / JS_CHUNK_BYTES;
                 L.cta_base = total_sync_ctas;
                 L.clean_off = clean_total;
+                L.tile_base = total_tiles; L.ntiles = (sg.end - (sg.start & ~15u) + JU_TILE - 1) / JU_TILE; total_tiles += L.ntiles;
                 total_chunks += (L.nchunks + JW_CTA - 1) / JW_CTA * JW_CTA;        // the write kernel's CTAs never span segments
                 total_sync_ctas += (L.nchunks + JS_OWN - 1) / JS_OWN;
                 clean_total += al((size_t)len + JS_PAD_BYTES + 16, 16);
@@ -1444,8 +1445,9 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         const int nlong = (int)longsegs.size();
         DevBuf d_long(sizeof(LongSeg) * ((size_t)nlong + 1)), d_clean(clean_total + 256), d_clen(4 * ((size_t)nlong + 1)),
                d_recs(sizeof(ChunkRec) * ((size_t)total_chunks + 1)), d_bases(sizeof(ChunkBase) * ((size_t)total_chunks + 1)),
-               d_entry(sizeof(ChunkState) * ((size_t)total_sync_ctas + 1)), d_unconv(256);
-        if (!d_long.p || !d_clean.p || !d_clen.p || !d_recs.p || !d_bases.p || !d_entry.p || !d_unconv.p) {
+               d_entry(sizeof(ChunkState) * ((size_t)total_sync_ctas + 1)), d_unconv(256),
+               d_tiles(sizeof(JuTile) * ((size_t)total_tiles + 1)), d_segend(4 * ((size_t)nlong + 1));
+        if (!d_tiles.p || !d_segend.p || !d_long.p || !d_clean.p || !d_clen.p || !d_recs.p || !d_bases.p || !d_entry.p || !d_unconv.p) {
             if (h_stage) pinned_free(h_stage); delete B; return nullptr;
         }
         DevBuf d_imgs(sizeof(JpegImage) * (size_t)m), d_segs(sizeof(Segment) * (segs.size() + 1)),
@@ -1513,7 +1515,10 @@ gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t*
         };
         if (nlong) {
             // long entropy segments: chunk-parallel self-synchronising decode (jpeg_sync.cuh), no host round trip
-            jpeg_unstuff_kernel<<<nlong, 256, 0, st>>>(dI, dL, clean, clen);
+            jpeg_unstuff_count_kernel<<<total_tiles, 256, 0, st>>>(dI, dL, nlong, d_tiles.as<JuTile>());
+            jpeg_unstuff_scan_kernel<<<nlong, 32, 0, st>>>(dL, d_tiles.as<JuTile>(), d_segend.as<uint32_t>());
+            jpeg_unstuff_write_kernel<<<total_tiles, 256, 0, st>>>(dI, dL, nlong, d_tiles.as<JuTile>(), d_segend.as<uint32_t>(), clean, clen);
+            count_launch(2);
             cudaEventRecord(ev[4], st);
             jpeg_sync_kernel<<<total_sync_ctas, JS_CTA, 0, st>>>(dI, dL, nlong, clean, clen, dT, recs, entry);
             jpeg_repair_kernel<<<rg, 64, 0, st>>>(dI, dL, nlong, total_sync_ctas, clean, clen, dT, recs, entry, 0, unconv);

@@ -87,6 +87,11 @@ extern(C)
                                          const(ubyte*)* files_dev, int req_comps, void* stream);
     gb200_batch* gb200_qoix_decode_batch(int n, const(ubyte*)* files, const(size_t)* lens,
                                          const(ubyte*)* files_dev, int flags, void* stream);
+    /// qoix_lz4_encode (plugins/qoix.d:251) for 10-bit 1/2-channel images: the qoiplane10_encode stream, compression 0
+    ubyte* gb200_qoix_encode(const(ubyte)* pixels, const(gb200_qoix_desc)* desc, int* out_len);
+    size_t gb200_qoix_encode_bound(const(gb200_qoix_desc)* desc);
+    int gb200_qoix_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_qoix_desc)* descs,
+                                       const(ubyte*)* out_dev, int* out_len, void* stream);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
     int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
     int gb200_download_by_kernel(void* dst_pinned, const(void)* src_dev, size_t bytes, void* stream);

@@ -70,6 +70,12 @@ def _L():
         L.gb200_qoi_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoiDesc), i32]
         L.gb200_qoix_decode.restype = vp
         L.gb200_qoix_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoixDesc), i32, ip]
+        L.gb200_qoix_encode.restype = vp
+        L.gb200_qoix_encode.argtypes = [vp, C.POINTER(QoixDesc), ip]
+        L.gb200_qoix_encode_bound.restype = sz
+        L.gb200_qoix_encode_bound.argtypes = [C.POINTER(QoixDesc)]
+        L.gb200_qoix_encode_batch_device.restype = i32
+        L.gb200_qoix_encode_batch_device.argtypes = [i32, C.POINTER(vp), C.POINTER(QoixDesc), C.POINTER(vp), ip, vp]
         L.gb200_qoix_decode_batch.restype = vp
         L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         L.gb200_jpeg_probe.argtypes = [C.c_char_p, sz]
@@ -271,6 +277,39 @@ def qoix_decode(data: bytes, flags: int = 0):
     if d.bitdepth == 10:
         a = a.view(np.uint16)
     return a.reshape(d.height, d.width, d.channels), d, t.value
+
+
+def qoix_encode(pixels: np.ndarray, bitdepth: int = 10, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0,
+                pitch: Optional[int] = None) -> Optional[bytes]:
+    """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, c) uint16 image whose samples are 10-bit values expanded to 16
+    bits: the QOI-Plane10 stream (qoiplane10.d:99), never LZ4-wrapped. None if the encoder refuses the image."""
+    h, w, c = pixels.shape
+    px = np.ascontiguousarray(pixels)
+    d = QoixDesc(w, h, pitch if pitch is not None else w * c * px.itemsize, c, bitdepth, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = _L().gb200_qoix_encode(px.ctypes.data, C.byref(d), C.byref(n))
+    if not p:
+        return None
+    return _take_host(p, n.value).tobytes()
+
+
+def qoix_encode_bound(w: int, h: int, c: int) -> int:
+    d = QoixDesc(w, h, w * c * 2, c, 10, 0, 0, -1.0, -1.0)
+    return int(_L().gb200_qoix_encode_bound(C.byref(d)))
+
+
+def qoix_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], out_dev: Sequence[int], stream: int = 0):
+    """gb200_qoix_encode_batch_device: device pointers of gapless (h, w, c) uint16 images -> device buffers; returns the
+    stream lengths."""
+    n = len(pixels_dev)
+    pin = (C.c_void_p * max(n, 1))(*pixels_dev)
+    pout = (C.c_void_p * max(n, 1))(*out_dev)
+    descs = (QoixDesc * max(n, 1))()
+    for i, (h, w, c) in enumerate(shapes):
+        descs[i] = QoixDesc(w, h, w * c * 2, c, 10, 0, 0, -1.0, -1.0)
+    lens = (C.c_int * max(n, 1))()
+    _lib.check(_L().gb200_qoix_encode_batch_device(n, pin, descs, pout, lens, stream), "qoix_encode_batch_device")
+    return [lens[i] for i in range(n)]
 
 
 def qoix_decode_batch(files: Sequence[bytes], flags: int = 0, files_dev: Optional[Sequence[int]] = None,

@@ -67,6 +67,8 @@ def lib():
         L.or_qoix_lz4_decode.argtypes = [C.c_char_p, C.c_int, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
         L.or_qoix_lz4_encode.restype = C.c_void_p
         L.or_qoix_lz4_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
+        L.or_qoiplane10_encode.restype = C.c_void_p
+        L.or_qoiplane10_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.or_lz4_compress_bound.argtypes = [C.c_int]
         L.or_lz4_decompress_fast.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
@@ -175,6 +177,18 @@ def qoix_encode(pixels: np.ndarray, bitdepth: int, colorspace: int = 0, force_lz
     p = lib().or_qoix_lz4_encode(px.ctypes.data, C.byref(d), 1 if force_lz4 else 0, C.byref(n))
     if not p:
         raise RuntimeError("qoix encode failed")
+    return _take(p, n.value).tobytes()
+
+
+def qoiplane10_encode(pixels: np.ndarray, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0, pitch=None):
+    """or_qoiplane10_encode (qoiplane10.d:99-314) of a (h, w, c) uint16 image: the stream without the LZ4 stage, or None."""
+    h, w, c = pixels.shape
+    px = np.ascontiguousarray(pixels)
+    d = QoixDesc(w, h, pitch if pitch is not None else w * c * px.itemsize, c, 10, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = lib().or_qoiplane10_encode(px.ctypes.data, C.byref(d), C.byref(n))
+    if not p:
+        return None
     return _take(p, n.value).tobytes()
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- hot-path throughput on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload jpeg|png|qoix|convert|qoi]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload jpeg|png|qoix|convert|qoi|bmp|qoix_encode]
                     [--impl reference] [--only]
 
 A "step" is one pass of the hot path over one batch of synthetic input. The DEFAULT workload is the decode
@@ -318,7 +318,7 @@ def main():
     if secondary:
         others = {}
         # at N > 1 only the workload whose BASELINE config is multi-GPU (QOIX, configs[4]) rides along
-        for name in (("convert", "png", "qoix", "qoi", "bmp") if ctx.world == 1 else ("qoix",)):
+        for name in (("convert", "png", "qoix", "qoi", "bmp", "qoix_encode") if ctx.world == 1 else ("qoix",)):
             if ctx.allmax([time.perf_counter() - T_BEGIN])[0] > SECONDARY_BUDGET_S:
                 others[name] = {"skipped": "time budget of the default run (%.0f s) used up" % SECONDARY_BUDGET_S}
                 continue

@@ -875,6 +875,96 @@ class QoiWorkload(_WorkloadBase):
         return 8 * n * QoiWorkload.W * QoiWorkload.H, times, f"8 decodes of the 512x512 image per thread, {n} thread(s)"
 
 
+class QoixEncodeWorkload(_WorkloadBase):
+    """SURVEY 8(f1), first encoder row: qoix_lz4_encode's QOI-Plane10 stage (plugins/qoix.d:251, qoiplane10.d:99) on
+    the config-5 shape, 2048x2048 10-bit LA. `value`: gb200_qoix_encode_batch_device on device-resident pixels;
+    `e2e`: gb200_qoix_encode, host pixels in, malloc'd stream out, image by image."""
+    name = "QOI-Plane10 encode 2048x2048 10-bit LA (QOIX encoder, SURVEY 8(f1); shape of BASELINE configs[4])"
+    dtype = "u16"
+    default_steps = 5
+    default_e2e_steps = 3
+    W = H = 2048
+    N = 128
+    DISTINCT = 8
+    E2E_IMAGES = 8
+    e2e_api = "gb200_qoix_encode (host la16 pixels in, malloc'd QOIX stream out), one call per image"
+
+    def __init__(self, rank, world, args):
+        import torch
+        from gamut_b200 import codecs
+        sys_path_tests()
+        from qoixutil import depth_map_la
+        self.torch, self.codecs = torch, codecs
+        self.n = args.batch or self.N
+        self.host = [depth_map_la(self.H, self.W, 100 + rank * 16 + i, 2) for i in range(self.DISTINCT)]
+        self.dev = [torch.from_numpy(self.host[i % self.DISTINCT].view(np.int16)).cuda().clone() for i in range(self.n)]
+        cap = codecs.qoix_encode_bound(self.W, self.H, 2) + 16
+        self.outs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(self.n)]
+        self.pin_, self.pout = [t.data_ptr() for t in self.dev], [o.data_ptr() for o in self.outs]
+        self.shapes = [(self.H, self.W, 2)] * self.n
+        self.px_per_step = self.n * self.W * self.H
+        self.e2e_px_per_step = self.E2E_IMAGES * self.W * self.H
+        self.lens = None
+        self.log = EventLog()
+        self.kernel_ms = {}
+
+    def step(self, stream, timed):
+        e = self.log.span("qe kernels (tile_ne/scan/count/scan/emit)", stream) if timed else None
+        self.lens = self.codecs.qoix_encode_batch_device(self.pin_, self.shapes, self.pout, stream.cuda_stream)
+        if e:
+            e.record(stream)
+        if not getattr(self, "_checked", False):
+            from oracle import pyoracle          # checker only: the first stream must be the reference encoder's
+            exp = pyoracle.qoiplane10_encode(self.host[0])
+            got = self.outs[0][:self.lens[0]].cpu().numpy().tobytes()
+            assert got == exp, "GPU QOI-Plane10 stream differs from the reference encoder's"
+            self._checked = True
+
+    def finish_timing(self):
+        self.kernel_ms = self.log.collect()
+
+    def config(self):
+        return {"units_per_rank": f"{self.n} images {self.W}x{self.H} la16 ({self.DISTINCT} distinct)",
+                "stream_bytes_per_image": int(np.mean(self.lens)) if self.lens else None,
+                "l2": "inputs larger than L2 (every image has its own device copy)"}
+
+    def roofline(self, peak, peak_kind):
+        avg = {k: float(np.mean(v)) for k, v in self.kernel_ms.items() if v}
+        k = max(avg, key=avg.get)
+        alg = self.n * (self.W * self.H * 4 + (int(np.mean(self.lens)) if self.lens else 0))
+        ach = alg / (avg[k] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "peak_kind": peak_kind, "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": round(avg[k], 3),
+                "launch": f"one encode call of {self.n} images (pixels are read by three of its five kernels)"}
+
+    def e2e_setup(self):
+        self.h2d = self.E2E_IMAGES * self.W * self.H * 4
+        self.d2h = self.E2E_IMAGES * (int(np.mean(self.lens)) if self.lens else 0)
+
+    def e2e_step(self):
+        for i in range(self.E2E_IMAGES):
+            if self.codecs.qoix_encode(self.host[i % self.DISTINCT]) is None:
+                raise RuntimeError("qoix_encode failed")
+
+    @staticmethod
+    def cpu_run(threads, reps, full):
+        from oracle import pyoracle
+        sys_path_tests()
+        from qoixutil import depth_map_la
+        img = depth_map_la(QoixEncodeWorkload.H, QoixEncodeWorkload.W, 100, 2)
+        n = threads if full else 1
+
+        def work(t):
+            assert pyoracle.qoiplane10_encode(img) is not None
+
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _threads_run(work, n)
+            times.append(time.perf_counter() - t0)
+        return n * QoixEncodeWorkload.W * QoixEncodeWorkload.H, times, f"{n} image(s) 2048x2048 la16, {n} thread(s), one image per worker"
+
+
 def make_qoi_file(w, h):
     """SURVEY 8d cfg 1: seeded gradient + low-amplitude noise + flat rectangles + alpha ramp (tests/qoixutil.py),
     encoded by PIL's QOI writer (an implementation independent of the reference and of this repo).
@@ -903,4 +993,4 @@ def sys_path_tests():
 
 
 WORKLOADS = {"convert": ConvertWorkload, "png": PngWorkload, "jpeg": JpegWorkload, "qoix": QoixWorkload, "qoi": QoiWorkload,
-             "bmp": BmpWorkload}
+             "bmp": BmpWorkload, "qoix_encode": QoixEncodeWorkload}

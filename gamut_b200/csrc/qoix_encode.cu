@@ -17,6 +17,7 @@
 // is returned with compression = 0, which is what the reference itself returns whenever LZ4 does not pay.
 #include "../../include/gamut_b200.h"
 #include "common.h"
+#include <algorithm>
 #include <vector>
 #include <cstring>
 
@@ -34,13 +35,6 @@ struct QeImage {
     uint8_t header[QOIX_HEADER_SIZE];
 };
 struct QeTile { int last_ne; int carry_ne; uint32_t bits; uint32_t bit_base; };
-
-__device__ __forceinline__ uint32_t qe_find(const QeImage* __restrict__ imgs, int n, uint32_t tile)
-{
-    int lo = 0, hi = n - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (imgs[mid].tile_base <= tile) lo = mid; else hi = mid - 1; }
-    return (uint32_t)lo;
-}
 
 struct QePx { uint32_t l, a; };
 __device__ __forceinline__ QePx qe_load(const QeImage& im, uint32_t y, uint32_t x)
@@ -62,15 +56,8 @@ __device__ __forceinline__ int qe_med(int left, int top, int topleft)       // l
 // Everything about pixel i that does not depend on other tiles: the pixel, whether it equals its predecessor, and the
 // code it would emit as a pixel of its own (the DIFF / ADIFF / LA part of the encoder's loop body, :230-262).
 struct QeEval { bool eq; uint32_t code; int nbits; uint32_t diff1; bool diff1_ok; };
-__device__ __forceinline__ QeEval qe_eval(const QeImage& im, uint32_t i, uint32_t y, uint32_t x)
+__device__ __forceinline__ QeEval qe_eval_px(QePx cur, QePx prev, int pred)
 {
-    const QePx cur = qe_load(im, y, x);
-    QePx prev; prev.l = 0; prev.a = 1023;                       // initialPredictor (:59)
-    if (i) prev = x ? qe_load(im, y, x - 1) : qe_load(im, y - 1, im.w - 1);
-    int pred;
-    if (y == 0) pred = (int)prev.l;
-    else if (x == 0) pred = (int)qe_load(im, y - 1, 0).l;
-    else pred = qe_med((int)prev.l, (int)qe_load(im, y - 1, x).l, (int)qe_load(im, y - 1, x - 1).l);
     QeEval e;
     e.eq = cur.l == prev.l && cur.a == prev.a;
     const uint32_t vg = (cur.l - (uint32_t)pred) & 1023u;
@@ -88,6 +75,26 @@ __device__ __forceinline__ QeEval qe_eval(const QeImage& im, uint32_t i, uint32_
         else { e.code = (e.code << 14) | (0xeu << 10) | vg; e.nbits += 14; }
     }
     return e;
+}
+__device__ __forceinline__ QeEval qe_eval(const QeImage& im, uint32_t i, uint32_t y, uint32_t x)
+{
+    const QePx cur = qe_load(im, y, x);
+    QePx prev; prev.l = 0; prev.a = 1023;                       // initialPredictor (:59)
+    if (i) prev = x ? qe_load(im, y, x - 1) : qe_load(im, y - 1, im.w - 1);
+    int pred;
+    if (y == 0) pred = (int)prev.l;
+    else if (x == 0) pred = (int)qe_load(im, y - 1, 0).l;
+    else pred = qe_med((int)prev.l, (int)qe_load(im, y - 1, x).l, (int)qe_load(im, y - 1, x - 1).l);
+    return qe_eval_px(cur, prev, pred);
+}
+// la16 pixels x0-1 .. x0+4 of row y (x0 a multiple of 4 inside the row, the row 16-byte aligned): one vector + two pixels
+__device__ __forceinline__ void qe_load6_la(const QeImage& im, uint32_t y, uint32_t x0, QePx (&p)[QE_PER + 2])
+{
+    const uint32_t* row = (const uint32_t*)(im.pixels + (size_t)im.pitch * y);
+    const uint4 v = __ldg((const uint4*)(row + x0));
+    const uint32_t w[6] = {__ldg(row + x0 - 1), v.x, v.y, v.z, v.w, __ldg(row + x0 + 4)};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { p[k].l = (w[k] & 0xffffu) >> 6; p[k].a = w[k] >> 22; }
 }
 
 // the code a pixel emits given its place in its run: nothing inside a run, the run's code at its last pixel
@@ -128,8 +135,11 @@ __global__ void __launch_bounds__(QE_THREADS)
 qe_tile_ne_kernel(const QeImage* __restrict__ imgs, int nimgs, QeTile* __restrict__ tiles)
 {
     __shared__ int s_warp[QE_THREADS / 32];
-    const QeImage& im = imgs[qe_find(imgs, nimgs, blockIdx.x)];
-    const uint32_t i0 = (blockIdx.x - im.tile_base) * QE_TILE + threadIdx.x * QE_PER;
+    // grid = (most tiles of an image, images): no search for the image at the start of every CTA
+    const QeImage& im = imgs[blockIdx.y];
+    if (blockIdx.x >= im.ntiles) return;
+    const uint32_t tile_index = im.tile_base + blockIdx.x;
+    const uint32_t i0 = blockIdx.x * QE_TILE + threadIdx.x * QE_PER;
     int last = -1;
     if (i0 < im.np) {
         uint32_t y = i0 / im.w, x = i0 - y * im.w;
@@ -148,7 +158,7 @@ qe_tile_ne_kernel(const QeImage* __restrict__ imgs, int nimgs, QeTile* __restric
     }
     int tot;
     qe_cta_scan<true>(last, -1, s_warp, &tot);
-    if (threadIdx.x == 0) tiles[blockIdx.x].last_ne = tot;
+    if (threadIdx.x == 0) tiles[tile_index].last_ne = tot;
 }
 
 // ---- E2 / E4: per image, exclusive prefix over its tiles (one CTA per image) ---------------------------------------
@@ -212,22 +222,37 @@ qe_tile_kernel(const QeImage* __restrict__ imgs, int nimgs, QeTile* __restrict__
 {
     __shared__ int s_warp[QE_THREADS / 32];
     __shared__ uint32_t s_bits[EMIT ? (QE_TILE * 28 / 32 + 4) : 1];
-    const QeImage& im = imgs[qe_find(imgs, nimgs, blockIdx.x)];
-    const QeTile tile = tiles[blockIdx.x];
-    const uint32_t i0 = (blockIdx.x - im.tile_base) * QE_TILE + threadIdx.x * QE_PER;
+    const QeImage& im = imgs[blockIdx.y];
+    if (blockIdx.x >= im.ntiles) return;
+    const uint32_t tile_index = im.tile_base + blockIdx.x;
+    const QeTile tile = tiles[tile_index];
+    const uint32_t i0 = blockIdx.x * QE_TILE + threadIdx.x * QE_PER;
     // evaluate my pixels and the one after them (whose eq decides whether my last pixel ends a run)
     QeEval ev[QE_PER + 1];
     int my_last = -1;
     {
         uint32_t y = i0 < im.np ? i0 / im.w : 0, x = i0 < im.np ? i0 - y * im.w : 0;
+        // interior of a row of an aligned la16 image: the six pixels of this row and of the row above as vectors
+        const bool fast = QE_PER == 4 && im.channels == 2 && i0 < im.np && y > 0 && x >= 4 && x + 8 <= im.w && (x & 3) == 0 &&
+                          (im.pitch & 15) == 0 && ((uintptr_t)im.pixels & 15) == 0;
+        if (fast) {
+            QePx c[QE_PER + 2], u[QE_PER + 2];
+            qe_load6_la(im, y, x, c); qe_load6_la(im, y - 1, x, u);
 #pragma unroll
-        for (int q = 0; q <= QE_PER; ++q) {
-            const uint32_t i = i0 + q;
-            ev[q].eq = false; ev[q].code = 0; ev[q].nbits = 0; ev[q].diff1 = 0; ev[q].diff1_ok = false;
-            if (i < im.np) {
-                ev[q] = qe_eval(im, i, y, x);
-                if (q < QE_PER && !ev[q].eq) my_last = (int)i;
-                if (++x == im.w) { x = 0; ++y; }
+            for (int q = 0; q <= QE_PER; ++q) {
+                ev[q] = qe_eval_px(c[q + 1], c[q], qe_med((int)c[q].l, (int)u[q + 1].l, (int)u[q].l));
+                if (q < QE_PER && !ev[q].eq) my_last = (int)(i0 + q);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q <= QE_PER; ++q) {
+                const uint32_t i = i0 + q;
+                ev[q].eq = false; ev[q].code = 0; ev[q].nbits = 0; ev[q].diff1 = 0; ev[q].diff1_ok = false;
+                if (i < im.np) {
+                    ev[q] = qe_eval(im, i, y, x);
+                    if (q < QE_PER && !ev[q].eq) my_last = (int)i;
+                    if (++x == im.w) { x = 0; ++y; }
+                }
             }
         }
     }
@@ -245,7 +270,7 @@ qe_tile_kernel(const QeImage* __restrict__ imgs, int nimgs, QeTile* __restrict__
     }
     int total;
     const int ex = qe_cta_scan<false>(mybits, 0, s_warp, &total);
-    if (!EMIT) { if (threadIdx.x == 0) tiles[blockIdx.x].bits = (uint32_t)total; return; }
+    if (!EMIT) { if (threadIdx.x == 0) tiles[tile_index].bits = (uint32_t)total; return; }
     // the tile's bits are put together in shared memory at the bit alignment they have in memory (bit 0 of s_bits =
     // the first bit of the aligned 32-bit word the tile starts in), MSB first
     const uint32_t g0 = QOIX_HEADER_SIZE * 8 + tile.bit_base;          // stream bit of the tile's first bit
@@ -315,14 +340,20 @@ bool qoiplane10_encode_device(int n, const uint8_t* const* pixels_dev, const gb2
     if (!d_imgs.p || !d_tiles.p || !d_len.p || !h_len.p) return false;
     bool ok = cuda_ok(cudaMemcpyAsync(d_imgs.p, imgs.data(), sizeof(QeImage) * (size_t)m, cudaMemcpyHostToDevice, st), "qe imgs", __FILE__, __LINE__);
     if (ok) {
-        const QeImage* dI = d_imgs.as<QeImage>(); QeTile* dT = d_tiles.as<QeTile>();
-        qe_tile_ne_kernel<<<total_tiles, QE_THREADS, 0, st>>>(dI, m, dT);
-        qe_scan_kernel<<<m, QE_THREADS, 0, st>>>(dI, dT, 0, d_len.as<int>());
-        qe_tile_kernel<false><<<total_tiles, QE_THREADS, 0, st>>>(dI, m, dT);
-        qe_scan_kernel<<<m, QE_THREADS, 0, st>>>(dI, dT, 1, d_len.as<int>());
-        qe_tile_kernel<true><<<total_tiles, QE_THREADS, 0, st>>>(dI, m, dT);
-        count_launch(5);
-        ok = dev_read_back_async(h_len.p, d_len.p, sizeof(int) * (size_t)m, st);
+        uint32_t most = 0;
+        for (const QeImage& Q : imgs) most = std::max(most, Q.ntiles);
+        for (int k0 = 0; ok && k0 < m; k0 += 65535) {           // grid.y is limited to 65535
+            const int mk = std::min(65535, m - k0);
+            const dim3 grid(most, (unsigned)mk);
+            const QeImage* dI = d_imgs.as<QeImage>() + k0; QeTile* dT = d_tiles.as<QeTile>(); int* dl = d_len.as<int>() + k0;
+            qe_tile_ne_kernel<<<grid, QE_THREADS, 0, st>>>(dI, mk, dT);
+            qe_scan_kernel<<<mk, QE_THREADS, 0, st>>>(dI, dT, 0, dl);
+            qe_tile_kernel<false><<<grid, QE_THREADS, 0, st>>>(dI, mk, dT);
+            qe_scan_kernel<<<mk, QE_THREADS, 0, st>>>(dI, dT, 1, dl);
+            qe_tile_kernel<true><<<grid, QE_THREADS, 0, st>>>(dI, mk, dT);
+            count_launch(5);
+        }
+        ok = ok && dev_read_back_async(h_len.p, d_len.p, sizeof(int) * (size_t)m, st);
     }
     ok = cuda_ok(cudaStreamSynchronize(st), "qe sync", __FILE__, __LINE__) && ok;
     ok = ok && cuda_ok(cudaGetLastError(), "qe kernels", __FILE__, __LINE__);

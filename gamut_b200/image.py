@@ -399,6 +399,24 @@ class Image:
         self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
 
     # -- getAdHocLayoutConstraints (image.d:1809-1905)
+    # -- Image.saveToMemory (image.d:966) for the one save path that is built: saveQOIX (plugins/qoix.d:156-241) of a
+    #    10-bit greyscale image, which the reference routes to qoiplane10_encode. Returns the file bytes or None (the
+    #    reference returns a null slice when the plugin's saveProc fails or the format has none).
+    def saveToMemory(self, fmt, flags: int = 0):
+        if not self.hasData() or int(fmt) != int(ImageFormat.QOIX):
+            return None
+        t = PixelType(int(self._type))
+        if t not in (PixelType.l16, PixelType.la16, PixelType.lap16):
+            return None                                    # the other sub-encoders are not built
+        if self._pitch < self._width * pixelTypeSize(t):
+            return None                                    # vertically flipped storage: not taken by the C entry point
+        import ctypes as C
+        d = codecs.QoixDesc(self._width, self._height, self._pitch, 1 if t == PixelType.l16 else 2, 10,
+                            2 if t == PixelType.lap16 else 0, 0, self._pixelAspectRatio, self._resolutionY)
+        n = C.c_int(0)
+        p = codecs._L().gb200_qoix_encode(self._area.ctypes.data + self._offset, C.byref(d), C.byref(n))
+        return codecs._take_host(p, n.value).tobytes() if p else None
+
     def getAdHocLayoutConstraints(self) -> int:
         pitch = self._pitch
         absPitch = abs(pitch)

@@ -91,3 +91,18 @@ def test_config5_shape_2048_and_batch(codecs, oracle, gb):
     torch.cuda.synchronize()
     for o, n, e in zip(outs, lens, exp):
         assert n == len(e) and o[:n].cpu().numpy().tobytes() == e
+
+
+def test_image_save_qoix(codecs, oracle):
+    """Image.saveToMemory(QOIX) of a loaded 10-bit image (saveQOIX, plugins/qoix.d:156-241): the stream the reference's
+    encoder writes for the image's pixels, metadata included, and it loads back to the same image."""
+    from gamut_b200.image import Image
+    from gamut_b200.types import ImageFormat, PixelType
+    for c in (1, 2):
+        img = depth_map_la(37, 61, 9, c)
+        src = oracle.qoiplane10_encode(img, par=2.0, dpi=72.0)
+        im = Image()
+        assert im.loadFromMemory(src, 0) and im.type() == (PixelType.l16 if c == 1 else PixelType.la16)
+        out = im.saveToMemory(ImageFormat.QOIX)
+        assert out == src
+        assert im.saveToMemory(ImageFormat.PNG) is None

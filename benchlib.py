@@ -417,23 +417,25 @@ class PngWorkload(_WorkloadBase):
         b.free()
         if bad:
             raise RuntimeError(f"{bad} PNG images failed to decode")
-        # unfilter-only leg on pre-inflated streams (kernel-level roofline; not part of `value`)
-        if timed:
-            e = self.log.span("unfilter", stream)
-            L = self.codecs._L()
-            ok = L.gb200_png_unfilter_device(self.d_raw.data_ptr(), self.raw_stride, self.d_unf.data_ptr(), self.out_stride,
+
+    def _unfilter_legs(self, stream):
+        """Unfilter-only legs on pre-inflated streams (kernel-level roofline). Run AFTER the timed region of the step
+        (finish_timing): they are not part of `value`."""
+        e = self.log.span("unfilter", stream)
+        L = self.codecs._L()
+        ok = L.gb200_png_unfilter_device(self.d_raw.data_ptr(), self.raw_stride, self.d_unf.data_ptr(), self.out_stride,
+                                         self.n, self.W * 4, self.H, 4, None, stream.cuda_stream)
+        e.record(stream)
+        assert ok
+        for name, d in self.variants.items():
+            e = self.log.span("unfilter_" + name, stream)
+            ok = L.gb200_png_unfilter_device(d.data_ptr(), self.raw_stride, self.d_unf.data_ptr(), self.out_stride,
                                              self.n, self.W * 4, self.H, 4, None, stream.cuda_stream)
             e.record(stream)
             assert ok
-            for name, d in self.variants.items():
-                e = self.log.span("unfilter_" + name, stream)
-                ok = L.gb200_png_unfilter_device(d.data_ptr(), self.raw_stride, self.d_unf.data_ptr(), self.out_stride,
-                                                 self.n, self.W * 4, self.H, 4, None, stream.cuda_stream)
-                e.record(stream)
-                assert ok
-                if not getattr(self, "_checked_" + name, False):
-                    assert self.torch.equal(self.d_unf[0].view(self.H, self.W * 4), self.ref_pixels), name
-                    setattr(self, "_checked_" + name, True)
+            if not getattr(self, "_checked_" + name, False):
+                assert self.torch.equal(self.d_unf[0].view(self.H, self.W * 4), self.ref_pixels), name
+                setattr(self, "_checked_" + name, True)
 
     @staticmethod
     def _unfilter_host(raw):
@@ -444,6 +446,9 @@ class PngWorkload(_WorkloadBase):
         return out.tobytes()
 
     def finish_timing(self):
+        stream = self.torch.cuda.current_stream()
+        for _ in range(3):
+            self._unfilter_legs(stream)
         c = self.log.collect()
         self.unf_ms = c.get("unfilter", [])
         self.variant_ms = {k: c.get("unfilter_" + k, []) for k in self.variants}

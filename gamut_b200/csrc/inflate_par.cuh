@@ -95,31 +95,42 @@ struct LaneRes { uint32_t end, nbytes, flags; };     // flags: 1 end-of-block se
 // words. The bytes of a match after its record are a hole that the resolve pass overwrites, so they may receive
 // anything: once a hole has crossed into a new word the lane owns every byte of that word that matters, and all
 // stores but those of the first and last word of the lane's region are full-word stores.
+// first word of a lane's region: bytes [k0, 4) only (the bytes below k0 belong to the lane before)
+__device__ __noinline__ void infp_store_head(uint8_t* p, uint32_t w, uint32_t k0)
+{
+    for (uint32_t q = k0; q < 4; ++q) p[q] = (uint8_t)(w >> (8 * q));
+}
+
 struct LaneWriter {
-    uint8_t* out; uint32_t off, acc, k0;
+    // One straight-line append for every kind of symbol (the lanes of a warp are at different symbols: a branch per
+    // kind, or per byte stored, runs for a handful of lanes at a time): up to three bytes enter a 64-bit accumulator
+    // at the byte position of `off`, a word that has been completed leaves with one predicated store, and a hole of
+    // `n` bytes follows. Only the first word of the lane's region -- shared with the lane before -- goes byte by byte.
+    uint8_t* out; uint32_t off; uint64_t acc; uint32_t k0;
     __device__ __forceinline__ void init(uint8_t* o, uint32_t at) { out = o; off = at; acc = 0; k0 = at & 3; }
-    __device__ __forceinline__ void store_word(uint32_t base, uint32_t e)        // bytes [k0, e) of the word at base
+    __device__ __forceinline__ void store_word(uint32_t base, uint32_t w)          // the word at base is complete (or abandoned to a hole)
     {
-        if (k0 == 0) *(uint32_t*)(out + base) = acc;
-        else for (uint32_t q = k0; q < e; ++q) out[base + q] = (uint8_t)(acc >> (8 * q));
+        if (k0 == 0) *(uint32_t*)(out + base) = w;
+        else { infp_store_head(out + base, w, k0); k0 = 0; }
     }
-    __device__ __forceinline__ void put(uint32_t b)
+    // k bytes of v (k <= 3), then a hole of n bytes
+    __device__ __forceinline__ void append(uint32_t v, uint32_t k, uint32_t n)
     {
-        acc |= b << (8 * (off & 3));
-        ++off;
-        if ((off & 3) == 0) { store_word(off - 4, 4); acc = 0; k0 = 0; }
-    }
-    __device__ __forceinline__ void skip(uint32_t n)
-    {
+        acc |= (uint64_t)v << (8 * (off & 3));
+        const uint32_t o1 = off + k;
+        if ((o1 ^ off) & ~3u) { store_word(off & ~3u, (uint32_t)acc); acc >>= 32; }        // the bytes completed a word
+        off = o1;
         const uint32_t e = off & 3;
-        if (n < 4 - e) { off += n; return; }                 // the hole ends inside the current word
-        if (e) store_word(off - e, 4);
-        off += n; acc = 0; k0 = 0;
+        if (n >= 4 - e) {                                    // the hole leaves the current word: what I own of it goes out now
+            if (e) store_word(off - e, (uint32_t)acc);
+            acc = 0;
+        }
+        off += n;
     }
     __device__ __forceinline__ void flush()                  // end of the lane's region: only bytes below off are mine
     {
         const uint32_t e = off & 3, base = off & ~3u;
-        for (uint32_t q = k0; q < e; ++q) out[base + q] = (uint8_t)(acc >> (8 * q));
+        for (uint32_t q = k0; q < e; ++q) out[base + q] = (uint8_t)((uint32_t)acc >> (8 * q));
         acc = 0; k0 = e;
     }
 };
@@ -205,21 +216,21 @@ __device__ __forceinline__ void lane_decode(const InflateSmem& S, uint32_t* col,
         const uint32_t val = (e >> 16) + ((bits >> len) & ((1u << xb) - 1));
         pos += len + xb;
         if (kind == 3) { flags = 2; break; }
-        if (want_dist) {
-            want_dist = 0;
-            if (WRITE) {
-                const uint32_t at = W.off;
+        if (!want_dist && kind == 2) { flags = 1; break; }   // end of block
+        if (WRITE) {
+            // literal: one byte. distance symbol: the match's 3-byte record, then the hole it will fill. length
+            // symbol: nothing yet.
+            const uint32_t at = W.off;
+            const uint32_t rec = (mlen - 3) | ((val - 1) << 8);
+            if (want_dist) {
                 if (val > at) *fail = 1;                    // reaches before the start of the output
-                W.put(mlen - 3); W.put((val - 1) & 255); W.put((val - 1) >> 8);
                 atomicOr(bitmap + (at >> 5), 1u << (at & 31));
-                W.skip(mlen - 3);
             }
-        } else if (kind == 0) {
-            ++nbytes;
-            if (WRITE) W.put(val);
-        } else if (kind == 1) {
-            nbytes += val; mlen = val; want_dist = 1;
-        } else { flags = 1; break; }
+            W.append(want_dist ? rec : (kind == 0 ? val : 0u), want_dist ? 3u : (kind == 0 ? 1u : 0u), want_dist ? mlen - 3 : 0u);
+        }
+        if (want_dist) want_dist = 0;
+        else if (kind == 0) ++nbytes;
+        else { nbytes += val; mlen = val; want_dist = 1; }
     }
     infp_wait<0>();
     if (WRITE) W.flush();

@@ -398,60 +398,69 @@ p10_write_kernel(const P10Image* __restrict__ imgs, int nimgs, const P10Chunk* _
         }
         qmask = 0;
     };
-    while (__any_sync(0xffffffffu, alive)) {
-        uint32_t n = 0, rec = 0;
-        if (alive) {
-            const uint32_t v = R.peek();
-            const uint32_t e = s_lut[v >> 24];
-            const uint32_t len = e & 31u;
-            if (e & P10L_END) alive = false;
-            else if ((e & (P10L_ALPHA | P10L_NPIX)) == P10L_ALPHA) {      // ADIFF: the pixel's own opcode follows
-                a_pend = (a + (uint32_t)((int)(v << 6) >> 26)) & 1023u; ing = true;
-                bp += len; R.drop((int)len);
-            } else {
-                if (e & P10L_ALPHA) a = (v >> 4) & 1023u;                  // LA
-                else if (ing) a = a_pend;
-                ing = false;
-                n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
-                const uint32_t kind = ((e >> 22) & 3u) << 10;
-                const uint32_t val = (kind & P10_REC_COPY) ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
-                rec = kind | val | (((a << 6) | (a >> 4)) << 16);
-                n = min(n, np - i);
-                bp += len; R.drop((int)len);
-                if (bp >= limit) alive = false;                   // the next group starts in a later chunk
-            }
+    // One straight-line round per opcode: a lane decodes when it has nothing left to place, then places ONE record
+    // (a short run takes several rounds; its lane does not decode meanwhile). The kinds of opcode differ in a few
+    // selects, not in the path taken: the lanes of a warp are at different opcodes.
+    uint32_t pend_n = 0, pend_rec = 0, pend_p0 = 0;
+    while (__any_sync(0xffffffffu, alive || pend_n)) {
+        const bool dec = alive && pend_n == 0;
+        const uint32_t v = R.peek();
+        const uint32_t e = s_lut[v >> 24];
+        const bool end = dec && (e & P10L_END);
+        const bool adiff = dec && (e & (P10L_ALPHA | P10L_NPIX | P10L_END)) == P10L_ALPHA;     // the pixel's own opcode follows
+        const bool pix = dec && !end && !adiff;
+        const uint32_t len = (dec && !end) ? e & 31u : 0u;
+        a_pend = adiff ? (a + (uint32_t)((int)(v << 6) >> 26)) & 1023u : a_pend;
+        a = pix ? ((e & P10L_ALPHA) ? (v >> 4) & 1023u : (ing ? a_pend : a)) : a;             // LA sets, ADIFF announced
+        ing = adiff || (ing && !pix);
+        {
+            uint32_t n = (e & P10L_EXT) ? ((v >> 18) & 0xffu) + 8u : (e >> 5) & 15u;
+            n = pix ? min(n, np - i) : 0u;
+            const uint32_t kind = ((e >> 22) & 3u) << 10;
+            const uint32_t val = (kind & P10_REC_COPY) ? 0u : (uint32_t)((int)(v << ((e >> 12) & 31u)) >> ((e >> 17) & 31u)) & 1023u;
+            pend_rec = dec ? (kind | val | (((a << 6) | (a >> 4)) << 16)) : pend_rec;
+            pend_n = dec ? n : pend_n;
+            pend_p0 = dec ? i : pend_p0;
         }
+        bp += len; R.drop((int)len);
+        alive = alive && !end && !(pix && bp >= limit);           // the next group starts in a later chunk
         // long runs: the whole warp places the records of one lane's run straight into memory, 32 per step (a lane
         // on its own would keep the other 31 waiting for up to 262 steps)
-        uint32_t big = __ballot_sync(0xffffffffu, n >= 8);
-        if (n >= 8 && qmask) flush_group();
-        while (big) {
-            const int l = __ffs(big) - 1; big &= big - 1;
-            const uint32_t rn = __shfl_sync(0xffffffffu, n, l), rrec = __shfl_sync(0xffffffffu, rec, l);
-            const uint32_t ri = __shfl_sync(0xffffffffu, i, l), rx = __shfl_sync(0xffffffffu, x, l), ry = __shfl_sync(0xffffffffu, y, l);
-            for (uint32_t j = lane; j < rn; j += 32) {
-                const uint32_t xx0 = rx + j, dy = xx0 / Wd, xx = xx0 - dy * Wd, yy = ry + dy;
-                recs[(size_t)yy * WP + xx] = rrec;
-                if (xx == 0) rowinfo[yy] = row_info(rrec, ri + j, yy, ri);
-            }
-            if (lane == l) {
-                const uint32_t xx0 = x + n, dy = xx0 / Wd;
-                i += n; x = xx0 - dy * Wd; y += dy; addr = y * WP + x;
-                n = 0;
+        uint32_t big = __ballot_sync(0xffffffffu, pend_n >= 8);
+        if (big) {
+            if (pend_n >= 8 && qmask) flush_group();
+            while (big) {
+                const int l = __ffs(big) - 1; big &= big - 1;
+                const uint32_t rn = __shfl_sync(0xffffffffu, pend_n, l), rrec = __shfl_sync(0xffffffffu, pend_rec, l);
+                const uint32_t ri = __shfl_sync(0xffffffffu, i, l), rx = __shfl_sync(0xffffffffu, x, l), ry = __shfl_sync(0xffffffffu, y, l);
+                for (uint32_t j = lane; j < rn; j += 32) {
+                    const uint32_t xx0 = rx + j, dy = xx0 / Wd, xx = xx0 - dy * Wd, yy = ry + dy;
+                    recs[(size_t)yy * WP + xx] = rrec;
+                    if (xx == 0) rowinfo[yy] = row_info(rrec, ri + j, yy, ri);
+                }
+                if (lane == l) {
+                    const uint32_t xx0 = x + pend_n, dy = xx0 / Wd;
+                    i += pend_n; x = xx0 - dy * Wd; y += dy; addr = y * WP + x;
+                    pend_n = 0;
+                }
             }
         }
-        const uint32_t p0 = i;
-        while (n) {
-            if (x == 0) rowinfo[y] = row_info(rec, i, y, p0);
-            const uint32_t k = addr & 3u;
-            q0 = k == 0 ? rec : q0; q1 = k == 1 ? rec : q1; q2 = k == 2 ? rec : q2; q3 = k == 3 ? rec : q3;
-            qmask |= 1u << k;
-            --n; ++i; ++addr;
-            if (k == 3) flush_group();
-            if (++x == Wd) { x = 0; ++y; if (skip) { if (qmask) flush_group(); addr += skip; } }
+        // one record
+        const bool place = pend_n != 0;
+        if (place && x == 0) rowinfo[y] = row_info(pend_rec, i, y, pend_p0);
+        const uint32_t k = addr & 3u;
+        q0 = (place && k == 0) ? pend_rec : q0; q1 = (place && k == 1) ? pend_rec : q1;
+        q2 = (place && k == 2) ? pend_rec : q2; q3 = (place && k == 3) ? pend_rec : q3;
+        qmask |= place ? 1u << k : 0u;
+        const uint32_t adv = place ? 1u : 0u;
+        pend_n -= adv; i += adv; addr += adv; x += adv;
+        if (place && k == 3) {
+            if (qmask == 15u) { *(uint4*)(recs + (addr - 4)) = make_uint4(q0, q1, q2, q3); qmask = 0; }
+            else flush_group();
         }
-        if (i >= np) alive = false;
-        if (!alive && qmask) flush_group();
+        if (x == Wd) { x = 0; ++y; if (skip) { if (qmask) flush_group(); addr += skip; } }
+        if (i >= np) { alive = false; pend_n = 0; }
+        if (!alive && pend_n == 0 && qmask) flush_group();
     }
 }
 

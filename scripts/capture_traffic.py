@@ -25,7 +25,7 @@ GROUPS = {   # workload -> (bench args, units per step, [(key, kernel-name regex
                 [("convert_direct<rgba8,rgbaf32>", r"convert_direct.*<\(?(int\))?12, \(?(int\))?14"),
                  ("convert_direct<rgbaf32,rgba8>", r"convert_direct.*<\(?(int\))?14, \(?(int\))?12")]),
     "jpeg": (["--workload", "jpeg", "--batch", "64", "--sub-batch", "64", "--steps", "1"], 64,
-             [("jpeg_entropy", r"jpeg_(unstuff|sync|repair|scan|write|huffman)_kernel"), ("jpeg_idct_colour_kernel", r"jpeg_idct_colour_kernel")]),
+             [("jpeg_entropy", r"jpeg_(unstuff_count|unstuff_scan|unstuff_write|sync|repair|scan|write|huffman)_kernel"), ("jpeg_idct_colour_kernel", r"jpeg_idct_colour_kernel")]),
     "png": (["--workload", "png", "--batch", "64", "--steps", "1"], 64,
             [("inflate", r"infp_|inflate_batch_kernel|gather_segments"), ("unfilter", r"unfilter_kernel")]),
     "qoix": (["--workload", "qoix", "--batch", "32", "--steps", "1"], 32,
@@ -56,8 +56,8 @@ def main():
             if row[mi] == "dram__bytes_read.sum":
                 launches[row[ki]] += 1
         nsteps = 3 + int(args[args.index("--steps") + 1])          # warm-up steps run the same launches
-        # the PNG workload also times unfilter-only legs inside step(): their launches are part of the kernel totals,
-        # so "unfilter" is reported per launch instead of per step
+        # the PNG workload also runs unfilter-only legs (after the timed region): their launches are part of the kernel
+        # totals, so "unfilter" is reported per launch instead of per step
         for key, pat in groups:
             tot = sum(v for k, v in per_kernel.items() if re.search(pat, k))
             nl = sum(n for k, n in launches.items() if re.search(pat, k))

@@ -11,7 +11,7 @@ P
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r4_launches_qoix.csv python bench.py --workload qoix --only --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 python scripts/launch_summary.py gpurun_out/r4_launches_qoix.csv | head -30
 # full ncu captures (with source) of the QOI-Plane10 kernels
-for K in lz4_sync_kernel lz4_pwrite_kernel; do
+for K in ; do
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:$K -s 1 -c 1 -f -o gpurun_out/r4_prof_$K python bench.py --workload qoix --only --batch 148 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r4_prof_$K.log 2>&1
 ls -la gpurun_out/r4_prof_$K.ncu-rep
 done

@@ -204,34 +204,79 @@ lz4_resolve_kernel(const Lz4Job* __restrict__ jobs, int njobs, const int* status
 
 struct QoiJob { const uint8_t* bytes; uint32_t size; uint8_t* out; uint32_t w, h; int channels; int image; };
 
-__global__ void __launch_bounds__(64)
+// Plain QOI is one serial chain per image: its index is hashed by pixel VALUE (qoi.d:536), so which slot a pixel
+// lands in -- and therefore what a later INDEX opcode reads -- is not known before the pixel is. One warp per image:
+// lane 0 walks the opcodes with everything it touches in shared memory (input window, index, a batch of output
+// pixels), the other lanes move the data -- 16-byte loads of the stream ahead of the walk, coalesced stores of every
+// batch of 1024 pixels. (One thread working out of global and local memory took 47 ms for a 512x512 image.)
+constexpr int QOI_WIN = 16384, QOI_BATCH = 1024;
+__global__ void __launch_bounds__(32)
 qoi_kernel(const QoiJob* __restrict__ jobs, int njobs)       // qoi.d:448-550
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
-    const QoiJob J = jobs[j];
-    uchar4 index[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) index[i] = make_uchar4(0, 0, 0, 0);
-    uchar4 px = make_uchar4(0, 0, 0, 255);
-    const uint8_t* b = J.bytes;
-    int p = 14, run = 0;
-    const int chunks_len = (int)J.size - 8;
-    const long long n = (long long)J.w * J.h;
-    for (long long i = 0; i < n; ++i) {
-        if (run > 0) --run;
-        else if (p < chunks_len) {
-            const int b1 = b[p++];
-            if (b1 == 0xfe) { px.x = b[p++]; px.y = b[p++]; px.z = b[p++]; }
-            else if (b1 == 0xff) { px.x = b[p++]; px.y = b[p++]; px.z = b[p++]; px.w = b[p++]; }
-            else if ((b1 & 0xc0) == 0x00) px = index[b1];
-            else if ((b1 & 0xc0) == 0x40) { px.x += ((b1 >> 4) & 3) - 2; px.y += ((b1 >> 2) & 3) - 2; px.z += (b1 & 3) - 2; }
-            else if ((b1 & 0xc0) == 0x80) { const int b2 = b[p++]; const int vg = (b1 & 0x3f) - 32; px.x += vg - 8 + ((b2 >> 4) & 0x0f); px.y += vg; px.z += vg - 8 + (b2 & 0x0f); }
-            else run = b1 & 0x3f;
-            index[(px.x * 3 + px.y * 5 + px.z * 7 + px.w * 11) & 63] = px;
+    __shared__ __align__(16) uint8_t s_in[QOI_WIN];
+    __shared__ uint32_t s_index[64];
+    __shared__ uint32_t s_out[QOI_BATCH];
+    if ((int)blockIdx.x >= njobs) return;
+    const QoiJob J = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    s_index[lane] = 0; s_index[lane + 32] = 0;
+    const uint8_t* gbase = (const uint8_t*)((uintptr_t)J.bytes & ~(uintptr_t)15);
+    const uint32_t a0 = (uint32_t)(J.bytes - gbase);             // stream byte k sits at gbase[a0 + k]
+    const uint32_t nvec = (a0 + J.size + 15) >> 4;
+    uint32_t fetched = 0;                                        // vectors [0, fetched) have been staged
+    uint32_t px = 0xff000000u;                                   // r | g << 8 | b << 16 | a << 24, start {0, 0, 0, 255}
+    uint32_t p = 14, run = 0;
+    const uint32_t chunks_len = J.size - 8;
+    const unsigned long long n = (unsigned long long)J.w * J.h;
+    for (unsigned long long i0 = 0; i0 < n; i0 += QOI_BATCH) {
+        const uint32_t cnt = (uint32_t)min((unsigned long long)QOI_BATCH, n - i0);
+        // the walk of one batch reads at most 5 bytes per pixel: stage the stream up to p + 5 * QOI_BATCH (+ slack);
+        // the window (a ring) is large enough to keep everything from p on
+        {
+            const uint32_t want = min(nvec, ((a0 + p + 5 * QOI_BATCH + 64) >> 4) + 1);
+            for (uint32_t v = fetched + lane; v < want; v += 32)
+                *(uint4*)(s_in + ((v << 4) & (QOI_WIN - 1))) = __ldg((const uint4*)gbase + v);
+            if (want > fetched) fetched = want;
         }
-        if (J.channels == 4) ((uchar4*)J.out)[i] = px;
-        else { uint8_t* d = J.out + i * 3; d[0] = px.x; d[1] = px.y; d[2] = px.z; }
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t j = 0; j < cnt; ++j) {
+                if (run > 0) --run;
+                else if (p < chunks_len) {
+                    auto in = [&](uint32_t k) -> uint32_t { return s_in[(a0 + k) & (QOI_WIN - 1)]; };
+                    const uint32_t b1 = in(p++);
+                    uint32_t r = px & 255u, g = (px >> 8) & 255u, b = (px >> 16) & 255u, a = px >> 24;
+                    if (b1 == 0xfe) { r = in(p); g = in(p + 1); b = in(p + 2); p += 3; }
+                    else if (b1 == 0xff) { r = in(p); g = in(p + 1); b = in(p + 2); a = in(p + 3); p += 4; }
+                    else if ((b1 & 0xc0) == 0x00) { const uint32_t v = s_index[b1]; r = v & 255u; g = (v >> 8) & 255u; b = (v >> 16) & 255u; a = v >> 24; }
+                    else if ((b1 & 0xc0) == 0x40) { r += ((b1 >> 4) & 3) - 2; g += ((b1 >> 2) & 3) - 2; b += (b1 & 3) - 2; }
+                    else if ((b1 & 0xc0) == 0x80) { const uint32_t b2 = in(p++); const uint32_t vg = (b1 & 0x3f) - 32; r += vg - 8 + ((b2 >> 4) & 0x0f); g += vg; b += vg - 8 + (b2 & 0x0f); }
+                    else run = b1 & 0x3f;
+                    r &= 255u; g &= 255u; b &= 255u;
+                    px = r | (g << 8) | (b << 16) | (a << 24);
+                    s_index[(r * 3 + g * 5 + b * 7 + a * 11) & 63] = px;
+                }
+                s_out[j] = px;
+            }
+        }
+        __syncwarp();
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (J.channels == 4) {
+            uint32_t* o = (uint32_t*)J.out + i0;
+            for (uint32_t j = lane; j < cnt; j += 32) o[j] = s_out[j];
+        } else {
+            // 4 pixels -> 3 words (i0 is a multiple of 4, the output buffer is 16-byte aligned)
+            uint32_t* o = (uint32_t*)(J.out + i0 * 3);
+            for (uint32_t q = lane; q < cnt / 4; q += 32) {
+                const uint32_t v0 = s_out[4 * q] & 0xffffffu, v1 = s_out[4 * q + 1] & 0xffffffu, v2 = s_out[4 * q + 2] & 0xffffffu, v3 = s_out[4 * q + 3] & 0xffffffu;
+                o[3 * q] = v0 | (v1 << 24); o[3 * q + 1] = (v1 >> 8) | (v2 << 16); o[3 * q + 2] = (v2 >> 16) | (v3 << 8);
+            }
+            for (uint32_t j = (cnt & ~3u) + lane; j < cnt; j += 32) {
+                uint8_t* d = J.out + (i0 + j) * 3; const uint32_t v = s_out[j];
+                d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -594,7 +639,7 @@ gb200_batch* qoi_decode_batch1(const uint8_t* data, int size, int channels, int*
     QoiJob J{d_in.as<uint8_t>(), (uint32_t)size, d_out, w, h, channels, 0};
     bool ok = cuda_ok(cudaMemcpyAsync(d_in.p, data, (size_t)size, cudaMemcpyHostToDevice, st), "h2d", __FILE__, __LINE__) &&
               cuda_ok(cudaMemcpyAsync(d_job.p, &J, sizeof(J), cudaMemcpyHostToDevice, st), "job", __FILE__, __LINE__);
-    if (ok) { qoi_kernel<<<1, 64, 0, st>>>(d_job.as<QoiJob>(), 1); count_launch(); }
+    if (ok) { qoi_kernel<<<1, 32, 0, st>>>(d_job.as<QoiJob>(), 1); count_launch(); }
     ok = ok && cuda_ok(cudaGetLastError(), "qoi_kernel", __FILE__, __LINE__) && cuda_ok(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__);
     if (!ok) { cudaStreamSynchronize(st); delete B; return nullptr; }
     D.pixels = d_out; D.width = (int)w; D.height = (int)h; D.channels = channels; D.file_channels = fch; D.bits = 8;

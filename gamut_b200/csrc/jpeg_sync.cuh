@@ -25,7 +25,8 @@
 //                           with the DC prediction already applied, and records the block's zig-zag extent.
 #pragma once
 
-constexpr int JS_CHUNK_BYTES = 128;
+constexpr int JS_CHUNK_BYTES = 256;
+constexpr uint32_t JS_RUNUP_BITS = 1024;         // the first pass starts this far before its chunk (see jpeg_sync_kernel)
 constexpr int JS_CHUNK_BITS = JS_CHUNK_BYTES * 8;
 constexpr uint32_t JS_LONG_MIN = 1024;           // shorter segments are decoded by one thread each (jpeg_huffman_kernel)
 constexpr int JS_CTA = 256;                      // threads (= chunks) per CTA of the sync kernel
@@ -399,7 +400,7 @@ jpeg_sync_kernel(const JpegImage* __restrict__ images, const LongSeg* __restrict
         ChunkState st; st.bitpos = lc * JS_CHUNK_BITS; st.bik = 0;
         uint32_t nb = 0; int dcs[3] = {0, 0, 0};
         if (active && lc > 0) {
-            st.bitpos = (lc - 1) * JS_CHUNK_BITS;
+            st.bitpos = lc * JS_CHUNK_BITS - JS_RUNUP_BITS;
             js_scan_chunk(words, st, min(lc * (uint32_t)JS_CHUNK_BITS, total_bits), tabs, cx, tables, nb, dcs);
         }
         s_entry[tid] = make_uint2(st.bitpos, st.bik);

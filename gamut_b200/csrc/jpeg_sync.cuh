@@ -25,8 +25,8 @@
 //                           with the DC prediction already applied, and records the block's zig-zag extent.
 #pragma once
 
-constexpr int JS_CHUNK_BYTES = 256;
-constexpr uint32_t JS_RUNUP_BITS = 1024;         // the first pass starts this far before its chunk (see jpeg_sync_kernel)
+constexpr int JS_CHUNK_BYTES = 512;
+constexpr uint32_t JS_RUNUP_BITS = 2048;         // the first pass starts this far before its chunk (see jpeg_sync_kernel)
 constexpr int JS_CHUNK_BITS = JS_CHUNK_BYTES * 8;
 constexpr uint32_t JS_LONG_MIN = 1024;           // shorter segments are decoded by one thread each (jpeg_huffman_kernel)
 constexpr int JS_CTA = 256;                      // threads (= chunks) per CTA of the sync kernel

@@ -29,6 +29,7 @@ constexpr int P10_CHUNK_WORDS = P10_CHUNK_BYTES / 4;
 // bits 16-31 the pixel's alpha already expanded to 16 bits
 constexpr uint32_t P10_REC_COPY = 1u << 10, P10_REC_LIT = 1u << 11;
 constexpr int P10_CTA = 256;                     // threads (= chunk slots) per CTA of the sync and write kernels
+constexpr uint32_t P10_RUNUP_BITS = 96;           // sync kernel: the first pass starts this far before its chunk
 constexpr int P10_WARM = 8;                      // sync: slots that re-parse the tail of the previous CTA's range
 constexpr int P10_OWN = P10_CTA - P10_WARM;
 constexpr int P10_STAGE_WORDS = P10_CTA * P10_CHUNK_WORDS + 32;     // the CTA's slice of the stream + what a parse may read past it
@@ -214,7 +215,15 @@ p10_sync_kernel(const P10Image* __restrict__ imgs, int nimgs, P10Chunk* __restri
     };
     __syncthreads();
     {
-        const uint32_t entry = active ? (uint32_t)lc * (uint32_t)P10_CHUNK_BITS : 0u;
+        // A parse started on the chunk's first bit is wrong more often than not (an opcode straddles the boundary),
+        // but opcodes fall into step within a few codes: the parse starts P10_RUNUP_BITS early, uncounted, and has
+        // usually found the true boundary by the time it reaches its chunk.
+        uint32_t entry = active ? (uint32_t)lc * (uint32_t)P10_CHUNK_BITS : 0u;
+        if (active && lc > 0 && tid > 0) {                          // (slot 0's run-up would lie before the staged slice)
+            uint32_t rel = entry - P10_RUNUP_BITS - (uint32_t)origin, np0 = 0, al0 = 0;
+            const bool e0 = p10_count(W, s_lut, rel, entry - (uint32_t)origin, np0, al0);
+            if (!e0) entry = rel + (uint32_t)origin;                // ended (on garbage): keep the chunk's own first bit
+        }
         uint32_t x = total_bits, np = 0, al = 0;
         if (active) parse(entry, x, np, al);
         s_entry[tid] = entry; s_exit[tid] = x; s_npix[tid] = np; s_alpha[tid] = al;

@@ -449,6 +449,7 @@ class PngWorkload(_WorkloadBase):
         stream = self.torch.cuda.current_stream()
         for _ in range(3):
             self._unfilter_legs(stream)
+        stream.synchronize()
         c = self.log.collect()
         self.unf_ms = c.get("unfilter", [])
         self.variant_ms = {k: c.get("unfilter_" + k, []) for k in self.variants}

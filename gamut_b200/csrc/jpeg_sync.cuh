@@ -1,13 +1,14 @@
 // jpeg_sync.cuh -- intra-image parallel Huffman decoding for long entropy segments (included by jpeg.cu).
 //
 // A baseline JPEG scan without restart markers is one serial bit stream (decode_next_row,
-// jpegload.d:2405-2525). Huffman codes self-synchronise, so the stream is cut into 128-byte chunks, one
+// jpegload.d:2405-2525). Huffman codes self-synchronise, so the stream is cut into 512-byte chunks, one
 // thread each, and the whole stage runs without a host round trip:
-//   1. jpeg_unstuff_*       (three small kernels over 4 KB tiles) remove FF00 byte stuffing and stops at the first marker, giving a plain bit
-//                           stream padded with 1-bits (the reference reads all-ones past a marker,
+//   1. jpeg_unstuff_*       (three small kernels over 4 KB tiles) remove the FF00 byte stuffing and stop at the first
+//                           marker, giving a plain bit stream padded with 1-bits (the reference reads all-ones past a marker,
 //                           jpegload.d:683-743);
 //   2. jpeg_sync_kernel     one CTA = 248 consecutive chunks of one segment (+ 8 warm-up chunks borrowed from
-//                           its predecessor). Every thread decodes its chunk from a guessed state, then the CTA
+//                           its predecessor). Every thread decodes its chunk from a guessed state (after a run-up of
+//                           256 bytes, so that the guess is usually right by then), then the CTA
 //                           relaxes in shared memory: a thread whose predecessor's exit state differs from the
 //                           entry state it used decodes again, until nothing changes (chunk 0 of a segment starts
 //                           from the true state, so the fixed point is the serial decode, by induction). Per chunk

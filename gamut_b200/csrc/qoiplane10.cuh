@@ -7,15 +7,17 @@
 //  A. parse, chunk-parallel.  Opcode lengths depend on the bits only, never on pixel values, and a parser
 //     started at a wrong position falls onto true code boundaries after a few codes. The stream is cut into
 //     128-byte chunks, one thread each:
-//       p10_sync_kernel   pass 0 parses every chunk from its first bit; passes 1..n re-parse the chunks whose
-//                         predecessor's exit position changed, until nothing changes. Chunk 0 starts at the
-//                         true position, so the fixed point is the serial parse (induction over chunks).
-//                         Every parse also records the chunk's pixel count, its effect on the running alpha
-//                         (set v / add d) and whether it met END.
+//       p10_sync_kernel   a CTA takes 248 consecutive chunks (+ 8 warm-up chunks of its predecessor) with its slice
+//                         of the stream in shared memory. Every thread parses its chunk (after a 96-bit uncounted
+//                         run-up), then the CTA relaxes: chunks whose predecessor's exit differs from the entry
+//                         they used parse again, until nothing changes. Chunk 0 starts at the true position, so
+//                         the fixed point is the serial parse (induction over chunks). Every parse also records
+//                         the chunk's pixel count, its effect on the running alpha (set v / add d) and whether it
+//                         met END. p10_repair_kernel checks the entry of every CTA's first own chunk.
 //       p10_scan_kernel   one CTA per image: exclusive scan of (pixels, alpha transform, ended) over chunks.
 //       p10_write_kernel  parses once more from the true entry state and writes one 32-bit record per pixel:
-//                         kind (DIFF residual / COPY of the previous pixel / literal) + residual + resolved alpha.
-//  B. p10_recon_kernel, one warp per image, 32 rows per band as a skewed wavefront: lane r runs one 8-pixel
+//                         residual, COPY (of the previous pixel) / LIT flags, the pixel's alpha.
+//  B. p10_recon_kernel, eight warps per image pipelined over bands of 32 rows, each band a skewed wavefront: lane r runs one 8-pixel
 //     block behind lane r-1, so the row above arrives by warp shuffle off the critical path and the chain
 //     per pixel is just the MED predictor. A run that crosses a row boundary makes the first pixel of a row
 //     depend on the end of the row above; such rows start later (exactly as late as the dependency demands)

@@ -8,6 +8,8 @@
 #include "common.h"
 #include "batch.h"
 #include <vector>
+#include <string>
+#include <thread>
 #include <memory>
 #include <chrono>
 #include <stdlib.h>
@@ -24,15 +26,11 @@ gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* 
                               int req_comp, cudaStream_t st);
 }
 
-GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* files, const size_t* lens, int arg, int want16,
-                                   uint8_t* dst_host, size_t dst_stride, gb200_image_desc* descs, int sub_batch)
+// one pipeline over files [0, n): decode calls on s_decode, downloads on s_copy
+static int decode_batch_host_range(int format, int n, const uint8_t* const* files, const size_t* lens, int arg, int want16,
+                                   uint8_t* dst_host, size_t dst_stride, gb200_image_desc* descs, int sub_batch,
+                                   cudaStream_t s_decode, cudaStream_t s_copy)
 {
-    gb::clear_error();
-    if (!gb::ensure_device()) return 0;
-    if (n < 0 || (n > 0 && (!files || !lens || !dst_host || !descs))) { gb::set_error("gb200_decode_batch_host: bad arguments"); return 0; }
-    if (format != GB200_FORMAT_JPEG && format != GB200_FORMAT_PNG && format != GB200_FORMAT_QOIX && format != GB200_FORMAT_BMP) {
-        gb::set_error("gb200_decode_batch_host: format %d has no batched decoder", format); return 0;
-    }
     if (sub_batch <= 0) {
         // The download of sub-batch k overlaps the upload + kernels of sub-batch k+1, so the call costs about one
         // (small) first decode plus the larger of the two sums. Sizes measured on B200 + PCIe 5 (profiles/r2_e2e_*):
@@ -46,8 +44,6 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
         else if (format == GB200_FORMAT_PNG) sub_batch = 256;
         else sub_batch = 128;
     }
-    cudaStream_t s_decode = gb::thread_stream(0), s_copy = gb::thread_stream(1);
-    if (!s_decode || !s_copy) return 0;
     struct InFlight { gb200_batch* B = nullptr; cudaEvent_t done = nullptr; cudaEvent_t start = nullptr; double t_dec0 = 0, t_dec1 = 0; int a = 0; };
     const bool trace = getenv("GB200_E2E_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -109,4 +105,44 @@ GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* file
     retire(fly[0]); retire(fly[1]);
     if (!ok && !gb200_last_error()[0]) gb::set_error("gb200_decode_batch_host: a transfer failed");
     return ok ? 1 : 0;
+}
+
+GB_API int gb200_decode_batch_host(int format, int n, const uint8_t* const* files, const size_t* lens, int arg, int want16,
+                                   uint8_t* dst_host, size_t dst_stride, gb200_image_desc* descs, int sub_batch)
+{
+    gb::clear_error();
+    if (!gb::ensure_device()) return 0;
+    if (n < 0 || (n > 0 && (!files || !lens || !dst_host || !descs))) { gb::set_error("gb200_decode_batch_host: bad arguments"); return 0; }
+    if (format != GB200_FORMAT_JPEG && format != GB200_FORMAT_PNG && format != GB200_FORMAT_QOIX && format != GB200_FORMAT_BMP) {
+        gb::set_error("gb200_decode_batch_host: format %d has no batched decoder", format); return 0;
+    }
+    // PNG: a decode call costs about 40 ms however few streams it holds (the LZ77 resolver is a chain of dependent
+    // chunks per stream) and leaves most of the machine idle while it does, so the batch is cut into slices that run
+    // their pipelines side by side from as many host threads, each on its own pair of streams (512 1080p files: one
+    // pipeline 207 ms, two slices 177, three 160, four 153). The other formats fill the machine with one call (QOIX
+    // two slices: 110 -> 138 ms).
+    int parts = 1;
+    if (format == GB200_FORMAT_PNG && sub_batch <= 0 && n >= 96) parts = n >= 128 ? 4 : 3;
+    if (const char* e = getenv("GB200_E2E_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= 4) parts = v; }
+    if (parts > n) parts = n > 0 ? n : 1;
+    cudaStream_t st[8];
+    for (int i = 0; i < 2 * parts; ++i) { st[i] = gb::thread_stream(i); if (!st[i]) return 0; }
+    if (parts == 1) return decode_batch_host_range(format, n, files, lens, arg, want16, dst_host, dst_stride, descs, sub_batch, st[0], st[1]);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::vector<int> rc((size_t)parts, 0);
+    std::vector<std::string> errs((size_t)parts);
+    auto run = [&](int t) {
+        const int a = (int)((long long)n * t / parts), b = (int)((long long)n * (t + 1) / parts);
+        if (t > 0) { cudaSetDevice(dev); gb::clear_error(); }      // the current device is per host thread
+        rc[t] = decode_batch_host_range(format, b - a, files + a, lens + a, arg, want16, dst_host + (size_t)a * dst_stride, dst_stride,
+                                        descs + a, sub_batch, st[2 * t], st[2 * t + 1]);
+        if (!rc[t]) errs[t] = gb200_last_error();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < parts; ++t) th.emplace_back(run, t);
+    run(0);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < parts; ++t) if (!rc[t]) { gb::set_error("%s", errs[t].empty() ? "gb200_decode_batch_host: a slice failed" : errs[t].c_str()); return 0; }
+    return 1;
 }

@@ -159,13 +159,13 @@ void  pinned_free(void* p) { pool_free(hpool(), p, true); }
 
 cudaStream_t thread_stream(int idx)
 {
-    // four streams per (thread, device): a stream belongs to the device that was current when it was created
-    static thread_local std::map<int, std::array<cudaStream_t, 4>> per_dev;
-    idx &= 3;
+    // eight streams per (thread, device): a stream belongs to the device that was current when it was created
+    static thread_local std::map<int, std::array<cudaStream_t, 8>> per_dev;
+    idx &= 7;
     if (!ensure_device()) return nullptr;
     const int dev = current_device();
     auto it = per_dev.find(dev);
-    if (it == per_dev.end()) it = per_dev.emplace(dev, std::array<cudaStream_t, 4>{nullptr, nullptr, nullptr, nullptr}).first;
+    if (it == per_dev.end()) it = per_dev.emplace(dev, std::array<cudaStream_t, 8>{}).first;
     cudaStream_t& st = it->second[idx];
     if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st = nullptr; }
     return st;

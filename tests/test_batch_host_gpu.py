@@ -85,3 +85,22 @@ def test_stride_too_small_fails_that_image_only(codecs):
     files = [jpegutil.encode(jpegutil.photo(16, 16, 3, 1), 90, 0), jpegutil.encode(jpegutil.photo(64, 64, 3, 2), 90, 0)]
     res = _run(codecs, 0, files, -1, 16 * 16 * 3, 0)
     assert res[0] is not None and res[1] is None
+
+
+def test_png_batch_host_sliced(codecs, oracle):
+    """100 files with the default sub-batch: the PNG pipeline runs as slices side by side from several host threads
+    (batch_host.cu); every image, including a corrupt one in each slice, must come out as from a single call."""
+    from pngwriter import write_png
+    rng = np.random.default_rng(11)
+    base = [write_png(rng.integers(0, 256, (12 + i, 17 + 2 * i, 4)).astype(np.uint8), 6, 8, filters="adaptive") for i in range(10)]
+    files = [base[i % 10] for i in range(100)]
+    for k in (5, 50, 95):
+        files[k] = files[k][:60]
+    res = _run(codecs, 1, files, 0, 64 * 64 * 4, 0)
+    exp10 = [oracle.png_load(f, 0, 0)[0] for f in base]
+    for i in range(100):
+        if i in (5, 50, 95):
+            assert res[i] is None
+            continue
+        px, d = res[i]
+        assert np.array_equal(px, exp10[i % 10].reshape(-1).view(np.uint8)), i

@@ -226,17 +226,20 @@ jpeg_unstuff_write_kernel(const JpegImage* __restrict__ images, const LongSeg* _
 
 // ---- bit reader over the unstuffed stream (big-endian bit order) -----------------------------------------------
 struct JsBits {
-    const uint32_t* __restrict__ w; uint32_t next; uint64_t buf; int cnt;      // cnt valid bits, MSB-aligned
+    // The word a refill needs was requested at the refill before it: the load's latency (the lanes of a warp read 32
+    // different lines) is off the decode chain.
+    const uint32_t* __restrict__ w; uint32_t next, ahead; uint64_t buf; int cnt;      // cnt valid bits, MSB-aligned
     __device__ __forceinline__ static uint32_t be(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
     __device__ __forceinline__ void init(const uint32_t* words, uint32_t bitpos)
     {
         w = words; next = bitpos >> 5;
         buf = ((uint64_t)be(__ldg(w + next)) << 32) | be(__ldg(w + next + 1));
         next += 2;
+        ahead = __ldg(w + next);
         const int sh = bitpos & 31;
         buf <<= sh; cnt = 64 - sh;
     }
-    __device__ __forceinline__ void refill() { if (cnt <= 32) { buf |= (uint64_t)be(__ldg(w + next)) << (32 - cnt); ++next; cnt += 32; } }
+    __device__ __forceinline__ void refill() { if (cnt <= 32) { buf |= (uint64_t)be(ahead) << (32 - cnt); ++next; cnt += 32; ahead = __ldg(w + next); } }
     __device__ __forceinline__ uint32_t pos() const { return next * 32u - (uint32_t)cnt; }
     __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(buf >> 32); }
     __device__ __forceinline__ void drop(int n) { buf <<= n; cnt -= n; }

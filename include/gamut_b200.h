@@ -149,10 +149,10 @@ int gb200_inflate_device(int n, const uint8_t* const* in_dev, const uint32_t* in
  * decoder for whatever it does not accept (default), 0 = one warp per stream only. Results are identical. */
 void gb200_inflate_set_mode(int parallel);
 
-/* ---- JPEG: source/gamut/codecs/jpegload.d (jpgd port), baseline / extended-sequential Huffman ---- */
+/* ---- JPEG: source/gamut/codecs/jpegload.d (jpgd port), baseline / extended-sequential and progressive Huffman ---- */
 /* decompress_jpeg_image_from_stream (jpegload.d:3720-3808) over a memory buffer. req_comps: -1 keep,
- * 1, 3 or 4. Returns malloc()'d host pixels or NULL. Progressive (SOF2) files are not on this path and
- * fail. pixelAspectRatio / dotsPerInchY are NaN when the file carries no JFIF/EXIF density (the
+ * 1, 3 or 4. Returns malloc()'d host pixels or NULL. Sequential files with one interleaved scan and progressive (SOF2)
+ * files are decoded; non-interleaved multi-scan sequential files fail (see gb200_jpeg_probe). pixelAspectRatio / dotsPerInchY are NaN when the file carries no JFIF/EXIF density (the
  * reference's D float members are never assigned in that case). */
 uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* width, int* height,
                          int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);

@@ -329,6 +329,35 @@ void loadQOIX_b200(ref Image image, IOStream* io, IOHandle handle, int page, int
     image.convertTo(applyLoadFlags(image._type, flags), cast(LayoutConstraints) flags);
 }
 
+/// Replaces saveQOIX (plugins/qoix.d:156-241) for the images the reference routes to qoiplane10_encode (10-bit
+/// greyscale, with or without alpha): the stream is qoiplane10_encode's byte for byte, without the LZ4 stage
+/// (compression = 0, which is what qoix_lz4_encode itself returns whenever LZ4 does not make the file smaller).
+/// Everything else falls through to the reference's own saveQOIX.
+bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    if (page != 0) return false;
+    const bool plane10 = image._type == PixelType.l16 || image._type == PixelType.la16 || image._type == PixelType.lap16;
+    if (!plane10 || image._pitch < 0)
+        return saveQOIX(image, io, handle, page, flags, data);
+
+    gb200_qoix_desc desc;
+    desc.width = image._width;
+    desc.height = image._height;
+    desc.pitchBytes = image._pitch;
+    desc.channels = image._type == PixelType.l16 ? 1 : 2;
+    desc.bitdepth = 10;
+    desc.colorspace = image._type == PixelType.lap16 ? 2 /* QOIX_SRGB_PREMUL */ : 0 /* QOIX_SRGB */;
+    desc.compression = 0;
+    desc.pixelAspectRatio = image._pixelAspectRatio;
+    desc.resolutionY = image._resolutionY;
+
+    int qoilen;
+    ubyte* encoded = gb200_qoix_encode(image._data, &desc, &qoilen);
+    if (encoded is null) return false;
+    scope(exit) free(encoded);
+    return qoilen == io.write(encoded, 1, qoilen, handle);
+}
+
 /// Replaces scanlinesConvert (scanline.d:70-121) for Image.convertTo (image.d:1296): same signature; the
 /// reference's interType / interBuf are accepted and unused (both stages are fused on the GPU).
 bool scanlinesConvert_b200(PixelType srcType, const(ubyte)* src, int srcPitch,

@@ -1,16 +1,19 @@
-// jpeg.cu -- baseline (sequential Huffman) JPEG decode for sm_100a.
+// jpeg.cu -- JPEG decode (sequential and progressive Huffman) for sm_100a.
 //
 // Drop-in for decompress_jpeg_image_from_stream (source/gamut/codecs/jpegload.d:3720-3808) as used by
 // loadJPEG (source/gamut/plugins/jpeg.d:42-104). The marker layer (jpegload.d:1177-1967: DQT, DHT, SOF,
 // DRI, SOS, JFIF/EXIF density) is header logic and runs on the host; every per-bit / per-coefficient /
 // per-pixel step runs on the GPU:
-//   jpeg_huffman_kernel   entropy decode + dequantisation into natural-order int16 blocks
-//                         (decode_next_row, jpegload.d:2405-2525; huff_decode :746-813)
-//   jpeg_idct_kernel      integer LL&M IDCT (Row/Col, :156-397) and, for 4:2:0, the frequency-domain
-//                         chroma upsampling DCT_Upsample + idct_4x4 (:827-1073, :2139-2255)
-//   jpeg_colour_kernel    YCbCr -> RGB(A) / Y with the 16.16 fixed-point constants of create_look_ups
-//                         (:2080-2094, H*Convert :2528-2823) fused with the final channel adaptation
-//                         (:3763-3801)
+//   entropy stage         long segments: jpeg_unstuff_* / jpeg_sync / jpeg_repair / jpeg_scan / jpeg_write
+//                         (jpeg_sync.cuh: chunk-parallel, self-synchronising); segments under 1 KB:
+//                         jpeg_huffman_kernel, one thread per segment; progressive files: jpeg_prog_kernel +
+//                         jpeg_prog_gather_kernel. Entropy decode + dequantisation into natural-order int16
+//                         blocks (decode_next_row, jpegload.d:2405-2525; huff_decode :746-813)
+//   jpeg_idct_colour_kernel  integer LL&M IDCT (Row/Col, :156-397) and, for 4:2:0, the frequency-domain chroma
+//                         upsampling DCT_Upsample + idct_4x4 (:827-1073, :2139-2255), fused with YCbCr ->
+//                         RGB(A) / Y with the 16.16 fixed-point constants of create_look_ups (:2080-2094,
+//                         H*Convert :2528-2823) and the final channel adaptation (:3763-3801): the sample
+//                         tiles never leave shared memory
 // Integer arithmetic throughout; results are bit-exact with the restated reference.
 #include "common.h"
 #include "batch.h"
@@ -405,184 +408,9 @@ __device__ __forceinline__ void idct8(const int in[8], int out[8])
     for (int i = 0; i < 8; ++i) out[i] = FINAL ? clamp255(s[i] >> SH) : (s[i] >> SH);
 }
 
-// Full 8x8 IDCT of a block held as blk[row*8+col] (NR rows x NC columns may be non-zero) -> 64 bytes.
-template <int NR, int NC>
-__device__ __forceinline__ void idct_block(const int16_t* blk, uint8_t* dst)
-{
-    int temp[64];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        int in[8], out[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) in[c] = c < NC ? (int)blk[r * 8 + c] : 0;
-        idct8<false>(in, out);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) temp[r * 8 + c] = out[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        int in[8], out[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) in[r] = r < NR ? temp[r * 8 + c] : 0;
-        idct8<true>(in, out);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) dst[r * 8 + c] = (uint8_t)out[r];
-    }
-}
-
 // DCT_Upsample (jpegload.d:827-1073): a chroma block -> four 4x4 frequency tiles -> idct_4x4 each.
 __device__ __forceinline__ int UD(int i) { return (i + 512) >> 10; }
-__device__ void chroma_upsample(const int16_t* src, uint8_t* dst /* 4 tiles */)
-{
-    // F!(x) = (int)(x * 1024 + 0.5f) evaluated for the 16 constants (jpegload.d:911)
-    const int a1[4] = {426, 810, -360, 284};
-    const int a2[4] = {23, -99, 502, 887};
-    const int b1[4] = {928, -325, 218, -184};
-    const int b2[4] = {-75, 526, 787, -383};
-    int X0[4][8], X1[4][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int s0 = src[j * 8 + 0], s1 = src[j * 8 + 1], s2 = src[j * 8 + 2], s3 = src[j * 8 + 3];
-        const int s4 = src[j * 8 + 4], s5 = src[j * 8 + 5], s6 = src[j * 8 + 6], s7 = src[j * 8 + 7];
-        X0[0][j] = s0;
-        X0[1][j] = UD(a1[0] * s1 + a1[1] * s3 + a1[2] * s5 + a1[3] * s7);
-        X0[2][j] = s4;
-        X0[3][j] = UD(a2[0] * s1 + a2[1] * s3 + a2[2] * s5 + a2[3] * s7);
-        X1[0][j] = UD(b1[0] * s1 + b1[1] * s3 + b1[2] * s5 + b1[3] * s7);
-        X1[1][j] = s2;
-        X1[2][j] = UD(b2[0] * s1 + b2[1] * s3 + b2[2] * s5 + b2[3] * s7);
-        X1[3][j] = s6;
-    }
-    int P[4][4], Q[4][4], R[4][4], S[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int* x = X0[i];
-        P[i][0] = x[0];
-        P[i][1] = UD(x[1] * a1[0] + x[3] * a1[1] + x[5] * a1[2] + x[7] * a1[3]);
-        P[i][2] = x[4];
-        P[i][3] = UD(x[1] * a2[0] + x[3] * a2[1] + x[5] * a2[2] + x[7] * a2[3]);
-        Q[i][0] = UD(x[1] * b1[0] + x[3] * b1[1] + x[5] * b1[2] + x[7] * b1[3]);
-        Q[i][1] = x[2];
-        Q[i][2] = UD(x[1] * b2[0] + x[3] * b2[1] + x[5] * b2[2] + x[7] * b2[3]);
-        Q[i][3] = x[6];
-        const int* y = X1[i];
-        R[i][0] = y[0];
-        R[i][1] = UD(y[1] * a1[0] + y[3] * a1[1] + y[5] * a1[2] + y[7] * a1[3]);
-        R[i][2] = y[4];
-        R[i][3] = UD(y[1] * a2[0] + y[3] * a2[1] + y[5] * a2[2] + y[7] * a2[3]);
-        S[i][0] = UD(y[1] * b1[0] + y[3] * b1[1] + y[5] * b1[2] + y[7] * b1[3]);
-        S[i][1] = y[2];
-        S[i][2] = UD(y[1] * b2[0] + y[3] * b2[1] + y[5] * b2[2] + y[7] * b2[3]);
-        S[i][3] = y[6];
-    }
-    // a = P+Q, b = P-Q, c = R+S, d = R-S; tiles: a+c, a-c, b+d, b-d, stored transposed as short
-    // (jpegload.d:886-902, :2230-2251)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        int16_t tb[32];   // rows 0..3 of the transposed tile, 8 columns each (columns 4..7 unused)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int a = P[r][c] + Q[r][c], b = P[r][c] - Q[r][c], cc = R[r][c] + S[r][c], d = R[r][c] - S[r][c];
-                const int v = t == 0 ? a + cc : t == 1 ? a - cc : t == 2 ? b + d : b - d;
-                tb[c * 8 + r] = (int16_t)v;
-            }
-        }
-        idct_block<4, 4>(tb, dst + t * 64);
-    }
-}
 
-__global__ void __launch_bounds__(128)
-jpeg_idct_kernel(const JpegImage* __restrict__ images, const int* __restrict__ block_base /* per image prefix */, int nimages,
-                 long long total_blocks, const int* __restrict__ status)
-{
-    long long gb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gb >= total_blocks) return;
-    // find the image (few images per launch: linear/binary search over the prefix array)
-    int lo = 0, hi = nimages - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((long long)block_base[mid] <= gb) lo = mid; else hi = mid - 1; }
-    const JpegImage& im = images[lo];
-    if (!status[lo]) return;
-    const int b = (int)(gb - block_base[lo]);
-    const int mcu = b / im.blocks_per_mcu, bi = b - mcu * im.blocks_per_mcu;
-    __align__(16) int16_t blk[64];
-    const int4* src = (const int4*)(im.coefs + (size_t)b * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int4 v = src[i]; *(int4*)(blk + i * 8) = v; }
-    uint8_t* tiles = im.samples + (size_t)mcu * im.tiles_per_mcu * 64;
-    if (im.scan_type == YH2V2 && bi >= 4) {
-        __align__(16) uint8_t out[256];
-        chroma_upsample(blk, out);
-        uint4* d = (uint4*)(tiles + (4 + (bi - 4) * 4) * 64);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = *(uint4*)(out + i * 16);
-    } else {
-        __align__(16) uint8_t out[64];
-        idct_block<8, 8>(blk, out);
-        uint4* d = (uint4*)(tiles + bi * 64);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = *(uint4*)(out + i * 16);
-    }
-}
-
-// ---- colour conversion + channel adaptation ------------------------------------------------------
-__global__ void __launch_bounds__(256)
-jpeg_colour_kernel(const JpegImage* __restrict__ images, const int* __restrict__ status)
-{
-    const JpegImage& im = images[blockIdx.y];
-    if (!status[blockIdx.y]) return;
-    const int W = im.width, H = im.height;
-    const long long npix = (long long)W * H;
-    // FIX!(x) = (int)(x * 65536 + 0.5f) (jpegload.d:2082)
-    const int F140200 = 91881, F177200 = 116130, F071414 = 46802, F034414 = 22554;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npix; i += (long long)gridDim.x * 256) {
-        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
-        int Y, cb = 128, cr = 128;
-        int mx, my, lx, ly;
-        const uint8_t* t;
-        switch (im.scan_type) {
-        case GRAYSCALE:
-            mx = x >> 3; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 64;
-            Y = t[(y & 7) * 8 + (x & 7)];
-            break;
-        case YH1V1:
-            mx = x >> 3; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 3 * 64;
-            lx = (y & 7) * 8 + (x & 7);
-            Y = t[lx]; cb = t[64 + lx]; cr = t[128 + lx];
-            break;
-        case YH2V1:
-            mx = x >> 4; my = y >> 3; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 4 * 64;
-            lx = x & 15; ly = y & 7;
-            Y = t[(lx >> 3) * 64 + ly * 8 + (lx & 7)];
-            cb = t[128 + ly * 8 + (lx >> 1)]; cr = t[192 + ly * 8 + (lx >> 1)];
-            break;
-        case YH1V2:
-            mx = x >> 3; my = y >> 4; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 4 * 64;
-            lx = x & 7; ly = y & 15;
-            Y = t[(ly >> 3) * 64 + (ly & 7) * 8 + lx];
-            cb = t[128 + (ly >> 1) * 8 + lx]; cr = t[192 + (ly >> 1) * 8 + lx];
-            break;
-        default: {   // YH2V2, frequency-domain upsampled: 12 tiles (jpegload.d:2731-2745)
-            mx = x >> 4; my = y >> 4; t = im.samples + ((size_t)my * im.mcus_per_row + mx) * 12 * 64;
-            lx = x & 15; ly = y & 15;
-            const int o = ((ly >> 3) * 2 + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7);
-            Y = t[o]; cb = t[256 + o]; cr = t[512 + o];
-            break; }
-        }
-        uint8_t* d = im.out + (size_t)i * im.req_comps;
-        if (im.comps == 1) {
-            if (im.req_comps == 1) d[0] = (uint8_t)Y;
-            else { d[0] = d[1] = d[2] = (uint8_t)Y; if (im.req_comps == 4) d[3] = 255; }
-        } else {
-            const int r = clamp255(Y + ((F140200 * (cr - 128) + 32768) >> 16));
-            const int g = clamp255(Y + (((-F071414) * (cr - 128) + (-F034414) * (cb - 128) + 32768) >> 16));
-            const int b = clamp255(Y + ((F177200 * (cb - 128) + 32768) >> 16));
-            if (im.req_comps == 1) d[0] = (uint8_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
-            else { d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b; if (im.req_comps == 4) d[3] = 255; }
-        }
-    }
-}
 
 // ---- fused IDCT + chroma upsampling + colour conversion -----------------------------------------
 // One CTA converts a run of consecutive MCUs of one MCU row: 8-thread groups run the two IDCT passes of a
@@ -696,7 +524,6 @@ jpeg_idct_colour_kernel(const JpegImage* __restrict__ images, const uint32_t* __
         const int4 cv = nv; const int zag = nzag;
         fetch(task + IC_GROUPS, nv, nzag);
         const int zmax = __reduce_max_sync(0xffffffffu, zag);
-        const int4* __restrict__ src = (const int4*)(coefs + ((size_t)m * bpm + bi) * 64);
         uint8_t* dst = s_tiles + (st == YH2V2 ? m * IC_MCU420 + bi * 64 : (m * tpm + bi) * 64);
         if (zmax <= 1) {
             // idct with block_max_zag <= 1 (jpegload.d:312-326): all 64 samples are ((dc + 4) >> 3) + 128, clamped

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(QE_THREADS)
 qe_scan_kernel(const QeImage* __restrict__ imgs, QeTile* __restrict__ tiles, int phase, int* __restrict__ out_len)
 {
     __shared__ int s_warp[QE_THREADS / 32];
-    __shared__ unsigned long long s_carry;
     const QeImage& im = imgs[blockIdx.x];
     QeTile* T = tiles + im.tile_base;
     if (phase == 0) {
@@ -212,7 +211,6 @@ qe_scan_kernel(const QeImage* __restrict__ imgs, QeTile* __restrict__ tiles, int
         for (int k = 0; k < QOIX_HEADER_SIZE; ++k) o[k] = im.header[k];
         out_len[blockIdx.x] = QOIX_HEADER_SIZE + (int)(total >> 3);
     }
-    (void)s_carry;
 }
 
 // ---- E3 / E5: codes of a tile. EMIT = false: bits of the tile. EMIT = true: the bits, MSB first, at their place ---

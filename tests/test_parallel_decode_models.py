@@ -193,3 +193,82 @@ def test_lz4_token_chain_self_synchronises():
             steps += 1
         met += x in true_pos and x < len(b)
     assert met >= 0.97 * len(starts)        # the rare miss is what the merge kernel's true-walk fallback is for
+
+
+# ---- QOI-Plane10 encoder: every code from four input pixels + a prefix maximum + a prefix sum ------------------
+def _p10_encode_model(img):
+    """numpy model of csrc/qoix_encode.cu: per-pixel codes computed independently (predictor of the ORIGINAL
+    neighbours), run positions from the distance to the last pixel that differs from its predecessor (a prefix
+    maximum), bit positions from the prefix sum of the code lengths. Returns the payload bits as a string."""
+    h, w, c = img.shape
+    v = (img.astype(np.int64) >> 6)
+    l = v[:, :, 0].reshape(-1)
+    a = v[:, :, 1].reshape(-1) if c == 2 else np.full(h * w, 1023, np.int64)
+    n = h * w
+    pl = np.concatenate(([0], l[:-1])); pa = np.concatenate(([1023], a[:-1]))          # previous pixel in raster order
+    idx = np.arange(n); y = idx // w; x = idx % w
+    up = np.where(y > 0, l[np.maximum(idx - w, 0)], 0)
+    upleft = np.where((y > 0) & (x > 0), l[np.maximum(idx - w - 1, 0)], 0)
+    mx, mn = np.maximum(pl, up), np.minimum(pl, up)
+    med = np.where(upleft >= mx, mn, np.where(upleft <= mn, mx, np.clip(pl + up - upleft, 0, 1023)))
+    pred = np.where(y == 0, pl, np.where(x == 0, up, med))
+    eq = (l == pl) & (a == pa)
+    last_ne = np.maximum.accumulate(np.where(eq, -1, idx))                             # the prefix maximum
+    r = (idx - (last_ne + 1)) & 255
+    nxt_eq = np.concatenate((eq[1:], [False]))
+    run_end = eq & ((r == 255) | (idx == n - 1) | ~nxt_eq)
+    vg = (l - pred) & 1023
+    va = (a - pa) & 1023
+    small = (vg < 4) | (vg >= 1020)
+    codes = []
+    for i in range(n):                      # the emit step, pixel by pixel (each entry depends on pixel i only)
+        if eq[i]:
+            if not run_end[i]:
+                codes.append("")
+            elif r[i] == 0 and small[i]:
+                codes.append(format(int(vg[i]) & 7, "04b"))
+            elif r[i] < 7:
+                codes.append(format(0x30 | int(r[i]), "06b"))
+            else:
+                codes.append(format(0x37, "06b") + format(int(r[i]) - 7, "08b"))
+            continue
+        s = ""
+        if va[i]:
+            if va[i] < 32 or va[i] >= 992:
+                s = format((0x3e << 6) | (int(va[i]) & 0x3f), "012b")
+            else:
+                codes.append(format(0xfe, "08b") + format(int(l[i]), "010b") + format(int(a[i]), "010b"))
+                continue
+        g = int(vg[i])
+        if small[i]:
+            s += format(g & 7, "04b")
+        elif g < 32 or g >= 992:
+            s += format(0x80 | (g & 0x3f), "08b")
+        elif g < 64 or g >= 960:
+            s += format((0x1e << 7) | (g & 0x7f), "012b")
+        else:
+            s += format((0xe << 10) | g, "014b")
+        codes.append(s)
+    lens = np.array([len(s) for s in codes])
+    offs = np.concatenate(([0], np.cumsum(lens)))                                       # the prefix sum
+    bits = ["0"] * int(offs[-1])
+    for i, s in enumerate(codes):           # any order: every code knows its place
+        bits[int(offs[i]):int(offs[i + 1])] = s
+    payload = "".join(bits) + "1" * 40
+    return payload + "1" * (-len(payload) % 8)
+
+
+def test_qoiplane10_encoder_parallel_formulation_equals_the_serial_encoder():
+    from oracle import pyoracle
+    from qoixutil import depth_map_la
+    rng = np.random.default_rng(4)
+    imgs = [depth_map_la(19, 37, 1, 2), depth_map_la(8, 300, 2, 1)]
+    flat = np.zeros((9, 70, 2), np.int64) + np.array([517, 1023])
+    flat[4, 10:] = [518, 1023]
+    imgs.append(((flat << 6) | (flat >> 4)).astype(np.uint16))                          # runs across rows, cut at 256
+    noise = rng.integers(0, 1024, (11, 13, 2))
+    imgs.append(((noise << 6) | (noise >> 4)).astype(np.uint16))
+    for img in imgs:
+        exp = pyoracle.qoiplane10_encode(img)
+        bits = "".join(format(b, "08b") for b in exp[25:])
+        assert _p10_encode_model(img) == bits

@@ -76,7 +76,7 @@ uint8_t* or_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* w, in
 /* ---- QOI (qoi.d) ---- */
 typedef struct { uint32_t width, height; uint8_t channels, colorspace; } or_qoi_desc;
 uint8_t* or_qoi_decode(const uint8_t* data, int size, or_qoi_desc* desc, int channels);  /* qoi.d:448 */
-uint8_t* or_qoi_encode(const uint8_t* pixels, const or_qoi_desc* desc, int* out_len);    /* qoi.d:295 */
+uint8_t* or_qoi_encode(const uint8_t* data, uint32_t width, uint32_t height, int pitchBytes, int channels, int colorspace, int* out_len);    /* qoi.d:295 */
 
 /* ---- QOIX family (qoi2avg.d, qoiplane.d, qoiplane10.d, qoi10b.d, plugins/qoix.d, lz4.d) ---- */
 typedef struct {

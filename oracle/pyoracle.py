@@ -67,6 +67,8 @@ def lib():
         L.or_qoix_lz4_decode.argtypes = [C.c_char_p, C.c_int, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
         L.or_qoix_lz4_encode.restype = C.c_void_p
         L.or_qoix_lz4_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
+        L.or_qoi_encode.restype = C.c_void_p
+        L.or_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.or_qoiplane10_encode.restype = C.c_void_p
         L.or_qoiplane10_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
@@ -177,6 +179,17 @@ def qoix_encode(pixels: np.ndarray, bitdepth: int, colorspace: int = 0, force_lz
     p = lib().or_qoix_lz4_encode(px.ctypes.data, C.byref(d), 1 if force_lz4 else 0, C.byref(n))
     if not p:
         raise RuntimeError("qoix encode failed")
+    return _take(p, n.value).tobytes()
+
+
+def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch=None):
+    """or_qoi_encode (qoi.d:295-426) of a (h, w, 3|4) uint8 image, or None."""
+    h, w, c = pixels.shape
+    px = np.ascontiguousarray(pixels)
+    n = C.c_int(0)
+    p = lib().or_qoi_encode(px.ctypes.data, w, h, pitch if pitch is not None else w * c, c, colorspace, C.byref(n))
+    if not p:
+        return None
     return _take(p, n.value).tobytes()
 
 

@@ -72,6 +72,63 @@ uint8_t* or_qoi_decode(const uint8_t* bytes, int size, or_qoi_desc* desc, int ch
     return pixels;
 }
 
+
+/* qoi.d:295-426 (qoi_encode): raw RGB / RGBA rows (pitch in bytes) -> QOI stream. */
+uint8_t* or_qoi_encode(const uint8_t* data, uint32_t width, uint32_t height, int pitchBytes, int channels, int colorspace, int* out_len)
+{
+    rgba_t index[64]; rgba_t px, px_prev;
+    if (!data || !out_len || width == 0 || height == 0 || channels < 3 || channels > 4 || colorspace < 0 || colorspace > 1 ||
+        height >= QOI_PIXELS_MAX / width) return NULL;
+    int max_size = (int)(width * height * (uint32_t)(channels + 1)) + QOI_HEADER_SIZE + 8;
+    int p = 0;
+    uint8_t* bytes = (uint8_t*)malloc((size_t)max_size);
+    if (!bytes) return NULL;
+    const uint32_t hdr[3] = {QOI_MAGIC, width, height};
+    for (int k = 0; k < 3; ++k) { bytes[p++] = (uint8_t)(hdr[k] >> 24); bytes[p++] = (uint8_t)(hdr[k] >> 16); bytes[p++] = (uint8_t)(hdr[k] >> 8); bytes[p++] = (uint8_t)hdr[k]; }
+    bytes[p++] = (uint8_t)channels;
+    bytes[p++] = (uint8_t)colorspace;
+    memset(index, 0, sizeof(index));
+    int run = 0;
+    px_prev.r = 0; px_prev.g = 0; px_prev.b = 0; px_prev.a = 255;
+    px = px_prev;
+    int px_len = (int)(width * height * (uint32_t)channels), px_end = px_len - channels, px_pos = 0;
+    for (int posy = 0; posy < (int)height; ++posy) {
+        const uint8_t* line = data + (size_t)pitchBytes * posy;
+        for (int posx = 0; posx < (int)width; ++posx) {
+            if (channels == 4) { px.r = line[posx * 4]; px.g = line[posx * 4 + 1]; px.b = line[posx * 4 + 2]; px.a = line[posx * 4 + 3]; }
+            else { px.r = line[posx * 3]; px.g = line[posx * 3 + 1]; px.b = line[posx * 3 + 2]; }
+            if (px.r == px_prev.r && px.g == px_prev.g && px.b == px_prev.b && px.a == px_prev.a) {
+                run++;
+                if (run == 62 || px_pos == px_end) { bytes[p++] = (uint8_t)(0xc0 | (run - 1)); run = 0; }
+            } else {
+                if (run > 0) { bytes[p++] = (uint8_t)(0xc0 | (run - 1)); run = 0; }
+                int index_pos = (px.r * 3 + px.g * 5 + px.b * 7 + px.a * 11) % 64;
+                if (index[index_pos].r == px.r && index[index_pos].g == px.g && index[index_pos].b == px.b && index[index_pos].a == px.a) {
+                    bytes[p++] = (uint8_t)(0x00 | index_pos);
+                } else {
+                    index[index_pos] = px;
+                    if (px.a == px_prev.a) {
+                        int8_t vr = (int8_t)(px.r - px_prev.r), vg = (int8_t)(px.g - px_prev.g), vb = (int8_t)(px.b - px_prev.b);
+                        int8_t vg_r = (int8_t)(vr - vg), vg_b = (int8_t)(vb - vg);
+                        if (vr > -3 && vr < 2 && vg > -3 && vg < 2 && vb > -3 && vb < 2)
+                            bytes[p++] = (uint8_t)(0x40 | (vr + 2) << 4 | (vg + 2) << 2 | (vb + 2));
+                        else if (vg_r > -9 && vg_r < 8 && vg > -33 && vg < 32 && vg_b > -9 && vg_b < 8) {
+                            bytes[p++] = (uint8_t)(0x80 | (vg + 32));
+                            bytes[p++] = (uint8_t)((vg_r + 8) << 4 | (vg_b + 8));
+                        } else { bytes[p++] = 0xfe; bytes[p++] = px.r; bytes[p++] = px.g; bytes[p++] = px.b; }
+                    } else { bytes[p++] = 0xff; bytes[p++] = px.r; bytes[p++] = px.g; bytes[p++] = px.b; bytes[p++] = px.a; }
+                }
+            }
+            px_prev = px;
+            px_pos += channels;
+        }
+    }
+    static const uint8_t padding[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+    for (int i = 0; i < 8; ++i) bytes[p++] = padding[i];
+    *out_len = p;
+    return bytes;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* LZ4 block (lz4.d:760-979)                                                                    */
 enum { ML_BITS = 4, ML_MASK = 15, RUN_MASK = 15, MINMATCH = 4, COPYLENGTH = 8, LASTLITERALS = 5, MFLIMIT = 12 };

@@ -272,3 +272,61 @@ def test_qoiplane10_encoder_parallel_formulation_equals_the_serial_encoder():
         exp = pyoracle.qoiplane10_encode(img)
         bits = "".join(format(b, "08b") for b in exp[25:])
         assert _p10_encode_model(img) == bits
+
+
+# ---- QOI encoder: the index hit of a pixel is a "previous occurrence with the same hash" query ------------------
+def _qoi_encode_model(img):
+    """numpy model of csrc/qoi_encode.cu. qoi_encode (qoi.d:295-426) keeps index[hash] = the latest pixel with that
+    hash that was not a run pixel, so "INDEX" for pixel i is: the latest earlier non-run pixel with i's hash has i's
+    value (or there is none and the pixel is all zero, the index's initial content). Everything else depends on pixels
+    i-1 and i only; runs are cut every 62 pixels from the start of the maximal sequence of equal pixels."""
+    h, w, c = img.shape
+    px = np.zeros((h * w, 4), np.int64); px[:, 3] = 255
+    px[:, :c] = img.reshape(-1, c)
+    v = px[:, 0] | (px[:, 1] << 8) | (px[:, 2] << 16) | (px[:, 3] << 24)
+    n = h * w
+    pv = np.concatenate(([255 << 24], v[:-1]))
+    pp = np.concatenate(([[0, 0, 0, 255]], px[:-1]))
+    idx = np.arange(n)
+    eq = v == pv
+    last_ne = np.maximum.accumulate(np.where(eq, -1, idx))
+    r = (idx - (last_ne + 1)) % 62
+    run_end = eq & ((r == 61) | (idx == n - 1) | ~np.concatenate((eq[1:], [False])))
+    hsh = (px[:, 0] * 3 + px[:, 1] * 5 + px[:, 2] * 7 + px[:, 3] * 11) % 64
+    # previous non-run pixel with the same hash (per-bucket prefix maximum over the non-run pixels)
+    prev_same = np.full(n, -1)
+    for b in range(64):
+        sel = np.flatnonzero(~eq & (hsh == b))
+        prev_same[sel[1:]] = sel[:-1]
+    hit = ~eq & np.where(prev_same >= 0, v[np.maximum(prev_same, 0)] == v, v == 0)
+    s8 = lambda x: ((x + 128) & 255) - 128
+    vr, vg, vb = s8(px[:, 0] - pp[:, 0]), s8(px[:, 1] - pp[:, 1]), s8(px[:, 2] - pp[:, 2])
+    vgr, vgb = s8(vr - vg), s8(vb - vg)
+    out = []
+    for i in range(n):
+        if eq[i]:
+            out.append(bytes([0xc0 | int(r[i])]) if run_end[i] else b"")
+        elif hit[i]:
+            out.append(bytes([int(hsh[i])]))
+        elif px[i, 3] != pp[i, 3]:
+            out.append(bytes([0xff, *px[i].tolist()]))
+        elif -3 < vr[i] < 2 and -3 < vg[i] < 2 and -3 < vb[i] < 2:
+            out.append(bytes([0x40 | (int(vr[i]) + 2) << 4 | (int(vg[i]) + 2) << 2 | (int(vb[i]) + 2)]))
+        elif -9 < vgr[i] < 8 and -33 < vg[i] < 32 and -9 < vgb[i] < 8:
+            out.append(bytes([0x80 | (int(vg[i]) + 32), (int(vgr[i]) + 8) << 4 | (int(vgb[i]) + 8)]))
+        else:
+            out.append(bytes([0xfe, *px[i, :3].tolist()]))
+    return b"".join(out)
+
+
+def test_qoi_encoder_parallel_formulation_equals_the_serial_encoder():
+    from oracle import pyoracle
+    from qoixutil import qoi_test_image
+    rng = np.random.default_rng(2)
+    imgs = [qoi_test_image(40, 50, 4, 1), qoi_test_image(33, 70, 3, 2), np.zeros((6, 40, 4), np.uint8),
+            np.zeros((3, 70, 3), np.uint8), rng.integers(0, 4, (30, 30, 4)).astype(np.uint8) * 60]
+    start255 = np.zeros((4, 30, 4), np.uint8); start255[..., 3] = 255; start255[2:, :, 0] = 9      # starts inside the initial run
+    imgs.append(start255)
+    for img in imgs:
+        exp = pyoracle.qoi_encode(img)
+        assert _qoi_encode_model(img) == exp[14:-8]

@@ -92,6 +92,11 @@ extern(C)
     size_t gb200_qoix_encode_bound(const(gb200_qoix_desc)* desc);
     int gb200_qoix_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_qoix_desc)* descs,
                                        const(ubyte*)* out_dev, int* out_len, void* stream);
+    /// qoi_encode (codecs/qoi.d:295) for rgb8 / rgba8 rows with a signed pitch: the reference encoder's stream
+    ubyte* gb200_qoi_encode(const(ubyte)* pixels, const(gb200_qoi_desc)* desc, int pitchBytes, int* out_len);
+    size_t gb200_qoi_encode_bound(const(gb200_qoi_desc)* desc);
+    int gb200_qoi_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_qoi_desc)* descs, const(int)* pitches,
+                                      const(ubyte*)* out_dev, int* out_len, void* stream);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
     int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
     int gb200_download_by_kernel(void* dst_pinned, const(void)* src_dev, size_t bytes, void* stream);
@@ -353,6 +358,28 @@ bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int pa
 
     int qoilen;
     ubyte* encoded = gb200_qoix_encode(image._data, &desc, &qoilen);
+    if (encoded is null) return false;
+    scope(exit) free(encoded);
+    return qoilen == io.write(encoded, 1, qoilen, handle);
+}
+
+/// Replaces saveQOI (plugins/qoi.d:150-185): same checks, same stream (qoi_encode's byte for byte), the encoder runs
+/// on the GPU. A vertically flipped image is taken as it is (negative pitch), like the reference's qoi_encode.
+bool saveQOI_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    if (page != 0) return false;
+    gb200_qoi_desc desc;
+    desc.width = image._width;
+    desc.height = image._height;
+    desc.colorspace = 0; // QOI_SRGB, as the reference (plugins/qoi.d:159)
+    switch (image._type)
+    {
+        case PixelType.rgb8:  desc.channels = 3; break;
+        case PixelType.rgba8: desc.channels = 4; break;
+        default: return false; // not supported
+    }
+    int qoilen;
+    ubyte* encoded = gb200_qoi_encode(image._data, &desc, image._pitch, &qoilen);
     if (encoded is null) return false;
     scope(exit) free(encoded);
     return qoilen == io.write(encoded, 1, qoilen, handle);

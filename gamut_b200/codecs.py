@@ -68,6 +68,12 @@ def _L():
         L.gb200_jpeg_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         L.gb200_qoi_decode.restype = vp
         L.gb200_qoi_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoiDesc), i32]
+        L.gb200_qoi_encode.restype = vp
+        L.gb200_qoi_encode.argtypes = [vp, C.POINTER(QoiDesc), i32, ip]
+        L.gb200_qoi_encode_bound.restype = sz
+        L.gb200_qoi_encode_bound.argtypes = [C.POINTER(QoiDesc)]
+        L.gb200_qoi_encode_batch_device.restype = i32
+        L.gb200_qoi_encode_batch_device.argtypes = [i32, C.POINTER(vp), C.POINTER(QoiDesc), ip, C.POINTER(vp), ip, vp]
         L.gb200_qoix_decode.restype = vp
         L.gb200_qoix_decode.argtypes = [C.c_char_p, i32, C.POINTER(QoixDesc), i32, ip]
         L.gb200_qoix_encode.restype = vp
@@ -264,6 +270,43 @@ def qoi_decode(data: bytes, channels: int = 0):
         return None
     c = channels if channels else d.channels
     return _take_host(p, d.width * d.height * c).reshape(d.height, d.width, c), d
+
+
+def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch: Optional[int] = None, first_scanline: int = 0,
+               shape: Optional[tuple] = None) -> Optional[bytes]:
+    """qoi_encode (qoi.d:295) as saveQOI calls it (plugins/qoi.d:150): a (h, w, 3|4) uint8 image -> the QOI file, or None
+    where the reference returns null. `pitch` (bytes, may be negative), `first_scanline` (byte offset of the first
+    scanline in `pixels`) and `shape` = (h, w, c) describe padded or vertically flipped storage."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    d = QoiDesc(w, h, c, colorspace)
+    n = C.c_int(0)
+    p = _L().gb200_qoi_encode(px.ctypes.data + first_scanline, C.byref(d), pitch if pitch is not None else w * c, C.byref(n))
+    if not p:
+        return None
+    return _take_host(p, n.value).tobytes()
+
+
+def qoi_encode_bound(w: int, h: int, c: int) -> int:
+    d = QoiDesc(w, h, c, 0)
+    return int(_L().gb200_qoi_encode_bound(C.byref(d)))
+
+
+def qoi_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], out_dev: Sequence[int], stream: int = 0,
+                            pitches: Optional[Sequence[int]] = None):
+    """gb200_qoi_encode_batch_device: device pointers of (h, w, c) uint8 images (gapless unless `pitches` is given) ->
+    device buffers; returns the stream lengths (0 = refused)."""
+    n = len(pixels_dev)
+    pin = (C.c_void_p * max(n, 1))(*pixels_dev)
+    pout = (C.c_void_p * max(n, 1))(*out_dev)
+    descs = (QoiDesc * max(n, 1))()
+    pit = (C.c_int * max(n, 1))()
+    for i, (h, w, c) in enumerate(shapes):
+        descs[i] = QoiDesc(w, h, c, 0)
+        pit[i] = pitches[i] if pitches is not None else w * c
+    lens = (C.c_int * max(n, 1))()
+    _lib.check(_L().gb200_qoi_encode_batch_device(n, pin, descs, pit, pout, lens, stream), "qoi_encode_batch_device")
+    return [lens[i] for i in range(n)]
 
 
 def qoix_decode(data: bytes, flags: int = 0):

@@ -399,22 +399,33 @@ class Image:
         self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
 
     # -- getAdHocLayoutConstraints (image.d:1809-1905)
-    # -- Image.saveToMemory (image.d:966) for the one save path that is built: saveQOIX (plugins/qoix.d:156-241) of a
-    #    10-bit greyscale image, which the reference routes to qoiplane10_encode. Returns the file bytes or None (the
-    #    reference returns a null slice when the plugin's saveProc fails or the format has none).
+    # -- Image.saveToMemory (image.d:966) for the save paths that are built: saveQOIX (plugins/qoix.d:156-241) of a
+    #    10-bit greyscale image, which the reference routes to qoiplane10_encode, and saveQOI (plugins/qoi.d:150-185) of
+    #    an rgb8 / rgba8 image. Returns the file bytes or None (the reference returns a null slice when the plugin's
+    #    saveProc fails or the format has none).
     def saveToMemory(self, fmt, flags: int = 0):
-        if not self.hasData() or int(fmt) != int(ImageFormat.QOIX):
+        if not self.hasData():
             return None
+        import ctypes as C
         t = PixelType(int(self._type))
+        first = self._area.ctypes.data + self._offset
+        if int(fmt) == int(ImageFormat.QOI):
+            if t not in (PixelType.rgb8, PixelType.rgba8):
+                return None                                # saveQOI: "not supported" (plugins/qoi.d:165-169)
+            d = codecs.QoiDesc(self._width, self._height, 3 if t == PixelType.rgb8 else 4, 0)     # QOI_SRGB (:159)
+            n = C.c_int(0)
+            p = codecs._L().gb200_qoi_encode(first, C.byref(d), self._pitch, C.byref(n))
+            return codecs._take_host(p, n.value).tobytes() if p else None
+        if int(fmt) != int(ImageFormat.QOIX):
+            return None
         if t not in (PixelType.l16, PixelType.la16, PixelType.lap16):
             return None                                    # the other sub-encoders are not built
         if self._pitch < self._width * pixelTypeSize(t):
             return None                                    # vertically flipped storage: not taken by the C entry point
-        import ctypes as C
         d = codecs.QoixDesc(self._width, self._height, self._pitch, 1 if t == PixelType.l16 else 2, 10,
                             2 if t == PixelType.lap16 else 0, 0, self._pixelAspectRatio, self._resolutionY)
         n = C.c_int(0)
-        p = codecs._L().gb200_qoix_encode(self._area.ctypes.data + self._offset, C.byref(d), C.byref(n))
+        p = codecs._L().gb200_qoix_encode(first, C.byref(d), C.byref(n))
         return codecs._take_host(p, n.value).tobytes() if p else None
 
     def getAdHocLayoutConstraints(self) -> int:

@@ -182,6 +182,18 @@ int gb200_jpeg_probe(const uint8_t* data, size_t len);
 typedef struct gb200_qoi_desc { uint32_t width, height; uint8_t channels, colorspace; } gb200_qoi_desc;  /* qoi.d:215-222 minus pitchBytes */
 /* qoi_decode (qoi.d:448-550). channels: 0 = as stored, 3 or 4. malloc()'d host pixels or NULL. */
 uint8_t* gb200_qoi_decode(const uint8_t* data, int size, gb200_qoi_desc* desc, int channels);
+/* ---- QOI encode: qoi_encode (qoi.d:295-426) as saveQOI calls it (plugins/qoi.d:150-185) ----
+ * `pixels` = the first scanline of an rgb8 (channels 3) or rgba8 (channels 4) image on the host, pitchBytes signed (the
+ * reference's qoi_desc.pitchBytes, qoi.d:220; negative for a vertically flipped Image). The stream is byte-identical to
+ * qoi_encode's. Returns malloc()'d bytes (gb200_free) and *out_len, or NULL where the reference returns null. */
+uint8_t* gb200_qoi_encode(const uint8_t* pixels, const gb200_qoi_desc* desc, int pitchBytes, int* out_len);
+/* Upper bound of the stream length for a device output buffer (qoi.d:313-315, rounded up). */
+size_t gb200_qoi_encode_bound(const gb200_qoi_desc* desc);
+/* Batched, device-resident: pixels_dev[i] (first scanline, pitches[i] signed) -> out_dev[i] (16-byte aligned, >=
+ * gb200_qoi_encode_bound bytes); out_len[i] = stream length, 0 for an image the encoder refuses. Returns 1 when the
+ * batch ran. */
+int gb200_qoi_encode_batch_device(int n, const uint8_t* const* pixels_dev, const gb200_qoi_desc* descs, const int* pitches,
+                                  uint8_t* const* out_dev, int* out_len, void* stream);
 
 /* ---- QOIX (+LZ4): source/gamut/plugins/qoix.d, codecs/{qoi2avg,qoiplane,qoiplane10,qoi10b,lz4}.d ---- */
 typedef struct gb200_qoix_desc {        /* qoi_desc, qoi2avg.d:276-287 */

@@ -182,12 +182,13 @@ def qoix_encode(pixels: np.ndarray, bitdepth: int, colorspace: int = 0, force_lz
     return _take(p, n.value).tobytes()
 
 
-def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch=None):
-    """or_qoi_encode (qoi.d:295-426) of a (h, w, 3|4) uint8 image, or None."""
-    h, w, c = pixels.shape
+def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch=None, first_scanline: int = 0, shape=None):
+    """or_qoi_encode (qoi.d:295-426) of a (h, w, 3|4) uint8 image, or None. pitch / first_scanline / shape as in
+    gamut_b200.codecs.qoi_encode (padded or vertically flipped storage)."""
     px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
     n = C.c_int(0)
-    p = lib().or_qoi_encode(px.ctypes.data, w, h, pitch if pitch is not None else w * c, c, colorspace, C.byref(n))
+    p = lib().or_qoi_encode(px.ctypes.data + first_scanline, w, h, pitch if pitch is not None else w * c, c, colorspace, C.byref(n))
     if not p:
         return None
     return _take(p, n.value).tobytes()

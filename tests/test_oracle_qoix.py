@@ -23,6 +23,28 @@ def test_qoi_matches_pil(oracle, c):
     assert oracle.qoi_decode(b"qoix" + data[4:], 0) is None
 
 
+@pytest.mark.parametrize("c", [3, 4])
+def test_qoi_encoder_matches_pil_writer(oracle, c):
+    """or_qoi_encode (qoi.d:295-426) against PIL's independent QOI writer, byte for byte: the opcode choice of the
+    format's reference encoder is deterministic (run, index, diff, luma, rgb / rgba in that order), so two faithful
+    encoders agree on the whole stream. PIL writes colorspace from its own default: read it from its header."""
+    rng = np.random.default_rng(c)
+    imgs = [qoi_test_image(64, 80, c, 1), qoi_test_image(3, 200, c, 2), np.zeros((5, 200, c), np.uint8),
+            rng.integers(0, 4, (40, 40, c)).astype(np.uint8) * 70, rng.integers(0, 256, (30, 50, c)).astype(np.uint8),
+            (np.cumsum(rng.integers(-9, 10, (40, 60, c)), axis=1) % 256).astype(np.uint8)]
+    for img in imgs:
+        pil = qoi_bytes(img)
+        assert oracle.qoi_encode(img, colorspace=pil[13]) == pil
+    # pitch: padded rows and a negative pitch address the same pixels
+    img = imgs[0]
+    wide = np.zeros((64, 100, c), np.uint8) + 77
+    wide[:, :80] = img
+    assert oracle.qoi_encode(wide, pitch=100 * c, shape=(64, 80, c)) == oracle.qoi_encode(img)
+    # qoi_encode's refusals (qoi.d:303-311)
+    assert oracle.qoi_encode(img, colorspace=2) is None
+    assert oracle.qoi_encode(img, shape=(64, 80, 2)) is None and oracle.qoi_encode(img, shape=(0, 80, c)) is None
+
+
 def test_qoi_3x1_kat(oracle):
     # image.d:2112-2183: 3x1 rgb8 [255,0,0, 15,64,255, 0,255,255] must survive encode -> decode
     img = np.array([[[255, 0, 0], [15, 64, 255], [0, 255, 255]]], np.uint8)

@@ -87,7 +87,8 @@ extern(C)
                                          const(ubyte*)* files_dev, int req_comps, void* stream);
     gb200_batch* gb200_qoix_decode_batch(int n, const(ubyte*)* files, const(size_t)* lens,
                                          const(ubyte*)* files_dev, int flags, void* stream);
-    /// qoix_lz4_encode (plugins/qoix.d:251) for 10-bit 1/2-channel images: the qoiplane10_encode stream, compression 0
+    /// qoix_lz4_encode (plugins/qoix.d:251) for 1/2-channel images: the qoiplane10_encode (10-bit) / qoiplane_encode
+    /// (8-bit) stream, compression 0
     ubyte* gb200_qoix_encode(const(ubyte)* pixels, const(gb200_qoix_desc)* desc, int* out_len);
     size_t gb200_qoix_encode_bound(const(gb200_qoix_desc)* desc);
     int gb200_qoix_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_qoix_desc)* descs,
@@ -335,23 +336,24 @@ void loadQOIX_b200(ref Image image, IOStream* io, IOHandle handle, int page, int
 }
 
 /// Replaces saveQOIX (plugins/qoix.d:156-241) for the images the reference routes to qoiplane10_encode (10-bit
-/// greyscale, with or without alpha): the stream is qoiplane10_encode's byte for byte, without the LZ4 stage
-/// (compression = 0, which is what qoix_lz4_encode itself returns whenever LZ4 does not make the file smaller).
-/// Everything else falls through to the reference's own saveQOIX.
+/// greyscale, with or without alpha) and to qoiplane_encode (8-bit greyscale, with or without alpha): the stream is the
+/// reference encoder's byte for byte, without the LZ4 stage (compression = 0, which is what qoix_lz4_encode itself
+/// returns whenever LZ4 does not make the file smaller). Everything else falls through to the reference's own saveQOIX.
 bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
 {
     if (page != 0) return false;
     const bool plane10 = image._type == PixelType.l16 || image._type == PixelType.la16 || image._type == PixelType.lap16;
-    if (!plane10 || image._pitch < 0)
+    const bool plane8 = image._type == PixelType.l8 || image._type == PixelType.la8 || image._type == PixelType.lap8;
+    if (!(plane10 || plane8) || image._pitch < 0)
         return saveQOIX(image, io, handle, page, flags, data);
 
     gb200_qoix_desc desc;
     desc.width = image._width;
     desc.height = image._height;
     desc.pitchBytes = image._pitch;
-    desc.channels = image._type == PixelType.l16 ? 1 : 2;
-    desc.bitdepth = 10;
-    desc.colorspace = image._type == PixelType.lap16 ? 2 /* QOIX_SRGB_PREMUL */ : 0 /* QOIX_SRGB */;
+    desc.channels = (image._type == PixelType.l16 || image._type == PixelType.l8) ? 1 : 2;
+    desc.bitdepth = plane10 ? 10 : 8;
+    desc.colorspace = (image._type == PixelType.lap16 || image._type == PixelType.lap8) ? 2 /* QOIX_SRGB_PREMUL */ : 0 /* QOIX_SRGB */;
     desc.compression = 0;
     desc.pixelAspectRatio = image._pixelAspectRatio;
     desc.resolutionY = image._resolutionY;

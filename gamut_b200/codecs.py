@@ -322,12 +322,15 @@ def qoix_decode(data: bytes, flags: int = 0):
     return a.reshape(d.height, d.width, d.channels), d, t.value
 
 
-def qoix_encode(pixels: np.ndarray, bitdepth: int = 10, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0,
+def qoix_encode(pixels: np.ndarray, bitdepth: Optional[int] = None, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0,
                 pitch: Optional[int] = None) -> Optional[bytes]:
-    """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, c) uint16 image whose samples are 10-bit values expanded to 16
-    bits: the QOI-Plane10 stream (qoiplane10.d:99), never LZ4-wrapped. None if the encoder refuses the image."""
+    """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, 1|2) image: uint16 (10-bit values expanded to 16 bits) -> the
+    QOI-Plane10 stream (qoiplane10.d:99), uint8 -> the QOI-Plane stream (qoiplane.d:109); never LZ4-wrapped. None if the
+    encoder refuses the image."""
     h, w, c = pixels.shape
     px = np.ascontiguousarray(pixels)
+    if bitdepth is None:
+        bitdepth = 10 if px.itemsize == 2 else 8
     d = QoixDesc(w, h, pitch if pitch is not None else w * c * px.itemsize, c, bitdepth, colorspace, 0, par, dpi)
     n = C.c_int(0)
     p = _L().gb200_qoix_encode(px.ctypes.data, C.byref(d), C.byref(n))
@@ -341,15 +344,17 @@ def qoix_encode_bound(w: int, h: int, c: int) -> int:
     return int(_L().gb200_qoix_encode_bound(C.byref(d)))
 
 
-def qoix_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], out_dev: Sequence[int], stream: int = 0):
-    """gb200_qoix_encode_batch_device: device pointers of gapless (h, w, c) uint16 images -> device buffers; returns the
-    stream lengths."""
+def qoix_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], out_dev: Sequence[int], stream: int = 0,
+                             bitdepths: Optional[Sequence[int]] = None):
+    """gb200_qoix_encode_batch_device: device pointers of gapless (h, w, c) images (uint16 for bitdepth 10, the default;
+    uint8 for bitdepth 8) -> device buffers; returns the stream lengths."""
     n = len(pixels_dev)
     pin = (C.c_void_p * max(n, 1))(*pixels_dev)
     pout = (C.c_void_p * max(n, 1))(*out_dev)
     descs = (QoixDesc * max(n, 1))()
     for i, (h, w, c) in enumerate(shapes):
-        descs[i] = QoixDesc(w, h, w * c * 2, c, 10, 0, 0, -1.0, -1.0)
+        bd = bitdepths[i] if bitdepths is not None else 10
+        descs[i] = QoixDesc(w, h, w * c * (2 if bd == 10 else 1), c, bd, 0, 0, -1.0, -1.0)
     lens = (C.c_int * max(n, 1))()
     _lib.check(_L().gb200_qoix_encode_batch_device(n, pin, descs, pout, lens, stream), "qoix_encode_batch_device")
     return [lens[i] for i in range(n)]

@@ -400,7 +400,7 @@ class Image:
 
     # -- getAdHocLayoutConstraints (image.d:1809-1905)
     # -- Image.saveToMemory (image.d:966) for the save paths that are built: saveQOIX (plugins/qoix.d:156-241) of a
-    #    10-bit greyscale image, which the reference routes to qoiplane10_encode, and saveQOI (plugins/qoi.d:150-185) of
+    #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode), and saveQOI (plugins/qoi.d:150-185) of
     #    an rgb8 / rgba8 image. Returns the file bytes or None (the reference returns a null slice when the plugin's
     #    saveProc fails or the format has none).
     def saveToMemory(self, fmt, flags: int = 0):
@@ -418,12 +418,16 @@ class Image:
             return codecs._take_host(p, n.value).tobytes() if p else None
         if int(fmt) != int(ImageFormat.QOIX):
             return None
-        if t not in (PixelType.l16, PixelType.la16, PixelType.lap16):
-            return None                                    # the other sub-encoders are not built
+        if t in (PixelType.l16, PixelType.la16, PixelType.lap16):
+            channels, bitdepth = (1 if t == PixelType.l16 else 2), 10          # -> qoiplane10_encode (plugins/qoix.d:199-212)
+        elif t in (PixelType.l8, PixelType.la8, PixelType.lap8):
+            channels, bitdepth = (1 if t == PixelType.l8 else 2), 8            # -> qoiplane_encode (plugins/qoix.d:172-184)
+        else:
+            return None                                    # the RGB sub-encoders (QOI2AVG, QOI-10b) are not built
         if self._pitch < self._width * pixelTypeSize(t):
             return None                                    # vertically flipped storage: not taken by the C entry point
-        d = codecs.QoixDesc(self._width, self._height, self._pitch, 1 if t == PixelType.l16 else 2, 10,
-                            2 if t == PixelType.lap16 else 0, 0, self._pixelAspectRatio, self._resolutionY)
+        d = codecs.QoixDesc(self._width, self._height, self._pitch, channels, bitdepth,
+                            2 if t in (PixelType.lap16, PixelType.lap8) else 0, 0, self._pixelAspectRatio, self._resolutionY)
         n = C.c_int(0)
         p = codecs._L().gb200_qoix_encode(first, C.byref(d), C.byref(n))
         return codecs._take_host(p, n.value).tobytes() if p else None

@@ -69,6 +69,8 @@ def lib():
         L.or_qoix_lz4_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
         L.or_qoi_encode.restype = C.c_void_p
         L.or_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.or_qoiplane_encode.restype = C.c_void_p
+        L.or_qoiplane_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_qoiplane10_encode.restype = C.c_void_p
         L.or_qoiplane10_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
@@ -189,6 +191,18 @@ def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch=None, first_scanli
     h, w, c = shape if shape is not None else px.shape
     n = C.c_int(0)
     p = lib().or_qoi_encode(px.ctypes.data + first_scanline, w, h, pitch if pitch is not None else w * c, c, colorspace, C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value).tobytes()
+
+
+def qoiplane_encode(pixels: np.ndarray, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0, pitch=None):
+    """or_qoiplane_encode (qoiplane.d:109-375) of a (h, w, 1|2) uint8 image: the stream without the LZ4 stage, or None."""
+    h, w, c = pixels.shape
+    px = np.ascontiguousarray(pixels)
+    d = QoixDesc(w, h, pitch if pitch is not None else w * c, c, 8, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = lib().or_qoiplane_encode(px.ctypes.data, C.byref(d), C.byref(n))
     if not p:
         return None
     return _take(p, n.value).tobytes()

@@ -336,3 +336,85 @@ uint8_t* or_qoi10b_decode(const uint8_t* data, int size, or_qoix_desc* desc, int
     free(cur); free(last);
     return pixels;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* qoiplane_encode (qoiplane.d:109-375): 8-bit L / LA -> QOI-Plane stream (no LZ4 stage). Restated so that the
+ * reference's round-trip property (image.d:2112-2183: encode -> decode == image) can be replayed for this codec and so
+ * that the GPU encoder has a byte-exact target. */
+typedef struct { uint8_t* bytes; int p; int hi; } nibw;
+static void outputNibble(nibw* w, uint8_t nibble)                 /* :158-170 */
+{
+    if (w->hi) w->bytes[w->p] = (uint8_t)(nibble << 4); else w->bytes[w->p++] |= nibble;
+    w->hi = !w->hi;
+}
+static void outputByte(nibw* w, uint8_t b)                        /* :172-184 */
+{
+    if (w->hi) w->bytes[w->p++] = b;
+    else { w->bytes[w->p++] |= (uint8_t)(b >> 4); w->bytes[w->p] = (uint8_t)(b << 4); }
+}
+static void encodeRun(nibw* w, int* run)                          /* :186-212 */
+{
+    if (*run <= 3) outputNibble(w, (uint8_t)(0xc | (*run - 1)));
+    else { *run -= 4; outputNibble(w, 0xf); outputByte(w, (uint8_t)*run); }
+    *run = 0;
+}
+uint8_t* or_qoiplane_encode(const uint8_t* data, const or_qoix_desc* desc, int* out_len)
+{
+    if ((desc->channels != 1 && desc->channels != 2) || desc->width == 0 ||      /* width == 0 divides by zero in the reference */
+        desc->height >= QOIX_PIXELS_MAX / desc->width || desc->compression != 0) return NULL;
+    if (desc->bitdepth != 8) return NULL;
+    const int channels = desc->channels;
+    const int num_pixels = (int)(desc->width * desc->height);
+    const int worst = channels == 1 ? 3 : 6;
+    const int max_size = (num_pixels * worst + 1) / 2 + QOIX_HEADER_SIZE + 4;
+    uint8_t* bytes = (uint8_t*)calloc((size_t)max_size + 2, 1);
+    if (!bytes) return NULL;
+    int p = 0;
+    const uint32_t hdr[3] = {0x716F6978u, desc->width, desc->height};
+    for (int k = 0; k < 3; ++k) { bytes[p++] = (uint8_t)(hdr[k] >> 24); bytes[p++] = (uint8_t)(hdr[k] >> 16); bytes[p++] = (uint8_t)(hdr[k] >> 8); bytes[p++] = (uint8_t)hdr[k]; }
+    bytes[p++] = 1;
+    bytes[p++] = desc->channels;
+    bytes[p++] = desc->bitdepth;
+    bytes[p++] = desc->colorspace;
+    bytes[p++] = 0;
+    uint32_t f[2];
+    memcpy(&f[0], &desc->pixelAspectRatio, 4); memcpy(&f[1], &desc->resolutionY, 4);
+    for (int k = 0; k < 2; ++k) { bytes[p++] = (uint8_t)(f[k] >> 24); bytes[p++] = (uint8_t)(f[k] >> 16); bytes[p++] = (uint8_t)(f[k] >> 8); bytes[p++] = (uint8_t)f[k]; }
+    nibw W = {bytes, p, 1};
+    uint8_t px_l = 0, px_a = 255, ref_l = 0, ref_a = 255;              /* initialPredictor (:95) */
+    int run = 0, pixels_encoded = 0;
+    for (int posy = 0; posy < (int)desc->height; ++posy) {
+        const uint8_t* line = data + (ptrdiff_t)desc->pitchBytes * posy;
+        const uint8_t* lineAbove = posy > 0 ? data + (ptrdiff_t)desc->pitchBytes * (posy - 1) : NULL;
+        for (int posx = 0; posx < (int)desc->width; ++posx) {
+            ref_l = px_l; ref_a = px_a;
+            px_l = line[posx * channels];
+            if (channels == 2) px_a = line[posx * channels + 1];
+            if (px_l == ref_l && px_a == ref_a) {
+                run++;
+                if (run == 258 || pixels_encoded + 1 == num_pixels) encodeRun(&W, &run);
+            } else {
+                if (run > 0) encodeRun(&W, &run);
+                const int8_t va = (int8_t)(px_a - ref_a);
+                int colour = 1;
+                if (va) {
+                    if (va >= -7 && va <= 7) { outputNibble(&W, 0xb); outputNibble(&W, (uint8_t)(va + 8)); }
+                    else { outputNibble(&W, 0xb); outputNibble(&W, 0x0); outputByte(&W, px_l); outputByte(&W, px_a); colour = 0; }
+                }
+                if (colour) {
+                    const uint8_t px_top = posy > 0 ? lineAbove[posx * channels] : ref_l;
+                    const uint8_t px_avg = (uint8_t)((px_top + ref_l + 1) / 2);
+                    const int8_t diff_avg = (int8_t)(px_l - px_avg);
+                    if (diff_avg >= -4 && diff_avg <= 3) outputNibble(&W, (uint8_t)(diff_avg + 4));
+                    else if (diff_avg >= -16 && diff_avg <= 15) outputByte(&W, (uint8_t)(0x80 | (uint8_t)(diff_avg + 16)));
+                    else { outputNibble(&W, 0xa); outputByte(&W, px_l); }
+                }
+            }
+            pixels_encoded++;
+        }
+    }
+    for (int i = 0; i < 9; ++i) outputNibble(&W, 0xf);                  /* :318-322 */
+    if (!W.hi) outputNibble(&W, 0xf);
+    *out_len = W.p;
+    return bytes;
+}

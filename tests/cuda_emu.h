@@ -60,6 +60,14 @@ static inline uint32_t __ballot_sync(unsigned, bool p)
 static inline int atomicMax(int* a, int v) { int old = __atomic_load_n(a, __ATOMIC_RELAXED); while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {} return old; }
 static inline uint32_t atomicOr(uint32_t* a, uint32_t v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t v = (uint64_t)b << 32 | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xff) << (8 * k);
+    return r;
+}
 static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 using std::max;
 using std::min;

@@ -73,7 +73,7 @@ def test_pitch_colorspace_and_rejects(codecs, oracle):
     n = C.c_int(0)
     p = cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(d), C.byref(n))
     assert p and cd._take_host(p, n.value).tobytes() == exp
-    for bad in (cd.QoixDesc(30, 20, 120, 3, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 8, 0, 0, -1, -1),
+    for bad in (cd.QoixDesc(30, 20, 120, 3, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 9, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 4, 8, 0, 0, -1, -1),
                 cd.QoixDesc(0, 20, 120, 2, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 10, 0, 1, -1, -1),
                 cd.QoixDesc(30, 20, 60, 2, 10, 0, 0, -1, -1)):
         assert not cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(bad), C.byref(n))
@@ -106,3 +106,61 @@ def test_image_save_qoix(codecs, oracle):
         out = im.saveToMemory(ImageFormat.QOIX)
         assert out == src
         assert im.saveToMemory(ImageFormat.PNG) is None
+
+
+# ---- QOI-Plane (8-bit L / LA): qoiplane_encode, codecs/qoiplane.d:109-375 --------------------------------------------
+def check8(codecs, oracle, img, **kw):
+    exp = oracle.qoiplane_encode(img, **kw)
+    got = codecs.qoix_encode(img, **kw)
+    assert exp is not None and got is not None
+    assert len(got) == len(exp)
+    assert got == exp
+    dec = codecs.qoix_decode(got)
+    assert dec is not None and np.array_equal(dec[0], img)
+    assert np.array_equal(oracle.qoix_decode(got, 0)[0], img)
+    return got
+
+
+@pytest.mark.parametrize("c", [1, 2])
+def test_qoiplane_8bit(codecs, oracle, c):
+    from test_qoix_encode_emulated import plane8_images
+    for img in plane8_images(c, np.random.default_rng(10 + c)):
+        check8(codecs, oracle, img, par=1.5, dpi=96.0, colorspace=1)
+    check8(codecs, oracle, (depth_map_la(257, 1024, 5, c) >> 8).astype(np.uint8))
+    check8(codecs, oracle, (depth_map_la(1080, 1920, 6, c) >> 8).astype(np.uint8))
+
+
+def test_qoiplane_8bit_pitch_and_mixed_batch(codecs, oracle):
+    import ctypes as C
+    import torch
+    from gamut_b200 import codecs as cd
+    rng = np.random.default_rng(3)
+    a8 = (depth_map_la(20, 30, 1, 2) >> 8).astype(np.uint8)
+    wide = rng.integers(0, 256, (20, 37, 2)).astype(np.uint8)
+    wide[:, :30] = a8                                              # row padding must not be read as pixels
+    d = cd.QoixDesc(30, 20, 74, 2, 8, 0, 0, -1.0, -1.0)
+    n = C.c_int(0)
+    p = cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(d), C.byref(n))
+    assert p and cd._take_host(p, n.value).tobytes() == oracle.qoiplane_encode(a8)
+    assert not cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(cd.QoixDesc(30, 20, 59, 2, 8, 0, 0, -1, -1)), C.byref(n))
+    # one device batch holding 10-bit and 8-bit images in any order
+    imgs = [(depth_map_la(300, 500, 6, 1) >> 8).astype(np.uint8), depth_map_la(200, 333, 7, 2), (depth_map_la(512, 512, 8, 2) >> 8).astype(np.uint8)]
+    exp = [oracle.qoiplane_encode(imgs[0]), oracle.qoiplane10_encode(imgs[1]), oracle.qoiplane_encode(imgs[2])]
+    dev = [torch.from_numpy(i.view(np.int16) if i.itemsize == 2 else i).cuda() for i in imgs]
+    outs = [torch.empty(codecs.qoix_encode_bound(i.shape[1], i.shape[0], i.shape[2]) + 16, dtype=torch.uint8, device="cuda") for i in imgs]
+    lens = codecs.qoix_encode_batch_device([t.data_ptr() for t in dev], [i.shape for i in imgs], [o.data_ptr() for o in outs], bitdepths=[8, 10, 8])
+    torch.cuda.synchronize()
+    for o, k, e in zip(outs, lens, exp):
+        assert k == len(e) and o[:k].cpu().numpy().tobytes() == e
+
+
+def test_image_save_qoix_8bit(codecs, oracle):
+    """Image.saveToMemory(QOIX) of an 8-bit greyscale image (saveQOIX -> qoiplane_encode, plugins/qoix.d:172-184)."""
+    from gamut_b200.image import Image
+    from gamut_b200.types import ImageFormat, PixelType
+    for c in (1, 2):
+        img = (depth_map_la(37, 61, 9, c) >> 8).astype(np.uint8)
+        src = oracle.qoiplane_encode(img, par=2.0, dpi=72.0)
+        im = Image()
+        assert im.loadFromMemory(src, 0) and im.type() == (PixelType.l8 if c == 1 else PixelType.la8)
+        assert im.saveToMemory(ImageFormat.QOIX) == src

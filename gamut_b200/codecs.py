@@ -85,6 +85,10 @@ def _L():
         L.gb200_qoix_decode_batch.restype = vp
         L.gb200_qoix_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), i32, vp]
         L.gb200_jpeg_probe.argtypes = [C.c_char_p, sz]
+        L.gb200_tga_load.restype = vp
+        L.gb200_tga_load.argtypes = [C.c_char_p, sz, ip, ip, ip]
+        L.gb200_tga_decode_batch.restype = vp
+        L.gb200_tga_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), vp]
         L.gb200_bmp_load.restype = vp
         L.gb200_bmp_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp, fp]
         L.gb200_bmp_decode_batch.restype = vp
@@ -378,6 +382,24 @@ def decode_batch_host(fmt: int, files: Sequence[bytes], arg: int, want16: int, d
     _lib.check(_L().gb200_decode_batch_host(int(fmt), n, arr, lens, arg, want16, dst_host, dst_stride, descs, sub_batch),
                "decode_batch_host")
     return [descs[i] for i in range(n)]
+
+
+def tga_load(data: bytes):
+    """TGADecoder.getImageInfo + decodeImage (codecs/tga.d:313-588), as plugins/tga.d:45-70 calls them: pixels
+    (h, w, c) uint8 with c = 1 (l8), 2 (la8), 3 (rgb8) or 4 (rgba8), or None."""
+    w, h, comp = C.c_int(0), C.c_int(0), C.c_int(0)
+    p = _L().gb200_tga_load(data, len(data), C.byref(w), C.byref(h), C.byref(comp))
+    if not p:
+        return None
+    return _take_host(p, w.value * h.value * comp.value).reshape(h.value, w.value, comp.value)
+
+
+def tga_decode_batch(files: Sequence[bytes], files_dev: Optional[Sequence[int]] = None, stream: int = 0) -> Batch:
+    n, arr, lens, dev = _batch_args(files, files_dev)
+    h = _L().gb200_tga_decode_batch(n, arr, lens, dev, stream)
+    if not h:
+        raise _lib.GamutB200Error("tga_decode_batch: " + _lib.last_error())
+    return Batch(h)
 
 
 def bmp_load(data: bytes, req_comp: int = 0) -> Optional[PngResult]:

@@ -20,6 +20,7 @@ gb200_batch* png_decode_batch(int n, const uint8_t* const* files, const size_t* 
                               int req_comp, int want16, cudaStream_t st);
 gb200_batch* jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
                                int req_comps, cudaStream_t st);
+gb200_batch* tga_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev, cudaStream_t st);
 gb200_batch* bmp_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
                               int req_comp, cudaStream_t st);
 gb200_batch* qoix_decode_batch(int n, const uint8_t* const* files, const size_t* lens, const uint8_t* const* files_dev,
@@ -131,11 +132,12 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
     // format without a loader are different errors
     const int fmt = gb200_identify_format(data, len);
     if (fmt < 0) return fail(kUnidentified);
-    if (fmt != GB200_FORMAT_JPEG && fmt != GB200_FORMAT_PNG && fmt != GB200_FORMAT_QOI && fmt != GB200_FORMAT_QOIX && fmt != GB200_FORMAT_BMP)
-        return fail(kNoLoadSupport);            // DDS / TGA / GIF / JXL / SQZ: detected, no decoder in this build
+    if (fmt != GB200_FORMAT_JPEG && fmt != GB200_FORMAT_PNG && fmt != GB200_FORMAT_QOI && fmt != GB200_FORMAT_QOIX && fmt != GB200_FORMAT_BMP &&
+        fmt != GB200_FORMAT_TGA)
+        return fail(kNoLoadSupport);            // DDS / GIF / JXL / SQZ: detected, no decoder in this build
     if (len > 0x7fffffffu) return fail(kDecodingFailed);
     int req = requested_components(flags);
-    if (req == 0) return fail(kInvalidFlags);
+    if (req == 0 && fmt != GB200_FORMAT_TGA) return fail(kInvalidFlags);      // loadTGA does not look at the component flags itself
     if (!gb::ensure_device()) { out->error = gb200_last_error(); return 0; }      // there is no CPU fallback
     cudaStream_t st = gb::thread_stream();
     const uint8_t* f[1] = {data}; size_t l[1] = {len};
@@ -183,6 +185,10 @@ GB_API int gb200_image_load(const uint8_t* data, size_t len, int flags, gb200_im
         type = t8[req ? req : D.file_channels];
         par = D.pixelAspectRatio == -1 ? -1.0f : D.pixelAspectRatio;
         resY = D.ppmY == -1 ? -1.0f : D.ppmY / 39.37007874f;            // convertInchesToMeters(ppmY), bmp.d:134
+    } else if (fmt == GB200_FORMAT_TGA) {       // plugins/tga.d:45-105: no flag logic of its own, unknown resolution
+        B = gb::tga_decode_batch(1, f, l, nullptr, st);
+        if (!B || !B->images[0].status) { delete B; return fail(kDecodingFailed); }
+        type = B->images[0].pixel_type;
     } else {                                    // plugins/qoix.d:64-146
         B = gb::qoix_decode_batch(1, f, l, nullptr, flags, st);
         if (!B || !B->images[0].status) { delete B; return fail(kDecodingFailed); }

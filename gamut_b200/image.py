@@ -296,12 +296,21 @@ class Image:
             self.error(kStrImageFormatUnidentified)
             return False
         loaders = {ImageFormat.PNG: self._loadPNG, ImageFormat.JPEG: self._loadJPEG, ImageFormat.QOI: self._loadQOI,
-                   ImageFormat.QOIX: self._loadQOIX, ImageFormat.BMP: self._loadBMP}
+                   ImageFormat.QOIX: self._loadQOIX, ImageFormat.BMP: self._loadBMP, ImageFormat.TGA: self._loadTGA}
         if fif not in loaders:                       # plugin.loadProc is null (image.d:1766-1770)
             self.error(kStrImageFormatNoLoadSupport)
             return False
         loaders[fif](data, flags)
         return self.isValid()
+
+    def _loadTGA(self, data, flags):  # plugins/tga.d:45-105
+        px = codecs.tga_load(data)
+        if px is None:
+            return self.error(kStrImageDecodingFailed)
+        comps = px.shape[2]
+        t = (None, _P.l8, _P.la8, _P.rgb8, _P.rgba8)[comps]
+        self._adopt(px, t, px.shape[1] * comps, 0, GAMUT_UNKNOWN_ASPECT_RATIO, GAMUT_UNKNOWN_RESOLUTION)
+        self.convertTo(applyLoadFlags(self._type, flags), flags & 0xFFFF)
 
     def _loadBMP(self, data, flags):  # plugins/bmp.d:93-163
         req = computeRequestedImageComponents(flags)

@@ -158,6 +158,16 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
                          int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
+/* ---- TGA ----
+ * TGADecoder.getImageInfo + decodeImage (codecs/tga.d:313-588) as loadTGA calls them (plugins/tga.d:45-105): grey,
+ * grey + alpha, 15/16-bit and 24/32-bit colour, colour-mapped files (8/16-bit indices; 8/15/16/24/32-bit entries), raw
+ * or run-length coded, bottom-up or top-down. Returns malloc'd pixels (gb200_free) or NULL; *comp = components of the
+ * decoded image (1 = l8, 2 = la8, 3 = rgb8, 4 = rgba8; the decoder has no req_comp, the plugin converts afterwards). */
+uint8_t* gb200_tga_load(const uint8_t* data, size_t len, int* width, int* height, int* comp);
+/* Batched, device-resident output. files[i] (host bytes) are always needed -- header and palette are read on the host;
+ * files_dev, when not NULL, holds the same bytes on the device and saves the upload. */
+gb200_batch* gb200_tga_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
+                                    const uint8_t* const* files_dev, void* stream);
 /* ---- BMP ----
  * stbi_load_from_callbacks on a BMP file (codecs/stbdec.d:725 -> stbi__bmp_load :2263-2466), as loadBMP calls it
  * (plugins/bmp.d:112): 1/4/8-bit palettes, 16/32-bit bit fields, 24/32-bit BGR(A), bottom-up and top-down, OS/2 and

@@ -64,6 +64,9 @@ int or_png_unfilter(const uint8_t* raw, size_t raw_len, int img_n, int out_n, in
  * absent from the reference tree). Returns malloc'd buffer, sets *outlen. */
 uint8_t* or_zlib_decode(const uint8_t* in, size_t inlen, size_t guess, int parse_header, size_t* outlen);
 
+/* ---- TGA (codecs/tga.d:313-646 as plugins/tga.d:45-105 calls it) ---- */
+uint8_t* or_tga_load(const uint8_t* data, size_t len, int* width, int* height, int* comp);
+
 /* ---- BMP (stbdec.d:2112-2510) and format detection (image.d:1045-1061, plugins' detect procs) ---- */
 uint8_t* or_bmp_load(const uint8_t* data, size_t len, int req_comp, int* x, int* y, int* comp,
                      float* ppmX, float* ppmY, float* pixelRatio);

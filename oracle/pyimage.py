@@ -280,6 +280,13 @@ def load_from_memory(data: bytes, flags: int = 0) -> OImage:
         comps = req if req else comp
         resY = -1.0 if ppmY == -1 else float(np.float32(ppmY) / np.float32(39.37007874))
         _adopt(im, px, (None, L8, LA8, RGB8, RGBA8)[comps], px.shape[1] * comps, -1.0 if ratio == -1 else ratio, resY)
+    elif pyoracle.identify_format(data) == 5:              # plugins/tga.d:45-105 (no component-flag logic of its own)
+        px = pyoracle.tga_load(data)
+        if px is None:
+            im.error = E_DECODE
+            return im
+        comps = px.shape[2]
+        _adopt(im, px, (None, L8, LA8, RGB8, RGBA8)[comps], px.shape[1] * comps, -1.0, -1.0)
     elif pyoracle.identify_format(data) >= 0:              # detected, but the build has no loader for it (image.d:1766-1770)
         im.error = E_NOLOAD
         return im

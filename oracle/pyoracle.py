@@ -76,6 +76,8 @@ def lib():
         L.or_lz4_compress.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.or_lz4_compress_bound.argtypes = [C.c_int]
         L.or_lz4_decompress_fast.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        L.or_tga_load.restype = C.c_void_p
+        L.or_tga_load.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
         L.or_bmp_load.restype = C.c_void_p
         L.or_bmp_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_float)] * 3
         L.or_identify_format.argtypes = [C.c_char_p, C.c_size_t]
@@ -245,6 +247,18 @@ def bmp_load(data: bytes, req_comp: int = 0):
     a = np.ctypeslib.as_array((C.c_uint8 * max(n, 1)).from_address(p))[:n].copy().reshape(y.value, x.value, c)
     lib().or_free(p)
     return a, comp.value, px.value, py.value, pr.value
+
+
+def tga_load(data: bytes):
+    """TGADecoder.getImageInfo + decodeImage (codecs/tga.d:313-588): pixels[h, w, c] (l8 / la8 / rgb8 / rgba8) or None."""
+    x, y, comp = C.c_int(), C.c_int(), C.c_int()
+    p = lib().or_tga_load(data, len(data), C.byref(x), C.byref(y), C.byref(comp))
+    if not p:
+        return None
+    n = x.value * y.value * comp.value
+    a = np.ctypeslib.as_array((C.c_uint8 * max(n, 1)).from_address(p))[:n].copy().reshape(y.value, x.value, comp.value)
+    lib().or_free(p)
+    return a
 
 
 def identify_format(data: bytes) -> int:

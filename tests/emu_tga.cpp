@@ -1,0 +1,26 @@
+// emu_tga.cpp -- gamut_b200/csrc/tga.cuh (header walk + the two TGA kernels) compiled for the host under
+// tests/cuda_emu.h. The launch sequence below is the one of gb::tga_decode_batch (tga.cu); test infrastructure only.
+#include "cuda_emu.h"
+#include "../gamut_b200/csrc/tga.cuh"
+#include <stdlib.h>
+
+// Decodes one file into out (capacity out_cap); returns 1 and w / h / comp, or 0 where the decoder fails.
+extern "C" int emu_tga_load(const uint8_t* data, size_t len, uint8_t* out, size_t out_cap, int* w, int* h, int* comp)
+{
+    TgaPlan P;
+    if (len > 0xfffffff0u || !tga_plan(data, len, P)) return 0;
+    if ((size_t)P.w * P.h * P.components > out_cap) return -1;
+    int fail = 0;
+    TgaJob J; memset(&J, 0, sizeof(J));
+    J.data = data; J.palette = P.palette.empty() ? nullptr : P.palette.data(); J.out = out; J.fail = &fail;
+    J.len = (uint32_t)len; J.pix_off = P.pix_off; J.palette_len = P.palette_len; J.pix_base = 0;
+    J.w = P.w; J.h = P.h; J.components = P.components; J.src_bytes = P.src_bytes; J.mode = P.mode; J.index16 = P.index16;
+    J.inverted = P.inverted; J.rle = P.rle;
+    const TgaJob* dj = &J;
+    const uint32_t total = (uint32_t)P.w * (uint32_t)P.h;
+    if (!P.rle) emu::launch(dim3((total + 255) / 256), 256, [&] { tga_raw_kernel(dj, 1, total); });
+    else emu::launch(dim3(1), 32, [&] { tga_rle_kernel(dj); });
+    if (fail) return 0;
+    *w = P.w; *h = P.h; *comp = P.components;
+    return 1;
+}

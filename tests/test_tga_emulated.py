@@ -1,0 +1,77 @@
+"""The TGA decoder's header walk and kernels without a GPU: gamut_b200/csrc/tga.cuh compiled for the host under the
+thread-per-CUDA-thread emulation (tests/cuda_emu.h, tests/emu_tga.cpp) and compared with the oracle's restatement of
+TGADecoder (codecs/tga.d:313-588) on every variant of tests/tgautil.py, truncated files included."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tgautil import make_tga, pil_tga
+from test_oracle_tga import CASES
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD, "libemu_tga.so")
+SRCS = [os.path.join(HERE, "emu_tga.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "..", "gamut_b200", "csrc", "tga.cuh")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(BUILD, exist_ok=True)
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", LIB, SRCS[0]])
+    L = C.CDLL(LIB)
+    L.emu_tga_load.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
+    return L
+
+
+def emu_load(L, data):
+    out = np.full(1 << 20, 0xEE, np.uint8)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    r = L.emu_tga_load(data, len(data), out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(c))
+    assert r >= 0
+    if r == 0:
+        return None
+    n = w.value * h.value * c.value
+    assert (out[n:] == 0xEE).all()
+    return out[:n].reshape(h.value, w.value, c.value).copy()
+
+
+def same(a, b):
+    return (a is None and b is None) or (a is not None and b is not None and a.shape == b.shape and np.array_equal(a, b))
+
+
+@pytest.mark.parametrize("kind,kw", CASES)
+def test_variants(emu, oracle, kind, kw):
+    rng = np.random.default_rng(7)
+    for rle in (False, True):
+        for top_down in (False, True):
+            for (w, h) in [(1, 1), (13, 9), (131, 40)]:
+                data, _ = make_tga(w, h, kind, rng, rle=rle, top_down=top_down, **kw)
+                exp = oracle.tga_load(data)
+                assert exp is not None and same(emu_load(emu, data), exp)
+                for cut in (len(data) - 1, len(data) - 7, len(data) // 2, 19, 18, 5):
+                    assert same(emu_load(emu, data[:cut]), oracle.tga_load(data[:cut]))
+
+
+def test_pil_files_overrun_and_rejects(emu, oracle):
+    rng = np.random.default_rng(1)
+    for c in (1, 3, 4):
+        img = rng.integers(0, 4, (23, 37, c)).astype(np.uint8) * 80
+        for rle in (False, True):
+            data = pil_tga(img, rle, bool(c & 1))
+            assert same(emu_load(emu, data), img)
+    data, _ = make_tga(17, 11, "bgr24", rng, rle=True, overrun=True)
+    assert same(emu_load(emu, data), oracle.tga_load(data))
+    ok, _ = make_tga(5, 4, "pal24", rng, pal_len=9)
+    for at, v in [(1, 2), (2, 4), (16, 12), (16, 24), (7, 12)]:
+        bad = bytearray(ok); bad[at] = v
+        assert emu_load(emu, bytes(bad)) is None and oracle.tga_load(bytes(bad)) is None
+    for _ in range(300):                                        # header fuzz: both sides accept / reject the same files
+        bad = bytearray(ok)
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, 18))] = int(rng.integers(0, 256))
+        bad[12:16] = (5).to_bytes(2, "little") + (4).to_bytes(2, "little")      # keep the size small
+        assert same(emu_load(emu, bytes(bad)), oracle.tga_load(bytes(bad)))

@@ -98,6 +98,15 @@ extern(C)
     size_t gb200_qoi_encode_bound(const(gb200_qoi_desc)* desc);
     int gb200_qoi_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_qoi_desc)* descs, const(int)* pitches,
                                       const(ubyte*)* out_dev, int* out_len, void* stream);
+    /// TGADecoder.getImageInfo + decodeImage (codecs/tga.d:313-588): malloc'd l8 / la8 / rgb8 / rgba8 pixels by *comp
+    ubyte* gb200_tga_load(const(ubyte)* data, size_t len, int* width, int* height, int* comp);
+    gb200_batch* gb200_tga_decode_batch(int n, const(ubyte*)* files, const(size_t)* lens, const(ubyte*)* files_dev, void* stream);
+    /// saveTGA -> TGAEncoder (codecs/tga.d:62-292): the run-length file, byte for byte
+    struct gb200_tga_desc { int width, height, pitchBytes, type; }
+    ubyte* gb200_tga_encode(const(ubyte)* pixels, const(gb200_tga_desc)* desc, int* out_len);
+    size_t gb200_tga_encode_bound(const(gb200_tga_desc)* desc);
+    int gb200_tga_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_tga_desc)* descs, const(ubyte*)* out_dev,
+                                      int* out_len, void* stream);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
     int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
     int gb200_download_by_kernel(void* dst_pinned, const(void)* src_dev, size_t bytes, void* stream);
@@ -191,6 +200,34 @@ void loadPNG_b200(ref Image image, IOStream* io, IOHandle handle, int page, int 
     static immutable PixelType[5] t8  = [PixelType.unknown, PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8];
     static immutable PixelType[5] t16 = [PixelType.unknown, PixelType.l16, PixelType.la16, PixelType.rgb16, PixelType.rgba16];
     image._type = decodeTo16bit ? t16[components] : t8[components];
+    image.convertTo(applyLoadFlags(image._type, flags), cast(LayoutConstraints) flags);
+}
+
+/// Replaces loadTGA (plugins/tga.d:45-105).
+void loadTGA_b200(ref Image image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    int len;
+    ubyte* buf = slurp(io, handle, len, image);
+    if (buf is null) return;
+    scope(exit) free(buf);
+
+    int width, height, components;
+    ubyte* decoded = gb200_tga_load(buf, len, &width, &height, &components);
+    if (decoded is null) { image.error(kStrImageDecodingFailed); return; }
+    if (!imageIsValidSize(1, width, height)) { image.error(kStrImageTooLarge); free(decoded); return; }
+
+    static immutable PixelType[5] t8 = [PixelType.unknown, PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8];
+    image._type = t8[components];
+    image._allocArea = decoded;
+    image._width = width;
+    image._height = height;
+    image._data = decoded;
+    image._pitch = width * components;
+    image._pixelAspectRatio = GAMUT_UNKNOWN_ASPECT_RATIO;
+    image._resolutionY = GAMUT_UNKNOWN_RESOLUTION;
+    image._layoutConstraints = LAYOUT_DEFAULT;
+    image._layerCount = 1;
+    image._layerOffset = 0;
     image.convertTo(applyLoadFlags(image._type, flags), cast(LayoutConstraints) flags);
 }
 
@@ -363,6 +400,23 @@ bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int pa
     if (encoded is null) return false;
     scope(exit) free(encoded);
     return qoilen == io.write(encoded, 1, qoilen, handle);
+}
+
+/// Replaces saveTGA (plugins/tga.d:123-149): the TGAEncoder's file (24- or 32-bit, run-length coded, bottom row first),
+/// every scanline coded in parallel on the GPU. The pixel types TGAEncoder.initialize refuses are refused here too.
+bool saveTGA_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    if (page != 0) return false;
+    gb200_tga_desc desc;
+    desc.width = image._width;
+    desc.height = image._height;
+    desc.pitchBytes = image._pitch;
+    desc.type = cast(int) image._type;
+    int len;
+    ubyte* encoded = gb200_tga_encode(image._data, &desc, &len);
+    if (encoded is null) return false;
+    scope(exit) free(encoded);
+    return len == io.write(encoded, 1, len, handle);
 }
 
 /// Replaces saveQOI (plugins/qoi.d:150-185): same checks, same stream (qoi_encode's byte for byte), the encoder runs

@@ -26,6 +26,10 @@ class LoadedImage(C.Structure):     # gb200_image
                 ("pixelAspectRatio", C.c_float), ("resolutionY", C.c_float), ("error", C.c_char_p)]
 
 
+class TgaDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("type", C.c_int32)]
+
+
 class QoiDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint8), ("colorspace", C.c_uint8)]
 
@@ -89,6 +93,12 @@ def _L():
         L.gb200_tga_load.argtypes = [C.c_char_p, sz, ip, ip, ip]
         L.gb200_tga_decode_batch.restype = vp
         L.gb200_tga_decode_batch.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(sz), C.POINTER(vp), vp]
+        L.gb200_tga_encode.restype = vp
+        L.gb200_tga_encode.argtypes = [vp, C.POINTER(TgaDesc), ip]
+        L.gb200_tga_encode_bound.restype = sz
+        L.gb200_tga_encode_bound.argtypes = [C.POINTER(TgaDesc)]
+        L.gb200_tga_encode_batch_device.restype = i32
+        L.gb200_tga_encode_batch_device.argtypes = [i32, C.POINTER(vp), C.POINTER(TgaDesc), C.POINTER(vp), ip, vp]
         L.gb200_bmp_load.restype = vp
         L.gb200_bmp_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp, fp]
         L.gb200_bmp_decode_batch.restype = vp
@@ -400,6 +410,42 @@ def tga_decode_batch(files: Sequence[bytes], files_dev: Optional[Sequence[int]] 
     if not h:
         raise _lib.GamutB200Error("tga_decode_batch: " + _lib.last_error())
     return Batch(h)
+
+
+_TGA_TYPE = {1: 0, 2: 3, 3: 9, 4: 12}          # channels -> PixelType l8 / la8 / rgb8 / rgba8
+
+
+def tga_encode(pixels: np.ndarray, pitch: Optional[int] = None, first_scanline: int = 0, shape: Optional[tuple] = None,
+               type_: Optional[int] = None) -> Optional[bytes]:
+    """saveTGA (plugins/tga.d:123-149) of a (h, w, 1|2|3|4) uint8 image (l8 / la8 / rgb8 / rgba8): the run-length TGA file
+    TGAEncoder writes, or None where saveTGA fails. pitch / first_scanline / shape describe padded or flipped storage."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    d = TgaDesc(w, h, pitch if pitch is not None else w * c, type_ if type_ is not None else _TGA_TYPE.get(c, -1))
+    n = C.c_int(0)
+    p = _L().gb200_tga_encode(px.ctypes.data + first_scanline, C.byref(d), C.byref(n))
+    if not p:
+        return None
+    return _take_host(p, n.value).tobytes()
+
+
+def tga_encode_bound(w: int, h: int, c: int) -> int:
+    d = TgaDesc(w, h, w * c, _TGA_TYPE[c])
+    return int(_L().gb200_tga_encode_bound(C.byref(d)))
+
+
+def tga_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], out_dev: Sequence[int], stream: int = 0):
+    """gb200_tga_encode_batch_device: device pointers of gapless (h, w, c) uint8 images -> device buffers; returns the file
+    lengths (0 = refused)."""
+    n = len(pixels_dev)
+    pin = (C.c_void_p * max(n, 1))(*pixels_dev)
+    pout = (C.c_void_p * max(n, 1))(*out_dev)
+    descs = (TgaDesc * max(n, 1))()
+    for i, (h, w, c) in enumerate(shapes):
+        descs[i] = TgaDesc(w, h, w * c, _TGA_TYPE.get(c, -1))
+    lens = (C.c_int * max(n, 1))()
+    _lib.check(_L().gb200_tga_encode_batch_device(n, pin, descs, pout, lens, stream), "tga_encode_batch_device")
+    return [lens[i] for i in range(n)]
 
 
 def bmp_load(data: bytes, req_comp: int = 0) -> Optional[PngResult]:

@@ -8,9 +8,12 @@
 // chain walked by the warp and the pixels of a packet placed by its lanes (tga_rle_kernel) -- the chain is serial by
 // the format (a packet header says where the next one is), so this half is a parity path, not a fast one.
 // The row flip (:537-551) and the B/R swap (:553-565) are folded into the store / the palette.
+// The encoder (saveTGA, plugins/tga.d:123-149 -> TGAEncoder, codecs/tga.d:62-292) is at the end of the file; its kernels
+// and their description are in tga_encode.cuh.
 #include "../../include/gamut_b200.h"
 #include "batch.h"
 #include "tga.cuh"
+#include "tga_encode.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -144,5 +147,102 @@ GB_API uint8_t* gb200_tga_load(const uint8_t* data, size_t len, int* width, int*
     if (comp) *comp = D.channels;
     delete B;
     if (!ok) { free(out); return nullptr; }
+    return out;
+}
+
+// ---- encoder -----------------------------------------------------------------------------------------------------------
+namespace gb {
+
+// Encodes n device-resident images into n device buffers (each at least gb200_tga_encode_bound bytes). out_len[i] =
+// file length, 0 for an image the encoder refuses.
+bool tga_encode_device(int n, const uint8_t* const* pixels_dev, const gb200_tga_desc* descs, uint8_t* const* out_dev, int* out_len,
+                       cudaStream_t st)
+{
+    if (!ensure_device()) return false;
+    std::vector<TeImage> imgs; std::vector<int> which;
+    uint32_t total_rows = 0; int most = 0;
+    for (int i = 0; i < n; ++i) {
+        out_len[i] = 0;
+        TeImage T;
+        if (!te_setup(T, pixels_dev[i], descs[i].type, descs[i].width, descs[i].height, descs[i].pitchBytes, out_dev[i], total_rows)) continue;
+        imgs.push_back(T); which.push_back(i);
+        most = std::max(most, T.h);
+    }
+    const int m = (int)imgs.size();
+    if (!m) return true;
+    DevBuf d_imgs(sizeof(TeImage) * (size_t)m), d_bytes(4 * ((size_t)total_rows + 1)), d_off(4 * ((size_t)total_rows + 1)), d_len(sizeof(int) * (size_t)m);
+    PinnedBuf h_len(sizeof(int) * (size_t)m);
+    if (!d_imgs.p || !d_bytes.p || !d_off.p || !d_len.p || !h_len.p) return false;
+    bool ok = cuda_ok(cudaMemcpyAsync(d_imgs.p, imgs.data(), sizeof(TeImage) * (size_t)m, cudaMemcpyHostToDevice, st), "te imgs", __FILE__, __LINE__);
+    for (int k0 = 0; ok && k0 < m; k0 += 65535) {               // grid.y is limited to 65535
+        const int mk = std::min(65535, m - k0);
+        const dim3 grid((unsigned)most, (unsigned)mk);
+        const TeImage* dI = d_imgs.as<TeImage>() + k0;
+        te_row_kernel<false><<<grid, 32, 0, st>>>(dI, d_bytes.as<uint32_t>(), d_off.as<uint32_t>());
+        te_scan_kernel<<<mk, 256, 0, st>>>(dI, d_bytes.as<uint32_t>(), d_off.as<uint32_t>(), d_len.as<int>() + k0);
+        te_row_kernel<true><<<grid, 32, 0, st>>>(dI, d_bytes.as<uint32_t>(), d_off.as<uint32_t>());
+        count_launch(3);
+    }
+    ok = ok && dev_read_back_async(h_len.p, d_len.p, sizeof(int) * (size_t)m, st);
+    ok = cuda_ok(cudaStreamSynchronize(st), "te sync", __FILE__, __LINE__) && ok;
+    ok = ok && cuda_ok(cudaGetLastError(), "te kernels", __FILE__, __LINE__);
+    if (ok) for (int k = 0; k < m; ++k) out_len[which[k]] = h_len.as<int>()[k];
+    return ok;
+}
+
+} // namespace gb
+
+GB_API size_t gb200_tga_encode_bound(const gb200_tga_desc* desc)
+{
+    return desc ? te_bound(desc->type, desc->width, desc->height) : 0;
+}
+
+GB_API int gb200_tga_encode_batch_device(int n, const uint8_t* const* pixels_dev, const gb200_tga_desc* descs, uint8_t* const* out_dev,
+                                         int* out_len, void* stream)
+{
+    gb::clear_error();
+    if (n < 0 || !pixels_dev || !descs || !out_dev || !out_len) { gb::set_error("tga_encode_batch_device: bad arguments"); return 0; }
+    return gb::tga_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream) ? 1 : 0;
+}
+
+// saveTGA (plugins/tga.d:123-149): `pixels` = the first scanline of an l8 / la8 / rgb8 / rgba8 image on the host,
+// desc->pitchBytes signed. malloc()'d file out (free with gb200_free), *out_len its length; NULL where saveTGA fails
+// (other pixel types, a side above 65535).
+GB_API uint8_t* gb200_tga_encode(const uint8_t* pixels, const gb200_tga_desc* desc, int* out_len)
+{
+    gb::clear_error();
+    if (!gb::ensure_device()) return nullptr;
+    const int sc = desc ? te_src_channels(desc->type) : 0;
+    if (!pixels || !out_len || !sc || desc->width < 0 || desc->height < 0 || desc->width > 65535 || desc->height > 65535) {
+        gb::set_error("tga_encode: unsupported image (TGA takes l8 / la8 / rgb8 / rgba8 up to 65535 x 65535)");
+        return nullptr;
+    }
+    if (desc->width == 0 || desc->height == 0) {                 // the reference writes the header and no scanline bytes (:147-148)
+        uint8_t* out = (uint8_t*)calloc(18, 1);
+        if (!out) return nullptr;
+        out[2] = 10; out[12] = (uint8_t)(desc->width & 0xff); out[13] = (uint8_t)(desc->width >> 8);
+        out[14] = (uint8_t)(desc->height & 0xff); out[15] = (uint8_t)(desc->height >> 8); out[16] = (uint8_t)(((sc & 1) ? 3 : 4) * 8);
+        *out_len = 18;
+        return out;
+    }
+    const size_t row = (size_t)desc->width * sc;
+    const size_t ap = desc->pitchBytes < 0 ? (size_t)(-(long long)desc->pitchBytes) : (size_t)desc->pitchBytes;
+    if (ap < row && desc->height > 1) { gb::set_error("tga_encode: pitch smaller than a scanline"); return nullptr; }
+    cudaStream_t st = gb::thread_stream();
+    const size_t span = ap * (size_t)(desc->height - 1) + row, cap = gb200_tga_encode_bound(desc);
+    if (cap > 0x7fffffffull) { gb::set_error("tga_encode: file would exceed 2 GiB"); return nullptr; }
+    const uint8_t* lowest = desc->pitchBytes < 0 ? pixels - ap * (size_t)(desc->height - 1) : pixels;
+    gb::DevBuf d_in(span), d_out(cap);
+    if (!d_in.p || !d_out.p) return nullptr;
+    if (!gb::cuda_ok(cudaMemcpyAsync(d_in.p, lowest, span, cudaMemcpyHostToDevice, st), "te h2d", __FILE__, __LINE__)) { cudaStreamSynchronize(st); return nullptr; }
+    const uint8_t* pin[1] = {d_in.as<uint8_t>() + (pixels - lowest)}; uint8_t* pout[1] = {d_out.as<uint8_t>()};
+    int len = 0;
+    if (!gb::tga_encode_device(1, pin, desc, pout, &len, st) || len <= 0) { cudaStreamSynchronize(st); return nullptr; }
+    uint8_t* out = (uint8_t*)malloc((size_t)len);
+    if (!out) return nullptr;
+    const bool ok = gb::cuda_ok(cudaMemcpyAsync(out, d_out.p, (size_t)len, cudaMemcpyDeviceToHost, st), "te d2h", __FILE__, __LINE__) &&
+                    gb::cuda_ok(cudaStreamSynchronize(st), "te sync", __FILE__, __LINE__);
+    if (!ok) { cudaStreamSynchronize(st); free(out); return nullptr; }
+    *out_len = len;
     return out;
 }

@@ -409,7 +409,8 @@ class Image:
 
     # -- getAdHocLayoutConstraints (image.d:1809-1905)
     # -- Image.saveToMemory (image.d:966) for the save paths that are built: saveQOIX (plugins/qoix.d:156-241) of a
-    #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode), and saveQOI (plugins/qoi.d:150-185) of
+    #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode), saveTGA (plugins/tga.d:123-149) of an
+    #    l8 / la8 / rgb8 / rgba8 image, and saveQOI (plugins/qoi.d:150-185) of
     #    an rgb8 / rgba8 image. Returns the file bytes or None (the reference returns a null slice when the plugin's
     #    saveProc fails or the format has none).
     def saveToMemory(self, fmt, flags: int = 0):
@@ -424,6 +425,13 @@ class Image:
             d = codecs.QoiDesc(self._width, self._height, 3 if t == PixelType.rgb8 else 4, 0)     # QOI_SRGB (:159)
             n = C.c_int(0)
             p = codecs._L().gb200_qoi_encode(first, C.byref(d), self._pitch, C.byref(n))
+            return codecs._take_host(p, n.value).tobytes() if p else None
+        if int(fmt) == int(ImageFormat.TGA):
+            if t not in (PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8):
+                return None                                # TGAEncoder.initialize: unsupported format (codecs/tga.d:108-110)
+            d = codecs.TgaDesc(self._width, self._height, self._pitch, int(t))
+            n = C.c_int(0)
+            p = codecs._L().gb200_tga_encode(first, C.byref(d), C.byref(n))
             return codecs._take_host(p, n.value).tobytes() if p else None
         if int(fmt) != int(ImageFormat.QOIX):
             return None

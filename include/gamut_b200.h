@@ -168,6 +168,14 @@ uint8_t* gb200_tga_load(const uint8_t* data, size_t len, int* width, int* height
  * files_dev, when not NULL, holds the same bytes on the device and saves the upload. */
 gb200_batch* gb200_tga_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                     const uint8_t* const* files_dev, void* stream);
+/* ---- TGA encode: saveTGA (plugins/tga.d:123-149) -> TGAEncoder (codecs/tga.d:62-292), run-length coding on ----
+ * type = gb200_pixel_type of the rows: l8 / la8 / rgb8 / rgba8 (written as a 24- or 32-bit file, bottom row first);
+ * pitchBytes signed, `pixels` = the first scanline. The file is byte-identical to the one saveTGA writes. */
+typedef struct gb200_tga_desc { int32_t width, height, pitchBytes, type; } gb200_tga_desc;
+uint8_t* gb200_tga_encode(const uint8_t* pixels, const gb200_tga_desc* desc, int* out_len);
+size_t gb200_tga_encode_bound(const gb200_tga_desc* desc);
+int gb200_tga_encode_batch_device(int n, const uint8_t* const* pixels_dev, const gb200_tga_desc* descs, uint8_t* const* out_dev,
+                                  int* out_len, void* stream);
 /* ---- BMP ----
  * stbi_load_from_callbacks on a BMP file (codecs/stbdec.d:725 -> stbi__bmp_load :2263-2466), as loadBMP calls it
  * (plugins/bmp.d:112): 1/4/8-bit palettes, 16/32-bit bit fields, 24/32-bit BGR(A), bottom-up and top-down, OS/2 and

@@ -66,6 +66,7 @@ uint8_t* or_zlib_decode(const uint8_t* in, size_t inlen, size_t guess, int parse
 
 /* ---- TGA (codecs/tga.d:313-646 as plugins/tga.d:45-105 calls it) ---- */
 uint8_t* or_tga_load(const uint8_t* data, size_t len, int* width, int* height, int* comp);
+uint8_t* or_tga_encode(const uint8_t* data, int type, int width, int height, int pitchBytes, int* out_len);   /* plugins/tga.d:123, codecs/tga.d:62-292 */
 
 /* ---- BMP (stbdec.d:2112-2510) and format detection (image.d:1045-1061, plugins' detect procs) ---- */
 uint8_t* or_bmp_load(const uint8_t* data, size_t len, int req_comp, int* x, int* y, int* comp,

@@ -78,6 +78,8 @@ def lib():
         L.or_lz4_decompress_fast.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.or_tga_load.restype = C.c_void_p
         L.or_tga_load.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
+        L.or_tga_encode.restype = C.c_void_p
+        L.or_tga_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.or_bmp_load.restype = C.c_void_p
         L.or_bmp_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_float)] * 3
         L.or_identify_format.argtypes = [C.c_char_p, C.c_size_t]
@@ -259,6 +261,19 @@ def tga_load(data: bytes):
     a = np.ctypeslib.as_array((C.c_uint8 * max(n, 1)).from_address(p))[:n].copy().reshape(y.value, x.value, comp.value)
     lib().or_free(p)
     return a
+
+
+def tga_encode(pixels: np.ndarray, pitch=None, first_scanline: int = 0, shape=None, type_=None):
+    """saveTGA -> TGAEncoder (plugins/tga.d:123-149, codecs/tga.d:62-292) of a (h, w, 1|2|3|4) uint8 image (l8 / la8 /
+    rgb8 / rgba8): the run-length TGA file, or None."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    t = type_ if type_ is not None else {1: 0, 2: 3, 3: 9, 4: 12}[c]
+    n = C.c_int(0)
+    p = lib().or_tga_encode(px.ctypes.data + first_scanline, t, w, h, pitch if pitch is not None else w * c, C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value).tobytes()
 
 
 def identify_format(data: bytes) -> int:

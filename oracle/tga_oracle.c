@@ -132,3 +132,78 @@ bad:
     free(palette); free(out);
     return NULL;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* saveTGA (plugins/tga.d:123-149) -> TGAEncoder.initialize / encodeScanline (codecs/tga.d:62-292) with RLE enabled:
+ * l8 / la8 / rgb8 / rgba8 rows (type = PixelType value 0, 3, 9, 12) -> a 24- or 32-bit run-length TGA, bottom-up.
+ * `data` = first scanline, pitchBytes signed. Returns malloc()'d file bytes or NULL (unsupported type, side > 65535). */
+uint8_t* or_tga_encode(const uint8_t* data, int type, int width, int height, int pitchBytes, int* out_len)
+{
+    int channels;
+    if (width > 65535 || height > 65535 || width < 0 || height < 0) return NULL;
+    switch (type) {                                             /* :88-111 */
+    case 0: channels = 3; break;      /* l8    -> rgb8 */
+    case 3: channels = 4; break;      /* la8   -> rgba8 */
+    case 9: channels = 3; break;      /* rgb8 */
+    case 12: channels = 4; break;     /* rgba8 */
+    default: return NULL;
+    }
+    const size_t cap = 18 + (size_t)height * ((size_t)width * (channels + 1) + 2);
+    uint8_t* out = (uint8_t*)malloc(cap);
+    uint8_t* scanSpace = (uint8_t*)malloc((size_t)width * channels + (size_t)width * 2 + 1);
+    if (!out || !scanSpace) { free(out); free(scanSpace); return NULL; }
+    int8_t* similarMask = (int8_t*)(scanSpace + (size_t)width * channels);
+    int8_t* opcode = similarMask + width;
+    size_t p = 0;
+    memset(out, 0, 18);                                         /* header :120-131 */
+    out[2] = 10;
+    out[12] = (uint8_t)(width & 0xff); out[13] = (uint8_t)((width & 0xff00) >> 8);
+    out[14] = (uint8_t)(height & 0xff); out[15] = (uint8_t)((height & 0xff00) >> 8);
+    out[16] = (uint8_t)(channels * 8);
+    p = 18;
+    for (int y = height - 1; y >= 0; --y) {                     /* plugins/tga.d:141-145 */
+        const uint8_t* scan = data + (ptrdiff_t)pitchBytes * y;
+        if (width == 0) continue;
+        /* _scanConvert, then swap R and B (:152-178) */
+        for (int x = 0; x < width; ++x) {
+            uint8_t r, g, b, a = 255;
+            if (type == 0) r = g = b = scan[x];
+            else if (type == 3) { r = g = b = scan[2 * x]; a = scan[2 * x + 1]; }
+            else if (type == 9) { r = scan[3 * x]; g = scan[3 * x + 1]; b = scan[3 * x + 2]; }
+            else { r = scan[4 * x]; g = scan[4 * x + 1]; b = scan[4 * x + 2]; a = scan[4 * x + 3]; }
+            scanSpace[channels * x] = b; scanSpace[channels * x + 1] = g; scanSpace[channels * x + 2] = r;
+            if (channels == 4) scanSpace[4 * x + 3] = a;
+        }
+        {   /* 1. similarity between consecutive pixels (:186-203) */
+            uint8_t last[4] = {0, 0, 0, 0};
+            for (int x = 0; x < width; ++x) {
+                uint8_t c[4] = {scanSpace[channels * x], scanSpace[channels * x + 1], scanSpace[channels * x + 2],
+                                (uint8_t)(channels == 3 ? 255 : scanSpace[x * 4 + 3])};
+                similarMask[x] = memcmp(c, last, 4) == 0 ? 1 : 0;
+                memcpy(last, c, 4);
+            }
+            similarMask[0] = 0;
+        }
+        int numSame = 0, numDifferent = 0;                       /* 2. (:207-243) */
+        for (int x = width - 1; x >= 0; --x) {
+            const float bppRaw = (1 + numDifferent * channels) / (float)numDifferent;
+            const float bppRLE = (1 + channels) / (float)numSame;
+            if (bppRaw <= bppRLE) opcode[x] = (int8_t)numDifferent;
+            else opcode[x] = (int8_t)(0x80 | numSame);
+            if (similarMask[x]) { numSame += 1; if (numSame >= 127) numSame = 127; numDifferent = 0; }
+            else { numDifferent += 1; if (numDifferent >= 127) numDifferent = 127; numSame = 0; }
+        }
+        for (int x = 0; x < width; ) {                           /* 3. (:252-271) */
+            const int8_t hint = opcode[x];
+            out[p++] = (uint8_t)hint;
+            const int num = (hint & 127) + 1;
+            const size_t nbytes = hint >= 0 ? (size_t)num * channels : (size_t)channels;
+            memcpy(out + p, &scanSpace[x * channels], nbytes);
+            p += nbytes;
+            x += num;
+        }
+    }
+    free(scanSpace);
+    *out_len = (int)p;
+    return out;
+}

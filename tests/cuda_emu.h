@@ -57,6 +57,8 @@ static inline uint32_t __ballot_sync(unsigned, bool p)
     pthread_barrier_wait(&emu::warp_barrier[warp]);
     return m;
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emu::warp_barrier[threadIdx.x >> 5]); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int atomicMax(int* a, int v) { int old = __atomic_load_n(a, __ATOMIC_RELAXED); while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {} return old; }
 static inline uint32_t atomicOr(uint32_t* a, uint32_t v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

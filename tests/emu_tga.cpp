@@ -24,3 +24,21 @@ extern "C" int emu_tga_load(const uint8_t* data, size_t len, uint8_t* out, size_
     *w = P.w; *h = P.h; *comp = P.components;
     return 1;
 }
+
+// ---- encoder: the launches of gb::tga_encode_device (tga.cu) -------------------------------------------------------------
+#include "../gamut_b200/csrc/tga_encode.cuh"
+
+extern "C" int emu_tga_encode(const uint8_t* pixels, int type, int width, int height, int pitch, uint8_t* out, size_t out_cap)
+{
+    TeImage T; uint32_t total_rows = 0;
+    if (te_bound(type, width, height) > out_cap) return -1;
+    if (!te_setup(T, pixels, type, width, height, pitch, out, total_rows)) return 0;
+    std::vector<uint32_t> bytes((size_t)total_rows + 1, 0xdeadbeefu), off((size_t)total_rows + 1, 0xdeadbeefu);
+    int len = -1;
+    const TeImage* dI = &T; uint32_t* dB = bytes.data(); uint32_t* dO = off.data(); int* dl = &len;
+    const dim3 grid((unsigned)T.h, 1);
+    emu::launch(grid, 32, [&] { te_row_kernel<false>(dI, dB, dO); });
+    emu::launch(dim3(1), 256, [&] { te_scan_kernel(dI, dB, dO, dl); });
+    emu::launch(grid, 32, [&] { te_row_kernel<true>(dI, dB, dO); });
+    return len;
+}

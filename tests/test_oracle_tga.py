@@ -98,3 +98,19 @@ def test_overrun_truncation_and_rejects(oracle):
     bad = bytearray(pal); bad[5] = bad[6] = 0; assert oracle.tga_load(bytes(bad)) is None    # empty palette
     bad = bytearray(pal); bad[7] = 12; assert oracle.tga_load(bytes(bad)) is None            # palette entry bits
     bad = bytearray(pal); bad[16] = 24; assert oracle.tga_load(bytes(bad)) is None           # index bits
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_encoder_read_back_by_pil(oracle, c):
+    """or_tga_encode (codecs/tga.d:62-292): PIL's independent reader and the oracle's decoder read the file back to the
+    image (l8 is written as a 24-bit file, :91-94); structure checks on the header saveTGA writes (:120-131)."""
+    rng = np.random.default_rng(c)
+    img = (rng.integers(0, 3, (17, 300, c)) * 100).astype(np.uint8)
+    img[5] = 7
+    img[6, :200] = 9
+    f = oracle.tga_encode(img)
+    rgb = img if c >= 3 else np.repeat(img, 3, axis=2)
+    assert np.array_equal(np.asarray(pil_read(f)), rgb) and np.array_equal(oracle.tga_load(f), rgb)
+    assert f[2] == 10 and f[12] | f[13] << 8 == 300 and f[14] | f[15] << 8 == 17 and f[16] == (24 if c != 4 else 32) and f[17] == 0
+    assert len(f) < 18 + img.size * (3 if c == 1 else 1)         # the run-length coding is on
+    assert oracle.tga_encode(img, type_=13) is None and oracle.tga_encode(img, shape=(17, 70000, c)) is None

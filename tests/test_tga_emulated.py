@@ -75,3 +75,62 @@ def test_pil_files_overrun_and_rejects(emu, oracle):
             bad[int(rng.integers(0, 18))] = int(rng.integers(0, 256))
         bad[12:16] = (5).to_bytes(2, "little") + (4).to_bytes(2, "little")      # keep the size small
         assert same(emu_load(emu, bytes(bad)), oracle.tga_load(bytes(bad)))
+
+
+# ---- encoder (tga_encode.cuh) ------------------------------------------------------------------------------------------
+def emu_encode(L, img, pitch=None, first_scanline=0, shape=None):
+    px = np.ascontiguousarray(img)
+    h, w, c = shape if shape is not None else px.shape
+    t = {1: 0, 2: 3, 3: 9, 4: 12}[c]
+    out = np.full(18 + h * (w * 5 + 2) + 64, 0xEE, np.uint8)
+    L.emu_tga_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    n = L.emu_tga_encode(px.ctypes.data + first_scanline, t, w, h, pitch if pitch is not None else w * c, out.ctypes.data, out.size)
+    assert n >= 0
+    if n == 0:
+        return None
+    assert (out[n:] == 0xEE).all()
+    return out[:n].tobytes()
+
+
+def tga_encode_images(c, rng):
+    """Images that exercise the packet choice: noise (raw packets of 128), flat (runs of 128), runs and raw stretches of
+    every length around 1 / 2 / 127 / 128 / 129, rows that end inside a run or a raw stretch, width 1."""
+    imgs = [rng.integers(0, 256, (5, 300, c)).astype(np.uint8), np.full((4, 300, c), 9, np.uint8), np.zeros((3, 1, c), np.uint8)]
+    imgs.append((rng.integers(0, 3, (17, 300, c)) * 100).astype(np.uint8))
+    rows = []
+    for seed in range(24):
+        row = []
+        while len(row) < 400:
+            n = int(rng.choice([1, 1, 2, 3, 126, 127, 128, 129, 130, 255, 256, 257, 5]))
+            if rng.random() < 0.5:
+                row += [rng.integers(0, 256, c)] * n                                # a run
+            else:
+                row += list(rng.integers(0, 256, (n, c)))                           # a stretch of (mostly) different pixels
+        rows.append(np.array(row[:400 - seed % 3], np.uint8))
+    for k in range(3):
+        imgs.append(np.stack([r[:397] for r in rows[k::3]]))
+    return imgs
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+def test_encoder_files_equal_the_oracle(emu, oracle, c):
+    rng = np.random.default_rng(20 + c)
+    for img in tga_encode_images(c, rng):
+        exp = oracle.tga_encode(img)
+        got = emu_encode(emu, img)
+        assert exp is not None and got == exp
+        dec = oracle.tga_load(got)                                # and the file decodes back to the image (as rgb8 / rgba8)
+        rgb = img if c >= 3 else np.concatenate([np.repeat(img[..., :1], 3, axis=2), img[..., 1:]], axis=2)
+        assert np.array_equal(dec, rgb)
+
+
+def test_encoder_pitch_and_flip(emu, oracle):
+    rng = np.random.default_rng(4)
+    img = (rng.integers(0, 3, (21, 45, 4)) * 90).astype(np.uint8)
+    exp = oracle.tga_encode(img)
+    wide = rng.integers(0, 256, (21, 60, 4)).astype(np.uint8)
+    wide[:, :45] = img
+    assert emu_encode(emu, wide, pitch=240, shape=(21, 45, 4)) == exp
+    flipped = np.ascontiguousarray(wide[::-1])
+    assert emu_encode(emu, flipped, pitch=-240, first_scanline=20 * 240, shape=(21, 45, 4)) == exp
+    assert oracle.tga_encode(flipped, pitch=-240, first_scanline=20 * 240, shape=(21, 45, 4)) == exp

@@ -108,3 +108,72 @@ def test_image_load(codecs, oracle):
     data, _ = make_tga(45, 31, "bgr24", rng)
     im.loadFromMemory(data[:-5])
     assert im.isError() and im.errorMessage() == kStrImageDecodingFailed
+
+
+# ---- encoder: saveTGA (plugins/tga.d:123-149) -> TGAEncoder (codecs/tga.d:62-292) ---------------------------------------
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+def test_encoder_files_equal_the_oracle(codecs, oracle, c):
+    from test_tga_emulated import tga_encode_images
+    rng = np.random.default_rng(20 + c)
+    imgs = tga_encode_images(c, rng)
+    big = np.zeros((1080, 1920, c), np.uint8)
+    big[..., 0] = np.linspace(0, 255, 1920)[None, :].astype(np.uint8)
+    big[200:500, 300:900] = rng.integers(0, 256, (300, 600, c))
+    imgs.append(big)
+    for img in imgs:
+        exp = oracle.tga_encode(img)
+        got = codecs.tga_encode(img)
+        assert exp is not None and got is not None and len(got) == len(exp) and got == exp
+        rgb = img if c >= 3 else np.concatenate([np.repeat(img[..., :1], 3, axis=2), img[..., 1:]], axis=2)
+        assert np.array_equal(codecs.tga_load(got), rgb)          # both decoders read it back
+        assert np.array_equal(oracle.tga_load(got), rgb)
+
+
+def test_encoder_pitch_flip_batch_and_rejects(codecs, oracle):
+    import torch
+    rng = np.random.default_rng(4)
+    img = (rng.integers(0, 3, (21, 45, 4)) * 90).astype(np.uint8)
+    exp = oracle.tga_encode(img)
+    wide = rng.integers(0, 256, (21, 60, 4)).astype(np.uint8)
+    wide[:, :45] = img
+    assert codecs.tga_encode(wide, pitch=240, shape=(21, 45, 4)) == exp
+    flipped = np.ascontiguousarray(wide[::-1])
+    assert codecs.tga_encode(flipped, pitch=-240, first_scanline=20 * 240, shape=(21, 45, 4)) == exp
+    # saveTGA's refusals: pixel types other than l8 / la8 / rgb8 / rgba8; and a pitch smaller than a scanline
+    assert codecs.tga_encode(img, type_=13) is None and codecs.tga_encode(img, type_=1) is None
+    assert codecs.tga_encode(img, pitch=100) is None
+    assert codecs.tga_encode(np.zeros((0, 5, 3), np.uint8) if False else img[:0], shape=(0, 45, 4)) == oracle.tga_encode(img, shape=(0, 45, 4))
+    # one device batch of mixed types; a refused image in the middle does not disturb its neighbours
+    imgs = [(rng.integers(0, 3, (300, 500, 3)) * 100).astype(np.uint8), rng.integers(0, 256, (64, 64, 1)).astype(np.uint8),
+            (rng.integers(0, 2, (512, 512, 4)) * 255).astype(np.uint8)]
+    exps = [oracle.tga_encode(i) for i in imgs]
+    dev = [torch.from_numpy(i).cuda() for i in imgs]
+    outs = [torch.empty(codecs.tga_encode_bound(i.shape[1], i.shape[0], i.shape[2]), dtype=torch.uint8, device="cuda") for i in imgs]
+    lens = codecs.tga_encode_batch_device([t.data_ptr() for t in dev], [i.shape for i in imgs], [o.data_ptr() for o in outs])
+    torch.cuda.synchronize()
+    for o, k, e in zip(outs, lens, exps):
+        assert k == len(e) and o[:k].cpu().numpy().tobytes() == e
+    lens = codecs.tga_encode_batch_device([t.data_ptr() for t in dev], [imgs[0].shape, (64, 64, 5), imgs[2].shape], [o.data_ptr() for o in outs])
+    assert lens[1] == 0 and lens[0] == len(exps[0]) and lens[2] == len(exps[2])
+
+
+def test_image_save_tga(codecs, oracle):
+    """Image.saveToMemory(TGA): load a TGA into several layouts, save it again: the file saveTGA writes for those pixels."""
+    from gamut_b200.image import Image
+    from gamut_b200.types import ImageFormat, LAYOUT_VERT_FLIPPED, LAYOUT_SCANLINE_ALIGNED_16, LAYOUT_BORDER_2, LOAD_16BIT
+    rng = np.random.default_rng(8)
+    for c in (1, 2, 3, 4):
+        img = (rng.integers(0, 3, (37, 61, c)) * 100).astype(np.uint8)
+        kind = {1: "l8", 2: "la16", 3: "bgr24", 4: "bgra32"}[c]
+        exp = oracle.tga_encode(img)
+        src = pil_tga(img, True) if c != 2 else None
+        if src is None:                                          # PIL cannot write grey + alpha: a raw hand-made file
+            from tgautil import header
+            src = header(0, 0, 3, 0, 0, 0, 61, 37, 16, 0x20) + img.tobytes()
+        for layout in (0, LAYOUT_VERT_FLIPPED, LAYOUT_SCANLINE_ALIGNED_16 | LAYOUT_BORDER_2):
+            im = Image()
+            assert im.loadFromMemory(src, layout) and im.width() == 61
+            assert im.saveToMemory(ImageFormat.TGA) == exp
+    im = Image()
+    assert im.loadFromMemory(pil_tga((rng.integers(0, 3, (8, 8, 3)) * 100).astype(np.uint8)), LOAD_16BIT)
+    assert im.saveToMemory(ImageFormat.TGA) is None              # rgb16: unsupported by TGAEncoder.initialize

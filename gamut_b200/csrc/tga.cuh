@@ -149,22 +149,41 @@ tga_raw_kernel(const TgaJob* __restrict__ jobs, int njobs, uint32_t total)
 
 // ---- T2: run-length packets (:468-486, :535), one warp per image: the packet chain is walked by the whole warp, the
 // pixels of a packet (at most 128) are placed by its lanes. A packet may cross rows; one that runs past the last pixel
-// is cut; a read past the end of the file fails the image.
+// is cut; a read past the end of the file fails the image. The chain is serial (a packet header says where the next one
+// is), so its cost is the latency of one header read per packet: the stream is staged through an 8 KB window in shared
+// memory (refilled with coalesced word loads whenever the next packet might not fit), which makes that read a shared-
+// memory access instead of a dependent global load.
+constexpr uint32_t TGA_WIN = 8192, TGA_PACKET_MAX = 1 + 128 * 4;
+
 __global__ void __launch_bounds__(32)
 tga_rle_kernel(const TgaJob* __restrict__ jobs)
 {
+    __shared__ __align__(16) uint8_t s_win[TGA_WIN];
     const TgaJob& J = jobs[blockIdx.x];
     const uint32_t total = (uint32_t)J.w * (uint32_t)J.h, lane = threadIdx.x;
     uint32_t pos = J.pix_off, i = 0;
+    uint32_t win_start = 0, win_end = 0;                          // file offsets held in s_win
     while (i < total) {
+        if (pos + TGA_PACKET_MAX > win_end && win_end < J.len) {
+            // refill from a 4-byte aligned address at or below pos (pos >= 18, so this never reaches before the file)
+            __syncwarp();
+            win_start = pos - (uint32_t)((uintptr_t)(J.data + pos) & 3u);
+            win_end = min(win_start + TGA_WIN, J.len);
+            const uint32_t nbytes = win_end - win_start, nwords = nbytes >> 2;
+            const uint32_t* src = (const uint32_t*)(J.data + win_start);
+            for (uint32_t k = lane; k < nwords; k += 32u) ((uint32_t*)s_win)[k] = src[k];
+            for (uint32_t k = (nwords << 2) + lane; k < nbytes; k += 32u) s_win[k] = J.data[win_start + k];
+            __syncwarp();
+        }
         if (pos + 1u > J.len) { if (lane == 0) *J.fail = 1; return; }
-        const uint32_t cmd = J.data[pos];
+        const uint32_t cmd = s_win[pos - win_start];
         const uint32_t count = 1u + (cmd & 127u), rep = cmd >> 7;
         const uint32_t n = min(count, total - i);
         const uint32_t need = rep ? (uint32_t)J.src_bytes : n * (uint32_t)J.src_bytes;
         if ((unsigned long long)pos + 1u + need > J.len) { if (lane == 0) *J.fail = 1; return; }
+        const uint8_t* pk = s_win + (pos - win_start) + 1u;
         for (uint32_t k = lane; k < n; k += 32u)
-            tga_pixel(J, J.data + pos + 1u + (rep ? 0u : k * (uint32_t)J.src_bytes), tga_dest(J, i + k));
+            tga_pixel(J, pk + (rep ? 0u : k * (uint32_t)J.src_bytes), tga_dest(J, i + k));
         pos += 1u + (rep ? (uint32_t)J.src_bytes : count * (uint32_t)J.src_bytes);
         i += n;
     }

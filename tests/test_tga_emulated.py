@@ -134,3 +134,24 @@ def test_encoder_pitch_and_flip(emu, oracle):
     flipped = np.ascontiguousarray(wide[::-1])
     assert emu_encode(emu, flipped, pitch=-240, first_scanline=20 * 240, shape=(21, 45, 4)) == exp
     assert oracle.tga_encode(flipped, pitch=-240, first_scanline=20 * 240, shape=(21, 45, 4)) == exp
+
+
+def test_rle_stream_longer_than_the_staging_window(emu, oracle):
+    """Run-length files several times the 8 KB window of tga_rle_kernel, at every byte alignment of the file start."""
+    rng = np.random.default_rng(12)
+    for kind, kw in [("bgra32", {}), ("bgr24", {"idlen": 5}), ("pal16", {"pal_len": 300, "index_bits": 16}), ("l8", {})]:
+        data, _ = make_tga(300, 90, kind, rng, rle=True, **kw)
+        assert len(data) > 20000 or kind in ("l8",)
+        exp = oracle.tga_load(data)
+        for shift in range(4):
+            buf = np.zeros(len(data) + 8, np.uint8)
+            o = (-buf.ctypes.data) % 4 + shift
+            buf[o:o + len(data)] = np.frombuffer(data, np.uint8)
+            out = np.full(1 << 20, 0xEE, np.uint8)
+            w, h, c = C.c_int(), C.c_int(), C.c_int()
+            emu.emu_tga_load.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
+            assert emu.emu_tga_load(buf.ctypes.data + o, len(data), out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(c)) == 1
+            assert np.array_equal(out[: exp.size].reshape(exp.shape), exp)
+        emu.emu_tga_load.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
+        for cut in (len(data) - 1, len(data) - 600, 8192 + 18, 9000):
+            assert same(emu_load(emu, data[:cut]), oracle.tga_load(data[:cut]))

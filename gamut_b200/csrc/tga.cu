@@ -4,9 +4,9 @@
 // grey + alpha, 15/16-bit and 24/32-bit colour, colour-mapped files with 8- or 16-bit indices and 8/15/16/24/32-bit
 // palette entries, each raw or run-length coded, bottom-up or top-down. The host walks the header and prepares the
 // palette in output channel order (tga.cuh: tga_plan); the device does the per-pixel work: files without packets are
-// one thread per pixel over the whole batch (tga_raw_kernel); run-length files are one warp per image, the packet
-// chain walked by the warp and the pixels of a packet placed by its lanes (tga_rle_kernel) -- the chain is serial by
-// the format (a packet header says where the next one is), so this half is a parity path, not a fast one.
+// one thread per pixel over the whole batch (tga_raw_kernel); run-length files take two passes: one warp per image walks
+// the packet headers only and leaves a checkpoint every 256 packets (the chain is serial by the format: a packet header
+// says where the next one is), then one warp per checkpoint places the pixels of its 256 packets (tga_rle_kernel).
 // The row flip (:537-551) and the B/R swap (:553-565) are folded into the store / the palette.
 // The encoder (saveTGA, plugins/tga.d:123-149 -> TGAEncoder, codecs/tga.d:62-292) is at the end of the file; its kernels
 // and their description are in tga_encode.cuh.
@@ -63,7 +63,7 @@ gb200_batch* tga_decode_batch(int n, const uint8_t* const* files, const size_t* 
     // the table holds the files without packets first (one flat launch over their pixels), then the run-length files
     std::vector<TgaJob> jobs; std::vector<int> which;
     std::vector<HostCopy> hcopies;
-    uint32_t raw_pixels = 0; int nraw = 0;
+    uint32_t raw_pixels = 0, ck_total = 0, most_segs = 0; int nraw = 0;
     for (int pass = 0; pass < 2; ++pass)
         for (int i : live) {
             const TgaPlan& p = P[i];
@@ -81,9 +81,12 @@ gb200_batch* tga_decode_batch(int n, const uint8_t* const* files, const size_t* 
             J.w = p.w; J.h = p.h; J.components = p.components; J.src_bytes = p.src_bytes; J.mode = p.mode; J.index16 = p.index16;
             J.inverted = p.inverted; J.rle = p.rle;
             if (!p.rle) { J.pix_base = raw_pixels; raw_pixels += (uint32_t)p.w * (uint32_t)p.h; ++nraw; }
+            else { const uint32_t ms = tga_max_segments((uint32_t)p.w * (uint32_t)p.h); J.ck_base = ck_total; ck_total += ms; most_segs = std::max(most_segs, ms); }
             jobs.push_back(J); which.push_back(i);
         }
     host_copy_parallel(hcopies.data(), hcopies.size());
+    DevBuf d_ck(sizeof(TgaCheckpoint) * ((size_t)ck_total + 1)), d_nseg(4 * (size_t)(m - nraw + 1));
+    if (!d_ck.p || !d_nseg.p) { delete B; return nullptr; }
     cudaEvent_t ev[3];
     for (auto& e : ev) cudaEventCreate(&e);
     bool okc = true;
@@ -94,7 +97,13 @@ gb200_batch* tga_decode_batch(int n, const uint8_t* const* files, const size_t* 
     cudaEventRecord(ev[1], st);
     if (okc) {
         if (nraw) { tga_raw_kernel<<<(raw_pixels + 255) / 256, 256, 0, st>>>(d_jobs.as<TgaJob>(), nraw, raw_pixels); count_launch(); }
-        if (m > nraw) { tga_rle_kernel<<<m - nraw, 32, 0, st>>>(d_jobs.as<TgaJob>() + nraw); count_launch(); }
+        for (int k0 = nraw; k0 < m; k0 += 65535) {              // grid.y is limited to 65535
+            const int mk = std::min(65535, m - k0);
+            const TgaJob* dj = d_jobs.as<TgaJob>() + k0; uint32_t* dn = d_nseg.as<uint32_t>() + (k0 - nraw);
+            tga_rle_index_kernel<<<mk, 32, 0, st>>>(dj, d_ck.as<TgaCheckpoint>(), dn);
+            tga_rle_kernel<<<dim3(most_segs, (unsigned)mk), 32, 0, st>>>(dj, d_ck.as<TgaCheckpoint>(), dn);
+            count_launch(2);
+        }
         okc = dev_read_back_async(h_fail.p, d_fail.p, sizeof(int) * (size_t)m, st);
     }
     cudaEventRecord(ev[2], st);

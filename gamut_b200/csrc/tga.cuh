@@ -21,6 +21,7 @@ struct TgaJob {
     int* fail;                  // set to 1 when a read of the packet walk fails
     uint32_t len, pix_off;      // file length; offset of the first pixel / packet
     uint32_t palette_len, pix_base;
+    uint32_t ck_base;            // first checkpoint of this image (run-length files)
     int w, h, components, src_bytes, mode, index16, inverted, rle;
 };
 
@@ -147,40 +148,74 @@ tga_raw_kernel(const TgaJob* __restrict__ jobs, int njobs, uint32_t total)
     tga_pixel(J, J.data + J.pix_off + (size_t)i * J.src_bytes, tga_dest(J, i));
 }
 
-// ---- T2: run-length packets (:468-486, :535), one warp per image: the packet chain is walked by the whole warp, the
-// pixels of a packet (at most 128) are placed by its lanes. A packet may cross rows; one that runs past the last pixel
-// is cut; a read past the end of the file fails the image. The chain is serial (a packet header says where the next one
-// is), so its cost is the latency of one header read per packet: the stream is staged through an 8 KB window in shared
-// memory (refilled with coalesced word loads whenever the next packet might not fit), which makes that read a shared-
-// memory access instead of a dependent global load.
-constexpr uint32_t TGA_WIN = 8192, TGA_PACKET_MAX = 1 + 128 * 4;
+// ---- T2 / T3: run-length packets (:468-486, :535). The packet chain is serial by the format (a packet header says
+// where the next one is) and a packet may cross rows, so nothing tells where a row starts. Two passes:
+//   T2 tga_rle_index_kernel: one warp per image walks the headers only -- no pixel is touched -- and writes a checkpoint
+//      (file offset, pixel index) every TGA_SEG packets; a read past the end of the file fails the image here.
+//   T3 tga_rle_kernel: one warp per checkpoint walks its TGA_SEG packets and its lanes place the pixels (at most 128 per
+//      packet): thousands of independent warps per image instead of one.
+// Both stage the stream through an 8 KB window in shared memory (coalesced word loads), so a header read is a shared-
+// memory access, not a dependent global load. A packet that runs past the last pixel is cut (:463, :535).
+constexpr uint32_t TGA_WIN = 8192, TGA_PACKET_MAX = 1 + 128 * 4, TGA_SEG = 256;
+
+struct TgaCheckpoint { uint32_t pos, pixel; };
+// checkpoints of job j: ck[J.ck_base .. J.ck_base + tga_max_segments(J)); the number in use is nseg[j]
+__host__ __device__ inline uint32_t tga_max_segments(uint32_t total_pixels) { return total_pixels / TGA_SEG + 1u; }   // a packet holds >= 1 pixel
+
+__device__ __forceinline__ void tga_refill(const TgaJob& J, uint8_t* s_win, uint32_t pos, uint32_t& win_start, uint32_t& win_end, uint32_t lane)
+{
+    // from a 4-byte aligned address at or below pos (pos >= 18, so this never reaches before the file)
+    __syncwarp();
+    win_start = pos - (uint32_t)((uintptr_t)(J.data + pos) & 3u);
+    win_end = min(win_start + TGA_WIN, J.len);
+    const uint32_t nbytes = win_end - win_start, nwords = nbytes >> 2;
+    const uint32_t* src = (const uint32_t*)(J.data + win_start);
+    for (uint32_t k = lane; k < nwords; k += 32u) ((uint32_t*)s_win)[k] = src[k];
+    for (uint32_t k = (nwords << 2) + lane; k < nbytes; k += 32u) s_win[k] = J.data[win_start + k];
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(32)
-tga_rle_kernel(const TgaJob* __restrict__ jobs)
+tga_rle_index_kernel(const TgaJob* __restrict__ jobs, TgaCheckpoint* __restrict__ ck, uint32_t* __restrict__ nseg)
 {
     __shared__ __align__(16) uint8_t s_win[TGA_WIN];
     const TgaJob& J = jobs[blockIdx.x];
     const uint32_t total = (uint32_t)J.w * (uint32_t)J.h, lane = threadIdx.x;
-    uint32_t pos = J.pix_off, i = 0;
+    TgaCheckpoint* C = ck + J.ck_base;
+    uint32_t pos = J.pix_off, i = 0, packets = 0, segs = 0;
     uint32_t win_start = 0, win_end = 0;                          // file offsets held in s_win
-    while (i < total) {
-        if (pos + TGA_PACKET_MAX > win_end && win_end < J.len) {
-            // refill from a 4-byte aligned address at or below pos (pos >= 18, so this never reaches before the file)
-            __syncwarp();
-            win_start = pos - (uint32_t)((uintptr_t)(J.data + pos) & 3u);
-            win_end = min(win_start + TGA_WIN, J.len);
-            const uint32_t nbytes = win_end - win_start, nwords = nbytes >> 2;
-            const uint32_t* src = (const uint32_t*)(J.data + win_start);
-            for (uint32_t k = lane; k < nwords; k += 32u) ((uint32_t*)s_win)[k] = src[k];
-            for (uint32_t k = (nwords << 2) + lane; k < nbytes; k += 32u) s_win[k] = J.data[win_start + k];
-            __syncwarp();
-        }
-        if (pos + 1u > J.len) { if (lane == 0) *J.fail = 1; return; }
+    while (i < total) {                                           // every lane walks the same chain
+        if (pos + 2u > win_end && win_end < J.len) tga_refill(J, s_win, pos, win_start, win_end, lane);
+        if ((packets & (TGA_SEG - 1u)) == 0u) { if (lane == 0) { C[segs].pos = pos; C[segs].pixel = i; } ++segs; }
+        if (pos + 1u > J.len) { if (lane == 0) *J.fail = 1; break; }
         const uint32_t cmd = s_win[pos - win_start];
         const uint32_t count = 1u + (cmd & 127u), rep = cmd >> 7;
         const uint32_t n = min(count, total - i);
         const uint32_t need = rep ? (uint32_t)J.src_bytes : n * (uint32_t)J.src_bytes;
-        if ((unsigned long long)pos + 1u + need > J.len) { if (lane == 0) *J.fail = 1; return; }
+        if ((unsigned long long)pos + 1u + need > J.len) { if (lane == 0) *J.fail = 1; break; }
+        pos += 1u + (rep ? (uint32_t)J.src_bytes : count * (uint32_t)J.src_bytes);
+        i += n;
+        ++packets;
+    }
+    if (lane == 0) nseg[blockIdx.x] = segs;
+}
+
+// grid = (most segments of an image, images); the jobs' fail flags are already final (same stream, after T2)
+__global__ void __launch_bounds__(32)
+tga_rle_kernel(const TgaJob* __restrict__ jobs, const TgaCheckpoint* __restrict__ ck, const uint32_t* __restrict__ nseg)
+{
+    __shared__ __align__(16) uint8_t s_win[TGA_WIN];
+    const TgaJob& J = jobs[blockIdx.y];
+    if (blockIdx.x >= nseg[blockIdx.y] || *J.fail) return;
+    const uint32_t total = (uint32_t)J.w * (uint32_t)J.h, lane = threadIdx.x;
+    const TgaCheckpoint c = ck[J.ck_base + blockIdx.x];
+    uint32_t pos = c.pos, i = c.pixel;
+    uint32_t win_start = 0, win_end = 0;
+    for (uint32_t packets = 0; packets < TGA_SEG && i < total; ++packets) {
+        if (pos + TGA_PACKET_MAX > win_end && win_end < J.len) tga_refill(J, s_win, pos, win_start, win_end, lane);
+        const uint32_t cmd = s_win[pos - win_start];              // T2 has checked every read of this walk
+        const uint32_t count = 1u + (cmd & 127u), rep = cmd >> 7;
+        const uint32_t n = min(count, total - i);
         const uint8_t* pk = s_win + (pos - win_start) + 1u;
         for (uint32_t k = lane; k < n; k += 32u)
             tga_pixel(J, pk + (rep ? 0u : k * (uint32_t)J.src_bytes), tga_dest(J, i + k));

@@ -19,7 +19,15 @@ extern "C" int emu_tga_load(const uint8_t* data, size_t len, uint8_t* out, size_
     const TgaJob* dj = &J;
     const uint32_t total = (uint32_t)P.w * (uint32_t)P.h;
     if (!P.rle) emu::launch(dim3((total + 255) / 256), 256, [&] { tga_raw_kernel(dj, 1, total); });
-    else emu::launch(dim3(1), 32, [&] { tga_rle_kernel(dj); });
+    else {
+        const uint32_t ms = tga_max_segments(total);
+        std::vector<TgaCheckpoint> ck((size_t)ms + 1, TgaCheckpoint{0xdeadbeefu, 0xdeadbeefu});
+        uint32_t nseg = 0xdeadbeefu;
+        TgaCheckpoint* dc = ck.data(); uint32_t* dn = &nseg;
+        emu::launch(dim3(1), 32, [&] { tga_rle_index_kernel(dj, dc, dn); });
+        if (!fail && nseg > ms) return -2;
+        emu::launch(dim3(ms, 1), 32, [&] { tga_rle_kernel(dj, dc, dn); });
+    }
     if (fail) return 0;
     *w = P.w; *h = P.h; *comp = P.components;
     return 1;

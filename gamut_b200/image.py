@@ -34,6 +34,30 @@ kStrInvalidFlags = "Invalid image decoding flags"
 kStrOutOfMemory = "Out of memory"
 kStrUnsupportedTypeConversion = "Unsupported image pixel type conversion"
 kStrImageNotInitialized = "Uninitialized image"
+kStrCannotOpenFile = "Cannot open file"                      # internals/errors.d:14
+kStrFileCloseFailed = "fclose() failed"                      # internals/errors.d:15
+
+# extensionList of the ten plugins in ImageFormat order (plugins/*.d, the `p.extensionList = ...` lines)
+_EXTENSIONS = (("jpg", "jpeg", "jif", "jfif"), ("png",), ("qoi",), ("qoix",), ("dds",), ("tga",), ("gif",), ("bmp", "dib"),
+               ("jxl",), ("sqz",))
+
+
+def identifyImageFormatFromFilename(filename) -> "ImageFormat":
+    """plugin.d:55-97: the text after the last '.' of the whole path (the whole path when it has none), compared case-
+    sensitively with each plugin's extension list in ImageFormat order."""
+    if filename is None:
+        return ImageFormat.unknown
+    name = filename if isinstance(filename, str) else bytes(filename).decode("utf-8", "surrogateescape")
+    pos = len(name)
+    while pos > 0 and (pos == len(name) or name[pos] != "."):
+        pos -= 1
+    if pos < len(name) and name[pos] == ".":
+        pos += 1
+    ext = name[pos:]
+    for fif, exts in enumerate(_EXTENSIONS):
+        if ext in exts:
+            return ImageFormat(fif)
+    return ImageFormat.unknown
 
 GAMUT_MAX_IMAGE_BYTES = 0x7FFFFFFF  # internals/types.d: a gamut image allocation is bounded by int.max
 LAYOUT_BORDER_MASK = 384
@@ -255,6 +279,88 @@ class Image:
     @staticmethod
     def identifyFormatFromMemory(data: bytes) -> ImageFormat:
         return ImageFormat(codecs.identify_format(bytes(data)))
+
+    # -- file / stream front end (image.d:859-1068, 1730-1790; io.d). The reference reads through an IOStream; here the
+    #    bytes of the file or of a Python binary stream are handed to the memory path. What the front end itself decides
+    #    is restated: content detection first and the file name's extension only when the content is not recognised
+    #    (image.d:866-870), "Cannot open file", no load support, and -- for saving -- the format from the extension.
+    @staticmethod
+    def identifyFormatFromFile(path) -> ImageFormat:             # image.d:1026-1037
+        try:
+            with open(path, "rb") as f:
+                data = f.read()
+        except OSError:
+            return ImageFormat.unknown
+        return Image.identifyFormatFromMemory(data)
+
+    @staticmethod
+    def identifyFormatFromFileName(path) -> ImageFormat:         # image.d:1066-1069
+        return identifyImageFormatFromFilename(path)
+
+    @staticmethod
+    def identifyFormatFromStream(stream) -> ImageFormat:         # image.d:1045-1061; the cursor is restored like the detect procs do
+        at = stream.tell()
+        data = stream.read()
+        stream.seek(at)
+        return Image.identifyFormatFromMemory(data)
+
+    def _loadAs(self, fif, data: bytes, flags: int) -> bool:
+        """loadFromStreamInternal (image.d:1751-1772) with the format already chosen."""
+        self.__init__()
+        self._error = None
+        if fif == ImageFormat.unknown:
+            self.error(kStrImageFormatUnidentified)
+            return False
+        if fif == self.identifyFormatFromMemory(data):
+            return self.loadFromMemory(data, flags)              # the one-call GPU path decides the same format itself
+        # the extension named a format the content does not look like: that plugin's loader still runs on the bytes
+        loaders = {ImageFormat.PNG: self._loadPNG, ImageFormat.JPEG: self._loadJPEG, ImageFormat.QOI: self._loadQOI,
+                   ImageFormat.QOIX: self._loadQOIX, ImageFormat.BMP: self._loadBMP, ImageFormat.TGA: self._loadTGA}
+        if fif not in loaders:
+            self.error(kStrImageFormatNoLoadSupport)
+            return False
+        loaders[fif](data, flags)
+        return self.isValid()
+
+    def loadFromFile(self, path, flags: int = 0) -> bool:         # image.d:859-873 + loadFromFileInternal (:1730-1749)
+        self.__init__()
+        fif = self.identifyFormatFromFile(path)
+        if fif == ImageFormat.unknown:
+            fif = identifyImageFormatFromFilename(path)
+        try:
+            with open(path, "rb") as f:
+                data = f.read()
+        except OSError:
+            self.error(kStrCannotOpenFile)
+            return False
+        return self._loadAs(fif, data, flags)
+
+    def loadFromStream(self, stream, flags: int = 0) -> bool:     # image.d:916-924: a binary file-like object, read from its cursor
+        self.__init__()
+        fif = self.identifyFormatFromStream(stream)
+        return self._loadAs(fif, stream.read(), flags)
+
+    def saveToStream(self, fif, stream, flags: int = 0) -> bool:  # image.d:992-1016
+        if fif == ImageFormat.unknown or not self.hasData():
+            return False
+        data = self.saveToMemory(fif, flags)
+        if data is None:                                          # no saveProc in this build, or the plugin refused the image
+            return False
+        return stream.write(data) == len(data)
+
+    def saveToFile(self, path_or_fif, path=None, flags: int = 0) -> bool:
+        """saveToFile(path, flags) (image.d:935-942: format from the extension) and saveToFile(fif, path, flags)
+        (:953-958) -> saveToFileInternal (:1774-1786)."""
+        if path is None:
+            path, fif = path_or_fif, identifyImageFormatFromFilename(path_or_fif)
+        else:
+            fif = ImageFormat(int(path_or_fif))
+        try:
+            f = open(path, "wb")
+        except OSError:
+            return False
+        with f:
+            return self.saveToStream(fif, f, flags)
 
     def _adopt(self, px: np.ndarray, type_, pitch: int, layout: int, par: float, resY: float):
         a = np.ascontiguousarray(px).view(np.uint8).reshape(-1)

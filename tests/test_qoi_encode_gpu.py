@@ -139,3 +139,28 @@ def test_image_save_qoi(codecs, oracle):
     im2 = Image()
     assert im2.loadFromMemory(oracle.qoi_encode(qoi_test_image(8, 8, 4, 1)), LOAD_16BIT)
     assert im2.saveToMemory(ImageFormat.QOI) is None                # saveQOI takes rgb8 / rgba8 only
+
+
+def test_file_front_end_round_trip(codecs, oracle, tmp_path):
+    """Image.loadFromFile / saveToFile (image.d:859-873, 935-958): a QOI file loaded from disk, saved again by extension
+    and as TGA by format; the content decides the format when the extension disagrees."""
+    from gamut_b200.image import Image
+    from gamut_b200.types import ImageFormat
+    img = qoi_test_image(20, 30, 4, 5)
+    src = oracle.qoi_encode(img)
+    p = tmp_path / "a.qoi"
+    p.write_bytes(src)
+    im = Image()
+    assert im.loadFromFile(str(p)) and im.width() == 30 and im.height() == 20
+    q = tmp_path / "b.qoi"
+    assert im.saveToFile(str(q)) and q.read_bytes() == src
+    t = tmp_path / "c.tga"
+    assert im.saveToFile(ImageFormat.TGA, str(t)) and t.read_bytes() == oracle.tga_encode(img)
+    im2 = Image()
+    assert im2.loadFromFile(str(t)) and np.array_equal(im2.pixels(), img)
+    w = tmp_path / "d.png"
+    w.write_bytes(src)
+    assert im2.loadFromFile(str(w)) and im2.width() == 30 and np.array_equal(im2.pixels(), img)
+    with open(str(p), "rb") as f:
+        im3 = Image()
+        assert im3.loadFromStream(f) and np.array_equal(im3.pixels(), img)

@@ -338,9 +338,9 @@ def qoix_decode(data: bytes, flags: int = 0):
 
 def qoix_encode(pixels: np.ndarray, bitdepth: Optional[int] = None, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0,
                 pitch: Optional[int] = None) -> Optional[bytes]:
-    """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, 1|2) image: uint16 (10-bit values expanded to 16 bits) -> the
-    QOI-Plane10 stream (qoiplane10.d:99), uint8 -> the QOI-Plane stream (qoiplane.d:109); never LZ4-wrapped. None if the
-    encoder refuses the image."""
+    """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, c) image: c = 1|2 uint16 (10-bit values expanded to 16 bits) -> the
+    QOI-Plane10 stream (qoiplane10.d:99), c = 1|2 uint8 -> the QOI-Plane stream (qoiplane.d:109), c = 3|4 uint8 -> the
+    QOI2AVG stream (qoi2avg.d:376); never LZ4-wrapped. None if the encoder refuses the image."""
     h, w, c = pixels.shape
     px = np.ascontiguousarray(pixels)
     if bitdepth is None:

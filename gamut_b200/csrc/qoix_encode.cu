@@ -25,6 +25,13 @@
 #include <vector>
 #include <cstring>
 
+// qoix_encode's own checks (qoi2avg.d:386-398); the kernels are in qoi2avg_encode.cu
+static bool q2_valid_desc(uint32_t width, uint32_t height, int channels, int bitdepth, int colorspace, int compression)
+{
+    return width && height && channels >= 3 && channels <= 4 && colorspace >= 0 && colorspace <= 2 && bitdepth == 8 && compression == 0 &&
+           height < 400000000u / width;
+}
+
 namespace gb {
 
 static bool qe_valid(const gb200_qoix_desc& d) { return ::qe_valid(d.width, d.height, d.channels, d.bitdepth, d.compression); }
@@ -82,6 +89,10 @@ bool qoiplane_encode_device(int n, const uint8_t* const* pixels_dev, const gb200
     return ok;
 }
 
+// qoi2avg_encode.cu: the 3 / 4-channel 8-bit images of a batch (QOI2AVG)
+bool qoi2avg_encode_device(int n, const uint8_t* const* pixels_dev, const gb200_qoix_desc* descs, uint8_t* const* out_dev,
+                           int* out_len, cudaStream_t st);
+
 }  // namespace gb
 
 // worst case of qoiplane10_encode's own allocation (:112-116; qoiplane_encode's, qoiplane.d:125-129, is smaller) rounded
@@ -90,6 +101,7 @@ GB_API size_t gb200_qoix_encode_bound(const gb200_qoix_desc* desc)
 {
     if (!desc) return 0;
     const unsigned long long np = (unsigned long long)desc->width * desc->height;
+    if (desc->channels >= 3) return (size_t)(np * ((unsigned)desc->channels + 1u) + QOIX_HEADER_SIZE + 4 + 16);     // qoix_encode's own (qoi2avg.d:408)
     return (size_t)((np * (desc->channels == 1 ? 14 : 28) + 7) / 8 + QOIX_HEADER_SIZE + 5 + 64);
 }
 
@@ -98,7 +110,10 @@ GB_API int gb200_qoix_encode_batch_device(int n, const uint8_t* const* pixels_de
 {
     gb::clear_error();
     if (n < 0 || !pixels_dev || !descs || !out_dev || !out_len) { gb::set_error("qoix_encode_batch_device: bad arguments"); return 0; }
-    return gb::qoiplane_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream) ? 1 : 0;
+    bool any_rgb = false;
+    for (int i = 0; i < n; ++i) any_rgb |= descs[i].channels >= 3;
+    if (!gb::qoiplane_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream)) return 0;       // 1 / 2 channels; others get 0
+    return !any_rgb || gb::qoi2avg_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream) ? 1 : 0;
 }
 
 // qoix_lz4_encode (plugins/qoix.d:251) for the images it hands to qoiplane10_encode (10-bit, 1 or 2 channels) and to
@@ -108,9 +123,10 @@ GB_API uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* 
 {
     gb::clear_error();
     if (!gb::ensure_device()) return nullptr;
-    if (!pixels || !desc || !out_len || !gb::qe_valid(*desc) ||
+    const bool rgb8 = desc && desc->channels >= 3 && ::q2_valid_desc(desc->width, desc->height, desc->channels, desc->bitdepth, desc->colorspace, desc->compression);
+    if (!pixels || !desc || !out_len || !(rgb8 || gb::qe_valid(*desc)) ||
         desc->pitchBytes < (int)(desc->width * desc->channels * (desc->bitdepth == 10 ? 2u : 1u))) {
-        gb::set_error("qoix_encode: unsupported image (QOI-Plane10 / QOI-Plane take 10-bit / 8-bit images with 1 or 2 channels)");
+        gb::set_error("qoix_encode: unsupported image (built: QOI-Plane10 / QOI-Plane for 10-bit / 8-bit images with 1 or 2 channels, QOI2AVG for 8-bit images with 3 or 4)");
         return nullptr;
     }
     cudaStream_t st = gb::thread_stream();
@@ -120,7 +136,8 @@ GB_API uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* 
     if (!gb::cuda_ok(cudaMemcpyAsync(d_in.p, pixels, in_bytes, cudaMemcpyHostToDevice, st), "qe h2d", __FILE__, __LINE__)) { cudaStreamSynchronize(st); return nullptr; }
     const uint8_t* pin[1] = {d_in.as<uint8_t>()}; uint8_t* pout[1] = {d_out.as<uint8_t>()};
     int len = 0;
-    if (!gb::qoiplane_encode_device(1, pin, desc, pout, &len, st) || len <= 0) { cudaStreamSynchronize(st); return nullptr; }
+    const bool ran = rgb8 ? gb::qoi2avg_encode_device(1, pin, desc, pout, &len, st) : gb::qoiplane_encode_device(1, pin, desc, pout, &len, st);
+    if (!ran || len <= 0) { cudaStreamSynchronize(st); return nullptr; }
     uint8_t* out = (uint8_t*)malloc((size_t)len);
     if (!out) return nullptr;
     const bool ok = gb::cuda_ok(cudaMemcpyAsync(out, d_out.p, (size_t)len, cudaMemcpyDeviceToHost, st), "qe d2h", __FILE__, __LINE__) &&

@@ -515,7 +515,8 @@ class Image:
 
     # -- getAdHocLayoutConstraints (image.d:1809-1905)
     # -- Image.saveToMemory (image.d:966) for the save paths that are built: saveQOIX (plugins/qoix.d:156-241) of a
-    #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode), saveTGA (plugins/tga.d:123-149) of an
+    #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode) or of an 8-bit RGB(A) image (-> qoix_encode,
+    #    QOI2AVG), saveTGA (plugins/tga.d:123-149) of an
     #    l8 / la8 / rgb8 / rgba8 image, and saveQOI (plugins/qoi.d:150-185) of
     #    an rgb8 / rgba8 image. Returns the file bytes or None (the reference returns a null slice when the plugin's
     #    saveProc fails or the format has none).
@@ -545,12 +546,14 @@ class Image:
             channels, bitdepth = (1 if t == PixelType.l16 else 2), 10          # -> qoiplane10_encode (plugins/qoix.d:199-212)
         elif t in (PixelType.l8, PixelType.la8, PixelType.lap8):
             channels, bitdepth = (1 if t == PixelType.l8 else 2), 8            # -> qoiplane_encode (plugins/qoix.d:172-184)
+        elif t in (PixelType.rgb8, PixelType.rgba8, PixelType.rgbap8):
+            channels, bitdepth = (3 if t == PixelType.rgb8 else 4), 8          # -> qoix_encode, QOI2AVG (plugins/qoix.d:185-198)
         else:
-            return None                                    # the RGB sub-encoders (QOI2AVG, QOI-10b) are not built
+            return None                                    # rgb16 / rgba16 / rgbap16 -> qoi10b_encode: not built
         if self._pitch < self._width * pixelTypeSize(t):
             return None                                    # vertically flipped storage: not taken by the C entry point
         d = codecs.QoixDesc(self._width, self._height, self._pitch, channels, bitdepth,
-                            2 if t in (PixelType.lap16, PixelType.lap8) else 0, 0, self._pixelAspectRatio, self._resolutionY)
+                            2 if t in (PixelType.lap16, PixelType.lap8, PixelType.rgbap8) else 0, 0, self._pixelAspectRatio, self._resolutionY)
         n = C.c_int(0)
         p = codecs._L().gb200_qoix_encode(first, C.byref(d), C.byref(n))
         return codecs._take_host(p, n.value).tobytes() if p else None

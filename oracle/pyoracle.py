@@ -69,6 +69,8 @@ def lib():
         L.or_qoix_lz4_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.c_int, C.POINTER(C.c_int)]
         L.or_qoi_encode.restype = C.c_void_p
         L.or_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.or_qoix_encode.restype = C.c_void_p
+        L.or_qoix_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_qoiplane_encode.restype = C.c_void_p
         L.or_qoiplane_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_qoiplane10_encode.restype = C.c_void_p
@@ -195,6 +197,18 @@ def qoi_encode(pixels: np.ndarray, colorspace: int = 0, pitch=None, first_scanli
     h, w, c = shape if shape is not None else px.shape
     n = C.c_int(0)
     p = lib().or_qoi_encode(px.ctypes.data + first_scanline, w, h, pitch if pitch is not None else w * c, c, colorspace, C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value).tobytes()
+
+
+def qoi2avg_encode(pixels: np.ndarray, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0, pitch=None, shape=None):
+    """or_qoix_encode (qoi2avg.d:376-617) of a (h, w, 3|4) uint8 image: the QOI2AVG stream without the LZ4 stage, or None."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    d = QoixDesc(w, h, pitch if pitch is not None else w * c, c, 8, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = lib().or_qoix_encode(px.ctypes.data, C.byref(d), C.byref(n))
     if not p:
         return None
     return _take(p, n.value).tobytes()

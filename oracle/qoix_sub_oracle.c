@@ -418,3 +418,95 @@ uint8_t* or_qoiplane_encode(const uint8_t* data, const or_qoix_desc* desc, int* 
     *out_len = W.p;
     return bytes;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* qoix_encode (qoi2avg.d:376-617): rgb8 / rgba8 rows -> QOI2AVG stream (no LZ4 stage). Restated so that the reference's
+ * round-trip property (image.d:2112-2183) can be replayed for this codec and so that the GPU encoder has a byte-exact
+ * target. pitchBytes must be >= width * channels (the reference memcpy()s pitchBytes bytes of an rgba8 row, :459). */
+static uint32_t q2_hash(uint32_t v) { return ((v * 2654435769u) >> 22) & 1023u; }                    /* :312-315 */
+static uint32_t q2_v(rgba8 p) { return (uint32_t)p.r | (uint32_t)p.g << 8 | (uint32_t)p.b << 16 | (uint32_t)p.a << 24; }
+uint8_t* or_qoix_encode(const uint8_t* data, const or_qoix_desc* desc, int* out_len)
+{
+    if (!data || !out_len || !desc || desc->width == 0 || desc->height == 0 || desc->channels < 3 || desc->channels > 4 ||
+        desc->colorspace > 2 || desc->bitdepth != 8 || desc->compression != 0 || desc->height >= QOIX_PIXELS_MAX / desc->width) return NULL;
+    const int W = (int)desc->width, H = (int)desc->height, channels = desc->channels;
+    const int max_size = W * H * (channels + 1) + QOIX_HEADER_SIZE + 4;
+    uint8_t* bytes = (uint8_t*)malloc((size_t)max_size + (size_t)W * 8);
+    if (!bytes) return NULL;
+    rgba8* inputScanline = (rgba8*)(bytes + max_size);
+    rgba8* lastInputScanline = inputScanline + W;
+    int p = 0;
+    const uint32_t hdr[3] = {QOIX_MAGIC, desc->width, desc->height};
+    for (int k = 0; k < 3; ++k) { bytes[p++] = (uint8_t)(hdr[k] >> 24); bytes[p++] = (uint8_t)(hdr[k] >> 16); bytes[p++] = (uint8_t)(hdr[k] >> 8); bytes[p++] = (uint8_t)hdr[k]; }
+    bytes[p++] = 1; bytes[p++] = desc->channels; bytes[p++] = desc->bitdepth; bytes[p++] = desc->colorspace; bytes[p++] = 0;
+    uint32_t f[2];
+    memcpy(&f[0], &desc->pixelAspectRatio, 4); memcpy(&f[1], &desc->resolutionY, 4);
+    for (int k = 0; k < 2; ++k) { bytes[p++] = (uint8_t)(f[k] >> 24); bytes[p++] = (uint8_t)(f[k] >> 16); bytes[p++] = (uint8_t)(f[k] >> 8); bytes[p++] = (uint8_t)f[k]; }
+    uint8_t index_lookup[1024]; uint32_t index[64]; uint32_t index_pos = 0;
+    memset(index, 0, sizeof(index)); memset(index_lookup, 0, sizeof(index_lookup));
+    int run = 0, px_pos = 0;
+    rgba8 px = {0, 0, 0, 255}, px_ref;
+    const int px_end = W * H * channels - channels;
+    for (int posy = 0; posy < H; ++posy) {
+        const uint8_t* line = data + (ptrdiff_t)desc->pitchBytes * posy;
+        for (int posx = 0; posx < W; ++posx) {                                                     /* :456-470 */
+            if (channels == 4) { inputScanline[posx].r = line[posx * 4]; inputScanline[posx].g = line[posx * 4 + 1]; inputScanline[posx].b = line[posx * 4 + 2]; inputScanline[posx].a = line[posx * 4 + 3]; }
+            else { inputScanline[posx].r = line[posx * 3]; inputScanline[posx].g = line[posx * 3 + 1]; inputScanline[posx].b = line[posx * 3 + 2]; inputScanline[posx].a = 255; }
+        }
+        for (int posx = 0; posx < W; ++posx) {
+            px_ref = px;
+            px = inputScanline[posx];
+            if (q2_v(px) == q2_v(px_ref)) {
+                run++;
+                if (run == 1024 || px_pos == px_end) { run--; bytes[p++] = (uint8_t)(0xf8 | ((run >> 8) & 3)); bytes[p++] = (uint8_t)(run & 0xff); run = 0; }
+            } else {
+                const uint32_t hash = q2_hash(q2_v(px));
+                if (run > 0) {
+                    run--;
+                    if (run < 8) bytes[p++] = (uint8_t)(0xf0 | run);
+                    else { bytes[p++] = (uint8_t)(0xf8 | ((run >> 8) & 3)); bytes[p++] = (uint8_t)(run & 0xff); }
+                    run = 0;
+                }
+                if (index[index_lookup[hash]] == q2_v(px)) bytes[p++] = (uint8_t)(0x80 | index_lookup[hash]);
+                else {
+                    index_lookup[hash] = (uint8_t)index_pos;
+                    index[index_pos] = q2_v(px);
+                    index_pos = (index_pos + 1) & 63;
+                    const int8_t va = (int8_t)(px.a - px_ref.a);
+                    int colour = 1;
+                    if (va) {
+                        if (va >= -4 && va <= 3) bytes[p++] = (uint8_t)(0xe8 | (va + 4));
+                        else { bytes[p++] = 0xfe; bytes[p++] = px.r; bytes[p++] = px.g; bytes[p++] = px.b; bytes[p++] = px.a; colour = 0; }
+                    }
+                    if (colour) {
+                        if (posy > 0) {
+                            if (posx == 0) { px_ref.r = lastInputScanline[0].r; px_ref.g = lastInputScanline[0].g; px_ref.b = lastInputScanline[0].b; }
+                            else {
+                                const rgba8 a = px_ref, b = lastInputScanline[posx], c = lastInputScanline[posx - 1];
+                                px_ref.r = (uint8_t)loco8(a.r, b.r, c.r); px_ref.g = (uint8_t)loco8(a.g, b.g, c.g); px_ref.b = (uint8_t)loco8(a.b, b.b, c.b);
+                            }
+                        }
+                        const int8_t vg = (int8_t)(px.g - px_ref.g);
+                        const int8_t vg_r = (int8_t)(px.r - px_ref.r - vg), vg_b = (int8_t)(px.b - px_ref.b - vg);
+                        if (vg >= -4 && vg < 0 && vg_r >= -1 && vg_r <= 2 && vg_b >= -1 && vg_b <= 2)
+                            bytes[p++] = (uint8_t)(0x00 | (vg + 4) << 4 | (vg_r + 1) << 2 | (vg_b + 1));
+                        else if (vg >= 0 && vg <= 3 && vg_r >= -2 && vg_r <= 1 && vg_b >= -2 && vg_b <= 1)
+                            bytes[p++] = (uint8_t)(0x00 | (vg + 4) << 4 | (vg_r + 2) << 2 | (vg_b + 2));
+                        else if (px.g == px.r && px.g == px.b) { bytes[p++] = 0xfc; bytes[p++] = px.g; }
+                        else if (vg_r >= -8 && vg_r <= 7 && vg >= -16 && vg <= 15 && vg_b >= -8 && vg_b <= 7) {
+                            bytes[p++] = (uint8_t)(0xc0 | (vg + 16)); bytes[p++] = (uint8_t)((vg_r + 8) << 4 | (vg_b + 8));
+                        } else if (vg_r >= -32 && vg_r <= 31 && vg >= -64 && vg <= 63 && vg_b >= -32 && vg_b <= 31) {
+                            const int dv = ((vg + 64) << 12) | ((vg_r + 32) << 6) | (vg_b + 32);
+                            bytes[p++] = (uint8_t)(0xe0 | ((dv >> 16) & 31)); bytes[p++] = (uint8_t)((dv >> 8) & 255); bytes[p++] = (uint8_t)(dv & 255);
+                        } else { bytes[p++] = 0xfd; bytes[p++] = px.r; bytes[p++] = px.g; bytes[p++] = px.b; }
+                    }
+                }
+            }
+            px_pos += channels;
+        }
+        rgba8* t = inputScanline; inputScanline = lastInputScanline; lastInputScanline = t;
+    }
+    for (int i = 0; i < 4; ++i) bytes[p++] = 255;
+    *out_len = p;
+    return bytes;
+}

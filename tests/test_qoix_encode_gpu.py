@@ -73,7 +73,7 @@ def test_pitch_colorspace_and_rejects(codecs, oracle):
     n = C.c_int(0)
     p = cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(d), C.byref(n))
     assert p and cd._take_host(p, n.value).tobytes() == exp
-    for bad in (cd.QoixDesc(30, 20, 120, 3, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 9, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 4, 8, 0, 0, -1, -1),
+    for bad in (cd.QoixDesc(30, 20, 120, 3, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 9, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 4, 10, 0, 0, -1, -1),
                 cd.QoixDesc(0, 20, 120, 2, 10, 0, 0, -1, -1), cd.QoixDesc(30, 20, 120, 2, 10, 0, 1, -1, -1),
                 cd.QoixDesc(30, 20, 60, 2, 10, 0, 0, -1, -1)):
         assert not cd._L().gb200_qoix_encode(wide.ctypes.data, C.byref(bad), C.byref(n))

@@ -1,8 +1,7 @@
 """GPU parity of the QOI2AVG encoder: gb200_qoix_encode on rgb8 / rgba8 images must produce, byte for byte,
 the stream of the reference's qoix_encode (codecs/qoi2avg.d:376-617, restated in oracle/qoix_sub_oracle.c), and both
 decoders must read it back to the original pixels (the round trip of the reference's own test, image.d:2112-2183).
-(This file sorts last on purpose: its kernels were added after the round's GPU budget ran out and had only been checked
-under the CPU emulation, tests/test_qoi2avg_encode_emulated.py, when it was written.)"""
+(Developed under the CPU emulation, tests/test_qoi2avg_encode_emulated.py; first GPU run: profiles/r2_qoi2avg_pytest.txt.)"""
 import numpy as np
 import pytest
 

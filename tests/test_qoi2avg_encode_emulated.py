@@ -21,10 +21,9 @@ SRCS = [os.path.join(HERE, "emu_qoi2avg_encode.cpp"), os.path.join(HERE, "cuda_e
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(BUILD, exist_ok=True)
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", LIB, SRCS[0]])
-    return C.CDLL(LIB)
+    import emu_build
+    L = emu_build.build("emu_qoi2avg_encode", SRCS)
+    return L
 
 
 def emu_encode(L, imgs, colorspace=0, par=-1.0, dpi=-1.0, descs=None):

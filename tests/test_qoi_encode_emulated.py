@@ -21,11 +21,9 @@ SRCS = [os.path.join(HERE, "emu_qoi_encode.cpp"), os.path.join(HERE, "cuda_emu.h
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(BUILD, exist_ok=True)
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas",
-                               "-o", LIB, SRCS[0]])
-    return C.CDLL(LIB)
+    import emu_build
+    L = emu_build.build("emu_qoi_encode", SRCS)
+    return L
 
 
 def emu_encode(L, imgs, pitches=None, colorspace=0, misalign=0):

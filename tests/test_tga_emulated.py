@@ -19,10 +19,8 @@ SRCS = [os.path.join(HERE, "emu_tga.cpp"), os.path.join(HERE, "cuda_emu.h"), os.
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(BUILD, exist_ok=True)
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", LIB, SRCS[0]])
-    L = C.CDLL(LIB)
+    import emu_build
+    L = emu_build.build("emu_tga", SRCS)
     L.emu_tga_load.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
     return L
 

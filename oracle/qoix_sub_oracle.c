@@ -1,5 +1,6 @@
 /*
- * qoix_sub_oracle.c -- CPU restatement of the remaining QOIX sub-decoders (TEST INFRASTRUCTURE ONLY; see oracle.h):
+ * qoix_sub_oracle.c -- CPU restatement of the remaining QOIX sub-decoders and of two of their encoders (TEST
+ * INFRASTRUCTURE ONLY; see oracle.h):
  *
  *   or_qoix_decode      qoix_decode      source/gamut/codecs/qoi2avg.d:625-839  (8-bit RGB/RGBA, "QOI2AVG")
  *                       locoIntraPredictionSIMD  qoi2avg.d:863-897
@@ -12,10 +13,11 @@
  *    QOI2AVG / QOI-10b and "repeat until the end" in QOI-Plane;
  *  - memory the reference leaves uninitialised (pixels after END, the scanline double buffer) is zero.
  *
- * parity: the reference's encoders for these three codecs are NOT restated, so the reference's round-trip
- * property cannot be replayed; the decoders are pinned by (a) independent minimal encoders written from the
- * format description (tests/qoixsynth.py: image -> stream -> or_*_decode == image) and (b) structural review
- * against the cited lines. "parity unpinned" by reference vectors -- none exist for these streams.
+ * parity: the decoders are pinned by (a) independent minimal encoders written from the format description
+ * (tests/qoixsynth.py: image -> stream -> or_*_decode == image), (b) structural review against the cited lines and,
+ * since round 2, (c) the reference's round-trip property through the restated encoders of two of the three codecs
+ * (or_qoiplane_encode, qoiplane.d:109-375; or_qoix_encode, qoi2avg.d:376-617, at the end of this file; qoi10b_encode is
+ * not restated). No reference-made vectors exist for these streams.
  */
 #include "oracle.h"
 #include <stdlib.h>

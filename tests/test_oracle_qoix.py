@@ -171,3 +171,28 @@ def test_sub_codec_rejects(oracle):
         bad = bytearray(good); bad[off] = val
         assert oracle.qoix_decode(bytes(bad), 0) is None
     assert oracle.qoix_decode(good[:27], 0) is None
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+def test_8bit_sub_encoders_round_trip(oracle, c):
+    """or_qoiplane_encode (qoiplane.d:109-375, c = 1|2) and or_qoix_encode (qoi2avg.d:376-617, c = 3|4): the reference's
+    round-trip property (image.d:2112-2183) through the restated decoders, on images that reach every opcode, the run
+    limits and -- for QOI2AVG -- the eviction of its 64-entry FIFO index; header fields survive; the refusals of the
+    cited checks."""
+    rng = np.random.default_rng(40 + c)
+    if c <= 2:
+        from test_qoix_encode_emulated import plane8_images
+        imgs, enc = plane8_images(c, rng), oracle.qoiplane_encode
+    else:
+        from test_qoi2avg_encode_emulated import qoi2avg_images
+        imgs, enc = qoi2avg_images(c, rng), oracle.qoi2avg_encode
+    for img in imgs:
+        s = enc(img, colorspace=1, par=1.25, dpi=300.0)
+        assert s is not None and s[:4] == b"qoix" and s[12] == 1 and s[13] == c and s[14] == 8 and s[15] == 1 and s[16] == 0
+        px, desc, _ = oracle.qoix_decode(s, 0)
+        assert np.array_equal(px, img) and desc.pixelAspectRatio == 1.25 and desc.resolutionY == 300.0
+    if c >= 3:
+        assert oracle.qoi2avg_encode(imgs[4], colorspace=3) is None           # desc.colorspace > 2 (qoi2avg.d:392)
+        assert oracle.qoiplane_encode(imgs[4]) is None                        # channels 3 / 4 are not QOI-Plane's (qoiplane.d:111)
+    else:
+        assert oracle.qoi2avg_encode(imgs[4]) is None                         # channels 1 / 2 are not QOI2AVG's (qoi2avg.d:391)

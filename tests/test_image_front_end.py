@@ -54,3 +54,18 @@ def test_save_refusals_without_data(img, tmp_path):
     assert not im.saveToStream(F.QOI, io.BytesIO()) and not im.saveToStream(F.unknown, io.BytesIO())
     assert not im.saveToFile(str(tmp_path / "out.qoi")) and not im.saveToFile(F.TGA, str(tmp_path / "out.tga"))
     assert not im.saveToFile(str(tmp_path / "no-such-dir" / "out.qoi"))
+
+
+def test_convert_cli_without_decoding(gb, tmp_path, capsys):
+    """python -m gamut_b200.convert (examples/convert/source/main.d): option conflicts and load errors, the part of the CLI
+    that runs without a GPU."""
+    from gamut_b200 import convert
+    for bad in (["a", "b", "--rgb", "--grey"], ["a", "b", "--alpha", "--drop-alpha"], ["a", "b", "-p", "--unpremul"]):
+        with pytest.raises(SystemExit):
+            convert.main(bad)
+    assert convert.main([str(tmp_path / "missing.qoi"), str(tmp_path / "o.qoi")]) == 1
+    assert "Cannot open file" in capsys.readouterr().err
+    p = tmp_path / "noise.png"
+    p.write_bytes(b"GIF89a" + b"\0" * 40)                          # content says GIF: no loader in this build
+    assert convert.main([str(p), str(tmp_path / "o.tga")]) == 1
+    assert "Cannot decode this image format in this build" in capsys.readouterr().err

@@ -375,24 +375,26 @@ void loadQOIX_b200(ref Image image, IOStream* io, IOHandle handle, int page, int
 /// Replaces saveQOIX (plugins/qoix.d:156-241) for the images the reference routes to qoiplane10_encode (10-bit
 /// greyscale), qoiplane_encode (8-bit greyscale) and qoix_encode / QOI2AVG (8-bit RGB / RGBA), premultiplied variants
 /// included: the stream is the reference sub-encoder's byte for byte, without the LZ4 stage (compression = 0, which is
-/// what qoix_lz4_encode itself returns whenever LZ4 does not make the file smaller). 16-bit RGB(A) (QOI-10b) and
-/// vertically flipped images fall through to the reference's own saveQOIX.
+/// what qoix_lz4_encode itself returns whenever LZ4 does not make the file smaller). 16-bit RGB(A) goes to qoi10b_encode
+/// (QOI-10b) the same way. fp32 types and vertically flipped images fall through to the reference's own saveQOIX.
 bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
 {
     if (page != 0) return false;
     const bool plane10 = image._type == PixelType.l16 || image._type == PixelType.la16 || image._type == PixelType.lap16;
     const bool plane8 = image._type == PixelType.l8 || image._type == PixelType.la8 || image._type == PixelType.lap8;
     const bool rgb8 = image._type == PixelType.rgb8 || image._type == PixelType.rgba8 || image._type == PixelType.rgbap8;
-    if (!(plane10 || plane8 || rgb8) || image._pitch < 0)
+    const bool rgb10 = image._type == PixelType.rgb16 || image._type == PixelType.rgba16 || image._type == PixelType.rgbap16;
+    if (!(plane10 || plane8 || rgb8 || rgb10) || image._pitch < 0)
         return saveQOIX(image, io, handle, page, flags, data);
 
     gb200_qoix_desc desc;
     desc.width = image._width;
     desc.height = image._height;
     desc.pitchBytes = image._pitch;
-    desc.channels = rgb8 ? (image._type == PixelType.rgb8 ? 3 : 4) : (image._type == PixelType.l16 || image._type == PixelType.l8) ? 1 : 2;
-    desc.bitdepth = plane10 ? 10 : 8;
-    desc.colorspace = (image._type == PixelType.lap16 || image._type == PixelType.lap8 || image._type == PixelType.rgbap8) ? 2 /* QOIX_SRGB_PREMUL */ : 0 /* QOIX_SRGB */;
+    desc.channels = (rgb8 || rgb10) ? ((image._type == PixelType.rgb8 || image._type == PixelType.rgb16) ? 3 : 4)
+                                    : (image._type == PixelType.l16 || image._type == PixelType.l8) ? 1 : 2;
+    desc.bitdepth = (plane10 || rgb10) ? 10 : 8;
+    desc.colorspace = (image._type == PixelType.lap16 || image._type == PixelType.lap8 || image._type == PixelType.rgbap8 || image._type == PixelType.rgbap16) ? 2 /* QOIX_SRGB_PREMUL */ : 0 /* QOIX_SRGB */;
     desc.compression = 0;
     desc.pixelAspectRatio = image._pixelAspectRatio;
     desc.resolutionY = image._resolutionY;

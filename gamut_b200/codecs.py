@@ -340,7 +340,8 @@ def qoix_encode(pixels: np.ndarray, bitdepth: Optional[int] = None, colorspace: 
                 pitch: Optional[int] = None) -> Optional[bytes]:
     """qoix_lz4_encode (plugins/qoix.d:251) of a (h, w, c) image: c = 1|2 uint16 (10-bit values expanded to 16 bits) -> the
     QOI-Plane10 stream (qoiplane10.d:99), c = 1|2 uint8 -> the QOI-Plane stream (qoiplane.d:109), c = 3|4 uint8 -> the
-    QOI2AVG stream (qoi2avg.d:376); never LZ4-wrapped. None if the encoder refuses the image."""
+    QOI2AVG stream (qoi2avg.d:376), c = 3|4 uint16 -> the QOI-10b stream (qoi10b.d:136); never LZ4-wrapped. None if the
+    encoder refuses the image."""
     h, w, c = pixels.shape
     px = np.ascontiguousarray(pixels)
     if bitdepth is None:

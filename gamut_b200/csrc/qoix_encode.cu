@@ -92,6 +92,9 @@ bool qoiplane_encode_device(int n, const uint8_t* const* pixels_dev, const gb200
 // qoi2avg_encode.cu: the 3 / 4-channel 8-bit images of a batch (QOI2AVG)
 bool qoi2avg_encode_device(int n, const uint8_t* const* pixels_dev, const gb200_qoix_desc* descs, uint8_t* const* out_dev,
                            int* out_len, cudaStream_t st);
+// qoi10b_encode.cu: the 3 / 4-channel 10-bit images of a batch (QOI-10b)
+bool qoi10b_encode_device(int n, const uint8_t* const* pixels_dev, const gb200_qoix_desc* descs, uint8_t* const* out_dev,
+                          int* out_len, cudaStream_t st);
 
 }  // namespace gb
 
@@ -101,6 +104,7 @@ GB_API size_t gb200_qoix_encode_bound(const gb200_qoix_desc* desc)
 {
     if (!desc) return 0;
     const unsigned long long np = (unsigned long long)desc->width * desc->height;
+    if (desc->channels >= 3 && desc->bitdepth == 10) return (size_t)((np * 52 + 7) / 8 + QOIX_HEADER_SIZE + 5 + 64); // QOI-10b: at most 52 bits per pixel
     if (desc->channels >= 3) return (size_t)(np * ((unsigned)desc->channels + 1u) + QOIX_HEADER_SIZE + 4 + 16);     // qoix_encode's own (qoi2avg.d:408)
     return (size_t)((np * (desc->channels == 1 ? 14 : 28) + 7) / 8 + QOIX_HEADER_SIZE + 5 + 64);
 }
@@ -110,10 +114,12 @@ GB_API int gb200_qoix_encode_batch_device(int n, const uint8_t* const* pixels_de
 {
     gb::clear_error();
     if (n < 0 || !pixels_dev || !descs || !out_dev || !out_len) { gb::set_error("qoix_encode_batch_device: bad arguments"); return 0; }
-    bool any_rgb = false;
-    for (int i = 0; i < n; ++i) any_rgb |= descs[i].channels >= 3;
+    bool any_rgb8 = false, any_rgb10 = false;
+    for (int i = 0; i < n; ++i) if (descs[i].channels >= 3) { if (descs[i].bitdepth == 10) any_rgb10 = true; else any_rgb8 = true; }
     if (!gb::qoiplane_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream)) return 0;       // 1 / 2 channels; others get 0
-    return !any_rgb || gb::qoi2avg_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream) ? 1 : 0;
+    if (any_rgb8 && !gb::qoi2avg_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream)) return 0;
+    if (any_rgb10 && !gb::qoi10b_encode_device(n, pixels_dev, descs, out_dev, out_len, (cudaStream_t)stream)) return 0;
+    return 1;
 }
 
 // qoix_lz4_encode (plugins/qoix.d:251) for the images it hands to qoiplane10_encode (10-bit, 1 or 2 channels) and to
@@ -124,9 +130,11 @@ GB_API uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* 
     gb::clear_error();
     if (!gb::ensure_device()) return nullptr;
     const bool rgb8 = desc && desc->channels >= 3 && ::q2_valid_desc(desc->width, desc->height, desc->channels, desc->bitdepth, desc->colorspace, desc->compression);
-    if (!pixels || !desc || !out_len || !(rgb8 || gb::qe_valid(*desc)) ||
+    const bool rgb10 = desc && desc->channels >= 3 && desc->channels <= 4 && desc->bitdepth == 10 && desc->compression == 0 && desc->width && desc->height &&
+                       desc->height < 400000000u / desc->width && (unsigned long long)desc->width * desc->height * 52ull + 4096 < 0xffffffffull;   // qoi10b.d:138-146
+    if (!pixels || !desc || !out_len || !(rgb8 || rgb10 || gb::qe_valid(*desc)) ||
         desc->pitchBytes < (int)(desc->width * desc->channels * (desc->bitdepth == 10 ? 2u : 1u))) {
-        gb::set_error("qoix_encode: unsupported image (built: QOI-Plane10 / QOI-Plane for 10-bit / 8-bit images with 1 or 2 channels, QOI2AVG for 8-bit images with 3 or 4)");
+        gb::set_error("qoix_encode: unsupported image (built: QOI-Plane10 / QOI-Plane for 10-bit / 8-bit images with 1 or 2 channels, QOI-10b / QOI2AVG for 10-bit / 8-bit images with 3 or 4)");
         return nullptr;
     }
     cudaStream_t st = gb::thread_stream();
@@ -136,7 +144,8 @@ GB_API uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* 
     if (!gb::cuda_ok(cudaMemcpyAsync(d_in.p, pixels, in_bytes, cudaMemcpyHostToDevice, st), "qe h2d", __FILE__, __LINE__)) { cudaStreamSynchronize(st); return nullptr; }
     const uint8_t* pin[1] = {d_in.as<uint8_t>()}; uint8_t* pout[1] = {d_out.as<uint8_t>()};
     int len = 0;
-    const bool ran = rgb8 ? gb::qoi2avg_encode_device(1, pin, desc, pout, &len, st) : gb::qoiplane_encode_device(1, pin, desc, pout, &len, st);
+    const bool ran = rgb8 ? gb::qoi2avg_encode_device(1, pin, desc, pout, &len, st) : rgb10 ? gb::qoi10b_encode_device(1, pin, desc, pout, &len, st)
+                          : gb::qoiplane_encode_device(1, pin, desc, pout, &len, st);
     if (!ran || len <= 0) { cudaStreamSynchronize(st); return nullptr; }
     uint8_t* out = (uint8_t*)malloc((size_t)len);
     if (!out) return nullptr;

@@ -548,12 +548,14 @@ class Image:
             channels, bitdepth = (1 if t == PixelType.l8 else 2), 8            # -> qoiplane_encode (plugins/qoix.d:172-184)
         elif t in (PixelType.rgb8, PixelType.rgba8, PixelType.rgbap8):
             channels, bitdepth = (3 if t == PixelType.rgb8 else 4), 8          # -> qoix_encode, QOI2AVG (plugins/qoix.d:185-198)
+        elif t in (PixelType.rgb16, PixelType.rgba16, PixelType.rgbap16):
+            channels, bitdepth = (3 if t == PixelType.rgb16 else 4), 10        # -> qoi10b_encode (plugins/qoix.d:213-228)
         else:
-            return None                                    # rgb16 / rgba16 / rgbap16 -> qoi10b_encode: not built
+            return None                                    # fp32 types: saveQOIX "not supported" (plugins/qoix.d:229-230)
         if self._pitch < self._width * pixelTypeSize(t):
             return None                                    # vertically flipped storage: not taken by the C entry point
         d = codecs.QoixDesc(self._width, self._height, self._pitch, channels, bitdepth,
-                            2 if t in (PixelType.lap16, PixelType.lap8, PixelType.rgbap8) else 0, 0, self._pixelAspectRatio, self._resolutionY)
+                            2 if t in (PixelType.lap16, PixelType.lap8, PixelType.rgbap8, PixelType.rgbap16) else 0, 0, self._pixelAspectRatio, self._resolutionY)
         n = C.c_int(0)
         p = codecs._L().gb200_qoix_encode(first, C.byref(d), C.byref(n))
         return codecs._take_host(p, n.value).tobytes() if p else None

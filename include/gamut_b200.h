@@ -231,12 +231,13 @@ gb200_batch* gb200_qoix_decode_batch(int n, const uint8_t* const* files, const s
 /* ---- QOIX encode: source/gamut/plugins/qoix.d:251-339, codecs/qoiplane10.d:99-314, qoiplane.d:109-375,
  * qoi2avg.d:376-617 ----
  * qoix_lz4_encode for the images it hands to qoiplane10_encode (bitdepth 10, 1 or 2 channels, 16-bit samples), to
- * qoiplane_encode (bitdepth 8, 1 or 2 channels) and to qoix_encode / QOI2AVG (bitdepth 8, 3 or 4 channels); desc->
+ * qoiplane_encode (bitdepth 8, 1 or 2 channels), to qoix_encode / QOI2AVG (bitdepth 8, 3 or 4 channels) and to
+ * qoi10b_encode / QOI-10b (bitdepth 10, 3 or 4 channels, 16-bit samples); desc->
  * compression must be 0, pitchBytes is honoured (not negative). The stream is bit-identical to the reference
  * sub-encoder's; the LZ4 stage (LZ4_compress, kept by the reference only when it makes the file smaller) is not built,
- * so the result always has compression = 0 -- a valid QOIX file that every decoder of the format reads. The 10-bit RGB
- * sub-encoder (QOI-10b) is not built: bitdepth 10 with 3 / 4 channels returns NULL. Returns malloc()'d bytes
- * (gb200_free) or NULL. */
+ * so the result always has compression = 0 -- a valid QOIX file that every decoder of the format reads. bitdepth 10
+ * with 3 or 4 channels (16-bit samples) goes to qoi10b_encode / QOI-10b (qoi10b.d:136-500): all four sub-encoders of
+ * qoix_lz4_encode are built. Returns malloc()'d bytes (gb200_free) or NULL. */
 uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* desc, int* out_len);
 /* Upper bound of the stream length for a device output buffer (qoiplane10.d:112-116, rounded up). */
 size_t gb200_qoix_encode_bound(const gb200_qoix_desc* desc);

@@ -99,6 +99,7 @@ uint8_t* or_qoiplane_encode(const uint8_t* pixels, const or_qoix_desc* desc, int
 uint8_t* or_qoix_decode(const uint8_t* data, int size, or_qoix_desc* desc, int channels);       /* qoi2avg.d:625 */
 uint8_t* or_qoix_encode(const uint8_t* pixels, const or_qoix_desc* desc, int* out_len);         /* qoi2avg.d:376 */
 uint8_t* or_qoi10b_decode(const uint8_t* data, int size, or_qoix_desc* desc, int channels);     /* qoi10b.d:504 */
+uint8_t* or_qoi10b_encode(const uint8_t* pixels, const or_qoix_desc* desc, int* out_len);       /* qoi10b.d:136 */
 int or_lz4_decompress_fast(const uint8_t* src, uint8_t* dst, int originalSize);  /* lz4.d:976 */
 int or_lz4_compress(const uint8_t* src, uint8_t* dst, int srcSize);              /* lz4.d:544 */
 int or_lz4_compress_bound(int isize);                                            /* lz4.d:68 */

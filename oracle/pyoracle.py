@@ -71,6 +71,8 @@ def lib():
         L.or_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.or_qoix_encode.restype = C.c_void_p
         L.or_qoix_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
+        L.or_qoi10b_encode.restype = C.c_void_p
+        L.or_qoi10b_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_qoiplane_encode.restype = C.c_void_p
         L.or_qoiplane_encode.argtypes = [C.c_void_p, C.POINTER(QoixDesc), C.POINTER(C.c_int)]
         L.or_qoiplane10_encode.restype = C.c_void_p
@@ -209,6 +211,19 @@ def qoi2avg_encode(pixels: np.ndarray, colorspace: int = 0, par: float = -1.0, d
     d = QoixDesc(w, h, pitch if pitch is not None else w * c, c, 8, colorspace, 0, par, dpi)
     n = C.c_int(0)
     p = lib().or_qoix_encode(px.ctypes.data, C.byref(d), C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value).tobytes()
+
+
+def qoi10b_encode(pixels: np.ndarray, colorspace: int = 0, par: float = -1.0, dpi: float = -1.0, pitch=None, shape=None):
+    """or_qoi10b_encode (qoi10b.d:136-500) of a (h, w, 1..4) uint16 image: the QOI-10b stream (version 1) without the LZ4
+    stage, or None."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    d = QoixDesc(w, h, pitch if pitch is not None else w * c * 2, c, 10, colorspace, 0, par, dpi)
+    n = C.c_int(0)
+    p = lib().or_qoi10b_encode(px.ctypes.data, C.byref(d), C.byref(n))
     if not p:
         return None
     return _take(p, n.value).tobytes()

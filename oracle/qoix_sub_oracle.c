@@ -512,3 +512,121 @@ uint8_t* or_qoix_encode(const uint8_t* data, const or_qoix_desc* desc, int* out_
     *out_len = p;
     return bytes;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* qoi10b_encode (qoi10b.d:136-500), stream version 1 (the only one the reference's encoder writes, :168): 16-bit
+ * samples (10 significant bits) of 1-4 channels -> QOI-10b stream (no LZ4 stage). The encoder declares a colour index
+ * (:233-235) but never emits an index opcode; the prediction is the rounded-up average of the previous pixel and the
+ * pixel above (:357-362). */
+typedef struct { uint8_t* bytes; int p; int currentBit; } bitw10;
+static void outputBits10(bitw10* w, uint32_t x, int nbits)          /* :196-211 */
+{
+    for (int b = nbits - 2; b >= 0; b -= 2) {
+        const uint8_t pair = (uint8_t)((x >> b) & 3);
+        w->bytes[w->p] |= (uint8_t)(pair << (w->currentBit - 1));
+        w->currentBit -= 2;
+        if (w->currentBit == -1) { w->p++; w->bytes[w->p] = 0; w->currentBit = 7; }
+    }
+}
+static int fits10(int v, int k) { return v >= 1024 - k || v < k; }
+uint8_t* or_qoi10b_encode(const uint8_t* data, const or_qoix_desc* desc, int* out_len)
+{
+    if ((desc->channels != 1 && desc->channels != 2 && desc->channels != 3 && desc->channels != 4) || desc->width == 0 ||
+        desc->height >= QOIX_PIXELS_MAX / desc->width || desc->compression != 0) return NULL;
+    if (desc->bitdepth != 10) return NULL;
+    const int channels = desc->channels, W = (int)desc->width, H = (int)desc->height;
+    const int num_pixels = W * H;
+    /* the reference sizes its buffer for 48 bits per pixel (:113, :152); ADIFF2 + RGB is 54, so allocate for 56 */
+    const size_t max_size = ((size_t)num_pixels * 56 + 7) / 8 + QOIX_HEADER_SIZE + 5 + 2;
+    uint8_t* bytes = (uint8_t*)calloc(max_size, 1);
+    rgba10* cur = (rgba10*)calloc((size_t)W, sizeof(rgba10)), *last = (rgba10*)calloc((size_t)W, sizeof(rgba10));
+    if (!bytes || !cur || !last) { free(bytes); free(cur); free(last); return NULL; }
+    int p = 0;
+    const uint32_t hdr[3] = {QOIX_MAGIC, desc->width, desc->height};
+    for (int k = 0; k < 3; ++k) { bytes[p++] = (uint8_t)(hdr[k] >> 24); bytes[p++] = (uint8_t)(hdr[k] >> 16); bytes[p++] = (uint8_t)(hdr[k] >> 8); bytes[p++] = (uint8_t)hdr[k]; }
+    bytes[p++] = 1; bytes[p++] = desc->channels; bytes[p++] = desc->bitdepth; bytes[p++] = desc->colorspace; bytes[p++] = 0;
+    uint32_t f[2];
+    memcpy(&f[0], &desc->pixelAspectRatio, 4); memcpy(&f[1], &desc->resolutionY, 4);
+    for (int k = 0; k < 2; ++k) { bytes[p++] = (uint8_t)(f[k] >> 24); bytes[p++] = (uint8_t)(f[k] >> 16); bytes[p++] = (uint8_t)(f[k] >> 8); bytes[p++] = (uint8_t)f[k]; }
+    bitw10 Wr = {bytes, p, 7};
+    const int grey = channels == 1 || channels == 2;
+    rgba10 px = {0, 0, 0, 1023}, ref;
+    int run = 0, encoded = 0;
+    for (int posy = 0; posy < H; ++posy) {
+        const uint16_t* line = (const uint16_t*)(data + (ptrdiff_t)desc->pitchBytes * posy);
+        for (int x = 0; x < W; ++x) {                                                          /* :254-297 */
+            rgba10 q;
+            if (channels == 4) { q.r = line[x * 4]; q.g = line[x * 4 + 1]; q.b = line[x * 4 + 2]; q.a = line[x * 4 + 3]; }
+            else if (channels == 3) { q.r = line[x * 3]; q.g = line[x * 3 + 1]; q.b = line[x * 3 + 2]; q.a = 65535; }
+            else if (channels == 2) { q.r = q.g = q.b = line[x * 2]; q.a = line[x * 2 + 1]; }
+            else { q.r = q.g = q.b = line[x]; q.a = 65535; }
+            q.r >>= 6; q.g >>= 6; q.b >>= 6; q.a >>= 6;
+            cur[x] = q;
+        }
+        for (int x = 0; x < W; ++x) {
+            ref = px;
+            px = cur[x];
+            if (px.r == ref.r && px.g == ref.g && px.b == ref.b && px.a == ref.a) {
+                run++;
+                if (run == 256 || encoded + 1 == num_pixels) goto flush_run;
+                goto next;
+            flush_run:
+                run--;
+                if (run < 7) outputBits10(&Wr, 0xf0u | (uint32_t)run, 8);
+                else { outputBits10(&Wr, 0xf7u, 8); outputBits10(&Wr, (uint32_t)(run - 7), 8); }
+                run = 0;
+            } else {
+                if (run > 0) {
+                    run--;
+                    if (run < 7) outputBits10(&Wr, 0xf0u | (uint32_t)run, 8);
+                    else { outputBits10(&Wr, 0xf7u, 8); outputBits10(&Wr, (uint32_t)(run - 7), 8); }
+                    run = 0;
+                }
+                const int va = (px.a - ref.a) & 1023;
+                if (va) {
+                    if (fits10(va, 16)) outputBits10(&Wr, (0x1du << 5) | (uint32_t)(va & 0x1f), 10);            /* QOI_OP_ADIFF */
+                    else if (fits10(va, 128)) { outputBits10(&Wr, 0xf8u >> 2, 6); outputBits10(&Wr, (uint32_t)va, 8); }   /* QOI_OP_ADIFF2 */
+                    else {
+                        outputBits10(&Wr, 0xfeu, 8); outputBits10(&Wr, px.r, 10);                               /* QOI_OP_RGBA */
+                        if (!grey) { outputBits10(&Wr, px.g, 10); outputBits10(&Wr, px.b, 10); }
+                        outputBits10(&Wr, px.a, 10);
+                        goto next;
+                    }
+                }
+                if (posy > 0) {                                                                                /* version 1: average */
+                    ref.r = (uint16_t)((ref.r + last[x].r + 1) >> 1);
+                    ref.g = (uint16_t)((ref.g + last[x].g + 1) >> 1);
+                    ref.b = (uint16_t)((ref.b + last[x].b + 1) >> 1);
+                }
+                const int vg = (px.g - ref.g) & 1023;
+                const int vg_r = (px.r - ref.r - vg) & 1023, vg_b = (px.b - ref.b - vg) & 1023;
+                if (fits10(vg_r, 4) && fits10(vg, 8) && fits10(vg_b, 4)) {
+                    outputBits10(&Wr, 0x20u | (uint32_t)(vg & 0x0f), 6);                                        /* QOI_OP_LUMA0 */
+                    if (!grey) outputBits10(&Wr, (uint32_t)((vg_r << 3) | (vg_b & 7)), 6);
+                } else if (fits10(vg_r, 8) && fits10(vg, 16) && fits10(vg_b, 8)) {
+                    outputBits10(&Wr, (uint32_t)(vg & 0x1f), 6);                                                /* QOI_OP_LUMA */
+                    if (!grey) { outputBits10(&Wr, (uint32_t)vg_r, 4); outputBits10(&Wr, (uint32_t)vg_b, 4); }
+                } else if (!grey && px.g == px.r && px.g == px.b) {
+                    outputBits10(&Wr, 0xfcu, 8); outputBits10(&Wr, px.g, 10);                                   /* QOI_OP_GRAY */
+                } else if (fits10(vg_r, 32) && fits10(vg, 64) && fits10(vg_b, 32)) {
+                    outputBits10(&Wr, (0x6u << 7) | (uint32_t)(vg & 0x7f), 10);                                 /* QOI_OP_LUMA2 */
+                    if (!grey) { outputBits10(&Wr, (uint32_t)vg_r, 6); outputBits10(&Wr, (uint32_t)vg_b, 6); }
+                } else if (fits10(vg_r, 128) && fits10(vg, 256) && fits10(vg_b, 128)) {
+                    outputBits10(&Wr, (0x1cu << 9) | (uint32_t)(vg & 0x1ff), 14);                               /* QOI_OP_LUMA3 */
+                    if (!grey) { outputBits10(&Wr, (uint32_t)vg_r, 8); outputBits10(&Wr, (uint32_t)vg_b, 8); }
+                } else {
+                    outputBits10(&Wr, 0xfdu, 8); outputBits10(&Wr, px.r, 10);                                   /* QOI_OP_RGB */
+                    if (!grey) { outputBits10(&Wr, px.g, 10); outputBits10(&Wr, px.b, 10); }
+                }
+            }
+        next:
+            encoded++;
+        }
+        rgba10* t = cur; cur = last; last = t;
+    }
+    for (int i = 0; i < 5; ++i) outputBits10(&Wr, 0xffu, 8);                                                    /* :488-491 */
+    if (Wr.currentBit != 7) outputBits10(&Wr, 0xffu, Wr.currentBit + 1);
+    free(cur); free(last);
+    *out_len = Wr.p;
+    return bytes;
+}

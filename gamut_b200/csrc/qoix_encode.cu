@@ -122,9 +122,10 @@ GB_API int gb200_qoix_encode_batch_device(int n, const uint8_t* const* pixels_de
     return 1;
 }
 
-// qoix_lz4_encode (plugins/qoix.d:251) for the images it hands to qoiplane10_encode (10-bit, 1 or 2 channels) and to
-// qoiplane_encode (8-bit, 1 or 2 channels): host pixels in, malloc()'d stream out (free with gb200_free), *out_len its
-// length. The stream is not LZ4-wrapped (compression 0).
+// qoix_lz4_encode (plugins/qoix.d:251-339) with its dispatch (:268-290): 10-bit with 1 / 2 channels -> qoiplane10_encode,
+// 10-bit with 3 / 4 -> qoi10b_encode, 8-bit with 1 / 2 -> qoiplane_encode, 8-bit with 3 / 4 -> qoix_encode (QOI2AVG). Host
+// pixels in, malloc()'d stream out (free with gb200_free), *out_len its length. The stream is not LZ4-wrapped
+// (compression 0).
 GB_API uint8_t* gb200_qoix_encode(const uint8_t* pixels, const gb200_qoix_desc* desc, int* out_len)
 {
     gb::clear_error();

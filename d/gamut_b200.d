@@ -107,6 +107,10 @@ extern(C)
     size_t gb200_tga_encode_bound(const(gb200_tga_desc)* desc);
     int gb200_tga_encode_batch_device(int n, const(ubyte*)* pixels_dev, const(gb200_tga_desc)* descs, const(ubyte*)* out_dev,
                                       int* out_len, void* stream);
+    /// saveBMP -> write_bmp (codecs/bmpenc.d:25-113): rgb8 / rgba8 rows -> a BMP file with a V4 header
+    struct gb200_bmp_desc { int width, height, pitchBytes, type; float ppmX, ppmY; }
+    ubyte* gb200_bmp_encode(const(ubyte)* pixels, const(gb200_bmp_desc)* desc, int* out_len);
+    size_t gb200_bmp_encode_size(const(gb200_bmp_desc)* desc);
     int gb200_copy_to_host(void* dst_host, const(void)* src_dev, size_t bytes);
     int gb200_copy_to_device(void* dst_dev, const(void)* src_host, size_t bytes);
     int gb200_download_by_kernel(void* dst_pinned, const(void)* src_dev, size_t bytes, void* stream);
@@ -404,6 +408,25 @@ bool saveQOIX_b200(ref const(Image) image, IOStream* io, IOHandle handle, int pa
     if (encoded is null) return false;
     scope(exit) free(encoded);
     return qoilen == io.write(encoded, 1, qoilen, handle);
+}
+
+/// Replaces saveBMP (plugins/bmp.d:166-194): the same file as write_bmp's (codecs/bmpenc.d:25-113); the padding bytes of
+/// 24-bit rows, which the reference leaves uninitialised, are zero.
+bool saveBMP_b200(ref const(Image) image, IOStream* io, IOHandle handle, int page, int flags, void* data) @trusted
+{
+    if (page != 0) return false;
+    gb200_bmp_desc desc;
+    desc.width = image._width;
+    desc.height = image._height;
+    desc.pitchBytes = image._pitch;
+    desc.type = cast(int) image._type;
+    desc.ppmX = image.pixelsPerMeterX();
+    desc.ppmY = image.pixelsPerMeterY();
+    int len;
+    ubyte* encoded = gb200_bmp_encode(image._data, &desc, &len);
+    if (encoded is null) return false;
+    scope(exit) free(encoded);
+    return len == io.write(encoded, 1, len, handle);
 }
 
 /// Replaces saveTGA (plugins/tga.d:123-149): the TGAEncoder's file (24- or 32-bit, run-length coded, bottom row first),

@@ -30,6 +30,11 @@ class TgaDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("type", C.c_int32)]
 
 
+class BmpDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("type", C.c_int32),
+                ("ppmX", C.c_float), ("ppmY", C.c_float)]
+
+
 class QoiDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint8), ("colorspace", C.c_uint8)]
 
@@ -99,6 +104,10 @@ def _L():
         L.gb200_tga_encode_bound.argtypes = [C.POINTER(TgaDesc)]
         L.gb200_tga_encode_batch_device.restype = i32
         L.gb200_tga_encode_batch_device.argtypes = [i32, C.POINTER(vp), C.POINTER(TgaDesc), C.POINTER(vp), ip, vp]
+        L.gb200_bmp_encode.restype = vp
+        L.gb200_bmp_encode.argtypes = [vp, C.POINTER(BmpDesc), ip]
+        L.gb200_bmp_encode_size.restype = sz
+        L.gb200_bmp_encode_size.argtypes = [C.POINTER(BmpDesc)]
         L.gb200_bmp_load.restype = vp
         L.gb200_bmp_load.argtypes = [C.c_char_p, sz, i32, ip, ip, ip, fp, fp, fp]
         L.gb200_bmp_decode_batch.restype = vp
@@ -447,6 +456,20 @@ def tga_encode_batch_device(pixels_dev: Sequence[int], shapes: Sequence[tuple], 
     lens = (C.c_int * max(n, 1))()
     _lib.check(_L().gb200_tga_encode_batch_device(n, pin, descs, pout, lens, stream), "tga_encode_batch_device")
     return [lens[i] for i in range(n)]
+
+
+def bmp_encode(pixels: np.ndarray, ppmX: float = -1.0, ppmY: float = -1.0, pitch: Optional[int] = None, first_scanline: int = 0,
+               shape: Optional[tuple] = None, type_: Optional[int] = None) -> Optional[bytes]:
+    """saveBMP (plugins/bmp.d:166-194) of a (h, w, 3|4) uint8 image (rgb8 / rgba8): the file write_bmp writes (row padding
+    zero), or None where saveBMP fails. ppmX / ppmY = Image.pixelsPerMeterX / Y (-1 = unknown)."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    d = BmpDesc(w, h, pitch if pitch is not None else w * c, type_ if type_ is not None else {3: 9, 4: 12}.get(c, -1), ppmX, ppmY)
+    n = C.c_int(0)
+    p = _L().gb200_bmp_encode(px.ctypes.data + first_scanline, C.byref(d), C.byref(n))
+    if not p:
+        return None
+    return _take_host(p, n.value).tobytes()
 
 
 def bmp_load(data: bytes, req_comp: int = 0) -> Optional[PngResult]:

@@ -263,6 +263,14 @@ class Image:
             return GAMUT_UNKNOWN_RESOLUTION
         return float(np.float32(self._resolutionY) * np.float32(self._pixelAspectRatio))
 
+    def pixelsPerMeterX(self):                                  # image.d:344-350 (convertMetersToInches: x * 39.37007874f)
+        dpi = self.dotsPerInchX()
+        return GAMUT_UNKNOWN_RESOLUTION if dpi == GAMUT_UNKNOWN_RESOLUTION else float(np.float32(dpi) * np.float32(39.37007874))
+
+    def pixelsPerMeterY(self):                                  # image.d:355-361
+        dpi = self.dotsPerInchY()
+        return GAMUT_UNKNOWN_RESOLUTION if dpi == GAMUT_UNKNOWN_RESOLUTION else float(np.float32(dpi) * np.float32(39.37007874))
+
     def scanline(self, y: int) -> np.ndarray:
         """Bytes of scanline y (image.d scanptr)."""
         n = self._width * pixelTypeSize(self._type)
@@ -517,7 +525,7 @@ class Image:
     # -- Image.saveToMemory (image.d:966) for the save paths that are built: saveQOIX (plugins/qoix.d:156-241) of a
     #    greyscale image (10-bit -> qoiplane10_encode, 8-bit -> qoiplane_encode) or of an 8-bit RGB(A) image (-> qoix_encode,
     #    QOI2AVG), saveTGA (plugins/tga.d:123-149) of an
-    #    l8 / la8 / rgb8 / rgba8 image, and saveQOI (plugins/qoi.d:150-185) of
+    #    l8 / la8 / rgb8 / rgba8 image, saveBMP (plugins/bmp.d:166-194) of an rgb8 / rgba8 image, and saveQOI (plugins/qoi.d:150-185) of
     #    an rgb8 / rgba8 image. Returns the file bytes or None (the reference returns a null slice when the plugin's
     #    saveProc fails or the format has none).
     def saveToMemory(self, fmt, flags: int = 0):
@@ -532,6 +540,13 @@ class Image:
             d = codecs.QoiDesc(self._width, self._height, 3 if t == PixelType.rgb8 else 4, 0)     # QOI_SRGB (:159)
             n = C.c_int(0)
             p = codecs._L().gb200_qoi_encode(first, C.byref(d), self._pitch, C.byref(n))
+            return codecs._take_host(p, n.value).tobytes() if p else None
+        if int(fmt) == int(ImageFormat.BMP):
+            if t not in (PixelType.rgb8, PixelType.rgba8):
+                return None                                # saveBMP: "can save RGB and RGBA 8-bit images" (plugins/bmp.d:173-183)
+            d = codecs.BmpDesc(self._width, self._height, self._pitch, int(t), self.pixelsPerMeterX(), self.pixelsPerMeterY())
+            n = C.c_int(0)
+            p = codecs._L().gb200_bmp_encode(first, C.byref(d), C.byref(n))
             return codecs._take_host(p, n.value).tobytes() if p else None
         if int(fmt) == int(ImageFormat.TGA):
             if t not in (PixelType.l8, PixelType.la8, PixelType.rgb8, PixelType.rgba8):

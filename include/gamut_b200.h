@@ -158,6 +158,14 @@ uint8_t* gb200_jpeg_load(const uint8_t* data, size_t len, int req_comps, int* wi
                          int* actual_comps, float* pixelAspectRatio, float* dotsPerInchY);
 gb200_batch* gb200_jpeg_decode_batch(int n, const uint8_t* const* files, const size_t* lens,
                                      const uint8_t* const* files_dev, int req_comps, void* stream);
+/* ---- BMP encode: saveBMP (plugins/bmp.d:166-194) -> write_bmp (codecs/bmpenc.d:25-113) ----
+ * type = gb200_pixel_type of the rows: rgb8 (24-bit file) or rgba8 (32-bit BI_BITFIELDS file, V4 header); sides
+ * 1..32767; pitchBytes signed, `pixels` = the first scanline; ppmX / ppmY = Image.pixelsPerMeterX / Y (-1 = unknown). The
+ * file equals the one write_bmp writes except for the row padding of 24-bit files, which the reference takes from an
+ * uninitialised buffer (bmpenc.d:40-43) and this writer sets to zero. */
+typedef struct gb200_bmp_desc { int32_t width, height, pitchBytes, type; float ppmX, ppmY; } gb200_bmp_desc;
+uint8_t* gb200_bmp_encode(const uint8_t* pixels, const gb200_bmp_desc* desc, int* out_len);
+size_t gb200_bmp_encode_size(const gb200_bmp_desc* desc);
 /* ---- TGA ----
  * TGADecoder.getImageInfo + decodeImage (codecs/tga.d:313-588) as loadTGA calls them (plugins/tga.d:45-105): grey,
  * grey + alpha, 15/16-bit and 24/32-bit colour, colour-mapped files (8/16-bit indices; 8/15/16/24/32-bit entries), raw

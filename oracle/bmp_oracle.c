@@ -365,3 +365,43 @@ int or_identify_format(const uint8_t* d, size_t len)
     if (tga_info(d, len)) return 5;
     return -1;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* saveBMP (plugins/bmp.d:166-194) -> write_bmp (codecs/bmpenc.d:25-113): rgb8 / rgba8 rows (type = PixelType value 9 / 12;
+ * `data` = first scanline, pitchBytes signed) -> BMP file with a V4 header. ppmX / ppmY = Image.pixelsPerMeterX / Y, -1 when
+ * unknown. The reference writes the row padding of 24-bit files from an uninitialised buffer (:40-43, :103); here it is 0. */
+#include <math.h>
+uint8_t* or_bmp_encode(const uint8_t* data, int type, int width, int height, int pitchBytes, float ppmX, float ppmY, int* out_len)
+{
+    const int chans = type == 9 ? 3 : type == 12 ? 4 : 0;
+    if (!chans || width < 1 || height < 1 || width > 32767 || height > 32767) return NULL;
+    enum { DIB_SIZE = 108 };
+    const int linesize = width * chans, pad = 3 - ((linesize - 1) & 3);
+    const int idat_offset = 14 + DIB_SIZE;
+    const size_t filesize = (size_t)idat_offset + (size_t)height * (size_t)(linesize + pad);
+    uint8_t* out = (uint8_t*)calloc(filesize, 1);
+    if (!out) return NULL;
+    uint8_t* hdr = out;
+#define LE32(at, v) do { const uint32_t v_ = (uint32_t)(v); hdr[at] = (uint8_t)v_; hdr[(at) + 1] = (uint8_t)(v_ >> 8); hdr[(at) + 2] = (uint8_t)(v_ >> 16); hdr[(at) + 3] = (uint8_t)(v_ >> 24); } while (0)
+    hdr[0] = 0x42; hdr[1] = 0x4d;
+    LE32(2, filesize); LE32(10, idat_offset); LE32(14, DIB_SIZE); LE32(18, width); LE32(22, height);
+    hdr[26] = 1; hdr[27] = 0; hdr[28] = (uint8_t)(chans * 8); hdr[29] = 0;
+    LE32(30, chans == 3 ? 0 : 3);
+    int ippmX = 0, ippmY = 0;
+    if (ppmX != -1.0f) ippmX = (int)round(ppmX);
+    if (ppmY != -1.0f) ippmY = (int)round(ppmY);
+    LE32(38, ippmX); LE32(42, ippmY);
+    if (chans == 4) { static const uint8_t b[16] = {0, 0, 0xff, 0, 0, 0xff, 0, 0, 0xff, 0, 0, 0, 0, 0, 0, 0xff}; memcpy(hdr + 54, b, 16); }
+    hdr[70] = 'B'; hdr[71] = 'G'; hdr[72] = 'R'; hdr[73] = 's';
+#undef LE32
+    for (int y = 0; y < height; ++y) {
+        const uint8_t* in = data + (ptrdiff_t)pitchBytes * (height - 1 - y);
+        uint8_t* o = out + idat_offset + (size_t)y * (size_t)(linesize + pad);
+        for (int x = 0; x < width; ++x) {
+            o[chans * x] = in[chans * x + 2]; o[chans * x + 1] = in[chans * x + 1]; o[chans * x + 2] = in[chans * x];
+            if (chans == 4) o[4 * x + 3] = in[4 * x + 3];
+        }
+    }
+    *out_len = (int)filesize;
+    return out;
+}

@@ -69,6 +69,7 @@ uint8_t* or_tga_load(const uint8_t* data, size_t len, int* width, int* height, i
 uint8_t* or_tga_encode(const uint8_t* data, int type, int width, int height, int pitchBytes, int* out_len);   /* plugins/tga.d:123, codecs/tga.d:62-292 */
 
 /* ---- BMP (stbdec.d:2112-2510) and format detection (image.d:1045-1061, plugins' detect procs) ---- */
+uint8_t* or_bmp_encode(const uint8_t* data, int type, int width, int height, int pitchBytes, float ppmX, float ppmY, int* out_len);   /* plugins/bmp.d:166, codecs/bmpenc.d:25-113 */
 uint8_t* or_bmp_load(const uint8_t* data, size_t len, int req_comp, int* x, int* y, int* comp,
                      float* ppmX, float* ppmY, float* pixelRatio);
 int or_identify_format(const uint8_t* data, size_t len);      /* ImageFormat value (types.d:14-28) or -1 */

@@ -84,6 +84,8 @@ def lib():
         L.or_tga_load.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
         L.or_tga_encode.restype = C.c_void_p
         L.or_tga_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.or_bmp_encode.restype = C.c_void_p
+        L.or_bmp_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int)]
         L.or_bmp_load.restype = C.c_void_p
         L.or_bmp_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_float)] * 3
         L.or_identify_format.argtypes = [C.c_char_p, C.c_size_t]
@@ -300,6 +302,19 @@ def tga_encode(pixels: np.ndarray, pitch=None, first_scanline: int = 0, shape=No
     t = type_ if type_ is not None else {1: 0, 2: 3, 3: 9, 4: 12}[c]
     n = C.c_int(0)
     p = lib().or_tga_encode(px.ctypes.data + first_scanline, t, w, h, pitch if pitch is not None else w * c, C.byref(n))
+    if not p:
+        return None
+    return _take(p, n.value).tobytes()
+
+
+def bmp_encode(pixels: np.ndarray, ppmX: float = -1.0, ppmY: float = -1.0, pitch=None, first_scanline: int = 0, shape=None, type_=None):
+    """saveBMP -> write_bmp (plugins/bmp.d:166-194, codecs/bmpenc.d:25-113) of a (h, w, 3|4) uint8 image: the file (row
+    padding zero), or None."""
+    px = np.ascontiguousarray(pixels)
+    h, w, c = shape if shape is not None else px.shape
+    t = type_ if type_ is not None else {3: 9, 4: 12}.get(c, -1)
+    n = C.c_int(0)
+    p = lib().or_bmp_encode(px.ctypes.data + first_scanline, t, w, h, pitch if pitch is not None else w * c, ppmX, ppmY, C.byref(n))
     if not p:
         return None
     return _take(p, n.value).tobytes()

@@ -1,5 +1,5 @@
 """One short GPU pass over the encoders (one process, so the box pays for one torch import): the parity tests of the
-QOI / QOI-Plane10 / QOI-Plane encoders, then device-resident timings of the two new ones (CUDA events, inputs larger
+QOI / QOIX (all four sub-codecs) / BMP encoders, then device-resident timings of the new ones (CUDA events, inputs larger
 than L2, 3 warm-up + 5 timed launches). Writes gpurun_out/r2_encoders_pytest.txt and gpurun_out/r2_encoders_bench.json.
 
     gpurun --timeout 200 -- 'timeout 170 python scripts/encoders_gpu_pass.py'
@@ -23,8 +23,9 @@ def main():
     t0 = time.time()
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        rc = pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_qoi_encode_gpu.py"),
-                          os.path.join(ROOT, "tests", "test_qoix_encode_gpu.py")])
+        rc = pytest.main(["-q", "-m", "gpu", "-p", "no:cacheprovider", "-rxX"] + [os.path.join(ROOT, "tests", f) for f in (
+            "test_qoi_encode_gpu.py", "test_qoix_encode_gpu.py", "test_zz_qoi2avg_encode_gpu.py", "test_zz_qoi10b_encode_gpu.py",
+            "test_zz_bmp_encode_gpu.py")])
     text = buf.getvalue()
     with open(os.path.join(OUT, "r2_encoders_pytest.txt"), "w") as f:
         f.write(text + f"\nexit code {int(rc)}, {time.time() - t0:.1f} s\n")
@@ -76,6 +77,19 @@ def main():
         res["qoiplane_encode"] = {"workload": "QOI-Plane encode, 64 la8 images 2048x2048, device-resident",
                                   "ms": med, "all_ms": all_ms, "Mpx_per_s": px / med / 1e3, "bytes_out": int(sum(lens[-1])),
                                   "GBps_in_plus_out": (px * 2 + sum(lens[-1])) / med / 1e6}
+        del dev, outs
+        # QOI2AVG (8-bit) and QOI-10b (10-bit): 64 rgba images 1920x1080 through the same entry point
+        for name, imgs, bd in (("qoi2avg_encode", [qoi_test_image(1080, 1920, 4, 300 + k) for k in range(4)], 8),
+                               ("qoi10b_encode", [(qoi_test_image(1080, 1920, 4, 400 + k).astype(np.uint16) * 257) & 0xffc0 for k in range(4)], 10)):
+            dev = [torch.from_numpy(imgs[k % 4].view(np.int16) if bd == 10 else imgs[k % 4]).cuda() for k in range(64)]
+            outs = [torch.empty(1080 * 1920 * 7 + 256, dtype=torch.uint8, device="cuda") for _ in range(64)]
+            ptrs, optrs, shapes = [t.data_ptr() for t in dev], [o.data_ptr() for o in outs], [(1080, 1920, 4)] * 64
+            lens = []
+            med, all_ms = timed(lambda: lens.append(codecs.qoix_encode_batch_device(ptrs, shapes, optrs, bitdepths=[bd] * 64)))
+            px = 64 * 1080 * 1920
+            res[name] = {"workload": "%s, 64 rgba images 1920x1080, device-resident" % name, "ms": med, "all_ms": all_ms,
+                         "Mpx_per_s": px / med / 1e3, "bytes_out": int(sum(lens[-1]))}
+            del dev, outs
     except Exception as e:                                      # the parity result above is what matters most
         res["bench_error"] = repr(e)
     res["seconds"] = time.time() - t0

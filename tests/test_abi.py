@@ -54,3 +54,16 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/gamut_b200.h is the drop-in boundary: it must compile as C (no C++, no torch types) for cgo / D / ctypes
+    style bindings; the structs a binding fills by position keep their field order."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gamut_b200.h"\n'
+                   'int main(void) { gb200_tga_desc t = {1, 1, 3, 9}; gb200_bmp_desc b = {1, 1, 3, 9, -1.f, -1.f};\n'
+                   '  gb200_qoi_desc q = {1, 1, 3, 0}; gb200_qoix_desc x = {1, 1, 4, 4, 8, 0, 0, -1.f, -1.f};\n'
+                   '  return (int)(sizeof(t) + sizeof(b) + sizeof(q) + sizeof(x) + sizeof(gb200_image)) == 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
